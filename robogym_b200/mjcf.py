@@ -1,0 +1,1250 @@
+"""MJCF -> compiled model ("model blob") compiler for the robogym step path.
+
+Consumes exactly what the reference's composer emits and hands to
+`mujoco_py.load_model_from_xml` (robogym/mujoco/mujoco_xml.py:249-260): one XML
+string with `<compiler angle="radian" coordinate="local" meshdir=...>`
+(mujoco_xml.py:172-186), includes already expanded, names prefixed, top-level
+sections possibly repeated (they are merged in document order).
+
+Only the MJCF feature set the five BASELINE.json configs exercise is handled
+(SURVEY.md Appendix C).  The output is a dict of flat numpy arrays laid out by
+include/rg_model_fields.h plus name tables; `modelblob.pack` turns it into the
+bytes that cross the C ABI.
+
+This is a from-scratch restatement of MuJoCo's documented compile semantics
+(defaults classes, frame composition, inertia inference, collision filtering,
+mj_setConst); it shares no code with MuJoCo or the reference.
+"""
+import os
+import struct
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import modelblob
+
+# mjtJoint
+JNT_FREE, JNT_BALL, JNT_SLIDE, JNT_HINGE = 0, 1, 2, 3
+# mjtGeom
+GEOM_PLANE, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH = range(8)
+GEOM_TYPES = dict(plane=0, hfield=1, sphere=2, capsule=3, ellipsoid=4, cylinder=5, box=6, mesh=7)
+# mjtWrap
+WRAP_NONE, WRAP_JOINT, WRAP_PULLEY, WRAP_SITE, WRAP_SPHERE, WRAP_CYLINDER = range(6)
+# mjtTrn
+TRN_JOINT, TRN_JOINTINPARENT, TRN_SLIDERCRANK, TRN_TENDON, TRN_SITE = range(5)
+# mjtGain / mjtBias (MuJoCo 2.0 numbering, as exposed by mujoco_py.const)
+GAIN_FIXED, GAIN_MUSCLE, GAIN_USER = 0, 1, 2
+BIAS_NONE, BIAS_AFFINE, BIAS_MUSCLE, BIAS_USER = 0, 1, 2, 3
+# mjtEq
+EQ_CONNECT, EQ_WELD, EQ_JOINT, EQ_TENDON, EQ_DISTANCE = range(5)
+# mjtSensor subset
+SENS_TOUCH, SENS_JOINTPOS, SENS_FORCE, SENS_TORQUE = 0, 8, 4, 5
+# disable flag bits (mjtDisableBit)
+DSBL = dict(constraint=1, equality=2, frictionloss=4, limit=8, contact=16, passive=32,
+            gravity=64, clampctrl=128, warmstart=256, filterparent=512, actuation=1024,
+            refsafe=2048)
+MINVAL = 1e-15
+
+DEFAULT_SOLREF = (0.02, 1.0)
+DEFAULT_SOLIMP = (0.9, 0.95, 0.001, 0.5, 2.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# small math helpers (quaternions are (w, x, y, z) as in MuJoCo)
+def _vec(s, n=None, dtype=float):
+    if s is None:
+        return None
+    if isinstance(s, str):
+        a = np.array(s.split(), dtype=dtype)
+    else:
+        a = np.array(s, dtype=dtype).reshape(-1)
+    if n is not None and a.size != n:
+        if a.size < n:
+            a = np.concatenate([a, np.zeros(n - a.size, dtype=dtype)])
+        else:
+            a = a[:n]
+    return a
+
+
+def quat_mul(a, b):
+    w1, x1, y1, z1 = a
+    w2, x2, y2, z2 = b
+    return np.array([
+        w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2,
+        w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
+        w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+        w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+    ])
+
+
+def quat_conj(q):
+    return np.array([q[0], -q[1], -q[2], -q[3]])
+
+
+def quat_normalize(q):
+    q = np.asarray(q, dtype=float)
+    n = np.linalg.norm(q)
+    if n < MINVAL:
+        return np.array([1.0, 0, 0, 0])
+    return q / n
+
+
+def quat2mat(q):
+    w, x, y, z = q
+    return np.array([
+        [w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z],
+    ])
+
+
+def mat2quat(m):
+    # Shepperd's method
+    t = np.trace(m)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (m[2, 1] - m[1, 2]) / s, (m[0, 2] - m[2, 0]) / s, (m[1, 0] - m[0, 1]) / s])
+    elif m[0, 0] > m[1, 1] and m[0, 0] > m[2, 2]:
+        s = np.sqrt(1.0 + m[0, 0] - m[1, 1] - m[2, 2]) * 2
+        q = np.array([(m[2, 1] - m[1, 2]) / s, 0.25 * s, (m[0, 1] + m[1, 0]) / s, (m[0, 2] + m[2, 0]) / s])
+    elif m[1, 1] > m[2, 2]:
+        s = np.sqrt(1.0 + m[1, 1] - m[0, 0] - m[2, 2]) * 2
+        q = np.array([(m[0, 2] - m[2, 0]) / s, (m[0, 1] + m[1, 0]) / s, 0.25 * s, (m[1, 2] + m[2, 1]) / s])
+    else:
+        s = np.sqrt(1.0 + m[2, 2] - m[0, 0] - m[1, 1]) * 2
+        q = np.array([(m[1, 0] - m[0, 1]) / s, (m[0, 2] + m[2, 0]) / s, (m[1, 2] + m[2, 1]) / s, 0.25 * s])
+    return quat_normalize(q)
+
+
+def axisangle2quat(axis, angle):
+    axis = np.asarray(axis, dtype=float)
+    n = np.linalg.norm(axis)
+    if n < MINVAL:
+        return np.array([1.0, 0, 0, 0])
+    axis = axis / n
+    return np.concatenate([[np.cos(angle / 2)], np.sin(angle / 2) * axis])
+
+
+def z2quat(vec):
+    """Quaternion rotating +z onto vec."""
+    vec = np.asarray(vec, dtype=float)
+    n = np.linalg.norm(vec)
+    if n < MINVAL:
+        return np.array([1.0, 0, 0, 0])
+    vec = vec / n
+    z = np.array([0.0, 0, 1])
+    axis = np.cross(z, vec)
+    s = np.linalg.norm(axis)
+    if s < 1e-10:
+        if vec[2] > 0:
+            return np.array([1.0, 0, 0, 0])
+        return np.array([0.0, 1, 0, 0])
+    ang = np.arctan2(s, vec[2])
+    return axisangle2quat(axis / s, ang)
+
+
+def rot_vec(q, v):
+    return quat2mat(q) @ np.asarray(v, dtype=float)
+
+
+# ----------------------------------------------------------------------------------------------
+# mesh loading
+def load_stl(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    (ntri,) = struct.unpack_from("<I", data, 80)
+    if 84 + 50 * ntri != len(data):
+        raise ValueError(f"{path}: not a binary STL")
+    rec = np.frombuffer(data, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", 9), ("a", "<u2")]),
+                        count=ntri, offset=84)
+    return rec["v"].reshape(-1, 3).astype(np.float64)
+
+
+def load_msh(path):
+    """MuJoCo legacy binary .msh: int32 nvertex,nnormal,ntexcoord,nface; float32 data."""
+    with open(path, "rb") as f:
+        data = f.read()
+    nv, nn, nt, nf = struct.unpack_from("<4i", data, 0)
+    verts = np.frombuffer(data, dtype="<f4", count=3 * nv, offset=16).reshape(-1, 3)
+    return verts.astype(np.float64)
+
+
+def convex_hull(points):
+    """Return (hull_vertices[n,3], faces[m,3] outward-oriented, local indices)."""
+    from scipy.spatial import ConvexHull
+
+    pts = np.unique(np.round(points, 12), axis=0)
+    hull = ConvexHull(pts, qhull_options="Qt")
+    used = np.sort(hull.vertices)
+    remap = -np.ones(len(pts), dtype=int)
+    remap[used] = np.arange(len(used))
+    verts = pts[used]
+    faces = remap[hull.simplices]
+    # orient outward using the facet equations
+    normals = hull.equations[:, :3]
+    a, b, c = verts[faces[:, 0]], verts[faces[:, 1]], verts[faces[:, 2]]
+    flip = np.einsum("ij,ij->i", np.cross(b - a, c - a), normals) < 0
+    faces[flip] = faces[flip][:, [0, 2, 1]]
+    return verts, faces
+
+
+def polyhedron_mass_props(verts, faces):
+    """Volume, centroid, inertia-about-centroid (unit density) of a closed triangle mesh."""
+    a, b, c = verts[faces[:, 0]], verts[faces[:, 1]], verts[faces[:, 2]]
+    vol6 = np.einsum("ij,ij->i", a, np.cross(b, c))
+    vol = vol6.sum() / 6.0
+    cen = ((a + b + c) * vol6[:, None]).sum(0) / (24.0 * vol)
+    # covariance integral via canonical tetrahedron
+    canon = np.array([[2, 1, 1], [1, 2, 1], [1, 1, 2]]) / 120.0
+    C = np.zeros((3, 3))
+    for i in range(len(faces)):
+        A = np.stack([a[i], b[i], c[i]], axis=1)  # columns
+        C += vol6[i] * (A @ canon @ A.T)
+    C -= vol * np.outer(cen, cen)
+    I = np.trace(C) * np.eye(3) - C
+    return vol, cen, I
+
+
+# ----------------------------------------------------------------------------------------------
+class _Defaults:
+    """MJCF default classes: nested <default class=..> with inheritance."""
+
+    TAGS = ("geom", "joint", "site", "general", "tendon", "mesh", "equality", "pair", "motor",
+            "position", "velocity")
+
+    def __init__(self):
+        self.classes = {"main": {t: {} for t in self.TAGS}}
+
+    def add(self, elem, parent=None):
+        """Register a <default> element; `parent` is the enclosing class name (None = top level)."""
+        if parent is None:
+            name = "main"
+            cur = self.classes["main"]
+        else:
+            name = elem.get("class")
+            if name is None:
+                raise ValueError("nested <default> needs a class name")
+            cur = {t: dict(self.classes[parent][t]) for t in self.TAGS}
+            self.classes[name] = cur
+        for child in elem:
+            if child.tag == "default":
+                continue
+            tag = child.tag
+            if tag in ("motor", "position", "velocity", "cylinder", "muscle"):
+                tag = "general"
+            if tag in ("fixed", "spatial"):
+                tag = "tendon"
+            if tag in cur:
+                cur[tag].update(child.attrib)
+        for child in elem:
+            if child.tag == "default":
+                self.add(child, parent=name)
+
+    def resolve(self, tag, elem, childclass):
+        cls = elem.get("class", childclass) or "main"
+        if cls not in self.classes:
+            raise ValueError(f"unknown default class {cls!r}")
+        attrs = dict(self.classes[cls].get(tag, {}))
+        attrs.update(elem.attrib)
+        return attrs
+
+
+def _frame_quat(attrs, angle_scale=1.0, eulerseq="xyz"):
+    """Orientation from quat / euler / axisangle / xyaxes / zaxis (MJCF frame orientations)."""
+    if "quat" in attrs:
+        return quat_normalize(_vec(attrs["quat"], 4))
+    if "euler" in attrs:
+        e = _vec(attrs["euler"], 3) * angle_scale
+        q = np.array([1.0, 0, 0, 0])
+        for i, ax in enumerate(eulerseq):
+            axis = np.zeros(3)
+            axis["xyz".index(ax.lower())] = 1.0
+            qi = axisangle2quat(axis, e[i])
+            if ax.islower():  # intrinsic: post-multiply
+                q = quat_mul(q, qi)
+            else:
+                q = quat_mul(qi, q)
+        return quat_normalize(q)
+    if "axisangle" in attrs:
+        a = _vec(attrs["axisangle"], 4)
+        return axisangle2quat(a[:3], a[3] * angle_scale)
+    if "xyaxes" in attrs:
+        a = _vec(attrs["xyaxes"], 6)
+        x = a[:3] / np.linalg.norm(a[:3])
+        y = a[3:] - x * np.dot(x, a[3:])
+        y /= np.linalg.norm(y)
+        z = np.cross(x, y)
+        return mat2quat(np.stack([x, y, z], axis=1))
+    if "zaxis" in attrs:
+        return z2quat(_vec(attrs["zaxis"], 3))
+    return np.array([1.0, 0, 0, 0])
+
+
+class CompiledModel:
+    """Result of compile_mjcf: `.m` (dict for modelblob.pack) + name tables."""
+
+    OBJ_TYPES = ("body", "joint", "geom", "site", "tendon", "actuator", "mesh", "sensor", "equality")
+
+    def __init__(self, m, names, xml):
+        self.m = m
+        self.names = names  # dict objtype -> list of names (None for unnamed)
+        self.xml = xml
+
+    def blob(self):
+        return modelblob.pack(self.m)
+
+    def name2id(self, objtype, name):
+        try:
+            return self.names[objtype].index(name)
+        except ValueError:
+            raise ValueError(f'No "{objtype}" with name {name} exists.')
+
+
+# ----------------------------------------------------------------------------------------------
+def compile_mjcf(xml_string, asset_loader=None):
+    """Compile an MJCF document (string) into a CompiledModel."""
+    root = ET.fromstring(xml_string)
+    if root.tag != "mujoco":
+        raise ValueError("root element must be <mujoco>")
+
+    # ---- compiler / option / size
+    comp = {}
+    for e in root.findall("compiler"):
+        comp.update(e.attrib)
+    angle_scale = 1.0 if comp.get("angle", "degree") == "radian" else np.pi / 180.0
+    if comp.get("coordinate", "local") != "local":
+        raise NotImplementedError("only coordinate=local is supported")
+    eulerseq = comp.get("eulerseq", "xyz")
+    meshdir = comp.get("meshdir", "")
+    boundmass = float(comp.get("boundmass", 0))
+    boundinertia = float(comp.get("boundinertia", 0))
+    inertiafromgeom = comp.get("inertiafromgeom", "auto")
+    settotalmass = float(comp.get("settotalmass", -1))
+
+    opt = {}
+    flags = {}
+    for e in root.findall("option"):
+        opt.update(e.attrib)
+        for fl in e.findall("flag"):
+            flags.update(fl.attrib)
+    size_attrs = {}
+    for e in root.findall("size"):
+        size_attrs.update(e.attrib)
+
+    defaults = _Defaults()
+    for e in root.findall("default"):
+        defaults.add(e, parent=None)
+
+    # ---- assets: meshes
+    mesh_names, mesh_verts, mesh_faces, mesh_center = [], [], [], []
+    mesh_props = []
+    for asset in root.findall("asset"):
+        for me in asset.findall("mesh"):
+            a = defaults.resolve("mesh", me, None)
+            name = a.get("name")
+            fname = a["file"]
+            if name is None:
+                name = os.path.splitext(os.path.basename(fname))[0]
+            path = fname if os.path.isabs(fname) else os.path.join(meshdir, fname)
+            if asset_loader is not None:
+                raw = asset_loader(path)
+            elif path.lower().endswith(".stl"):
+                raw = load_stl(path)
+            elif path.lower().endswith(".msh"):
+                raw = load_msh(path)
+            else:
+                raise NotImplementedError(f"mesh format of {path}")
+            scale = _vec(a.get("scale", "1 1 1"), 3)
+            raw = raw * scale
+            verts, faces = convex_hull(raw)
+            vol, cen, inertia = polyhedron_mass_props(verts, faces)
+            verts = verts - cen
+            mesh_names.append(name)
+            mesh_verts.append(verts)
+            mesh_faces.append(faces)
+            mesh_center.append(cen)
+            mesh_props.append((vol, inertia))
+
+    # ---- kinematic tree (document-order DFS over merged <worldbody> sections)
+    B = dict(name=[], parent=[], pos=[], quat=[], inertial=[], childclass=[], mocap=[])
+    J = []  # joint dicts
+    G = []  # geom dicts
+    S = []  # site dicts
+
+    def add_body(elem, parent, childclass):
+        a = elem.attrib
+        bid = len(B["name"])
+        cc = a.get("childclass", childclass)
+        B["name"].append(a.get("name"))
+        B["parent"].append(parent)
+        B["pos"].append(_vec(a.get("pos", "0 0 0"), 3))
+        B["quat"].append(_frame_quat(a, angle_scale, eulerseq))
+        B["childclass"].append(cc)
+        B["mocap"].append(a.get("mocap", "false") == "true")
+        inertial = elem.find("inertial")
+        B["inertial"].append(dict(inertial.attrib) if inertial is not None else None)
+        add_body_content(elem, bid, cc)
+        return bid
+
+    def add_body_content(elem, bid, cc):
+        for ch in elem:
+            if ch.tag == "joint":
+                ja = defaults.resolve("joint", ch, cc)
+                ja["_body"] = bid
+                J.append(ja)
+            elif ch.tag == "freejoint":
+                ja = dict(ch.attrib)
+                ja.update(type="free", _body=bid)
+                J.append(ja)
+            elif ch.tag == "geom":
+                ga = defaults.resolve("geom", ch, cc)
+                ga["_body"] = bid
+                G.append(ga)
+            elif ch.tag == "site":
+                sa = defaults.resolve("site", ch, cc)
+                sa["_body"] = bid
+                S.append(sa)
+        for ch in elem:
+            if ch.tag == "body":
+                add_body(ch, bid, cc)
+
+    # world body
+    B["name"].append("world")
+    B["parent"].append(0)
+    B["pos"].append(np.zeros(3))
+    B["quat"].append(np.array([1.0, 0, 0, 0]))
+    B["inertial"].append(None)
+    B["childclass"].append(None)
+    B["mocap"].append(False)
+    for wb in root.findall("worldbody"):
+        add_body_content(wb, 0, wb.get("childclass"))
+
+    nbody = len(B["name"])
+    # MuJoCo numbers joints/geoms/sites grouped by body id
+    J.sort(key=lambda d: d["_body"])
+    G.sort(key=lambda d: d["_body"])
+    S.sort(key=lambda d: d["_body"])
+    njnt, ngeom, nsite = len(J), len(G), len(S)
+
+    m = {}
+    names = dict(body=list(B["name"]), joint=[j.get("name") for j in J], geom=[g.get("name") for g in G],
+                 site=[s.get("name") for s in S], mesh=mesh_names)
+
+    # ---- joints / dofs
+    jtype_map = dict(free=JNT_FREE, ball=JNT_BALL, slide=JNT_SLIDE, hinge=JNT_HINGE)
+    jnt_type = np.zeros(njnt, int)
+    jnt_qposadr = np.zeros(njnt, int)
+    jnt_dofadr = np.zeros(njnt, int)
+    jnt_bodyid = np.zeros(njnt, int)
+    jnt_limited = np.zeros(njnt, int)
+    jnt_pos = np.zeros((njnt, 3))
+    jnt_axis = np.zeros((njnt, 3))
+    jnt_stiffness = np.zeros(njnt)
+    jnt_range = np.zeros((njnt, 2))
+    jnt_margin = np.zeros(njnt)
+    jnt_solref = np.zeros((njnt, 2))
+    jnt_solimp = np.zeros((njnt, 5))
+    qpos0, qpos_spring = [], []
+    dof_bodyid, dof_jntid, dof_armature, dof_damping, dof_frictionloss = [], [], [], [], []
+    dof_solref, dof_solimp = [], []
+    nq = nv = 0
+    for i, ja in enumerate(J):
+        t = jtype_map[ja.get("type", "hinge")]
+        jnt_type[i] = t
+        jnt_bodyid[i] = ja["_body"]
+        jnt_qposadr[i] = nq
+        jnt_dofadr[i] = nv
+        jnt_pos[i] = _vec(ja.get("pos", "0 0 0"), 3)
+        ax = _vec(ja.get("axis", "0 0 1"), 3)
+        jnt_axis[i] = ax / max(np.linalg.norm(ax), MINVAL)
+        limited = ja.get("limited", "false") == "true"
+        jnt_limited[i] = int(limited)
+        rng = _vec(ja.get("range", "0 0"), 2)
+        if t in (JNT_HINGE, JNT_BALL):
+            rng = rng * angle_scale
+        jnt_range[i] = rng
+        jnt_stiffness[i] = float(ja.get("stiffness", 0))
+        jnt_margin[i] = float(ja.get("margin", 0))
+        jnt_solref[i] = _vec(ja.get("solreflimit", DEFAULT_SOLREF), 2)
+        jnt_solimp[i] = _solimp(ja.get("solimplimit"))
+        ref = float(ja.get("ref", 0))
+        sref = float(ja.get("springref", 0))
+        if t == JNT_HINGE:
+            ref *= angle_scale
+            sref *= angle_scale
+        nqi, nvi = {JNT_FREE: (7, 6), JNT_BALL: (4, 3), JNT_SLIDE: (1, 1), JNT_HINGE: (1, 1)}[t]
+        if t == JNT_FREE:
+            # qpos0 of a free joint is the body's pose in the world (filled after frames are known)
+            qpos0 += [None] * 7
+            qpos_spring += [None] * 7
+        elif t == JNT_BALL:
+            qpos0 += [1.0, 0, 0, 0]
+            qpos_spring += [1.0, 0, 0, 0]
+        else:
+            qpos0.append(ref)
+            qpos_spring.append(sref)
+        for _ in range(nvi):
+            dof_bodyid.append(ja["_body"])
+            dof_jntid.append(i)
+            dof_armature.append(float(ja.get("armature", 0)))
+            dof_damping.append(float(ja.get("damping", 0)))
+            dof_frictionloss.append(float(ja.get("frictionloss", 0)))
+            dof_solref.append(_vec(ja.get("solreffriction", DEFAULT_SOLREF), 2))
+            dof_solimp.append(_solimp(ja.get("solimpfriction")))
+        nq += nqi
+        nv += nvi
+
+    body_jntadr = -np.ones(nbody, int)
+    body_jntnum = np.zeros(nbody, int)
+    body_dofadr = -np.ones(nbody, int)
+    body_dofnum = np.zeros(nbody, int)
+    for i in range(njnt):
+        b = jnt_bodyid[i]
+        if body_jntadr[b] < 0:
+            body_jntadr[b] = i
+            body_dofadr[b] = jnt_dofadr[i]
+        body_jntnum[b] += 1
+        body_dofnum[b] += {JNT_FREE: 6, JNT_BALL: 3}.get(jnt_type[i], 1)
+
+    parent = np.array(B["parent"], int)
+    body_pos = np.array(B["pos"], float)
+    body_quat = np.array(B["quat"], float)
+    # free-joint bodies: qpos0 is the body frame (must be children of world)
+    for i in range(njnt):
+        if jnt_type[i] == JNT_FREE:
+            b = jnt_bodyid[i]
+            a = jnt_qposadr[i]
+            vals = list(body_pos[b]) + list(body_quat[b])
+            qpos0[a:a + 7] = vals
+            qpos_spring[a:a + 7] = vals
+    qpos0 = np.array(qpos0, float)
+    qpos_spring = np.array(qpos_spring, float)
+
+    # dof parent chain
+    dof_parentid = -np.ones(nv, int)
+    last_dof_of_body = -np.ones(nbody, int)  # last dof on path from root up to and including body
+    for b in range(1, nbody):
+        last = last_dof_of_body[parent[b]]
+        if body_dofnum[b] > 0:
+            for d in range(body_dofadr[b], body_dofadr[b] + body_dofnum[b]):
+                dof_parentid[d] = last
+                last = d
+        last_dof_of_body[b] = last
+
+    # levels, roots, weld ids
+    level = np.zeros(nbody, int)
+    rootid = np.zeros(nbody, int)
+    weldid = np.zeros(nbody, int)
+    for b in range(1, nbody):
+        level[b] = level[parent[b]] + 1
+        rootid[b] = b if parent[b] == 0 else rootid[parent[b]]
+        weldid[b] = b if body_jntnum[b] > 0 else weldid[parent[b]]
+    order = np.array(sorted(range(nbody), key=lambda b: (level[b], b)), int)
+    nlevel = int(level.max()) + 1
+    level_adr = np.zeros(nlevel + 1, int)
+    for b in range(nbody):
+        level_adr[level[b] + 1] += 1
+    level_adr = np.cumsum(level_adr)
+
+    nmaskw = max(1, (nv + 31) // 32)
+    dofmask = np.zeros((nbody, nmaskw), np.uint32)
+    for b in range(1, nbody):
+        dofmask[b] = dofmask[parent[b]]
+        for d in range(body_dofadr[b], body_dofadr[b] + body_dofnum[b]) if body_dofnum[b] else []:
+            dofmask[b, d // 32] |= np.uint32(1 << (d % 32))
+
+    mocapid = -np.ones(nbody, int)
+    nmocap = 0
+    for b in range(nbody):
+        if B["mocap"][b]:
+            mocapid[b] = nmocap
+            nmocap += 1
+
+    # ---- geoms
+    geom_type = np.zeros(ngeom, int)
+    geom_bodyid = np.zeros(ngeom, int)
+    geom_dataid = -np.ones(ngeom, int)
+    geom_contype = np.zeros(ngeom, int)
+    geom_conaffinity = np.zeros(ngeom, int)
+    geom_condim = np.zeros(ngeom, int)
+    geom_priority = np.zeros(ngeom, int)
+    geom_size = np.zeros((ngeom, 3))
+    geom_pos = np.zeros((ngeom, 3))
+    geom_quat = np.zeros((ngeom, 4))
+    geom_rbound = np.zeros(ngeom)
+    geom_friction = np.zeros((ngeom, 3))
+    geom_margin = np.zeros(ngeom)
+    geom_gap = np.zeros(ngeom)
+    geom_solmix = np.zeros(ngeom)
+    geom_solref = np.zeros((ngeom, 2))
+    geom_solimp = np.zeros((ngeom, 5))
+    geom_mass = np.zeros(ngeom)
+    geom_inertia = np.zeros((ngeom, 3, 3))  # about geom centre, in geom frame
+    body_geomadr = -np.ones(nbody, int)
+    body_geomnum = np.zeros(nbody, int)
+    for i, ga in enumerate(G):
+        b = ga["_body"]
+        if body_geomadr[b] < 0:
+            body_geomadr[b] = i
+        body_geomnum[b] += 1
+        geom_bodyid[i] = b
+        if "mesh" in ga and "type" not in ga:
+            ga["type"] = "mesh"
+        t = GEOM_TYPES[ga.get("type", "sphere")]
+        geom_type[i] = t
+        size = _vec(ga.get("size", "0 0 0"), 3)
+        pos = _vec(ga.get("pos", "0 0 0"), 3)
+        quat = _frame_quat(ga, angle_scale, eulerseq)
+        if "fromto" in ga and t in (GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_ELLIPSOID):
+            ft = _vec(ga["fromto"], 6)
+            pos = 0.5 * (ft[:3] + ft[3:])
+            quat = z2quat(ft[:3] - ft[3:])
+            half = 0.5 * np.linalg.norm(ft[3:] - ft[:3])
+            if t in (GEOM_CAPSULE, GEOM_CYLINDER):
+                size = np.array([size[0], half, 0.0])
+            else:
+                size = np.array([size[0], size[0], half])
+        if t == GEOM_MESH:
+            mid = mesh_names.index(ga["mesh"])
+            geom_dataid[i] = mid
+            # mesh vertices were recentred on the hull centroid: shift the geom frame to match
+            pos = pos + quat2mat(quat) @ mesh_center[mid]
+            size = np.abs(mesh_verts[mid]).max(axis=0)
+            geom_rbound[i] = np.linalg.norm(mesh_verts[mid], axis=1).max()
+        elif t == GEOM_SPHERE:
+            geom_rbound[i] = size[0]
+        elif t == GEOM_CAPSULE:
+            geom_rbound[i] = size[0] + size[1]
+        elif t == GEOM_CYLINDER:
+            geom_rbound[i] = np.hypot(size[0], size[1])
+        elif t in (GEOM_BOX, GEOM_ELLIPSOID):
+            geom_rbound[i] = np.linalg.norm(size) if t == GEOM_BOX else size.max()
+        geom_size[i] = size
+        geom_pos[i] = pos
+        geom_quat[i] = quat
+        geom_contype[i] = int(ga.get("contype", 1))
+        geom_conaffinity[i] = int(ga.get("conaffinity", 1))
+        geom_condim[i] = int(ga.get("condim", 3))
+        geom_priority[i] = int(ga.get("priority", 0))
+        geom_friction[i] = _vec(ga.get("friction", "1 0.005 0.0001"), 3)
+        geom_margin[i] = float(ga.get("margin", 0))
+        geom_gap[i] = float(ga.get("gap", 0))
+        geom_solmix[i] = float(ga.get("solmix", 1))
+        geom_solref[i] = _vec(ga.get("solref", DEFAULT_SOLREF), 2)
+        geom_solimp[i] = _solimp(ga.get("solimp"))
+        # mass / inertia (used only if the body has no <inertial>)
+        vol, I = _geom_volume_inertia(t, size, mesh_props[geom_dataid[i]] if t == GEOM_MESH else None)
+        if "mass" in ga:
+            mass = float(ga["mass"])
+        else:
+            mass = float(ga.get("density", 1000)) * vol
+        geom_mass[i] = mass
+        geom_inertia[i] = I * (mass / vol if vol > 0 else 0.0)
+
+    # ---- body inertial properties
+    body_mass = np.zeros(nbody)
+    body_ipos = np.zeros((nbody, 3))
+    body_iquat = np.tile(np.array([1.0, 0, 0, 0]), (nbody, 1))
+    body_inertia = np.zeros((nbody, 3))
+    for b in range(1, nbody):
+        ia = B["inertial"][b]
+        use_geoms = (inertiafromgeom == "true") or (inertiafromgeom == "auto" and ia is None)
+        if not use_geoms and ia is not None:
+            body_mass[b] = float(ia["mass"])
+            body_ipos[b] = _vec(ia.get("pos", "0 0 0"), 3)
+            iq = _frame_quat(ia, angle_scale, eulerseq)
+            if "fullinertia" in ia:
+                f = _vec(ia["fullinertia"], 6)
+                full = np.array([[f[0], f[3], f[4]], [f[3], f[1], f[5]], [f[4], f[5], f[2]]])
+                w, v = _eig_frame(full)
+                body_inertia[b] = w
+                iq = quat_mul(iq, mat2quat(v))
+            else:
+                body_inertia[b] = _vec(ia["diaginertia"], 3)
+            body_iquat[b] = quat_normalize(iq)
+        elif body_geomnum[b] > 0:
+            gs = range(body_geomadr[b], body_geomadr[b] + body_geomnum[b])
+            mtot = sum(geom_mass[g] for g in gs)
+            if mtot > 0:
+                com = sum(geom_mass[g] * geom_pos[g] for g in gs) / mtot
+                I = np.zeros((3, 3))
+                for g in gs:
+                    R = quat2mat(geom_quat[g])
+                    d = geom_pos[g] - com
+                    I += R @ geom_inertia[g] @ R.T + geom_mass[g] * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+                w, v = _eig_frame(I)
+                body_mass[b] = mtot
+                body_ipos[b] = com
+                body_inertia[b] = w
+                body_iquat[b] = mat2quat(v)
+        if body_mass[b] > 0 or body_inertia[b].any():
+            body_mass[b] = max(body_mass[b], boundmass)
+            body_inertia[b] = np.maximum(body_inertia[b], boundinertia)
+    if settotalmass > 0:
+        s = settotalmass / body_mass.sum()
+        body_mass *= s
+        body_inertia *= s
+    subtreemass = body_mass.copy()
+    for b in range(nbody - 1, 0, -1):
+        subtreemass[parent[b]] += subtreemass[b]
+
+    # ---- sites
+    site_bodyid = np.array([s["_body"] for s in S], int).reshape(-1)
+    site_pos = np.zeros((nsite, 3))
+    site_quat = np.zeros((nsite, 4))
+    for i, sa in enumerate(S):
+        pos = _vec(sa.get("pos", "0 0 0"), 3)
+        quat = _frame_quat(sa, angle_scale, eulerseq)
+        if "fromto" in sa:
+            ft = _vec(sa["fromto"], 6)
+            pos = 0.5 * (ft[:3] + ft[3:])
+            quat = z2quat(ft[:3] - ft[3:])
+        site_pos[i] = pos
+        site_quat[i] = quat
+
+    # ---- collision pair list (static filtering; MuJoCo's mj_collision body/geom filters)
+    disableflags = 0
+    for k, v in flags.items():
+        if k in DSBL and v == "disable":
+            disableflags |= DSBL[k]
+    excludes = set()
+    for ce in root.findall("contact"):
+        for ex in ce.findall("exclude"):
+            b1 = names["body"].index(ex.get("body1"))
+            b2 = names["body"].index(ex.get("body2"))
+            excludes.add((min(b1, b2), max(b1, b2)))
+        if ce.findall("pair"):
+            raise NotImplementedError("explicit <contact><pair> is not used by the robogym configs")
+    pair1, pair2 = [], []
+    filterparent = not (disableflags & DSBL["filterparent"])
+    for g1 in range(ngeom):
+        for g2 in range(g1 + 1, ngeom):
+            b1, b2 = geom_bodyid[g1], geom_bodyid[g2]
+            if b1 == b2:
+                continue
+            w1, w2 = weldid[b1], weldid[b2]
+            if w1 == w2:
+                continue  # welded together (incl. both static)
+            if (min(b1, b2), max(b1, b2)) in excludes:
+                continue
+            if filterparent and w1 != 0 and w2 != 0:
+                if weldid[parent[w1]] == w2 or weldid[parent[w2]] == w1:
+                    continue
+            if not ((geom_contype[g1] & geom_conaffinity[g2]) or (geom_contype[g2] & geom_conaffinity[g1])):
+                continue
+            t1, t2 = geom_type[g1], geom_type[g2]
+            if t1 == GEOM_PLANE and t2 == GEOM_PLANE:
+                continue
+            # order so that type1 <= type2 (collision function table is upper-triangular)
+            if t1 > t2:
+                pair1.append(g2)
+                pair2.append(g1)
+            else:
+                pair1.append(g1)
+                pair2.append(g2)
+
+    # ---- tendons
+    T = []
+    W_type, W_obj, W_prm = [], [], []
+    for te in root.findall("tendon"):
+        for t in te:
+            if t.tag not in ("fixed", "spatial"):
+                continue
+            ta = defaults.resolve("tendon", t, None)
+            adr = len(W_type)
+            for w in t:
+                if w.tag == "joint":
+                    W_type.append(WRAP_JOINT)
+                    W_obj.append(names["joint"].index(w.get("joint")))
+                    W_prm.append(float(w.get("coef", 1)))
+                elif w.tag == "site":
+                    W_type.append(WRAP_SITE)
+                    W_obj.append(names["site"].index(w.get("site")))
+                    W_prm.append(-1)
+                elif w.tag == "geom":
+                    g = names["geom"].index(w.get("geom"))
+                    if geom_type[g] == GEOM_SPHERE:
+                        W_type.append(WRAP_SPHERE)
+                    elif geom_type[g] == GEOM_CYLINDER:
+                        W_type.append(WRAP_CYLINDER)
+                    else:
+                        raise ValueError("tendon can only wrap spheres and cylinders")
+                    W_obj.append(g)
+                    ss = w.get("sidesite")
+                    W_prm.append(names["site"].index(ss) if ss is not None else -1)
+                elif w.tag == "pulley":
+                    W_type.append(WRAP_PULLEY)
+                    W_obj.append(-1)
+                    W_prm.append(float(w.get("divisor")))
+            ta["_adr"] = adr
+            ta["_num"] = len(W_type) - adr
+            T.append(ta)
+    ntendon = len(T)
+    names["tendon"] = [t.get("name") for t in T]
+    tendon_range = np.zeros((ntendon, 2))
+    tendon_limited = np.zeros(ntendon, int)
+    tendon_margin = np.zeros(ntendon)
+    tendon_stiffness = np.zeros(ntendon)
+    tendon_damping = np.zeros(ntendon)
+    tendon_frictionloss = np.zeros(ntendon)
+    tendon_lengthspring = np.zeros(ntendon)
+    tendon_solref_lim = np.zeros((ntendon, 2))
+    tendon_solimp_lim = np.zeros((ntendon, 5))
+    for i, ta in enumerate(T):
+        tendon_limited[i] = int(ta.get("limited", "false") == "true")
+        tendon_range[i] = _vec(ta.get("range", "0 0"), 2)
+        tendon_margin[i] = float(ta.get("margin", 0))
+        tendon_stiffness[i] = float(ta.get("stiffness", 0))
+        tendon_damping[i] = float(ta.get("damping", 0))
+        tendon_frictionloss[i] = float(ta.get("frictionloss", 0))
+        tendon_lengthspring[i] = float(ta.get("springlength", -1))
+        tendon_solref_lim[i] = _vec(ta.get("solreflimit", DEFAULT_SOLREF), 2)
+        tendon_solimp_lim[i] = _solimp(ta.get("solimplimit"))
+
+    # ---- actuators
+    A = []
+    for ae in root.findall("actuator"):
+        for a in ae:
+            aa = defaults.resolve("general", a, None)
+            aa["_tag"] = a.tag
+            A.append(aa)
+    nu = len(A)
+    names["actuator"] = [a.get("name") for a in A]
+    act_trntype = np.zeros(nu, int)
+    act_trnid = np.zeros(nu, int)
+    act_gaintype = np.zeros(nu, int)
+    act_biastype = np.zeros(nu, int)
+    act_ctrllimited = np.zeros(nu, int)
+    act_forcelimited = np.zeros(nu, int)
+    act_gainprm = np.zeros((nu, 10))
+    act_biasprm = np.zeros((nu, 10))
+    act_ctrlrange = np.zeros((nu, 2))
+    act_forcerange = np.zeros((nu, 2))
+    act_gear = np.zeros((nu, 6))
+    act_user0 = np.zeros(nu)
+    gmap = dict(fixed=GAIN_FIXED, muscle=GAIN_MUSCLE, user=GAIN_USER)
+    bmap = dict(none=BIAS_NONE, affine=BIAS_AFFINE, muscle=BIAS_MUSCLE, user=BIAS_USER)
+    for i, aa in enumerate(A):
+        if "joint" in aa:
+            act_trntype[i] = TRN_JOINT
+            act_trnid[i] = names["joint"].index(aa["joint"])
+        elif "tendon" in aa:
+            act_trntype[i] = TRN_TENDON
+            act_trnid[i] = names["tendon"].index(aa["tendon"])
+        else:
+            raise NotImplementedError("actuator transmission must be joint or tendon")
+        act_gainprm[i, 0] = 1.0
+        tag = aa["_tag"]
+        if tag == "general":
+            act_gaintype[i] = gmap[aa.get("gaintype", "fixed")]
+            act_biastype[i] = bmap[aa.get("biastype", "none")]
+            if "gainprm" in aa:
+                act_gainprm[i] = _vec(aa["gainprm"], 10)
+            if "biasprm" in aa:
+                act_biasprm[i] = _vec(aa["biasprm"], 10)
+        elif tag == "motor":
+            pass
+        elif tag == "position":
+            kp = float(aa.get("kp", 1))
+            act_gainprm[i, 0] = kp
+            act_biastype[i] = BIAS_AFFINE
+            act_biasprm[i, 1] = -kp
+        elif tag == "velocity":
+            kv = float(aa.get("kv", 1))
+            act_gainprm[i, 0] = kv
+            act_biastype[i] = BIAS_AFFINE
+            act_biasprm[i, 2] = -kv
+        else:
+            raise NotImplementedError(f"actuator <{tag}>")
+        act_ctrllimited[i] = int(aa.get("ctrllimited", "false") == "true")
+        act_forcelimited[i] = int(aa.get("forcelimited", "false") == "true")
+        act_ctrlrange[i] = _vec(aa.get("ctrlrange", "0 0"), 2)
+        act_forcerange[i] = _vec(aa.get("forcerange", "0 0"), 2)
+        act_gear[i] = _vec(aa.get("gear", "1 0 0 0 0 0"), 6)
+        if "user" in aa:
+            act_user0[i] = _vec(aa["user"])[0]
+
+    # ---- equality (weld / joint), sensors: parsed for the rearrange rows
+    E = []
+    for ee in root.findall("equality"):
+        for e in ee:
+            ea = defaults.resolve("equality", e, None)
+            ea["_tag"] = e.tag
+            E.append(ea)
+    neq = len(E)
+    names["equality"] = [e.get("name") for e in E]
+    eq_type = np.zeros(neq, int)
+    eq_obj1 = np.zeros(neq, int)
+    eq_obj2 = -np.ones(neq, int)
+    eq_active = np.ones(neq, int)
+    eq_data = np.zeros((neq, 7))
+    eq_solref = np.zeros((neq, 2))
+    eq_solimp = np.zeros((neq, 5))
+    for i, ea in enumerate(E):
+        tag = ea["_tag"]
+        eq_active[i] = int(ea.get("active", "true") == "true")
+        eq_solref[i] = _vec(ea.get("solref", DEFAULT_SOLREF), 2)
+        eq_solimp[i] = _solimp(ea.get("solimp"))
+        if tag == "weld":
+            eq_type[i] = EQ_WELD
+            eq_obj1[i] = names["body"].index(ea["body1"])
+            eq_obj2[i] = names["body"].index(ea["body2"]) if "body2" in ea else 0
+            eq_data[i, 3] = 1.0  # relpose filled by setconst (relative pose at qpos0)
+        elif tag == "joint":
+            eq_type[i] = EQ_JOINT
+            eq_obj1[i] = names["joint"].index(ea["joint1"])
+            eq_obj2[i] = names["joint"].index(ea["joint2"]) if "joint2" in ea else -1
+            eq_data[i, :5] = _vec(ea.get("polycoef", "0 1 0 0 0"), 5)
+        else:
+            raise NotImplementedError(f"equality <{tag}>")
+
+    SENS = []
+    for se in root.findall("sensor"):
+        for s in se:
+            SENS.append(s)
+    nsensor = len(SENS)
+    names["sensor"] = [s.get("name") for s in SENS]
+    sensor_type = np.zeros(nsensor, int)
+    sensor_objid = np.zeros(nsensor, int)
+    sensor_adr = np.zeros(nsensor, int)
+    sensor_dim = np.zeros(nsensor, int)
+    adr = 0
+    for i, s in enumerate(SENS):
+        if s.tag == "touch":
+            sensor_type[i], sensor_dim[i] = SENS_TOUCH, 1
+            sensor_objid[i] = names["site"].index(s.get("site"))
+        elif s.tag == "jointpos":
+            sensor_type[i], sensor_dim[i] = SENS_JOINTPOS, 1
+            sensor_objid[i] = names["joint"].index(s.get("joint"))
+        elif s.tag in ("force", "torque"):
+            sensor_type[i], sensor_dim[i] = (SENS_FORCE if s.tag == "force" else SENS_TORQUE), 3
+            sensor_objid[i] = names["site"].index(s.get("site"))
+        else:
+            raise NotImplementedError(f"sensor <{s.tag}>")
+        sensor_adr[i] = adr
+        adr += sensor_dim[i]
+
+    # ---- mesh tables
+    nmesh = len(mesh_names)
+    mesh_vertadr = np.zeros(nmesh, int)
+    mesh_vertnum = np.zeros(nmesh, int)
+    mesh_faceadr = np.zeros(nmesh, int)
+    mesh_facenum = np.zeros(nmesh, int)
+    adj_lists = []
+    va = fa = 0
+    for i in range(nmesh):
+        nvert = len(mesh_verts[i])
+        mesh_vertadr[i], mesh_vertnum[i] = va, nvert
+        mesh_faceadr[i], mesh_facenum[i] = fa, len(mesh_faces[i])
+        nb = [set() for _ in range(nvert)]
+        for f in mesh_faces[i]:
+            for a, b in ((0, 1), (1, 2), (2, 0)):
+                nb[f[a]].add(int(f[b]))
+                nb[f[b]].add(int(f[a]))
+        adj_lists += [sorted(s) for s in nb]
+        va += nvert
+        fa += len(mesh_faces[i])
+    adjadr = np.zeros(va + 1, int)
+    for i, l in enumerate(adj_lists):
+        adjadr[i + 1] = adjadr[i] + len(l)
+    mesh_adj = np.array([x for l in adj_lists for x in l], int)
+    mesh_vert = np.concatenate(mesh_verts) if nmesh else np.zeros((0, 3))
+    mesh_face = np.concatenate(mesh_faces) if nmesh else np.zeros((0, 3), int)
+
+    cone = dict(pyramidal=0, elliptic=1)[opt.get("cone", "pyramidal")]
+    if opt.get("solver", "Newton") != "Newton":
+        raise NotImplementedError("only the Newton solver (MuJoCo's default) is implemented")
+    if opt.get("integrator", "Euler") != "Euler":
+        raise NotImplementedError("only the Euler integrator is implemented")
+
+    m.update(
+        nq=nq, nv=nv, nu=nu, nbody=nbody, njnt=njnt, ngeom=ngeom, nsite=nsite, ntendon=ntendon,
+        nwrap=len(W_type), nmesh=nmesh, nmeshvert=len(mesh_vert), nmeshadj=len(mesh_adj),
+        nmeshface=len(mesh_face), npair=len(pair1), nlevel=nlevel, nmaskw=nmaskw,
+        nuserdata=int(size_attrs.get("nuserdata", 0)), nconmax=int(size_attrs.get("nconmax", -1)),
+        njmax=int(size_attrs.get("njmax", -1)), neq=neq, nmocap=nmocap, nsensor=nsensor, nsensordata=adr,
+        opt_timestep=[float(opt.get("timestep", 0.002))],
+        opt_gravity=_vec(opt.get("gravity", "0 0 -9.81"), 3),
+        opt_tolerance=[float(opt.get("tolerance", 1e-8))],
+        opt_impratio=[float(opt.get("impratio", 1))],
+        opt_mpr_tolerance=[float(opt.get("mpr_tolerance", 1e-6))],
+        opt_ls_tolerance=[0.01],
+        opt_meaninertia=[1.0],
+        opt_iterations=[int(opt.get("iterations", 100))],
+        opt_ls_iterations=[50],
+        opt_mpr_iterations=[int(opt.get("mpr_iterations", 50))],
+        opt_cone=[cone], opt_disableflags=[disableflags], opt_pid=[0],
+        body_parentid=parent, body_rootid=rootid, body_weldid=weldid, body_mocapid=mocapid,
+        body_jntadr=body_jntadr, body_jntnum=body_jntnum, body_dofadr=body_dofadr,
+        body_dofnum=body_dofnum, body_geomadr=body_geomadr, body_geomnum=body_geomnum,
+        body_level=level, body_order=order, level_adr=level_adr,
+        body_dofmask=dofmask.view(np.int32), body_pos=body_pos, body_quat=body_quat,
+        body_ipos=body_ipos, body_iquat=body_iquat, body_mass=body_mass,
+        body_subtreemass=subtreemass, body_inertia=body_inertia,
+        body_invweight0=np.zeros((nbody, 2)),
+        jnt_type=jnt_type, jnt_qposadr=jnt_qposadr, jnt_dofadr=jnt_dofadr, jnt_bodyid=jnt_bodyid,
+        jnt_limited=jnt_limited, jnt_pos=jnt_pos, jnt_axis=jnt_axis, jnt_stiffness=jnt_stiffness,
+        jnt_range=jnt_range, jnt_margin=jnt_margin, jnt_solref=jnt_solref, jnt_solimp=jnt_solimp,
+        dof_bodyid=np.array(dof_bodyid, int), dof_jntid=np.array(dof_jntid, int),
+        dof_parentid=dof_parentid, dof_armature=np.array(dof_armature),
+        dof_damping=np.array(dof_damping), dof_frictionloss=np.array(dof_frictionloss),
+        dof_invweight0=np.zeros(nv), dof_solref=np.array(dof_solref).reshape(nv, 2),
+        dof_solimp=np.array(dof_solimp).reshape(nv, 5), qpos0=qpos0, qpos_spring=qpos_spring,
+        geom_type=geom_type, geom_bodyid=geom_bodyid, geom_dataid=geom_dataid,
+        geom_contype=geom_contype, geom_conaffinity=geom_conaffinity, geom_condim=geom_condim,
+        geom_priority=geom_priority, geom_size=geom_size, geom_pos=geom_pos, geom_quat=geom_quat,
+        geom_rbound=geom_rbound, geom_friction=geom_friction, geom_margin=geom_margin,
+        geom_gap=geom_gap, geom_solmix=geom_solmix, geom_solref=geom_solref, geom_solimp=geom_solimp,
+        site_bodyid=site_bodyid, site_pos=site_pos, site_quat=site_quat,
+        mesh_vertadr=mesh_vertadr, mesh_vertnum=mesh_vertnum, mesh_faceadr=mesh_faceadr,
+        mesh_facenum=mesh_facenum, mesh_vert=mesh_vert, mesh_adjadr=adjadr, mesh_adj=mesh_adj,
+        mesh_face=mesh_face, pair_geom1=np.array(pair1, int), pair_geom2=np.array(pair2, int),
+        tendon_adr=np.array([t["_adr"] for t in T], int), tendon_num=np.array([t["_num"] for t in T], int),
+        tendon_limited=tendon_limited, tendon_range=tendon_range, tendon_margin=tendon_margin,
+        tendon_stiffness=tendon_stiffness, tendon_damping=tendon_damping,
+        tendon_frictionloss=tendon_frictionloss, tendon_lengthspring=tendon_lengthspring,
+        tendon_length0=np.zeros(ntendon), tendon_invweight0=np.zeros(ntendon),
+        tendon_solref_lim=tendon_solref_lim, tendon_solimp_lim=tendon_solimp_lim,
+        wrap_type=np.array(W_type, int), wrap_objid=np.array(W_obj, int), wrap_prm=np.array(W_prm, float),
+        actuator_trntype=act_trntype, actuator_trnid=act_trnid, actuator_gaintype=act_gaintype,
+        actuator_biastype=act_biastype, actuator_ctrllimited=act_ctrllimited,
+        actuator_forcelimited=act_forcelimited, actuator_gainprm=act_gainprm,
+        actuator_biasprm=act_biasprm, actuator_ctrlrange=act_ctrlrange,
+        actuator_forcerange=act_forcerange, actuator_gear=act_gear, actuator_user0=act_user0,
+        eq_type=eq_type, eq_obj1id=eq_obj1, eq_obj2id=eq_obj2, eq_active=eq_active, eq_data=eq_data,
+        eq_solref=eq_solref, eq_solimp=eq_solimp,
+        sensor_type=sensor_type, sensor_objid=sensor_objid, sensor_adr=sensor_adr, sensor_dim=sensor_dim,
+    )
+    for k, v in list(m.items()):
+        if not isinstance(v, (int, np.integer)):
+            m[k] = np.ascontiguousarray(np.asarray(v)).reshape(-1)
+    cm = CompiledModel(m, names, xml_string)
+    set_const(m)
+    return cm
+
+
+def _solimp(s):
+    if s is None:
+        return np.array(DEFAULT_SOLIMP)
+    v = _vec(s)
+    out = np.array(DEFAULT_SOLIMP)
+    out[:len(v)] = v
+    return out
+
+
+def _eig_frame(I):
+    """Principal moments + right-handed principal axes of a symmetric 3x3."""
+    w, v = np.linalg.eigh(I)
+    # MuJoCo sorts principal moments in decreasing order
+    idx = np.argsort(-w)
+    w, v = w[idx], v[:, idx]
+    if np.linalg.det(v) < 0:
+        v[:, 2] = -v[:, 2]
+    return w, v
+
+
+def _geom_volume_inertia(t, size, meshprop):
+    """Volume and unit-density inertia tensor (geom frame, about geom centre)."""
+    if t == GEOM_BOX:
+        a, b, c = size
+        vol = 8 * a * b * c
+        I = vol / 3.0 * np.diag([b * b + c * c, a * a + c * c, a * a + b * b])
+    elif t == GEOM_SPHERE:
+        r = size[0]
+        vol = 4.0 / 3.0 * np.pi * r ** 3
+        I = 0.4 * vol * r * r * np.eye(3)
+    elif t == GEOM_CYLINDER:
+        r, h = size[0], size[1]
+        vol = np.pi * r * r * 2 * h
+        ix = vol * (3 * r * r + 4 * h * h) / 12.0
+        I = np.diag([ix, ix, vol * r * r / 2.0])
+    elif t == GEOM_CAPSULE:
+        r, h = size[0], size[1]
+        vc = np.pi * r * r * 2 * h
+        vs = 4.0 / 3.0 * np.pi * r ** 3
+        vol = vc + vs
+        iz = vc * r * r / 2.0 + vs * 0.4 * r * r
+        ix = vc * (3 * r * r + 4 * h * h) / 12.0 + vs * (0.4 * r * r + h * h + 0.75 * r * h)
+        I = np.diag([ix, ix, iz])
+    elif t == GEOM_ELLIPSOID:
+        a, b, c = size
+        vol = 4.0 / 3.0 * np.pi * a * b * c
+        I = vol / 5.0 * np.diag([b * b + c * c, a * a + c * c, a * a + b * b])
+    elif t == GEOM_MESH:
+        vol, I = meshprop
+    else:  # plane / hfield
+        vol, I = 0.0, np.zeros((3, 3))
+    return vol, np.asarray(I, float)
+
+
+# ----------------------------------------------------------------------------------------------
+# mj_setConst restatement (numpy, dense): quantities that depend on qpos0 and on editable
+# model parameters.  Called at compile time and from MjSim.set_constants()
+# (robogym/mujoco/simulation_interface.py:197-201).
+def kinematics(m, qpos):
+    """Dense numpy forward kinematics.  Returns xpos, xquat, per-dof (axis, anchor) in world."""
+    nbody, njnt = m["nbody"], m["njnt"]
+    bp = m["body_pos"].reshape(-1, 3)
+    bq = m["body_quat"].reshape(-1, 4)
+    xpos = np.zeros((nbody, 3))
+    xquat = np.zeros((nbody, 4))
+    xquat[0, 0] = 1
+    jaxis = np.zeros((njnt, 3))
+    janchor = np.zeros((njnt, 3))
+    jpos = m["jnt_pos"].reshape(-1, 3)
+    jax = m["jnt_axis"].reshape(-1, 3)
+    for b in range(1, nbody):
+        p = m["body_parentid"][b]
+        pos = xpos[p] + rot_vec(xquat[p], bp[b])
+        quat = quat_mul(xquat[p], bq[b])
+        for j in range(m["body_jntadr"][b], m["body_jntadr"][b] + m["body_jntnum"][b]) if m["body_jntnum"][b] else []:
+            t = m["jnt_type"][j]
+            qa = m["jnt_qposadr"][j]
+            if t == JNT_FREE:
+                pos = qpos[qa:qa + 3].copy()
+                quat = quat_normalize(qpos[qa + 3:qa + 7])
+                janchor[j] = pos
+                jaxis[j] = [0, 0, 1]
+                continue
+            anchor = pos + rot_vec(quat, jpos[j])
+            axis = rot_vec(quat, jax[j])
+            if t == JNT_SLIDE:
+                pos = pos + axis * (qpos[qa] - m["qpos0"][qa])
+            elif t == JNT_HINGE:
+                quat = quat_mul(quat, axisangle2quat(jax[j], qpos[qa] - m["qpos0"][qa]))
+                pos = anchor - rot_vec(quat, jpos[j])
+            elif t == JNT_BALL:
+                quat = quat_mul(quat, quat_normalize(qpos[qa:qa + 4]))
+                pos = anchor - rot_vec(quat, jpos[j])
+            janchor[j] = anchor
+            jaxis[j] = axis
+        xpos[b] = pos
+        xquat[b] = quat_normalize(quat)
+    return xpos, xquat, jaxis, janchor
+
+
+def body_jacobian(m, xpos, xquat, jaxis, janchor, b, point):
+    """3xnv translational and rotational Jacobians of `point` fixed to body b."""
+    nv = m["nv"]
+    jp = np.zeros((3, nv))
+    jr = np.zeros((3, nv))
+    mask = m["body_dofmask"].view(np.uint32).reshape(m["nbody"], -1)[b]
+    for d in range(nv):
+        if not (mask[d // 32] >> (d % 32)) & 1:
+            continue
+        j = m["dof_jntid"][d]
+        t = m["jnt_type"][j]
+        k = d - m["jnt_dofadr"][j]
+        if t == JNT_SLIDE:
+            jp[:, d] = jaxis[j]
+        elif t == JNT_HINGE:
+            jr[:, d] = jaxis[j]
+            jp[:, d] = np.cross(jaxis[j], point - janchor[j])
+        elif t == JNT_BALL:
+            ax = quat2mat(xquat[m["jnt_bodyid"][j]])[:, k]
+            jr[:, d] = ax
+            jp[:, d] = np.cross(ax, point - janchor[j])
+        elif t == JNT_FREE:
+            if k < 3:
+                jp[k, d] = 1.0
+            else:
+                ax = quat2mat(xquat[m["jnt_bodyid"][j]])[:, k - 3]
+                jr[:, d] = ax
+                jp[:, d] = np.cross(ax, point - xpos[m["jnt_bodyid"][j]])
+    return jp, jr
+
+
+def mass_matrix(m, qpos):
+    xpos, xquat, jaxis, janchor = kinematics(m, qpos)
+    nv = m["nv"]
+    M = np.diag(m["dof_armature"].astype(float))
+    for b in range(1, m["nbody"]):
+        mass = m["body_mass"][b]
+        if mass == 0 and not m["body_inertia"].reshape(-1, 3)[b].any():
+            continue
+        R = quat2mat(quat_mul(xquat[b], m["body_iquat"].reshape(-1, 4)[b]))
+        com = xpos[b] + rot_vec(xquat[b], m["body_ipos"].reshape(-1, 3)[b])
+        Iw = R @ np.diag(m["body_inertia"].reshape(-1, 3)[b]) @ R.T
+        jp, jr = body_jacobian(m, xpos, xquat, jaxis, janchor, b, com)
+        M += mass * jp.T @ jp + jr.T @ Iw @ jr
+    return M, (xpos, xquat, jaxis, janchor)
+
+
+def tendon_length_fixed(m, qpos, i):
+    """Length of a fixed tendon; spatial tendons are evaluated by the simulator (set_const_tendon)."""
+    L = 0.0
+    for w in range(m["tendon_adr"][i], m["tendon_adr"][i] + m["tendon_num"][i]):
+        if m["wrap_type"][w] != WRAP_JOINT:
+            return None
+        L += m["wrap_prm"][w] * qpos[m["jnt_qposadr"][m["wrap_objid"][w]]]
+    return L
+
+
+def set_const(m, spatial_tendon_eval=None):
+    """Recompute body_subtreemass, dof_invweight0, body_invweight0, tendon_length0/invweight0,
+    opt_meaninertia from the current model parameters (MuJoCo's mj_setConst).
+
+    spatial_tendon_eval(qpos0) -> (length[ntendon], J[ntendon, nv]) is supplied by a simulator
+    backend for spatial tendons; without it spatial-tendon constants keep their current values
+    (the engines recompute them at load time, see rg_model_load).
+    """
+    nbody, nv = m["nbody"], m["nv"]
+    parent = m["body_parentid"]
+    st = m["body_mass"].astype(float).copy()
+    for b in range(nbody - 1, 0, -1):
+        st[parent[b]] += st[b]
+    m["body_subtreemass"][:] = st
+    if nv == 0:
+        return
+    M, (xpos, xquat, jaxis, janchor) = mass_matrix(m, m["qpos0"])
+    Minv = np.linalg.inv(M)
+    m["opt_meaninertia"][0] = float(np.mean(np.diag(M)))
+    # dof_invweight0: diagonal of M^-1, averaged over the 3 dofs of ball / free-joint triplets
+    dinv = np.diag(Minv).copy()
+    for j in range(m["njnt"]):
+        t, a = m["jnt_type"][j], m["jnt_dofadr"][j]
+        if t == JNT_BALL:
+            dinv[a:a + 3] = dinv[a:a + 3].mean()
+        elif t == JNT_FREE:
+            dinv[a:a + 3] = dinv[a:a + 3].mean()
+            dinv[a + 3:a + 6] = dinv[a + 3:a + 6].mean()
+    m["dof_invweight0"][:] = dinv
+    # body_invweight0: mean translational / rotational diag of J M^-1 J^T at the body com
+    biw = m["body_invweight0"].reshape(-1, 2)
+    biw[:] = 0
+    for b in range(1, nbody):
+        if m["body_weldid"][b] == 0:
+            continue
+        com = xpos[b] + rot_vec(xquat[b], m["body_ipos"].reshape(-1, 3)[b])
+        jp, jr = body_jacobian(m, xpos, xquat, jaxis, janchor, b, com)
+        Ap = jp @ Minv @ jp.T
+        Ar = jr @ Minv @ jr.T
+        biw[b, 0] = max(np.trace(Ap) / 3.0, MINVAL)
+        biw[b, 1] = max(np.trace(Ar) / 3.0, MINVAL)
+    # tendons (fixed ones here; spatial through the callback)
+    if m["ntendon"]:
+        if spatial_tendon_eval is not None:
+            L, Jt = spatial_tendon_eval(m["qpos0"])
+        else:
+            L, Jt = None, None
+        for i in range(m["ntendon"]):
+            lf = tendon_length_fixed(m, m["qpos0"], i)
+            if lf is not None:
+                row = np.zeros(nv)
+                for w in range(m["tendon_adr"][i], m["tendon_adr"][i] + m["tendon_num"][i]):
+                    row[m["jnt_dofadr"][m["wrap_objid"][w]]] += m["wrap_prm"][w]
+                m["tendon_length0"][i] = lf
+                m["tendon_invweight0"][i] = max(row @ Minv @ row, MINVAL)
+            elif L is not None:
+                m["tendon_length0"][i] = L[i]
+                m["tendon_invweight0"][i] = max(Jt[i] @ Minv @ Jt[i], MINVAL)
+            if m["tendon_lengthspring"][i] < 0 and (lf is not None or L is not None):
+                m["tendon_lengthspring"][i] = m["tendon_length0"][i]
+    # weld relpose at qpos0
+    for i in range(m["neq"]):
+        if m["eq_type"][i] == EQ_WELD:
+            b1, b2 = m["eq_obj1id"][i], m["eq_obj2id"][i]
+            d = m["eq_data"].reshape(-1, 7)[i]
+            q1c = quat_conj(xquat[b1])
+            d[:3] = rot_vec(q1c, xpos[b2] - xpos[b1])
+            d[3:7] = quat_mul(q1c, xquat[b2])

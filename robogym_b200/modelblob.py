@@ -1,0 +1,87 @@
+"""Pack / unpack the compiled-model blob described by include/rg_model_fields.h.
+
+The blob is what crosses the C ABI (`rg_model_load`, include/robogym_b200.h); it
+plays the role of the `mjModel` that `mujoco_py.load_model_from_xml` returns in
+the reference (robogym/mujoco/mujoco_xml.py:259).
+"""
+import os
+import re
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FIELDS_H = os.path.join(_HERE, "..", "include", "rg_model_fields.h")
+MAGIC = b"RGMODEL1"
+
+_pat = re.compile(r"^\s*RG_(DIM|I|F)\(\s*(\w+)\s*(?:,\s*(.+?)\s*)?\)\s*(?:/\*.*)?$")
+
+
+def field_list(path=FIELDS_H):
+    """Return (dims, arrays): dims = [name], arrays = [(kind, name, count_expr)]."""
+    dims, arrays = [], []
+    with open(path) as f:
+        for line in f:
+            m = _pat.match(line)
+            if not m:
+                continue
+            kind, name, cnt = m.groups()
+            if kind == "DIM":
+                dims.append(name)
+            else:
+                arrays.append((kind, name, cnt))
+    return dims, arrays
+
+
+DIMS, ARRAYS = field_list()
+
+
+def _count(expr, dims):
+    return int(eval(expr, {"__builtins__": {}}, dict(dims)))
+
+
+def pack(model):
+    """model: dict name -> int (dims) / ndarray (arrays). Returns bytes."""
+    dims = {d: int(model[d]) for d in DIMS}
+    out = bytearray()
+    out += MAGIC
+    out += struct.pack("<i", len(DIMS))
+    for d in DIMS:
+        out += struct.pack("<i", dims[d])
+    for kind, name, cnt in ARRAYS:
+        n = _count(cnt, dims)
+        while len(out) % 8:
+            out += b"\0"
+        arr = np.asarray(model[name]).reshape(-1)
+        if arr.size != n:
+            raise ValueError(f"field {name}: expected {n} values, got {arr.size}")
+        if kind == "I":
+            out += arr.astype("<i4").tobytes()
+        else:
+            out += arr.astype("<f8").tobytes()
+    while len(out) % 8:
+        out += b"\0"
+    return bytes(out)
+
+
+def unpack(blob):
+    """Inverse of pack(): returns dict of ints and (writable) flat numpy arrays."""
+    blob = bytes(blob)
+    if blob[:8] != MAGIC:
+        raise ValueError("bad model blob magic")
+    (ndim,) = struct.unpack_from("<i", blob, 8)
+    if ndim != len(DIMS):
+        raise ValueError("model blob was built against a different rg_model_fields.h")
+    vals = struct.unpack_from("<%di" % ndim, blob, 12)
+    model = dict(zip(DIMS, vals))
+    off = 12 + 4 * ndim
+    for kind, name, cnt in ARRAYS:
+        n = _count(cnt, model)
+        off = (off + 7) & ~7
+        if kind == "I":
+            model[name] = np.frombuffer(blob, dtype="<i4", count=n, offset=off).copy()
+            off += 4 * n
+        else:
+            model[name] = np.frombuffer(blob, dtype="<f8", count=n, offset=off).copy()
+            off += 8 * n
+    return model

@@ -1,0 +1,93 @@
+"""Compose the reference's MJCF documents with the reference's OWN composer.
+
+Runs only in the build container (needs /root/reference).  It imports
+robogym.mujoco.mujoco_xml.MujocoXML under a 10-line `mujoco_py` stub (the real
+mujoco-py is not installable here) and repeats, call for call, what
+robogym/envs/dactyl/common/cube_env.py:172-218 + robogym/envs/dactyl/locked.py:79-96 (locked) and
+robogym/envs/dactyl/reach.py:79-143 (reach) do before `xml.build()`.
+The resulting XML strings are then compiled by robogym_b200.mjcf (tools/compile_models.py).
+"""
+import os
+import sys
+import tempfile
+import types
+
+REF = os.environ.get("ROBOGYM_REFERENCE", "/root/reference")
+
+
+def _install_stub():
+    if "mujoco_py" in sys.modules:
+        return
+    mp = types.ModuleType("mujoco_py")
+
+    class MjSim:  # noqa
+        pass
+
+    class MjSimState:  # noqa
+        pass
+
+    mp.MjSim, mp.MjSimState, mp.cymj = MjSim, MjSimState, None
+    gen = types.ModuleType("mujoco_py.generated")
+    const = types.ModuleType("mujoco_py.generated.const")
+    const.JNT_FREE, const.JNT_BALL, const.JNT_SLIDE, const.JNT_HINGE = 0, 1, 2, 3
+    gen.const = const
+    mp.generated, mp.const = gen, const
+    sys.modules.update({"mujoco_py": mp, "mujoco_py.generated": gen, "mujoco_py.generated.const": const})
+
+
+def mujoco_xml_cls():
+    import numpy as np
+
+    if not hasattr(np, "float"):
+        np.float = float
+    _install_stub()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from robogym.mujoco.mujoco_xml import MujocoXML
+
+    return MujocoXML
+
+
+def locked_xml():
+    import numpy as np
+
+    X = mujoco_xml_cls()
+    xml = X()
+    xml.add_default_compiler_directive()
+    p = "rubik/rubik_locked.xml"
+    xml.append(X.parse(p).remove_objects_by_name("annotation:outer_bound").add_name_prefix("cube:")
+               .set_named_objects_attr("cube:middle", tag="body", pos=[1.0, 0.87, 0.2])
+               .set_named_objects_attr("cube:middle", tag="geom", density=421.0))
+    xml.append(X.parse(p).remove_objects_by_name("annotation:outer_bound").add_name_prefix("target:")
+               .set_named_objects_attr("target:middle", tag="body", pos=[1.0, 0.87, 0.2])
+               .set_objects_attr(tag="geom", group="2", conaffinity="0", contype="0"))
+    xml.append(X.parse("floor/basic_floor.xml").set_named_objects_attr("floor", tag="body", pos=[1, 1, 0]))
+    xml.append(X.parse("robot/shadowhand/main.xml").add_name_prefix("robot0:")
+               .set_objects_attr(tag="size")
+               .set_named_objects_attr("robot0:hand_mount", tag="body", pos=[1.0, 1.25, 0.15],
+                                       euler=[np.pi / 2, 0, np.pi])
+               .remove_objects_by_name("robot0:annotation:outer_bound")
+               .remove_objects_by_name("robot0:hand_base"))
+    xml.append(X.parse("light/default.xml"))
+    return xml.xml_string()
+
+
+def reach_xml():
+    import numpy as np
+
+    X = mujoco_xml_cls()
+    xml = X()
+    xml.add_default_compiler_directive()
+    xml.append(X.parse("floor/basic_floor.xml").set_named_objects_attr("floor", tag="body", pos=[1, 1, 0]))
+    xml.append(X.parse("robot/shadowhand/main.xml").add_name_prefix("robot0:")
+               .set_named_objects_attr("robot0:hand_mount", tag="body", pos=[1.0, 1.25, 0.15],
+                                       euler=[np.pi / 2, 0, np.pi])
+               .remove_objects_by_name("robot0:annotation:outer_bound")
+               .remove_objects_by_name("robot0:hand_base"))
+    xml.append(X.parse("light/default.xml"))
+    return xml.xml_string()
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "locked"
+    sys.stdout.write({"locked": locked_xml, "reach": reach_xml}[which]())
