@@ -133,12 +133,6 @@ RG_I(mesh_vertadr, nmesh)
 RG_I(mesh_vertnum, nmesh)
 RG_I(mesh_faceadr, nmesh)
 RG_I(mesh_facenum, nmesh)
-RG_F(mesh_vert, nmeshvert * 3)       /* hull vertices, centred on the hull's volume centroid */
-RG_I(mesh_adjadr, nmeshvert + 1)     /* CSR into mesh_adj, global vertex ids */
-RG_I(mesh_adj, nmeshadj)             /* neighbour vertex ids, LOCAL to the mesh */
-RG_I(mesh_face, nmeshface * 3)       /* hull triangles, LOCAL vertex ids (rendering/inertia only) */
-RG_I(pair_geom1, npair)
-RG_I(pair_geom2, npair)
 
 /* ---- tendons ---- */
 RG_I(tendon_adr, ntendon)
@@ -186,3 +180,12 @@ RG_I(sensor_type, nsensor)
 RG_I(sensor_objid, nsensor)
 RG_I(sensor_adr, nsensor)
 RG_I(sensor_dim, nsensor)
+
+/* ---- BIG arrays (kept in global memory by the CUDA engine; everything above is small enough
+ *      to be staged into shared memory with one bulk copy).  Keep these LAST. ---- */
+RG_F(mesh_vert, nmeshvert * 3)       /* hull vertices, centred on the hull's volume centroid */
+RG_I(mesh_adjadr, nmeshvert + 1)     /* CSR into mesh_adj, global vertex ids */
+RG_I(mesh_adj, nmeshadj)             /* neighbour vertex ids, LOCAL to the mesh */
+RG_I(mesh_face, nmeshface * 3)       /* hull triangles, LOCAL vertex ids (rendering/inertia only) */
+RG_I(pair_geom1, npair)
+RG_I(pair_geom2, npair)

@@ -1,0 +1,235 @@
+/* rg_defs.h -- shared definitions of the batched rigid-body step engine.
+ *
+ * Execution model: ONE WARP PER ENVIRONMENT.  The device code is written as a sequence of
+ * "phases": inside RG_PHASE_BEGIN/RG_PHASE_END every lane runs the body with its own `lane`
+ * index; lanes exchange data only through the per-warp shared-memory scratch or through the
+ * warp helpers below (sum/max/broadcast/compaction).  Everything outside a phase is warp-uniform.
+ *
+ * The same source compiles two ways:
+ *   - nvcc, sm_100a (the product): a phase is straight-line SIMT code followed by __syncwarp();
+ *     the warp helpers are shuffles / ballots.
+ *   - g++ with -DRG_EMU (tests only, tests/emu): a phase is a `for (lane = 0..31)` loop and the
+ *     helpers run the same butterfly order on arrays.  This lets the CPU-only CI check the
+ *     kernel's logic against the fp64 oracle; it is never used as a product fallback.
+ */
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#ifdef RG_EMU
+#include <string.h>
+#define RG_DEV static inline
+#define RG_DEV_NOINLINE static
+#define RG_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
+#define RG_PHASE_END }
+#define RG_LANE_DECL
+#define LANEVAR(T, x) T x[32]
+#define LANEARR(T, x, n) T x[32][n]
+#define LV(x) x[lane]
+#define LA(x, i) x[lane][i]
+#define RG_LDG(p) (*(p))
+#define RG_RSQRT(x) (1.0f / sqrtf(x))
+#else
+#include <cuda_runtime.h>
+#define RG_DEV __device__ __forceinline__
+#define RG_DEV_NOINLINE __device__ __noinline__
+#define RG_PHASE_BEGIN {
+#define RG_PHASE_END } __syncwarp();
+#define RG_LANE_DECL const int lane = threadIdx.x & 31;
+#define LANEVAR(T, x) T x
+#define LANEARR(T, x, n) T x[n]
+#define LV(x) x
+#define LA(x, i) x[i]
+#define RG_LDG(p) __ldg(p)
+#define RG_RSQRT(x) rsqrtf(x)
+#endif
+
+#define RG_MINVAL 1e-15f
+#define RG_EPS 1.1920929e-07f
+#define RG_NCON 48       /* contacts kept per environment (reference nconmax=100, assets.xml:6) */
+#define RG_NEL 128       /* single-row constraint elements (friction loss + limits) */
+#define RG_CON_STRIDE 32
+#define RG_TILE 24       /* max dofs touched by one contact */
+
+enum { RG_JNT_FREE = 0, RG_JNT_BALL = 1, RG_JNT_SLIDE = 2, RG_JNT_HINGE = 3 };
+enum { RG_GEOM_PLANE = 0, RG_GEOM_SPHERE = 2, RG_GEOM_CAPSULE = 3, RG_GEOM_ELLIPSOID = 4, RG_GEOM_CYLINDER = 5, RG_GEOM_BOX = 6, RG_GEOM_MESH = 7 };
+enum { RG_WRAP_JOINT = 1, RG_WRAP_PULLEY = 2, RG_WRAP_SITE = 3, RG_WRAP_SPHERE = 4, RG_WRAP_CYLINDER = 5 };
+enum { RG_TRN_JOINT = 0, RG_TRN_TENDON = 3 };
+enum { RG_GAIN_FIXED = 0, RG_GAIN_USER = 2, RG_BIAS_NONE = 0, RG_BIAS_AFFINE = 1, RG_BIAS_USER = 3 };
+enum { RG_DSBL_CONSTRAINT = 1, RG_DSBL_EQUALITY = 2, RG_DSBL_FRICTIONLOSS = 4, RG_DSBL_LIMIT = 8, RG_DSBL_CONTACT = 16,
+       RG_DSBL_PASSIVE = 32, RG_DSBL_GRAVITY = 64, RG_DSBL_CLAMPCTRL = 128, RG_DSBL_WARMSTART = 256,
+       RG_DSBL_ACTUATION = 1024, RG_DSBL_REFSAFE = 2048 };
+enum { RG_EL_FLOSS = 0, RG_EL_JLIMIT = 1, RG_EL_TLIMIT = 2 };
+enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8 };
+
+/* Device view of the compiled model: fp32 / int32 copies of every rg_model_fields.h array. */
+struct RgModel {
+#define RG_DIM(n) int n;
+#define RG_I(n, c) const int* n;
+#define RG_F(n, c) const float* n;
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
+  const int* dof_treeroot;     /* first dof of the kinematic tree a dof belongs to (Cholesky envelope) */
+  float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
+  int small_bytes;             /* leading part of the arena that is staged into shared memory */
+};
+
+/* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
+struct RgLayout {
+  int qpos, qvel, ctrl, pid, warm;
+  int lpos, lquat, xpos, xquat, xipos, gxpos, sxpos;
+  int S, M, H;                       /* H aliases the block {Sdot,cvel,cacc,I10,crb} that is dead by then */
+  int Sdot, cvel, cacc, I10, crb;
+  int bias, passive, qfa, smooth, qacc, Ma, grad, search, Mv, qfc, tmp;
+  int tlen, tvel, tJ, alen, aforce;
+  int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
+  int el_i, el_D, el_R, el_aref, el_floss, el_jar, el_jv, el_f;
+  int tileJ, tileWJ, tileDof, cand, scal, eldof, env;
+  int total;
+};
+
+#ifndef RG_EMU
+/* ---- warp helpers (GPU) ---- */
+RG_DEV float rg_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+RG_DEV float rg_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+RG_DEV int rg_warp_or(int v) { return __reduce_or_sync(0xffffffffu, (unsigned)v); }
+RG_DEV int rg_warp_isum(int v) { return __reduce_add_sync(0xffffffffu, v); }
+RG_DEV float rg_warp_bcast(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+/* exclusive prefix sum of small non-negative ints; returns total in *total */
+RG_DEV int rg_warp_excl_scan(int v, int* total) {
+  const int lane = threadIdx.x & 31;
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+  *total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}
+#define RG_WARP_SUM(x) rg_warp_sum(x)
+#define RG_WARP_MAX(x) rg_warp_max(x)
+#define RG_WARP_OR(x) rg_warp_or(x)
+#define RG_WARP_ISUM(x) rg_warp_isum(x)
+#define RG_WARP_BCAST(x, src) rg_warp_bcast(x, src)
+#define RG_WARP_SCAN(cnt, pos, total) pos = rg_warp_excl_scan(cnt, &(total))
+#else
+/* ---- warp helpers (emulation: identical combination order) ---- */
+static inline float rg_emu_sum(const float* x) {
+  float t[32], u[32];
+  memcpy(t, x, sizeof t);
+  for (int o = 16; o > 0; o >>= 1) { for (int l = 0; l < 32; l++) u[l] = t[l] + t[l ^ o]; memcpy(t, u, sizeof t); }
+  return t[0];
+}
+static inline float rg_emu_max(const float* x) { float m = x[0]; for (int l = 1; l < 32; l++) m = fmaxf(m, x[l]); return m; }
+static inline int rg_emu_or(const int* x) { int m = 0; for (int l = 0; l < 32; l++) m |= x[l]; return m; }
+static inline int rg_emu_isum(const int* x) { int m = 0; for (int l = 0; l < 32; l++) m += x[l]; return m; }
+static inline int rg_emu_scan(const int* c, int* pos) { int s = 0; for (int l = 0; l < 32; l++) { pos[l] = s; s += c[l]; } return s; }
+#define RG_WARP_SUM(x) rg_emu_sum(x)
+#define RG_WARP_MAX(x) rg_emu_max(x)
+#define RG_WARP_OR(x) rg_emu_or(x)
+#define RG_WARP_ISUM(x) rg_emu_isum(x)
+#define RG_WARP_BCAST(x, src) (x[src])
+#define RG_WARP_SCAN(cnt, pos, total) total = rg_emu_scan(cnt, pos)
+#endif
+
+/* ---- small vector math ---- */
+RG_DEV float rg_dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+RG_DEV void rg_cross(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+RG_DEV void rg_sub3(float* r, const float* a, const float* b) { r[0] = a[0] - b[0]; r[1] = a[1] - b[1]; r[2] = a[2] - b[2]; }
+RG_DEV void rg_add3(float* r, const float* a, const float* b) { r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; }
+RG_DEV void rg_copy3(float* r, const float* a) { r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; }
+RG_DEV void rg_scl3(float* r, const float* a, float s) { r[0] = a[0] * s; r[1] = a[1] * s; r[2] = a[2] * s; }
+RG_DEV void rg_addscl3(float* r, const float* a, float s) { r[0] += a[0] * s; r[1] += a[1] * s; r[2] += a[2] * s; }
+RG_DEV float rg_normalize3(float* a) {
+  float n2 = rg_dot3(a, a);
+  if (n2 < 1e-30f) { a[0] = 1; a[1] = 0; a[2] = 0; return 0.f; }
+  float n = sqrtf(n2), inv = 1.0f / n;
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+  return n;
+}
+RG_DEV void rg_quat_mul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+RG_DEV void rg_quat_norm(float* q) {
+  float n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2 < 1e-30f) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  float inv = 1.0f / sqrtf(n2);
+  q[0] *= inv; q[1] *= inv; q[2] *= inv; q[3] *= inv;
+}
+/* r = q v q^-1 */
+RG_DEV void rg_rot(float* r, const float* q, const float* v) {
+  float t[3], u[3] = {q[1], q[2], q[3]};
+  rg_cross(t, u, v);
+  t[0] *= 2; t[1] *= 2; t[2] *= 2;
+  float c[3];
+  rg_cross(c, u, t);
+  r[0] = v[0] + q[0] * t[0] + c[0];
+  r[1] = v[1] + q[0] * t[1] + c[1];
+  r[2] = v[2] + q[0] * t[2] + c[2];
+}
+RG_DEV void rg_quat2mat(float* m, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+RG_DEV void rg_mulmat3(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+RG_DEV void rg_mulmatT3(float* r, const float* m, const float* v) {
+  float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+RG_DEV float rg_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+RG_DEV int rg_dof_in_body(const RgModel& m, int body, int dof) {
+  return (((const unsigned*)m.body_dofmask)[body * m.nmaskw + (dof >> 5)] >> (dof & 31)) & 1u;
+}
+/* spatial vectors: V = [w; vO] (motion), F = [nO; f] (force), both about the (shifted) world origin */
+RG_DEV float rg_dot6(const float* a, const float* b) { return rg_dot3(a, b) + rg_dot3(a + 3, b + 3); }
+/* origin-form spatial inertia I = (m, h[3] = m*com, IO[6] = xx yy zz xy xz yz): F = I V */
+RG_DEV void rg_inertia_mul(float* F, const float* I, const float* V) {
+  float t[3], n[3];
+  rg_cross(t, V, I + 1);                 /* w x h */
+  float f0 = I[0] * V[3] + t[0], f1 = I[0] * V[4] + t[1], f2 = I[0] * V[5] + t[2];
+  n[0] = I[4] * V[0] + I[7] * V[1] + I[8] * V[2];
+  n[1] = I[7] * V[0] + I[5] * V[1] + I[9] * V[2];
+  n[2] = I[8] * V[0] + I[9] * V[1] + I[6] * V[2];
+  rg_cross(t, I + 1, V + 3);             /* h x vO */
+  F[0] = n[0] + t[0]; F[1] = n[1] + t[1]; F[2] = n[2] + t[2];
+  F[3] = f0; F[4] = f1; F[5] = f2;
+}
+RG_DEV void rg_cross_motion(float* r, const float* V, const float* S) {
+  float a[3], b[3], c[3];
+  rg_cross(a, V, S); rg_cross(b, V, S + 3); rg_cross(c, V + 3, S);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2];
+  r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+RG_DEV void rg_cross_force(float* r, const float* V, const float* F) {
+  float a[3], b[3], c[3];
+  rg_cross(a, V, F); rg_cross(b, V + 3, F + 3); rg_cross(c, V, F + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2];
+  r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+/* velocity of the body point at `p` generated by unit rate of motion axis S */
+RG_DEV void rg_jacp(float* jp, const float* S, const float* p) {
+  float t[3];
+  rg_cross(t, S, p);
+  jp[0] = S[3] + t[0]; jp[1] = S[4] + t[1]; jp[2] = S[5] + t[2];
+}

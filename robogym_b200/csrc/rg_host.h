@@ -1,0 +1,126 @@
+/* rg_host.h -- host-side model loading shared by the CUDA engine and the CPU emulation build:
+ * unpack the model blob (include/rg_model_fields.h) into one contiguous fp32/int32 arena whose
+ * leading `small_bytes` hold every small per-body/joint/dof/geom array (staged into shared memory
+ * by the kernel with one bulk copy) followed by the big read-only arrays (hull vertices, hull
+ * adjacency, candidate pair list) that stay in global memory.
+ */
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "rg_defs.h"
+
+struct RgHostModel {
+  std::vector<char> arena;
+  RgModel view;                 /* pointers into `arena` (host) */
+  std::vector<size_t> offsets;  /* byte offset of every RgModel pointer field, in struct order */
+  size_t small_bytes = 0;
+};
+
+static inline size_t rg_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, std::string& err) {
+  const char* p = (const char*)blob;
+  if (len < 12 || memcmp(p, "RGMODEL1", 8)) { err = "bad model blob magic"; return false; }
+  int ndim;
+  memcpy(&ndim, p + 8, 4);
+  RgModel& m = hm.view;
+  memset(&m, 0, sizeof m);
+  const int* dims = (const int*)(p + 12);
+  int k = 0;
+#define RG_DIM(n) if (k < ndim) m.n = dims[k]; k++;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  if (k != ndim) { err = "model blob built against a different rg_model_fields.h"; return false; }
+#define RG_DIM(n) const int n = m.n; (void)n;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  /* pass 1: sizes */
+  size_t src = 12 + 4 * (size_t)ndim, dst = 0;
+  std::vector<size_t> srcoff, dstoff, counts;
+  std::vector<int> isint;
+  std::vector<std::string> names;
+#define RG_DIM(n)
+#define RG_I(n, c) src = (src + 7) & ~(size_t)7; srcoff.push_back(src); src += 4 * (size_t)(c); dst = rg_align16(dst); dstoff.push_back(dst); dst += 4 * (size_t)(c); counts.push_back((size_t)(c)); isint.push_back(1); names.push_back(#n);
+#define RG_F(n, c) src = (src + 7) & ~(size_t)7; srcoff.push_back(src); src += 8 * (size_t)(c); dst = rg_align16(dst); dstoff.push_back(dst); dst += 4 * (size_t)(c); counts.push_back((size_t)(c)); isint.push_back(0); names.push_back(#n);
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  if (src > len) { err = "model blob truncated"; return false; }
+  /* derived arrays appended to the small section would disturb the order; put them right after the blob fields
+     but account for them in small_bytes by placing them BEFORE the first big field. */
+  size_t first_big = names.size();
+  for (size_t i = 0; i < names.size(); i++) if (names[i] == "mesh_vert") { first_big = i; break; }
+  /* re-run the destination layout: small fields, derived, big fields */
+  dst = 0;
+  for (size_t i = 0; i < first_big; i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
+  dst = rg_align16(dst); const size_t off_subtree = dst; dst += 4 * (size_t)m.nbody;
+  dst = rg_align16(dst); const size_t off_treeroot = dst; dst += 4 * (size_t)m.nv;
+  dst = rg_align16(dst);
+  hm.small_bytes = dst;
+  for (size_t i = first_big; i < names.size(); i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
+  dst = rg_align16(dst);
+  hm.arena.assign(dst, 0);
+  char* base = hm.arena.data();
+  for (size_t i = 0; i < names.size(); i++) {
+    if (isint[i]) memcpy(base + dstoff[i], p + srcoff[i], 4 * counts[i]);
+    else {
+      const double* s = (const double*)(p + srcoff[i]);
+      float* d = (float*)(base + dstoff[i]);
+      for (size_t q = 0; q < counts[i]; q++) d[q] = (float)s[q];
+    }
+  }
+  /* wire the view */
+  size_t idx = 0;
+  hm.offsets.clear();
+#define RG_DIM(n)
+#define RG_I(n, c) m.n = (const int*)(base + dstoff[idx]); hm.offsets.push_back(dstoff[idx]); idx++;
+#define RG_F(n, c) m.n = (const float*)(base + dstoff[idx]); hm.offsets.push_back(dstoff[idx]); idx++;
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  int* subtree = (int*)(base + off_subtree);
+  int* treeroot = (int*)(base + off_treeroot);
+  for (int b = 0; b < m.nbody; b++) subtree[b] = 1;
+  for (int b = m.nbody - 1; b > 0; b--) subtree[m.body_parentid[b]] += subtree[b];
+  for (int d = 0; d < m.nv; d++) { int r = d; while (m.dof_parentid[r] >= 0) r = m.dof_parentid[r]; treeroot[d] = r; }
+  /* depth-first numbering check: every body's parent must precede it and subtrees must be contiguous */
+  for (int b = 1; b < m.nbody; b++) {
+    const int par = m.body_parentid[b];
+    if (par >= b || b >= par + subtree[par]) { err = "bodies are not numbered depth-first"; return false; }
+  }
+  m.body_subtreesize = subtree;
+  m.dof_treeroot = treeroot;
+  hm.offsets.push_back(off_subtree);
+  hm.offsets.push_back(off_treeroot);
+  /* fp32 conditioning: translate the world so the scene sits near the origin */
+  double o[3] = {0, 0, 0};
+  int cnt = 0;
+  const double* bp = nullptr;
+  {
+    size_t i = 0;
+    for (; i < names.size(); i++) if (names[i] == "body_pos") break;
+    bp = (const double*)(p + srcoff[i]);
+  }
+  for (int b = 1; b < m.nbody; b++) if (m.body_parentid[b] == 0) { for (int a = 0; a < 3; a++) o[a] += bp[3 * b + a]; cnt++; }
+  for (int a = 0; a < 3; a++) m.origin[a] = cnt ? (float)(o[a] / cnt) : 0.0f;
+  float* body_pos = (float*)m.body_pos;
+  for (int b = 1; b < m.nbody; b++)
+    if (m.body_parentid[b] == 0) for (int a = 0; a < 3; a++) body_pos[3 * b + a] = (float)(bp[3 * b + a] - (double)m.origin[a]);
+  m.small_bytes = (int)hm.small_bytes;
+  if (m.nv > 32 * 8 || m.nmaskw > 8) { err = "model too large for the warp-per-env engine"; return false; }
+  return true;
+}

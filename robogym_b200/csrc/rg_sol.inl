@@ -1,0 +1,661 @@
+/* rg_sol.inl -- S8/S9/S13/S15 of the fused step: constraint elements (dof friction loss, joint and
+ * tendon limits, pyramidal frictional contacts) with solref/solimp impedance, Newton solver with
+ * exact line search on the primal convex problem, semi-implicit Euler with implicit joint damping.
+ * Replaces mj_makeConstraint / mj_fwdConstraint / mj_Euler inside the mj_step behind
+ * sim.step() (robogym/mujoco/simulation_interface.py:184; solver options from
+ * robogym/assets/xmls/robot/shadowhand/assets.xml:14-15).
+ *
+ * Jacobians are never materialised as nefc x nv: single-dof rows are handled by index, tendon
+ * rows reuse the tendon Jacobian, contact rows are rebuilt from the motion axes S on the fly.
+ */
+#pragma once
+#include "rg_col.inl"
+
+#define RG_MINIMP 0.0001f
+#define RG_MAXIMP 0.9999f
+
+RG_DEV float rg_impedance(const float* solimp, float xabs) {
+  const float dmin = rg_clamp(solimp[0], RG_MINIMP, RG_MAXIMP), dmax = rg_clamp(solimp[1], RG_MINIMP, RG_MAXIMP);
+  const float width = fmaxf(1e-12f, solimp[2]), mid = rg_clamp(solimp[3], RG_MINIMP, RG_MAXIMP), power = fmaxf(1.0f, solimp[4]);
+  const float x = xabs / width;
+  if (x >= 1.0f) return dmax;
+  if (x <= 0.0f) return dmin;
+  float y;
+  if (power == 1.0f) y = x;
+  else if (x <= mid) y = powf(x, power) / powf(mid, power - 1.0f);
+  else y = 1.0f - powf(1.0f - x, power) / powf(1.0f - mid, power - 1.0f);
+  return dmin + y * (dmax - dmin);
+}
+/* R (regulariser) and aref for one row; K is dropped for friction rows */
+RG_DEV void rg_row_params(const RgCtx& c, const float* solref_in, const float* solimp, float pos, float margin, float vel, float diagApprox,
+                          int isfriction, float* R, float* aref, float* Bout, float* KIout) {
+  float sr0 = solref_in[0];
+  const float sr1 = solref_in[1];
+  if (!(c.m.opt_disableflags[0] & RG_DSBL_REFSAFE) && sr0 > 0) sr0 = fmaxf(sr0, 2.0f * c.timestep);
+  const float p = pos - margin;
+  const float imp = rg_impedance(solimp, fabsf(p));
+  const float dmax = rg_clamp(solimp[1], RG_MINIMP, RG_MAXIMP);
+  *R = fmaxf(1e-12f, (1.0f - imp) * diagApprox / imp);
+  float K, B;
+  if (sr0 > 0) { K = 1.0f / fmaxf(1e-12f, dmax * dmax * sr0 * sr0 * sr1 * sr1); B = 2.0f / fmaxf(1e-12f, dmax * sr0); }
+  else { K = -sr0 / fmaxf(1e-12f, dmax * dmax); B = -sr1 / fmaxf(1e-12f, dmax); }
+  if (isfriction) K = 0.0f;
+  *aref = -B * vel - K * imp * p;
+  *Bout = B;
+  *KIout = K * imp * p;
+}
+
+/* contact-frame Jacobian column of dof d for contact record r (dim components), sign included; 0 if untouched */
+RG_DEV int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float* col) {
+  const RgModel& m = c.m;
+  const int b1 = (int)r[18], b2 = (int)r[19];
+  const int in1 = rg_dof_in_body(m, b1, d), in2 = rg_dof_in_body(m, b2, d);
+  if (in1 == in2) return 0;
+  const float* S = c.s + c.L.S + 6 * d;
+  float jp[3];
+  rg_jacp_world(c, d, r + 1, jp);
+  const float sg = in2 ? 1.0f : -1.0f;
+  col[0] = sg * rg_dot3(r + 4, jp);
+  if (dim > 1) { col[1] = sg * rg_dot3(r + 7, jp); col[2] = sg * rg_dot3(r + 10, jp); }
+  if (dim > 3) col[3] = sg * rg_dot3(r + 4, S);
+  if (dim > 4) { col[4] = sg * rg_dot3(r + 7, S); col[5] = sg * rg_dot3(r + 10, S); }
+  return 1;
+}
+RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k == 3 ? r[15] : r[16]); }
+
+/* y = M x (dense, symmetric) */
+RG_DEV void rg_matvec_phase(RgCtx& c, int y, int x) {
+  RG_LANE_DECL
+  const int nv = c.m.nv;
+  float* s = c.s;
+  RG_PHASE_BEGIN
+  for (int i = lane; i < nv; i += 32) {
+    float acc = 0.0f;
+    const float* row = s + c.L.M + i * nv;
+    for (int k = 0; k < nv; k++) acc += row[k] * s[x + k];
+    s[y + i] = acc;
+  }
+  RG_PHASE_END
+}
+
+/* in-place envelope Cholesky of the lower triangle of A (row stride nv); env[i] = first nonzero column */
+RG_DEV void rg_cholesky(RgCtx& c, int A, const int* env) {
+  RG_LANE_DECL
+  const int n = c.m.nv;
+  float* s = c.s;
+  for (int j = 0; j < n; j++) {
+    LANEVAR(float, sumv);
+    RG_PHASE_BEGIN
+    const int i = j + lane;
+    float acc = 0.0f;
+    if (i < n && env[i] <= j) {
+      acc = s[A + i * n + j];
+      const int k0 = env[i] > env[j] ? env[i] : env[j];
+      for (int k = k0; k < j; k++) acc -= s[A + i * n + k] * s[A + j * n + k];
+    }
+    LV(sumv) = acc;
+    RG_PHASE_END
+    const float diag = sqrtf(fmaxf(RG_WARP_BCAST(sumv, 0), 1e-20f));
+    const float inv = 1.0f / diag;
+    RG_PHASE_BEGIN
+    const int i = j + lane;
+    if (i == j) s[A + j * n + j] = diag;
+    else if (i < n) s[A + i * n + j] = LV(sumv) * inv;
+    for (int i2 = i + 32; i2 < n; i2 += 32) {
+      float acc = 0.0f;
+      if (env[i2] <= j) {
+        acc = s[A + i2 * n + j];
+        const int k0 = env[i2] > env[j] ? env[i2] : env[j];
+        for (int k = k0; k < j; k++) acc -= s[A + i2 * n + k] * s[A + j * n + k];
+      }
+      s[A + i2 * n + j] = acc * inv;
+    }
+    RG_PHASE_END
+  }
+}
+/* x <- (L L^T)^-1 x ; uses `tmp` as staging */
+RG_DEV void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int tmp) {
+  RG_LANE_DECL
+  const int n = c.m.nv;
+  float* s = c.s;
+  for (int j = 0; j < n; j++) {
+    RG_PHASE_BEGIN
+    const float xj = s[x + j] / s[A + j * n + j];
+    if (lane == 0) s[tmp + j] = xj;
+    for (int i = j + 1 + lane; i < n; i += 32)
+      if (env[i] <= j) s[x + i] -= s[A + i * n + j] * xj;
+    RG_PHASE_END
+  }
+  for (int j = n - 1; j >= 0; j--) {
+    RG_PHASE_BEGIN
+    const float xj = s[tmp + j] / s[A + j * n + j];
+    if (lane == 0) s[x + j] = xj;
+    for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + j * n + i] * xj;
+    RG_PHASE_END
+  }
+}
+
+/* ---------------------------------------------------------------- S8/S9 constraint elements */
+RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
+  RG_LANE_DECL
+  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const int nv = m.nv, flags = m.opt_disableflags[0];
+  int* el_i = (int*)(s + L.el_i);
+  int* eldof = (int*)(s + L.eldof);
+  int nel = 0, warn = 0;
+  RG_PHASE_BEGIN
+  for (int i = lane; i < 3 * nv; i += 32) eldof[i] = -1;
+  RG_PHASE_END
+  const int on = !(flags & RG_DSBL_CONSTRAINT);
+  /* dof friction loss: one element per dof with frictionloss > 0 */
+  for (int base = 0; on && !(flags & RG_DSBL_FRICTIONLOSS) && base < nv; base += 32) {
+    LANEVAR(int, cnt); LANEVAR(int, pos);
+    int tot;
+    RG_PHASE_BEGIN
+    const int d = base + lane;
+    LV(cnt) = (d < nv && m.dof_frictionloss[d] > 0.0f) ? 1 : 0;
+    RG_PHASE_END
+    RG_WARP_SCAN(cnt, pos, tot);
+    RG_PHASE_BEGIN
+    const int d = base + lane;
+    const int e = nel + LV(pos);
+    if (LV(cnt) && e < RG_NEL) {
+      float R, aref, B, KI;
+      rg_row_params(c, m.dof_solref + 2 * d, m.dof_solimp + 5 * d, 0.0f, 0.0f, s[L.qvel + d], m.dof_invweight0[d], 1, &R, &aref, &B, &KI);
+      el_i[e] = RG_EL_FLOSS + 8 * d;
+      s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = m.dof_frictionloss[d];
+      eldof[3 * d] = e;
+    }
+    RG_PHASE_END
+    nel += tot;
+  }
+  /* joint limits (hinge / slide) */
+  for (int base = 0; on && !(flags & RG_DSBL_LIMIT) && base < m.njnt; base += 32) {
+    LANEVAR(int, cnt); LANEVAR(int, pos);
+    int tot;
+    RG_PHASE_BEGIN
+    const int j = base + lane;
+    int cn = 0;
+    if (j < m.njnt && m.jnt_limited[j] && (m.jnt_type[j] == RG_JNT_SLIDE || m.jnt_type[j] == RG_JNT_HINGE)) {
+      const float q = s[L.qpos + m.jnt_qposadr[j]];
+      if (q - m.jnt_range[2 * j] < m.jnt_margin[j]) cn++;
+      if (m.jnt_range[2 * j + 1] - q < m.jnt_margin[j]) cn++;
+    }
+    LV(cnt) = cn;
+    RG_PHASE_END
+    RG_WARP_SCAN(cnt, pos, tot);
+    RG_PHASE_BEGIN
+    const int j = base + lane;
+    if (LV(cnt)) {
+      const int d = m.jnt_dofadr[j];
+      const float q = s[L.qpos + m.jnt_qposadr[j]];
+      int e = nel + LV(pos);
+      for (int side = 0; side < 2; side++) {
+        const float dist = side == 0 ? q - m.jnt_range[2 * j] : m.jnt_range[2 * j + 1] - q;
+        if (!(dist < m.jnt_margin[j]) || e >= RG_NEL) continue;
+        const float sg = side == 0 ? 1.0f : -1.0f;
+        float R, aref, B, KI;
+        rg_row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, m.jnt_margin[j], sg * s[L.qvel + d], m.dof_invweight0[d], 0, &R, &aref, &B, &KI);
+        el_i[e] = RG_EL_JLIMIT + 4 * side + 8 * d;
+        s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = 0.0f;
+        eldof[3 * d + 1 + side] = e;
+        e++;
+      }
+    }
+    RG_PHASE_END
+    nel += tot;
+  }
+  const int tl0 = nel < RG_NEL ? nel : RG_NEL;
+  /* tendon limits */
+  for (int base = 0; on && !(flags & RG_DSBL_LIMIT) && base < m.ntendon; base += 32) {
+    LANEVAR(int, cnt); LANEVAR(int, pos);
+    int tot;
+    RG_PHASE_BEGIN
+    const int t = base + lane;
+    int cn = 0;
+    if (t < m.ntendon && m.tendon_limited[t]) {
+      const float len = s[L.tlen + t];
+      if (len - m.tendon_range[2 * t] < m.tendon_margin[t]) cn++;
+      if (m.tendon_range[2 * t + 1] - len < m.tendon_margin[t]) cn++;
+    }
+    LV(cnt) = cn;
+    RG_PHASE_END
+    RG_WARP_SCAN(cnt, pos, tot);
+    RG_PHASE_BEGIN
+    const int t = base + lane;
+    if (LV(cnt)) {
+      const float len = s[L.tlen + t];
+      int e = nel + LV(pos);
+      for (int side = 0; side < 2; side++) {
+        const float dist = side == 0 ? len - m.tendon_range[2 * t] : m.tendon_range[2 * t + 1] - len;
+        if (!(dist < m.tendon_margin[t]) || e >= RG_NEL) continue;
+        const float sg = side == 0 ? 1.0f : -1.0f;
+        float R, aref, B, KI;
+        rg_row_params(c, m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, dist, m.tendon_margin[t], sg * s[L.tvel + t], m.tendon_invweight0[t], 0, &R, &aref, &B, &KI);
+        el_i[e] = RG_EL_TLIMIT + 4 * side + 8 * t;
+        s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = 0.0f;
+        e++;
+      }
+    }
+    RG_PHASE_END
+    nel += tot;
+  }
+  if (nel > RG_NEL) { nel = RG_NEL; warn |= RG_WARN_ROWS_FULL; }
+  /* contacts: per-contact solver parameters; cu = B * (Jc qvel) + [K imp (dist-margin)] on the normal row */
+  const int ncon = RG_SI(c, RG_S_NCON);
+  RG_PHASE_BEGIN
+  for (int k = lane; k < ncon; k += 32) {
+    float* r = s + L.con + RG_CON_STRIDE * k;
+    float* prm = s + L.cprm + 8 * k;
+    int dim = (int)r[17];
+    if ((flags & (RG_DSBL_CONTACT | RG_DSBL_CONSTRAINT)) || !(r[0] < r[13])) dim = 0; /* inactive: outside includemargin */
+    const int b1 = (int)r[18], b2 = (int)r[19];
+    const float tran = m.body_invweight0[2 * b1] + m.body_invweight0[2 * b2];
+    float R, aref, B, KI;
+    /* first row's diagApprox: tran + mu^2 tran (dim>1) or tran */
+    const float mu0 = r[14];
+    rg_row_params(c, r + 22, r + 24, r[0], r[13], 0.0f, dim > 1 ? tran + mu0 * mu0 * tran : tran, 0, &R, &aref, &B, &KI);
+    if (dim > 1) {
+      float mu = mu0 * sqrtf(1.0f / m.opt_impratio[0]);
+      if (mu < 1e-5f) mu = 1e-5f;
+      R = fmaxf(1e-12f, 2.0f * mu * mu * R);
+    }
+    prm[0] = 1.0f / R; prm[1] = (float)dim; prm[2] = B; prm[3] = KI;
+    /* velocity part of jar */
+    float v[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < nv && dim > 0; d++) {
+      float col[6];
+      if (!rg_contact_col(c, r, d, dim, col)) continue;
+      const float qd = s[L.qvel + d];
+      for (int a = 0; a < dim; a++) v[a] += col[a] * qd;
+    }
+    float* cb = s + L.cF + 6 * k; /* staged here until the solver initialises cu */
+    for (int a = 0; a < 6; a++) cb[a] = B * v[a];
+    cb[0] += KI;
+  }
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  if (lane == 0) { RG_SI(c, RG_S_NEL) = nel; RG_SI(c, RG_S_WARN) |= warn; RG_SI(c, RG_S_TL0) = tl0; }
+  RG_PHASE_END
+}
+
+/* ---------------------------------------------------------------- S13 Newton solver */
+/* jar of single-row element e for a candidate acceleration vector at offset x */
+RG_DEV float rg_el_Jx(const RgCtx& c, int code, int x) {
+  const int type = code & 3, side = (code >> 2) & 1, id = code >> 3;
+  const float* s = c.s;
+  if (type == RG_EL_FLOSS) return s[x + id];
+  if (type == RG_EL_JLIMIT) return side ? -s[x + id] : s[x + id];
+  float acc = 0.0f;
+  const float* J = s + c.L.tJ + id * c.m.nv;
+  for (int k = 0; k < c.m.nv; k++) acc += J[k] * s[x + k];
+  return side ? -acc : acc;
+}
+
+/* forces + cost at the current jar (el_jar, cu); returns total constraint cost; fills el_f and cF */
+RG_DEV float rg_solver_update(RgCtx& c, int nel, int ncon) {
+  RG_LANE_DECL
+  const RgLayout& L = c.L; float* s = c.s;
+  const int* el_i = (const int*)(s + L.el_i);
+  LANEVAR(float, part);
+  RG_PHASE_BEGIN
+  float cost = 0.0f;
+  for (int e = lane; e < nel; e += 32) {
+    const float jar = s[L.el_jar + e], D = s[L.el_D + e];
+    float f;
+    if ((el_i[e] & 3) == RG_EL_FLOSS) {
+      const float fl = s[L.el_floss + e], rf = s[L.el_R + e] * fl;
+      if (jar <= -rf) { f = fl; cost += -0.5f * rf * fl - fl * jar; }
+      else if (jar >= rf) { f = -fl; cost += -0.5f * rf * fl + fl * jar; }
+      else { f = -D * jar; cost += 0.5f * D * jar * jar; }
+    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; }
+    else f = 0.0f;
+    s[L.el_f + e] = f;
+  }
+  for (int k = lane; k < ncon; k += 32) {
+    const float* r = s + L.con + RG_CON_STRIDE * k;
+    const float* prm = s + L.cprm + 8 * k;
+    const float* u = s + L.cu + 6 * k;
+    const int dim = (int)prm[1];
+    const float D = prm[0];
+    float F[6] = {0, 0, 0, 0, 0, 0};
+    if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; } }
+    else for (int a = 1; a < dim; a++) {
+      const float mu = rg_contact_mu(r, a);
+      const float jp = u[0] + mu * u[a], jm = u[0] - mu * u[a];
+      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; }
+      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; }
+    }
+    float* cf = s + L.cF + 6 * k;
+    for (int a = 0; a < 6; a++) cf[a] = F[a];
+  }
+  LV(part) = cost;
+  RG_PHASE_END
+  return RG_WARP_SUM(part);
+}
+
+/* out[d] = sum_rows J^T f for every dof (single-row elements, tendon rows, contacts) */
+RG_DEV void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
+  RG_LANE_DECL
+  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const int* el_i = (const int*)(s + L.el_i);
+  const int* eldof = (const int*)(s + L.eldof);
+  RG_PHASE_BEGIN
+  for (int d = lane; d < m.nv; d += 32) {
+    float acc = 0.0f;
+    const int e0 = eldof[3 * d], e1 = eldof[3 * d + 1], e2 = eldof[3 * d + 2];
+    if (e0 >= 0) acc += s[L.el_f + e0];
+    if (e1 >= 0) acc += s[L.el_f + e1];
+    if (e2 >= 0) acc -= s[L.el_f + e2];
+    for (int e = tl0; e < nel; e++) {
+      const int code = el_i[e];
+      const float f = s[L.el_f + e];
+      if (f != 0.0f) acc += ((code >> 2) & 1 ? -f : f) * s[L.tJ + (code >> 3) * m.nv + d];
+    }
+    for (int k = 0; k < ncon; k++) {
+      const float* r = s + L.con + RG_CON_STRIDE * k;
+      const int dim = (int)s[L.cprm + 8 * k + 1];
+      float col[6];
+      if (dim == 0 || !rg_contact_col(c, r, d, dim, col)) continue;
+      const float* F = s + L.cF + 6 * k;
+      for (int a = 0; a < dim; a++) acc += col[a] * F[a];
+    }
+    s[out + d] = acc;
+  }
+  RG_PHASE_END
+}
+
+/* el_x[e] = J_e x, cx[k] = Jc_k x  (x = vector at offset xoff); if init, adds -aref / staged velocity terms */
+RG_DEV void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
+  RG_LANE_DECL
+  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const int* el_i = (const int*)(s + L.el_i);
+  RG_PHASE_BEGIN
+  for (int e = lane; e < nel; e += 32) {
+    float v = rg_el_Jx(c, el_i[e], xoff);
+    if (init) v -= s[L.el_aref + e];
+    s[el_out + e] = v;
+  }
+  for (int k = lane; k < ncon; k += 32) {
+    const float* r = s + L.con + RG_CON_STRIDE * k;
+    const int dim = (int)s[L.cprm + 8 * k + 1];
+    float v[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = 0; d < m.nv && dim > 0; d++) {
+      float col[6];
+      if (!rg_contact_col(c, r, d, dim, col)) continue;
+      const float xd = s[xoff + d];
+      for (int a = 0; a < dim; a++) v[a] += col[a] * xd;
+    }
+    if (init) for (int a = 0; a < 6; a++) v[a] += s[L.cF + 6 * k + a];
+    for (int a = 0; a < 6; a++) s[c_out + 6 * k + a] = v[a];
+  }
+  RG_PHASE_END
+}
+
+RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
+  RG_LANE_DECL
+  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const int nv = m.nv;
+  const int nel = RG_SI(c, RG_S_NEL), tl0 = RG_SI(c, RG_S_TL0), ncon = RG_SI(c, RG_S_NCON);
+  const int* el_i = (const int*)(s + L.el_i);
+  const int* eldof = (const int*)(s + L.eldof);
+  int* env = (int*)(s + L.env);
+  /* start from the previous solution (warm start) */
+  RG_PHASE_BEGIN
+  for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
+  RG_PHASE_END
+  rg_matvec_phase(c, L.Ma, L.qacc);
+  rg_J_mul_phase(c, L.qacc, L.el_jar, L.cu, nel, ncon, 1);
+  float cost_con = rg_solver_update(c, nel, ncon);
+  const float scale = 1.0f / (m.opt_meaninertia[0] * (float)(nv > 1 ? nv : 1));
+  const float tol = fmaxf(m.opt_tolerance[0], 1e-7f);
+  int iter = 0;
+  float cost;
+  {
+    LANEVAR(float, gp);
+    RG_PHASE_BEGIN
+    float a = 0.0f;
+    for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
+    LV(gp) = a;
+    RG_PHASE_END
+    cost = RG_WARP_SUM(gp) + cost_con;
+  }
+  for (; iter < m.opt_iterations[0]; iter++) {
+    /* gradient */
+    rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
+    LANEVAR(float, gn);
+    RG_PHASE_BEGIN
+    float a = 0.0f;
+    for (int d = lane; d < nv; d += 32) {
+      const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
+      s[L.grad + d] = g;
+      s[L.search + d] = -g;
+      a += g * g;
+    }
+    LV(gn) = a;
+    RG_PHASE_END
+    const float gnorm = sqrtf(RG_WARP_SUM(gn));
+    if (scale * gnorm < tol) break;
+    /* Hessian H = M + J' diag(D active) J */
+    RG_PHASE_BEGIN
+    for (int i = lane; i < nv * nv; i += 32) s[L.H + i] = s[L.M + i];
+    RG_PHASE_END
+    RG_PHASE_BEGIN
+    for (int d = lane; d < nv; d += 32) {
+      float add = 0.0f;
+      const int e0 = eldof[3 * d];
+      if (e0 >= 0) { const float rf = s[L.el_R + e0] * s[L.el_floss + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
+      for (int q = 1; q < 3; q++) { const int e = eldof[3 * d + q]; if (e >= 0 && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
+      s[L.H + d * nv + d] += add;
+    }
+    RG_PHASE_END
+    for (int e = tl0; e < nel; e++) {
+      if (!(s[L.el_jar + e] < 0.0f)) continue;
+      const int t = el_i[e] >> 3;
+      const float D = s[L.el_D + e];
+      RG_PHASE_BEGIN
+      for (int i = lane; i < nv; i += 32) {
+        const float ji = s[L.tJ + t * nv + i];
+        if (ji != 0.0f) for (int k = 0; k < nv; k++) s[L.H + i * nv + k] += D * ji * s[L.tJ + t * nv + k];
+      }
+      RG_PHASE_END
+    }
+    for (int k = 0; k < ncon; k++) {
+      const float* r = s + L.con + RG_CON_STRIDE * k;
+      const float* prm = s + L.cprm + 8 * k;
+      const int dim = (int)prm[1];
+      if (dim == 0) continue;
+      /* W = sum over active pyramid rows of D c c^T, c = e0 +- mu e_a */
+      const float* u = s + L.cu + 6 * k;
+      const float D = prm[0];
+      float W00 = 0.0f, W0a[6] = {0, 0, 0, 0, 0, 0}, Waa[6] = {0, 0, 0, 0, 0, 0};
+      int anyact = 0;
+      if (dim == 1) { if (u[0] < 0.0f) { W00 = D; anyact = 1; } }
+      else for (int a = 1; a < dim; a++) {
+        const float mu = rg_contact_mu(r, a);
+        if (u[0] + mu * u[a] < 0.0f) { W00 += D; W0a[a] += D * mu; Waa[a] += D * mu * mu; anyact = 1; }
+        if (u[0] - mu * u[a] < 0.0f) { W00 += D; W0a[a] -= D * mu; Waa[a] += D * mu * mu; anyact = 1; }
+      }
+      if (!anyact) continue;
+      /* tile: columns of Jc for the dofs this contact touches, and W Jc */
+      const int b1 = (int)r[18], b2 = (int)r[19];
+      int* tdof = (int*)(s + L.tileDof);
+      LANEVAR(int, cnt); LANEVAR(int, pos);
+      int nd = 0;
+      for (int base = 0; base < nv; base += 32) {
+        int tot;
+        RG_PHASE_BEGIN
+        const int d = base + lane;
+        LV(cnt) = (d < nv && rg_dof_in_body(m, b1, d) != rg_dof_in_body(m, b2, d)) ? 1 : 0;
+        RG_PHASE_END
+        RG_WARP_SCAN(cnt, pos, tot);
+        RG_PHASE_BEGIN
+        const int d = base + lane;
+        const int i = nd + LV(pos);
+        if (LV(cnt) && i < RG_TILE) {
+          float col[6] = {0, 0, 0, 0, 0, 0};
+          rg_contact_col(c, r, d, dim, col);
+          tdof[i] = d;
+          float* tj = s + L.tileJ + 6 * i;
+          float* tw = s + L.tileWJ + 6 * i;
+          float w0 = W00 * col[0];
+          for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
+          tj[0] = col[0]; tw[0] = w0;
+          for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
+        }
+        RG_PHASE_END
+        nd += tot;
+      }
+      if (nd > RG_TILE) nd = RG_TILE;
+      RG_PHASE_BEGIN
+      for (int p = lane; p < nd * nd; p += 32) {
+        const int i = p / nd, j = p - i * nd;
+        const float* tj = s + L.tileJ + 6 * i;
+        const float* tw = s + L.tileWJ + 6 * j;
+        float acc = 0.0f;
+        for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
+        s[L.H + tdof[i] * nv + tdof[j]] += acc;
+      }
+      RG_PHASE_END
+    }
+    /* envelope, factor, Newton direction */
+    RG_PHASE_BEGIN
+    for (int i = lane; i < nv; i += 32) {
+      int e = 0;
+      while (e < i && s[L.H + i * nv + e] == 0.0f) e++;
+      env[i] = e;
+    }
+    RG_PHASE_END
+    rg_cholesky(c, L.H, env);
+    rg_chol_solve(c, L.H, env, L.search, L.tmp);
+    /* line search along `search` */
+    rg_matvec_phase(c, L.Mv, L.search);
+    rg_J_mul_phase(c, L.search, L.el_jv, L.cw, nel, ncon, 0);
+    float q1, q2;
+    {
+      LANEVAR(float, p1); LANEVAR(float, p2);
+      RG_PHASE_BEGIN
+      float a = 0.0f, b = 0.0f;
+      for (int d = lane; d < nv; d += 32) { a += s[L.search + d] * (s[L.Ma + d] - s[L.smooth + d]); b += s[L.search + d] * s[L.Mv + d]; }
+      LV(p1) = a; LV(p2) = 0.5f * b;
+      RG_PHASE_END
+      q1 = RG_WARP_SUM(p1); q2 = RG_WARP_SUM(p2);
+    }
+    float alpha = 0.0f, lo = 0.0f, hi = -1.0f, g0 = 0.0f;
+    for (int ls = 0; ls < 12; ls++) {
+      LANEVAR(float, pg); LANEVAR(float, ph);
+      RG_PHASE_BEGIN
+      float g = 0.0f, h = 0.0f;
+      for (int e = lane; e < nel; e += 32) {
+        const float jv = s[L.el_jv + e], x = s[L.el_jar + e] + alpha * jv, D = s[L.el_D + e];
+        if ((el_i[e] & 3) == RG_EL_FLOSS) {
+          const float fl = s[L.el_floss + e], rf = s[L.el_R + e] * fl;
+          if (x <= -rf) g -= fl * jv;
+          else if (x >= rf) g += fl * jv;
+          else { g += D * x * jv; h += D * jv * jv; }
+        } else if (x < 0.0f) { g += D * x * jv; h += D * jv * jv; }
+      }
+      for (int k = lane; k < ncon; k += 32) {
+        const float* r = s + L.con + RG_CON_STRIDE * k;
+        const float* prm = s + L.cprm + 8 * k;
+        const float* u = s + L.cu + 6 * k;
+        const float* w = s + L.cw + 6 * k;
+        const int dim = (int)prm[1];
+        const float D = prm[0];
+        if (dim == 1) { const float x = u[0] + alpha * w[0]; if (x < 0.0f) { g += D * x * w[0]; h += D * w[0] * w[0]; } }
+        else for (int a = 1; a < dim; a++) {
+          const float mu = rg_contact_mu(r, a);
+          const float xp = u[0] + alpha * w[0] + mu * (u[a] + alpha * w[a]), vp = w[0] + mu * w[a];
+          const float xm = u[0] + alpha * w[0] - mu * (u[a] + alpha * w[a]), vm = w[0] - mu * w[a];
+          if (xp < 0.0f) { g += D * xp * vp; h += D * vp * vp; }
+          if (xm < 0.0f) { g += D * xm * vm; h += D * vm * vm; }
+        }
+      }
+      LV(pg) = g; LV(ph) = h;
+      RG_PHASE_END
+      const float g = RG_WARP_SUM(pg) + q1 + 2.0f * alpha * q2;
+      const float h = RG_WARP_SUM(ph) + 2.0f * q2;
+      if (ls == 0) { g0 = g; if (!(g0 < 0.0f)) break; }
+      else {
+        if (fabsf(g) <= 1e-6f * fabsf(g0)) break;
+        if (g < 0.0f) lo = alpha; else hi = alpha;
+        if (hi >= 0.0f && hi - lo <= 1e-7f * hi) break;
+      }
+      float a2 = alpha - g / fmaxf(h, 1e-30f);
+      if (hi >= 0.0f && (a2 <= lo || a2 >= hi)) a2 = 0.5f * (lo + hi);
+      alpha = a2;
+    }
+    if (!(alpha > 0.0f)) break;
+    /* take the step */
+    RG_PHASE_BEGIN
+    for (int d = lane; d < nv; d += 32) { s[L.qacc + d] += alpha * s[L.search + d]; s[L.Ma + d] += alpha * s[L.Mv + d]; }
+    for (int e = lane; e < nel; e += 32) s[L.el_jar + e] += alpha * s[L.el_jv + e];
+    for (int i = lane; i < 6 * ncon; i += 32) s[L.cu + i] += alpha * s[L.cw + i];
+    RG_PHASE_END
+    cost_con = rg_solver_update(c, nel, ncon);
+    float newcost;
+    {
+      LANEVAR(float, gp);
+      RG_PHASE_BEGIN
+      float a = 0.0f;
+      for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
+      LV(gp) = a;
+      RG_PHASE_END
+      newcost = RG_WARP_SUM(gp) + cost_con;
+    }
+    const float improvement = scale * (cost - newcost);
+    cost = newcost;
+    if (improvement < tol) { iter++; break; }
+  }
+  rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
+  RG_PHASE_BEGIN
+  for (int d = lane; d < nv; d += 32) s[L.warm + d] = s[L.qacc + d];
+  if (lane == 0) RG_SI(c, RG_S_NITER) = iter;
+  RG_PHASE_END
+}
+
+/* ---------------------------------------------------------------- S15 semi-implicit Euler */
+RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
+  RG_LANE_DECL
+  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const int nv = m.nv;
+  const float h = c.timestep;
+  int* env = (int*)(s + L.env);
+  /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
+  RG_PHASE_BEGIN
+  for (int i = lane; i < nv * nv; i += 32) s[L.H + i] = s[L.M + i];
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  for (int d = lane; d < nv; d += 32) {
+    s[L.H + d * nv + d] += h * m.dof_damping[d];
+    s[L.search + d] = s[L.smooth + d] + s[L.qfc + d];
+    env[d] = m.dof_treeroot[d];
+  }
+  RG_PHASE_END
+  rg_cholesky(c, L.H, env);
+  rg_chol_solve(c, L.H, env, L.search, L.tmp);
+  RG_PHASE_BEGIN
+  for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  for (int j = lane; j < m.njnt; j += 32) {
+    const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j], type = m.jnt_type[j];
+    if (type == RG_JNT_SLIDE || type == RG_JNT_HINGE) s[L.qpos + qa] += h * s[L.qvel + da];
+    else {
+      int qq = qa, dd = da;
+      if (type == RG_JNT_FREE) { for (int a = 0; a < 3; a++) s[L.qpos + qa + a] += h * s[L.qvel + da + a]; qq += 3; dd += 3; }
+      float w[3] = {s[L.qvel + dd], s[L.qvel + dd + 1], s[L.qvel + dd + 2]};
+      const float ang = sqrtf(rg_dot3(w, w)) * h;
+      if (ang > 1e-15f) {
+        rg_normalize3(w);
+        const float sn = sinf(0.5f * ang), cs = cosf(0.5f * ang);
+        const float dq[4] = {cs, w[0] * sn, w[1] * sn, w[2] * sn};
+        float q[4] = {s[L.qpos + qq], s[L.qpos + qq + 1], s[L.qpos + qq + 2], s[L.qpos + qq + 3]}, rq[4];
+        rg_quat_mul(rq, q, dq);
+        rg_quat_norm(rq);
+        for (int a = 0; a < 4; a++) s[L.qpos + qq + a] = rq[a];
+      }
+    }
+  }
+  RG_PHASE_END
+}

@@ -1,0 +1,156 @@
+/* rg_step.inl -- per-environment driver of the fused step and the scratch layout.
+ *
+ * rg_env_step() is what one warp does for one environment in one launch of rg_step():
+ *   load state -> nsub x { mj_step } -> optional mj_forward -> store state + derived outputs,
+ * i.e. SimulationInterface.step() = sim.step() + sim.forward()
+ * (robogym/mujoco/simulation_interface.py:176-189) for the whole batch in a single kernel.
+ */
+#pragma once
+#include "rg_sol.inl"
+
+/* Batched state: row-major [nenv][n] fp32 tensors owned by the caller (torch). */
+struct RgBatchIO {
+  int nenv;
+  float* qpos; float* qvel; float* ctrl; float* pid; float* warm; float* time;
+  const float* xfrc;        /* [nenv][nbody*6] or nullptr */
+  const float* timestep;    /* [nenv] per-env opt.timestep override or nullptr */
+  /* derived outputs (any may be nullptr) */
+  float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
+  float* contact;           /* [nenv][RG_NCON][4] = geom1, geom2, dist, dim */
+  int* ncon; int* warn;
+  float* dbg;               /* [nenv][rg_dbg_size] stage dump for the parity tests */
+};
+
+static inline int rg_dbg_size(const RgModel& m) {
+  return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv;
+}
+
+static inline int rg_imax(int a, int b) { return a > b ? a : b; }
+
+/* host: compute the per-warp scratch layout for a model */
+static inline RgLayout rg_make_layout(const RgModel& m) {
+  RgLayout L;
+  int o = 0;
+#define RG_ALLOC(field, n) do { L.field = o; o += ((n) + 3) & ~3; } while (0)
+  RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
+  RG_ALLOC(lpos, 3 * m.nbody); RG_ALLOC(lquat, 4 * m.nbody); RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
+  RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
+  RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nv * m.nv);
+  /* H aliases the smooth-dynamics temporaries */
+  const int h0 = o;
+  RG_ALLOC(Sdot, 6 * m.nv); RG_ALLOC(cvel, 6 * m.nbody); RG_ALLOC(cacc, 6 * m.nbody); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
+  L.H = h0;
+  o = h0 + rg_imax(o - h0, (m.nv * m.nv + 3) & ~3);
+  RG_ALLOC(bias, m.nv); RG_ALLOC(passive, m.nv); RG_ALLOC(qfa, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
+  RG_ALLOC(Ma, m.nv); RG_ALLOC(grad, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
+  RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
+  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJ, m.ntendon * m.nv); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
+  RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, 8 * RG_NCON);
+  RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_R, RG_NEL); RG_ALLOC(el_aref, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
+  RG_ALLOC(el_jar, RG_NEL); RG_ALLOC(el_jv, RG_NEL); RG_ALLOC(el_f, RG_NEL);
+  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(cand, 64); RG_ALLOC(scal, 8);
+  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv);
+#undef RG_ALLOC
+  L.total = o;
+  return L;
+}
+
+/* mj_forward: everything but the integrator */
+RG_DEV void rg_forward(RgCtx& c) {
+  rg_kinematics(c);
+  rg_massmatrix(c);
+  rg_bias(c);
+  rg_tendon(c);
+  rg_forces(c);
+  rg_collision(c);
+  rg_make_constraints(c);
+  rg_solve(c);
+}
+
+RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward) {
+  RG_LANE_DECL
+  RgCtx c = {m, L, s, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0]};
+  const int npid = 3 * m.nu;
+  /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
+  RG_PHASE_BEGIN
+  for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = io.qpos[(size_t)env * m.nq + i];
+  for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = io.qvel[(size_t)env * m.nv + i]; s[L.warm + i] = io.warm[(size_t)env * m.nv + i]; }
+  for (int i = lane; i < m.nu; i += 32) s[L.ctrl + i] = io.ctrl[(size_t)env * m.nu + i];
+  for (int i = lane; i < npid; i += 32) s[L.pid + i] = io.pid[(size_t)env * npid + i];
+  if (lane < 8) RG_SI(c, lane) = 0;
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  for (int j = lane; j < m.njnt; j += 32)
+    if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
+  RG_PHASE_END
+  for (int sub = 0; sub < nsub; sub++) {
+    rg_forward(c);
+    rg_euler(c);
+    /* mj_checkPos / mj_checkVel: reset on a bad state, like mj_step does */
+    LANEVAR(int, badl);
+    RG_PHASE_BEGIN
+    int bad = 0;
+    for (int i = lane; i < m.nq; i += 32) { const float v = s[L.qpos + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
+    for (int i = lane; i < m.nv; i += 32) { const float v = s[L.qvel + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
+    LV(badl) = bad;
+    RG_PHASE_END
+    if (RG_WARP_OR(badl)) {
+      RG_PHASE_BEGIN
+      for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = m.qpos0[i];
+      for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = 0.0f; s[L.warm + i] = 0.0f; }
+      for (int i = lane; i < npid; i += 32) s[L.pid + i] = 0.0f;
+      if (lane == 0) RG_SI(c, RG_S_WARN) |= RG_WARN_BAD_STATE;
+      RG_PHASE_END
+      RG_PHASE_BEGIN
+      for (int j = lane; j < m.njnt; j += 32)
+        if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
+      RG_PHASE_END
+    }
+  }
+  if (final_forward) rg_forward(c);
+  /* ---- store */
+  RG_PHASE_BEGIN
+  for (int j = lane; j < m.njnt; j += 32)
+    if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] += m.origin[a];
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  for (int i = lane; i < m.nq; i += 32) io.qpos[(size_t)env * m.nq + i] = s[L.qpos + i];
+  for (int i = lane; i < m.nv; i += 32) { io.qvel[(size_t)env * m.nv + i] = s[L.qvel + i]; io.warm[(size_t)env * m.nv + i] = s[L.warm + i]; }
+  for (int i = lane; i < npid; i += 32) io.pid[(size_t)env * npid + i] = s[L.pid + i];
+  if (lane == 0 && io.time) io.time[env] += c.timestep * (float)nsub;
+  if (io.site_xpos) for (int i = lane; i < 3 * m.nsite; i += 32) io.site_xpos[(size_t)env * 3 * m.nsite + i] = s[L.sxpos + i] + m.origin[i % 3];
+  if (io.body_xpos) for (int i = lane; i < 3 * m.nbody; i += 32) io.body_xpos[(size_t)env * 3 * m.nbody + i] = s[L.xpos + i] + m.origin[i % 3];
+  if (io.body_xquat) for (int i = lane; i < 4 * m.nbody; i += 32) io.body_xquat[(size_t)env * 4 * m.nbody + i] = s[L.xquat + i];
+  if (io.geom_xpos) for (int i = lane; i < 3 * m.ngeom; i += 32) io.geom_xpos[(size_t)env * 3 * m.ngeom + i] = s[L.gxpos + i] + m.origin[i % 3];
+  if (io.act_force) for (int i = lane; i < m.nu; i += 32) io.act_force[(size_t)env * m.nu + i] = s[L.aforce + i];
+  if (io.qacc) for (int i = lane; i < m.nv; i += 32) io.qacc[(size_t)env * m.nv + i] = s[L.qacc + i];
+  const int ncon = RG_SI(c, RG_S_NCON);
+  if (io.contact) for (int k = lane; k < RG_NCON; k += 32) {
+    float* o = io.contact + ((size_t)env * RG_NCON + k) * 4;
+    const float* r = s + L.con + RG_CON_STRIDE * k;
+    if (k < ncon) { o[0] = r[20]; o[1] = r[21]; o[2] = r[0]; o[3] = r[17]; } else { o[0] = o[1] = -1.0f; o[2] = 0.0f; o[3] = 0.0f; }
+  }
+  if (lane == 0) { if (io.ncon) io.ncon[env] = ncon; if (io.warn) io.warn[env] |= RG_SI(c, RG_S_WARN); }
+  if (io.dbg) {
+    float* g = io.dbg + (size_t)env * rg_dbg_size(m);
+    const int nv = m.nv;
+    int o = 0;
+    for (int i = lane; i < nv * nv; i += 32) g[o + i] = s[L.M + i];
+    o += nv * nv;
+    for (int i = lane; i < nv; i += 32) {
+      g[o + i] = s[L.bias + i]; g[o + nv + i] = s[L.passive + i]; g[o + 2 * nv + i] = s[L.qfa + i];
+      g[o + 3 * nv + i] = s[L.smooth + i]; g[o + 4 * nv + i] = s[L.qacc + i]; g[o + 5 * nv + i] = s[L.qfc + i];
+    }
+    o += 6 * nv;
+    for (int i = lane; i < m.ntendon; i += 32) g[o + i] = s[L.tlen + i];
+    o += m.ntendon;
+    for (int i = lane; i < m.nu; i += 32) { g[o + i] = s[L.alen + i]; g[o + m.nu + i] = s[L.aforce + i]; }
+    o += 2 * m.nu;
+    if (lane == 0) { g[o] = (float)ncon; g[o + 1] = (float)RG_SI(c, RG_S_NEL); g[o + 2] = (float)RG_SI(c, RG_S_NITER); g[o + 3] = (float)RG_SI(c, RG_S_WARN); }
+    o += 4;
+    for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
+    o += RG_NCON * RG_CON_STRIDE;
+    for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = s[L.tJ + i];
+  }
+  RG_PHASE_END
+}

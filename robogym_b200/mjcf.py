@@ -338,6 +338,7 @@ def compile_mjcf(xml_string, asset_loader=None):
     # ---- assets: meshes
     mesh_names, mesh_verts, mesh_faces, mesh_center = [], [], [], []
     mesh_props = []
+    used_meshes = {g.get("mesh") for wb in root.findall("worldbody") for g in wb.iter("geom") if g.get("mesh")}
     for asset in root.findall("asset"):
         for me in asset.findall("mesh"):
             a = defaults.resolve("mesh", me, None)
@@ -345,6 +346,8 @@ def compile_mjcf(xml_string, asset_loader=None):
             fname = a["file"]
             if name is None:
                 name = os.path.splitext(os.path.basename(fname))[0]
+            if name not in used_meshes:
+                continue  # unreferenced assets do not affect the physics; keep the blob small
             path = fname if os.path.isabs(fname) else os.path.join(meshdir, fname)
             if asset_loader is not None:
                 raw = asset_loader(path)

@@ -1,0 +1,62 @@
+/* rg_emu.cpp -- CPU EMULATION BUILD of the CUDA engine's device code.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles robogym_b200/csrc/rg_*.inl with -DRG_EMU: every warp phase becomes a loop over 32
+ * lanes (see rg_defs.h).  It lets the CPU-only test tier (`pytest -m "not gpu"`) check the
+ * kernel's fp32 logic against the fp64 oracle; it is not reachable from the package and the
+ * product path never falls back to it.
+ */
+#define RG_EMU 1
+#include "../../robogym_b200/csrc/rg_step.inl"
+#include "../../robogym_b200/csrc/rg_host.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; };
+
+extern "C" {
+
+void* rge_create(const void* blob, size_t len) {
+  RgeHandle* h = new RgeHandle();
+  std::string err;
+  if (!rg_host_load(blob, len, h->hm, err)) { fprintf(stderr, "rge_create: %s\n", err.c_str()); delete h; return nullptr; }
+  h->L = rg_make_layout(h->hm.view);
+  h->scratch.assign(h->L.total, 0.0f);
+  return h;
+}
+void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
+int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view); }
+int rge_scratch_floats(void* hv) { return ((RgeHandle*)hv)->L.total; }
+int rge_small_bytes(void* hv) { return (int)((RgeHandle*)hv)->hm.small_bytes; }
+/* writable pointer to a model array (float32/int32 copy) so tests can edit parameters */
+void* rge_model_field(void* hv, const char* name, int* count) {
+  RgeHandle* h = (RgeHandle*)hv;
+  RgModel& m = h->hm.view;
+#define RG_DIM(n) const int n = m.n; (void)n;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+#define RG_DIM(n)
+#define RG_I(n, c) if (!strcmp(name, #n)) { *count = (c); return (void*)m.n; }
+#define RG_F(n, c) if (!strcmp(name, #n)) { *count = (c); return (void*)m.n; }
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  return nullptr;
+}
+
+void rge_step(void* hv, int nenv, float* qpos, float* qvel, float* ctrl, float* pid, float* warm, float* time, const float* xfrc,
+              const float* timestep, float* site_xpos, float* body_xpos, float* body_xquat, float* geom_xpos, float* act_force, float* qacc,
+              float* contact, int* ncon, int* warn, float* dbg, int nsub, int final_forward) {
+  RgeHandle* h = (RgeHandle*)hv;
+  RgBatchIO io;
+  io.nenv = nenv; io.qpos = qpos; io.qvel = qvel; io.ctrl = ctrl; io.pid = pid; io.warm = warm; io.time = time; io.xfrc = xfrc;
+  io.timestep = timestep; io.site_xpos = site_xpos; io.body_xpos = body_xpos; io.body_xquat = body_xquat; io.geom_xpos = geom_xpos;
+  io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg;
+  for (int env = 0; env < nenv; env++) rg_env_step(h->hm.view, h->L, h->scratch.data(), io, env, nsub, final_forward);
+}
+}
