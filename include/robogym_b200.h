@@ -1,0 +1,92 @@
+/* robogym_b200.h -- C ABI of the B200-native batched step engine (librobogym_b200.so).
+ *
+ * This is the drop-in boundary for robogym's physics path.  Each entry point names the
+ * reference interface it replaces (paths relative to /root/reference/):
+ *
+ *   rg_model_load      <- mujoco_py.load_model_from_xml(xml) + MjSim(model, nsubsteps)
+ *                         (robogym/mujoco/mujoco_xml.py:249-260).  The MJCF itself is compiled on
+ *                         the host by robogym_b200.mjcf into the blob of include/rg_model_fields.h.
+ *   rg_model_set_field <- in-place edits of sim.model.<array> by randomizers / modifiers
+ *                         (robogym/wrappers/randomizations.py:84,139,188,302,589,643,713,745;
+ *                          robogym/envs/dactyl/common/mujoco_modifiers.py:95-101).
+ *   rg_batch_create/bind <- the mjData that MjSim owns (qpos, qvel, ctrl, userdata = PID state,
+ *                         qacc_warmstart, xfrc_applied, time), here one row per environment in
+ *                         caller-owned device tensors (torch) -- robogym reads/writes them through
+ *                         SimulationInterface.qpos/qvel/set_qpos/... (simulation_interface.py:127-172)
+ *                         and robot code writes sim.data.ctrl (robot/shadow_hand/mujoco/mujoco_shadow_hand.py:120-137).
+ *   rg_step            <- SimulationInterface.step(): sim.step() [nsubsteps x mj_step, with the
+ *                         mujoco-py PID callback enabled by cymj.set_pid_control,
+ *                         simulation_interface.py:86-88] followed by sim.forward()
+ *                         (robogym/mujoco/simulation_interface.py:176-189; robogym/robot_env.py:837).
+ *   rg_forward         <- SimulationInterface.forward() (simulation_interface.py:203-207).
+ *   rg_reset           <- SimulationInterface.reset() = mj_resetData (simulation_interface.py:191-195).
+ *
+ * Conventions: every function returns 0 on success or a negative code and sets a thread-local
+ * message readable with rg_last_error(); no exceptions or callbacks cross the ABI.  All device
+ * work is stream-ordered and asynchronous on the stream the caller passes (a cudaStream_t as
+ * void*); the library never synchronises and never allocates or frees the bound tensors.
+ * State layout: row-major [nenv][n] float32 (int32 for ncon/warn); one environment per row.
+ */
+#ifndef ROBOGYM_B200_H
+#define ROBOGYM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rg_model rg_model;
+typedef struct rg_batch rg_batch;
+
+/* bindable per-environment arrays (rg_batch_bind) */
+enum rg_field {
+  RG_QPOS = 0,       /* [nenv][nq]          in/out */
+  RG_QVEL = 1,       /* [nenv][nv]          in/out */
+  RG_CTRL = 2,       /* [nenv][nu]          in     */
+  RG_PID = 3,        /* [nenv][3*nu]        in/out : mujoco-py PID state (integral, last error, last derivative) */
+  RG_WARMSTART = 4,  /* [nenv][nv]          in/out : qacc_warmstart */
+  RG_TIME = 5,       /* [nenv]              in/out (optional) */
+  RG_XFRC = 6,       /* [nenv][nbody*6]     in     (optional) : data.xfrc_applied */
+  RG_TIMESTEP = 7,   /* [nenv]              in     (optional) : per-env opt.timestep override */
+  RG_SITE_XPOS = 8,  /* [nenv][nsite*3]     out    (optional) */
+  RG_BODY_XPOS = 9,  /* [nenv][nbody*3]     out    (optional) */
+  RG_BODY_XQUAT = 10,/* [nenv][nbody*4]     out    (optional) */
+  RG_GEOM_XPOS = 11, /* [nenv][ngeom*3]     out    (optional) */
+  RG_ACT_FORCE = 12, /* [nenv][nu]          out    (optional) */
+  RG_QACC = 13,      /* [nenv][nv]          out    (optional) */
+  RG_CONTACT = 14,   /* [nenv][RG_MAX_CONTACTS][4] out (optional): geom1, geom2, dist, condim */
+  RG_NCON = 15,      /* [nenv] int32        out    (optional) */
+  RG_WARN = 16,      /* [nenv] int32        in/out (optional): bit0 contact buffer full, bit1 row buffer full, bit2 bad state -> reset */
+  RG_DBG = 17,       /* [nenv][rg_dbg_size] out    (optional): stage dump used by the parity tests */
+  RG_NFIELDS = 18
+};
+#define RG_MAX_CONTACTS 32
+
+int rg_model_load(const void* blob, size_t len, int device, rg_model** out);
+void rg_model_destroy(rg_model* m);
+/* value of a dimension of rg_model_fields.h (nq, nv, nu, nbody, ...) or -1 */
+int rg_model_dim(const rg_model* m, const char* name);
+/* overwrite a model array (host float64 / int32 values, `count` elements) and re-upload it */
+int rg_model_set_field(rg_model* m, const char* name, const void* data, size_t count);
+/* floats per environment of the RG_DBG dump; bytes of shared memory per environment (one warp) */
+int rg_dbg_size(const rg_model* m);
+int rg_scratch_bytes(const rg_model* m);
+
+int rg_batch_create(const rg_model* m, int nenv, rg_batch** out);
+void rg_batch_destroy(rg_batch* b);
+int rg_batch_bind(rg_batch* b, int field, void* device_ptr);
+/* launch geometry actually used (for reporting): CTAs, warps per CTA, dynamic shared bytes */
+int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps_per_cta, int* smem_bytes);
+
+/* nsub x mj_step, then (final_forward != 0) one mj_forward; derived outputs written once at the end */
+int rg_step(rg_batch* b, int nsub, int final_forward, void* stream);
+int rg_forward(rg_batch* b, void* stream);
+/* mj_resetData for the environments whose mask byte is non-zero (mask == NULL: all) */
+int rg_reset(rg_batch* b, const uint8_t* mask_device, void* stream);
+
+const char* rg_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

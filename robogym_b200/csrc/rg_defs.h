@@ -46,8 +46,8 @@
 
 #define RG_MINVAL 1e-15f
 #define RG_EPS 1.1920929e-07f
-#define RG_NCON 48       /* contacts kept per environment (reference nconmax=100, assets.xml:6) */
-#define RG_NEL 128       /* single-row constraint elements (friction loss + limits) */
+#define RG_NCON 32       /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
+#define RG_NEL 64        /* single-row constraint elements (friction loss + limits) */
 #define RG_CON_STRIDE 32
 #define RG_TILE 24       /* max dofs touched by one contact */
 

@@ -1,0 +1,296 @@
+/* rg_engine.cu -- sm_100a kernels + C ABI (include/robogym_b200.h) of the batched step engine.
+ *
+ * One persistent CTA per SM; each WARP owns one environment at a time and runs the whole fused
+ * SimulationInterface.step() for it (robogym/mujoco/simulation_interface.py:176-189): state row
+ * -> shared-memory scratch -> nsub x (kinematics, CRB mass matrix, RNE bias, tendons, PID,
+ * collision, constraint rows, Newton solve, Euler) -> final forward -> state row + outputs.
+ * The small per-model constant arrays are staged once per CTA into shared memory with a single
+ * TMA bulk copy (cp.async.bulk + mbarrier); hull vertices / adjacency / pair list stay in global
+ * memory behind the read-only path.  No tensor cores: nothing here is a dense contraction.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/robogym_b200.h"
+#include "rg_step.inl"
+#include "rg_host.h"
+
+#define RG_MAX_WARPS 8
+
+static thread_local std::string g_err;
+static int rg_fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define RG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return rg_fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct RgKernelArgs {
+  RgModel m;          /* pointers into the device arena */
+  RgLayout L;
+  RgBatchIO io;
+  const char* arena;  /* device arena base (16B aligned) */
+  int nsub, final_forward, warps;
+};
+
+__device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __grid_constant__ RgKernelArgs args) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  /* shared layout: [RgModel (rebased)] [small arena] [warps x scratch] */
+  RgModel* sm = (RgModel*)smem_raw;
+  const int model_bytes = (int)((sizeof(RgModel) + 127) & ~(size_t)127);
+  unsigned char* sarena = smem_raw + model_bytes;
+  const int small_bytes = args.m.small_bytes;
+  float* scratch0 = (float*)(sarena + ((small_bytes + 127) & ~127));
+
+  /* ---- stage the small model arrays with one TMA bulk copy */
+  if (threadIdx.x == 0) {
+    const uint32_t bar = rg_smem_u32(&mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)small_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rg_smem_u32(sarena)), "l"(args.arena), "r"((uint32_t)small_bytes), "r"(bar) : "memory");
+  }
+  /* meanwhile: rebased model view in shared memory (pointers into the staged copy where possible) */
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    if (lane == 0) *sm = args.m;
+    __syncwarp();
+    int k = 0;
+    const char* abase = args.arena;
+#define RG_REBASE(field) { if (lane == (k & 31)) { const char* p_ = (const char*)args.m.field; const size_t off_ = (size_t)(p_ - abase); \
+      if (off_ < (size_t)small_bytes) *(const void**)&sm->field = (const void*)(sarena + off_); } k++; }
+#define RG_DIM(n)
+#define RG_I(n, c) RG_REBASE(n)
+#define RG_F(n, c) RG_REBASE(n)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+    RG_REBASE(body_subtreesize)
+    RG_REBASE(dof_treeroot)
+#undef RG_REBASE
+  }
+  __syncthreads();
+  {
+    const uint32_t bar = rg_smem_u32(&mbar);
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+  }
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5;
+  if (warp >= args.warps) return;
+  float* s = scratch0 + (size_t)warp * args.L.total;
+  const RgModel& m = *sm;
+  for (int env = blockIdx.x * args.warps + warp; env < args.io.nenv; env += gridDim.x * args.warps)
+    rg_env_step(m, args.L, s, args.io, env, args.nsub, args.final_forward);
+}
+
+__global__ void rg_reset_kernel(RgModel m, RgBatchIO io, const uint8_t* mask) {
+  const int env = blockIdx.x;
+  if (env >= io.nenv || (mask && !mask[env])) return;
+  for (int i = threadIdx.x; i < m.nq; i += blockDim.x) io.qpos[(size_t)env * m.nq + i] = m.qpos0[i];
+  for (int i = threadIdx.x; i < m.nv; i += blockDim.x) { io.qvel[(size_t)env * m.nv + i] = 0.0f; io.warm[(size_t)env * m.nv + i] = 0.0f; }
+  for (int i = threadIdx.x; i < m.nu; i += blockDim.x) io.ctrl[(size_t)env * m.nu + i] = 0.0f;
+  for (int i = threadIdx.x; i < 3 * m.nu; i += blockDim.x) io.pid[(size_t)env * 3 * m.nu + i] = 0.0f;
+  if (threadIdx.x == 0) { if (io.time) io.time[env] = 0.0f; if (io.warn) io.warn[env] = 0; }
+}
+
+/* ------------------------------------------------------------------ host objects */
+struct rg_model {
+  RgHostModel hm;
+  RgModel dev;          /* same view with device pointers */
+  char* d_arena = nullptr;
+  int device = 0;
+  RgLayout L;
+  std::vector<std::string> names;
+  std::vector<size_t> src_counts;
+};
+struct rg_batch {
+  const rg_model* model;
+  int nenv;
+  void* ptr[RG_NFIELDS];
+  int ctas, warps, smem;
+};
+
+static void rg_wire_device_view(rg_model* mm) {
+  mm->dev = mm->hm.view;
+  const char* hbase = mm->hm.arena.data();
+#define RG_DEVPTR(field) *(const void**)&mm->dev.field = (const void*)(mm->d_arena + ((const char*)mm->hm.view.field - hbase));
+#define RG_DIM(n)
+#define RG_I(n, c) RG_DEVPTR(n)
+#define RG_F(n, c) RG_DEVPTR(n)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  RG_DEVPTR(body_subtreesize)
+  RG_DEVPTR(dof_treeroot)
+#undef RG_DEVPTR
+}
+
+extern "C" {
+
+const char* rg_last_error(void) { return g_err.c_str(); }
+
+int rg_model_load(const void* blob, size_t len, int device, rg_model** out) {
+  if (!blob || !out) return rg_fail(-1, "rg_model_load: null argument");
+  rg_model* mm = new rg_model();
+  std::string err;
+  if (!rg_host_load(blob, len, mm->hm, err)) { delete mm; return rg_fail(-1, "rg_model_load: " + err); }
+  mm->device = device;
+  mm->L = rg_make_layout(mm->hm.view);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&mm->d_arena, mm->hm.arena.size());
+  if (e == cudaSuccess) e = cudaMemcpy(mm->d_arena, mm->hm.arena.data(), mm->hm.arena.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { std::string msg = std::string("rg_model_load: CUDA: ") + cudaGetErrorString(e); delete mm; return rg_fail(-2, msg); }
+  rg_wire_device_view(mm);
+  *out = mm;
+  return 0;
+}
+
+void rg_model_destroy(rg_model* m) {
+  if (!m) return;
+  if (m->d_arena) cudaFree(m->d_arena);
+  delete m;
+}
+
+int rg_model_dim(const rg_model* m, const char* name) {
+  if (!m || !name) return -1;
+#define RG_DIM(n) if (!strcmp(name, #n)) return m->hm.view.n;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  return -1;
+}
+
+int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t count) {
+  if (!mm || !name || !data) return rg_fail(-1, "rg_model_set_field: null argument");
+  RgModel& m = mm->hm.view;
+#define RG_DIM(n) const int n = m.n; (void)n;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  void* hptr = nullptr;
+  size_t n = 0;
+  int isint = 0;
+#define RG_DIM(n)
+#define RG_I(f, c) if (!strcmp(name, #f)) { hptr = (void*)m.f; n = (size_t)(c); isint = 1; }
+#define RG_F(f, c) if (!strcmp(name, #f)) { hptr = (void*)m.f; n = (size_t)(c); isint = 0; }
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  if (!hptr) return rg_fail(-1, std::string("rg_model_set_field: unknown field ") + name);
+  if (n != count) return rg_fail(-1, std::string("rg_model_set_field: size mismatch for ") + name);
+  if (isint) memcpy(hptr, data, 4 * n);
+  else {
+    const double* s = (const double*)data;
+    float* d = (float*)hptr;
+    for (size_t i = 0; i < n; i++) d[i] = (float)s[i];
+    if (!strcmp(name, "body_pos")) /* keep the fp32 world shift */
+      for (int b = 1; b < m.nbody; b++)
+        if (m.body_parentid[b] == 0) for (int a = 0; a < 3; a++) d[3 * b + a] = (float)(s[3 * b + a] - (double)m.origin[a]);
+  }
+  const size_t off = (const char*)hptr - mm->hm.arena.data();
+  RG_CUDA(cudaSetDevice(mm->device));
+  RG_CUDA(cudaMemcpy(mm->d_arena + off, hptr, 4 * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int rg_dbg_size(const rg_model* m) { return m ? ::rg_dbg_size(m->hm.view) : -1; }
+int rg_scratch_bytes(const rg_model* m) { return m ? 4 * m->L.total : -1; }
+
+int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
+  if (!m || !out || nenv <= 0) return rg_fail(-1, "rg_batch_create: bad argument");
+  rg_batch* b = new rg_batch();
+  b->model = m;
+  b->nenv = nenv;
+  for (int i = 0; i < RG_NFIELDS; i++) b->ptr[i] = nullptr;
+  RG_CUDA(cudaSetDevice(m->device));
+  int sms = 0, maxsmem = 0;
+  RG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
+  RG_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+  const int model_bytes = (int)((sizeof(RgModel) + 127) & ~(size_t)127);
+  const int fixed = model_bytes + (int)((m->hm.small_bytes + 127) & ~(size_t)127) + 64;
+  const int per_warp = 4 * m->L.total;
+  int warps = (maxsmem - fixed) / per_warp;
+  if (warps < 1) { delete b; return rg_fail(-3, "rg_batch_create: model scratch does not fit in shared memory"); }
+  if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
+  const char* wenv = getenv("RG_WARPS_PER_CTA");
+  if (wenv && atoi(wenv) > 0 && atoi(wenv) < warps) warps = atoi(wenv);
+  b->warps = warps;
+  b->smem = fixed - 64 + warps * per_warp;
+  int ctas = (nenv + warps - 1) / warps;
+  if (ctas > sms) ctas = sms;
+  b->ctas = ctas;
+  RG_CUDA(cudaFuncSetAttribute(rg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem));
+  *out = b;
+  return 0;
+}
+void rg_batch_destroy(rg_batch* b) { delete b; }
+
+int rg_batch_bind(rg_batch* b, int field, void* p) {
+  if (!b || field < 0 || field >= RG_NFIELDS) return rg_fail(-1, "rg_batch_bind: bad argument");
+  b->ptr[field] = p;
+  return 0;
+}
+int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
+  if (!b) return -1;
+  if (ctas) *ctas = b->ctas;
+  if (warps) *warps = b->warps;
+  if (smem) *smem = b->smem;
+  return 0;
+}
+
+static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
+  for (int f = RG_QPOS; f <= RG_WARMSTART; f++)
+    if (!b->ptr[f]) return rg_fail(-1, "rg_step: qpos, qvel, ctrl, pid and warmstart must be bound");
+  io.nenv = b->nenv;
+  io.qpos = (float*)b->ptr[RG_QPOS]; io.qvel = (float*)b->ptr[RG_QVEL]; io.ctrl = (float*)b->ptr[RG_CTRL];
+  io.pid = (float*)b->ptr[RG_PID]; io.warm = (float*)b->ptr[RG_WARMSTART]; io.time = (float*)b->ptr[RG_TIME];
+  io.xfrc = (const float*)b->ptr[RG_XFRC]; io.timestep = (const float*)b->ptr[RG_TIMESTEP];
+  io.site_xpos = (float*)b->ptr[RG_SITE_XPOS]; io.body_xpos = (float*)b->ptr[RG_BODY_XPOS]; io.body_xquat = (float*)b->ptr[RG_BODY_XQUAT];
+  io.geom_xpos = (float*)b->ptr[RG_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_QACC];
+  io.contact = (float*)b->ptr[RG_CONTACT]; io.ncon = (int*)b->ptr[RG_NCON]; io.warn = (int*)b->ptr[RG_WARN]; io.dbg = (float*)b->ptr[RG_DBG];
+  return 0;
+}
+
+int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
+  if (!b || nsub < 0) return rg_fail(-1, "rg_step: bad argument");
+  RgKernelArgs args;
+  const int rc = rg_fill_io(b, args.io);
+  if (rc) return rc;
+  args.m = b->model->dev;
+  args.L = b->model->L;
+  args.arena = b->model->d_arena;
+  args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
+  RG_CUDA(cudaSetDevice(b->model->device));
+  rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
+  RG_CUDA(cudaGetLastError());
+  return 0;
+}
+int rg_forward(rg_batch* b, void* stream) { return rg_step(b, 0, 1, stream); }
+
+int rg_reset(rg_batch* b, const uint8_t* mask, void* stream) {
+  if (!b) return rg_fail(-1, "rg_reset: bad argument");
+  RgBatchIO io;
+  const int rc = rg_fill_io(b, io);
+  if (rc) return rc;
+  RG_CUDA(cudaSetDevice(b->model->device));
+  rg_reset_kernel<<<b->nenv, 64, 0, (cudaStream_t)stream>>>(b->model->dev, io, mask);
+  RG_CUDA(cudaGetLastError());
+  return 0;
+}
+}

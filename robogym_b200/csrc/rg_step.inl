@@ -21,7 +21,12 @@ struct RgBatchIO {
   float* dbg;               /* [nenv][rg_dbg_size] stage dump for the parity tests */
 };
 
-static inline int rg_dbg_size(const RgModel& m) {
+#ifdef RG_EMU
+#define RG_HD static inline
+#else
+#define RG_HD __host__ __device__ static inline
+#endif
+RG_HD int rg_dbg_size(const RgModel& m) {
   return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv;
 }
 

@@ -1,0 +1,208 @@
+"""Python binding of the C ABI (include/robogym_b200.h) + the batched simulation object.
+
+`BatchedSim` is the batched counterpart of `robogym.mujoco.simulation_interface.SimulationInterface`
+(robogym/mujoco/simulation_interface.py:25-250): `step()` = `sim.step()` (nsubsteps x mj_step)
++ `sim.forward()`, `forward()`, `reset()`, `qpos`/`qvel`/`ctrl` accessors -- for `nenv`
+independent environments whose state lives in torch CUDA tensors ([nenv, n], float32).
+
+There is NO CPU fallback: without the compiled CUDA library or without a GPU the constructors
+raise.  (The fp64 CPU oracle under oracle/ is test infrastructure and is never imported here.)
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import modelblob
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librobogym_b200.so")
+
+# enum rg_field (include/robogym_b200.h)
+(QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,
+ ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG) = range(18)
+MAX_CONTACTS = 32
+CON_STRIDE = 32
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load librobogym_b200.so (built in-tree by `python -m robogym_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} is missing: build it with `python -m robogym_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci = ctypes.c_void_p, ctypes.c_int
+        L.rg_last_error.restype = ctypes.c_char_p
+        L.rg_model_load.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ci, ctypes.POINTER(vp)]
+        L.rg_model_destroy.argtypes = [vp]
+        L.rg_model_dim.argtypes = [vp, ctypes.c_char_p]
+        L.rg_model_set_field.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
+        L.rg_dbg_size.argtypes = [vp]
+        L.rg_scratch_bytes.argtypes = [vp]
+        L.rg_batch_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
+        L.rg_batch_destroy.argtypes = [vp]
+        L.rg_batch_bind.argtypes = [vp, ci, vp]
+        L.rg_batch_launch_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.rg_step.argtypes = [vp, ci, ci, vp]
+        L.rg_forward.argtypes = [vp, vp]
+        L.rg_reset.argtypes = [vp, vp, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EngineError(lib().rg_last_error().decode())
+
+
+class DeviceModel:
+    """A compiled model uploaded to one GPU (rg_model)."""
+
+    def __init__(self, blob, device=0):
+        self.blob = bytes(blob)
+        self.host = modelblob.unpack(self.blob)  # float64 host copy, source of truth for edits
+        self.device = int(device)
+        h = ctypes.c_void_p()
+        _check(lib().rg_model_load(self.blob, len(self.blob), self.device, ctypes.byref(h)))
+        self.h = h
+
+    def dim(self, name):
+        return self.host[name]
+
+    def set_field(self, name, values):
+        """Overwrite a model array (randomisers write e.g. geom_friction, dof_damping, opt_gravity)."""
+        arr = self.host[name]
+        arr[...] = np.asarray(values, dtype=arr.dtype).reshape(arr.shape)
+        buf = np.ascontiguousarray(arr)
+        _check(lib().rg_model_set_field(self.h, name.encode(), buf.ctypes.data, buf.size))
+
+    @property
+    def dbg_size(self):
+        return lib().rg_dbg_size(self.h)
+
+    @property
+    def scratch_bytes(self):
+        return lib().rg_scratch_bytes(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and _lib is not None:
+            _lib.rg_model_destroy(self.h)
+            self.h = None
+
+
+class BatchedSim:
+    """nenv independent copies of one model, stepped by one fused kernel launch per env-step."""
+
+    def __init__(self, model, nenv, n_substeps=10, outputs=("site_xpos", "act_force", "ncon", "warn"), debug=False):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise EngineError("BatchedSim needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.model = model
+        self.nenv = int(nenv)
+        self.n_substeps = int(n_substeps)
+        self.device = torch.device("cuda", model.device)
+        m = model.host
+        f32 = dict(dtype=torch.float32, device=self.device)
+        i32 = dict(dtype=torch.int32, device=self.device)
+        n = self.nenv
+        self.qpos = torch.tensor(m["qpos0"], **f32).repeat(n, 1).contiguous()
+        self.qvel = torch.zeros(n, m["nv"], **f32)
+        self.ctrl = torch.zeros(n, m["nu"], **f32)
+        self.pid = torch.zeros(n, 3 * m["nu"], **f32)
+        self.qacc_warmstart = torch.zeros(n, m["nv"], **f32)
+        self.time = torch.zeros(n, **f32)
+        h = ctypes.c_void_p()
+        _check(lib().rg_batch_create(model.h, n, ctypes.byref(h)))
+        self.h = h
+        self._bound = {}
+        for fid, t in ((QPOS, self.qpos), (QVEL, self.qvel), (CTRL, self.ctrl), (PID, self.pid),
+                       (WARMSTART, self.qacc_warmstart), (TIME, self.time)):
+            self._bind(fid, t)
+        shapes = dict(site_xpos=(SITE_XPOS, (n, m["nsite"], 3), f32), body_xpos=(BODY_XPOS, (n, m["nbody"], 3), f32),
+                      body_xquat=(BODY_XQUAT, (n, m["nbody"], 4), f32), geom_xpos=(GEOM_XPOS, (n, m["ngeom"], 3), f32),
+                      act_force=(ACT_FORCE, (n, m["nu"]), f32), qacc=(QACC, (n, m["nv"]), f32),
+                      contact=(CONTACT, (n, MAX_CONTACTS, 4), f32), ncon=(NCON, (n,), i32), warn=(WARN, (n,), i32))
+        for name in outputs:
+            fid, shape, kw = shapes[name]
+            t = torch.zeros(*shape, **kw)
+            setattr(self, name, t)
+            self._bind(fid, t)
+        self.dbg = None
+        if debug:
+            self.dbg = torch.zeros(n, model.dbg_size, **f32)
+            self._bind(DBG, self.dbg)
+        self.xfrc_applied = None
+        self.timestep = None
+
+    def _bind(self, fid, t):
+        assert t.is_contiguous()
+        self._bound[fid] = t  # keep alive
+        _check(lib().rg_batch_bind(self.h, fid, ctypes.c_void_p(t.data_ptr())))
+
+    def enable_xfrc(self):
+        m = self.model.host
+        self.xfrc_applied = self.torch.zeros(self.nenv, m["nbody"], 6, dtype=self.torch.float32, device=self.device)
+        self._bind(XFRC, self.xfrc_applied)
+        return self.xfrc_applied
+
+    def enable_per_env_timestep(self):
+        self.timestep = self.torch.full((self.nenv,), float(self.model.host["opt_timestep"][0]), dtype=self.torch.float32, device=self.device)
+        self._bind(TIMESTEP, self.timestep)
+        return self.timestep
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def step(self, n_substeps=None, final_forward=True):
+        """SimulationInterface.step(): nsubsteps x mj_step then mj_forward, for every environment."""
+        _check(lib().rg_step(self.h, self.n_substeps if n_substeps is None else int(n_substeps), int(bool(final_forward)), self._stream()))
+
+    def forward(self):
+        _check(lib().rg_forward(self.h, self._stream()))
+
+    def reset(self, mask=None):
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            mp = ctypes.c_void_p(mask.data_ptr())
+        _check(lib().rg_reset(self.h, mp, self._stream()))
+
+    def launch_info(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib().rg_batch_launch_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return dict(ctas=a.value, warps_per_cta=b.value, smem_bytes=c.value)
+
+    def dbg_view(self, env=0):
+        """Decode the stage dump of one environment (tests)."""
+        m = self.model.host
+        nv, nt, nu = m["nv"], m["ntendon"], m["nu"]
+        g = self.dbg[env].cpu().numpy()
+        o = 0
+        out = {}
+        out["M"] = g[o:o + nv * nv].reshape(nv, nv); o += nv * nv
+        for k in ("bias", "passive", "qfa", "smooth", "qacc", "qfc"):
+            out[k] = g[o:o + nv]; o += nv
+        out["tlen"] = g[o:o + nt]; o += nt
+        out["alen"] = g[o:o + nu]; o += nu
+        out["aforce"] = g[o:o + nu]; o += nu
+        out["ncon"], out["nel"], out["niter"], out["warn"] = [int(x) for x in g[o:o + 4]]; o += 4
+        out["con"] = g[o:o + MAX_CONTACTS * CON_STRIDE].reshape(MAX_CONTACTS, CON_STRIDE); o += MAX_CONTACTS * CON_STRIDE
+        out["tJ"] = g[o:o + nt * nv].reshape(nt, nv)
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and _lib is not None:
+            _lib.rg_batch_destroy(self.h)
+            self.h = None

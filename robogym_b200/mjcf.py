@@ -1226,10 +1226,9 @@ def set_const(m, spatial_tendon_eval=None):
         biw[b, 1] = max(np.trace(Ar) / 3.0, MINVAL)
     # tendons (fixed ones here; spatial through the callback)
     if m["ntendon"]:
-        if spatial_tendon_eval is not None:
-            L, Jt = spatial_tendon_eval(m["qpos0"])
-        else:
-            L, Jt = None, None
+        if spatial_tendon_eval is None:
+            spatial_tendon_eval = lambda q: tendon_eval(m, q)
+        L, Jt = spatial_tendon_eval(m["qpos0"])
         for i in range(m["ntendon"]):
             lf = tendon_length_fixed(m, m["qpos0"], i)
             if lf is not None:
@@ -1251,3 +1250,144 @@ def set_const(m, spatial_tendon_eval=None):
             q1c = quat_conj(xquat[b1])
             d[:3] = rot_vec(q1c, xpos[b2] - xpos[b1])
             d[3:7] = quat_mul(q1c, xquat[b2])
+
+
+# ----------------------------------------------------------------------------------------------
+# spatial tendons at compile time (mj_setConst needs tendon_length0 / tendon_invweight0):
+# numpy restatement of the site -> sphere/cylinder wrap -> site path geometry.
+def _seg_intersect(p1, p2, p3, p4):
+    det = (p4[1] - p3[1]) * (p2[0] - p1[0]) - (p4[0] - p3[0]) * (p2[1] - p1[1])
+    if abs(det) < MINVAL:
+        return False
+    a = ((p4[0] - p3[0]) * (p1[1] - p3[1]) - (p4[1] - p3[1]) * (p1[0] - p3[0])) / det
+    b = ((p2[0] - p1[0]) * (p1[1] - p3[1]) - (p2[1] - p1[1]) * (p1[0] - p3[0])) / det
+    return 0 <= a <= 1 and 0 <= b <= 1
+
+
+def _wrap_circle(d0, d1, sd, rad):
+    sq0, sq1, sqr = d0 @ d0, d1 @ d1, rad * rad
+    dif = d1 - d0
+    dd = dif @ dif
+    if sq0 < sqr or sq1 < sqr or rad < MINVAL or dd < MINVAL:
+        return None
+    a = min(max(-(dif @ d0) / dd, 0.0), 1.0)
+    tmp = a * dif + d0
+    if tmp @ tmp > sqr and (sd is None or tmp @ sd >= 0):
+        return None
+    s0, s1 = np.sqrt(sq0 - sqr), np.sqrt(sq1 - sqr)
+    sols, good = [], []
+    for sgn in (1.0, -1.0):
+        a0 = np.array([(d0[0] * sqr + sgn * rad * d0[1] * s0) / sq0, (d0[1] * sqr - sgn * rad * d0[0] * s0) / sq0])
+        a1 = np.array([(d1[0] * sqr - sgn * rad * d1[1] * s1) / sq1, (d1[1] * sqr + sgn * rad * d1[0] * s1) / sq1])
+        if sd is not None:
+            t = a0 + a1
+            g = (t @ sd) / max(np.linalg.norm(t), MINVAL)
+        else:
+            t = a0 - a1
+            g = -(t @ t)
+        if _seg_intersect(d0, a0, d1, a1):
+            g = -10000.0
+        sols.append((a0, a1))
+        good.append(g)
+    a0, a1 = sols[0] if good[0] > good[1] else sols[1]
+    if _seg_intersect(d0, a0, d1, a1):
+        return None
+    return rad * np.arccos(np.clip((a0 @ a1) / sqr, -1, 1)), a0, a1
+
+
+def _wrap_geom(x0, x1, gpos, gmat, rad, wtype, side):
+    p0, p1 = gmat.T @ (x0 - gpos), gmat.T @ (x1 - gpos)
+    if np.linalg.norm(p0) < MINVAL or np.linalg.norm(p1) < MINVAL:
+        return None
+    if wtype == WRAP_SPHERE:
+        ax0 = p0 / np.linalg.norm(p0)
+        nrm = np.cross(p0, p1)
+        if np.linalg.norm(nrm) < MINVAL:
+            e = np.array([0.0, 1, 0]) if abs(ax0[0]) > 0.9 else np.array([1.0, 0, 0])
+            nrm = np.cross(ax0, e)
+        nrm /= np.linalg.norm(nrm)
+        ax1 = np.cross(nrm, ax0)
+        ax1 /= np.linalg.norm(ax1)
+    else:
+        ax0, ax1 = np.array([1.0, 0, 0]), np.array([0.0, 1, 0])
+    d0 = np.array([p0 @ ax0, p0 @ ax1])
+    d1 = np.array([p1 @ ax0, p1 @ ax1])
+    sd = None
+    if side is not None:
+        sl = gmat.T @ (side - gpos)
+        sd = np.array([sl @ ax0, sl @ ax1])
+        n = np.linalg.norm(sd)
+        if n < rad:
+            raise NotImplementedError("inside tendon wrap (sidesite inside the wrap geom)")
+        sd = sd / n
+    res = _wrap_circle(d0, d1, sd, rad)
+    if res is None:
+        return None
+    wlen, a0, a1 = res
+    r0 = ax0 * a0[0] + ax1 * a0[1]
+    r1 = ax0 * a1[0] + ax1 * a1[1]
+    if wtype == WRAP_CYLINDER:
+        L0, L1 = np.linalg.norm(d0 - a0), np.linalg.norm(d1 - a1)
+        tot = L0 + wlen + L1
+        r0[2] = p0[2] + (p1[2] - p0[2]) * L0 / tot
+        r1[2] = p0[2] + (p1[2] - p0[2]) * (L0 + wlen) / tot
+        wlen = np.hypot(wlen, r1[2] - r0[2])
+    return wlen, gmat @ r0 + gpos, gmat @ r1 + gpos
+
+
+def tendon_eval(m, qpos):
+    """Lengths and dense Jacobians of all tendons at qpos (fixed + spatial)."""
+    nv, nt = m["nv"], m["ntendon"]
+    xpos, xquat, jaxis, janchor = kinematics(m, qpos)
+    site_x = [xpos[b] + rot_vec(xquat[b], p) for b, p in zip(m["site_bodyid"], m["site_pos"].reshape(-1, 3))]
+    L = np.zeros(nt)
+    J = np.zeros((nt, nv))
+
+    def seg(t, ba, pa, bb, pb, scale):
+        d = pb - pa
+        n = np.linalg.norm(d)
+        d = d / max(n, MINVAL)
+        if ba != bb:
+            ja, _ = body_jacobian(m, xpos, xquat, jaxis, janchor, ba, pa)
+            jb, _ = body_jacobian(m, xpos, xquat, jaxis, janchor, bb, pb)
+            J[t] += scale * (d @ (jb - ja))
+        return n * scale
+
+    for t in range(nt):
+        adr, num = m["tendon_adr"][t], m["tendon_num"][t]
+        if m["wrap_type"][adr] == WRAP_JOINT:
+            for w in range(adr, adr + num):
+                j = m["wrap_objid"][w]
+                L[t] += m["wrap_prm"][w] * qpos[m["jnt_qposadr"][j]]
+                J[t, m["jnt_dofadr"][j]] += m["wrap_prm"][w]
+            continue
+        divisor, w = 1.0, adr
+        while w < adr + num - 1:
+            t0, t1 = m["wrap_type"][w], m["wrap_type"][w + 1]
+            if t0 == WRAP_PULLEY:
+                divisor = m["wrap_prm"][w]
+                w += 1
+                continue
+            if t1 == WRAP_PULLEY:
+                w += 1
+                continue
+            s0 = m["wrap_objid"][w]
+            b0 = m["site_bodyid"][s0]
+            if t1 == WRAP_SITE:
+                s1 = m["wrap_objid"][w + 1]
+                L[t] += seg(t, b0, site_x[s0], m["site_bodyid"][s1], site_x[s1], 1 / divisor)
+                w += 1
+            else:
+                g, s1, sid = m["wrap_objid"][w + 1], m["wrap_objid"][w + 2], int(m["wrap_prm"][w + 1])
+                b1, bg = m["site_bodyid"][s1], m["geom_bodyid"][g]
+                gq = quat_normalize(quat_mul(xquat[bg], m["geom_quat"].reshape(-1, 4)[g]))
+                gpos = xpos[bg] + rot_vec(xquat[bg], m["geom_pos"].reshape(-1, 3)[g])
+                res = _wrap_geom(site_x[s0], site_x[s1], gpos, quat2mat(gq), m["geom_size"].reshape(-1, 3)[g, 0], t1,
+                                 site_x[sid] if sid >= 0 else None)
+                if res is None:
+                    L[t] += seg(t, b0, site_x[s0], b1, site_x[s1], 1 / divisor)
+                else:
+                    wlen, w0, w1 = res
+                    L[t] += seg(t, b0, site_x[s0], bg, w0, 1 / divisor) + wlen / divisor + seg(t, bg, w1, b1, site_x[s1], 1 / divisor)
+                w += 2
+    return L, J

@@ -7,7 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "librg_emu.so")
-NCON = 48
+NCON = 32
 CON_STRIDE = 32
 _lib = None
 

@@ -1,0 +1,40 @@
+"""Compile the reference's MJCF models into committed model blobs (robogym_b200/assets/*.rgm).
+
+Runs in the build container only: it needs /root/reference for the XML + STL assets and composes the
+documents with the reference's own MujocoXML (tools/compose_reference_xml.py).  The GPU box has no
+/root/reference, so bench.py / the gpu tests load these blobs.  A blob holds derived data only
+(frames, inertias, convex-hull vertices and adjacency, collision pair list, constants of
+mj_setConst); no reference source text.
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+import compose_reference_xml as ref  # noqa: E402
+from robogym_b200 import mjcf  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "robogym_b200", "assets")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in (("dactyl_locked", ref.locked_xml), ("dactyl_reach", ref.reach_xml)):
+        try:
+            xml = fn()
+        except Exception as e:  # reach needs extra assets
+            print(f"skip {name}: {e}")
+            continue
+        cm = mjcf.compile_mjcf(xml)
+        cm.m["opt_pid"][0] = 1  # the dactyl sims call enable_pid() right after build (cube_env.py:157-160)
+        with open(os.path.join(OUT, name + ".rgm"), "wb") as f:
+            f.write(cm.blob())
+        with open(os.path.join(OUT, name + ".names.json"), "w") as f:
+            json.dump(cm.names, f)
+        print(name, {k: cm.m[k] for k in ("nq", "nv", "nu", "nbody", "ngeom", "npair", "nmeshvert")}, len(cm.blob()), "bytes")
+
+
+if __name__ == "__main__":
+    main()
