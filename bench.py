@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the dactyl/locked step path at batch 8192 per GPU (BASELINE.json).
+
+One "step" = one SimulationInterface.step() for every environment of the batch
+(robogym/mujoco/simulation_interface.py:176-189: 10 x mj_step + mj_forward), i.e. one launch of
+the fused rg_step kernel per rank.  `value` = whole-job env-steps/s with inputs resident in HBM;
+`e2e` = the same through the public API (robogym_b200.engine.BatchedSim) with HOST buffers: pinned
+ctrl -> device, step, qpos/qvel -> pinned host, every step, inside the timed region.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 20 --warmup 3
+    python bench.py --impl reference        # the CPU port of the reference path on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NENV_PER_GPU = 8192
+NSUB = 10
+ALGO_BYTES_PER_ENV_STEP = 1664       # 784 B read + 680 B written + ~200 B derived outputs
+ACTION_SCALE = 0.3                   # relative random actions: ctrl += a * 0.3 * half-range, a ~ U(-1, 1)
+METRIC = "env-steps/sec dactyl/locked batch 8192 @1/2/4/8 B200 vs CPU mujoco-py"
+
+
+# ---------------------------------------------------------------- host logic shared with tests/test_dist.py
+def shard_range(total, rank, world):
+    per = total // world
+    return rank * per, (rank + 1) * per
+
+
+def rank_seed(seed, rank):
+    return seed * 1000003 + rank
+
+
+def max_over_ranks(x, dist, device):
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, dist, device):
+    import torch
+
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    if dist is not None and dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def load_blob():
+    with open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.rgm"), "rb") as f:
+        return f.read()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+# ---------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------- CPU arm (oracle port of the reference path)
+def _cpu_worker(args):
+    blob, seed, n_steps = args
+    import numpy as np
+
+    from oracle import pyoracle
+
+    om = pyoracle.OracleModel(blob)
+    d = pyoracle.OracleData(om)
+    cr = om.field("actuator_ctrlrange").reshape(-1, 2)
+    rng = np.random.RandomState(seed)
+    d.ctrl[:] = cr.mean(1)
+    for _ in range(5):
+        d.env_step(NSUB)
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        a = rng.uniform(-1, 1, len(cr))
+        d.ctrl[:] = np.clip(d.ctrl + ACTION_SCALE * a * (cr[:, 1] - cr[:, 0]) / 2, cr[:, 0], cr[:, 1])
+        d.env_step(NSUB)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(blob, seconds=10.0):
+    """Single-thread timing of the fp64 CPU port on a bounded sample (about `seconds` of CPU work)."""
+    from oracle import pyoracle
+
+    pyoracle.build()
+    probe = _cpu_worker((blob, 1, 20))
+    n = max(20, int(seconds / (probe / 20)))
+    t = _cpu_worker((blob, 2, n))
+    return {"value": n / t, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n} env-steps (x{NSUB} substeps) of one dactyl/locked env, relative random actions, fp64 CPU port (oracle/)"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on all host cores.  mujoco-py 2.0.2.13 is
+    not installable here (no network, closed binary), so this times the fp64 CPU port under oracle/."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import pyoracle
+
+    pyoracle.build()
+    blob = load_blob()
+    cores = os.cpu_count() or 1
+    per_step = 8                      # env-steps per worker per bench "step" (bounded sample)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, [(blob, 100 + w, per_step) for w in range(cores)])
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            pool.map(_cpu_worker, [(blob, 1000 * k + w, per_step) for w in range(cores)])
+        dt = time.perf_counter() - t0
+    value = cores * per_step * args.steps / dt
+    sample = f"each step = {cores} worker processes x {per_step} env-steps of one env (fp64 CPU port, settle excluded from the metric but inside the timing)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "dactyl/locked, ShadowHand + locked cube, 10 substeps of 0.008 s per env-step, relative random actions"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+
+    from robogym_b200 import build, engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    build.build()
+    blob = load_blob()
+    model = engine.DeviceModel(blob, local)
+    N = NENV_PER_GPU                                  # weak scaling: 8192 envs per GPU
+    lo_env, hi_env = shard_range(N * world, rank, world)
+    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"))
+    m = model.host
+    nu, nq, nv = m["nu"], m["nq"], m["nv"]
+    cr = torch.tensor(m["actuator_ctrlrange"].reshape(-1, 2), dtype=torch.float32, device=dev)
+    lo, hi = cr[:, 0].contiguous(), cr[:, 1].contiguous()
+    half = 0.5 * (hi - lo)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(rank_seed(1234, rank))
+
+    def new_ctrl(cur):
+        a = torch.rand(N, nu, device=dev, generator=gen) * 2 - 1
+        return torch.minimum(torch.maximum(cur + ACTION_SCALE * a * half, lo), hi)
+
+    # setup (untimed): settle 20 env-steps at mid-range targets, then perturb the cube pose per env
+    sim.ctrl.copy_((0.5 * (lo + hi)).repeat(N, 1))
+    for _ in range(20):
+        sim.step()
+    sim.qpos[:, 0:3] += 0.005 * torch.randn(N, 3, device=dev, generator=gen)
+    quat = torch.randn(N, 4, device=dev, generator=gen)
+    sim.qpos[:, 3:7] = quat / quat.norm(dim=1, keepdim=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+    for _ in range(max(args.warmup, 3)):
+        sim.ctrl.copy_(new_ctrl(sim.ctrl))
+        sim.step()
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: device-resident (kernel) throughput
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for k in range(args.steps):
+        nxt = new_ctrl(sim.ctrl)
+        flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
+        sim.ctrl.copy_(nxt)
+        ev[k][0].record()
+        sim.step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_dev = max_over_ranks(sum(step_ms) / 1e3, dist, dev)
+    total_steps = sum_over_ranks(float(N * args.steps), dist, dev)
+    value = total_steps / t_dev
+    on_palm = float((sim.site_xpos[:, model_site(model, "cube:center"), 2] > 0.04).float().mean().item())
+    warn = int(sim.warn.max().item())
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    h_ctrl = torch.empty(N, nu, dtype=torch.float32).pin_memory()
+    h_q = torch.empty(N, nq, dtype=torch.float32).pin_memory()
+    h_v = torch.empty(N, nv, dtype=torch.float32).pin_memory()
+    h_ctrl.copy_(sim.ctrl)
+    rng = np.random.RandomState(rank_seed(99, rank) % (2 ** 31))
+    lo_h, hi_h, half_h = lo.cpu().numpy(), hi.cpu().numpy(), half.cpu().numpy()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acts = [(rng.uniform(-1, 1, (N, nu)).astype(np.float32)) for _ in range(args.steps)]
+    e0.record()
+    for k in range(args.steps):
+        np.clip(h_ctrl.numpy() + ACTION_SCALE * acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
+        sim.ctrl.copy_(h_ctrl, non_blocking=True)       # H2D of this step's inputs
+        sim.step()
+        h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
+        h_v.copy_(sim.qvel, non_blocking=True)
+        torch.cuda.synchronize()                        # the host consumes the observation every step
+    e1.record()
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(e0.elapsed_time(e1) / 1e3, dist, dev)
+    e2e_value = total_steps / t_e2e
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        kernel_s = statistics.mean(step_ms) / 1e3
+        achieved = ALGO_BYTES_PER_ENV_STEP * N / kernel_s / 1e9
+        info = sim.launch_info()
+        line = {
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "dactyl/locked (BASELINE.json configs[1]): ShadowHand + locked cube, nq38/nv36/nu20, batch 8192 per GPU, "
+                                   "10 substeps of 0.008 s + forward per env-step, relative random actions (ctrl += 0.3*a*half-range)",
+                       "envs_per_gpu": N, "substeps": NSUB, "physics_substeps_per_s": value * NSUB,
+                       "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
+                       "launch": info, "cubes_on_palm_at_end": on_palm, "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
+            "gpu_launches": args.steps * world,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                         "note": "algorithmic 1664 B/env-step; the path is FP32-issue/latency bound, not HBM bound (DESIGN.md)"},
+        }
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(blob, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def model_site(model, name):
+    import json as _json
+
+    names = _json.load(open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.names.json")))
+    return names["site"].index(name)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,24 +40,24 @@ typedef struct rg_batch rg_batch;
 
 /* bindable per-environment arrays (rg_batch_bind) */
 enum rg_field {
-  RG_QPOS = 0,       /* [nenv][nq]          in/out */
-  RG_QVEL = 1,       /* [nenv][nv]          in/out */
-  RG_CTRL = 2,       /* [nenv][nu]          in     */
-  RG_PID = 3,        /* [nenv][3*nu]        in/out : mujoco-py PID state (integral, last error, last derivative) */
-  RG_WARMSTART = 4,  /* [nenv][nv]          in/out : qacc_warmstart */
-  RG_TIME = 5,       /* [nenv]              in/out (optional) */
-  RG_XFRC = 6,       /* [nenv][nbody*6]     in     (optional) : data.xfrc_applied */
-  RG_TIMESTEP = 7,   /* [nenv]              in     (optional) : per-env opt.timestep override */
-  RG_SITE_XPOS = 8,  /* [nenv][nsite*3]     out    (optional) */
-  RG_BODY_XPOS = 9,  /* [nenv][nbody*3]     out    (optional) */
-  RG_BODY_XQUAT = 10,/* [nenv][nbody*4]     out    (optional) */
-  RG_GEOM_XPOS = 11, /* [nenv][ngeom*3]     out    (optional) */
-  RG_ACT_FORCE = 12, /* [nenv][nu]          out    (optional) */
-  RG_QACC = 13,      /* [nenv][nv]          out    (optional) */
-  RG_CONTACT = 14,   /* [nenv][RG_MAX_CONTACTS][4] out (optional): geom1, geom2, dist, condim */
-  RG_NCON = 15,      /* [nenv] int32        out    (optional) */
-  RG_WARN = 16,      /* [nenv] int32        in/out (optional): bit0 contact buffer full, bit1 row buffer full, bit2 bad state -> reset */
-  RG_DBG = 17,       /* [nenv][rg_dbg_size] out    (optional): stage dump used by the parity tests */
+  RG_FIELD_QPOS = 0,       /* [nenv][nq]          in/out */
+  RG_FIELD_QVEL = 1,       /* [nenv][nv]          in/out */
+  RG_FIELD_CTRL = 2,       /* [nenv][nu]          in     */
+  RG_FIELD_PID = 3,        /* [nenv][3*nu]        in/out : mujoco-py PID state (integral, last error, last derivative) */
+  RG_FIELD_WARMSTART = 4,  /* [nenv][nv]          in/out : qacc_warmstart */
+  RG_FIELD_TIME = 5,       /* [nenv]              in/out (optional) */
+  RG_FIELD_XFRC = 6,       /* [nenv][nbody*6]     in     (optional) : data.xfrc_applied */
+  RG_FIELD_TIMESTEP = 7,   /* [nenv]              in     (optional) : per-env opt.timestep override */
+  RG_FIELD_SITE_XPOS = 8,  /* [nenv][nsite*3]     out    (optional) */
+  RG_FIELD_BODY_XPOS = 9,  /* [nenv][nbody*3]     out    (optional) */
+  RG_FIELD_BODY_XQUAT = 10,/* [nenv][nbody*4]     out    (optional) */
+  RG_FIELD_GEOM_XPOS = 11, /* [nenv][ngeom*3]     out    (optional) */
+  RG_FIELD_ACT_FORCE = 12, /* [nenv][nu]          out    (optional) */
+  RG_FIELD_QACC = 13,      /* [nenv][nv]          out    (optional) */
+  RG_FIELD_CONTACT = 14,   /* [nenv][RG_MAX_CONTACTS][4] out (optional): geom1, geom2, dist, condim */
+  RG_FIELD_NCON = 15,      /* [nenv] int32        out    (optional) */
+  RG_FIELD_WARN = 16,      /* [nenv] int32        in/out (optional): bit0 contact buffer full, bit1 row buffer full, bit2 bad state -> reset */
+  RG_FIELD_DBG = 17,       /* [nenv][rg_dbg_size] out    (optional): stage dump used by the parity tests */
   RG_NFIELDS = 18
 };
 #define RG_MAX_CONTACTS 32
@@ -68,7 +68,7 @@ void rg_model_destroy(rg_model* m);
 int rg_model_dim(const rg_model* m, const char* name);
 /* overwrite a model array (host float64 / int32 values, `count` elements) and re-upload it */
 int rg_model_set_field(rg_model* m, const char* name, const void* data, size_t count);
-/* floats per environment of the RG_DBG dump; bytes of shared memory per environment (one warp) */
+/* floats per environment of the RG_FIELD_DBG dump; bytes of shared memory per environment (one warp) */
 int rg_dbg_size(const rg_model* m);
 int rg_scratch_bytes(const rg_model* m);
 

@@ -24,5 +24,16 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_profile():
+    """Same engine with per-stage clock64 counters in the RG_DBG dump (profiling only)."""
+    out = os.path.join(HERE, "librobogym_b200_prof.so")
+    cmd = nvcc_cmd(("-DRG_PROFILE",))
+    cmd[cmd.index("-o") + 1] = out
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--profile" in sys.argv:
+        print(build_profile())

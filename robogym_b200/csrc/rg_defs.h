@@ -49,6 +49,7 @@
 #define RG_NCON 32       /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
 #define RG_NEL 64        /* single-row constraint elements (friction loss + limits) */
 #define RG_CON_STRIDE 32
+#define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds) */
 #define RG_TILE 24       /* max dofs touched by one contact */
 
 enum { RG_JNT_FREE = 0, RG_JNT_BALL = 1, RG_JNT_SLIDE = 2, RG_JNT_HINGE = 3 };

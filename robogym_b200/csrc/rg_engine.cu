@@ -255,15 +255,15 @@ int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
 }
 
 static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
-  for (int f = RG_QPOS; f <= RG_WARMSTART; f++)
+  for (int f = RG_FIELD_QPOS; f <= RG_FIELD_WARMSTART; f++)
     if (!b->ptr[f]) return rg_fail(-1, "rg_step: qpos, qvel, ctrl, pid and warmstart must be bound");
   io.nenv = b->nenv;
-  io.qpos = (float*)b->ptr[RG_QPOS]; io.qvel = (float*)b->ptr[RG_QVEL]; io.ctrl = (float*)b->ptr[RG_CTRL];
-  io.pid = (float*)b->ptr[RG_PID]; io.warm = (float*)b->ptr[RG_WARMSTART]; io.time = (float*)b->ptr[RG_TIME];
-  io.xfrc = (const float*)b->ptr[RG_XFRC]; io.timestep = (const float*)b->ptr[RG_TIMESTEP];
-  io.site_xpos = (float*)b->ptr[RG_SITE_XPOS]; io.body_xpos = (float*)b->ptr[RG_BODY_XPOS]; io.body_xquat = (float*)b->ptr[RG_BODY_XQUAT];
-  io.geom_xpos = (float*)b->ptr[RG_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_QACC];
-  io.contact = (float*)b->ptr[RG_CONTACT]; io.ncon = (int*)b->ptr[RG_NCON]; io.warn = (int*)b->ptr[RG_WARN]; io.dbg = (float*)b->ptr[RG_DBG];
+  io.qpos = (float*)b->ptr[RG_FIELD_QPOS]; io.qvel = (float*)b->ptr[RG_FIELD_QVEL]; io.ctrl = (float*)b->ptr[RG_FIELD_CTRL];
+  io.pid = (float*)b->ptr[RG_FIELD_PID]; io.warm = (float*)b->ptr[RG_FIELD_WARMSTART]; io.time = (float*)b->ptr[RG_FIELD_TIME];
+  io.xfrc = (const float*)b->ptr[RG_FIELD_XFRC]; io.timestep = (const float*)b->ptr[RG_FIELD_TIMESTEP];
+  io.site_xpos = (float*)b->ptr[RG_FIELD_SITE_XPOS]; io.body_xpos = (float*)b->ptr[RG_FIELD_BODY_XPOS]; io.body_xquat = (float*)b->ptr[RG_FIELD_BODY_XQUAT];
+  io.geom_xpos = (float*)b->ptr[RG_FIELD_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_FIELD_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_FIELD_QACC];
+  io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;
 }
 

@@ -27,7 +27,7 @@ struct RgBatchIO {
 #define RG_HD __host__ __device__ static inline
 #endif
 RG_HD int rg_dbg_size(const RgModel& m) {
-  return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv;
+  return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv + RG_NPROF;
 }
 
 static inline int rg_imax(int a, int b) { return a > b ? a : b; }
@@ -53,7 +53,7 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
   RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, 8 * RG_NCON);
   RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_R, RG_NEL); RG_ALLOC(el_aref, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
   RG_ALLOC(el_jar, RG_NEL); RG_ALLOC(el_jv, RG_NEL); RG_ALLOC(el_f, RG_NEL);
-  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(cand, 64); RG_ALLOC(scal, 8);
+  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(cand, 64); RG_ALLOC(scal, 8 + RG_NPROF);
   RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv);
 #undef RG_ALLOC
   L.total = o;
@@ -61,15 +61,24 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
 }
 
 /* mj_forward: everything but the integrator */
+/* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
+#if !defined(RG_EMU) && defined(RG_PROFILE)
+#define RG_PROF_BEGIN long long prof_t_ = clock64();
+#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) (c).s[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
+#else
+#define RG_PROF_BEGIN
+#define RG_PROF(c, k)
+#endif
 RG_DEV void rg_forward(RgCtx& c) {
-  rg_kinematics(c);
-  rg_massmatrix(c);
-  rg_bias(c);
-  rg_tendon(c);
-  rg_forces(c);
-  rg_collision(c);
-  rg_make_constraints(c);
-  rg_solve(c);
+  RG_PROF_BEGIN
+  rg_kinematics(c); RG_PROF(c, 0)
+  rg_massmatrix(c); RG_PROF(c, 1)
+  rg_bias(c); RG_PROF(c, 2)
+  rg_tendon(c); RG_PROF(c, 3)
+  rg_forces(c); RG_PROF(c, 4)
+  rg_collision(c); RG_PROF(c, 5)
+  rg_make_constraints(c); RG_PROF(c, 6)
+  rg_solve(c); RG_PROF(c, 7)
 }
 
 RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward) {
@@ -82,7 +91,7 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
   for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = io.qvel[(size_t)env * m.nv + i]; s[L.warm + i] = io.warm[(size_t)env * m.nv + i]; }
   for (int i = lane; i < m.nu; i += 32) s[L.ctrl + i] = io.ctrl[(size_t)env * m.nu + i];
   for (int i = lane; i < npid; i += 32) s[L.pid + i] = io.pid[(size_t)env * npid + i];
-  if (lane < 8) RG_SI(c, lane) = 0;
+  if (lane < 8 + RG_NPROF) RG_SI(c, lane) = 0;
   RG_PHASE_END
   RG_PHASE_BEGIN
   for (int j = lane; j < m.njnt; j += 32)
@@ -90,7 +99,7 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
   RG_PHASE_END
   for (int sub = 0; sub < nsub; sub++) {
     rg_forward(c);
-    rg_euler(c);
+    { RG_PROF_BEGIN rg_euler(c); RG_PROF(c, 8) }
     /* mj_checkPos / mj_checkVel: reset on a bad state, like mj_step does */
     LANEVAR(int, badl);
     RG_PHASE_BEGIN
@@ -156,6 +165,8 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
     for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
     o += RG_NCON * RG_CON_STRIDE;
     for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = s[L.tJ + i];
+    o += m.ntendon * nv;
+    for (int i = lane; i < RG_NPROF; i += 32) g[o + i] = s[L.scal + 8 + i];
   }
   RG_PHASE_END
 }

@@ -16,7 +16,7 @@ import numpy as np
 from . import modelblob
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librobogym_b200.so")
+LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librobogym_b200.so"))  # RG_LIB: e.g. the -DRG_PROFILE build
 
 # enum rg_field (include/robogym_b200.h)
 (QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,

@@ -1,0 +1,43 @@
+"""The C-ABI library exports every symbol include/robogym_b200.h declares (no compute calls, no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "robogym_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rg_[a-z_]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    fns = declared_functions()
+    for f in ("rg_model_load", "rg_batch_create", "rg_batch_bind", "rg_step", "rg_forward", "rg_reset", "rg_last_error"):
+        assert f in fns
+
+
+def test_library_exports_every_declared_symbol():
+    from robogym_b200 import build
+
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    for f in declared_functions():
+        assert hasattr(lib, f), f"{f} declared in robogym_b200.h but not exported"
+    lib.rg_last_error.restype = ctypes.c_char_p
+    assert lib.rg_last_error() is not None
+
+
+def test_product_path_fails_loudly_without_gpu(locked_blob):
+    """No CPU fallback: on a box without CUDA the engine raises instead of routing elsewhere."""
+    import torch
+
+    from robogym_b200 import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(engine.EngineError):
+        engine.DeviceModel(locked_blob, 0)

@@ -1,0 +1,160 @@
+"""Parity tests proper (run on the B200 box with -m gpu): the CUDA path, called through the C ABI
+(robogym_b200.engine -> librobogym_b200.so), against the fp64 oracle on identical seeded states,
+plus size-independent properties at BASELINE.json's full batch (8192)."""
+import numpy as np
+import pytest
+
+from helpers import live_indices, oracle_pair, rollout_states, step_errors
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(locked_blob):
+    import torch
+
+    from robogym_b200 import build, engine
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    build.build()
+    model = engine.DeviceModel(locked_blob, 0)
+    return torch, engine, model
+
+
+@pytest.fixture(scope="module")
+def states(locked_blob):
+    return rollout_states(locked_blob, 48, seed=11)
+
+
+def put(torch, sim, sts):
+    f = lambda i: torch.tensor(np.stack([s[i] for s in sts]), dtype=torch.float32, device=sim.device)
+    sim.qpos.copy_(f(0)); sim.qvel.copy_(f(1)); sim.ctrl.copy_(f(2)); sim.pid.copy_(f(3)); sim.qacc_warmstart.copy_(f(4))
+
+
+def test_native_library_is_loaded(gpu):
+    torch, engine, model = gpu
+    import ctypes
+
+    assert isinstance(engine.lib(), ctypes.CDLL) and engine.LIB_PATH.endswith(".so")
+    maps = open("/proc/self/maps").read()
+    assert "librobogym_b200" in maps
+
+
+def test_teacher_forced_env_step_vs_oracle(gpu, states, locked_names):
+    """10 x mj_step + forward from identical states.  Tolerances (fp32 vs fp64, contact-rich):
+    median |dq| < 2e-4 (rad / m), median |dv| < 5e-3, >= 70 % of states within 1e-3 in qpos."""
+    torch, engine, model = gpu
+    sts, after, om = states
+    sim = engine.BatchedSim(model, len(sts), 10, outputs=("site_xpos", "ncon", "warn"))
+    put(torch, sim, sts)
+    sim.step()
+    torch.cuda.synchronize()
+    iq, iv = live_indices(om, locked_names)
+    eq, ev = step_errors(sim.qpos.cpu().numpy(), sim.qvel.cpu().numpy(), after, iq, iv)
+    assert int(sim.warn.max()) == 0
+    assert np.median(eq) < 2e-4 and np.median(ev) < 5e-3
+    assert np.mean(eq < 1e-3) > 0.7
+    ncon = sim.ncon.cpu().numpy()
+    assert np.mean(ncon == np.array([a[2] for a in after])) > 0.7
+
+
+def test_stagewise_forward_vs_oracle(gpu, states, locked_blob):
+    torch, engine, model = gpu
+    sts, after, om = states
+    sub = sts[::8]
+    sim = engine.BatchedSim(model, len(sub), 10, outputs=("site_xpos", "act_force", "ncon", "warn"), debug=True)
+    put(torch, sim, sub)
+    sim.forward()
+    torch.cuda.synchronize()
+    _, d = oracle_pair(locked_blob)
+    rel = lambda a, b: np.abs(np.asarray(a, float) - b).max() / max(np.abs(b).max(), 1e-12)
+    for k, st in enumerate(sub):
+        d.qpos[:], d.qvel[:], d.ctrl[:] = st[0], st[1], st[2]
+        d.userdata[:60] = st[3]
+        d.qacc_warmstart[:] = st[4]
+        d.forward()
+        g = sim.dbg_view(k)
+        assert rel(sim.site_xpos[k].cpu().numpy().ravel(), d.site_xpos) < 1e-6
+        assert rel(g["M"].ravel(), d.M) < 1e-5
+        assert rel(g["tlen"], d.ten_length) < 1e-6
+        assert rel(g["bias"], d.qfrc_bias) < 1e-4
+        assert rel(g["smooth"], d.qfrc_smooth) < 1e-4
+        assert rel(sim.act_force[k].cpu().numpy(), d.actuator_force) < 1e-4
+        assert g["ncon"] == d.ncon[0]
+
+
+def test_free_running_hand_only(gpu, locked_blob, locked_names):
+    """T2 of SURVEY 8(d): 200 substeps free-running with the cube parked away from the hand
+    (no contact-mode switches): hand qpos within 1e-3 of the oracle."""
+    torch, engine, model = gpu
+    om, d = oracle_pair(locked_blob)
+    cr = om.field("actuator_ctrlrange").reshape(-1, 2)
+    sim = engine.BatchedSim(model, 4, 10, outputs=("warn",))
+    d.qpos[0] += 0.5
+    sim.qpos[:, 0] += 0.5
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        c = cr[:, 0] + (cr[:, 1] - cr[:, 0]) * rng.uniform(0.3, 0.7, len(cr))
+        d.ctrl[:] = c
+        sim.ctrl.copy_(torch.tensor(c, dtype=torch.float32, device=sim.device).repeat(4, 1))
+        d.env_step(10)
+        sim.step()
+    torch.cuda.synchronize()
+    q = sim.qpos.cpu().numpy()
+    hand = [om.field("jnt_qposadr")[j] for j, n in enumerate(locked_names["joint"]) if n.startswith("robot0:")]
+    assert np.abs(q[0][hand] - d.qpos[hand]).max() < 1e-3
+    assert np.array_equal(q[0], q[3])
+
+
+def test_full_batch_properties(gpu, states):
+    """BASELINE.json config[1] size (8192 envs): identical inputs -> bitwise identical outputs in every
+    slot (determinism / slot independence), no warnings, finite state, cubes stay on the palm."""
+    torch, engine, model = gpu
+    sts, after, om = states
+    N = 8192
+    sim = engine.BatchedSim(model, N, 10, outputs=("site_xpos", "ncon", "warn"))
+    small = engine.BatchedSim(model, len(sts), 10, outputs=("warn",))
+    put(torch, small, sts)
+    idx = torch.arange(N, device=sim.device) % len(sts)
+    for name in ("qpos", "qvel", "ctrl", "pid", "qacc_warmstart"):
+        getattr(sim, name).copy_(getattr(small, name)[idx])
+    for _ in range(3):
+        sim.step()
+        small.step()
+    torch.cuda.synchronize()
+    assert torch.equal(sim.qpos, small.qpos[idx]) and torch.equal(sim.qvel, small.qvel[idx])
+    assert torch.isfinite(sim.qpos).all() and torch.isfinite(sim.qvel).all()
+    assert int((sim.warn & 4).max()) == 0
+
+
+def test_reset_restores_qpos0(gpu):
+    torch, engine, model = gpu
+    sim = engine.BatchedSim(model, 16, 10, outputs=("warn",))
+    q0 = sim.qpos.clone()
+    sim.ctrl.fill_(0.1)
+    sim.step()
+    mask = torch.zeros(16, dtype=torch.uint8, device=sim.device)
+    mask[::2] = 1
+    sim.reset(mask)
+    torch.cuda.synchronize()
+    assert torch.equal(sim.qpos[::2], q0[::2]) and not torch.equal(sim.qpos[1::2], q0[1::2])
+    assert float(sim.qvel[::2].abs().max()) == 0.0 and float(sim.pid[::2].abs().max()) == 0.0
+
+
+def test_model_edit_changes_dynamics(gpu):
+    """Randomisers write model arrays in place (robogym/wrappers/randomizations.py:188): gravity here."""
+    torch, engine, model = gpu
+    sim = engine.BatchedSim(model, 2, 10, outputs=("warn",))
+    sim.step()
+    torch.cuda.synchronize()
+    z1 = float(sim.qpos[0, 9])      # free-falling target cube z
+    g0 = model.host["opt_gravity"].copy()
+    try:
+        model.set_field("opt_gravity", [0.0, 0.0, -1.0])
+        sim2 = engine.BatchedSim(model, 2, 10, outputs=("warn",))
+        sim2.step()
+        torch.cuda.synchronize()
+        z2 = float(sim2.qpos[0, 9])
+    finally:
+        model.set_field("opt_gravity", g0)
+    assert z1 < 0 and z2 < 0 and abs(z1 / z2 - 9.81) < 1e-3

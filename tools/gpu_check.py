@@ -68,3 +68,16 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
 print(json.dumps(dict(nenv=N, ms_per_env_step=ms, env_steps_per_s=N / ms * 1e3, launch=sim2.launch_info(), warn_max=int(sim2.warn.max().item()), ncon_mean=float(sim2.ncon.float().mean().item()))))
+
+# stage profile (only meaningful with RG_LIB=...librobogym_b200_prof.so)
+g = sim.dbg_view(0)
+print("dbg env0: ncon", g["ncon"], "nel", g["nel"], "niter", g["niter"])
+prof = sim.dbg.cpu().numpy()[:, -16:]
+names = ["kin", "massm", "bias", "tendon", "forces", "collide", "mkcon", "solve", "euler"]
+tot = prof[:, :9].sum(1).mean()
+print("stage cycles per env-step (mean over envs, lane0 clock64):")
+for i, nme in enumerate(names):
+    print("  %-8s %10.0f  %5.1f%%" % (nme, prof[:, i].mean(), 100 * prof[:, i].mean() / max(tot, 1)))
+print("  total %.0f cycles/env-step/warp" % tot)
+niters = np.array([sim.dbg_view(k)["niter"] for k in range(min(K, 32))])
+print("newton iters (final forward)", niters)
