@@ -120,6 +120,7 @@ RG_F(geom_size, ngeom * 3)
 RG_F(geom_pos, ngeom * 3)
 RG_F(geom_quat, ngeom * 4)
 RG_F(geom_rbound, ngeom)
+RG_F(geom_aabb, ngeom * 6)      /* geom-frame bounding box: centre[3], half extents[3] (OBB cull before the narrow phase) */
 RG_F(geom_friction, ngeom * 3)
 RG_F(geom_margin, ngeom)
 RG_F(geom_gap, ngeom)

@@ -9,10 +9,16 @@
 #pragma once
 #include "rg_dyn.inl"
 
+#if defined(RG_EMU) && defined(RG_STATS)
+static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_stat_mpr_hit = 0, rg_stat_narrow = 0, rg_stat_maxsup = 0, rg_stat_cur = 0;
+#define RG_STAT(x) x
+#else
+#define RG_STAT(x)
+#endif
 struct RgGeomView {
   float pos[3], mat[9], size[3];
-  int type, vadr, vnum;
-  int hint;
+  int type, vadr, vnum, mid;
+  int hint;              /* last support vertex (hill-climb warm start), -1 = pick an extreme vertex */
   float halfmargin;
 };
 
@@ -26,14 +32,15 @@ RG_DEV void rg_geom_view(const RgCtx& c, int g, float margin, RgGeomView& v) {
   rg_copy3(v.pos, c.s + c.L.gxpos + 3 * g);
   rg_copy3(v.size, m.geom_size + 3 * g);
   v.type = m.geom_type[g];
-  v.hint = 0;
+  v.hint = -1;
   v.halfmargin = 0.5f * margin;
-  v.vadr = 0; v.vnum = 0;
-  if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
+  v.vadr = 0; v.vnum = 0; v.mid = 0;
+  if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.mid = mid; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
 }
 
 RG_DEV void rg_support(const RgModel& m, RgGeomView& v, const float* dir, float* res) {
   float dl[3], loc[3] = {0, 0, 0};
+  RG_STAT(rg_stat_support++; rg_stat_cur++;)
   rg_mulmatT3(dl, v.mat, dir);
   switch (v.type) {
     case RG_GEOM_SPHERE: rg_scl3(loc, dl, v.size[0]); break;
@@ -57,24 +64,33 @@ RG_DEV void rg_support(const RgModel& m, RgGeomView& v, const float* dir, float*
       if (n > 1e-20f) { loc[0] = t[0] * v.size[0] / n; loc[1] = t[1] * v.size[1] / n; loc[2] = t[2] * v.size[2] / n; }
     } break;
     case RG_GEOM_MESH: {
-      /* steepest-ascent hill climb on the convex hull's edge graph */
+      /* steepest-ascent hill climb on the convex hull's edge graph; neighbour coordinates are stored
+         inline (mesh_nbr) so one step costs one dependent load level, not two */
       const float* vert = m.mesh_vert + 3 * v.vadr;
       const int* adjadr = m.mesh_adjadr + v.vadr;
       int cur = v.hint;
-      float best = RG_LDG(vert + 3 * cur) * dl[0] + RG_LDG(vert + 3 * cur + 1) * dl[1] + RG_LDG(vert + 3 * cur + 2) * dl[2];
+      if (cur < 0) {
+        const float ax = fabsf(dl[0]), ay = fabsf(dl[1]), az = fabsf(dl[2]);
+        const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+        cur = RG_LDG(m.mesh_ext + 6 * v.mid + 2 * axis + (dl[axis] >= 0 ? 0 : 1));
+      }
+      float bx = RG_LDG(vert + 3 * cur), by = RG_LDG(vert + 3 * cur + 1), bz = RG_LDG(vert + 3 * cur + 2);
+      float best = bx * dl[0] + by * dl[1] + bz * dl[2];
       for (int guard = 0; guard < v.vnum; guard++) {
         const int a0 = RG_LDG(adjadr + cur), a1 = RG_LDG(adjadr + cur + 1);
         int nxt = cur;
         for (int a = a0; a < a1; a++) {
-          const int nb = RG_LDG(m.mesh_adj + a);
-          const float dd = RG_LDG(vert + 3 * nb) * dl[0] + RG_LDG(vert + 3 * nb + 1) * dl[1] + RG_LDG(vert + 3 * nb + 2) * dl[2];
-          if (dd > best) { best = dd; nxt = nb; }
+          float n4[4];
+          RG_LDG4(m.mesh_nbr, a, n4);
+          const float dd = n4[0] * dl[0] + n4[1] * dl[1] + n4[2] * dl[2];
+          if (dd > best) { best = dd; nxt = rg_f2i(n4[3]); bx = n4[0]; by = n4[1]; bz = n4[2]; }
         }
         if (nxt == cur) break;
         cur = nxt;
+        RG_STAT(rg_stat_climb++;)
       }
       v.hint = cur;
-      loc[0] = RG_LDG(vert + 3 * cur); loc[1] = RG_LDG(vert + 3 * cur + 1); loc[2] = RG_LDG(vert + 3 * cur + 2);
+      loc[0] = bx; loc[1] = by; loc[2] = bz;
     } break;
     default: break;
   }
@@ -93,21 +109,27 @@ RG_DEV void rg_mpr_support(const RgModel& m, RgGeomView& o1, RgGeomView& o2, con
   rg_sub3(sp.v, sp.v1, sp.v2);
 }
 RG_DEV int rg_mpr_zero(float x) { return fabsf(x) < RG_EPS; }
-RG_DEV void rg_portal_dir(const RgSup* p, float* dir) {
-  float a[3], b[3];
-  rg_sub3(a, p[2].v, p[1].v); rg_sub3(b, p[3].v, p[1].v);
-  rg_cross(dir, a, b);
+/* ---- Minkowski Portal Refinement (XenoCollide), written as ONE loop around the support call:
+ * the portal lives in named registers (no indexed local arrays) and lanes that are in different
+ * stages of the algorithm (portal discovery / refinement / penetration) still execute the expensive
+ * support evaluation together -- only the cheap bookkeeping diverges.  The sequence of operations
+ * per pair is the textbook one (discover portal -> refine until the origin is inside -> push the
+ * portal to the surface), identical to the oracle's three-loop formulation. */
+RG_DEV void rg_portal_dir3(const RgSup& a, const RgSup& b, const RgSup& cc, float* dir) {
+  float u[3], w[3];
+  rg_sub3(u, b.v, a.v); rg_sub3(w, cc.v, a.v);
+  rg_cross(dir, u, w);
   rg_normalize3(dir);
 }
-RG_DEV void rg_expand_portal(RgSup* p, const RgSup& v4) {
+RG_DEV void rg_expand_portal3(RgSup& p1, RgSup& p2, RgSup& p3, const float* v0, const RgSup& v4) {
   float c4[3];
-  rg_cross(c4, v4.v, p[0].v);
-  if (rg_dot3(p[1].v, c4) > 0) { if (rg_dot3(p[2].v, c4) > 0) p[1] = v4; else p[3] = v4; }
-  else { if (rg_dot3(p[3].v, c4) > 0) p[2] = v4; else p[1] = v4; }
+  rg_cross(c4, v4.v, v0);
+  if (rg_dot3(p1.v, c4) > 0) { if (rg_dot3(p2.v, c4) > 0) p1 = v4; else p3 = v4; }
+  else { if (rg_dot3(p3.v, c4) > 0) p2 = v4; else p1 = v4; }
 }
-RG_DEV int rg_reach_tol(const RgSup* p, const RgSup& v4, const float* dir, float tol) {
+RG_DEV int rg_reach_tol3(const RgSup& p1, const RgSup& p2, const RgSup& p3, const RgSup& v4, const float* dir, float tol) {
   const float dv4 = rg_dot3(v4.v, dir);
-  const float mn = fminf(fminf(dv4 - rg_dot3(p[1].v, dir), dv4 - rg_dot3(p[2].v, dir)), dv4 - rg_dot3(p[3].v, dir));
+  const float mn = fminf(fminf(dv4 - rg_dot3(p1.v, dir), dv4 - rg_dot3(p2.v, dir)), dv4 - rg_dot3(p3.v, dir));
   return mn <= tol || rg_mpr_zero(mn - tol);
 }
 /* closest point of triangle abc to the origin */
@@ -135,95 +157,103 @@ RG_DEV float rg_tri_closest(const float* a, const float* b, const float* cc, flo
   rg_copy3(w, a); rg_addscl3(w, ab, vb * den); rg_addscl3(w, ac, vc * den);
   return rg_dot3(w, w);
 }
-RG_DEV void rg_find_pos(const RgSup* p, float* pos) {
+RG_DEV void rg_find_pos3(const float* v0, const float* c1, const float* c2, const RgSup& p1, const RgSup& p2, const RgSup& p3, float* pos) {
   float dir[3], b[4], t[3];
-  rg_portal_dir(p, dir);
-  rg_cross(t, p[1].v, p[2].v); b[0] = rg_dot3(t, p[3].v);
-  rg_cross(t, p[3].v, p[2].v); b[1] = rg_dot3(t, p[0].v);
-  rg_cross(t, p[0].v, p[1].v); b[2] = rg_dot3(t, p[3].v);
-  rg_cross(t, p[2].v, p[1].v); b[3] = rg_dot3(t, p[0].v);
+  rg_portal_dir3(p1, p2, p3, dir);
+  rg_cross(t, p1.v, p2.v); b[0] = rg_dot3(t, p3.v);
+  rg_cross(t, p3.v, p2.v); b[1] = rg_dot3(t, v0);
+  rg_cross(t, v0, p1.v); b[2] = rg_dot3(t, p3.v);
+  rg_cross(t, p2.v, p1.v); b[3] = rg_dot3(t, v0);
   float sum = b[0] + b[1] + b[2] + b[3];
   if (sum <= 1e-30f) {
     b[0] = 0;
-    rg_cross(t, p[2].v, p[3].v); b[1] = rg_dot3(t, dir);
-    rg_cross(t, p[3].v, p[1].v); b[2] = rg_dot3(t, dir);
-    rg_cross(t, p[1].v, p[2].v); b[3] = rg_dot3(t, dir);
+    rg_cross(t, p2.v, p3.v); b[1] = rg_dot3(t, dir);
+    rg_cross(t, p3.v, p1.v); b[2] = rg_dot3(t, dir);
+    rg_cross(t, p1.v, p2.v); b[3] = rg_dot3(t, dir);
     sum = b[1] + b[2] + b[3];
   }
   const float inv = 0.5f / sum;
   for (int i = 0; i < 3; i++)
-    pos[i] = inv * (b[0] * (p[0].v1[i] + p[0].v2[i]) + b[1] * (p[1].v1[i] + p[1].v2[i]) + b[2] * (p[2].v1[i] + p[2].v2[i]) + b[3] * (p[3].v1[i] + p[3].v2[i]));
+    pos[i] = inv * (b[0] * (c1[i] + c2[i]) + b[1] * (p1.v1[i] + p1.v2[i]) + b[2] * (p2.v1[i] + p2.v2[i]) + b[3] * (p3.v1[i] + p3.v2[i]));
 }
 
 /* depth >= 0 with dir,pos when the inflated geoms intersect; -1 otherwise */
-RG_DEV float rg_mpr(const RgModel& m, RgGeomView& o1, RgGeomView& o2, float tol, int maxiter, float* dir_out, float* pos) {
-  RgSup p[4], v4;
-  float dir[3], va[3], vb[3], dot;
-  rg_copy3(p[0].v1, o1.pos); rg_copy3(p[0].v2, o2.pos);
-  rg_sub3(p[0].v, p[0].v1, p[0].v2);
-  if (rg_mpr_zero(p[0].v[0]) && rg_mpr_zero(p[0].v[1]) && rg_mpr_zero(p[0].v[2])) p[0].v[0] = 1e-5f;
-  rg_scl3(dir, p[0].v, -1.0f); rg_normalize3(dir);
-  rg_mpr_support(m, o1, o2, dir, p[1]);
-  dot = rg_dot3(p[1].v, dir);
-  if (dot < 0 || rg_mpr_zero(dot)) return -1.0f;
-  rg_cross(dir, p[0].v, p[1].v);
-  /* fp32: the parallel test must be scale-free (libccd compares the raw squared norm with DBL_EPSILON) */
-  if (rg_dot3(dir, dir) <= 1e-12f * rg_dot3(p[0].v, p[0].v) * rg_dot3(p[1].v, p[1].v)) {
-    const float n = sqrtf(rg_dot3(p[1].v, p[1].v));
-    for (int i = 0; i < 3; i++) pos[i] = 0.5f * (p[1].v1[i] + p[1].v2[i]);
-    if (n < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; return 0.0f; }
-    rg_scl3(dir_out, p[1].v, 1.0f / n);
-    return n;
-  }
-  rg_normalize3(dir);
-  rg_mpr_support(m, o1, o2, dir, p[2]);
-  dot = rg_dot3(p[2].v, dir);
-  if (dot < 0 || rg_mpr_zero(dot)) return -1.0f;
-  rg_sub3(va, p[1].v, p[0].v); rg_sub3(vb, p[2].v, p[0].v);
-  rg_cross(dir, va, vb); rg_normalize3(dir);
-  if (rg_dot3(dir, p[0].v) > 0) { RgSup t = p[1]; p[1] = p[2]; p[2] = t; rg_scl3(dir, dir, -1.0f); }
-  for (int guard = 0;; guard++) {
-    if (guard > 100) return -1.0f;
-    rg_mpr_support(m, o1, o2, dir, p[3]);
-    dot = rg_dot3(p[3].v, dir);
-    if (dot < 0 || rg_mpr_zero(dot)) return -1.0f;
-    int cont = 0;
-    rg_cross(va, p[1].v, p[3].v);
-    dot = rg_dot3(va, p[0].v);
-    if (dot < 0) { p[2] = p[3]; cont = 1; } /* triple products are ~1e-6: sign only */
-    if (!cont) {
-      rg_cross(va, p[3].v, p[2].v);
-      dot = rg_dot3(va, p[0].v);
-      if (dot < 0) { p[1] = p[3]; cont = 1; }
+RG_DEV_NOINLINE float rg_mpr(const RgModel& m, RgGeomView& o1, RgGeomView& o2, float tol, int maxiter, float* dir_out, float* pos) {
+  enum { S_V1 = 0, S_V2 = 1, S_V3 = 2, S_REFINE = 3, S_PENETR = 4, S_DONE = 5 };
+  RgSup P1, P2, P3, sp;
+  float v0[3], dir[3], va[3], vb[3];
+  float result = -1.0f;
+  rg_sub3(v0, o1.pos, o2.pos);
+  if (rg_mpr_zero(v0[0]) && rg_mpr_zero(v0[1]) && rg_mpr_zero(v0[2])) v0[0] = 1e-5f;
+  rg_scl3(dir, v0, -1.0f); rg_normalize3(dir);
+  int state = S_V1, pen_it = 0;
+  P1 = RgSup(); P2 = RgSup(); P3 = RgSup();
+  for (int it = 0; it < 200 + maxiter && state != S_DONE; it++) {
+    rg_mpr_support(m, o1, o2, dir, sp);
+    const float dot = rg_dot3(sp.v, dir);
+    if (state == S_V1) {
+      P1 = sp;
+      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
+      rg_cross(dir, v0, P1.v);
+      /* fp32: the parallel test must be scale-free (libccd compares the raw squared norm with DBL_EPSILON) */
+      if (rg_dot3(dir, dir) <= 1e-12f * rg_dot3(v0, v0) * rg_dot3(P1.v, P1.v)) {
+        const float n = sqrtf(rg_dot3(P1.v, P1.v));
+        for (int i = 0; i < 3; i++) pos[i] = 0.5f * (P1.v1[i] + P1.v2[i]);
+        if (n < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; result = 0.0f; }
+        else { rg_scl3(dir_out, P1.v, 1.0f / n); result = n; }
+        state = S_DONE;
+        continue;
+      }
+      rg_normalize3(dir);
+      state = S_V2;
+    } else if (state == S_V2) {
+      P2 = sp;
+      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
+      rg_sub3(va, P1.v, v0); rg_sub3(vb, P2.v, v0);
+      rg_cross(dir, va, vb); rg_normalize3(dir);
+      if (rg_dot3(dir, v0) > 0) { const RgSup t = P1; P1 = P2; P2 = t; rg_scl3(dir, dir, -1.0f); }
+      state = S_V3;
+    } else if (state == S_V3) {
+      P3 = sp;
+      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
+      int cont = 0;
+      rg_cross(va, P1.v, P3.v);
+      if (rg_dot3(va, v0) < 0) { P2 = P3; cont = 1; }     /* triple products are ~1e-6: sign only */
+      if (!cont) {
+        rg_cross(va, P3.v, P2.v);
+        if (rg_dot3(va, v0) < 0) { P1 = P3; cont = 1; }
+      }
+      if (cont) {
+        rg_sub3(va, P1.v, v0); rg_sub3(vb, P2.v, v0);
+        rg_cross(dir, va, vb); rg_normalize3(dir);
+      } else {
+        rg_portal_dir3(P1, P2, P3, dir);
+        const float d1 = rg_dot3(dir, P1.v);
+        state = (d1 > 0 || rg_mpr_zero(d1)) ? S_PENETR : S_REFINE;
+      }
+    } else if (state == S_REFINE) {
+      if (!(dot > 0 || rg_mpr_zero(dot)) || rg_reach_tol3(P1, P2, P3, sp, dir, tol)) { state = S_DONE; continue; }
+      rg_expand_portal3(P1, P2, P3, v0, sp);
+      rg_portal_dir3(P1, P2, P3, dir);
+      const float d1 = rg_dot3(dir, P1.v);
+      if (d1 > 0 || rg_mpr_zero(d1)) state = S_PENETR;
+    } else { /* S_PENETR */
+      if (rg_reach_tol3(P1, P2, P3, sp, dir, tol) || pen_it > maxiter) {
+        float w[3];
+        const float depth = sqrtf(rg_tri_closest(P1.v, P2.v, P3.v, w));
+        if (depth < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; }
+        else rg_scl3(dir_out, w, 1.0f / depth);
+        rg_find_pos3(v0, o1.pos, o2.pos, P1, P2, P3, pos);
+        result = depth;
+        state = S_DONE;
+        continue;
+      }
+      rg_expand_portal3(P1, P2, P3, v0, sp);
+      rg_portal_dir3(P1, P2, P3, dir);
+      pen_it++;
     }
-    if (!cont) break;
-    rg_sub3(va, p[1].v, p[0].v); rg_sub3(vb, p[2].v, p[0].v);
-    rg_cross(dir, va, vb); rg_normalize3(dir);
   }
-  for (int guard = 0;; guard++) {
-    if (guard > 1000) return -1.0f;
-    rg_portal_dir(p, dir);
-    dot = rg_dot3(dir, p[1].v);
-    if (dot > 0 || rg_mpr_zero(dot)) break;
-    rg_mpr_support(m, o1, o2, dir, v4);
-    dot = rg_dot3(v4.v, dir);
-    if (!(dot > 0 || rg_mpr_zero(dot))) return -1.0f;
-    if (rg_reach_tol(p, v4, dir, tol)) return -1.0f;
-    rg_expand_portal(p, v4);
-  }
-  for (int it = 0;; it++) {
-    rg_portal_dir(p, dir);
-    rg_mpr_support(m, o1, o2, dir, v4);
-    if (rg_reach_tol(p, v4, dir, tol) || it > maxiter) {
-      float w[3];
-      const float depth = sqrtf(rg_tri_closest(p[1].v, p[2].v, p[3].v, w));
-      if (depth < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; }
-      else rg_scl3(dir_out, w, 1.0f / depth);
-      rg_find_pos(p, pos);
-      return depth;
-    }
-    rg_expand_portal(p, v4);
-  }
+  return result;
 }
 
 RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
@@ -236,7 +266,42 @@ RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
 }
 
 /* narrow phase of one pair; writes up to 4 (dist,pos,normal) records to out[7*i..]; returns count */
-RG_DEV int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
+/* oriented-box overlap (separating-axis test on the geoms' local bounding boxes, box 1 grown by margin):
+ * a conservative cull between the bounding-sphere test and MPR; it never removes a pair that could touch */
+RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx& c, int g1, int g2, float margin) {
+  const RgModel& m = c.m;
+  float q[4], A[9], B[9], ca[3], cb[3], t[3], d[3];
+  rg_quat_mul(q, c.s + c.L.xquat + 4 * m.geom_bodyid[g1], m.geom_quat + 4 * g1); rg_quat_norm(q); rg_quat2mat(A, q);
+  rg_quat_mul(q, c.s + c.L.xquat + 4 * m.geom_bodyid[g2], m.geom_quat + 4 * g2); rg_quat_norm(q); rg_quat2mat(B, q);
+  rg_mulmat3(ca, A, m.geom_aabb + 6 * g1); rg_add3(ca, ca, c.s + c.L.gxpos + 3 * g1);
+  rg_mulmat3(cb, B, m.geom_aabb + 6 * g2); rg_add3(cb, cb, c.s + c.L.gxpos + 3 * g2);
+  const float a[3] = {m.geom_aabb[6 * g1 + 3] + margin, m.geom_aabb[6 * g1 + 4] + margin, m.geom_aabb[6 * g1 + 5] + margin};
+  const float* b = m.geom_aabb + 6 * g2 + 3;
+  rg_sub3(d, cb, ca);
+  rg_mulmatT3(t, A, d);
+  float R[9], AR[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      R[3 * i + j] = A[i] * B[j] + A[3 + i] * B[3 + j] + A[6 + i] * B[6 + j];
+      AR[3 * i + j] = fabsf(R[3 * i + j]) + 1e-6f;
+    }
+  for (int i = 0; i < 3; i++)
+    if (fabsf(t[i]) > a[i] + b[0] * AR[3 * i] + b[1] * AR[3 * i + 1] + b[2] * AR[3 * i + 2]) return 0;
+  for (int j = 0; j < 3; j++)
+    if (fabsf(t[0] * R[j] + t[1] * R[3 + j] + t[2] * R[6 + j]) > a[0] * AR[j] + a[1] * AR[3 + j] + a[2] * AR[6 + j] + b[j]) return 0;
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    for (int j = 0; j < 3; j++) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      const float ra = a[i1] * AR[3 * i2 + j] + a[i2] * AR[3 * i1 + j];
+      const float rb = b[j1] * AR[3 * i + j2] + b[j2] * AR[3 * i + j1];
+      if (fabsf(t[i2] * R[3 * i1 + j] - t[i1] * R[3 * i2 + j]) > ra + rb) return 0;
+    }
+  }
+  return 1;
+}
+
+RG_DEV_NOINLINE int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
   const RgModel& m = c.m;
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   int cnt = 0;
@@ -302,11 +367,13 @@ RG_DEV int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
     }
     return cnt;
   }
+  RG_STAT(rg_stat_mpr++; rg_stat_cur = 0;)
   RgGeomView o1, o2;
   rg_geom_view(c, g1, margin, o1);
   rg_geom_view(c, g2, margin, o2);
   float dir[3], pos[3];
   const float depth = rg_mpr(m, o1, o2, m.opt_mpr_tolerance[0], m.opt_mpr_iterations[0], dir, pos);
+  RG_STAT(if (rg_stat_cur > rg_stat_maxsup) rg_stat_maxsup = rg_stat_cur; if (depth >= 0) rg_stat_mpr_hit++;)
   if (depth < 0 || rg_dot3(dir, dir) < 0.5f) return 0;
   out[0] = margin - depth;
   rg_copy3(out + 1, pos);
@@ -314,22 +381,32 @@ RG_DEV int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
   return 1;
 }
 
+/* append the first `n` survivors (flag per lane) of list `src` to list `dst`, then drop them from `src` */
+RG_DEV void rg_pair(const RgModel& m, int k, int& g1, int& g2) {
+  if (m.pair_packed) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
+  else { g1 = RG_LDG(m.pair_geom1 + k); g2 = RG_LDG(m.pair_geom2 + k); }
+}
 RG_DEV_NOINLINE void rg_collision(RgCtx& c) {
   RG_LANE_DECL
   const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
   int* cand = (int*)(s + L.cand);
-  int ncon = 0, ncand = 0, k0 = 0, warn = 0;
+  int* cand2 = (int*)(s + L.cand2);
+  int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0;
   const int cap = (m.nconmax > 0 && m.nconmax < RG_NCON) ? m.nconmax : RG_NCON;
   const int enabled = !(m.opt_disableflags[0] & (RG_DSBL_CONTACT | RG_DSBL_CONSTRAINT));
-  while (enabled && (k0 < m.npair || ncand > 0)) {
-    while (ncand < 32 && k0 < m.npair) {
+  RG_PROF_BEGIN
+  while (enabled && (k0 < m.npair || n1 > 0 || n2 > 0)) {
+    /* stage A: bounding spheres over the static pair list -> cand */
+    RG_PROF(c, 15)
+    while (n1 < 32 && k0 < m.npair) {
       LANEVAR(int, pred); LANEVAR(int, pos);
       int tot;
       RG_PHASE_BEGIN
       const int k = k0 + lane;
       int pr = 0;
       if (k < m.npair) {
-        const int g1 = RG_LDG(m.pair_geom1 + k), g2 = RG_LDG(m.pair_geom2 + k);
+        int g1, g2;
+        rg_pair(m, k, g1, g2);
         const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
         float dif[3];
         rg_sub3(dif, s + L.gxpos + 3 * g2, s + L.gxpos + 3 * g1);
@@ -348,77 +425,110 @@ RG_DEV_NOINLINE void rg_collision(RgCtx& c) {
       RG_PHASE_END
       RG_WARP_SCAN(pred, pos, tot);
       RG_PHASE_BEGIN
-      if (LV(pred)) cand[ncand + LV(pos)] = k0 + lane;
+      if (LV(pred)) cand[n1 + LV(pos)] = k0 + lane;
       RG_PHASE_END
-      ncand += tot;
+      n1 += tot;
       k0 += 32;
     }
-    const int n = ncand < 32 ? ncand : 32;
-    LANEVAR(int, cnt); LANEVAR(int, cpos); LANEVAR(int, keep);
-    LANEARR(float, cb, 28);
-    int tot;
-    RG_PHASE_BEGIN
-    int cn = 0;
-    if (lane < n) {
-      const int k = cand[lane];
-      const int g1 = RG_LDG(m.pair_geom1 + k), g2 = RG_LDG(m.pair_geom2 + k);
-      cn = rg_narrow(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), &LA(cb, 0));
-    }
-    LV(cnt) = cn;
-    LV(keep) = (lane + 32 < ncand) ? cand[lane + 32] : -1;
-    RG_PHASE_END
-    RG_WARP_SCAN(cnt, cpos, tot);
-    RG_PHASE_BEGIN
-    if (lane < n && LV(cnt) > 0) {
-      const int k = cand[lane];
-      const int g1 = RG_LDG(m.pair_geom1 + k), g2 = RG_LDG(m.pair_geom2 + k);
-      /* mixed contact parameters: max condim / friction, solmix-weighted solref / solimp */
-      int condim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
-      float fri[3], solref[2], solimp[5];
-      const int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
-      if (p1 != p2) {
-        const int gp = p1 > p2 ? g1 : g2;
-        condim = m.geom_condim[gp];
-        for (int i = 0; i < 3; i++) fri[i] = m.geom_friction[3 * gp + i];
-        for (int i = 0; i < 2; i++) solref[i] = m.geom_solref[2 * gp + i];
-        for (int i = 0; i < 5; i++) solimp[i] = m.geom_solimp[5 * gp + i];
-      } else {
-        for (int i = 0; i < 3; i++) fri[i] = fmaxf(m.geom_friction[3 * g1 + i], m.geom_friction[3 * g2 + i]);
-        const float s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2];
-        float mix;
-        if (s1 >= RG_MINVAL && s2 >= RG_MINVAL) mix = s1 / (s1 + s2);
-        else if (s1 < RG_MINVAL && s2 < RG_MINVAL) mix = 0.5f;
-        else mix = s1 < RG_MINVAL ? 0.0f : 1.0f;
-        const float* r1 = m.geom_solref + 2 * g1; const float* r2 = m.geom_solref + 2 * g2;
-        if (r1[0] > 0 && r2[0] > 0) for (int i = 0; i < 2; i++) solref[i] = mix * r1[i] + (1 - mix) * r2[i];
-        else for (int i = 0; i < 2; i++) solref[i] = fminf(r1[i], r2[i]);
-        for (int i = 0; i < 5; i++) solimp[i] = mix * m.geom_solimp[5 * g1 + i] + (1 - mix) * m.geom_solimp[5 * g2 + i];
+    RG_PROF(c, 9)
+    /* stage B: oriented bounding boxes on up to 32 candidates -> cand2 */
+    if (n1 > 0 && n2 < 32) {
+      const int n = n1 < 32 ? n1 : 32;
+      LANEVAR(int, pred); LANEVAR(int, pos); LANEVAR(int, keep); LANEVAR(int, mine);
+      int tot;
+      RG_PHASE_BEGIN
+      int pr = 0, k = -1;
+      if (lane < n) {
+        k = cand[lane];
+        int g1, g2;
+        rg_pair(m, k, g1, g2);
+        pr = m.geom_type[g1] == RG_GEOM_PLANE ? 1 : rg_obb_overlap(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]));
       }
-      const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
-      for (int i = 0; i < LV(cnt); i++) {
-        const int idx = ncon + LV(cpos) + i;
-        if (idx >= cap) break;
-        float* r = s + L.con + RG_CON_STRIDE * idx;
-        const float* o = &LA(cb, 7 * i);
-        r[0] = o[0];
-        rg_copy3(r + 1, o + 1);
-        rg_copy3(r + 4, o + 4);
-        rg_make_frame(r + 4, r + 7, r + 10);
-        r[13] = margin - gap;
-        r[14] = fri[0]; r[15] = fri[1]; r[16] = fri[2];
-        r[17] = (float)condim;
-        r[18] = (float)m.geom_bodyid[g1]; r[19] = (float)m.geom_bodyid[g2];
-        r[20] = (float)g1; r[21] = (float)g2;
-        r[22] = solref[0]; r[23] = solref[1];
-        for (int q = 0; q < 5; q++) r[24 + q] = solimp[q];
-      }
+      LV(pred) = pr; LV(mine) = k;
+      LV(keep) = (lane + 32 < n1) ? cand[lane + 32] : -1;
+      RG_PHASE_END
+      RG_WARP_SCAN(pred, pos, tot);
+      RG_PHASE_BEGIN
+      if (LV(pred)) cand2[n2 + LV(pos)] = LV(mine);
+      if (LV(keep) >= 0) cand[lane] = LV(keep);
+      RG_PHASE_END
+      n2 += tot;
+      n1 = n1 > 32 ? n1 - 32 : 0;
     }
-    RG_PHASE_END
-    if (ncon + tot > cap) { warn |= RG_WARN_CONTACT_FULL; ncon = cap; } else ncon += tot;
-    RG_PHASE_BEGIN
-    if (LV(keep) >= 0) cand[lane] = LV(keep);
-    RG_PHASE_END
-    ncand = ncand > 32 ? ncand - 32 : 0;
+    RG_PROF(c, 10)
+    /* stage C: narrow phase, one pair per lane, once a full warp of work is queued (or at the end) */
+    if (n2 >= 32 || (n2 > 0 && k0 >= m.npair && n1 == 0)) {
+      const int n = n2 < 32 ? n2 : 32;
+      LANEVAR(int, cnt); LANEVAR(int, cpos); LANEVAR(int, keep);
+      LANEARR(float, cb, 28);
+      int tot;
+      RG_PHASE_BEGIN
+      int cn = 0;
+      if (lane < n) {
+        const int k = cand2[lane];
+        int g1, g2;
+        rg_pair(m, k, g1, g2);
+        cn = rg_narrow(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), &LA(cb, 0));
+      }
+      LV(cnt) = cn;
+      LV(keep) = (lane + 32 < n2) ? cand2[lane + 32] : -1;
+      RG_PHASE_END
+      RG_WARP_SCAN(cnt, cpos, tot);
+      RG_PHASE_BEGIN
+      if (lane < n && LV(cnt) > 0) {
+        const int k = cand2[lane];
+        int g1, g2;
+        rg_pair(m, k, g1, g2);
+        /* mixed contact parameters: max condim / friction, solmix-weighted solref / solimp */
+        int condim = m.geom_condim[g1] > m.geom_condim[g2] ? m.geom_condim[g1] : m.geom_condim[g2];
+        float fri[3], solref[2], solimp[5];
+        const int p1 = m.geom_priority[g1], p2 = m.geom_priority[g2];
+        if (p1 != p2) {
+          const int gp = p1 > p2 ? g1 : g2;
+          condim = m.geom_condim[gp];
+          for (int i = 0; i < 3; i++) fri[i] = m.geom_friction[3 * gp + i];
+          for (int i = 0; i < 2; i++) solref[i] = m.geom_solref[2 * gp + i];
+          for (int i = 0; i < 5; i++) solimp[i] = m.geom_solimp[5 * gp + i];
+        } else {
+          for (int i = 0; i < 3; i++) fri[i] = fmaxf(m.geom_friction[3 * g1 + i], m.geom_friction[3 * g2 + i]);
+          const float s1 = m.geom_solmix[g1], s2 = m.geom_solmix[g2];
+          float mix;
+          if (s1 >= RG_MINVAL && s2 >= RG_MINVAL) mix = s1 / (s1 + s2);
+          else if (s1 < RG_MINVAL && s2 < RG_MINVAL) mix = 0.5f;
+          else mix = s1 < RG_MINVAL ? 0.0f : 1.0f;
+          const float* r1 = m.geom_solref + 2 * g1; const float* r2 = m.geom_solref + 2 * g2;
+          if (r1[0] > 0 && r2[0] > 0) for (int i = 0; i < 2; i++) solref[i] = mix * r1[i] + (1 - mix) * r2[i];
+          else for (int i = 0; i < 2; i++) solref[i] = fminf(r1[i], r2[i]);
+          for (int i = 0; i < 5; i++) solimp[i] = mix * m.geom_solimp[5 * g1 + i] + (1 - mix) * m.geom_solimp[5 * g2 + i];
+        }
+        const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]), gap = fmaxf(m.geom_gap[g1], m.geom_gap[g2]);
+        for (int i = 0; i < LV(cnt); i++) {
+          const int idx = ncon + LV(cpos) + i;
+          if (idx >= cap) break;
+          float* r = s + L.con + RG_CON_STRIDE * idx;
+          const float* o = &LA(cb, 7 * i);
+          r[0] = o[0];
+          rg_copy3(r + 1, o + 1);
+          rg_copy3(r + 4, o + 4);
+          rg_make_frame(r + 4, r + 7, r + 10);
+          r[13] = margin - gap;
+          r[14] = fri[0]; r[15] = fri[1]; r[16] = fri[2];
+          r[17] = (float)condim;
+          r[18] = (float)m.geom_bodyid[g1]; r[19] = (float)m.geom_bodyid[g2];
+          r[20] = (float)g1; r[21] = (float)g2;
+          r[22] = solref[0]; r[23] = solref[1];
+          for (int q = 0; q < 5; q++) s[L.cprm + 8 * idx + q] = solimp[q];   /* consumed by rg_make_constraints */
+        }
+      }
+      RG_PHASE_END
+      if (ncon + tot > cap) { warn |= RG_WARN_CONTACT_FULL; ncon = cap; } else ncon += tot;
+      RG_PHASE_BEGIN
+      if (LV(keep) >= 0) cand2[lane] = LV(keep);
+      RG_PHASE_END
+      n2 = n2 > 32 ? n2 - 32 : 0;
+      RG_PROF(c, 12)
+    }
+    RG_PROF(c, 11)
   }
   RG_PHASE_BEGIN
   if (lane == 0) { RG_SI(c, RG_S_NCON) = ncon; RG_SI(c, RG_S_WARN) |= warn; }

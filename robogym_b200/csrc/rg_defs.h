@@ -28,9 +28,11 @@
 #define LV(x) x[lane]
 #define LA(x, i) x[lane][i]
 #define RG_LDG(p) (*(p))
+#define RG_LDG4(base, idx, out) { const float* q_ = (base) + 4 * (size_t)(idx); (out)[0] = q_[0]; (out)[1] = q_[1]; (out)[2] = q_[2]; (out)[3] = q_[3]; }
 #define RG_RSQRT(x) (1.0f / sqrtf(x))
 #else
 #include <cuda_runtime.h>
+#include <string.h>
 #define RG_DEV __device__ __forceinline__
 #define RG_DEV_NOINLINE __device__ __noinline__
 #define RG_PHASE_BEGIN {
@@ -41,6 +43,7 @@
 #define LV(x) x
 #define LA(x, i) x[i]
 #define RG_LDG(p) __ldg(p)
+#define RG_LDG4(base, idx, out) { const float4 q_ = __ldg((const float4*)(base) + (idx)); (out)[0] = q_.x; (out)[1] = q_.y; (out)[2] = q_.z; (out)[3] = q_.w; }
 #define RG_RSQRT(x) rsqrtf(x)
 #endif
 
@@ -48,9 +51,11 @@
 #define RG_EPS 1.1920929e-07f
 #define RG_NCON 32       /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
 #define RG_NEL 64        /* single-row constraint elements (friction loss + limits) */
-#define RG_CON_STRIDE 32
+#define RG_CON_STRIDE 24
+#define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
 #define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds) */
-#define RG_TILE 24       /* max dofs touched by one contact */
+#define RG_TRI(i, j) ((((i) * ((i) + 1)) >> 1) + (j))   /* packed lower triangle, i >= j */
+#define RG_TILE 16       /* max dofs touched by one contact */
 
 enum { RG_JNT_FREE = 0, RG_JNT_BALL = 1, RG_JNT_SLIDE = 2, RG_JNT_HINGE = 3 };
 enum { RG_GEOM_PLANE = 0, RG_GEOM_SPHERE = 2, RG_GEOM_CAPSULE = 3, RG_GEOM_ELLIPSOID = 4, RG_GEOM_CYLINDER = 5, RG_GEOM_BOX = 6, RG_GEOM_MESH = 7 };
@@ -61,7 +66,7 @@ enum { RG_DSBL_CONSTRAINT = 1, RG_DSBL_EQUALITY = 2, RG_DSBL_FRICTIONLOSS = 4, R
        RG_DSBL_PASSIVE = 32, RG_DSBL_GRAVITY = 64, RG_DSBL_CLAMPCTRL = 128, RG_DSBL_WARMSTART = 256,
        RG_DSBL_ACTUATION = 1024, RG_DSBL_REFSAFE = 2048 };
 enum { RG_EL_FLOSS = 0, RG_EL_JLIMIT = 1, RG_EL_TLIMIT = 2 };
-enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8 };
+enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8, RG_WARN_TENDON_NNZ = 16 };
 
 /* Device view of the compiled model: fp32 / int32 copies of every rg_model_fields.h array. */
 struct RgModel {
@@ -74,6 +79,9 @@ struct RgModel {
 #undef RG_F
   const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
   const int* dof_treeroot;     /* first dof of the kinematic tree a dof belongs to (Cholesky envelope) */
+  const float* mesh_nbr;       /* [nmeshadj][4]: neighbour vertex x,y,z + its local index (as int bits): hill-climb without a second indirection */
+  const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
+  const int* mesh_ext;         /* [nmesh][6]: extreme vertices along +x,-x,+y,-y,+z,-z (hill-climb starting points) */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
 };
@@ -82,13 +90,13 @@ struct RgModel {
 struct RgLayout {
   int qpos, qvel, ctrl, pid, warm;
   int lpos, lquat, xpos, xquat, xipos, gxpos, sxpos;
-  int S, M, H;                       /* H aliases the block {Sdot,cvel,cacc,I10,crb} that is dead by then */
-  int Sdot, cvel, cacc, I10, crb;
-  int bias, passive, qfa, smooth, qacc, Ma, grad, search, Mv, qfc, tmp;
-  int tlen, tvel, tJ, alen, aforce;
+  int S, M, H;                       /* packed lower triangles; H aliases the block {Sdot,I10,crb} that is dead by then */
+  int Sdot, I10, crb;
+  int bias, smooth, qacc, Ma, search, Mv, qfc, tmp;
+  int tlen, tvel, tJn, tJi, tJv, alen, aforce;
   int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
-  int el_i, el_D, el_R, el_aref, el_floss, el_jar, el_jv, el_f;
-  int tileJ, tileWJ, tileDof, cand, scal, eldof, env;
+  int el_i, el_D, el_floss, el_jar, el_jv, el_f;
+  int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof;
   int total;
 };
 
@@ -198,6 +206,7 @@ RG_DEV void rg_mulmatT3(float* r, const float* m, const float* v) {
   float x = m[0] * v[0] + m[3] * v[1] + m[6] * v[2], y = m[1] * v[0] + m[4] * v[1] + m[7] * v[2], z = m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
   r[0] = x; r[1] = y; r[2] = z;
 }
+RG_DEV int rg_f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
 RG_DEV float rg_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 RG_DEV int rg_dof_in_body(const RgModel& m, int body, int dof) {
   return (((const unsigned*)m.body_dofmask)[body * m.nmaskw + (dof >> 5)] >> (dof & 31)) & 1u;

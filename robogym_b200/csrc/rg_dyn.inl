@@ -15,10 +15,20 @@ struct RgCtx {
   float* s;              /* per-warp scratch */
   const float* xfrc;     /* global: this env's xfrc_applied [nbody*6] or nullptr */
   float timestep;        /* per-env timestep (opt.timestep unless overridden) */
+  int sig;               /* signature of the solver's active set (warp-uniform), see rg_solver_update */
 };
 
 #define RG_SI(c, k) (((int*)((c).s + (c).L.scal))[k])
 enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4 };
+
+/* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
+#if !defined(RG_EMU) && defined(RG_PROFILE)
+#define RG_PROF_BEGIN long long prof_t_ = clock64();
+#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) (c).s[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
+#else
+#define RG_PROF_BEGIN
+#define RG_PROF(c, k)
+#endif
 
 /* Spatial vectors of a kinematic tree are expressed about that tree's own reference point (the
  * world position of its root body), not the world origin: in fp32 the parallel-axis terms m*c^2
@@ -41,7 +51,7 @@ RG_DEV int rg_ctz(unsigned x) {
 }
 
 /* apply joint j (of body b) to the running frame (pos, quat) */
-RG_DEV void rg_apply_joint(const RgModel& m, const float* qpos, int j, float* pos, float* quat) {
+RG_DEV_NOINLINE void rg_apply_joint(const RgModel& m, const float* qpos, int j, float* pos, float* quat) {
   const int type = m.jnt_type[j], qa = m.jnt_qposadr[j];
   if (type == RG_JNT_FREE) {
     pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
@@ -197,7 +207,7 @@ RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
     I[8] = Ic[4] - mass * cm[0] * cm[2];
     I[9] = Ic[5] - mass * cm[1] * cm[2];
   }
-  for (int i = lane; i < nv * nv; i += 32) s[L.M + i] = 0.0f;
+  for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.M + i] = 0.0f;
   RG_PHASE_END
   /* composite inertias: subtree(b) is the contiguous id range [b, b+size) */
   RG_PHASE_BEGIN
@@ -217,8 +227,7 @@ RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
     while (j >= 0) {
       float v = rg_dot6(s + L.S + 6 * j, F);
       if (j == i) v += m.dof_armature[i];
-      s[L.M + i * nv + j] = v;
-      s[L.M + j * nv + i] = v;
+      s[L.M + RG_TRI(i, j)] = v;   /* ancestors have smaller indices: j <= i */
       j = m.dof_parentid[j];
     }
   }
@@ -258,29 +267,27 @@ RG_DEV_NOINLINE void rg_bias(RgCtx& c) {
         for (int k = 0; k < 6; k++) { V[k] += Sd[k] * qd; A[k] += Sp[k] * qd; }
       }
     }
-    float* cv = s + L.cvel + 6 * b;
-    for (int k = 0; k < 6; k++) cv[k] = V[k];
     const float* I = s + L.I10 + 10 * b;
     float F[6], H[6], G[6];
     rg_inertia_mul(F, I, A);
     rg_inertia_mul(H, I, V);
     rg_cross_force(G, V, H);
-    float* ca = s + L.cacc + 6 * b;
+    float* ca = s + L.crb + 10 * b;   /* crb is dead once M is assembled: reuse it for the per-body force */
     for (int k = 0; k < 6; k++) ca[k] = b == 0 ? 0.0f : F[k] + G[k];
   }
   RG_PHASE_END
-  /* subtree force sums (into the crb slot, dead after rg_massmatrix) */
+  /* subtree force sums (into the Sdot slot, dead after the previous phase) */
   RG_PHASE_BEGIN
   for (int i = lane; i < m.nbody * 6; i += 32) {
     const int b = i / 6, k = i - 6 * b;
     float acc = 0.0f;
     const int e = b + m.body_subtreesize[b];
-    for (int bb = b; bb < e; bb++) acc += s[L.cacc + 6 * bb + k];
-    s[L.crb + 10 * b + k] = acc;
+    for (int bb = b; bb < e; bb++) acc += s[L.crb + 10 * bb + k];
+    s[L.Sdot + 6 * b + k] = acc;
   }
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int d = lane; d < m.nv; d += 32) s[L.bias + d] = rg_dot6(s + L.S + 6 * d, s + L.crb + 10 * m.dof_bodyid[d]);
+  for (int d = lane; d < m.nv; d += 32) s[L.bias + d] = rg_dot6(s + L.S + 6 * d, s + L.Sdot + 6 * m.dof_bodyid[d]);
   RG_PHASE_END
 }
 
@@ -325,7 +332,7 @@ RG_DEV float rg_wrap_circle(float* pnt, const float* d0, const float* d1, const 
   return rad * acosf(rg_clamp((pnt[0] * pnt[2] + pnt[1] * pnt[3]) / sqr, -1.0f, 1.0f));
 }
 /* x0 -> wrap geom -> x1: tangent points wp[0..2], wp[3..5]; returns curved length or -1 */
-RG_DEV float rg_wrap_geom(float* wp, const float* x0, const float* x1, const float* gpos, const float* gmat, float rad, int type, const float* side) {
+RG_DEV_NOINLINE float rg_wrap_geom(float* wp, const float* x0, const float* x1, const float* gpos, const float* gmat, float rad, int type, const float* side) {
   float t[3], p0[3], p1[3];
   rg_sub3(t, x0, gpos); rg_mulmatT3(p0, gmat, t);
   rg_sub3(t, x1, gpos); rg_mulmatT3(p1, gmat, t);
@@ -372,7 +379,7 @@ RG_DEV float rg_wrap_geom(float* wp, const float* x0, const float* x1, const flo
   rg_mulmat3(t, gmat, r1); rg_add3(wp + 3, t, gpos);
   return wlen;
 }
-RG_DEV void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
+RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
   if (ba == bb) return;
   const RgModel& m = c.m;
   for (int d = 0; d < m.nv; d++) {
@@ -384,13 +391,21 @@ RG_DEV void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const float* pa,
   }
 }
 
+/* entry (t, d) of the sparse tendon Jacobian */
+RG_DEV float rg_tendon_J(const RgCtx& c, int t, int d) {
+  const int n = ((const int*)(c.s + c.L.tJn))[t];
+  const int* ji = (const int*)(c.s + c.L.tJi) + RG_TJ * t;
+  float v = 0.0f;
+  for (int k = 0; k < n; k++) if (ji[k] == d) v = c.s[c.L.tJv + RG_TJ * t + k];
+  return v;
+}
 RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
   RG_LANE_DECL
   const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
   const int nv = m.nv;
   RG_PHASE_BEGIN
   for (int t = lane; t < m.ntendon; t += 32) {
-    float* J = s + L.tJ + t * nv;
+    float* J = s + L.H + t * nv;   /* dense scratch row in the (currently dead) H region, compressed below */
     for (int k = 0; k < nv; k++) J[k] = 0.0f;
     const int adr = m.tendon_adr[t], num = m.tendon_num[t];
     float len = 0.0f, divisor = 1.0f;
@@ -446,7 +461,16 @@ RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
     }
     s[L.tlen + t] = len;
     float v = 0.0f;
-    for (int k = 0; k < nv; k++) v += J[k] * s[L.qvel + k];
+    int nnz = 0;
+    int* ji = (int*)(s + L.tJi) + RG_TJ * t;
+    float* jv = s + L.tJv + RG_TJ * t;
+    for (int k = 0; k < nv; k++) {
+      if (J[k] == 0.0f) continue;
+      v += J[k] * s[L.qvel + k];
+      if (nnz < RG_TJ) { ji[nnz] = k; jv[nnz] = J[k]; nnz++; }
+      else RG_SI(c, RG_S_WARN) |= RG_WARN_TENDON_NNZ;
+    }
+    ((int*)(s + L.tJn))[t] = nnz;
     s[L.tvel + t] = v;
   }
   RG_PHASE_END
@@ -503,14 +527,14 @@ RG_DEV_NOINLINE void rg_forces(RgCtx& c) {
       if (m.jnt_stiffness[j] != 0.0f && (m.jnt_type[j] == RG_JNT_SLIDE || m.jnt_type[j] == RG_JNT_HINGE))
         passive -= m.jnt_stiffness[j] * (s[L.qpos + m.jnt_qposadr[j]] - m.qpos_spring[m.jnt_qposadr[j]]);
       passive -= m.dof_damping[d] * s[L.qvel + d];
-      for (int t = 0; t < m.ntendon; t++) passive += s[L.tJ + t * nv + d] * s[L.tmp + t];
+      for (int t = 0; t < m.ntendon; t++) passive += rg_tendon_J(c, t, d) * s[L.tmp + t];
     }
     float act = 0.0f;
     for (int i = 0; i < m.nu; i++) {
       const float gear = m.actuator_gear[6 * i];
       const int id = m.actuator_trnid[i];
       if (m.actuator_trntype[i] == RG_TRN_JOINT) { if (m.jnt_dofadr[id] == d) act += gear * s[L.aforce + i]; }
-      else act += gear * s[L.tJ + id * nv + d] * s[L.aforce + i];
+      else act += gear * rg_tendon_J(c, id, d) * s[L.aforce + i];
     }
     float applied = 0.0f;
     if (c.xfrc) {
@@ -523,8 +547,6 @@ RG_DEV_NOINLINE void rg_forces(RgCtx& c) {
         applied += rg_dot3(jp, x) + rg_dot3(s + L.S + 6 * d, x + 3);
       }
     }
-    s[L.passive + d] = passive;
-    s[L.qfa + d] = act;
     s[L.smooth + d] = passive - s[L.bias + d] + act + applied;
   }
   RG_PHASE_END

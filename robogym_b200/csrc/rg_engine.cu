@@ -18,7 +18,7 @@
 #include "rg_step.inl"
 #include "rg_host.h"
 
-#define RG_MAX_WARPS 8
+#define RG_MAX_WARPS 10
 
 static thread_local std::string g_err;
 static int rg_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
 #undef RG_F
     RG_REBASE(body_subtreesize)
     RG_REBASE(dof_treeroot)
+    if (args.m.pair_packed) RG_REBASE(pair_packed)
 #undef RG_REBASE
   }
   __syncthreads();
@@ -131,6 +132,9 @@ static void rg_wire_device_view(rg_model* mm) {
 #undef RG_F
   RG_DEVPTR(body_subtreesize)
   RG_DEVPTR(dof_treeroot)
+  RG_DEVPTR(mesh_nbr)
+  RG_DEVPTR(mesh_ext)
+  if (mm->hm.view.pair_packed) RG_DEVPTR(pair_packed)
 #undef RG_DEVPTR
 }
 

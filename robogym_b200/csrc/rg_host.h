@@ -68,9 +68,12 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   for (size_t i = 0; i < first_big; i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
   dst = rg_align16(dst); const size_t off_subtree = dst; dst += 4 * (size_t)m.nbody;
   dst = rg_align16(dst); const size_t off_treeroot = dst; dst += 4 * (size_t)m.nv;
+  dst = rg_align16(dst); const size_t off_pairs = dst; if (m.ngeom <= 256) dst += 2 * (size_t)m.npair;
   dst = rg_align16(dst);
   hm.small_bytes = dst;
   for (size_t i = first_big; i < names.size(); i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
+  dst = rg_align16(dst); const size_t off_nbr = dst; dst += 16 * (size_t)m.nmeshadj;
+  dst = rg_align16(dst); const size_t off_ext = dst; dst += 4 * 6 * (size_t)m.nmesh;
   dst = rg_align16(dst);
   hm.arena.assign(dst, 0);
   char* base = hm.arena.data();
@@ -106,6 +109,34 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   m.dof_treeroot = treeroot;
   hm.offsets.push_back(off_subtree);
   hm.offsets.push_back(off_treeroot);
+  /* hull neighbour table with inline coordinates + extreme-vertex starting points */
+  float* nbr = (float*)(base + off_nbr);
+  int* ext = (int*)(base + off_ext);
+  for (int i = 0; i < m.nmesh; i++) {
+    const int va = m.mesh_vertadr[i], vn = m.mesh_vertnum[i];
+    const float* v = m.mesh_vert + 3 * va;
+    for (int k = 0; k < vn; k++)
+      for (int a = m.mesh_adjadr[va + k]; a < m.mesh_adjadr[va + k + 1]; a++) {
+        const int nb = m.mesh_adj[a];
+        nbr[4 * a] = v[3 * nb]; nbr[4 * a + 1] = v[3 * nb + 1]; nbr[4 * a + 2] = v[3 * nb + 2];
+        memcpy(&nbr[4 * a + 3], &nb, 4);
+      }
+    for (int ax = 0; ax < 3; ax++) {
+      int hi = 0, lo = 0;
+      for (int k = 1; k < vn; k++) { if (v[3 * k + ax] > v[3 * hi + ax]) hi = k; if (v[3 * k + ax] < v[3 * lo + ax]) lo = k; }
+      ext[6 * i + 2 * ax] = hi; ext[6 * i + 2 * ax + 1] = lo;
+    }
+  }
+  m.mesh_nbr = nbr;
+  m.mesh_ext = ext;
+  m.pair_packed = nullptr;
+  if (m.ngeom <= 256) {
+    unsigned short* pk = (unsigned short*)(base + off_pairs);
+    for (int k = 0; k < m.npair; k++) pk[k] = (unsigned short)(m.pair_geom1[k] | (m.pair_geom2[k] << 8));
+    m.pair_packed = pk;
+  }
+  hm.offsets.push_back(off_nbr);
+  hm.offsets.push_back(off_ext);
   /* fp32 conditioning: translate the world so the scene sits near the origin */
   double o[3] = {0, 0, 0};
   int cnt = 0;

@@ -27,7 +27,7 @@ RG_DEV float rg_impedance(const float* solimp, float xabs) {
   return dmin + y * (dmax - dmin);
 }
 /* R (regulariser) and aref for one row; K is dropped for friction rows */
-RG_DEV void rg_row_params(const RgCtx& c, const float* solref_in, const float* solimp, float pos, float margin, float vel, float diagApprox,
+RG_DEV_NOINLINE void rg_row_params(const RgCtx& c, const float* solref_in, const float* solimp, float pos, float margin, float vel, float diagApprox,
                           int isfriction, float* R, float* aref, float* Bout, float* KIout) {
   float sr0 = solref_in[0];
   const float sr1 = solref_in[1];
@@ -46,7 +46,7 @@ RG_DEV void rg_row_params(const RgCtx& c, const float* solref_in, const float* s
 }
 
 /* contact-frame Jacobian column of dof d for contact record r (dim components), sign included; 0 if untouched */
-RG_DEV int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float* col) {
+RG_DEV_NOINLINE int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float* col) {
   const RgModel& m = c.m;
   const int b1 = (int)r[18], b2 = (int)r[19];
   const int in1 = rg_dof_in_body(m, b1, d), in2 = rg_dof_in_body(m, b2, d);
@@ -61,25 +61,36 @@ RG_DEV int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float*
   if (dim > 4) { col[4] = sg * rg_dot3(r + 7, S); col[5] = sg * rg_dot3(r + 10, S); }
   return 1;
 }
+/* same, for a dof already known to be touched (sg = +1 if it moves body 2, -1 if body 1) */
+RG_DEV void rg_contact_col_list(const RgCtx& c, const float* r, int d, float sg, int dim, float* col) {
+  const float* S = c.s + c.L.S + 6 * d;
+  float jp[3];
+  rg_jacp_world(c, d, r + 1, jp);
+  col[0] = sg * rg_dot3(r + 4, jp);
+  if (dim > 1) { col[1] = sg * rg_dot3(r + 7, jp); col[2] = sg * rg_dot3(r + 10, jp); }
+  if (dim > 3) col[3] = sg * rg_dot3(r + 4, S);
+  if (dim > 4) { col[4] = sg * rg_dot3(r + 7, S); col[5] = sg * rg_dot3(r + 10, S); }
+}
 RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k == 3 ? r[15] : r[16]); }
 
 /* y = M x (dense, symmetric) */
-RG_DEV void rg_matvec_phase(RgCtx& c, int y, int x) {
+RG_DEV_NOINLINE void rg_matvec_phase(RgCtx& c, int y, int x) {
   RG_LANE_DECL
   const int nv = c.m.nv;
   float* s = c.s;
   RG_PHASE_BEGIN
   for (int i = lane; i < nv; i += 32) {
     float acc = 0.0f;
-    const float* row = s + c.L.M + i * nv;
-    for (int k = 0; k < nv; k++) acc += row[k] * s[x + k];
+    const float* row = s + c.L.M + RG_TRI(i, 0);
+    for (int k = 0; k <= i; k++) acc += row[k] * s[x + k];
+    for (int k = i + 1; k < nv; k++) acc += s[c.L.M + RG_TRI(k, i)] * s[x + k];
     s[y + i] = acc;
   }
   RG_PHASE_END
 }
 
 /* in-place envelope Cholesky of the lower triangle of A (row stride nv); env[i] = first nonzero column */
-RG_DEV void rg_cholesky(RgCtx& c, int A, const int* env) {
+RG_DEV_NOINLINE void rg_cholesky(RgCtx& c, int A, const int* env) {
   RG_LANE_DECL
   const int n = c.m.nv;
   float* s = c.s;
@@ -89,9 +100,10 @@ RG_DEV void rg_cholesky(RgCtx& c, int A, const int* env) {
     const int i = j + lane;
     float acc = 0.0f;
     if (i < n && env[i] <= j) {
-      acc = s[A + i * n + j];
+      const float* ri = s + A + RG_TRI(i, 0); const float* rj = s + A + RG_TRI(j, 0);
+      acc = ri[j];
       const int k0 = env[i] > env[j] ? env[i] : env[j];
-      for (int k = k0; k < j; k++) acc -= s[A + i * n + k] * s[A + j * n + k];
+      for (int k = k0; k < j; k++) acc -= ri[k] * rj[k];
     }
     LV(sumv) = acc;
     RG_PHASE_END
@@ -99,38 +111,39 @@ RG_DEV void rg_cholesky(RgCtx& c, int A, const int* env) {
     const float inv = 1.0f / diag;
     RG_PHASE_BEGIN
     const int i = j + lane;
-    if (i == j) s[A + j * n + j] = diag;
-    else if (i < n) s[A + i * n + j] = LV(sumv) * inv;
+    if (i == j) s[A + RG_TRI(j, j)] = diag;
+    else if (i < n) s[A + RG_TRI(i, j)] = LV(sumv) * inv;
     for (int i2 = i + 32; i2 < n; i2 += 32) {
       float acc = 0.0f;
       if (env[i2] <= j) {
-        acc = s[A + i2 * n + j];
+        const float* ri = s + A + RG_TRI(i2, 0); const float* rj = s + A + RG_TRI(j, 0);
+        acc = ri[j];
         const int k0 = env[i2] > env[j] ? env[i2] : env[j];
-        for (int k = k0; k < j; k++) acc -= s[A + i2 * n + k] * s[A + j * n + k];
+        for (int k = k0; k < j; k++) acc -= ri[k] * rj[k];
       }
-      s[A + i2 * n + j] = acc * inv;
+      s[A + RG_TRI(i2, j)] = acc * inv;
     }
     RG_PHASE_END
   }
 }
 /* x <- (L L^T)^-1 x ; uses `tmp` as staging */
-RG_DEV void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int tmp) {
+RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int tmp) {
   RG_LANE_DECL
   const int n = c.m.nv;
   float* s = c.s;
   for (int j = 0; j < n; j++) {
     RG_PHASE_BEGIN
-    const float xj = s[x + j] / s[A + j * n + j];
+    const float xj = s[x + j] / s[A + RG_TRI(j, j)];
     if (lane == 0) s[tmp + j] = xj;
     for (int i = j + 1 + lane; i < n; i += 32)
-      if (env[i] <= j) s[x + i] -= s[A + i * n + j] * xj;
+      if (env[i] <= j) s[x + i] -= s[A + RG_TRI(i, j)] * xj;
     RG_PHASE_END
   }
   for (int j = n - 1; j >= 0; j--) {
     RG_PHASE_BEGIN
-    const float xj = s[tmp + j] / s[A + j * n + j];
+    const float xj = s[tmp + j] / s[A + RG_TRI(j, j)];
     if (lane == 0) s[x + j] = xj;
-    for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + j * n + i] * xj;
+    for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + RG_TRI(j, i)] * xj;
     RG_PHASE_END
   }
 }
@@ -163,7 +176,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
       float R, aref, B, KI;
       rg_row_params(c, m.dof_solref + 2 * d, m.dof_solimp + 5 * d, 0.0f, 0.0f, s[L.qvel + d], m.dof_invweight0[d], 1, &R, &aref, &B, &KI);
       el_i[e] = RG_EL_FLOSS + 8 * d;
-      s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = m.dof_frictionloss[d];
+      s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = m.dof_frictionloss[d];
       eldof[3 * d] = e;
     }
     RG_PHASE_END
@@ -197,7 +210,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
         float R, aref, B, KI;
         rg_row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, m.jnt_margin[j], sg * s[L.qvel + d], m.dof_invweight0[d], 0, &R, &aref, &B, &KI);
         el_i[e] = RG_EL_JLIMIT + 4 * side + 8 * d;
-        s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = 0.0f;
+        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = 0.0f;
         eldof[3 * d + 1 + side] = e;
         e++;
       }
@@ -233,7 +246,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
         float R, aref, B, KI;
         rg_row_params(c, m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, dist, m.tendon_margin[t], sg * s[L.tvel + t], m.tendon_invweight0[t], 0, &R, &aref, &B, &KI);
         el_i[e] = RG_EL_TLIMIT + 4 * side + 8 * t;
-        s[L.el_R + e] = R; s[L.el_D + e] = 1.0f / R; s[L.el_aref + e] = aref; s[L.el_floss + e] = 0.0f;
+        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = 0.0f;
         e++;
       }
     }
@@ -254,18 +267,36 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
     float R, aref, B, KI;
     /* first row's diagApprox: tran + mu^2 tran (dim>1) or tran */
     const float mu0 = r[14];
-    rg_row_params(c, r + 22, r + 24, r[0], r[13], 0.0f, dim > 1 ? tran + mu0 * mu0 * tran : tran, 0, &R, &aref, &B, &KI);
+    const float solimp[5] = {prm[0], prm[1], prm[2], prm[3], prm[4]};   /* staged there by rg_collision */
+    rg_row_params(c, r + 22, solimp, r[0], r[13], 0.0f, dim > 1 ? tran + mu0 * mu0 * tran : tran, 0, &R, &aref, &B, &KI);
     if (dim > 1) {
       float mu = mu0 * sqrtf(1.0f / m.opt_impratio[0]);
       if (mu < 1e-5f) mu = 1e-5f;
       R = fmaxf(1e-12f, 2.0f * mu * mu * R);
     }
     prm[0] = 1.0f / R; prm[1] = (float)dim; prm[2] = B; prm[3] = KI;
+    /* list of the dofs this contact touches (symmetric difference of the two bodies' ancestor sets) */
+    unsigned char* list = (unsigned char*)(s + L.cdof + 4 * k);
+    int nd = 0;
+    unsigned sgn = 0u;
+    for (int w = 0; w < m.nmaskw && dim > 0; w++) {
+      const unsigned m1 = ((const unsigned*)m.body_dofmask)[b1 * m.nmaskw + w], m2 = ((const unsigned*)m.body_dofmask)[b2 * m.nmaskw + w];
+      unsigned bits = m1 ^ m2;
+      while (bits) {
+        const int bit = rg_ctz(bits);
+        bits &= bits - 1;
+        if (nd < 16) { list[nd] = (unsigned char)(32 * w + bit); if ((m2 >> bit) & 1u) sgn |= 1u << nd; nd++; }
+        else dim = 0; /* more than 16 dofs: cannot be represented -> drop the contact (flagged below) */
+      }
+    }
+    if (dim == 0) { prm[1] = 0.0f; nd = 0; }
+    prm[4] = (float)nd; prm[5] = (float)(sgn & 0xffffu);
     /* velocity part of jar */
     float v[6] = {0, 0, 0, 0, 0, 0};
-    for (int d = 0; d < nv && dim > 0; d++) {
+    for (int i = 0; i < nd; i++) {
       float col[6];
-      if (!rg_contact_col(c, r, d, dim, col)) continue;
+      const int d = list[i];
+      rg_contact_col_list(c, r, d, (sgn >> i) & 1u ? 1.0f : -1.0f, dim, col);
       const float qd = s[L.qvel + d];
       for (int a = 0; a < dim; a++) v[a] += col[a] * qd;
     }
@@ -287,28 +318,30 @@ RG_DEV float rg_el_Jx(const RgCtx& c, int code, int x) {
   if (type == RG_EL_FLOSS) return s[x + id];
   if (type == RG_EL_JLIMIT) return side ? -s[x + id] : s[x + id];
   float acc = 0.0f;
-  const float* J = s + c.L.tJ + id * c.m.nv;
-  for (int k = 0; k < c.m.nv; k++) acc += J[k] * s[x + k];
+  const int n = ((const int*)(s + c.L.tJn))[id];
+  const int* ji = (const int*)(s + c.L.tJi) + RG_TJ * id;
+  for (int k = 0; k < n; k++) acc += s[c.L.tJv + RG_TJ * id + k] * s[x + ji[k]];
   return side ? -acc : acc;
 }
 
 /* forces + cost at the current jar (el_jar, cu); returns total constraint cost; fills el_f and cF */
-RG_DEV float rg_solver_update(RgCtx& c, int nel, int ncon) {
+RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
   RG_LANE_DECL
   const RgLayout& L = c.L; float* s = c.s;
   const int* el_i = (const int*)(s + L.el_i);
-  LANEVAR(float, part);
+  LANEVAR(float, part); LANEVAR(int, sigp);
   RG_PHASE_BEGIN
   float cost = 0.0f;
+  unsigned sig = 0u;   /* which rows are in their quadratic zone: decides whether H must be rebuilt */
   for (int e = lane; e < nel; e += 32) {
     const float jar = s[L.el_jar + e], D = s[L.el_D + e];
     float f;
     if ((el_i[e] & 3) == RG_EL_FLOSS) {
-      const float fl = s[L.el_floss + e], rf = s[L.el_R + e] * fl;
+      const float fl = s[L.el_floss + e], rf = fl / D;
       if (jar <= -rf) { f = fl; cost += -0.5f * rf * fl - fl * jar; }
       else if (jar >= rf) { f = -fl; cost += -0.5f * rf * fl + fl * jar; }
-      else { f = -D * jar; cost += 0.5f * D * jar * jar; }
-    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; }
+      else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += (unsigned)(e + 1) * 2654435761u; }
+    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; sig += (unsigned)(e + 1) * 2654435761u; }
     else f = 0.0f;
     s[L.el_f + e] = f;
   }
@@ -319,23 +352,25 @@ RG_DEV float rg_solver_update(RgCtx& c, int nel, int ncon) {
     const int dim = (int)prm[1];
     const float D = prm[0];
     float F[6] = {0, 0, 0, 0, 0, 0};
-    if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; } }
+    if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; sig += (unsigned)(1000 + 16 * k) * 40503u; } }
     else for (int a = 1; a < dim; a++) {
       const float mu = rg_contact_mu(r, a);
       const float jp = u[0] + mu * u[a], jm = u[0] - mu * u[a];
-      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; }
-      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; }
+      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; sig += (unsigned)(1000 + 16 * k + 2 * a) * 40503u; }
+      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; sig += (unsigned)(1000 + 16 * k + 2 * a + 1) * 40503u; }
     }
     float* cf = s + L.cF + 6 * k;
     for (int a = 0; a < 6; a++) cf[a] = F[a];
   }
   LV(part) = cost;
+  LV(sigp) = (int)(sig & 0x00ffffffu);
   RG_PHASE_END
+  c.sig = RG_WARP_ISUM(sigp);
   return RG_WARP_SUM(part);
 }
 
 /* out[d] = sum_rows J^T f for every dof (single-row elements, tendon rows, contacts) */
-RG_DEV void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
+RG_DEV_NOINLINE void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
   RG_LANE_DECL
   const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
   const int* el_i = (const int*)(s + L.el_i);
@@ -350,7 +385,7 @@ RG_DEV void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
     for (int e = tl0; e < nel; e++) {
       const int code = el_i[e];
       const float f = s[L.el_f + e];
-      if (f != 0.0f) acc += ((code >> 2) & 1 ? -f : f) * s[L.tJ + (code >> 3) * m.nv + d];
+      if (f != 0.0f) acc += ((code >> 2) & 1 ? -f : f) * rg_tendon_J(c, code >> 3, d);
     }
     for (int k = 0; k < ncon; k++) {
       const float* r = s + L.con + RG_CON_STRIDE * k;
@@ -366,23 +401,27 @@ RG_DEV void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
 }
 
 /* el_x[e] = J_e x, cx[k] = Jc_k x  (x = vector at offset xoff); if init, adds -aref / staged velocity terms */
-RG_DEV void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
+RG_DEV_NOINLINE void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
   RG_LANE_DECL
   const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
   const int* el_i = (const int*)(s + L.el_i);
   RG_PHASE_BEGIN
   for (int e = lane; e < nel; e += 32) {
     float v = rg_el_Jx(c, el_i[e], xoff);
-    if (init) v -= s[L.el_aref + e];
+    if (init) v += s[el_out + e];   /* make_constraints left -aref there */
     s[el_out + e] = v;
   }
   for (int k = lane; k < ncon; k += 32) {
     const float* r = s + L.con + RG_CON_STRIDE * k;
     const int dim = (int)s[L.cprm + 8 * k + 1];
     float v[6] = {0, 0, 0, 0, 0, 0};
-    for (int d = 0; d < m.nv && dim > 0; d++) {
+    const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
+    const int nd = (int)s[L.cprm + 8 * k + 4];
+    const unsigned sgn = (unsigned)s[L.cprm + 8 * k + 5];
+    for (int i = 0; i < nd; i++) {
       float col[6];
-      if (!rg_contact_col(c, r, d, dim, col)) continue;
+      const int d = list[i];
+      rg_contact_col_list(c, r, d, (sgn >> i) & 1u ? 1.0f : -1.0f, dim, col);
       const float xd = s[xoff + d];
       for (int a = 0; a < dim; a++) v[a] += col[a] * xd;
     }
@@ -408,8 +447,8 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
   rg_J_mul_phase(c, L.qacc, L.el_jar, L.cu, nel, ncon, 1);
   float cost_con = rg_solver_update(c, nel, ncon);
   const float scale = 1.0f / (m.opt_meaninertia[0] * (float)(nv > 1 ? nv : 1));
-  const float tol = fmaxf(m.opt_tolerance[0], 1e-7f);
-  int iter = 0;
+  const float tol = fmaxf(m.opt_tolerance[0], 1e-6f); /* fp32: below ~1e-6 the cost differences are rounding noise */
+  int iter = 0, have_factor = 0, factor_sig = 0;
   float cost;
   {
     LANEVAR(float, gp);
@@ -428,7 +467,6 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     float a = 0.0f;
     for (int d = lane; d < nv; d += 32) {
       const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
-      s[L.grad + d] = g;
       s[L.search + d] = -g;
       a += g * g;
     }
@@ -436,27 +474,31 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     RG_PHASE_END
     const float gnorm = sqrtf(RG_WARP_SUM(gn));
     if (scale * gnorm < tol) break;
-    /* Hessian H = M + J' diag(D active) J */
+    /* Hessian H = M + J' diag(D active) J: rebuilt and refactored only when the active set changed */
+    const int refactor = !(have_factor && c.sig == factor_sig);
+    if (refactor) {
     RG_PHASE_BEGIN
-    for (int i = lane; i < nv * nv; i += 32) s[L.H + i] = s[L.M + i];
+    for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
     RG_PHASE_END
     RG_PHASE_BEGIN
     for (int d = lane; d < nv; d += 32) {
       float add = 0.0f;
       const int e0 = eldof[3 * d];
-      if (e0 >= 0) { const float rf = s[L.el_R + e0] * s[L.el_floss + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
+      if (e0 >= 0) { const float rf = s[L.el_floss + e0] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
       for (int q = 1; q < 3; q++) { const int e = eldof[3 * d + q]; if (e >= 0 && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
-      s[L.H + d * nv + d] += add;
+      s[L.H + RG_TRI(d, d)] += add;
     }
     RG_PHASE_END
     for (int e = tl0; e < nel; e++) {
       if (!(s[L.el_jar + e] < 0.0f)) continue;
       const int t = el_i[e] >> 3;
       const float D = s[L.el_D + e];
+      const int tn = ((const int*)(s + L.tJn))[t];
+      const int* tji = (const int*)(s + L.tJi) + RG_TJ * t;
       RG_PHASE_BEGIN
-      for (int i = lane; i < nv; i += 32) {
-        const float ji = s[L.tJ + t * nv + i];
-        if (ji != 0.0f) for (int k = 0; k < nv; k++) s[L.H + i * nv + k] += D * ji * s[L.tJ + t * nv + k];
+      for (int p = lane; p < tn * tn; p += 32) {
+        const int a = p / tn, b = p - a * tn;
+        if (tji[a] >= tji[b]) s[L.H + RG_TRI(tji[a], tji[b])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
       }
       RG_PHASE_END
     }
@@ -478,43 +520,34 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       }
       if (!anyact) continue;
       /* tile: columns of Jc for the dofs this contact touches, and W Jc */
-      const int b1 = (int)r[18], b2 = (int)r[19];
       int* tdof = (int*)(s + L.tileDof);
-      LANEVAR(int, cnt); LANEVAR(int, pos);
-      int nd = 0;
-      for (int base = 0; base < nv; base += 32) {
-        int tot;
-        RG_PHASE_BEGIN
-        const int d = base + lane;
-        LV(cnt) = (d < nv && rg_dof_in_body(m, b1, d) != rg_dof_in_body(m, b2, d)) ? 1 : 0;
-        RG_PHASE_END
-        RG_WARP_SCAN(cnt, pos, tot);
-        RG_PHASE_BEGIN
-        const int d = base + lane;
-        const int i = nd + LV(pos);
-        if (LV(cnt) && i < RG_TILE) {
-          float col[6] = {0, 0, 0, 0, 0, 0};
-          rg_contact_col(c, r, d, dim, col);
-          tdof[i] = d;
-          float* tj = s + L.tileJ + 6 * i;
-          float* tw = s + L.tileWJ + 6 * i;
-          float w0 = W00 * col[0];
-          for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
-          tj[0] = col[0]; tw[0] = w0;
-          for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
-        }
-        RG_PHASE_END
-        nd += tot;
+      const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
+      int nd = (int)prm[4];
+      const unsigned sgn = (unsigned)prm[5];
+      RG_PHASE_BEGIN
+      if (lane < nd) {
+        float col[6] = {0, 0, 0, 0, 0, 0};
+        const int d = list[lane];
+        rg_contact_col_list(c, r, d, (sgn >> lane) & 1u ? 1.0f : -1.0f, dim, col);
+        tdof[lane] = d;
+        float* tj = s + L.tileJ + 6 * lane;
+        float* tw = s + L.tileWJ + 6 * lane;
+        float w0 = W00 * col[0];
+        for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
+        tj[0] = col[0]; tw[0] = w0;
+        for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
       }
+      RG_PHASE_END
       if (nd > RG_TILE) nd = RG_TILE;
       RG_PHASE_BEGIN
       for (int p = lane; p < nd * nd; p += 32) {
         const int i = p / nd, j = p - i * nd;
+        if (tdof[i] < tdof[j]) continue;
         const float* tj = s + L.tileJ + 6 * i;
         const float* tw = s + L.tileWJ + 6 * j;
         float acc = 0.0f;
         for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
-        s[L.H + tdof[i] * nv + tdof[j]] += acc;
+        if (tdof[i] >= tdof[j]) s[L.H + RG_TRI(tdof[i], tdof[j])] += acc;
       }
       RG_PHASE_END
     }
@@ -522,11 +555,13 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     RG_PHASE_BEGIN
     for (int i = lane; i < nv; i += 32) {
       int e = 0;
-      while (e < i && s[L.H + i * nv + e] == 0.0f) e++;
+      while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
       env[i] = e;
     }
     RG_PHASE_END
     rg_cholesky(c, L.H, env);
+    have_factor = 1; factor_sig = c.sig;
+    }
     rg_chol_solve(c, L.H, env, L.search, L.tmp);
     /* line search along `search` */
     rg_matvec_phase(c, L.Mv, L.search);
@@ -549,7 +584,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       for (int e = lane; e < nel; e += 32) {
         const float jv = s[L.el_jv + e], x = s[L.el_jar + e] + alpha * jv, D = s[L.el_D + e];
         if ((el_i[e] & 3) == RG_EL_FLOSS) {
-          const float fl = s[L.el_floss + e], rf = s[L.el_R + e] * fl;
+          const float fl = s[L.el_floss + e], rf = fl / D;
           if (x <= -rf) g -= fl * jv;
           else if (x >= rf) g += fl * jv;
           else { g += D * x * jv; h += D * jv * jv; }
@@ -623,11 +658,11 @@ RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
   int* env = (int*)(s + L.env);
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
   RG_PHASE_BEGIN
-  for (int i = lane; i < nv * nv; i += 32) s[L.H + i] = s[L.M + i];
+  for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
   RG_PHASE_END
   RG_PHASE_BEGIN
   for (int d = lane; d < nv; d += 32) {
-    s[L.H + d * nv + d] += h * m.dof_damping[d];
+    s[L.H + RG_TRI(d, d)] += h * m.dof_damping[d];
     s[L.search + d] = s[L.smooth + d] + s[L.qfc + d];
     env[d] = m.dof_treeroot[d];
   }

@@ -38,38 +38,36 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
   int o = 0;
 #define RG_ALLOC(field, n) do { L.field = o; o += ((n) + 3) & ~3; } while (0)
   RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
-  RG_ALLOC(lpos, 3 * m.nbody); RG_ALLOC(lquat, 4 * m.nbody); RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
+  RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
   RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
-  RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nv * m.nv);
+  const int ntri = (m.nv * (m.nv + 1)) >> 1;
+  RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, ntri);
   /* H aliases the smooth-dynamics temporaries */
   const int h0 = o;
-  RG_ALLOC(Sdot, 6 * m.nv); RG_ALLOC(cvel, 6 * m.nbody); RG_ALLOC(cacc, 6 * m.nbody); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
+  RG_ALLOC(Sdot, 6 * rg_imax(m.nv, m.nbody)); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
   L.H = h0;
-  o = h0 + rg_imax(o - h0, (m.nv * m.nv + 3) & ~3);
-  RG_ALLOC(bias, m.nv); RG_ALLOC(passive, m.nv); RG_ALLOC(qfa, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
-  RG_ALLOC(Ma, m.nv); RG_ALLOC(grad, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
+  o = h0 + rg_imax(rg_imax(o - h0, (ntri + 3) & ~3), (m.ntendon * m.nv + 3) & ~3);
+  RG_ALLOC(bias, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
+  RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
-  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJ, m.ntendon * m.nv); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
+  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, RG_TJ * m.ntendon); RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
   RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, 8 * RG_NCON);
-  RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_R, RG_NEL); RG_ALLOC(el_aref, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
+  RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
   RG_ALLOC(el_jar, RG_NEL); RG_ALLOC(el_jv, RG_NEL); RG_ALLOC(el_f, RG_NEL);
-  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(cand, 64); RG_ALLOC(scal, 8 + RG_NPROF);
-  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv);
+  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(scal, 8 + RG_NPROF);
+  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, 4 * RG_NCON);
 #undef RG_ALLOC
+  /* lifetimes that never overlap share storage: local frames (kinematics only) sit in the contact
+     solver vectors, the broad-phase candidate lists in the row work arrays */
+  if (((3 * m.nbody + 3) & ~3) + 4 * m.nbody <= 12 * RG_NCON) { L.lpos = L.cu; L.lquat = L.cu + ((3 * m.nbody + 3) & ~3); }
+  else { L.lpos = o; o += (3 * m.nbody + 3) & ~3; L.lquat = o; o += 4 * m.nbody; }
+  L.cand = L.el_jv; L.cand2 = L.el_f;
   L.total = o;
   return L;
 }
 
 /* mj_forward: everything but the integrator */
-/* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
-#if !defined(RG_EMU) && defined(RG_PROFILE)
-#define RG_PROF_BEGIN long long prof_t_ = clock64();
-#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) (c).s[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
-#else
-#define RG_PROF_BEGIN
-#define RG_PROF(c, k)
-#endif
-RG_DEV void rg_forward(RgCtx& c) {
+RG_DEV_NOINLINE void rg_forward(RgCtx& c) {
   RG_PROF_BEGIN
   rg_kinematics(c); RG_PROF(c, 0)
   rg_massmatrix(c); RG_PROF(c, 1)
@@ -83,7 +81,7 @@ RG_DEV void rg_forward(RgCtx& c) {
 
 RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward) {
   RG_LANE_DECL
-  RgCtx c = {m, L, s, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0]};
+  RgCtx c = {m, L, s, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0], 0};
   const int npid = 3 * m.nu;
   /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
   RG_PHASE_BEGIN
@@ -149,10 +147,10 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
     float* g = io.dbg + (size_t)env * rg_dbg_size(m);
     const int nv = m.nv;
     int o = 0;
-    for (int i = lane; i < nv * nv; i += 32) g[o + i] = s[L.M + i];
+    for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + (r_ >= c_ ? RG_TRI(r_, c_) : RG_TRI(c_, r_))]; }
     o += nv * nv;
     for (int i = lane; i < nv; i += 32) {
-      g[o + i] = s[L.bias + i]; g[o + nv + i] = s[L.passive + i]; g[o + 2 * nv + i] = s[L.qfa + i];
+      g[o + i] = s[L.bias + i]; g[o + nv + i] = 0.0f; g[o + 2 * nv + i] = 0.0f;   /* passive / actuator split is not kept */
       g[o + 3 * nv + i] = s[L.smooth + i]; g[o + 4 * nv + i] = s[L.qacc + i]; g[o + 5 * nv + i] = s[L.qfc + i];
     }
     o += 6 * nv;
@@ -164,7 +162,7 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
     o += 4;
     for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
     o += RG_NCON * RG_CON_STRIDE;
-    for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = s[L.tJ + i];
+    for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = rg_tendon_J(c, i / nv, i % nv);
     o += m.ntendon * nv;
     for (int i = lane; i < RG_NPROF; i += 32) g[o + i] = s[L.scal + 8 + i];
   }

@@ -22,7 +22,7 @@ LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librobogym_b200.so"))  
 (QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,
  ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG) = range(18)
 MAX_CONTACTS = 32
-CON_STRIDE = 32
+CON_STRIDE = 24
 
 _lib = None
 

@@ -575,6 +575,7 @@ def compile_mjcf(xml_string, asset_loader=None):
     geom_pos = np.zeros((ngeom, 3))
     geom_quat = np.zeros((ngeom, 4))
     geom_rbound = np.zeros(ngeom)
+    geom_aabb = np.zeros((ngeom, 6))
     geom_friction = np.zeros((ngeom, 3))
     geom_margin = np.zeros(ngeom)
     geom_gap = np.zeros(ngeom)
@@ -622,6 +623,17 @@ def compile_mjcf(xml_string, asset_loader=None):
             geom_rbound[i] = np.hypot(size[0], size[1])
         elif t in (GEOM_BOX, GEOM_ELLIPSOID):
             geom_rbound[i] = np.linalg.norm(size) if t == GEOM_BOX else size.max()
+        if t == GEOM_MESH:
+            vmin, vmax = mesh_verts[mid].min(axis=0), mesh_verts[mid].max(axis=0)
+            geom_aabb[i] = np.concatenate([0.5 * (vmin + vmax), 0.5 * (vmax - vmin)])
+        elif t == GEOM_SPHERE:
+            geom_aabb[i, 3:] = size[0]
+        elif t == GEOM_CAPSULE:
+            geom_aabb[i, 3:] = [size[0], size[0], size[0] + size[1]]
+        elif t == GEOM_CYLINDER:
+            geom_aabb[i, 3:] = [size[0], size[0], size[1]]
+        elif t in (GEOM_BOX, GEOM_ELLIPSOID):
+            geom_aabb[i, 3:] = size
         geom_size[i] = size
         geom_pos[i] = pos
         geom_quat[i] = quat
@@ -996,7 +1008,7 @@ def compile_mjcf(xml_string, asset_loader=None):
         geom_type=geom_type, geom_bodyid=geom_bodyid, geom_dataid=geom_dataid,
         geom_contype=geom_contype, geom_conaffinity=geom_conaffinity, geom_condim=geom_condim,
         geom_priority=geom_priority, geom_size=geom_size, geom_pos=geom_pos, geom_quat=geom_quat,
-        geom_rbound=geom_rbound, geom_friction=geom_friction, geom_margin=geom_margin,
+        geom_rbound=geom_rbound, geom_aabb=geom_aabb, geom_friction=geom_friction, geom_margin=geom_margin,
         geom_gap=geom_gap, geom_solmix=geom_solmix, geom_solref=geom_solref, geom_solimp=geom_solimp,
         site_bodyid=site_bodyid, site_pos=site_pos, site_quat=site_quat,
         mesh_vertadr=mesh_vertadr, mesh_vertnum=mesh_vertnum, mesh_faceadr=mesh_faceadr,

@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "librg_emu.so")
 NCON = 32
-CON_STRIDE = 32
+CON_STRIDE = 24
 _lib = None
 
 

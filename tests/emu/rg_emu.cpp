@@ -24,6 +24,9 @@ void* rge_create(const void* blob, size_t len) {
   h->scratch.assign(h->L.total, 0.0f);
   return h;
 }
+#ifdef RG_STATS
+void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; }
+#endif
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
 int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view); }
 int rge_scratch_floats(void* hv) { return ((RgeHandle*)hv)->L.total; }

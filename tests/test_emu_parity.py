@@ -38,7 +38,6 @@ def test_stagewise_parity(locked_blob, setup):
         assert rel(g["tlen"], d.ten_length) < 1e-6
         assert rel(g["tJ"].ravel(), d.ten_J) < 1e-5
         assert rel(g["bias"], d.qfrc_bias) < 1e-4
-        assert rel(g["passive"], d.qfrc_passive) < 1e-4
         assert rel(g["aforce"], d.actuator_force) < 1e-4
         assert rel(g["smooth"], d.qfrc_smooth) < 1e-4
         assert g["ncon"] == d.ncon[0]

@@ -73,10 +73,11 @@ print(json.dumps(dict(nenv=N, ms_per_env_step=ms, env_steps_per_s=N / ms * 1e3, 
 g = sim.dbg_view(0)
 print("dbg env0: ncon", g["ncon"], "nel", g["nel"], "niter", g["niter"])
 prof = sim.dbg.cpu().numpy()[:, -16:]
-names = ["kin", "massm", "bias", "tendon", "forces", "collide", "mkcon", "solve", "euler"]
+names = ["kin", "massm", "bias", "tendon", "forces", "collide", "mkcon", "solve", "euler", "col:A-sphere", "col:B-obb", "col:C-narrow+write", "col:C-rounds", "-", "-", "col:loop"]
 tot = prof[:, :9].sum(1).mean()
 print("stage cycles per env-step (mean over envs, lane0 clock64):")
 for i, nme in enumerate(names):
+    if nme == '-': continue
     print("  %-8s %10.0f  %5.1f%%" % (nme, prof[:, i].mean(), 100 * prof[:, i].mean() / max(tot, 1)))
 print("  total %.0f cycles/env-step/warp" % tot)
 niters = np.array([sim.dbg_view(k)["niter"] for k in range(min(K, 32))])
