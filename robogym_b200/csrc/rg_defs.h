@@ -30,6 +30,9 @@
 #define RG_LDG(p) (*(p))
 #define RG_LDG4(base, idx, out) { const float* q_ = (base) + 4 * (size_t)(idx); (out)[0] = q_[0]; (out)[1] = q_[1]; (out)[2] = q_[2]; (out)[3] = q_[3]; }
 #define RG_RSQRT(x) (1.0f / sqrtf(x))
+#define RG_CTA_SYNC()
+#define RG_CTA_ANY(x) (x)
+#define RG_SINCOS(x, sn, cs) { *(sn) = sinf(x); *(cs) = cosf(x); }
 #else
 #include <cuda_runtime.h>
 #include <string.h>
@@ -45,6 +48,12 @@
 #define RG_LDG(p) __ldg(p)
 #define RG_LDG4(base, idx, out) { const float4 q_ = __ldg((const float4*)(base) + (idx)); (out)[0] = q_.x; (out)[1] = q_.y; (out)[2] = q_.z; (out)[3] = q_.w; }
 #define RG_RSQRT(x) rsqrtf(x)
+/* The warps of a CTA walk the step in loose lock-step (one barrier per stage / Newton iteration): the
+ * kernel's code is far larger than the instruction cache, so keeping the warps in the same stage lets
+ * one instruction fetch feed all of them.  Every warp executes the same number of barriers. */
+#define RG_CTA_SYNC() __syncthreads()
+#define RG_CTA_ANY(x) __syncthreads_or(x)
+#define RG_SINCOS(x, sn, cs) __sincosf(x, sn, cs)
 #endif
 
 #define RG_MINVAL 1e-15f

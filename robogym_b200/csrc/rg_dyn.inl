@@ -67,7 +67,8 @@ RG_DEV_NOINLINE void rg_apply_joint(const RgModel& m, const float* qpos, int j, 
     rg_add3(anchor, pos, t);
     if (type == RG_JNT_HINGE) {
       float half = 0.5f * (qpos[qa] - m.qpos0[qa]);
-      float sn = sinf(half), cs = cosf(half);
+      float sn, cs;
+      RG_SINCOS(half, &sn, &cs);
       ql[0] = cs; ql[1] = m.jnt_axis[3 * j] * sn; ql[2] = m.jnt_axis[3 * j + 1] * sn; ql[3] = m.jnt_axis[3 * j + 2] * sn;
     } else {
       ql[0] = qpos[qa]; ql[1] = qpos[qa + 1]; ql[2] = qpos[qa + 2]; ql[3] = qpos[qa + 3];

@@ -88,8 +88,14 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   if (warp >= args.warps) return;
   float* s = scratch0 + (size_t)warp * args.L.total;
   const RgModel& m = *sm;
-  for (int env = blockIdx.x * args.warps + warp; env < args.io.nenv; env += gridDim.x * args.warps)
-    rg_env_step(m, args.L, s, args.io, env, args.nsub, args.final_forward);
+  /* every warp of the CTA runs the same number of iterations (the stage barriers need all of them) */
+  const int stride = gridDim.x * args.warps;
+  const int iters = (args.io.nenv + stride - 1) / stride;
+  for (int it = 0; it < iters; it++) {
+    const int env = it * stride + blockIdx.x * args.warps + warp;
+    const int valid = env < args.io.nenv;
+    rg_env_step(m, args.L, s, args.io, valid ? env : args.io.nenv - 1, args.nsub, args.final_forward, valid);
+  }
 }
 
 __global__ void rg_reset_kernel(RgModel m, RgBatchIO io, const uint8_t* mask) {

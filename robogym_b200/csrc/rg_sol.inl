@@ -459,7 +459,13 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     RG_PHASE_END
     cost = RG_WARP_SUM(gp) + cost_con;
   }
-  for (; iter < m.opt_iterations[0]; iter++) {
+  int active = 1;
+  for (;;) {
+  const int go = active && iter < m.opt_iterations[0];
+  if (!RG_CTA_ANY(go)) break;          /* CTA-wide: warps that have converged wait here for the others */
+  if (!go) continue;
+  int done = 1;
+  do {
     /* gradient */
     rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
     LANEVAR(float, gn);
@@ -641,6 +647,9 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     const float improvement = scale * (cost - newcost);
     cost = newcost;
     if (improvement < tol) { iter++; break; }
+    done = 0;
+  } while (0);
+  if (done) active = 0; else iter++;
   }
   rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
   RG_PHASE_BEGIN
@@ -683,7 +692,8 @@ RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
       const float ang = sqrtf(rg_dot3(w, w)) * h;
       if (ang > 1e-15f) {
         rg_normalize3(w);
-        const float sn = sinf(0.5f * ang), cs = cosf(0.5f * ang);
+        float sn, cs;
+        RG_SINCOS(0.5f * ang, &sn, &cs);
         const float dq[4] = {cs, w[0] * sn, w[1] * sn, w[2] * sn};
         float q[4] = {s[L.qpos + qq], s[L.qpos + qq + 1], s[L.qpos + qq + 2], s[L.qpos + qq + 3]}, rq[4];
         rg_quat_mul(rq, q, dq);

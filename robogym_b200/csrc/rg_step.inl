@@ -69,17 +69,18 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
 /* mj_forward: everything but the integrator */
 RG_DEV_NOINLINE void rg_forward(RgCtx& c) {
   RG_PROF_BEGIN
-  rg_kinematics(c); RG_PROF(c, 0)
-  rg_massmatrix(c); RG_PROF(c, 1)
-  rg_bias(c); RG_PROF(c, 2)
-  rg_tendon(c); RG_PROF(c, 3)
-  rg_forces(c); RG_PROF(c, 4)
-  rg_collision(c); RG_PROF(c, 5)
-  rg_make_constraints(c); RG_PROF(c, 6)
-  rg_solve(c); RG_PROF(c, 7)
+  RG_CTA_SYNC(); rg_kinematics(c); RG_PROF(c, 0)
+  RG_CTA_SYNC(); rg_massmatrix(c); RG_PROF(c, 1)
+  RG_CTA_SYNC(); rg_bias(c); RG_PROF(c, 2)
+  RG_CTA_SYNC(); rg_tendon(c); RG_PROF(c, 3)
+  RG_CTA_SYNC(); rg_forces(c); RG_PROF(c, 4)
+  RG_CTA_SYNC(); rg_collision(c); RG_PROF(c, 5)
+  RG_CTA_SYNC(); rg_make_constraints(c); RG_PROF(c, 6)
+  RG_CTA_SYNC(); rg_solve(c); RG_PROF(c, 7)
 }
 
-RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward) {
+/* `store` == 0: a padding iteration that keeps this warp in step with its CTA (same barriers), results discarded */
+RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
   RG_LANE_DECL
   RgCtx c = {m, L, s, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0], 0};
   const int npid = 3 * m.nu;
@@ -97,7 +98,7 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
   RG_PHASE_END
   for (int sub = 0; sub < nsub; sub++) {
     rg_forward(c);
-    { RG_PROF_BEGIN rg_euler(c); RG_PROF(c, 8) }
+    { RG_PROF_BEGIN RG_CTA_SYNC(); rg_euler(c); RG_PROF(c, 8) }
     /* mj_checkPos / mj_checkVel: reset on a bad state, like mj_step does */
     LANEVAR(int, badl);
     RG_PHASE_BEGIN
@@ -121,6 +122,7 @@ RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, 
   }
   if (final_forward) rg_forward(c);
   /* ---- store */
+  if (!store) return;
   RG_PHASE_BEGIN
   for (int j = lane; j < m.njnt; j += 32)
     if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] += m.origin[a];
