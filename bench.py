@@ -75,40 +75,48 @@ def measured_peak():
 
 # ---------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clock and throttle reasons of one GPU every 50 ms in a thread (NVML) during the timed region."""
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.samples, self.reasons, self.smax, self._stop, self._thr = index, [], set(), None, False, None
 
     def start(self):
+        import threading
+
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
+        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(pynvml, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+
+        def run():
+            while not self._stop:
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+                time.sleep(0.05)
+
+        self._thr = threading.Thread(target=run, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, smax, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                if v == "Active":
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons)}
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
 # ---------------------------------------------------------------- CPU arm (oracle port of the reference path)

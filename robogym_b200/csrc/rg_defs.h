@@ -64,6 +64,10 @@
 #define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
 #define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds) */
 #define RG_TRI(i, j) ((((i) * ((i) + 1)) >> 1) + (j))   /* packed lower triangle, i >= j */
+/* The solver's Hessian is stored with the dof order REVERSED (leaves of the kinematic tree first, roots and
+ * free objects last): Cholesky then eliminates children before parents, so the tree-structured part
+ * of the matrix produces no fill-in and the envelope of most rows is a handful of entries. */
+#define RG_HR(nv, i, j) ((i) <= (j) ? RG_TRI((nv) - 1 - (i), (nv) - 1 - (j)) : RG_TRI((nv) - 1 - (j), (nv) - 1 - (i)))
 #define RG_TILE 16       /* max dofs touched by one contact */
 
 enum { RG_JNT_FREE = 0, RG_JNT_BALL = 1, RG_JNT_SLIDE = 2, RG_JNT_HINGE = 3 };

@@ -9,7 +9,9 @@
  * memory behind the read-only path.  No tensor cores: nothing here is a dense contraction.
  */
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -238,8 +240,21 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   int warps = (maxsmem - fixed) / per_warp;
   if (warps < 1) { delete b; return rg_fail(-3, "rg_batch_create: model scratch does not fit in shared memory"); }
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
+  /* every warp of a CTA runs the same number of environments (stage barriers), so pick the warp count
+     that wastes the fewest padded slots: maximise padding-efficiency x warps^0.9 */
+  {
+    int best = warps;
+    double best_score = -1.0;
+    for (int w = warps; w >= 1; w--) {
+      int c = (nenv + w - 1) / w; if (c > sms) c = sms;
+      const long long slots = (long long)((nenv + (long long)c * w - 1) / ((long long)c * w)) * c * w;
+      const double score = (double)nenv / (double)slots * pow((double)w, 0.9);
+      if (score > best_score + 1e-9) { best_score = score; best = w; }
+    }
+    warps = best;
+  }
   const char* wenv = getenv("RG_WARPS_PER_CTA");
-  if (wenv && atoi(wenv) > 0 && atoi(wenv) < warps) warps = atoi(wenv);
+  if (wenv && atoi(wenv) > 0 && atoi(wenv) <= RG_MAX_WARPS && 4 * m->L.total * atoi(wenv) + fixed <= maxsmem) warps = atoi(wenv);
   b->warps = warps;
   b->smem = fixed - 64 + warps * per_warp;
   int ctas = (nenv + warps - 1) / warps;

@@ -148,6 +148,16 @@ RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int t
   }
 }
 
+/* x <- reversed x (solver dof order <-> model dof order) */
+RG_DEV void rg_reverse_phase(RgCtx& c, int x) {
+  RG_LANE_DECL
+  const int n = c.m.nv;
+  float* s = c.s;
+  RG_PHASE_BEGIN
+  for (int d = lane; d < n / 2; d += 32) { const float a = s[x + d], b = s[x + n - 1 - d]; s[x + d] = b; s[x + n - 1 - d] = a; }
+  RG_PHASE_END
+}
+
 /* ---------------------------------------------------------------- S8/S9 constraint elements */
 RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
   RG_LANE_DECL
@@ -324,6 +334,8 @@ RG_DEV float rg_el_Jx(const RgCtx& c, int code, int x) {
   return side ? -acc : acc;
 }
 
+/* well-mixed per-row hash: the active-set signature is a SUM of these, so it must not be linear in the row id */
+RG_DEV unsigned rg_mix(unsigned h) { h *= 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16; return h; }
 /* forces + cost at the current jar (el_jar, cu); returns total constraint cost; fills el_f and cF */
 RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
   RG_LANE_DECL
@@ -340,8 +352,8 @@ RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
       const float fl = s[L.el_floss + e], rf = fl / D;
       if (jar <= -rf) { f = fl; cost += -0.5f * rf * fl - fl * jar; }
       else if (jar >= rf) { f = -fl; cost += -0.5f * rf * fl + fl * jar; }
-      else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += (unsigned)(e + 1) * 2654435761u; }
-    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; sig += (unsigned)(e + 1) * 2654435761u; }
+      else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); }
+    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); }
     else f = 0.0f;
     s[L.el_f + e] = f;
   }
@@ -352,12 +364,12 @@ RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
     const int dim = (int)prm[1];
     const float D = prm[0];
     float F[6] = {0, 0, 0, 0, 0, 0};
-    if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; sig += (unsigned)(1000 + 16 * k) * 40503u; } }
+    if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; sig += rg_mix((unsigned)(1000 + 16 * k)); } }
     else for (int a = 1; a < dim; a++) {
       const float mu = rg_contact_mu(r, a);
       const float jp = u[0] + mu * u[a], jm = u[0] - mu * u[a];
-      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; sig += (unsigned)(1000 + 16 * k + 2 * a) * 40503u; }
-      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; sig += (unsigned)(1000 + 16 * k + 2 * a + 1) * 40503u; }
+      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a)); }
+      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a + 1)); }
     }
     float* cf = s + L.cF + 6 * k;
     for (int a = 0; a < 6; a++) cf[a] = F[a];
@@ -439,6 +451,11 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
   const int* el_i = (const int*)(s + L.el_i);
   const int* eldof = (const int*)(s + L.eldof);
   int* env = (int*)(s + L.env);
+#if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
+  printf("solve: nel %d tl0 %d ncon %d:", nel, tl0, ncon);
+  for (int e = 0; e < nel; e++) printf(" %d/%d/%d", el_i[e] & 3, (el_i[e] >> 2) & 1, el_i[e] >> 3);
+  printf("\n");
+#endif
   /* start from the previous solution (warm start) */
   RG_PHASE_BEGIN
   for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
@@ -462,8 +479,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
   int active = 1;
   for (;;) {
   const int go = active && iter < m.opt_iterations[0];
-  if (!RG_CTA_ANY(go)) break;          /* CTA-wide: warps that have converged wait here for the others */
-  if (!go) continue;
+  if (!go) break;   /* (a CTA-wide barrier per Newton iteration was measured: no gain over the per-stage barriers) */
   int done = 1;
   do {
     /* gradient */
@@ -473,7 +489,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     float a = 0.0f;
     for (int d = lane; d < nv; d += 32) {
       const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
-      s[L.search + d] = -g;
+      s[L.search + (nv - 1 - d)] = -g;   /* right-hand side in the solver's reversed dof order */
       a += g * g;
     }
     LV(gn) = a;
@@ -481,10 +497,15 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     const float gnorm = sqrtf(RG_WARP_SUM(gn));
     if (scale * gnorm < tol) break;
     /* Hessian H = M + J' diag(D active) J: rebuilt and refactored only when the active set changed */
+#ifdef RG_NO_REUSE
+    const int refactor = 1;
+#else
     const int refactor = !(have_factor && c.sig == factor_sig);
+#endif
     if (refactor) {
     RG_PHASE_BEGIN
-    for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
+    for (int i = lane; i < nv; i += 32)
+      for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_TRI(i, j)];
     RG_PHASE_END
     RG_PHASE_BEGIN
     for (int d = lane; d < nv; d += 32) {
@@ -492,7 +513,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       const int e0 = eldof[3 * d];
       if (e0 >= 0) { const float rf = s[L.el_floss + e0] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
       for (int q = 1; q < 3; q++) { const int e = eldof[3 * d + q]; if (e >= 0 && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
-      s[L.H + RG_TRI(d, d)] += add;
+      s[L.H + RG_HR(nv, d, d)] += add;
     }
     RG_PHASE_END
     for (int e = tl0; e < nel; e++) {
@@ -504,7 +525,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       RG_PHASE_BEGIN
       for (int p = lane; p < tn * tn; p += 32) {
         const int a = p / tn, b = p - a * tn;
-        if (tji[a] >= tji[b]) s[L.H + RG_TRI(tji[a], tji[b])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
+        if (tji[a] >= tji[b]) s[L.H + RG_HR(nv, tji[a], tji[b])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
       }
       RG_PHASE_END
     }
@@ -553,7 +574,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
         const float* tw = s + L.tileWJ + 6 * j;
         float acc = 0.0f;
         for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
-        if (tdof[i] >= tdof[j]) s[L.H + RG_TRI(tdof[i], tdof[j])] += acc;
+        if (tdof[i] >= tdof[j]) s[L.H + RG_HR(nv, tdof[i], tdof[j])] += acc;
       }
       RG_PHASE_END
     }
@@ -568,7 +589,37 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     rg_cholesky(c, L.H, env);
     have_factor = 1; factor_sig = c.sig;
     }
+#if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
+    { double cs = 0; for (int i = 0; i < (nv * (nv + 1)) / 2; i++) cs += s[L.H + i] * (1 + (i % 7)); int es = 0; for (int i = 0; i < nv; i++) es += env[i] * (i + 1); printf("    L checksum %.9g env %d\n", cs, es); }
+#endif
     rg_chol_solve(c, L.H, env, L.search, L.tmp);
+    rg_reverse_phase(c, L.search);
+#if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
+    { /* finite-difference check of the Newton direction: g(q + eps*s) should be ~ (1-eps) g(q) when the active set holds */
+      static float q0[256], g0v[256], ma0[256], jar0[256], cu0[6 * RG_NCON], f0[256], cf0[6 * RG_NCON], qfc0[256];
+      for (int d = 0; d < nv; d++) { q0[d] = s[L.qacc + d]; ma0[d] = s[L.Ma + d]; qfc0[d] = s[L.qfc + d]; g0v[d] = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d]; }
+      for (int e = 0; e < nel; e++) { jar0[e] = s[L.el_jar + e]; f0[e] = s[L.el_f + e]; }
+      for (int i = 0; i < 6 * ncon; i++) { cu0[i] = s[L.cu + i]; cf0[i] = s[L.cF + i]; }
+      const float eps = 1e-3f;
+      for (int d = 0; d < nv; d++) s[L.qacc + d] = q0[d] + eps * s[L.search + d];
+      rg_matvec_phase(c, L.Ma, L.qacc);
+      for (int e = 0; e < nel; e++) s[L.el_jar + e] = jar0[e] - rg_el_Jx(c, el_i[e], L.qacc) + rg_el_Jx(c, el_i[e], L.qacc);   /* placeholder */
+      /* recompute jar from scratch: jar = J q - aref ; we know jar0 = J q0 - aref */
+      rg_J_mul_phase(c, L.search, L.el_jv, L.cw, nel, ncon, 0);
+      for (int e = 0; e < nel; e++) s[L.el_jar + e] = jar0[e] + eps * s[L.el_jv + e];
+      for (int i = 0; i < 6 * ncon; i++) s[L.cu + i] = cu0[i] + eps * s[L.cw + i];
+      const int sig_before = c.sig;
+      rg_solver_update(c, nel, ncon);
+      rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
+      float num = 0, den = 0, dotg = 0;
+      for (int d = 0; d < nv; d++) { const float g1 = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d]; const float pred = (1.0f - eps) * g0v[d]; num += (g1 - pred) * (g1 - pred); den += g0v[d] * g0v[d]; dotg += g0v[d] * s[L.search + d]; }
+      printf("    FD check: |g(q+eps s) - (1-eps) g|/|g| = %.3g  (sig %d -> %d)  g.s %.4g\n", sqrtf(num / den), sig_before, c.sig, dotg);
+      for (int d = 0; d < nv; d++) { s[L.qacc + d] = q0[d]; s[L.Ma + d] = ma0[d]; s[L.qfc + d] = qfc0[d]; }
+      for (int e = 0; e < nel; e++) { s[L.el_jar + e] = jar0[e]; s[L.el_f + e] = f0[e]; }
+      for (int i = 0; i < 6 * ncon; i++) { s[L.cu + i] = cu0[i]; s[L.cF + i] = cf0[i]; }
+      c.sig = sig_before;
+    }
+#endif
     /* line search along `search` */
     rg_matvec_phase(c, L.Mv, L.search);
     rg_J_mul_phase(c, L.search, L.el_jv, L.cw, nel, ncon, 0);
@@ -645,8 +696,12 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       newcost = RG_WARP_SUM(gp) + cost_con;
     }
     const float improvement = scale * (cost - newcost);
+#if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
+    printf("  it %d cost %.9g new %.9g impr %.3g alpha %.6g gnorm %.3g refactor %d sig %d\n", iter, cost, newcost, improvement, alpha, gnorm, refactor, c.sig);
+#endif
     cost = newcost;
-    if (improvement < tol) { iter++; break; }
+    /* fp32: cost differences below ~2 ulp of the cost itself are rounding noise, not progress */
+    if (improvement < tol + 2.4e-7f * fabsf(cost) * scale) { iter++; break; }
     done = 0;
   } while (0);
   if (done) active = 0; else iter++;
@@ -667,17 +722,20 @@ RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
   int* env = (int*)(s + L.env);
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
   RG_PHASE_BEGIN
-  for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
+  for (int i = lane; i < nv; i += 32)
+    for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_TRI(i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
+  for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int d = lane; d < nv; d += 32) {
-    s[L.H + RG_TRI(d, d)] += h * m.dof_damping[d];
-    s[L.search + d] = s[L.smooth + d] + s[L.qfc + d];
-    env[d] = m.dof_treeroot[d];
+  for (int i = lane; i < nv; i += 32) {
+    int e = 0;
+    while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
+    env[i] = e;
   }
   RG_PHASE_END
   rg_cholesky(c, L.H, env);
   rg_chol_solve(c, L.H, env, L.search, L.tmp);
+  rg_reverse_phase(c, L.search);
   RG_PHASE_BEGIN
   for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
   RG_PHASE_END
