@@ -153,9 +153,40 @@ def cpu_baseline(blob, seconds=10.0):
             "sample": f"{n} env-steps (x{NSUB} substeps) of one dactyl/locked env, relative random actions, fp64 CPU port (oracle/)"}
 
 
+_REF = {}
+
+
+def _ref_init(blob, base_seed):
+    """Pool initializer: one persistent oracle environment per worker process (model loaded and settled once)."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    om = pyoracle.OracleModel(blob)
+    d = pyoracle.OracleData(om)
+    cr = om.field("actuator_ctrlrange").reshape(-1, 2)
+    d.ctrl[:] = cr.mean(1)
+    for _ in range(20):
+        d.env_step(NSUB)
+    _REF.update(om=om, d=d, cr=cr, rng=np.random.RandomState(base_seed + os.getpid()))
+
+
+def _ref_step(n_steps):
+    import numpy as np
+
+    d, cr, rng = _REF["d"], _REF["cr"], _REF["rng"]
+    for _ in range(n_steps):
+        a = rng.uniform(-1, 1, len(cr))
+        d.ctrl[:] = np.clip(d.ctrl + ACTION_SCALE * a * (cr[:, 1] - cr[:, 0]) / 2, cr[:, 0], cr[:, 1])
+        d.env_step(NSUB)
+    return n_steps
+
+
 def run_reference_arm(args):
-    """--impl reference: the CPU implementation of the path on all host cores.  mujoco-py 2.0.2.13 is
-    not installable here (no network, closed binary), so this times the fp64 CPU port under oracle/."""
+    """--impl reference: the CPU implementation of the path on all host cores.  mujoco-py 2.0.2.13 /
+    MuJoCo 2.0 (robogym setup.py:16) is a closed binary that is not installable here (no network, not in
+    the wheelhouse), so this arm times the fp64 CPU port under oracle/ -- one persistent single-env
+    simulation per host core, the way robogym would be vectorised on CPUs."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -166,21 +197,23 @@ def run_reference_arm(args):
     pyoracle.build()
     blob = load_blob()
     cores = os.cpu_count() or 1
-    per_step = 8                      # env-steps per worker per bench "step" (bounded sample)
+    per_step = 16                     # env-steps per worker per bench "step" (bounded sample of the 8192-env workload)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        for _ in range(args.warmup):
-            pool.map(_cpu_worker, [(blob, 100 + w, per_step) for w in range(cores)])
+    with ctx.Pool(cores, initializer=_ref_init, initargs=(blob, 1234)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_ref_step, [per_step] * cores, chunksize=1)
         t0 = time.perf_counter()
-        for k in range(args.steps):
-            pool.map(_cpu_worker, [(blob, 1000 * k + w, per_step) for w in range(cores)])
+        for _ in range(args.steps):
+            pool.map(_ref_step, [per_step] * cores, chunksize=1)
         dt = time.perf_counter() - t0
     value = cores * per_step * args.steps / dt
-    sample = f"each step = {cores} worker processes x {per_step} env-steps of one env (fp64 CPU port, settle excluded from the metric but inside the timing)"
+    sample = (f"each bench step = {cores} persistent worker processes x {per_step} env-steps of one dactyl/locked env each "
+              f"(fp64 CPU port of the reference path; 10 substeps + forward per env-step)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dactyl/locked, ShadowHand + locked cube, 10 substeps of 0.008 s per env-step, relative random actions"},
+            "config": {"workload": "dactyl/locked (BASELINE.json configs[1]): ShadowHand + locked cube, 10 substeps of 0.008 s + forward per env-step, "
+                                   "relative random actions (ctrl += 0.3*a*half-range); CPU arm = bounded sample of that workload"},
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
