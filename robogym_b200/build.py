@@ -12,7 +12,8 @@ DEPS += [os.path.join(HERE, "..", "include", f) for f in ("rg_model_fields.h", "
 
 def nvcc_cmd(extra=()):
     nvcc = os.environ.get("NVCC", "nvcc")
-    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # -prec-div/-prec-sqrt=false: 2-ulp division / square root without the slow-path calls (measured +6 %, parity unchanged)
+    return [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-prec-div=false", "-prec-sqrt=false", "-ftz=true",
             "-Xcompiler", "-fPIC", "-shared", *extra, "-o", OUT, os.path.join(SRC, "rg_engine.cu")]
 
 
