@@ -61,6 +61,7 @@ enum rg_field {
   RG_NFIELDS = 18
 };
 #define RG_MAX_CONTACTS 32
+#define RG_MAX_PARAM_OVERRIDES 16
 
 int rg_model_load(const void* blob, size_t len, int device, rg_model** out);
 void rg_model_destroy(rg_model* m);
@@ -75,6 +76,13 @@ int rg_scratch_bytes(const rg_model* m);
 int rg_batch_create(const rg_model* m, int nenv, rg_batch** out);
 void rg_batch_destroy(rg_batch* b);
 int rg_batch_bind(rg_batch* b, int field, void* device_ptr);
+/* Per-environment override of a float model array (domain randomisation, SURVEY 5.6: robogym's wrappers write
+ * sim.model.geom_friction / dof_damping / actuator_gainprm / opt_gravity / ... per env and per episode):
+ * device_ptr is a float32 [nenv][count(name)] tensor that replaces the shared array `name` for each environment.
+ * Up to RG_MAX_PARAM_OVERRIDES arrays; device_ptr == NULL removes the override.  body_pos rows of bodies attached
+ * to the world must be given relative to rg_model_origin(). */
+int rg_batch_bind_param(rg_batch* b, const char* name, void* device_ptr);
+int rg_model_origin(const rg_model* m, float origin[3]);
 /* launch geometry actually used (for reporting): CTAs, warps per CTA, dynamic shared bytes */
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps_per_cta, int* smem_bytes);
 

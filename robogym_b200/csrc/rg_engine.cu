@@ -32,6 +32,11 @@ struct RgKernelArgs {
   RgBatchIO io;
   const char* arena;  /* device arena base (16B aligned) */
   int nsub, final_forward, warps;
+  /* per-environment overrides of float model arrays */
+  int nover;
+  int over_off[RG_MAX_PARAM_OVERRIDES];          /* byte offset of the pointer member inside RgModel */
+  int over_cnt[RG_MAX_PARAM_OVERRIDES];          /* floats per environment */
+  const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,14 +94,24 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   const int warp = threadIdx.x >> 5;
   if (warp >= args.warps) return;
   float* s = scratch0 + (size_t)warp * args.L.total;
-  const RgModel& m = *sm;
+  /* with per-env overrides every warp keeps its own model view (CTA view + patched pointers) after the scratch */
+  RgModel* wm = sm;
+  if (args.nover > 0) wm = (RgModel*)((unsigned char*)(scratch0 + (size_t)args.warps * args.L.total) + (size_t)warp * model_bytes);
   /* every warp of the CTA runs the same number of iterations (the stage barriers need all of them) */
   const int stride = gridDim.x * args.warps;
   const int iters = (args.io.nenv + stride - 1) / stride;
   for (int it = 0; it < iters; it++) {
     const int env = it * stride + blockIdx.x * args.warps + warp;
     const int valid = env < args.io.nenv;
-    rg_env_step(m, args.L, s, args.io, valid ? env : args.io.nenv - 1, args.nsub, args.final_forward, valid);
+    const int e = valid ? env : args.io.nenv - 1;
+    if (args.nover > 0) {
+      const int lane = threadIdx.x & 31;
+      for (int i = lane; i < (int)(sizeof(RgModel) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
+      __syncwarp();
+      if (lane < args.nover) *(const float**)((char*)wm + args.over_off[lane]) = args.over_ptr[lane] + (size_t)e * args.over_cnt[lane];
+      __syncwarp();
+    }
+    rg_env_step(*wm, args.L, s, args.io, e, args.nsub, args.final_forward, valid);
   }
 }
 
@@ -125,6 +140,10 @@ struct rg_batch {
   int nenv;
   void* ptr[RG_NFIELDS];
   int ctas, warps, smem;
+  int nover = 0;
+  int over_off[RG_MAX_PARAM_OVERRIDES], over_cnt[RG_MAX_PARAM_OVERRIDES];
+  const float* over_ptr[RG_MAX_PARAM_OVERRIDES];
+  std::string over_name[RG_MAX_PARAM_OVERRIDES];
 };
 
 static void rg_wire_device_view(rg_model* mm) {
@@ -236,7 +255,7 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   RG_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
   const int model_bytes = (int)((sizeof(RgModel) + 127) & ~(size_t)127);
   const int fixed = model_bytes + (int)((m->hm.small_bytes + 127) & ~(size_t)127) + 64;
-  const int per_warp = 4 * m->L.total;
+  const int per_warp = 4 * m->L.total + model_bytes;   /* + room for a per-warp model view (per-env parameter overrides) */
   int warps = (maxsmem - fixed) / per_warp;
   if (warps < 1) { delete b; return rg_fail(-3, "rg_batch_create: model scratch does not fit in shared memory"); }
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
@@ -254,7 +273,7 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
     warps = best;
   }
   const char* wenv = getenv("RG_WARPS_PER_CTA");
-  if (wenv && atoi(wenv) > 0 && atoi(wenv) <= RG_MAX_WARPS && 4 * m->L.total * atoi(wenv) + fixed <= maxsmem) warps = atoi(wenv);
+  if (wenv && atoi(wenv) > 0 && atoi(wenv) <= RG_MAX_WARPS && per_warp * atoi(wenv) + fixed <= maxsmem) warps = atoi(wenv);
   b->warps = warps;
   b->smem = fixed - 64 + warps * per_warp;
   int ctas = (nenv + warps - 1) / warps;
@@ -271,6 +290,42 @@ int rg_batch_bind(rg_batch* b, int field, void* p) {
   b->ptr[field] = p;
   return 0;
 }
+int rg_model_origin(const rg_model* m, float origin[3]) {
+  if (!m || !origin) return rg_fail(-1, "rg_model_origin: null argument");
+  for (int a = 0; a < 3; a++) origin[a] = m->hm.view.origin[a];
+  return 0;
+}
+
+int rg_batch_bind_param(rg_batch* b, const char* name, void* p) {
+  if (!b || !name) return rg_fail(-1, "rg_batch_bind_param: null argument");
+  const RgModel& m = b->model->hm.view;
+#define RG_DIM(n) const int n = m.n; (void)n;
+#define RG_I(n, c)
+#define RG_F(n, c)
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  int off = -1, cnt = 0;
+#define RG_DIM(n)
+#define RG_I(f, c)
+#define RG_F(f, c) if (!strcmp(name, #f)) { off = (int)((const char*)&m.f - (const char*)&m); cnt = (int)(c); }
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+  if (off < 0) return rg_fail(-1, std::string("rg_batch_bind_param: not a float model array: ") + name);
+  int slot = -1;
+  for (int i = 0; i < b->nover; i++) if (b->over_name[i] == name) slot = i;
+  if (!p) {
+    if (slot >= 0) { for (int i = slot; i + 1 < b->nover; i++) { b->over_off[i] = b->over_off[i + 1]; b->over_cnt[i] = b->over_cnt[i + 1]; b->over_ptr[i] = b->over_ptr[i + 1]; b->over_name[i] = b->over_name[i + 1]; } b->nover--; }
+    return 0;
+  }
+  if (slot < 0) { if (b->nover >= RG_MAX_PARAM_OVERRIDES) return rg_fail(-3, "rg_batch_bind_param: too many overrides"); slot = b->nover++; }
+  b->over_off[slot] = off; b->over_cnt[slot] = cnt; b->over_ptr[slot] = (const float*)p; b->over_name[slot] = name;
+  return 0;
+}
+
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
   if (!b) return -1;
   if (ctas) *ctas = b->ctas;
@@ -301,6 +356,8 @@ int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
   args.L = b->model->L;
   args.arena = b->model->d_arena;
   args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
+  args.nover = b->nover;
+  for (int i = 0; i < b->nover; i++) { args.over_off[i] = b->over_off[i]; args.over_cnt[i] = b->over_cnt[i]; args.over_ptr[i] = b->over_ptr[i]; }
   RG_CUDA(cudaSetDevice(b->model->device));
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());

@@ -52,6 +52,8 @@ def lib():
         L.rg_batch_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
         L.rg_batch_destroy.argtypes = [vp]
         L.rg_batch_bind.argtypes = [vp, ci, vp]
+        L.rg_batch_bind_param.argtypes = [vp, ctypes.c_char_p, vp]
+        L.rg_model_origin.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.rg_batch_launch_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.rg_step.argtypes = [vp, ci, ci, vp]
         L.rg_forward.argtypes = [vp, vp]
@@ -156,6 +158,31 @@ class BatchedSim:
         self.xfrc_applied = self.torch.zeros(self.nenv, m["nbody"], 6, dtype=self.torch.float32, device=self.device)
         self._bind(XFRC, self.xfrc_applied)
         return self.xfrc_applied
+
+    def set_param(self, name, values):
+        """Per-environment override of a float model array (domain randomisation): `values` is [nenv, count]
+        (float64/float32 host array or tensor).  The device copy is created on first use and updated in place."""
+        t = self.torch
+        m = self.model.host
+        v = t.as_tensor(np.asarray(values, dtype=np.float64) if not t.is_tensor(values) else values).to(t.float64).reshape(self.nenv, -1).clone()
+        if v.shape[1] != m[name].size:
+            raise EngineError(f"set_param({name}): expected {m[name].size} values per environment, got {v.shape[1]}")
+        if name == "body_pos":   # keep the engine's fp32 world shift for bodies attached to the world
+            o = (ctypes.c_float * 3)()
+            _check(lib().rg_model_origin(self.model.h, o))
+            rows = v.reshape(self.nenv, -1, 3)
+            root = t.as_tensor(np.asarray(m["body_parentid"]) == 0)
+            root[0] = False
+            rows[:, root] -= t.tensor(list(o), dtype=t.float64)
+        dev = v.to(device=self.device, dtype=t.float32).contiguous()
+        if not hasattr(self, "_params"):
+            self._params = {}
+        if name in self._params:
+            self._params[name].copy_(dev)
+        else:
+            self._params[name] = dev
+            _check(lib().rg_batch_bind_param(self.h, name.encode(), ctypes.c_void_p(dev.data_ptr())))
+        return self._params[name]
 
     def enable_per_env_timestep(self):
         self.timestep = self.torch.full((self.nenv,), float(self.model.host["opt_timestep"][0]), dtype=self.torch.float32, device=self.device)
