@@ -296,7 +296,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
         const int bit = rg_ctz(bits);
         bits &= bits - 1;
         if (nd < 16) { list[nd] = (unsigned char)(32 * w + bit); if ((m2 >> bit) & 1u) sgn |= 1u << nd; nd++; }
-        else dim = 0; /* more than 16 dofs: cannot be represented -> drop the contact (flagged below) */
+        else { dim = 0; RG_SI(c, RG_S_WARN) |= RG_WARN_ROWS_FULL; } /* more than 16 dofs: not representable -> contact dropped, flagged */
       }
     }
     if (dim == 0) { prm[1] = 0.0f; nd = 0; }

@@ -1,0 +1,39 @@
+"""Small inline MJCF models (no reference assets) that exercise engine paths dactyl/locked does not:
+free joints, plane-box / plane-sphere contacts, box-box through MPR, capsule inertia from geoms,
+affine (position) actuators, condim 1/3/6, joint springs."""
+
+FREE_BODIES = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.004" iterations="20"/>
+  <size nuserdata="0" njmax="200" nconmax="50"/>
+  <worldbody>
+    <body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3" friction="0.9 0.005 0.0001"/></body>
+    <body name="box" pos="0 0 0.2" euler="0.3 0.2 0.1">
+      <joint name="box_free" type="free"/>
+      <geom name="box" type="box" size="0.05 0.04 0.03" density="800" condim="3"/>
+    </body>
+    <body name="ball" pos="0.3 0.1 0.15">
+      <joint name="ball_free" type="free"/>
+      <geom name="ball" type="sphere" size="0.04" density="600" condim="3"/>
+    </body>
+    <body name="brick" pos="0.02 0.01 0.45" euler="0.1 0.4 0.7">
+      <joint name="brick_free" type="free"/>
+      <geom name="brick" type="box" size="0.04 0.03 0.02" density="900" condim="4"/>
+    </body>
+    <body name="arm" pos="-0.4 0 0.5">
+      <joint name="shoulder" type="hinge" axis="0 1 0" damping="0.05" armature="0.001" limited="true" range="-1.5 1.5" stiffness="0.2"/>
+      <geom name="upper" type="capsule" fromto="0 0 0 0.2 0 0" size="0.02" density="500" contype="0" conaffinity="0"/>
+      <body name="fore" pos="0.2 0 0">
+        <joint name="elbow" type="hinge" axis="0 1 0" damping="0.02" frictionloss="0.01"/>
+        <geom name="lower" type="capsule" fromto="0 0 0 0.15 0 0" size="0.015" density="500" contype="0" conaffinity="0"/>
+        <site name="tip" pos="0.15 0 0"/>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <position name="a_shoulder" joint="shoulder" kp="2.0" ctrllimited="true" ctrlrange="-1 1"/>
+    <motor name="a_elbow" joint="elbow" gear="0.5" ctrllimited="true" ctrlrange="-1 1"/>
+  </actuator>
+</mujoco>
+"""
