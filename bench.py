@@ -185,6 +185,25 @@ def _ref_step(n_steps):
     return n_steps
 
 
+def usable_cores():
+    """Host threads this process can really use: affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    n = min(n, max(1, q // int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())))
+            break
+        except Exception:
+            continue
+    return n
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU implementation of the path on all host cores.  mujoco-py 2.0.2.13 /
     MuJoCo 2.0 (robogym setup.py:16) is a closed binary that is not installable here (no network, not in
@@ -199,7 +218,7 @@ def run_reference_arm(args):
 
     pyoracle.build()
     blob = load_blob()
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_step = 16                     # env-steps per worker per bench "step" (bounded sample of the 8192-env workload)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores, initializer=_ref_init, initargs=(blob, 1234)) as pool:
