@@ -16,8 +16,15 @@
  *   boundary; RG_I arrays are int32, RG_F arrays are float64.
  *
  * Usage: define RG_DIM(name), RG_I(name, count), RG_F(name, count) then include.
+ * RG_IB / RG_FB mark the BIG arrays at the end of the list (they default to RG_I / RG_F).
  * `count` is a C expression over the dims (the includer provides them in scope).
  */
+
+#ifndef RG_IB
+#define RG_IB(n, c) RG_I(n, c)
+#define RG_FB(n, c) RG_F(n, c)
+#define RG_BIG_DEFAULTED
+#endif
 
 /* ---- dimensions ---- */
 RG_DIM(nq)        /* generalized positions */
@@ -184,9 +191,15 @@ RG_I(sensor_dim, nsensor)
 
 /* ---- BIG arrays (kept in global memory by the CUDA engine; everything above is small enough
  *      to be staged into shared memory with one bulk copy).  Keep these LAST. ---- */
-RG_F(mesh_vert, nmeshvert * 3)       /* hull vertices, centred on the hull's volume centroid */
-RG_I(mesh_adjadr, nmeshvert + 1)     /* CSR into mesh_adj, global vertex ids */
-RG_I(mesh_adj, nmeshadj)             /* neighbour vertex ids, LOCAL to the mesh */
-RG_I(mesh_face, nmeshface * 3)       /* hull triangles, LOCAL vertex ids (rendering/inertia only) */
-RG_I(pair_geom1, npair)
-RG_I(pair_geom2, npair)
+RG_FB(mesh_vert, nmeshvert * 3)       /* hull vertices, centred on the hull's volume centroid */
+RG_IB(mesh_adjadr, nmeshvert + 1)     /* CSR into mesh_adj, global vertex ids */
+RG_IB(mesh_adj, nmeshadj)             /* neighbour vertex ids, LOCAL to the mesh */
+RG_IB(mesh_face, nmeshface * 3)       /* hull triangles, LOCAL vertex ids (rendering/inertia only) */
+RG_IB(pair_geom1, npair)
+RG_IB(pair_geom2, npair)
+
+#ifdef RG_BIG_DEFAULTED
+#undef RG_IB
+#undef RG_FB
+#undef RG_BIG_DEFAULTED
+#endif

@@ -23,13 +23,13 @@ struct RgGeomView {
 };
 
 RG_DEV void rg_geom_view(const RgCtx& c, int g, float margin, RgGeomView& v) {
-  const RgModel& m = c.m;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int b = m.geom_bodyid[g];
   float q[4];
-  rg_quat_mul(q, c.s + c.L.xquat + 4 * b, m.geom_quat + 4 * g);
+  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * b, m.geom_quat + 4 * g);
   rg_quat_norm(q);
   rg_quat2mat(v.mat, q);
-  rg_copy3(v.pos, c.s + c.L.gxpos + 3 * g);
+  rg_copy3(v.pos, RG_SCRATCH(c) + c.L.gxpos + 3 * g);
   rg_copy3(v.size, m.geom_size + 3 * g);
   v.type = m.geom_type[g];
   v.hint = -1;
@@ -38,7 +38,7 @@ RG_DEV void rg_geom_view(const RgCtx& c, int g, float margin, RgGeomView& v) {
   if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.mid = mid; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
 }
 
-RG_DEV void rg_support(const RgModel& m, RgGeomView& v, const float* dir, float* res) {
+RG_DEV void rg_support(const RG_MODEL_T& m, RgGeomView& v, const float* dir, float* res) {
   float dl[3], loc[3] = {0, 0, 0};
   RG_STAT(rg_stat_support++; rg_stat_cur++;)
   rg_mulmatT3(dl, v.mat, dir);
@@ -102,7 +102,7 @@ RG_DEV void rg_support(const RgModel& m, RgGeomView& v, const float* dir, float*
 
 struct RgSup { float v[3], v1[3], v2[3]; };
 
-RG_DEV void rg_mpr_support(const RgModel& m, RgGeomView& o1, RgGeomView& o2, const float* dir, RgSup& sp) {
+RG_DEV void rg_mpr_support(const RG_MODEL_T& m, RgGeomView& o1, RgGeomView& o2, const float* dir, RgSup& sp) {
   const float nd[3] = {-dir[0], -dir[1], -dir[2]};
   rg_support(m, o1, dir, sp.v1);
   rg_support(m, o2, nd, sp.v2);
@@ -178,7 +178,8 @@ RG_DEV void rg_find_pos3(const float* v0, const float* c1, const float* c2, cons
 }
 
 /* depth >= 0 with dir,pos when the inflated geoms intersect; -1 otherwise */
-RG_DEV_NOINLINE float rg_mpr(const RgModel& m, RgGeomView& o1, RgGeomView& o2, float tol, int maxiter, float* dir_out, float* pos) {
+RG_DEV_NOINLINE float rg_mpr(RgMRef mr, RgGeomView& o1, RgGeomView& o2, float tol, int maxiter, float* dir_out, float* pos) {
+  const RG_MODEL_T& m = RG_MDEREF(mr);
   enum { S_V1 = 0, S_V2 = 1, S_V3 = 2, S_REFINE = 3, S_PENETR = 4, S_DONE = 5 };
   RgSup P1, P2, P3, sp;
   float v0[3], dir[3], va[3], vb[3];
@@ -269,12 +270,12 @@ RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
 /* oriented-box overlap (separating-axis test on the geoms' local bounding boxes, box 1 grown by margin):
  * a conservative cull between the bounding-sphere test and MPR; it never removes a pair that could touch */
 RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx& c, int g1, int g2, float margin) {
-  const RgModel& m = c.m;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
   float q[4], A[9], B[9], ca[3], cb[3], t[3], d[3];
-  rg_quat_mul(q, c.s + c.L.xquat + 4 * m.geom_bodyid[g1], m.geom_quat + 4 * g1); rg_quat_norm(q); rg_quat2mat(A, q);
-  rg_quat_mul(q, c.s + c.L.xquat + 4 * m.geom_bodyid[g2], m.geom_quat + 4 * g2); rg_quat_norm(q); rg_quat2mat(B, q);
-  rg_mulmat3(ca, A, m.geom_aabb + 6 * g1); rg_add3(ca, ca, c.s + c.L.gxpos + 3 * g1);
-  rg_mulmat3(cb, B, m.geom_aabb + 6 * g2); rg_add3(cb, cb, c.s + c.L.gxpos + 3 * g2);
+  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * m.geom_bodyid[g1], m.geom_quat + 4 * g1); rg_quat_norm(q); rg_quat2mat(A, q);
+  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * m.geom_bodyid[g2], m.geom_quat + 4 * g2); rg_quat_norm(q); rg_quat2mat(B, q);
+  rg_mulmat3(ca, A, m.geom_aabb + 6 * g1); rg_add3(ca, ca, RG_SCRATCH(c) + c.L.gxpos + 3 * g1);
+  rg_mulmat3(cb, B, m.geom_aabb + 6 * g2); rg_add3(cb, cb, RG_SCRATCH(c) + c.L.gxpos + 3 * g2);
   const float a[3] = {m.geom_aabb[6 * g1 + 3] + margin, m.geom_aabb[6 * g1 + 4] + margin, m.geom_aabb[6 * g1 + 5] + margin};
   const float* b = m.geom_aabb + 6 * g2 + 3;
   rg_sub3(d, cb, ca);
@@ -302,7 +303,7 @@ RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx& c, int g1, int g2, float margin)
 }
 
 RG_DEV_NOINLINE int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
-  const RgModel& m = c.m;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   int cnt = 0;
   if (t1 == RG_GEOM_PLANE) {
@@ -372,7 +373,7 @@ RG_DEV_NOINLINE int rg_narrow(const RgCtx& c, int g1, int g2, float margin, floa
   rg_geom_view(c, g1, margin, o1);
   rg_geom_view(c, g2, margin, o2);
   float dir[3], pos[3];
-  const float depth = rg_mpr(m, o1, o2, m.opt_mpr_tolerance[0], m.opt_mpr_iterations[0], dir, pos);
+  const float depth = rg_mpr(RG_MREF(m), o1, o2, m.opt_mpr_tolerance[0], m.opt_mpr_iterations[0], dir, pos);
   RG_STAT(if (rg_stat_cur > rg_stat_maxsup) rg_stat_maxsup = rg_stat_cur; if (depth >= 0) rg_stat_mpr_hit++;)
   if (depth < 0 || rg_dot3(dir, dir) < 0.5f) return 0;
   out[0] = margin - depth;
@@ -382,13 +383,13 @@ RG_DEV_NOINLINE int rg_narrow(const RgCtx& c, int g1, int g2, float margin, floa
 }
 
 /* append the first `n` survivors (flag per lane) of list `src` to list `dst`, then drop them from `src` */
-RG_DEV void rg_pair(const RgModel& m, int k, int& g1, int& g2) {
-  if (m.pair_packed) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
+RG_DEV void rg_pair(const RG_MODEL_T& m, int k, int& g1, int& g2) {
+  if (RG_HAS_PAIRS(m)) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
   else { g1 = RG_LDG(m.pair_geom1 + k); g2 = RG_LDG(m.pair_geom2 + k); }
 }
 RG_DEV_NOINLINE void rg_collision(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   int* cand = (int*)(s + L.cand);
   int* cand2 = (int*)(s + L.cand2);
   int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0;

@@ -30,6 +30,7 @@
 #define RG_LDG(p) (*(p))
 #define RG_LDG4(base, idx, out) { const float* q_ = (base) + 4 * (size_t)(idx); (out)[0] = q_[0]; (out)[1] = q_[1]; (out)[2] = q_[2]; (out)[3] = q_[3]; }
 #define RG_RSQRT(x) (1.0f / sqrtf(x))
+#define RG_SCRATCH(c) ((c).s)
 #define RG_CTA_SYNC()
 #define RG_CTA_ANY(x) (x)
 #define RG_SINCOS(x, sn, cs) { *(sn) = sinf(x); *(cs) = cosf(x); }
@@ -48,6 +49,11 @@
 #define RG_LDG(p) __ldg(p)
 #define RG_LDG4(base, idx, out) { const float4 q_ = __ldg((const float4*)(base) + (idx)); (out)[0] = q_.x; (out)[1] = q_.y; (out)[2] = q_.z; (out)[3] = q_.w; }
 #define RG_RSQRT(x) rsqrtf(x)
+/* The per-warp scratch is addressed as (dynamic shared memory base + offset) so that the compiler can prove the
+ * address space and emit LDS/STS with 32-bit addresses; a plain float* carried through the noinline stage
+ * functions compiles to generic 64-bit LD/ST (measured: most of the instruction stream was address arithmetic). */
+extern __shared__ __align__(128) unsigned char rg_smem_raw[];
+#define RG_SCRATCH(c) (((float*)rg_smem_raw) + (c).soff)
 /* The warps of a CTA walk the step in loose lock-step (one barrier per stage / Newton iteration): the
  * kernel's code is far larger than the instruction cache, so keeping the warps in the same stage lets
  * one instruction fetch feed all of them.  Every warp executes the same number of barriers. */
@@ -98,6 +104,54 @@ struct RgModel {
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
 };
+
+#ifndef RG_EMU
+/* Device-side model view.  The small arrays of the model are staged in the CTA's dynamic shared memory, so
+ * the view stores 32-bit OFFSETS from the shared-memory base instead of pointers: every `m.field[i]` then
+ * compiles to an LDS with a 32-bit address instead of a generic 64-bit load.  The big read-only arrays
+ * (hull vertices / adjacency, pair list) stay global pointers. */
+template <class T>
+struct RgArr {
+  int off; /* bytes from rg_smem_raw */
+  __device__ __forceinline__ const T* p() const { return (const T*)(rg_smem_raw + off); }
+  __device__ __forceinline__ const T& operator[](int i) const { return p()[i]; }
+  __device__ __forceinline__ const T* operator+(int i) const { return p() + i; }
+};
+struct RgModelDev {
+#define RG_DIM(n) int n;
+#define RG_I(n, c) RgArr<int> n;
+#define RG_F(n, c) RgArr<float> n;
+#define RG_IB(n, c) const int* n;
+#define RG_FB(n, c) const float* n;
+#include "../../include/rg_model_fields.h"
+#undef RG_DIM
+#undef RG_I
+#undef RG_F
+#undef RG_IB
+#undef RG_FB
+  RgArr<int> body_subtreesize;
+  RgArr<int> dof_treeroot;
+  RgArr<unsigned short> pair_packed;
+  int has_pairs;
+  const float* mesh_nbr;
+  const int* mesh_ext;
+  float origin[3];
+  int small_bytes;
+};
+#define RG_MODEL_T RgModelDev
+#define RG_HAS_PAIRS(m) ((m).has_pairs)
+/* the model view is handed to non-inlined code as its byte offset in the CTA's dynamic shared memory, so that
+   every access through it compiles to LDS rather than a generic load */
+typedef int RgMRef;
+#define RG_MDEREF(r) (*(const RgModelDev*)(rg_smem_raw + (r)))
+#define RG_MREF(m) ((int)((const unsigned char*)&(m) - rg_smem_raw))
+#else
+#define RG_MODEL_T RgModel
+#define RG_HAS_PAIRS(m) ((m).pair_packed != nullptr)
+typedef const RgModel* RgMRef;
+#define RG_MDEREF(r) (*(r))
+#define RG_MREF(m) (&(m))
+#endif
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
 struct RgLayout {
@@ -221,8 +275,8 @@ RG_DEV void rg_mulmatT3(float* r, const float* m, const float* v) {
 }
 RG_DEV int rg_f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
 RG_DEV float rg_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-RG_DEV int rg_dof_in_body(const RgModel& m, int body, int dof) {
-  return (((const unsigned*)m.body_dofmask)[body * m.nmaskw + (dof >> 5)] >> (dof & 31)) & 1u;
+RG_DEV int rg_dof_in_body(const RG_MODEL_T& m, int body, int dof) {
+  return ((unsigned)m.body_dofmask[body * m.nmaskw + (dof >> 5)] >> (dof & 31)) & 1u;
 }
 /* spatial vectors: V = [w; vO] (motion), F = [nO; f] (force), both about the (shifted) world origin */
 RG_DEV float rg_dot6(const float* a, const float* b) { return rg_dot3(a, b) + rg_dot3(a + 3, b + 3); }

@@ -10,21 +10,22 @@
 #include "rg_defs.h"
 
 struct RgCtx {
-  const RgModel& m;
+  RgMRef mref;           /* the model view (see RG_MDEREF) */
   const RgLayout& L;
-  float* s;              /* per-warp scratch */
+  float* s;              /* per-warp scratch (emulation build) */
+  int soff;              /* the same, as a float offset into the CTA's dynamic shared memory (CUDA build) */
   const float* xfrc;     /* global: this env's xfrc_applied [nbody*6] or nullptr */
   float timestep;        /* per-env timestep (opt.timestep unless overridden) */
   int sig;               /* signature of the solver's active set (warp-uniform), see rg_solver_update */
 };
 
-#define RG_SI(c, k) (((int*)((c).s + (c).L.scal))[k])
+#define RG_SI(c, k) (((int*)(RG_SCRATCH(c) + (c).L.scal))[k])
 enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4 };
 
 /* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
 #if !defined(RG_EMU) && defined(RG_PROFILE)
 #define RG_PROF_BEGIN long long prof_t_ = clock64();
-#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) (c).s[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
+#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) RG_SCRATCH(c)[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
 #else
 #define RG_PROF_BEGIN
 #define RG_PROF(c, k)
@@ -33,13 +34,13 @@ enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4 
 /* Spatial vectors of a kinematic tree are expressed about that tree's own reference point (the
  * world position of its root body), not the world origin: in fp32 the parallel-axis terms m*c^2
  * would otherwise swamp the link inertias of anything that drifts far away (a dropped cube). */
-RG_DEV const float* rg_body_ref(const RgCtx& c, int body) { return c.s + c.L.xpos + 3 * c.m.body_rootid[body]; }
-RG_DEV const float* rg_dof_ref(const RgCtx& c, int dof) { return rg_body_ref(c, c.m.dof_bodyid[dof]); }
+RG_DEV const float* rg_body_ref(const RgCtx& c, int body) { return RG_SCRATCH(c) + c.L.xpos + 3 * RG_MDEREF(c.mref).body_rootid[body]; }
+RG_DEV const float* rg_dof_ref(const RgCtx& c, int dof) { return rg_body_ref(c, RG_MDEREF(c.mref).dof_bodyid[dof]); }
 /* translational Jacobian column of dof d at world point p */
 RG_DEV void rg_jacp_world(const RgCtx& c, int d, const float* p, float* jp) {
   float rel[3];
   rg_sub3(rel, p, rg_dof_ref(c, d));
-  rg_jacp(jp, c.s + c.L.S + 6 * d, rel);
+  rg_jacp(jp, RG_SCRATCH(c) + c.L.S + 6 * d, rel);
 }
 
 RG_DEV int rg_ctz(unsigned x) {
@@ -51,7 +52,8 @@ RG_DEV int rg_ctz(unsigned x) {
 }
 
 /* apply joint j (of body b) to the running frame (pos, quat) */
-RG_DEV_NOINLINE void rg_apply_joint(const RgModel& m, const float* qpos, int j, float* pos, float* quat) {
+RG_DEV_NOINLINE void rg_apply_joint(RgMRef mr, const float* qpos, int j, float* pos, float* quat) {
+  const RG_MODEL_T& m = RG_MDEREF(mr);
   const int type = m.jnt_type[j], qa = m.jnt_qposadr[j];
   if (type == RG_JNT_FREE) {
     pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
@@ -84,14 +86,14 @@ RG_DEV_NOINLINE void rg_apply_joint(const RgModel& m, const float* qpos, int j, 
 /* ---------------------------------------------------------------- S1 kinematics + axes */
 RG_DEV_NOINLINE void rg_kinematics(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   /* local frames of every body relative to its parent */
   RG_PHASE_BEGIN
   for (int b = lane; b < m.nbody; b += 32) {
     float pos[3] = {m.body_pos[3 * b], m.body_pos[3 * b + 1], m.body_pos[3 * b + 2]};
     float quat[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
     const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
-    for (int k = 0; k < jn; k++) rg_apply_joint(m, s + L.qpos, ja + k, pos, quat);
+    for (int k = 0; k < jn; k++) rg_apply_joint(RG_MREF(m), s + L.qpos, ja + k, pos, quat);
     rg_copy3(s + L.lpos + 3 * b, pos);
     float* lq = s + L.lquat + 4 * b;
     lq[0] = quat[0]; lq[1] = quat[1]; lq[2] = quat[2]; lq[3] = quat[3];
@@ -145,7 +147,7 @@ RG_DEV_NOINLINE void rg_kinematics(RgCtx& c) {
     rg_rot(t, s + L.xquat + 4 * par, m.body_pos + 3 * b);
     rg_add3(pos, s + L.xpos + 3 * par, t);
     rg_quat_mul(quat, s + L.xquat + 4 * par, m.body_quat + 4 * b);
-    for (int jj = m.body_jntadr[b]; jj < j; jj++) rg_apply_joint(m, s + L.qpos, jj, pos, quat);
+    for (int jj = m.body_jntadr[b]; jj < j; jj++) rg_apply_joint(RG_MREF(m), s + L.qpos, jj, pos, quat);
     if (type == RG_JNT_SLIDE) {
       S[0] = S[1] = S[2] = 0;
       rg_rot(S + 3, quat, m.jnt_axis + 3 * j);
@@ -179,7 +181,7 @@ RG_DEV_NOINLINE void rg_kinematics(RgCtx& c) {
 /* ---------------------------------------------------------------- S2/S5 inertias + mass matrix */
 RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
   for (int b = lane; b < m.nbody; b += 32) {
@@ -238,7 +240,7 @@ RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
 /* ---------------------------------------------------------------- velocities + bias force */
 RG_DEV_NOINLINE void rg_bias(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const float* qvel = s + L.qvel;
   RG_PHASE_BEGIN
   for (int d = lane; d < m.nv; d += 32) {
@@ -258,7 +260,7 @@ RG_DEV_NOINLINE void rg_bias(RgCtx& c) {
     float V[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
     if (!(m.opt_disableflags[0] & RG_DSBL_GRAVITY)) { A[3] = -m.opt_gravity[0]; A[4] = -m.opt_gravity[1]; A[5] = -m.opt_gravity[2]; }
     for (int w = 0; w < m.nmaskw; w++) {
-      unsigned bits = ((const unsigned*)m.body_dofmask)[b * m.nmaskw + w];
+      unsigned bits = (unsigned)m.body_dofmask[b * m.nmaskw + w];
       while (bits) {
         const int d = 32 * w + rg_ctz(bits);
         bits &= bits - 1;
@@ -382,7 +384,7 @@ RG_DEV_NOINLINE float rg_wrap_geom(float* wp, const float* x0, const float* x1, 
 }
 RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
   if (ba == bb) return;
-  const RgModel& m = c.m;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
   for (int d = 0; d < m.nv; d++) {
     const int ina = rg_dof_in_body(m, ba, d), inb = rg_dof_in_body(m, bb, d);
     if (ina == inb) continue;
@@ -394,15 +396,15 @@ RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const f
 
 /* entry (t, d) of the sparse tendon Jacobian */
 RG_DEV float rg_tendon_J(const RgCtx& c, int t, int d) {
-  const int n = ((const int*)(c.s + c.L.tJn))[t];
-  const int* ji = (const int*)(c.s + c.L.tJi) + RG_TJ * t;
+  const int n = ((const int*)(RG_SCRATCH(c) + c.L.tJn))[t];
+  const int* ji = (const int*)(RG_SCRATCH(c) + c.L.tJi) + RG_TJ * t;
   float v = 0.0f;
-  for (int k = 0; k < n; k++) if (ji[k] == d) v = c.s[c.L.tJv + RG_TJ * t + k];
+  for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[c.L.tJv + RG_TJ * t + k];
   return v;
 }
 RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
   for (int t = lane; t < m.ntendon; t += 32) {
@@ -480,7 +482,7 @@ RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
 /* ---------------------------------------------------------------- S4/S10/S11/S12 passive, PID actuation, smooth force */
 RG_DEV_NOINLINE void rg_forces(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv, flags = m.opt_disableflags[0];
   const float dt = c.timestep;
   /* actuators: transmission, mujoco-py PID bias callback (stateful), force clamp */

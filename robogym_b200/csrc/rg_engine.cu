@@ -10,6 +10,7 @@
  */
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -27,26 +28,30 @@ static int rg_fail(int code, const std::string& msg) { g_err = msg; return code;
 #define RG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return rg_fail(-2, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 struct RgKernelArgs {
-  RgModel m;          /* pointers into the device arena */
+  RgModel m;          /* host-style view whose pointers point into the DEVICE arena (source of the staged copy) */
   RgLayout L;
   RgBatchIO io;
   const char* arena;  /* device arena base (16B aligned) */
   int nsub, final_forward, warps;
-  /* per-environment overrides of float model arrays */
+  /* per-environment overrides of float model arrays (domain randomisation) */
   int nover;
-  int over_off[RG_MAX_PARAM_OVERRIDES];          /* byte offset of the pointer member inside RgModel */
+  int over_floats;                               /* floats of the per-warp override area */
+  int over_off[RG_MAX_PARAM_OVERRIDES];          /* byte offset of the RgArr member inside RgModelDev */
   int over_cnt[RG_MAX_PARAM_OVERRIDES];          /* floats per environment */
-  const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] */
+  int over_dst[RG_MAX_PARAM_OVERRIDES];          /* float offset inside the per-warp override area */
+  const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] in global memory */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#define RG_MODEL_DEV_BYTES ((int)((sizeof(RgModelDev) + 127) & ~(size_t)127))
+
 __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __grid_constant__ RgKernelArgs args) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem_raw = rg_smem_raw;
   __shared__ __align__(8) unsigned long long mbar;
-  /* shared layout: [RgModel (rebased)] [small arena] [warps x scratch] */
-  RgModel* sm = (RgModel*)smem_raw;
-  const int model_bytes = (int)((sizeof(RgModel) + 127) & ~(size_t)127);
+  /* dynamic shared layout: [RgModelDev] [small model arena] [warps x scratch] [warps x (RgModelDev + override rows)] */
+  RgModelDev* sm = (RgModelDev*)smem_raw;
+  const int model_bytes = RG_MODEL_DEV_BYTES;
   unsigned char* sarena = smem_raw + model_bytes;
   const int small_bytes = args.m.small_bytes;
   float* scratch0 = (float*)(sarena + ((small_bytes + 127) & ~127));
@@ -60,26 +65,36 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(rg_smem_u32(sarena)), "l"(args.arena), "r"((uint32_t)small_bytes), "r"(bar) : "memory");
   }
-  /* meanwhile: rebased model view in shared memory (pointers into the staged copy where possible) */
+  /* meanwhile: the device model view (shared-memory offsets of the staged arrays, global pointers of the big ones) */
   if (threadIdx.x < 32) {
     const int lane = threadIdx.x;
-    if (lane == 0) *sm = args.m;
-    __syncwarp();
     int k = 0;
     const char* abase = args.arena;
-#define RG_REBASE(field) { if (lane == (k & 31)) { const char* p_ = (const char*)args.m.field; const size_t off_ = (size_t)(p_ - abase); \
-      if (off_ < (size_t)small_bytes) *(const void**)&sm->field = (const void*)(sarena + off_); } k++; }
-#define RG_DIM(n)
-#define RG_I(n, c) RG_REBASE(n)
-#define RG_F(n, c) RG_REBASE(n)
+#define RG_SETOFF(field) { if (lane == (k & 31)) sm->field.off = model_bytes + (int)((const char*)args.m.field - abase); k++; }
+#define RG_SETPTR(field) { if (lane == (k & 31)) sm->field = args.m.field; k++; }
+#define RG_DIM(n) { if (lane == (k & 31)) sm->n = args.m.n; k++; }
+#define RG_I(n, c) RG_SETOFF(n)
+#define RG_F(n, c) RG_SETOFF(n)
+#define RG_IB(n, c) RG_SETPTR(n)
+#define RG_FB(n, c) RG_SETPTR(n)
 #include "../../include/rg_model_fields.h"
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
-    RG_REBASE(body_subtreesize)
-    RG_REBASE(dof_treeroot)
-    if (args.m.pair_packed) RG_REBASE(pair_packed)
-#undef RG_REBASE
+#undef RG_IB
+#undef RG_FB
+    RG_SETOFF(body_subtreesize)
+    RG_SETOFF(dof_treeroot)
+    RG_SETPTR(mesh_nbr)
+    RG_SETPTR(mesh_ext)
+    if (lane == 0) {
+      sm->has_pairs = args.m.pair_packed != nullptr;
+      sm->pair_packed.off = args.m.pair_packed ? model_bytes + (int)((const char*)args.m.pair_packed - abase) : 0;
+      sm->origin[0] = args.m.origin[0]; sm->origin[1] = args.m.origin[1]; sm->origin[2] = args.m.origin[2];
+      sm->small_bytes = small_bytes;
+    }
+#undef RG_SETOFF
+#undef RG_SETPTR
   }
   __syncthreads();
   {
@@ -94,9 +109,14 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   const int warp = threadIdx.x >> 5;
   if (warp >= args.warps) return;
   float* s = scratch0 + (size_t)warp * args.L.total;
-  /* with per-env overrides every warp keeps its own model view (CTA view + patched pointers) after the scratch */
-  RgModel* wm = sm;
-  if (args.nover > 0) wm = (RgModel*)((unsigned char*)(scratch0 + (size_t)args.warps * args.L.total) + (size_t)warp * model_bytes);
+  /* with per-env overrides every warp keeps its own model view + a copy of this env's rows after the scratch */
+  RgModelDev* wm = sm;
+  float* wover = nullptr;
+  if (args.nover > 0) {
+    unsigned char* base = (unsigned char*)(scratch0 + (size_t)args.warps * args.L.total) + (size_t)warp * (model_bytes + 4 * args.over_floats);
+    wm = (RgModelDev*)base;
+    wover = (float*)(base + model_bytes);
+  }
   /* every warp of the CTA runs the same number of iterations (the stage barriers need all of them) */
   const int stride = gridDim.x * args.warps;
   const int iters = (args.io.nenv + stride - 1) / stride;
@@ -106,12 +126,16 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     const int e = valid ? env : args.io.nenv - 1;
     if (args.nover > 0) {
       const int lane = threadIdx.x & 31;
-      for (int i = lane; i < (int)(sizeof(RgModel) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
+      for (int i = lane; i < (int)(sizeof(RgModelDev) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
+      for (int o = 0; o < args.nover; o++) {
+        const float* src = args.over_ptr[o] + (size_t)e * args.over_cnt[o];
+        for (int i = lane; i < args.over_cnt[o]; i += 32) wover[args.over_dst[o] + i] = src[i];
+      }
       __syncwarp();
-      if (lane < args.nover) *(const float**)((char*)wm + args.over_off[lane]) = args.over_ptr[lane] + (size_t)e * args.over_cnt[lane];
+      if (lane < args.nover) *(int*)((char*)wm + args.over_off[lane]) = (int)((unsigned char*)(wover + args.over_dst[lane]) - rg_smem_raw);
       __syncwarp();
     }
-    rg_env_step(*wm, args.L, s, args.io, e, args.nsub, args.final_forward, valid);
+    rg_env_step((int)((unsigned char*)wm - rg_smem_raw), args.L, s, (int)(s - (float*)rg_smem_raw), args.io, e, args.nsub, args.final_forward, valid);
   }
 }
 
@@ -141,7 +165,8 @@ struct rg_batch {
   void* ptr[RG_NFIELDS];
   int ctas, warps, smem;
   int nover = 0;
-  int over_off[RG_MAX_PARAM_OVERRIDES], over_cnt[RG_MAX_PARAM_OVERRIDES];
+  int over_off[RG_MAX_PARAM_OVERRIDES], over_cnt[RG_MAX_PARAM_OVERRIDES], over_dst[RG_MAX_PARAM_OVERRIDES];
+  int over_floats = 0;
   const float* over_ptr[RG_MAX_PARAM_OVERRIDES];
   std::string over_name[RG_MAX_PARAM_OVERRIDES];
 };
@@ -243,21 +268,20 @@ int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t 
 int rg_dbg_size(const rg_model* m) { return m ? ::rg_dbg_size(m->hm.view) : -1; }
 int rg_scratch_bytes(const rg_model* m) { return m ? 4 * m->L.total : -1; }
 
-int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
-  if (!m || !out || nenv <= 0) return rg_fail(-1, "rg_batch_create: bad argument");
-  rg_batch* b = new rg_batch();
-  b->model = m;
-  b->nenv = nenv;
-  for (int i = 0; i < RG_NFIELDS; i++) b->ptr[i] = nullptr;
+/* launch geometry: warps per CTA, dynamic shared memory, CTA count (re-run when the override set changes) */
+static int rg_batch_size(rg_batch* b) {
+  const rg_model* m = b->model;
+  const int nenv = b->nenv;
   RG_CUDA(cudaSetDevice(m->device));
   int sms = 0, maxsmem = 0;
   RG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
   RG_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
-  const int model_bytes = (int)((sizeof(RgModel) + 127) & ~(size_t)127);
+  const int model_bytes = RG_MODEL_DEV_BYTES;
   const int fixed = model_bytes + (int)((m->hm.small_bytes + 127) & ~(size_t)127) + 64;
-  const int per_warp = 4 * m->L.total + model_bytes;   /* + room for a per-warp model view (per-env parameter overrides) */
+  /* with per-env parameter overrides every warp also holds its own model view + this env's rows */
+  const int per_warp = 4 * m->L.total + (b->nover > 0 ? model_bytes + 4 * b->over_floats : 0);
   int warps = (maxsmem - fixed) / per_warp;
-  if (warps < 1) { delete b; return rg_fail(-3, "rg_batch_create: model scratch does not fit in shared memory"); }
+  if (warps < 1) return rg_fail(-3, "rg_batch: model scratch does not fit in shared memory");
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
   /* every warp of a CTA runs the same number of environments (stage barriers), so pick the warp count
      that wastes the fewest padded slots: maximise padding-efficiency x warps^0.9 */
@@ -280,6 +304,17 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   if (ctas > sms) ctas = sms;
   b->ctas = ctas;
   RG_CUDA(cudaFuncSetAttribute(rg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem));
+  return 0;
+}
+
+int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
+  if (!m || !out || nenv <= 0) return rg_fail(-1, "rg_batch_create: bad argument");
+  rg_batch* b = new rg_batch();
+  b->model = m;
+  b->nenv = nenv;
+  for (int i = 0; i < RG_NFIELDS; i++) b->ptr[i] = nullptr;
+  const int rc = rg_batch_size(b);
+  if (rc) { delete b; return rc; }
   *out = b;
   return 0;
 }
@@ -309,21 +344,30 @@ int rg_batch_bind_param(rg_batch* b, const char* name, void* p) {
   int off = -1, cnt = 0;
 #define RG_DIM(n)
 #define RG_I(f, c)
-#define RG_F(f, c) if (!strcmp(name, #f)) { off = (int)((const char*)&m.f - (const char*)&m); cnt = (int)(c); }
+#define RG_IB(f, c)
+#define RG_FB(f, c)
+#define RG_F(f, c) if (!strcmp(name, #f)) { off = (int)offsetof(RgModelDev, f); cnt = (int)(c); }
 #include "../../include/rg_model_fields.h"
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
-  if (off < 0) return rg_fail(-1, std::string("rg_batch_bind_param: not a float model array: ") + name);
+#undef RG_IB
+#undef RG_FB
+  if (off < 0) return rg_fail(-1, std::string("rg_batch_bind_param: not a (small) float model array: ") + name);
   int slot = -1;
   for (int i = 0; i < b->nover; i++) if (b->over_name[i] == name) slot = i;
   if (!p) {
-    if (slot >= 0) { for (int i = slot; i + 1 < b->nover; i++) { b->over_off[i] = b->over_off[i + 1]; b->over_cnt[i] = b->over_cnt[i + 1]; b->over_ptr[i] = b->over_ptr[i + 1]; b->over_name[i] = b->over_name[i + 1]; } b->nover--; }
-    return 0;
+    if (slot < 0) return 0;
+    for (int i = slot; i + 1 < b->nover; i++) { b->over_off[i] = b->over_off[i + 1]; b->over_cnt[i] = b->over_cnt[i + 1]; b->over_ptr[i] = b->over_ptr[i + 1]; b->over_name[i] = b->over_name[i + 1]; }
+    b->nover--;
+  } else {
+    if (slot < 0) { if (b->nover >= RG_MAX_PARAM_OVERRIDES) return rg_fail(-3, "rg_batch_bind_param: too many overrides"); slot = b->nover++; }
+    b->over_off[slot] = off; b->over_cnt[slot] = cnt; b->over_ptr[slot] = (const float*)p; b->over_name[slot] = name;
   }
-  if (slot < 0) { if (b->nover >= RG_MAX_PARAM_OVERRIDES) return rg_fail(-3, "rg_batch_bind_param: too many overrides"); slot = b->nover++; }
-  b->over_off[slot] = off; b->over_cnt[slot] = cnt; b->over_ptr[slot] = (const float*)p; b->over_name[slot] = name;
-  return 0;
+  int fl = 0;
+  for (int i = 0; i < b->nover; i++) { b->over_dst[i] = fl; fl += (b->over_cnt[i] + 3) & ~3; }
+  b->over_floats = fl;
+  return rg_batch_size(b);
 }
 
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
@@ -357,7 +401,8 @@ int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
   args.arena = b->model->d_arena;
   args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
   args.nover = b->nover;
-  for (int i = 0; i < b->nover; i++) { args.over_off[i] = b->over_off[i]; args.over_cnt[i] = b->over_cnt[i]; args.over_ptr[i] = b->over_ptr[i]; }
+  args.over_floats = b->over_floats;
+  for (int i = 0; i < b->nover; i++) { args.over_off[i] = b->over_off[i]; args.over_cnt[i] = b->over_cnt[i]; args.over_dst[i] = b->over_dst[i]; args.over_ptr[i] = b->over_ptr[i]; }
   RG_CUDA(cudaSetDevice(b->model->device));
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());

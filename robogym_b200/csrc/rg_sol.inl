@@ -31,7 +31,7 @@ RG_DEV_NOINLINE void rg_row_params(const RgCtx& c, const float* solref_in, const
                           int isfriction, float* R, float* aref, float* Bout, float* KIout) {
   float sr0 = solref_in[0];
   const float sr1 = solref_in[1];
-  if (!(c.m.opt_disableflags[0] & RG_DSBL_REFSAFE) && sr0 > 0) sr0 = fmaxf(sr0, 2.0f * c.timestep);
+  if (!(RG_MDEREF(c.mref).opt_disableflags[0] & RG_DSBL_REFSAFE) && sr0 > 0) sr0 = fmaxf(sr0, 2.0f * c.timestep);
   const float p = pos - margin;
   const float imp = rg_impedance(solimp, fabsf(p));
   const float dmax = rg_clamp(solimp[1], RG_MINIMP, RG_MAXIMP);
@@ -47,11 +47,11 @@ RG_DEV_NOINLINE void rg_row_params(const RgCtx& c, const float* solref_in, const
 
 /* contact-frame Jacobian column of dof d for contact record r (dim components), sign included; 0 if untouched */
 RG_DEV_NOINLINE int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float* col) {
-  const RgModel& m = c.m;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int b1 = (int)r[18], b2 = (int)r[19];
   const int in1 = rg_dof_in_body(m, b1, d), in2 = rg_dof_in_body(m, b2, d);
   if (in1 == in2) return 0;
-  const float* S = c.s + c.L.S + 6 * d;
+  const float* S = RG_SCRATCH(c) + c.L.S + 6 * d;
   float jp[3];
   rg_jacp_world(c, d, r + 1, jp);
   const float sg = in2 ? 1.0f : -1.0f;
@@ -63,7 +63,7 @@ RG_DEV_NOINLINE int rg_contact_col(const RgCtx& c, const float* r, int d, int di
 }
 /* same, for a dof already known to be touched (sg = +1 if it moves body 2, -1 if body 1) */
 RG_DEV void rg_contact_col_list(const RgCtx& c, const float* r, int d, float sg, int dim, float* col) {
-  const float* S = c.s + c.L.S + 6 * d;
+  const float* S = RG_SCRATCH(c) + c.L.S + 6 * d;
   float jp[3];
   rg_jacp_world(c, d, r + 1, jp);
   col[0] = sg * rg_dot3(r + 4, jp);
@@ -76,8 +76,8 @@ RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k =
 /* y = M x (dense, symmetric) */
 RG_DEV_NOINLINE void rg_matvec_phase(RgCtx& c, int y, int x) {
   RG_LANE_DECL
-  const int nv = c.m.nv;
-  float* s = c.s;
+  const int nv = RG_MDEREF(c.mref).nv;
+  float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
   for (int i = lane; i < nv; i += 32) {
     float acc = 0.0f;
@@ -92,8 +92,8 @@ RG_DEV_NOINLINE void rg_matvec_phase(RgCtx& c, int y, int x) {
 /* in-place envelope Cholesky of the lower triangle of A (row stride nv); env[i] = first nonzero column */
 RG_DEV_NOINLINE void rg_cholesky(RgCtx& c, int A, const int* env) {
   RG_LANE_DECL
-  const int n = c.m.nv;
-  float* s = c.s;
+  const int n = RG_MDEREF(c.mref).nv;
+  float* s = RG_SCRATCH(c);
   for (int j = 0; j < n; j++) {
     LANEVAR(float, sumv);
     RG_PHASE_BEGIN
@@ -129,8 +129,8 @@ RG_DEV_NOINLINE void rg_cholesky(RgCtx& c, int A, const int* env) {
 /* x <- (L L^T)^-1 x ; uses `tmp` as staging */
 RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int tmp) {
   RG_LANE_DECL
-  const int n = c.m.nv;
-  float* s = c.s;
+  const int n = RG_MDEREF(c.mref).nv;
+  float* s = RG_SCRATCH(c);
   for (int j = 0; j < n; j++) {
     RG_PHASE_BEGIN
     const float xj = s[x + j] / s[A + RG_TRI(j, j)];
@@ -151,8 +151,8 @@ RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int t
 /* x <- reversed x (solver dof order <-> model dof order) */
 RG_DEV void rg_reverse_phase(RgCtx& c, int x) {
   RG_LANE_DECL
-  const int n = c.m.nv;
-  float* s = c.s;
+  const int n = RG_MDEREF(c.mref).nv;
+  float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
   for (int d = lane; d < n / 2; d += 32) { const float a = s[x + d], b = s[x + n - 1 - d]; s[x + d] = b; s[x + n - 1 - d] = a; }
   RG_PHASE_END
@@ -161,7 +161,7 @@ RG_DEV void rg_reverse_phase(RgCtx& c, int x) {
 /* ---------------------------------------------------------------- S8/S9 constraint elements */
 RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv, flags = m.opt_disableflags[0];
   int* el_i = (int*)(s + L.el_i);
   int* eldof = (int*)(s + L.eldof);
@@ -290,7 +290,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
     int nd = 0;
     unsigned sgn = 0u;
     for (int w = 0; w < m.nmaskw && dim > 0; w++) {
-      const unsigned m1 = ((const unsigned*)m.body_dofmask)[b1 * m.nmaskw + w], m2 = ((const unsigned*)m.body_dofmask)[b2 * m.nmaskw + w];
+      const unsigned m1 = (unsigned)m.body_dofmask[b1 * m.nmaskw + w], m2 = (unsigned)m.body_dofmask[b2 * m.nmaskw + w];
       unsigned bits = m1 ^ m2;
       while (bits) {
         const int bit = rg_ctz(bits);
@@ -324,7 +324,7 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
 /* jar of single-row element e for a candidate acceleration vector at offset x */
 RG_DEV float rg_el_Jx(const RgCtx& c, int code, int x) {
   const int type = code & 3, side = (code >> 2) & 1, id = code >> 3;
-  const float* s = c.s;
+  const float* s = RG_SCRATCH(c);
   if (type == RG_EL_FLOSS) return s[x + id];
   if (type == RG_EL_JLIMIT) return side ? -s[x + id] : s[x + id];
   float acc = 0.0f;
@@ -339,7 +339,7 @@ RG_DEV unsigned rg_mix(unsigned h) { h *= 2654435761u; h ^= h >> 15; h *= 224682
 /* forces + cost at the current jar (el_jar, cu); returns total constraint cost; fills el_f and cF */
 RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
   RG_LANE_DECL
-  const RgLayout& L = c.L; float* s = c.s;
+  const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   LANEVAR(float, part); LANEVAR(int, sigp);
   RG_PHASE_BEGIN
@@ -384,7 +384,7 @@ RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
 /* out[d] = sum_rows J^T f for every dof (single-row elements, tendon rows, contacts) */
 RG_DEV_NOINLINE void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   const int* eldof = (const int*)(s + L.eldof);
   RG_PHASE_BEGIN
@@ -415,7 +415,7 @@ RG_DEV_NOINLINE void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int 
 /* el_x[e] = J_e x, cx[k] = Jc_k x  (x = vector at offset xoff); if init, adds -aref / staged velocity terms */
 RG_DEV_NOINLINE void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   RG_PHASE_BEGIN
   for (int e = lane; e < nel; e += 32) {
@@ -445,7 +445,7 @@ RG_DEV_NOINLINE void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, i
 
 RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   const int nel = RG_SI(c, RG_S_NEL), tl0 = RG_SI(c, RG_S_TL0), ncon = RG_SI(c, RG_S_NCON);
   const int* el_i = (const int*)(s + L.el_i);
@@ -716,7 +716,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
 /* ---------------------------------------------------------------- S15 semi-implicit Euler */
 RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
   RG_LANE_DECL
-  const RgModel& m = c.m; const RgLayout& L = c.L; float* s = c.s;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   const float h = c.timestep;
   int* env = (int*)(s + L.env);

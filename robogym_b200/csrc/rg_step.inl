@@ -26,7 +26,8 @@ struct RgBatchIO {
 #else
 #define RG_HD __host__ __device__ static inline
 #endif
-RG_HD int rg_dbg_size(const RgModel& m) {
+template <class MT>
+RG_HD int rg_dbg_size(const MT& m) {
   return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv + RG_NPROF;
 }
 
@@ -80,9 +81,11 @@ RG_DEV_NOINLINE void rg_forward(RgCtx& c) {
 }
 
 /* `store` == 0: a padding iteration that keeps this warp in step with its CTA (same barriers), results discarded */
-RG_DEV_NOINLINE void rg_env_step(const RgModel& m, const RgLayout& L, float* s, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
+RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L, float* s_in, int soff, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
   RG_LANE_DECL
-  RgCtx c = {m, L, s, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0], 0};
+  const RG_MODEL_T& m = RG_MDEREF(mr);
+  RgCtx c = {mr, L, s_in, soff, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0], 0};
+  float* s = RG_SCRATCH(c);
   const int npid = 3 * m.nu;
   /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
   RG_PHASE_BEGIN

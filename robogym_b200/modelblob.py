@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 FIELDS_H = os.path.join(_HERE, "..", "include", "rg_model_fields.h")
 MAGIC = b"RGMODEL1"
 
-_pat = re.compile(r"^\s*RG_(DIM|I|F)\(\s*(\w+)\s*(?:,\s*(.+?)\s*)?\)\s*(?:/\*.*)?$")
+_pat = re.compile(r"^\s*RG_(DIM|IB|FB|I|F)\(\s*(\w+)\s*(?:,\s*(.+?)\s*)?\)\s*(?:/\*.*)?$")
 
 
 def field_list(path=FIELDS_H):
@@ -26,6 +26,7 @@ def field_list(path=FIELDS_H):
             if not m:
                 continue
             kind, name, cnt = m.groups()
+            kind = {"IB": "I", "FB": "F"}.get(kind, kind)
             if kind == "DIM":
                 dims.append(name)
             else:

@@ -60,6 +60,6 @@ void rge_step(void* hv, int nenv, float* qpos, float* qvel, float* ctrl, float* 
   io.nenv = nenv; io.qpos = qpos; io.qvel = qvel; io.ctrl = ctrl; io.pid = pid; io.warm = warm; io.time = time; io.xfrc = xfrc;
   io.timestep = timestep; io.site_xpos = site_xpos; io.body_xpos = body_xpos; io.body_xquat = body_xquat; io.geom_xpos = geom_xpos;
   io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg;
-  for (int env = 0; env < nenv; env++) rg_env_step(h->hm.view, h->L, h->scratch.data(), io, env, nsub, final_forward, 1);
+  for (int env = 0; env < nenv; env++) rg_env_step(&h->hm.view, h->L, h->scratch.data(), 0, io, env, nsub, final_forward, 1);
 }
 }
