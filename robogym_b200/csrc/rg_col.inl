@@ -22,14 +22,14 @@ struct RgGeomView {
   float halfmargin;
 };
 
-RG_DEV void rg_geom_view(const RgCtx& c, int g, float margin, RgGeomView& v) {
+RG_DEV void rg_geom_view(const RgCtx c, int g, float margin, RgGeomView& v) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int b = m.geom_bodyid[g];
   float q[4];
-  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * b, m.geom_quat + 4 * g);
+  rg_quat_mul(q, RG_SCRATCH(c) + RG_CL(c).xquat + 4 * b, m.geom_quat + 4 * g);
   rg_quat_norm(q);
   rg_quat2mat(v.mat, q);
-  rg_copy3(v.pos, RG_SCRATCH(c) + c.L.gxpos + 3 * g);
+  rg_copy3(v.pos, RG_SCRATCH(c) + RG_CL(c).gxpos + 3 * g);
   rg_copy3(v.size, m.geom_size + 3 * g);
   v.type = m.geom_type[g];
   v.hint = -1;
@@ -269,13 +269,13 @@ RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
 /* narrow phase of one pair; writes up to 4 (dist,pos,normal) records to out[7*i..]; returns count */
 /* oriented-box overlap (separating-axis test on the geoms' local bounding boxes, box 1 grown by margin):
  * a conservative cull between the bounding-sphere test and MPR; it never removes a pair that could touch */
-RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx& c, int g1, int g2, float margin) {
+RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx c, int g1, int g2, float margin) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   float q[4], A[9], B[9], ca[3], cb[3], t[3], d[3];
-  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * m.geom_bodyid[g1], m.geom_quat + 4 * g1); rg_quat_norm(q); rg_quat2mat(A, q);
-  rg_quat_mul(q, RG_SCRATCH(c) + c.L.xquat + 4 * m.geom_bodyid[g2], m.geom_quat + 4 * g2); rg_quat_norm(q); rg_quat2mat(B, q);
-  rg_mulmat3(ca, A, m.geom_aabb + 6 * g1); rg_add3(ca, ca, RG_SCRATCH(c) + c.L.gxpos + 3 * g1);
-  rg_mulmat3(cb, B, m.geom_aabb + 6 * g2); rg_add3(cb, cb, RG_SCRATCH(c) + c.L.gxpos + 3 * g2);
+  rg_quat_mul(q, RG_SCRATCH(c) + RG_CL(c).xquat + 4 * m.geom_bodyid[g1], m.geom_quat + 4 * g1); rg_quat_norm(q); rg_quat2mat(A, q);
+  rg_quat_mul(q, RG_SCRATCH(c) + RG_CL(c).xquat + 4 * m.geom_bodyid[g2], m.geom_quat + 4 * g2); rg_quat_norm(q); rg_quat2mat(B, q);
+  rg_mulmat3(ca, A, m.geom_aabb + 6 * g1); rg_add3(ca, ca, RG_SCRATCH(c) + RG_CL(c).gxpos + 3 * g1);
+  rg_mulmat3(cb, B, m.geom_aabb + 6 * g2); rg_add3(cb, cb, RG_SCRATCH(c) + RG_CL(c).gxpos + 3 * g2);
   const float a[3] = {m.geom_aabb[6 * g1 + 3] + margin, m.geom_aabb[6 * g1 + 4] + margin, m.geom_aabb[6 * g1 + 5] + margin};
   const float* b = m.geom_aabb + 6 * g2 + 3;
   rg_sub3(d, cb, ca);
@@ -302,7 +302,7 @@ RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx& c, int g1, int g2, float margin)
   return 1;
 }
 
-RG_DEV_NOINLINE int rg_narrow(const RgCtx& c, int g1, int g2, float margin, float* out) {
+RG_DEV_NOINLINE int rg_narrow(const RgCtx c, int g1, int g2, float margin, float* out) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   int cnt = 0;
@@ -387,9 +387,9 @@ RG_DEV void rg_pair(const RG_MODEL_T& m, int k, int& g1, int& g2) {
   if (RG_HAS_PAIRS(m)) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
   else { g1 = RG_LDG(m.pair_geom1 + k); g2 = RG_LDG(m.pair_geom2 + k); }
 }
-RG_DEV_NOINLINE void rg_collision(RgCtx& c) {
+RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   int* cand = (int*)(s + L.cand);
   int* cand2 = (int*)(s + L.cand2);
   int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0;

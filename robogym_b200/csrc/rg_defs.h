@@ -105,6 +105,20 @@ struct RgModel {
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
 };
 
+/* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
+struct RgLayout {
+  int qpos, qvel, ctrl, pid, warm;
+  int lpos, lquat, xpos, xquat, xipos, gxpos, sxpos;
+  int S, M, H;                       /* packed lower triangles; H aliases the block {Sdot,I10,crb} that is dead by then */
+  int Sdot, I10, crb;
+  int bias, smooth, qacc, Ma, search, Mv, qfc, tmp;
+  int tlen, tvel, tJn, tJi, tJv, alen, aforce;
+  int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
+  int el_i, el_D, el_floss, el_jar, el_jv, el_f;
+  int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof;
+  int total;
+};
+
 #ifndef RG_EMU
 /* Device-side model view.  The small arrays of the model are staged in the CTA's dynamic shared memory, so
  * the view stores 32-bit OFFSETS from the shared-memory base instead of pointers: every `m.field[i]` then
@@ -137,6 +151,7 @@ struct RgModelDev {
   const int* mesh_ext;
   float origin[3];
   int small_bytes;
+  RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev
 #define RG_HAS_PAIRS(m) ((m).has_pairs)
@@ -153,19 +168,6 @@ typedef const RgModel* RgMRef;
 #define RG_MREF(m) (&(m))
 #endif
 
-/* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
-struct RgLayout {
-  int qpos, qvel, ctrl, pid, warm;
-  int lpos, lquat, xpos, xquat, xipos, gxpos, sxpos;
-  int S, M, H;                       /* packed lower triangles; H aliases the block {Sdot,I10,crb} that is dead by then */
-  int Sdot, I10, crb;
-  int bias, smooth, qacc, Ma, search, Mv, qfc, tmp;
-  int tlen, tvel, tJn, tJi, tJv, alen, aforce;
-  int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
-  int el_i, el_D, el_floss, el_jar, el_jv, el_f;
-  int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof;
-  int total;
-};
 
 #ifndef RG_EMU
 /* ---- warp helpers (GPU) ---- */

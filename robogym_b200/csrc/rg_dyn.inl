@@ -9,23 +9,34 @@
 #pragma once
 #include "rg_defs.h"
 
+/* Per-environment context.  It is passed BY VALUE (a handful of registers) to the non-inlined stage functions:
+ * behind a reference it would live in local memory and every scratch / layout access would start with an LDL. */
+#ifdef RG_EMU
 struct RgCtx {
   RgMRef mref;           /* the model view (see RG_MDEREF) */
-  const RgLayout& L;
-  float* s;              /* per-warp scratch (emulation build) */
-  int soff;              /* the same, as a float offset into the CTA's dynamic shared memory (CUDA build) */
+  const RgLayout* L;
+  float* s;              /* per-warp scratch */
+  const float* xfrc;     /* this env's xfrc_applied [nbody*6] or nullptr */
+  float timestep;        /* per-env timestep (opt.timestep unless overridden) */
+};
+#define RG_CL(c) (*(c).L)
+#else
+struct RgCtx {
+  RgMRef mref;           /* byte offset of the model view in the CTA's dynamic shared memory */
+  int soff;              /* float offset of this warp's scratch in it */
   const float* xfrc;     /* global: this env's xfrc_applied [nbody*6] or nullptr */
   float timestep;        /* per-env timestep (opt.timestep unless overridden) */
-  int sig;               /* signature of the solver's active set (warp-uniform), see rg_solver_update */
 };
+#define RG_CL(c) (RG_MDEREF((c).mref).L)
+#endif
 
-#define RG_SI(c, k) (((int*)(RG_SCRATCH(c) + (c).L.scal))[k])
-enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4 };
+#define RG_SI(c, k) (((int*)(RG_SCRATCH(c) + RG_CL(c).scal))[k])
+enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4, RG_S_SIG = 5 /* signature of the solver's active set, see rg_solver_update */ };
 
 /* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
 #if !defined(RG_EMU) && defined(RG_PROFILE)
 #define RG_PROF_BEGIN long long prof_t_ = clock64();
-#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) RG_SCRATCH(c)[(c).L.scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
+#define RG_PROF(c, k) { const long long t2_ = clock64(); if ((threadIdx.x & 31) == 0) RG_SCRATCH(c)[RG_CL(c).scal + 8 + (k)] += (float)(t2_ - prof_t_); prof_t_ = clock64(); }
 #else
 #define RG_PROF_BEGIN
 #define RG_PROF(c, k)
@@ -34,13 +45,13 @@ enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4 
 /* Spatial vectors of a kinematic tree are expressed about that tree's own reference point (the
  * world position of its root body), not the world origin: in fp32 the parallel-axis terms m*c^2
  * would otherwise swamp the link inertias of anything that drifts far away (a dropped cube). */
-RG_DEV const float* rg_body_ref(const RgCtx& c, int body) { return RG_SCRATCH(c) + c.L.xpos + 3 * RG_MDEREF(c.mref).body_rootid[body]; }
-RG_DEV const float* rg_dof_ref(const RgCtx& c, int dof) { return rg_body_ref(c, RG_MDEREF(c.mref).dof_bodyid[dof]); }
+RG_DEV const float* rg_body_ref(const RgCtx c, int body) { return RG_SCRATCH(c) + RG_CL(c).xpos + 3 * RG_MDEREF(c.mref).body_rootid[body]; }
+RG_DEV const float* rg_dof_ref(const RgCtx c, int dof) { return rg_body_ref(c, RG_MDEREF(c.mref).dof_bodyid[dof]); }
 /* translational Jacobian column of dof d at world point p */
-RG_DEV void rg_jacp_world(const RgCtx& c, int d, const float* p, float* jp) {
+RG_DEV void rg_jacp_world(const RgCtx c, int d, const float* p, float* jp) {
   float rel[3];
   rg_sub3(rel, p, rg_dof_ref(c, d));
-  rg_jacp(jp, RG_SCRATCH(c) + c.L.S + 6 * d, rel);
+  rg_jacp(jp, RG_SCRATCH(c) + RG_CL(c).S + 6 * d, rel);
 }
 
 RG_DEV int rg_ctz(unsigned x) {
@@ -84,9 +95,9 @@ RG_DEV_NOINLINE void rg_apply_joint(RgMRef mr, const float* qpos, int j, float* 
 }
 
 /* ---------------------------------------------------------------- S1 kinematics + axes */
-RG_DEV_NOINLINE void rg_kinematics(RgCtx& c) {
+RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   /* local frames of every body relative to its parent */
   RG_PHASE_BEGIN
   for (int b = lane; b < m.nbody; b += 32) {
@@ -179,9 +190,9 @@ RG_DEV_NOINLINE void rg_kinematics(RgCtx& c) {
 }
 
 /* ---------------------------------------------------------------- S2/S5 inertias + mass matrix */
-RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
+RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
   for (int b = lane; b < m.nbody; b += 32) {
@@ -238,9 +249,9 @@ RG_DEV_NOINLINE void rg_massmatrix(RgCtx& c) {
 }
 
 /* ---------------------------------------------------------------- velocities + bias force */
-RG_DEV_NOINLINE void rg_bias(RgCtx& c) {
+RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const float* qvel = s + L.qvel;
   RG_PHASE_BEGIN
   for (int d = lane; d < m.nv; d += 32) {
@@ -382,7 +393,7 @@ RG_DEV_NOINLINE float rg_wrap_geom(float* wp, const float* x0, const float* x1, 
   rg_mulmat3(t, gmat, r1); rg_add3(wp + 3, t, gpos);
   return wlen;
 }
-RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
+RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
   if (ba == bb) return;
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   for (int d = 0; d < m.nv; d++) {
@@ -395,16 +406,16 @@ RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx& c, float* J, int ba, const f
 }
 
 /* entry (t, d) of the sparse tendon Jacobian */
-RG_DEV float rg_tendon_J(const RgCtx& c, int t, int d) {
-  const int n = ((const int*)(RG_SCRATCH(c) + c.L.tJn))[t];
-  const int* ji = (const int*)(RG_SCRATCH(c) + c.L.tJi) + RG_TJ * t;
+RG_DEV float rg_tendon_J(const RgCtx c, int t, int d) {
+  const int n = ((const int*)(RG_SCRATCH(c) + RG_CL(c).tJn))[t];
+  const int* ji = (const int*)(RG_SCRATCH(c) + RG_CL(c).tJi) + RG_TJ * t;
   float v = 0.0f;
-  for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[c.L.tJv + RG_TJ * t + k];
+  for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[RG_CL(c).tJv + RG_TJ * t + k];
   return v;
 }
-RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
+RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
   for (int t = lane; t < m.ntendon; t += 32) {
@@ -480,9 +491,9 @@ RG_DEV_NOINLINE void rg_tendon(RgCtx& c) {
 }
 
 /* ---------------------------------------------------------------- S4/S10/S11/S12 passive, PID actuation, smooth force */
-RG_DEV_NOINLINE void rg_forces(RgCtx& c) {
+RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv, flags = m.opt_disableflags[0];
   const float dt = c.timestep;
   /* actuators: transmission, mujoco-py PID bias callback (stateful), force clamp */

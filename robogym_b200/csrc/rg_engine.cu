@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       sm->origin[0] = args.m.origin[0]; sm->origin[1] = args.m.origin[1]; sm->origin[2] = args.m.origin[2];
       sm->small_bytes = small_bytes;
     }
+    for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
 #undef RG_SETPTR
   }

@@ -27,7 +27,7 @@ RG_DEV float rg_impedance(const float* solimp, float xabs) {
   return dmin + y * (dmax - dmin);
 }
 /* R (regulariser) and aref for one row; K is dropped for friction rows */
-RG_DEV_NOINLINE void rg_row_params(const RgCtx& c, const float* solref_in, const float* solimp, float pos, float margin, float vel, float diagApprox,
+RG_DEV_NOINLINE void rg_row_params(const RgCtx c, const float* solref_in, const float* solimp, float pos, float margin, float vel, float diagApprox,
                           int isfriction, float* R, float* aref, float* Bout, float* KIout) {
   float sr0 = solref_in[0];
   const float sr1 = solref_in[1];
@@ -46,12 +46,12 @@ RG_DEV_NOINLINE void rg_row_params(const RgCtx& c, const float* solref_in, const
 }
 
 /* contact-frame Jacobian column of dof d for contact record r (dim components), sign included; 0 if untouched */
-RG_DEV_NOINLINE int rg_contact_col(const RgCtx& c, const float* r, int d, int dim, float* col) {
+RG_DEV_NOINLINE int rg_contact_col(const RgCtx c, const float* r, int d, int dim, float* col) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int b1 = (int)r[18], b2 = (int)r[19];
   const int in1 = rg_dof_in_body(m, b1, d), in2 = rg_dof_in_body(m, b2, d);
   if (in1 == in2) return 0;
-  const float* S = RG_SCRATCH(c) + c.L.S + 6 * d;
+  const float* S = RG_SCRATCH(c) + RG_CL(c).S + 6 * d;
   float jp[3];
   rg_jacp_world(c, d, r + 1, jp);
   const float sg = in2 ? 1.0f : -1.0f;
@@ -62,8 +62,8 @@ RG_DEV_NOINLINE int rg_contact_col(const RgCtx& c, const float* r, int d, int di
   return 1;
 }
 /* same, for a dof already known to be touched (sg = +1 if it moves body 2, -1 if body 1) */
-RG_DEV void rg_contact_col_list(const RgCtx& c, const float* r, int d, float sg, int dim, float* col) {
-  const float* S = RG_SCRATCH(c) + c.L.S + 6 * d;
+RG_DEV void rg_contact_col_list(const RgCtx c, const float* r, int d, float sg, int dim, float* col) {
+  const float* S = RG_SCRATCH(c) + RG_CL(c).S + 6 * d;
   float jp[3];
   rg_jacp_world(c, d, r + 1, jp);
   col[0] = sg * rg_dot3(r + 4, jp);
@@ -74,23 +74,23 @@ RG_DEV void rg_contact_col_list(const RgCtx& c, const float* r, int d, float sg,
 RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k == 3 ? r[15] : r[16]); }
 
 /* y = M x (dense, symmetric) */
-RG_DEV_NOINLINE void rg_matvec_phase(RgCtx& c, int y, int x) {
+RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
   RG_LANE_DECL
   const int nv = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
   for (int i = lane; i < nv; i += 32) {
     float acc = 0.0f;
-    const float* row = s + c.L.M + RG_TRI(i, 0);
+    const float* row = s + RG_CL(c).M + RG_TRI(i, 0);
     for (int k = 0; k <= i; k++) acc += row[k] * s[x + k];
-    for (int k = i + 1; k < nv; k++) acc += s[c.L.M + RG_TRI(k, i)] * s[x + k];
+    for (int k = i + 1; k < nv; k++) acc += s[RG_CL(c).M + RG_TRI(k, i)] * s[x + k];
     s[y + i] = acc;
   }
   RG_PHASE_END
 }
 
 /* in-place envelope Cholesky of the lower triangle of A (row stride nv); env[i] = first nonzero column */
-RG_DEV_NOINLINE void rg_cholesky(RgCtx& c, int A, const int* env) {
+RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
@@ -127,7 +127,7 @@ RG_DEV_NOINLINE void rg_cholesky(RgCtx& c, int A, const int* env) {
   }
 }
 /* x <- (L L^T)^-1 x ; uses `tmp` as staging */
-RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int tmp) {
+RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, int tmp) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
@@ -149,7 +149,7 @@ RG_DEV_NOINLINE void rg_chol_solve(RgCtx& c, int A, const int* env, int x, int t
 }
 
 /* x <- reversed x (solver dof order <-> model dof order) */
-RG_DEV void rg_reverse_phase(RgCtx& c, int x) {
+RG_DEV void rg_reverse_phase(const RgCtx c, int x) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
@@ -159,9 +159,9 @@ RG_DEV void rg_reverse_phase(RgCtx& c, int x) {
 }
 
 /* ---------------------------------------------------------------- S8/S9 constraint elements */
-RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
+RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv, flags = m.opt_disableflags[0];
   int* el_i = (int*)(s + L.el_i);
   int* eldof = (int*)(s + L.eldof);
@@ -322,24 +322,24 @@ RG_DEV_NOINLINE void rg_make_constraints(RgCtx& c) {
 
 /* ---------------------------------------------------------------- S13 Newton solver */
 /* jar of single-row element e for a candidate acceleration vector at offset x */
-RG_DEV float rg_el_Jx(const RgCtx& c, int code, int x) {
+RG_DEV float rg_el_Jx(const RgCtx c, int code, int x) {
   const int type = code & 3, side = (code >> 2) & 1, id = code >> 3;
   const float* s = RG_SCRATCH(c);
   if (type == RG_EL_FLOSS) return s[x + id];
   if (type == RG_EL_JLIMIT) return side ? -s[x + id] : s[x + id];
   float acc = 0.0f;
-  const int n = ((const int*)(s + c.L.tJn))[id];
-  const int* ji = (const int*)(s + c.L.tJi) + RG_TJ * id;
-  for (int k = 0; k < n; k++) acc += s[c.L.tJv + RG_TJ * id + k] * s[x + ji[k]];
+  const int n = ((const int*)(s + RG_CL(c).tJn))[id];
+  const int* ji = (const int*)(s + RG_CL(c).tJi) + RG_TJ * id;
+  for (int k = 0; k < n; k++) acc += s[RG_CL(c).tJv + RG_TJ * id + k] * s[x + ji[k]];
   return side ? -acc : acc;
 }
 
 /* well-mixed per-row hash: the active-set signature is a SUM of these, so it must not be linear in the row id */
 RG_DEV unsigned rg_mix(unsigned h) { h *= 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16; return h; }
 /* forces + cost at the current jar (el_jar, cu); returns total constraint cost; fills el_f and cF */
-RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
+RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
   RG_LANE_DECL
-  const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   LANEVAR(float, part); LANEVAR(int, sigp);
   RG_PHASE_BEGIN
@@ -377,14 +377,14 @@ RG_DEV_NOINLINE float rg_solver_update(RgCtx& c, int nel, int ncon) {
   LV(part) = cost;
   LV(sigp) = (int)(sig & 0x00ffffffu);
   RG_PHASE_END
-  c.sig = RG_WARP_ISUM(sigp);
+  RG_SI(c, RG_S_SIG) = RG_WARP_ISUM(sigp);
   return RG_WARP_SUM(part);
 }
 
 /* out[d] = sum_rows J^T f for every dof (single-row elements, tendon rows, contacts) */
-RG_DEV_NOINLINE void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int ncon) {
+RG_DEV_NOINLINE void rg_JT_force_phase(const RgCtx c, int out, int nel, int tl0, int ncon) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   const int* eldof = (const int*)(s + L.eldof);
   RG_PHASE_BEGIN
@@ -413,9 +413,9 @@ RG_DEV_NOINLINE void rg_JT_force_phase(RgCtx& c, int out, int nel, int tl0, int 
 }
 
 /* el_x[e] = J_e x, cx[k] = Jc_k x  (x = vector at offset xoff); if init, adds -aref / staged velocity terms */
-RG_DEV_NOINLINE void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
+RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_out, int nel, int ncon, int init) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   RG_PHASE_BEGIN
   for (int e = lane; e < nel; e += 32) {
@@ -443,9 +443,9 @@ RG_DEV_NOINLINE void rg_J_mul_phase(RgCtx& c, int xoff, int el_out, int c_out, i
   RG_PHASE_END
 }
 
-RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
+RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   const int nel = RG_SI(c, RG_S_NEL), tl0 = RG_SI(c, RG_S_TL0), ncon = RG_SI(c, RG_S_NCON);
   const int* el_i = (const int*)(s + L.el_i);
@@ -500,7 +500,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
 #ifdef RG_NO_REUSE
     const int refactor = 1;
 #else
-    const int refactor = !(have_factor && c.sig == factor_sig);
+    const int refactor = !(have_factor && RG_SI(c, RG_S_SIG) == factor_sig);
 #endif
     if (refactor) {
     RG_PHASE_BEGIN
@@ -587,7 +587,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     }
     RG_PHASE_END
     rg_cholesky(c, L.H, env);
-    have_factor = 1; factor_sig = c.sig;
+    have_factor = 1; factor_sig = RG_SI(c, RG_S_SIG);
     }
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
     { double cs = 0; for (int i = 0; i < (nv * (nv + 1)) / 2; i++) cs += s[L.H + i] * (1 + (i % 7)); int es = 0; for (int i = 0; i < nv; i++) es += env[i] * (i + 1); printf("    L checksum %.9g env %d\n", cs, es); }
@@ -608,16 +608,16 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
       rg_J_mul_phase(c, L.search, L.el_jv, L.cw, nel, ncon, 0);
       for (int e = 0; e < nel; e++) s[L.el_jar + e] = jar0[e] + eps * s[L.el_jv + e];
       for (int i = 0; i < 6 * ncon; i++) s[L.cu + i] = cu0[i] + eps * s[L.cw + i];
-      const int sig_before = c.sig;
+      const int sig_before = RG_SI(c, RG_S_SIG);
       rg_solver_update(c, nel, ncon);
       rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
       float num = 0, den = 0, dotg = 0;
       for (int d = 0; d < nv; d++) { const float g1 = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d]; const float pred = (1.0f - eps) * g0v[d]; num += (g1 - pred) * (g1 - pred); den += g0v[d] * g0v[d]; dotg += g0v[d] * s[L.search + d]; }
-      printf("    FD check: |g(q+eps s) - (1-eps) g|/|g| = %.3g  (sig %d -> %d)  g.s %.4g\n", sqrtf(num / den), sig_before, c.sig, dotg);
+      printf("    FD check: |g(q+eps s) - (1-eps) g|/|g| = %.3g  (sig %d -> %d)  g.s %.4g\n", sqrtf(num / den), sig_before, RG_SI(c, RG_S_SIG), dotg);
       for (int d = 0; d < nv; d++) { s[L.qacc + d] = q0[d]; s[L.Ma + d] = ma0[d]; s[L.qfc + d] = qfc0[d]; }
       for (int e = 0; e < nel; e++) { s[L.el_jar + e] = jar0[e]; s[L.el_f + e] = f0[e]; }
       for (int i = 0; i < 6 * ncon; i++) { s[L.cu + i] = cu0[i]; s[L.cF + i] = cf0[i]; }
-      c.sig = sig_before;
+      RG_SI(c, RG_S_SIG) = sig_before;
     }
 #endif
     /* line search along `search` */
@@ -697,7 +697,7 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
     }
     const float improvement = scale * (cost - newcost);
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
-    printf("  it %d cost %.9g new %.9g impr %.3g alpha %.6g gnorm %.3g refactor %d sig %d\n", iter, cost, newcost, improvement, alpha, gnorm, refactor, c.sig);
+    printf("  it %d cost %.9g new %.9g impr %.3g alpha %.6g gnorm %.3g refactor %d sig %d\n", iter, cost, newcost, improvement, alpha, gnorm, refactor, RG_SI(c, RG_S_SIG));
 #endif
     cost = newcost;
     /* fp32: cost differences below ~2 ulp of the cost itself are rounding noise, not progress */
@@ -714,9 +714,9 @@ RG_DEV_NOINLINE void rg_solve(RgCtx& c) {
 }
 
 /* ---------------------------------------------------------------- S15 semi-implicit Euler */
-RG_DEV_NOINLINE void rg_euler(RgCtx& c) {
+RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = c.L; float* s = RG_SCRATCH(c);
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   const float h = c.timestep;
   int* env = (int*)(s + L.env);

@@ -68,7 +68,7 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
 }
 
 /* mj_forward: everything but the integrator */
-RG_DEV_NOINLINE void rg_forward(RgCtx& c) {
+RG_DEV_NOINLINE void rg_forward(const RgCtx c) {
   RG_PROF_BEGIN
   RG_CTA_SYNC(); rg_kinematics(c); RG_PROF(c, 0)
   RG_CTA_SYNC(); rg_massmatrix(c); RG_PROF(c, 1)
@@ -81,10 +81,17 @@ RG_DEV_NOINLINE void rg_forward(RgCtx& c) {
 }
 
 /* `store` == 0: a padding iteration that keeps this warp in step with its CTA (same barriers), results discarded */
-RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L, float* s_in, int soff, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
+RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, int soff, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(mr);
-  RgCtx c = {mr, L, s_in, soff, io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr, io.timestep ? io.timestep[env] : m.opt_timestep[0], 0};
+  const float* xfrc_env = io.xfrc ? io.xfrc + (size_t)env * m.nbody * 6 : nullptr;
+  const float dt_env = io.timestep ? io.timestep[env] : m.opt_timestep[0];
+#ifdef RG_EMU
+  const RgCtx c = {mr, &L_in, s_in, xfrc_env, dt_env};
+#else
+  const RgCtx c = {mr, soff, xfrc_env, dt_env};   /* the layout travels inside the shared-memory model view */
+#endif
+  const RgLayout& L = RG_CL(c);
   float* s = RG_SCRATCH(c);
   const int npid = 3 * m.nu;
   /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
