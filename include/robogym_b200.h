@@ -83,6 +83,11 @@ int rg_batch_bind(rg_batch* b, int field, void* device_ptr);
  * to the world must be given relative to rg_model_origin(). */
 int rg_batch_bind_param(rg_batch* b, const char* name, void* device_ptr);
 int rg_model_origin(const rg_model* m, float origin[3]);
+/* Work-ordered scheduling (default on; RG_BALANCE=0 in the environment turns it off at create): every launch records a
+ * per-environment work estimate and the next launch groups environments of similar cost into the same CTA, which
+ * shortens the waits at the per-stage CTA barriers.  Results are independent of the setting.  No reference
+ * counterpart: mujoco-py steps one MjSim at a time (robogym/mujoco/simulation_interface.py:176). */
+int rg_batch_set_balance(rg_batch* b, int on);
 /* launch geometry actually used (for reporting): CTAs, warps per CTA, dynamic shared bytes */
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps_per_cta, int* smem_bytes);
 

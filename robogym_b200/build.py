@@ -34,7 +34,20 @@ def build_profile():
     return out
 
 
+def build_variant(tag, defines):
+    """Experimental build with extra -D flags (A/B measurements): librobogym_b200_<tag>.so."""
+    out = os.path.join(HERE, "librobogym_b200_%s.so" % tag)
+    cmd = nvcc_cmd(tuple("-D" + d for d in defines))
+    cmd[cmd.index("-o") + 1] = out
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     if "--profile" in sys.argv:
         print(build_profile())
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):   # --variant=skew1:RG_SKEW=1
+            tag, _, defs = a[len("--variant="):].partition(":")
+            print(build_variant(tag, [d for d in defs.split(",") if d]))

@@ -10,7 +10,7 @@
 #include "rg_dyn.inl"
 
 #if defined(RG_EMU) && defined(RG_STATS)
-static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_stat_mpr_hit = 0, rg_stat_narrow = 0, rg_stat_maxsup = 0, rg_stat_cur = 0;
+static long long rg_stat_hist[2][64] = {{0}}; static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_stat_mpr_hit = 0, rg_stat_narrow = 0, rg_stat_maxsup = 0, rg_stat_cur = 0;
 #define RG_STAT(x) x
 #else
 #define RG_STAT(x)
@@ -18,7 +18,8 @@ static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_sta
 struct RgGeomView {
   float pos[3], mat[9], size[3];
   int type, vadr, vnum, mid;
-  int hint;              /* last support vertex (hill-climb warm start), -1 = pick an extreme vertex */
+  int hint;              /* adjacency range of the last support vertex (hill-climb warm start), -1 = pick an extreme vertex */
+  float hv[3];           /* ... and its local coordinates */
   float halfmargin;
 };
 
@@ -33,15 +34,15 @@ RG_DEV void rg_geom_view(const RgCtx c, int g, float margin, RgGeomView& v) {
   rg_copy3(v.size, m.geom_size + 3 * g);
   v.type = m.geom_type[g];
   v.hint = -1;
+  v.hv[0] = v.hv[1] = v.hv[2] = 0.0f;
   v.halfmargin = 0.5f * margin;
   v.vadr = 0; v.vnum = 0; v.mid = 0;
   if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.mid = mid; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
 }
 
-RG_DEV void rg_support(const RG_MODEL_T& m, RgGeomView& v, const float* dir, float* res) {
-  float dl[3], loc[3] = {0, 0, 0};
-  RG_STAT(rg_stat_support++; rg_stat_cur++;)
-  rg_mulmatT3(dl, v.mat, dir);
+/* support point of a primitive in its own frame */
+RG_DEV void rg_support_prim(const RgGeomView& v, const float* dl, float* loc) {
+  loc[0] = loc[1] = loc[2] = 0.0f;
   switch (v.type) {
     case RG_GEOM_SPHERE: rg_scl3(loc, dl, v.size[0]); break;
     case RG_GEOM_BOX:
@@ -63,49 +64,115 @@ RG_DEV void rg_support(const RG_MODEL_T& m, RgGeomView& v, const float* dir, flo
       const float n = sqrtf(rg_dot3(t, t));
       if (n > 1e-20f) { loc[0] = t[0] * v.size[0] / n; loc[1] = t[1] * v.size[1] / n; loc[2] = t[2] * v.size[2] / n; }
     } break;
-    case RG_GEOM_MESH: {
-      /* steepest-ascent hill climb on the convex hull's edge graph; neighbour coordinates are stored
-         inline (mesh_nbr) so one step costs one dependent load level, not two */
-      const float* vert = m.mesh_vert + 3 * v.vadr;
-      const int* adjadr = m.mesh_adjadr + v.vadr;
-      int cur = v.hint;
-      if (cur < 0) {
-        const float ax = fabsf(dl[0]), ay = fabsf(dl[1]), az = fabsf(dl[2]);
-        const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-        cur = RG_LDG(m.mesh_ext + 6 * v.mid + 2 * axis + (dl[axis] >= 0 ? 0 : 1));
-      }
-      float bx = RG_LDG(vert + 3 * cur), by = RG_LDG(vert + 3 * cur + 1), bz = RG_LDG(vert + 3 * cur + 2);
-      float best = bx * dl[0] + by * dl[1] + bz * dl[2];
-      for (int guard = 0; guard < v.vnum; guard++) {
-        const int a0 = RG_LDG(adjadr + cur), a1 = RG_LDG(adjadr + cur + 1);
-        int nxt = cur;
-        for (int a = a0; a < a1; a++) {
-          float n4[4];
-          RG_LDG4(m.mesh_nbr, a, n4);
-          const float dd = n4[0] * dl[0] + n4[1] * dl[1] + n4[2] * dl[2];
-          if (dd > best) { best = dd; nxt = rg_f2i(n4[3]); bx = n4[0]; by = n4[1]; bz = n4[2]; }
-        }
-        if (nxt == cur) break;
-        cur = nxt;
-        RG_STAT(rg_stat_climb++;)
-      }
-      v.hint = cur;
-      loc[0] = bx; loc[1] = by; loc[2] = bz;
-    } break;
     default: break;
   }
+}
+
+/* ---- hull support mapping: steepest-ascent hill climb on the convex hull's edge graph.  A vertex is known by its
+ * adjacency range (first entry | degree << 20) in mesh_nbr; every entry carries the neighbour's coordinates AND the
+ * neighbour's own range, so one climb step is ONE level of dependent loads, and the RG_CLIMB_W entries of a step are
+ * fetched together (independent loads in flight) before any of them is compared. */
+#define RG_CLIMB_W 6
+struct RgClimb { int pk; float b[3], best; };
+
+RG_DEV void rg_climb_init(const RG_MODEL_T& m, const RgGeomView& v, const float* dl, RgClimb& st) {
+  if (v.hint >= 0) { st.pk = v.hint; rg_copy3(st.b, v.hv); }
+  else {
+    const float ax = fabsf(dl[0]), ay = fabsf(dl[1]), az = fabsf(dl[2]);
+    const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    float n4[4];
+    RG_LDG4(m.mesh_ext, 6 * v.mid + 2 * axis + (dl[axis] >= 0 ? 0 : 1), n4);
+    rg_copy3(st.b, n4); st.pk = rg_f2i(n4[3]);
+  }
+  st.best = st.b[0] * dl[0] + st.b[1] * dl[1] + st.b[2] * dl[2];
+}
+/* entries [base, base + RG_CLIMB_W) of the current vertex (clamped to its last entry: a repeated entry never wins the
+   strict comparison twice, so the visiting order -- and with it every tie-break -- is that of a plain loop) */
+RG_DEV void rg_climb_load(const RG_MODEL_T& m, int pk, int base, float n[RG_CLIMB_W][4]) {
+  const int a0 = pk & 0xFFFFF, last = (int)((unsigned)pk >> 20) - 1;
+#pragma unroll
+  for (int i = 0; i < RG_CLIMB_W; i++) { const int k = base + i < last ? base + i : last; RG_LDG4(m.mesh_nbr, a0 + k, n[i]); }
+}
+RG_DEV void rg_climb_eval(const float n[RG_CLIMB_W][4], const float* dl, RgClimb& st, int& nxt) {
+#pragma unroll
+  for (int i = 0; i < RG_CLIMB_W; i++) {
+    const float dd = n[i][0] * dl[0] + n[i][1] * dl[1] + n[i][2] * dl[2];
+    if (dd > st.best) { st.best = dd; nxt = rg_f2i(n[i][3]); st.b[0] = n[i][0]; st.b[1] = n[i][1]; st.b[2] = n[i][2]; }
+  }
+}
+/* one step; returns 1 when the climb moved to a better neighbour */
+RG_DEV int rg_climb_step(const RG_MODEL_T& m, const float* dl, RgClimb& st) {
+  const int deg = (int)((unsigned)st.pk >> 20);
+  int nxt = st.pk;
+  for (int base = 0; base < deg; base += RG_CLIMB_W) {
+    float n[RG_CLIMB_W][4];
+    rg_climb_load(m, st.pk, base, n);
+    rg_climb_eval(n, dl, st, nxt);
+  }
+  const int moved = nxt != st.pk;
+  st.pk = nxt;
+  RG_STAT(rg_stat_climb += moved;)
+  return moved;
+}
+
+RG_DEV void rg_support_world(const RgGeomView& v, const float* loc, const float* dir, float* res) {
   rg_mulmat3(res, v.mat, loc);
   res[0] += v.pos[0] + dir[0] * v.halfmargin;
   res[1] += v.pos[1] + dir[1] * v.halfmargin;
   res[2] += v.pos[2] + dir[2] * v.halfmargin;
 }
 
+RG_DEV void rg_support(const RG_MODEL_T& m, RgGeomView& v, const float* dir, float* res) {
+  float dl[3], loc[3];
+  RG_STAT(rg_stat_support++; rg_stat_cur++;)
+  rg_mulmatT3(dl, v.mat, dir);
+  if (v.type == RG_GEOM_MESH) {
+    RgClimb st;
+    rg_climb_init(m, v, dl, st);
+    for (int guard = 0; guard < v.vnum; guard++) if (!rg_climb_step(m, dl, st)) break;
+    v.hint = st.pk; rg_copy3(v.hv, st.b);
+    rg_copy3(loc, st.b);
+  } else rg_support_prim(v, dl, loc);
+  rg_support_world(v, loc, dir, res);
+}
+
 struct RgSup { float v[3], v1[3], v2[3]; };
 
+/* support of the Minkowski difference o1 - o2.  For two hulls the two climbs advance together, so that the loads of
+   both are in flight at the same time (the narrow phase is a chain of dependent L2 round trips, not arithmetic). */
 RG_DEV void rg_mpr_support(const RG_MODEL_T& m, RgGeomView& o1, RgGeomView& o2, const float* dir, RgSup& sp) {
   const float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  rg_support(m, o1, dir, sp.v1);
-  rg_support(m, o2, nd, sp.v2);
+  if (o1.type == RG_GEOM_MESH && o2.type == RG_GEOM_MESH) {
+    float d1[3], d2[3];
+    RG_STAT(rg_stat_support += 2; rg_stat_cur += 2;)
+    rg_mulmatT3(d1, o1.mat, dir);
+    rg_mulmatT3(d2, o2.mat, nd);
+    RgClimb s1, s2;
+    rg_climb_init(m, o1, d1, s1);
+    rg_climb_init(m, o2, d2, s2);
+    int go1 = 1, go2 = 1;
+    for (int guard = 0; guard < o1.vnum + o2.vnum && (go1 | go2); guard++) {
+      const int deg1 = go1 ? (int)((unsigned)s1.pk >> 20) : 0, deg2 = go2 ? (int)((unsigned)s2.pk >> 20) : 0;
+      int n1 = s1.pk, n2 = s2.pk;
+      for (int base = 0; base < deg1 || base < deg2; base += RG_CLIMB_W) {
+        float e1[RG_CLIMB_W][4], e2[RG_CLIMB_W][4];
+        if (base < deg1) rg_climb_load(m, s1.pk, base, e1);
+        if (base < deg2) rg_climb_load(m, s2.pk, base, e2);
+        if (base < deg1) rg_climb_eval(e1, d1, s1, n1);
+        if (base < deg2) rg_climb_eval(e2, d2, s2, n2);
+      }
+      go1 = go1 && n1 != s1.pk; go2 = go2 && n2 != s2.pk;
+      RG_STAT(rg_stat_climb += go1 + go2;)
+      s1.pk = n1; s2.pk = n2;
+    }
+    o1.hint = s1.pk; rg_copy3(o1.hv, s1.b);
+    o2.hint = s2.pk; rg_copy3(o2.hv, s2.b);
+    rg_support_world(o1, s1.b, dir, sp.v1);
+    rg_support_world(o2, s2.b, nd, sp.v2);
+  } else {
+    rg_support(m, o1, dir, sp.v1);
+    rg_support(m, o2, nd, sp.v2);
+  }
   rg_sub3(sp.v, sp.v1, sp.v2);
 }
 RG_DEV int rg_mpr_zero(float x) { return fabsf(x) < RG_EPS; }
@@ -178,8 +245,19 @@ RG_DEV void rg_find_pos3(const float* v0, const float* c1, const float* c2, cons
 }
 
 /* depth >= 0 with dir,pos when the inflated geoms intersect; -1 otherwise */
-RG_DEV_NOINLINE float rg_mpr(RgMRef mr, RgGeomView& o1, RgGeomView& o2, float tol, int maxiter, float* dir_out, float* pos) {
-  const RG_MODEL_T& m = RG_MDEREF(mr);
+/* The geom views are built HERE (not handed in by reference): a reference into the caller's frame would pin them in
+   local memory, and with ~28 KB of L1 beside the shared-memory scratch every access to them is an L2 round trip. */
+struct RgMprOut { float depth, dir[3], pos[3]; };
+RG_DEV_NOINLINE RgMprOut rg_mpr(const RgCtx c, int g1, int g2, float margin) {
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const float tol = m.opt_mpr_tolerance[0];
+  const int maxiter = m.opt_mpr_iterations[0];
+  RgGeomView o1, o2;
+  rg_geom_view(c, g1, margin, o1);
+  rg_geom_view(c, g2, margin, o2);
+  RgMprOut out;
+  float* dir_out = out.dir; float* pos = out.pos;
+  dir_out[0] = dir_out[1] = dir_out[2] = 0.0f; pos[0] = pos[1] = pos[2] = 0.0f;
   enum { S_V1 = 0, S_V2 = 1, S_V3 = 2, S_REFINE = 3, S_PENETR = 4, S_DONE = 5 };
   RgSup P1, P2, P3, sp;
   float v0[3], dir[3], va[3], vb[3];
@@ -189,7 +267,8 @@ RG_DEV_NOINLINE float rg_mpr(RgMRef mr, RgGeomView& o1, RgGeomView& o2, float to
   rg_scl3(dir, v0, -1.0f); rg_normalize3(dir);
   int state = S_V1, pen_it = 0;
   P1 = RgSup(); P2 = RgSup(); P3 = RgSup();
-  for (int it = 0; it < 200 + maxiter && state != S_DONE; it++) {
+  int it = 0;
+  for (; it < 200 + maxiter && state != S_DONE; it++) {
     rg_mpr_support(m, o1, o2, dir, sp);
     const float dot = rg_dot3(sp.v, dir);
     if (state == S_V1) {
@@ -254,7 +333,9 @@ RG_DEV_NOINLINE float rg_mpr(RgMRef mr, RgGeomView& o1, RgGeomView& o2, float to
       pen_it++;
     }
   }
-  return result;
+  RG_STAT(rg_stat_hist[result >= 0][it < 63 ? it : 63]++;)
+  out.depth = result;
+  return out;
 }
 
 RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
@@ -369,16 +450,12 @@ RG_DEV_NOINLINE int rg_narrow(const RgCtx c, int g1, int g2, float margin, float
     return cnt;
   }
   RG_STAT(rg_stat_mpr++; rg_stat_cur = 0;)
-  RgGeomView o1, o2;
-  rg_geom_view(c, g1, margin, o1);
-  rg_geom_view(c, g2, margin, o2);
-  float dir[3], pos[3];
-  const float depth = rg_mpr(RG_MREF(m), o1, o2, m.opt_mpr_tolerance[0], m.opt_mpr_iterations[0], dir, pos);
-  RG_STAT(if (rg_stat_cur > rg_stat_maxsup) rg_stat_maxsup = rg_stat_cur; if (depth >= 0) rg_stat_mpr_hit++;)
-  if (depth < 0 || rg_dot3(dir, dir) < 0.5f) return 0;
-  out[0] = margin - depth;
-  rg_copy3(out + 1, pos);
-  rg_copy3(out + 4, dir);
+  const RgMprOut r = rg_mpr(c, g1, g2, margin);
+  RG_STAT(if (rg_stat_cur > rg_stat_maxsup) rg_stat_maxsup = rg_stat_cur; if (r.depth >= 0) rg_stat_mpr_hit++;)
+  if (r.depth < 0 || rg_dot3(r.dir, r.dir) < 0.5f) return 0;
+  out[0] = margin - r.depth;
+  rg_copy3(out + 1, r.pos);
+  rg_copy3(out + 4, r.dir);
   return 1;
 }
 
@@ -392,7 +469,7 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   int* cand = (int*)(s + L.cand);
   int* cand2 = (int*)(s + L.cand2);
-  int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0;
+  int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0, work = 0;
   const int cap = (m.nconmax > 0 && m.nconmax < RG_NCON) ? m.nconmax : RG_NCON;
   const int enabled = !(m.opt_disableflags[0] & (RG_DSBL_CONTACT | RG_DSBL_CONSTRAINT));
   RG_PROF_BEGIN
@@ -460,6 +537,7 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
     /* stage C: narrow phase, one pair per lane, once a full warp of work is queued (or at the end) */
     if (n2 >= 32 || (n2 > 0 && k0 >= m.npair && n1 == 0)) {
       const int n = n2 < 32 ? n2 : 32;
+      work += n;
       LANEVAR(int, cnt); LANEVAR(int, cpos); LANEVAR(int, keep);
       LANEARR(float, cb, 28);
       int tot;
@@ -532,6 +610,6 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
     RG_PROF(c, 11)
   }
   RG_PHASE_BEGIN
-  if (lane == 0) { RG_SI(c, RG_S_NCON) = ncon; RG_SI(c, RG_S_WARN) |= warn; }
+  if (lane == 0) { RG_SI(c, RG_S_NCON) = ncon; RG_SI(c, RG_S_WARN) |= warn; RG_SI(c, RG_S_WORK) += work; }
   RG_PHASE_END
 }

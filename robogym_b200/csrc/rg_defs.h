@@ -57,15 +57,51 @@ extern __shared__ __align__(128) unsigned char rg_smem_raw[];
 /* The warps of a CTA walk the step in loose lock-step (one barrier per stage / Newton iteration): the
  * kernel's code is far larger than the instruction cache, so keeping the warps in the same stage lets
  * one instruction fetch feed all of them.  Every warp executes the same number of barriers. */
+#ifndef RG_SKEW
+#define RG_SKEW 0
+#endif
+#if RG_SKEW == 0
 #define RG_CTA_SYNC() __syncthreads()
+#else
+/* Skewed variant: a warp may run up to RG_SKEW stages ahead of the slowest warp of its CTA.  Stage boundary k is an
+ * mbarrier (ring of RG_SKEW+1): arrive on boundary k, then wait for boundary k-RG_SKEW.  A warp passes boundary k+R-1
+ * only after boundary k completed, so a ring slot is never re-armed before its previous phase is over. */
+#define RG_BAR_RING (RG_SKEW + 1)
+__shared__ __align__(8) unsigned long long rg_stage_bar[RG_BAR_RING];
+__shared__ int rg_stage_k[32];
+__device__ __forceinline__ void rg_stage_sync() {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    const int k = rg_stage_k[w];
+    rg_stage_k[w] = k + 1;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(&rg_stage_bar[k % RG_BAR_RING]);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+    if (k >= RG_SKEW) {
+      const int j = k - RG_SKEW;
+      const unsigned b = (unsigned)__cvta_generic_to_shared(&rg_stage_bar[j % RG_BAR_RING]);
+      const unsigned parity = (unsigned)((j / RG_BAR_RING) & 1);
+      unsigned done = 0;
+      while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(b), "r"(parity) : "memory");
+    }
+  }
+  __syncwarp();
+}
+#define RG_CTA_SYNC() rg_stage_sync()
+#endif
 #define RG_CTA_ANY(x) __syncthreads_or(x)
 #define RG_SINCOS(x, sn, cs) __sincosf(x, sn, cs)
 #endif
 
 #define RG_MINVAL 1e-15f
 #define RG_EPS 1.1920929e-07f
-#define RG_NCON 32       /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
-#define RG_NEL 64        /* single-row constraint elements (friction loss + limits) */
+#ifndef RG_NCON
+#define RG_NCON 32
+#endif                   /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
+#ifndef RG_NEL
+#define RG_NEL 64
+#endif                   /* single-row constraint elements (friction loss + limits) */
 #define RG_CON_STRIDE 24
 #define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
 #define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds) */
@@ -98,9 +134,9 @@ struct RgModel {
 #undef RG_F
   const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
   const int* dof_treeroot;     /* first dof of the kinematic tree a dof belongs to (Cholesky envelope) */
-  const float* mesh_nbr;       /* [nmeshadj][4]: neighbour vertex x,y,z + its local index (as int bits): hill-climb without a second indirection */
+  const float* mesh_nbr;       /* [nmeshadj][4]: neighbour vertex x,y,z + that vertex's own adjacency range (first | degree << 20, as int bits) */
   const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
-  const int* mesh_ext;         /* [nmesh][6]: extreme vertices along +x,-x,+y,-y,+z,-z (hill-climb starting points) */
+  const float* mesh_ext;       /* [nmesh][6][4]: extreme vertices along +x,-x,+y,-y,+z,-z in the same x,y,z,range format (hill-climb starting points) */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
 };
@@ -148,7 +184,7 @@ struct RgModelDev {
   RgArr<unsigned short> pair_packed;
   int has_pairs;
   const float* mesh_nbr;
-  const int* mesh_ext;
+  const float* mesh_ext;
   float origin[3];
   int small_bytes;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */

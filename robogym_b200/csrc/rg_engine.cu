@@ -21,7 +21,9 @@
 #include "rg_step.inl"
 #include "rg_host.h"
 
+#ifndef RG_MAX_WARPS
 #define RG_MAX_WARPS 10
+#endif
 
 static thread_local std::string g_err;
 static int rg_fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -40,6 +42,7 @@ struct RgKernelArgs {
   int over_cnt[RG_MAX_PARAM_OVERRIDES];          /* floats per environment */
   int over_dst[RG_MAX_PARAM_OVERRIDES];          /* float offset inside the per-warp override area */
   const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] in global memory */
+  const int* order;   /* [nenv] slot -> environment (work-sorted, see rg_order_kernel) or nullptr = identity */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,6 +63,10 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   if (threadIdx.x == 0) {
     const uint32_t bar = rg_smem_u32(&mbar);
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+#if RG_SKEW > 0
+    for (int i = 0; i < RG_BAR_RING; i++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(rg_smem_u32(&rg_stage_bar[i])), "r"((uint32_t)args.warps));
+    for (int i = 0; i < 32; i++) rg_stage_k[i] = 0;
+#endif
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)small_bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -122,9 +129,9 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   const int stride = gridDim.x * args.warps;
   const int iters = (args.io.nenv + stride - 1) / stride;
   for (int it = 0; it < iters; it++) {
-    const int env = it * stride + blockIdx.x * args.warps + warp;
-    const int valid = env < args.io.nenv;
-    const int e = valid ? env : args.io.nenv - 1;
+    const int slot = it * stride + blockIdx.x * args.warps + warp;
+    const int valid = slot < args.io.nenv;
+    const int e = args.order ? args.order[valid ? slot : args.io.nenv - 1] : (valid ? slot : args.io.nenv - 1);
     if (args.nover > 0) {
       const int lane = threadIdx.x & 31;
       for (int i = lane; i < (int)(sizeof(RgModelDev) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
@@ -150,6 +157,41 @@ __global__ void rg_reset_kernel(RgModel m, RgBatchIO io, const uint8_t* mask) {
   if (threadIdx.x == 0) { if (io.time) io.time[env] = 0.0f; if (io.warn) io.warn[env] = 0; }
 }
 
+/* Work-ordered scheduling.  The warps of a CTA meet at a barrier after every stage, so a CTA runs at the pace of
+ * its slowest environment (most Newton iterations / narrow-phase pairs).  Contact configurations persist from one
+ * env-step to the next, so the step kernel records a work estimate per environment and this kernel turns it into
+ * the slot -> environment table of the NEXT launch (counting sort, one CTA): environments of similar cost share a
+ * CTA.  Results do not depend on the table -- environments are independent -- only the barrier waits do. */
+#define RG_ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) rg_order_kernel(const int* __restrict__ cost, int* __restrict__ order, int nenv) {
+  __shared__ int bin[RG_ORDER_BINS];
+  __shared__ int wsum[32];
+  const int t = threadIdx.x;
+  bin[t] = 0;
+  __syncthreads();
+  for (int e = t; e < nenv; e += 1024) atomicAdd(&bin[min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1);
+  __syncthreads();
+  /* exclusive scan of the 1024 bins */
+  const int v = bin[t];
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((t & 31) >= o) x += y; }
+  if ((t & 31) == 31) wsum[t >> 5] = x;
+  __syncthreads();
+  if (t < 32) {
+    int w = wsum[t];
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (t >= o) w += y; }
+    wsum[t] = w;
+  }
+  __syncthreads();
+  bin[t] = x - v + (t >= 32 ? wsum[(t >> 5) - 1] : 0);
+  __syncthreads();
+  for (int e = t; e < nenv; e += 1024) order[atomicAdd(&bin[min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1)] = e;
+}
+__global__ void rg_iota_kernel(int* order, int* cost, int nenv) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nenv) { order[e] = e; cost[e] = 0; }
+}
+
 /* ------------------------------------------------------------------ host objects */
 struct rg_model {
   RgHostModel hm;
@@ -170,6 +212,9 @@ struct rg_batch {
   int over_floats = 0;
   const float* over_ptr[RG_MAX_PARAM_OVERRIDES];
   std::string over_name[RG_MAX_PARAM_OVERRIDES];
+  int* d_order = nullptr;  /* slot -> environment of the next launch */
+  int* d_cost = nullptr;   /* work estimate written by the last launch */
+  int balance = 1;
 };
 
 static void rg_wire_device_view(rg_model* mm) {
@@ -316,10 +361,27 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   for (int i = 0; i < RG_NFIELDS; i++) b->ptr[i] = nullptr;
   const int rc = rg_batch_size(b);
   if (rc) { delete b; return rc; }
+  const char* benv = getenv("RG_BALANCE");
+  if (benv) b->balance = atoi(benv) != 0;
+  cudaError_t e = cudaMalloc((void**)&b->d_order, sizeof(int) * (size_t)nenv);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
+  if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, nenv); e = cudaDeviceSynchronize(); }
+  if (e != cudaSuccess) { std::string msg = std::string("rg_batch_create: CUDA: ") + cudaGetErrorString(e); rg_batch_destroy(b); return rg_fail(-2, msg); }
   *out = b;
   return 0;
 }
-void rg_batch_destroy(rg_batch* b) { delete b; }
+void rg_batch_destroy(rg_batch* b) {
+  if (!b) return;
+  if (b->d_order) cudaFree(b->d_order);
+  if (b->d_cost) cudaFree(b->d_cost);
+  delete b;
+}
+
+int rg_batch_set_balance(rg_batch* b, int on) {
+  if (!b) return rg_fail(-1, "rg_batch_set_balance: null argument");
+  b->balance = on != 0;
+  return 0;
+}
 
 int rg_batch_bind(rg_batch* b, int field, void* p) {
   if (!b || field < 0 || field >= RG_NFIELDS) return rg_fail(-1, "rg_batch_bind: bad argument");
@@ -388,6 +450,7 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   io.xfrc = (const float*)b->ptr[RG_FIELD_XFRC]; io.timestep = (const float*)b->ptr[RG_FIELD_TIMESTEP];
   io.site_xpos = (float*)b->ptr[RG_FIELD_SITE_XPOS]; io.body_xpos = (float*)b->ptr[RG_FIELD_BODY_XPOS]; io.body_xquat = (float*)b->ptr[RG_FIELD_BODY_XQUAT];
   io.geom_xpos = (float*)b->ptr[RG_FIELD_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_FIELD_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_FIELD_QACC];
+  io.cost = b->balance ? b->d_cost : nullptr;
   io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;
 }
@@ -403,10 +466,15 @@ int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
   args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
   args.nover = b->nover;
   args.over_floats = b->over_floats;
+  args.order = b->balance ? b->d_order : nullptr;
   for (int i = 0; i < b->nover; i++) { args.over_off[i] = b->over_off[i]; args.over_cnt[i] = b->over_cnt[i]; args.over_dst[i] = b->over_dst[i]; args.over_ptr[i] = b->over_ptr[i]; }
   RG_CUDA(cudaSetDevice(b->model->device));
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());
+  if (b->balance && nsub > 0) {
+    rg_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b->d_cost, b->d_order, b->nenv);
+    RG_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 int rg_forward(rg_batch* b, void* stream) { return rg_step(b, 0, 1, stream); }

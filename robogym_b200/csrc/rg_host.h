@@ -73,7 +73,7 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   hm.small_bytes = dst;
   for (size_t i = first_big; i < names.size(); i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
   dst = rg_align16(dst); const size_t off_nbr = dst; dst += 16 * (size_t)m.nmeshadj;
-  dst = rg_align16(dst); const size_t off_ext = dst; dst += 4 * 6 * (size_t)m.nmesh;
+  dst = rg_align16(dst); const size_t off_ext = dst; dst += 16 * 6 * (size_t)m.nmesh;
   dst = rg_align16(dst);
   hm.arena.assign(dst, 0);
   char* base = hm.arena.data();
@@ -109,22 +109,38 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   m.dof_treeroot = treeroot;
   hm.offsets.push_back(off_subtree);
   hm.offsets.push_back(off_treeroot);
-  /* hull neighbour table with inline coordinates + extreme-vertex starting points */
+  /* hull neighbour table with inline coordinates + extreme-vertex starting points.  The 4th word of an entry is the
+     neighbour's OWN adjacency range (first entry | degree << 20), so a hill-climb step is one dependent load level:
+     the entries of the vertex it moves to are addressed without another lookup. */
   float* nbr = (float*)(base + off_nbr);
-  int* ext = (int*)(base + off_ext);
+  float* ext = (float*)(base + off_ext);
+  if (m.nmeshadj >= (1 << 20)) { err = "hull adjacency too large for the packed neighbour table"; return false; }
   for (int i = 0; i < m.nmesh; i++) {
     const int va = m.mesh_vertadr[i], vn = m.mesh_vertnum[i];
     const float* v = m.mesh_vert + 3 * va;
-    for (int k = 0; k < vn; k++)
+    auto packed = [&](int k) {
+      const int a0 = m.mesh_adjadr[va + k], deg = m.mesh_adjadr[va + k + 1] - a0;
+      return (int)((unsigned)a0 | ((unsigned)(deg > 4095 ? 4095 : deg) << 20));
+    };
+    for (int k = 0; k < vn; k++) {
+      if (m.mesh_adjadr[va + k + 1] - m.mesh_adjadr[va + k] > 4095) { err = "hull vertex degree too large"; return false; }
       for (int a = m.mesh_adjadr[va + k]; a < m.mesh_adjadr[va + k + 1]; a++) {
         const int nb = m.mesh_adj[a];
+        const int pk = packed(nb);
         nbr[4 * a] = v[3 * nb]; nbr[4 * a + 1] = v[3 * nb + 1]; nbr[4 * a + 2] = v[3 * nb + 2];
-        memcpy(&nbr[4 * a + 3], &nb, 4);
+        memcpy(&nbr[4 * a + 3], &pk, 4);
       }
+    }
     for (int ax = 0; ax < 3; ax++) {
       int hi = 0, lo = 0;
       for (int k = 1; k < vn; k++) { if (v[3 * k + ax] > v[3 * hi + ax]) hi = k; if (v[3 * k + ax] < v[3 * lo + ax]) lo = k; }
-      ext[6 * i + 2 * ax] = hi; ext[6 * i + 2 * ax + 1] = lo;
+      const int sel[2] = {hi, lo};
+      for (int q = 0; q < 2; q++) {
+        float* e = ext + 4 * (6 * i + 2 * ax + q);
+        const int pk = packed(sel[q]);
+        e[0] = v[3 * sel[q]]; e[1] = v[3 * sel[q] + 1]; e[2] = v[3 * sel[q] + 2];
+        memcpy(&e[3], &pk, 4);
+      }
     }
   }
   m.mesh_nbr = nbr;

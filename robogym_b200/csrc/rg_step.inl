@@ -18,6 +18,7 @@ struct RgBatchIO {
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
   float* contact;           /* [nenv][RG_NCON][4] = geom1, geom2, dist, dim */
   int* ncon; int* warn;
+  int* cost;                /* [nenv] work estimate of this launch (engine-internal, see rg_order_kernel) */
   float* dbg;               /* [nenv][rg_dbg_size] stage dump for the parity tests */
 };
 
@@ -154,7 +155,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     const float* r = s + L.con + RG_CON_STRIDE * k;
     if (k < ncon) { o[0] = r[20]; o[1] = r[21]; o[2] = r[0]; o[3] = r[17]; } else { o[0] = o[1] = -1.0f; o[2] = 0.0f; o[3] = 0.0f; }
   }
-  if (lane == 0) { if (io.ncon) io.ncon[env] = ncon; if (io.warn) io.warn[env] |= RG_SI(c, RG_S_WARN); }
+  if (lane == 0) { if (io.ncon) io.ncon[env] = ncon; if (io.warn) io.warn[env] |= RG_SI(c, RG_S_WARN); if (io.cost) io.cost[env] = RG_SI(c, RG_S_WORK); }
   if (io.dbg) {
     float* g = io.dbg + (size_t)env * rg_dbg_size(m);
     const int nv = m.nv;

@@ -55,6 +55,7 @@ def lib():
         L.rg_batch_bind_param.argtypes = [vp, ctypes.c_char_p, vp]
         L.rg_model_origin.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
         L.rg_batch_launch_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.rg_batch_set_balance.argtypes = [vp, ci]
         L.rg_step.argtypes = [vp, ci, ci, vp]
         L.rg_forward.argtypes = [vp, vp]
         L.rg_reset.argtypes = [vp, vp, vp]
@@ -205,6 +206,10 @@ class BatchedSim:
             mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
             mp = ctypes.c_void_p(mask.data_ptr())
         _check(lib().rg_reset(self.h, mp, self._stream()))
+
+    def set_balance(self, on):
+        """Work-ordered scheduling on/off (include/robogym_b200.h: rg_batch_set_balance); results do not depend on it."""
+        _check(lib().rg_batch_set_balance(self.h, int(bool(on))))
 
     def launch_info(self):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
