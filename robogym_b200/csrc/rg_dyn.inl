@@ -242,7 +242,7 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     while (j >= 0) {
       float v = rg_dot6(s + L.S + 6 * j, F);
       if (j == i) v += m.dof_armature[i];
-      s[L.M + RG_TRI(i, j)] = v;   /* ancestors have smaller indices: j <= i */
+      s[L.M + RG_HR(nv, i, j)] = v;   /* packed in the solver's reversed dof order, so H starts as a straight copy */
       j = m.dof_parentid[j];
     }
   }

@@ -80,11 +80,15 @@ RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
   float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
   for (int i = lane; i < nv; i += 32) {
-    float acc = 0.0f;
-    const float* row = s + RG_CL(c).M + RG_TRI(i, 0);
-    for (int k = 0; k <= i; k++) acc += row[k] * s[x + k];
-    for (int k = i + 1; k < nv; k++) acc += s[RG_CL(c).M + RG_TRI(k, i)] * s[x + k];
-    s[y + i] = acc;
+    /* M is packed in reversed dof order: row r = nv-1-i, column q = nv-1-k */
+    const int r = nv - 1 - i;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    const float* row = s + RG_CL(c).M + RG_TRI(r, 0);
+    int q = 0;
+    for (; q + 1 <= r; q += 2) { acc0 += row[q] * s[x + nv - 1 - q]; acc1 += row[q + 1] * s[x + nv - 2 - q]; }
+    if (q <= r) acc0 += row[q] * s[x + nv - 1 - q];
+    for (q = r + 1; q < nv; q++) acc1 += s[RG_CL(c).M + RG_TRI(q, r)] * s[x + nv - 1 - q];
+    s[y + i] = acc0 + acc1;
   }
   RG_PHASE_END
 }
@@ -102,24 +106,30 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
     if (i < n && env[i] <= j) {
       const float* ri = s + A + RG_TRI(i, 0); const float* rj = s + A + RG_TRI(j, 0);
       acc = ri[j];
-      const int k0 = env[i] > env[j] ? env[i] : env[j];
-      for (int k = k0; k < j; k++) acc -= ri[k] * rj[k];
+      float acc1 = 0.0f;
+      int k = env[i] > env[j] ? env[i] : env[j];
+      for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
+      if (k < j) acc -= ri[k] * rj[k];
+      acc += acc1;
     }
     LV(sumv) = acc;
     RG_PHASE_END
-    const float diag = sqrtf(fmaxf(RG_WARP_BCAST(sumv, 0), 1e-20f));
-    const float inv = 1.0f / diag;
+    /* the diagonal slot keeps 1/L[j][j]: the factor is only ever used to solve (rg_chol_solve) */
+    const float inv = RG_RSQRT(fmaxf(RG_WARP_BCAST(sumv, 0), 1e-20f));
     RG_PHASE_BEGIN
     const int i = j + lane;
-    if (i == j) s[A + RG_TRI(j, j)] = diag;
+    if (i == j) s[A + RG_TRI(j, j)] = inv;
     else if (i < n) s[A + RG_TRI(i, j)] = LV(sumv) * inv;
     for (int i2 = i + 32; i2 < n; i2 += 32) {
       float acc = 0.0f;
       if (env[i2] <= j) {
         const float* ri = s + A + RG_TRI(i2, 0); const float* rj = s + A + RG_TRI(j, 0);
         acc = ri[j];
-        const int k0 = env[i2] > env[j] ? env[i2] : env[j];
-        for (int k = k0; k < j; k++) acc -= ri[k] * rj[k];
+        float acc1 = 0.0f;
+        int k = env[i2] > env[j] ? env[i2] : env[j];
+        for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
+        if (k < j) acc -= ri[k] * rj[k];
+        acc += acc1;
       }
       s[A + RG_TRI(i2, j)] = acc * inv;
     }
@@ -133,7 +143,7 @@ RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, 
   float* s = RG_SCRATCH(c);
   for (int j = 0; j < n; j++) {
     RG_PHASE_BEGIN
-    const float xj = s[x + j] / s[A + RG_TRI(j, j)];
+    const float xj = s[x + j] * s[A + RG_TRI(j, j)];   /* diagonal slot = 1/L[j][j] */
     if (lane == 0) s[tmp + j] = xj;
     for (int i = j + 1 + lane; i < n; i += 32)
       if (env[i] <= j) s[x + i] -= s[A + RG_TRI(i, j)] * xj;
@@ -141,7 +151,7 @@ RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, 
   }
   for (int j = n - 1; j >= 0; j--) {
     RG_PHASE_BEGIN
-    const float xj = s[tmp + j] / s[A + RG_TRI(j, j)];
+    const float xj = s[tmp + j] * s[A + RG_TRI(j, j)];
     if (lane == 0) s[x + j] = xj;
     for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + RG_TRI(j, i)] * xj;
     RG_PHASE_END
@@ -504,8 +514,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #endif
     if (refactor) {
     RG_PHASE_BEGIN
-    for (int i = lane; i < nv; i += 32)
-      for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_TRI(i, j)];
+    for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
     RG_PHASE_END
     RG_PHASE_BEGIN
     for (int d = lane; d < nv; d += 32) {
@@ -723,7 +732,7 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
   RG_PHASE_BEGIN
   for (int i = lane; i < nv; i += 32)
-    for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_TRI(i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
+    for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_HR(nv, i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
   for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
   RG_PHASE_BEGIN

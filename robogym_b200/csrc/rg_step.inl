@@ -160,7 +160,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     float* g = io.dbg + (size_t)env * rg_dbg_size(m);
     const int nv = m.nv;
     int o = 0;
-    for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + (r_ >= c_ ? RG_TRI(r_, c_) : RG_TRI(c_, r_))]; }
+    for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + RG_HR(nv, r_, c_)]; }
     o += nv * nv;
     for (int i = lane; i < nv; i += 32) {
       g[o + i] = s[L.bias + i]; g[o + nv + i] = 0.0f; g[o + 2 * nv + i] = 0.0f;   /* passive / actuator split is not kept */
