@@ -91,9 +91,15 @@ int rg_batch_set_balance(rg_batch* b, int on);
 /* launch geometry actually used (for reporting): CTAs, warps per CTA, dynamic shared bytes */
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps_per_cta, int* smem_bytes);
 
-/* nsub x mj_step, then (final_forward != 0) one mj_forward; derived outputs written once at the end */
+/* nsub x mj_step, then `final_forward` x mj_forward (0..4: SimulationInterface.step ends with one sim.forward(); the
+ * observation path of RobotEnv runs more of them (robogym/robot_env.py:677, observation/mujoco.py:27) and mujoco-py's
+ * PID state in userdata advances in each); derived outputs written once at the end */
 int rg_step(rg_batch* b, int nsub, int final_forward, void* stream);
 int rg_forward(rg_batch* b, void* stream);
+/* the same for the environments whose mask byte (device memory, [nenv]) is non-zero; the others are untouched and cost
+ * nothing (the launch covers only the selected environments).  What a Python loop over MjSim objects does when it
+ * calls sim.forward()/sim.step() on some environments only (goal switches, resets). */
+int rg_step_subset(rg_batch* b, const uint8_t* mask_device, int nsub, int final_forward, void* stream);
 /* mj_resetData for the environments whose mask byte is non-zero (mask == NULL: all) */
 int rg_reset(rg_batch* b, const uint8_t* mask_device, void* stream);
 

@@ -43,6 +43,7 @@ struct RgKernelArgs {
   int over_dst[RG_MAX_PARAM_OVERRIDES];          /* float offset inside the per-warp override area */
   const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] in global memory */
   const int* order;   /* [nenv] slot -> environment (work-sorted, see rg_order_kernel) or nullptr = identity */
+  const int* nslots;  /* device: number of slots of a subset launch (rg_step_subset) or nullptr = every environment */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,11 +128,12 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   }
   /* every warp of the CTA runs the same number of iterations (the stage barriers need all of them) */
   const int stride = gridDim.x * args.warps;
-  const int iters = (args.io.nenv + stride - 1) / stride;
+  const int total = args.nslots ? *args.nslots : args.io.nenv;
+  const int iters = (total + stride - 1) / stride;   /* 0 for an empty subset */
   for (int it = 0; it < iters; it++) {
     const int slot = it * stride + blockIdx.x * args.warps + warp;
-    const int valid = slot < args.io.nenv;
-    const int e = args.order ? args.order[valid ? slot : args.io.nenv - 1] : (valid ? slot : args.io.nenv - 1);
+    const int valid = slot < total;
+    const int e = args.order ? args.order[valid ? slot : total - 1] : (valid ? slot : total - 1);
     if (args.nover > 0) {
       const int lane = threadIdx.x & 31;
       for (int i = lane; i < (int)(sizeof(RgModelDev) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
@@ -187,6 +189,28 @@ __global__ void __launch_bounds__(1024) rg_order_kernel(const int* __restrict__ 
   __syncthreads();
   for (int e = t; e < nenv; e += 1024) order[atomicAdd(&bin[min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1)] = e;
 }
+/* slot table of a subset launch: the selected environments in ascending order (one CTA, ballot + scan compaction) */
+__global__ void __launch_bounds__(1024) rg_subset_kernel(const uint8_t* __restrict__ mask, int* __restrict__ order, int* __restrict__ count, int nenv) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  const int t = threadIdx.x;
+  if (t == 0) base = 0;
+  __syncthreads();
+  for (int e0 = 0; e0 < nenv; e0 += 1024) {
+    const int e = e0 + t;
+    const int sel = e < nenv && mask[e] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, sel);
+    if ((t & 31) == 0) wsum[t >> 5] = __popc(bal);
+    __syncthreads();
+    int before = base;
+    for (int w = 0; w < (t >> 5); w++) before += wsum[w];
+    if (sel) order[before + __popc(bal & ((1u << (t & 31)) - 1u))] = e;
+    __syncthreads();
+    if (t == 0) { int s = 0; for (int w = 0; w < 32; w++) s += wsum[w]; base += s; }
+    __syncthreads();
+  }
+  if (t == 0) *count = base;
+}
 __global__ void rg_iota_kernel(int* order, int* cost, int nenv) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < nenv) { order[e] = e; cost[e] = 0; }
@@ -214,6 +238,7 @@ struct rg_batch {
   std::string over_name[RG_MAX_PARAM_OVERRIDES];
   int* d_order = nullptr;  /* slot -> environment of the next launch */
   int* d_cost = nullptr;   /* work estimate written by the last launch */
+  int* d_subset = nullptr; /* [nenv + 1] slot table of a subset launch, followed by its length */
   int balance = 1;
 };
 
@@ -365,6 +390,7 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   if (benv) b->balance = atoi(benv) != 0;
   cudaError_t e = cudaMalloc((void**)&b->d_order, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_subset, sizeof(int) * ((size_t)nenv + 1));
   if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, nenv); e = cudaDeviceSynchronize(); }
   if (e != cudaSuccess) { std::string msg = std::string("rg_batch_create: CUDA: ") + cudaGetErrorString(e); rg_batch_destroy(b); return rg_fail(-2, msg); }
   *out = b;
@@ -374,6 +400,7 @@ void rg_batch_destroy(rg_batch* b) {
   if (!b) return;
   if (b->d_order) cudaFree(b->d_order);
   if (b->d_cost) cudaFree(b->d_cost);
+  if (b->d_subset) cudaFree(b->d_subset);
   delete b;
 }
 
@@ -455,8 +482,8 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   return 0;
 }
 
-int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
-  if (!b || nsub < 0) return rg_fail(-1, "rg_step: bad argument");
+static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_forward, void* stream) {
+  if (!b || nsub < 0 || final_forward < 0 || final_forward > 4) return rg_fail(-1, "rg_step: bad argument");
   RgKernelArgs args;
   const int rc = rg_fill_io(b, args.io);
   if (rc) return rc;
@@ -467,15 +494,28 @@ int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) {
   args.nover = b->nover;
   args.over_floats = b->over_floats;
   args.order = b->balance ? b->d_order : nullptr;
+  args.nslots = nullptr;
   for (int i = 0; i < b->nover; i++) { args.over_off[i] = b->over_off[i]; args.over_cnt[i] = b->over_cnt[i]; args.over_dst[i] = b->over_dst[i]; args.over_ptr[i] = b->over_ptr[i]; }
   RG_CUDA(cudaSetDevice(b->model->device));
+  if (mask) {
+    rg_subset_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(mask, b->d_subset, b->d_subset + b->nenv, b->nenv);
+    RG_CUDA(cudaGetLastError());
+    args.order = b->d_subset;
+    args.nslots = b->d_subset + b->nenv;
+    args.io.cost = nullptr;
+  }
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());
-  if (b->balance && nsub > 0) {
+  if (!mask && b->balance && nsub > 0) {
     rg_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b->d_cost, b->d_order, b->nenv);
     RG_CUDA(cudaGetLastError());
   }
   return 0;
+}
+int rg_step(rg_batch* b, int nsub, int final_forward, void* stream) { return rg_launch_step(b, nullptr, nsub, final_forward, stream); }
+int rg_step_subset(rg_batch* b, const uint8_t* mask, int nsub, int final_forward, void* stream) {
+  if (!mask) return rg_fail(-1, "rg_step_subset: null mask");
+  return rg_launch_step(b, mask, nsub, final_forward, stream);
 }
 int rg_forward(rg_batch* b, void* stream) { return rg_step(b, 0, 1, stream); }
 

@@ -131,7 +131,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
       RG_PHASE_END
     }
   }
-  if (final_forward) rg_forward(c);
+  for (int f = 0; f < final_forward; f++) rg_forward(c);   /* robogym steps, then observes: sim.forward() runs again in RobotEnv._observe_sync */
   /* ---- store */
   if (!store) return;
   RG_PHASE_BEGIN

@@ -57,6 +57,7 @@ def lib():
         L.rg_batch_launch_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
         L.rg_batch_set_balance.argtypes = [vp, ci]
         L.rg_step.argtypes = [vp, ci, ci, vp]
+        L.rg_step_subset.argtypes = [vp, vp, ci, ci, vp]
         L.rg_forward.argtypes = [vp, vp]
         L.rg_reset.argtypes = [vp, vp, vp]
         _lib = L
@@ -193,12 +194,23 @@ class BatchedSim:
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
-    def step(self, n_substeps=None, final_forward=True):
-        """SimulationInterface.step(): nsubsteps x mj_step then mj_forward, for every environment."""
-        _check(lib().rg_step(self.h, self.n_substeps if n_substeps is None else int(n_substeps), int(bool(final_forward)), self._stream()))
+    def step(self, n_substeps=None, final_forward=True, mask=None):
+        """SimulationInterface.step(): nsubsteps x mj_step then mj_forward, for every environment (or, with `mask`
+        -- a [nenv] bool/uint8 device tensor -- only for the selected ones; the launch then covers just those).
+        final_forward may be an integer > 1 to fuse the extra sim.forward() calls of the reference's observation path."""
+        nsub = self.n_substeps if n_substeps is None else int(n_substeps)
+        if mask is None:
+            _check(lib().rg_step(self.h, nsub, int(final_forward), self._stream()))
+        else:
+            mk = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            _check(lib().rg_step_subset(self.h, ctypes.c_void_p(mk.data_ptr()), nsub, int(final_forward), self._stream()))
+            self._keep_mask = mk   # alive until the launch has consumed it
 
-    def forward(self):
-        _check(lib().rg_forward(self.h, self._stream()))
+    def forward(self, mask=None, count=1):
+        if mask is None and count == 1:
+            _check(lib().rg_forward(self.h, self._stream()))
+        else:
+            self.step(0, count, mask)
 
     def reset(self, mask=None):
         mp = None

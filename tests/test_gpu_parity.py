@@ -193,3 +193,34 @@ def test_per_env_parameter_overrides(gpu, locked_blob):
         d.env_step(10)
         assert np.abs(q[k][hand] - d.qpos[hand]).max() < 2e-4
     assert np.abs(q[0][hand] - q[2][hand]).max() > 1e-3      # the override really changed the dynamics
+
+
+def test_subset_launch_matches_full_launch(gpu, states):
+    """rg_step_subset: selected environments get bit-identical results to a full launch, the others are untouched;
+    an empty selection is a no-op; extra forwards (final_forward > 1) advance only the PID state and the solve."""
+    torch, engine, model = gpu
+    sts, _, _ = states
+    n = len(sts)
+    full = engine.BatchedSim(model, n, 10, outputs=("site_xpos", "act_force", "ncon", "warn"))
+    part = engine.BatchedSim(model, n, 10, outputs=("site_xpos", "act_force", "ncon", "warn"))
+    put(torch, full, sts); put(torch, part, sts)
+    mask = torch.zeros(n, dtype=torch.bool, device=full.device)
+    mask[::3] = True
+    before = {k: getattr(part, k).clone() for k in ("qpos", "qvel", "pid", "qacc_warmstart")}
+    full.step(final_forward=3)
+    part.step(final_forward=3, mask=mask)
+    torch.cuda.synchronize()
+    for k in ("qpos", "qvel", "pid", "qacc_warmstart", "site_xpos", "act_force"):
+        assert torch.equal(getattr(part, k)[mask], getattr(full, k)[mask]), k
+    for k, v in before.items():
+        assert torch.equal(getattr(part, k)[~mask], v[~mask]), k
+    snap = {k: getattr(part, k).clone() for k in before}
+    part.step(mask=torch.zeros(n, dtype=torch.bool, device=full.device))
+    torch.cuda.synchronize()
+    for k, v in snap.items():
+        assert torch.equal(getattr(part, k), v), k
+    # forwards leave qpos/qvel alone but advance the PID state
+    q = part.qpos.clone(); p = part.pid.clone()
+    part.forward(mask=mask, count=2)
+    torch.cuda.synchronize()
+    assert torch.equal(part.qpos, q) and not torch.equal(part.pid[mask], p[mask]) and torch.equal(part.pid[~mask], p[~mask])
