@@ -68,16 +68,22 @@ class ShadowHandCubeFacade:
     def joint_positions_to_control(self, qpos):
         return qpos[:, self.hand_qpos_idx] @ self.P.T
 
-    def denormalize_position_control(self, action, qpos=None, relative_action=True):
+    def denormalize_position_control(self, action, qpos=None, relative_action=True, ctrlrange=None):
+        """`ctrlrange` ([nenv, nu, 2], optional): per-environment control ranges (joint-limit randomisation)."""
         torch = self.torch
-        base = 0.5 * (self.ctrl_hi - self.ctrl_lo)
+        lo, hi = (self.ctrl_lo, self.ctrl_hi) if ctrlrange is None else (ctrlrange[..., 0], ctrlrange[..., 1])
+        return self._denormalize(action, qpos, relative_action, lo, hi)
+
+    def _denormalize(self, action, qpos, relative_action, ctrl_lo, ctrl_hi):
+        torch = self.torch
+        base = 0.5 * (ctrl_hi - ctrl_lo)
         if relative_action:
             center = self.joint_positions_to_control(qpos)
             rng = torch.clamp(base, max=self.max_position_change) if self.max_position_change else base
         else:
-            center = 0.5 * (self.ctrl_hi + self.ctrl_lo)
+            center = 0.5 * (ctrl_hi + ctrl_lo)
             rng = base
-        return torch.minimum(torch.maximum(center + action * rng, self.ctrl_lo), self.ctrl_hi)
+        return torch.minimum(torch.maximum(center + action * rng, ctrl_lo), ctrl_hi)
 
     # ---- a7: observations
     def fingertip_relative_positions(self, site_xpos):

@@ -347,6 +347,9 @@ static int rg_batch_size(rg_batch* b) {
   int sms = 0, maxsmem = 0;
   RG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device));
   RG_CUDA(cudaDeviceGetAttribute(&maxsmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+  cudaFuncAttributes fa;
+  RG_CUDA(cudaFuncGetAttributes(&fa, rg_step_kernel));
+  maxsmem -= (int)fa.sharedSizeBytes;   /* the opt-in limit covers static + dynamic shared memory */
   const int model_bytes = RG_MODEL_DEV_BYTES;
   const int fixed = model_bytes + (int)((m->hm.small_bytes + 127) & ~(size_t)127) + 64;
   /* with per-env parameter overrides every warp also holds its own model view + this env's rows */
@@ -374,7 +377,9 @@ static int rg_batch_size(rg_batch* b) {
   int ctas = (nenv + warps - 1) / warps;
   if (ctas > sms) ctas = sms;
   b->ctas = ctas;
-  RG_CUDA(cudaFuncSetAttribute(rg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem));
+  /* the attribute belongs to the kernel, not to this batch: batches with different footprints coexist, so opt in to the
+     device maximum once rather than to this batch's size */
+  RG_CUDA(cudaFuncSetAttribute(rg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsmem));
   return 0;
 }
 

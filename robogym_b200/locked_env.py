@@ -113,33 +113,52 @@ class InitialStatePool:
     computed once; absolute mid-range targets) -> cube position wiggle + uniform random orientation -> `n_random_initial_steps` steps holding one
     random action -> keep the state if the cube is still on the palm (the reference re-draws until it is)."""
 
-    def __init__(self, sim, facade, rand, reset_initial_steps=20, n_random_initial_steps=10, cube_position_wiggle_std=0.005):
+    def __init__(self, sim, facade, rand, reset_initial_steps=20, n_random_initial_steps=10, cube_position_wiggle_std=0.005, randomizer=None):
         self.sim, self.fac, self.rand = sim, facade, rand
         self.torch = facade.torch
+        self.reset_initial_steps = reset_initial_steps
         self.n_random_initial_steps = n_random_initial_steps
         self.wiggle = cube_position_wiggle_std
-        sim.reset()
-        zero = self.torch.zeros(sim.nenv, facade.P.shape[0], dtype=sim.qpos.dtype, device=sim.qpos.device)
-        for _ in range(reset_initial_steps):
-            sim.ctrl.copy_(facade.denormalize_position_control(zero, None, relative_action=False))   # locked.py:197-201 (absolute)
-            sim.step()
-        self.settled = {k: getattr(sim, k)[:1].clone() for k in ("qpos", "qvel", "ctrl", "pid", "qacc_warmstart", "time")}
+        self.randomizer = randomizer        # per-episode model parameters: the settle steps then run under each episode's own
+        self.params = None                  # parameters (as in the reference, whose wrappers write the model before env.reset)
+        self.settled = None
+        if randomizer is None:
+            self._settle()
+            self.settled = {k: getattr(sim, k)[:1].clone() for k in ("qpos", "qvel", "ctrl", "pid", "qacc_warmstart", "time")}
         self.store = None
         self.cursor = 0
         self.generated = 0
         self.rejected = 0
 
+    def _settle(self):
+        sim, fac = self.sim, self.fac
+        sim.reset()
+        zero = self.torch.zeros(sim.nenv, fac.P.shape[0], dtype=sim.qpos.dtype, device=sim.qpos.device)
+        for _ in range(self.reset_initial_steps):
+            sim.ctrl.copy_(self._absolute_ctrl(zero))   # locked.py:197-201 (absolute targets)
+            sim.step()
+
+    def _absolute_ctrl(self, action):
+        """denormalize_position_control(relative_action=False) under the pool's own (possibly randomised) control ranges."""
+        cr = None
+        if self.params is not None and "actuator_ctrlrange" in self.params:
+            cr = self.params["actuator_ctrlrange"].reshape(action.shape[0], -1, 2).to(action.dtype)
+        return self.fac.denormalize_position_control(action, None, relative_action=False, ctrlrange=cr)
+
     def randomize(self, wiggle, quat, action):
         """Apply given draws to the settled state and run the random-action steps; returns the on-palm mask."""
         sim, fac, torch = self.sim, self.fac, self.torch
-        for k, v in self.settled.items():
-            getattr(sim, k).copy_(v.expand_as(getattr(sim, k)))
+        if self.settled is None:
+            self._settle()
+        else:
+            for k, v in self.settled.items():
+                getattr(sim, k).copy_(v.expand_as(getattr(sim, k)))
         sim.qpos[:, fac.cube_pos_idx] += wiggle * self.wiggle
         q = quat / quat.norm(dim=1, keepdim=True)
         sim.qpos[:, fac.cube_quat_idx] = quat_positive(torch, q)      # rotation.uniform_quat (rotation.py:440-446)
         sim.forward()
         for _ in range(self.n_random_initial_steps):
-            sim.ctrl.copy_(fac.denormalize_position_control(action, None, relative_action=False))   # locked.py:216-221 (absolute)
+            sim.ctrl.copy_(self._absolute_ctrl(action))   # locked.py:216-221 (absolute targets)
             sim.step()
         if self.n_random_initial_steps == 0:
             sim.forward()
@@ -147,6 +166,9 @@ class InitialStatePool:
 
     def refill(self):
         n = self.sim.nenv
+        if self.randomizer is not None:
+            self.params = self.randomizer.sample(n)
+            self.randomizer.apply(self.sim, self.params)
         ok = self.randomize(self.rand.randn(n, 3), self.rand.randn(n, 4), self.rand.uniform(-1.0, 1.0, n, self.fac.P.shape[0]))
         idx = ok.nonzero().squeeze(1)
         self.generated += n
@@ -154,6 +176,8 @@ class InitialStatePool:
         if idx.numel() == 0:
             raise RuntimeError("no valid initial state: the cube fell off the palm in every environment of the pool")
         self.store = {k: getattr(self.sim, k)[idx].clone() for k in STATE_FIELDS}
+        if self.params is not None:
+            self.store.update({"param:" + k: v[idx].clone() for k, v in self.params.items()})
         self.cursor = 0
 
     def take(self, k):
@@ -168,7 +192,7 @@ class InitialStatePool:
             parts.append({f: v[a:b] for f, v in self.store.items()})
             self.cursor = b
             k -= b - a
-        return {f: torch.cat([p[f] for p in parts], dim=0) for f in STATE_FIELDS}
+        return {f: torch.cat([p[f] for p in parts], dim=0) for f in parts[0]}
 
 
 class BatchedLockedEnv:
@@ -177,7 +201,8 @@ class BatchedLockedEnv:
     def __init__(self, sim_factory, model, names, nenv, device, seed=0, pool_size=None, rand=None, relative_action=True,
                  successes_needed=50, max_timesteps_per_goal=400, min_timesteps_per_goal=0, success_threshold=0.4,
                  success_reward=5.0, stop_on_fall=True, drop_reward=-20.0, reset_initial_steps=20,
-                 n_random_initial_steps=10, cube_position_wiggle_std=0.005, auto_reset=True, observe_forwards=None):
+                 n_random_initial_steps=10, cube_position_wiggle_std=0.005, auto_reset=True, observe_forwards=None,
+                 randomize=False):
         import torch
 
         self.torch = torch
@@ -188,7 +213,17 @@ class BatchedLockedEnv:
         self.fac = ShadowHandCubeFacade(model, names, device, dtype=dtype)
         self.rand = rand or TorchRand(torch, device, seed, dtype)
         pool_sim = sim_factory(int(pool_size or min(self.nenv, 1184)))
-        self.pool = InitialStatePool(pool_sim, self.fac, self.rand, reset_initial_steps, n_random_initial_steps, cube_position_wiggle_std)
+        self.randomizer = None
+        if randomize:
+            # the randomisation stack of locked.py:263-277, sampled per environment on the device (randomization.py)
+            from .randomization import LockedRandomizer
+
+            self.randomizer = LockedRandomizer(model, names, self.rand, torch, device, dtype)
+            self.ts_state = self.randomizer.timestep_state(self.nenv)
+            self.wind_state = self.randomizer.wind_state(self.nenv, self.sim.n_substeps * self.randomizer.timestep0)
+            self.timestep = self.sim.enable_per_env_timestep()
+            self.xfrc = self.sim.enable_xfrc()
+        self.pool = InitialStatePool(pool_sim, self.fac, self.rand, reset_initial_steps, n_random_initial_steps, cube_position_wiggle_std, self.randomizer)
         self.relative_action = relative_action
         self.successes_needed, self.max_timesteps_per_goal, self.min_timesteps_per_goal = successes_needed, max_timesteps_per_goal, min_timesteps_per_goal
         self.success_threshold, self.success_reward = success_threshold, success_reward
@@ -263,7 +298,16 @@ class BatchedLockedEnv:
         k = int(idx.numel())
         if k == 0:
             return
-        self._load_states(idx, self.pool.take(k))
+        st = self.pool.take(k)
+        self._load_states(idx, st)
+        if self.randomizer is not None:
+            self.randomizer.apply(self.sim, {f[6:]: v for f, v in st.items() if f.startswith("param:")}, idx)
+            ts, ws = self.randomizer.timestep_state(k), self.randomizer.wind_state(k, self.sim.n_substeps * self.randomizer.timestep0)
+            for key, v in ts.items():
+                self.ts_state[key][idx] = v
+            self.wind_state["hit_prob"][idx] = ws["hit_prob"]
+            self.timestep[idx] = self.randomizer.timestep0
+            self.xfrc[idx] = 0
         self.t[idx] = 0
         self.successes_so_far[idx] = 0
         self.goals_so_far[idx] = 0
@@ -305,8 +349,14 @@ class BatchedLockedEnv:
         torch = self.torch
         s = self.sim
         a = torch.clamp(torch.as_tensor(action, dtype=s.qpos.dtype, device=self.device), -1.0, 1.0)
-        s.ctrl.copy_(self.fac.denormalize_position_control(a, s.qpos, relative_action=self.relative_action))
+        cr = None
+        if self.randomizer is not None:
+            cr = s._params["actuator_ctrlrange"].reshape(self.nenv, -1, 2)
+        s.ctrl.copy_(self.fac.denormalize_position_control(a, s.qpos, relative_action=self.relative_action, ctrlrange=cr))
         s.step(final_forward=self.final_forward)
+        if self.randomizer is not None:     # RandomizedTimestepWrapper.step / RandomizedWindWrapper.step: set up the NEXT step
+            self.timestep.copy_(self.randomizer.next_timestep(self.ts_state))
+            self.randomizer.next_wind(self.wind_state, self.xfrc)
         self.t += 1
         # _get_goal_info
         dist = self.goal_distance()

@@ -208,3 +208,29 @@ def test_cuda_env_runs_and_autoresets():
     assert ndone >= 512 and env.episodes == 512 + ndone                  # every environment hit the 8-step goal timeout at least once
     assert int(env.sim.warn.max()) == 0
     assert float(env.goal_distance().max()) <= math.pi + 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_env_with_domain_randomisation():
+    """The locked.py:263-277 randomisation stack sampled per environment on the device: episodes start from pool states
+    generated under their own parameters, parameters travel with the state on reset, timestep / wind change per step."""
+    import torch
+
+    from robogym_b200.locked_env import make_cuda_env
+
+    env = make_cuda_env(256, seed=3, max_timesteps_per_goal=6, pool_size=128, randomize=True)
+    env.reset()
+    p = env.sim._params
+    assert len(p) == 16 and float(p["dof_damping"].std(dim=0).max()) > 0 and float(p["opt_gravity"].std(dim=0).min()) > 0.1
+    gen = torch.Generator(device=env.device); gen.manual_seed(0)
+    damp0 = p["dof_damping"].clone()
+    seen_ts = []
+    for k in range(14):
+        obs, rew, done, info = env.step(torch.rand(256, 20, device=env.device, generator=gen) * 2 - 1)
+        assert torch.isfinite(rew).all() and all(torch.isfinite(v).all() for v in obs.values())
+        seen_ts.append(env.timestep.clone())
+    ts = torch.stack(seen_ts)
+    assert float(ts.min()) >= 0.004 - 1e-7 and float(ts.max()) < 0.03 and float(ts.std()) > 1e-6
+    assert env.episodes > 256 and not torch.equal(env.sim._params["dof_damping"], damp0)    # restarted envs got new parameters
+    assert int(env.sim.warn.max()) & ~1 == 0          # bit0 (contact buffer full) may occur with 5x torsional friction; nothing else
+    assert float(env.fac.on_palm(env.sim.site_xpos).float().mean()) > 0.8
