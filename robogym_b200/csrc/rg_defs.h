@@ -99,6 +99,9 @@ __device__ __forceinline__ void rg_stage_sync() {
 #ifndef RG_NCON
 #define RG_NCON 32
 #endif                   /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
+#ifndef RG_COST_ITER
+#define RG_COST_ITER 3   /* weight of one Newton iteration against one narrow-phase pair in the work estimate (rg_order_kernel) */
+#endif
 #ifndef RG_NEL
 #define RG_NEL 64
 #endif                   /* single-row constraint elements (friction loss + limits) */

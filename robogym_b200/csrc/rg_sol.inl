@@ -718,7 +718,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
   RG_PHASE_BEGIN
   for (int d = lane; d < nv; d += 32) s[L.warm + d] = s[L.qacc + d];
-  if (lane == 0) { RG_SI(c, RG_S_NITER) = iter; RG_SI(c, RG_S_WORK) += 12 * iter; }
+  if (lane == 0) { RG_SI(c, RG_S_NITER) = iter; RG_SI(c, RG_S_WORK) += RG_COST_ITER * iter; }
   RG_PHASE_END
 }
 
