@@ -101,7 +101,7 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   /* local frames of every body relative to its parent */
   RG_PHASE_BEGIN
-  for (int b = lane; b < m.nbody; b += 32) {
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
     float pos[3] = {m.body_pos[3 * b], m.body_pos[3 * b + 1], m.body_pos[3 * b + 2]};
     float quat[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
     const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
@@ -113,7 +113,7 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
   RG_PHASE_END
   /* world frames: compose along the ancestor chain (no level barriers needed) */
   RG_PHASE_BEGIN
-  for (int b = lane; b < m.nbody; b += 32) {
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
     float p[3], q[4];
     rg_copy3(p, s + L.lpos + 3 * b);
     const float* lq = s + L.lquat + 4 * b;
@@ -139,19 +139,19 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
   RG_PHASE_END
   /* geom / site positions, motion axes */
   RG_PHASE_BEGIN
-  for (int g = lane; g < m.ngeom; g += 32) {
+  RG_NOUNROLL for (int g = lane; g < m.ngeom; g += 32) {
     const int b = m.geom_bodyid[g];
     float t[3];
     rg_rot(t, s + L.xquat + 4 * b, m.geom_pos + 3 * g);
     rg_add3(s + L.gxpos + 3 * g, s + L.xpos + 3 * b, t);
   }
-  for (int k = lane; k < m.nsite; k += 32) {
+  RG_NOUNROLL for (int k = lane; k < m.nsite; k += 32) {
     const int b = m.site_bodyid[k];
     float t[3];
     rg_rot(t, s + L.xquat + 4 * b, m.site_pos + 3 * k);
     rg_add3(s + L.sxpos + 3 * k, s + L.xpos + 3 * b, t);
   }
-  for (int d = lane; d < m.nv; d += 32) {
+  RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) {
     const int b = m.dof_bodyid[d], j = m.dof_jntid[d], par = m.body_parentid[b];
     const int type = m.jnt_type[j];
     float* S = s + L.S + 6 * d;
@@ -196,7 +196,7 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
-  for (int b = lane; b < m.nbody; b += 32) {
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
     float* I = s + L.I10 + 10 * b;
     float q[4], R[9];
     rg_quat_mul(q, s + L.xquat + 4 * b, m.body_iquat + 4 * b);
@@ -222,11 +222,11 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     I[8] = Ic[4] - mass * cm[0] * cm[2];
     I[9] = Ic[5] - mass * cm[1] * cm[2];
   }
-  for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.M + i] = 0.0f;
+  RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.M + i] = 0.0f;
   RG_PHASE_END
   /* composite inertias: subtree(b) is the contiguous id range [b, b+size) */
   RG_PHASE_BEGIN
-  for (int i = lane; i < m.nbody * 10; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < m.nbody * 10; i += 32) {
     const int b = i / 10, k = i - 10 * b;
     float acc = 0.0f;
     const int e = b + m.body_subtreesize[b];
@@ -235,7 +235,7 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
   }
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int i = lane; i < nv; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
     float F[6];
     rg_inertia_mul(F, s + L.crb + 10 * m.dof_bodyid[i], s + L.S + 6 * i);
     int j = i;
@@ -255,7 +255,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const float* qvel = s + L.qvel;
   RG_PHASE_BEGIN
-  for (int d = lane; d < m.nv; d += 32) {
+  RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) {
     float V[6] = {0, 0, 0, 0, 0, 0};
     int a = m.dof_parentid[d];
     while (a >= 0) {
@@ -268,7 +268,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   }
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int b = lane; b < m.nbody; b += 32) {
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
     float V[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
     if (!(m.opt_disableflags[0] & RG_DSBL_GRAVITY)) { A[3] = -m.opt_gravity[0]; A[4] = -m.opt_gravity[1]; A[5] = -m.opt_gravity[2]; }
     for (int w = 0; w < m.nmaskw; w++) {
@@ -293,7 +293,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   RG_PHASE_END
   /* subtree force sums (into the Sdot slot, dead after the previous phase) */
   RG_PHASE_BEGIN
-  for (int i = lane; i < m.nbody * 6; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < m.nbody * 6; i += 32) {
     const int b = i / 6, k = i - 6 * b;
     float acc = 0.0f;
     const int e = b + m.body_subtreesize[b];
@@ -302,7 +302,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   }
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int d = lane; d < m.nv; d += 32) s[L.bias + d] = rg_dot6(s + L.S + 6 * d, s + L.Sdot + 6 * m.dof_bodyid[d]);
+  RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) s[L.bias + d] = rg_dot6(s + L.S + 6 * d, s + L.Sdot + 6 * m.dof_bodyid[d]);
   RG_PHASE_END
 }
 
@@ -419,7 +419,7 @@ RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
-  for (int t = lane; t < m.ntendon; t += 32) {
+  RG_NOUNROLL for (int t = lane; t < m.ntendon; t += 32) {
     float* J = s + L.H + t * nv;   /* dense scratch row in the (currently dead) H region, compressed below */
     for (int k = 0; k < nv; k++) J[k] = 0.0f;
     const int adr = m.tendon_adr[t], num = m.tendon_num[t];
@@ -499,7 +499,7 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
   const float dt = c.timestep;
   /* actuators: transmission, mujoco-py PID bias callback (stateful), force clamp */
   RG_PHASE_BEGIN
-  for (int i = lane; i < m.nu; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) {
     const float gear = m.actuator_gear[6 * i];
     const int id = m.actuator_trnid[i];
     float len, vel;
@@ -531,11 +531,11 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
     s[L.aforce + i] = f;
   }
   /* tendon spring-damper force, stored over tvel's twin slot in tmp */
-  for (int t = lane; t < m.ntendon; t += 32)
+  RG_NOUNROLL for (int t = lane; t < m.ntendon; t += 32)
     s[L.tmp + t] = -m.tendon_stiffness[t] * (s[L.tlen + t] - m.tendon_lengthspring[t]) - m.tendon_damping[t] * s[L.tvel + t];
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int d = lane; d < nv; d += 32) {
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
     float passive = 0.0f;
     if (!(flags & RG_DSBL_PASSIVE)) {
       const int j = m.dof_jntid[d];

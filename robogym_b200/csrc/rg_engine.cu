@@ -375,7 +375,10 @@ static int rg_batch_size(rg_batch* b) {
   b->warps = warps;
   b->smem = fixed - 64 + warps * per_warp;
   int ctas = (nenv + warps - 1) / warps;
-  if (ctas > sms) ctas = sms;
+  /* experiment hook: RG_CTAS_PER_SM=2 with RG_WARPS_PER_CTA=4 runs two independent barrier domains per SM */
+  const char* cenv = getenv("RG_CTAS_PER_SM");
+  const int per_sm = cenv && atoi(cenv) > 0 ? atoi(cenv) : 1;
+  if (ctas > sms * per_sm) ctas = sms * per_sm;
   b->ctas = ctas;
   /* the attribute belongs to the kernel, not to this batch: batches with different footprints coexist, so opt in to the
      device maximum once rather than to this batch's size */

@@ -79,7 +79,7 @@ RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
   const int nv = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
-  for (int i = lane; i < nv; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
     /* M is packed in reversed dof order: row r = nv-1-i, column q = nv-1-k */
     const int r = nv - 1 - i;
     float acc0 = 0.0f, acc1 = 0.0f;
@@ -164,7 +164,7 @@ RG_DEV void rg_reverse_phase(const RgCtx c, int x) {
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
-  for (int d = lane; d < n / 2; d += 32) { const float a = s[x + d], b = s[x + n - 1 - d]; s[x + d] = b; s[x + n - 1 - d] = a; }
+  RG_NOUNROLL for (int d = lane; d < n / 2; d += 32) { const float a = s[x + d], b = s[x + n - 1 - d]; s[x + d] = b; s[x + n - 1 - d] = a; }
   RG_PHASE_END
 }
 
@@ -177,7 +177,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
   int* eldof = (int*)(s + L.eldof);
   int nel = 0, warn = 0;
   RG_PHASE_BEGIN
-  for (int i = lane; i < 3 * nv; i += 32) eldof[i] = -1;
+  RG_NOUNROLL for (int i = lane; i < 3 * nv; i += 32) eldof[i] = -1;
   RG_PHASE_END
   const int on = !(flags & RG_DSBL_CONSTRAINT);
   /* dof friction loss: one element per dof with frictionloss > 0 */
@@ -277,7 +277,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
   /* contacts: per-contact solver parameters; cu = B * (Jc qvel) + [K imp (dist-margin)] on the normal row */
   const int ncon = RG_SI(c, RG_S_NCON);
   RG_PHASE_BEGIN
-  for (int k = lane; k < ncon; k += 32) {
+  RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     float* r = s + L.con + RG_CON_STRIDE * k;
     float* prm = s + L.cprm + 8 * k;
     int dim = (int)r[17];
@@ -355,7 +355,7 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
   RG_PHASE_BEGIN
   float cost = 0.0f;
   unsigned sig = 0u;   /* which rows are in their quadratic zone: decides whether H must be rebuilt */
-  for (int e = lane; e < nel; e += 32) {
+  RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
     const float jar = s[L.el_jar + e], D = s[L.el_D + e];
     float f;
     if ((el_i[e] & 3) == RG_EL_FLOSS) {
@@ -367,7 +367,7 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
     else f = 0.0f;
     s[L.el_f + e] = f;
   }
-  for (int k = lane; k < ncon; k += 32) {
+  RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     const float* r = s + L.con + RG_CON_STRIDE * k;
     const float* prm = s + L.cprm + 8 * k;
     const float* u = s + L.cu + 6 * k;
@@ -398,7 +398,7 @@ RG_DEV_NOINLINE void rg_JT_force_phase(const RgCtx c, int out, int nel, int tl0,
   const int* el_i = (const int*)(s + L.el_i);
   const int* eldof = (const int*)(s + L.eldof);
   RG_PHASE_BEGIN
-  for (int d = lane; d < m.nv; d += 32) {
+  RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) {
     float acc = 0.0f;
     const int e0 = eldof[3 * d], e1 = eldof[3 * d + 1], e2 = eldof[3 * d + 2];
     if (e0 >= 0) acc += s[L.el_f + e0];
@@ -428,12 +428,12 @@ RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_o
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   RG_PHASE_BEGIN
-  for (int e = lane; e < nel; e += 32) {
+  RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
     float v = rg_el_Jx(c, el_i[e], xoff);
     if (init) v += s[el_out + e];   /* make_constraints left -aref there */
     s[el_out + e] = v;
   }
-  for (int k = lane; k < ncon; k += 32) {
+  RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     const float* r = s + L.con + RG_CON_STRIDE * k;
     const int dim = (int)s[L.cprm + 8 * k + 1];
     float v[6] = {0, 0, 0, 0, 0, 0};
@@ -468,7 +468,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #endif
   /* start from the previous solution (warm start) */
   RG_PHASE_BEGIN
-  for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
   RG_PHASE_END
   rg_matvec_phase(c, L.Ma, L.qacc);
   rg_J_mul_phase(c, L.qacc, L.el_jar, L.cu, nel, ncon, 1);
@@ -481,7 +481,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     LANEVAR(float, gp);
     RG_PHASE_BEGIN
     float a = 0.0f;
-    for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
     LV(gp) = a;
     RG_PHASE_END
     cost = RG_WARP_SUM(gp) + cost_con;
@@ -497,7 +497,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     LANEVAR(float, gn);
     RG_PHASE_BEGIN
     float a = 0.0f;
-    for (int d = lane; d < nv; d += 32) {
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
       s[L.search + (nv - 1 - d)] = -g;   /* right-hand side in the solver's reversed dof order */
       a += g * g;
@@ -514,10 +514,10 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #endif
     if (refactor) {
     RG_PHASE_BEGIN
-    for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
+    RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
     RG_PHASE_END
     RG_PHASE_BEGIN
-    for (int d = lane; d < nv; d += 32) {
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       float add = 0.0f;
       const int e0 = eldof[3 * d];
       if (e0 >= 0) { const float rf = s[L.el_floss + e0] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
@@ -532,7 +532,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       const int tn = ((const int*)(s + L.tJn))[t];
       const int* tji = (const int*)(s + L.tJi) + RG_TJ * t;
       RG_PHASE_BEGIN
-      for (int p = lane; p < tn * tn; p += 32) {
+      RG_NOUNROLL for (int p = lane; p < tn * tn; p += 32) {
         const int a = p / tn, b = p - a * tn;
         if (tji[a] >= tji[b]) s[L.H + RG_HR(nv, tji[a], tji[b])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
       }
@@ -576,7 +576,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       RG_PHASE_END
       if (nd > RG_TILE) nd = RG_TILE;
       RG_PHASE_BEGIN
-      for (int p = lane; p < nd * nd; p += 32) {
+      RG_NOUNROLL for (int p = lane; p < nd * nd; p += 32) {
         const int i = p / nd, j = p - i * nd;
         if (tdof[i] < tdof[j]) continue;
         const float* tj = s + L.tileJ + 6 * i;
@@ -589,7 +589,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     }
     /* envelope, factor, Newton direction */
     RG_PHASE_BEGIN
-    for (int i = lane; i < nv; i += 32) {
+    RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
       int e = 0;
       while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
       env[i] = e;
@@ -637,7 +637,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       LANEVAR(float, p1); LANEVAR(float, p2);
       RG_PHASE_BEGIN
       float a = 0.0f, b = 0.0f;
-      for (int d = lane; d < nv; d += 32) { a += s[L.search + d] * (s[L.Ma + d] - s[L.smooth + d]); b += s[L.search + d] * s[L.Mv + d]; }
+      RG_NOUNROLL for (int d = lane; d < nv; d += 32) { a += s[L.search + d] * (s[L.Ma + d] - s[L.smooth + d]); b += s[L.search + d] * s[L.Mv + d]; }
       LV(p1) = a; LV(p2) = 0.5f * b;
       RG_PHASE_END
       q1 = RG_WARP_SUM(p1); q2 = RG_WARP_SUM(p2);
@@ -647,7 +647,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       LANEVAR(float, pg); LANEVAR(float, ph);
       RG_PHASE_BEGIN
       float g = 0.0f, h = 0.0f;
-      for (int e = lane; e < nel; e += 32) {
+      RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
         const float jv = s[L.el_jv + e], x = s[L.el_jar + e] + alpha * jv, D = s[L.el_D + e];
         if ((el_i[e] & 3) == RG_EL_FLOSS) {
           const float fl = s[L.el_floss + e], rf = fl / D;
@@ -656,7 +656,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
           else { g += D * x * jv; h += D * jv * jv; }
         } else if (x < 0.0f) { g += D * x * jv; h += D * jv * jv; }
       }
-      for (int k = lane; k < ncon; k += 32) {
+      RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
         const float* r = s + L.con + RG_CON_STRIDE * k;
         const float* prm = s + L.cprm + 8 * k;
         const float* u = s + L.cu + 6 * k;
@@ -689,9 +689,9 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     if (!(alpha > 0.0f)) break;
     /* take the step */
     RG_PHASE_BEGIN
-    for (int d = lane; d < nv; d += 32) { s[L.qacc + d] += alpha * s[L.search + d]; s[L.Ma + d] += alpha * s[L.Mv + d]; }
-    for (int e = lane; e < nel; e += 32) s[L.el_jar + e] += alpha * s[L.el_jv + e];
-    for (int i = lane; i < 6 * ncon; i += 32) s[L.cu + i] += alpha * s[L.cw + i];
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) { s[L.qacc + d] += alpha * s[L.search + d]; s[L.Ma + d] += alpha * s[L.Mv + d]; }
+    RG_NOUNROLL for (int e = lane; e < nel; e += 32) s[L.el_jar + e] += alpha * s[L.el_jv + e];
+    RG_NOUNROLL for (int i = lane; i < 6 * ncon; i += 32) s[L.cu + i] += alpha * s[L.cw + i];
     RG_PHASE_END
     cost_con = rg_solver_update(c, nel, ncon);
     float newcost;
@@ -699,7 +699,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       LANEVAR(float, gp);
       RG_PHASE_BEGIN
       float a = 0.0f;
-      for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
+      RG_NOUNROLL for (int d = lane; d < nv; d += 32) a += s[L.qacc + d] * (0.5f * s[L.Ma + d] - s[L.smooth + d]);
       LV(gp) = a;
       RG_PHASE_END
       newcost = RG_WARP_SUM(gp) + cost_con;
@@ -717,7 +717,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   }
   rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
   RG_PHASE_BEGIN
-  for (int d = lane; d < nv; d += 32) s[L.warm + d] = s[L.qacc + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.warm + d] = s[L.qacc + d];
   if (lane == 0) { RG_SI(c, RG_S_NITER) = iter; RG_SI(c, RG_S_WORK) += RG_COST_ITER * iter; }
   RG_PHASE_END
 }
@@ -731,12 +731,12 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   int* env = (int*)(s + L.env);
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
   RG_PHASE_BEGIN
-  for (int i = lane; i < nv; i += 32)
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32)
     for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_HR(nv, i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
-  for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int i = lane; i < nv; i += 32) {
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
     int e = 0;
     while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
     env[i] = e;
@@ -746,10 +746,10 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   rg_chol_solve(c, L.H, env, L.search, L.tmp);
   rg_reverse_phase(c, L.search);
   RG_PHASE_BEGIN
-  for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int j = lane; j < m.njnt; j += 32) {
+  RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32) {
     const int qa = m.jnt_qposadr[j], da = m.jnt_dofadr[j], type = m.jnt_type[j];
     if (type == RG_JNT_SLIDE || type == RG_JNT_HINGE) s[L.qpos + qa] += h * s[L.qvel + da];
     else {

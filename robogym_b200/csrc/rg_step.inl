@@ -97,14 +97,14 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   const int npid = 3 * m.nu;
   /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
   RG_PHASE_BEGIN
-  for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = io.qpos[(size_t)env * m.nq + i];
-  for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = io.qvel[(size_t)env * m.nv + i]; s[L.warm + i] = io.warm[(size_t)env * m.nv + i]; }
-  for (int i = lane; i < m.nu; i += 32) s[L.ctrl + i] = io.ctrl[(size_t)env * m.nu + i];
-  for (int i = lane; i < npid; i += 32) s[L.pid + i] = io.pid[(size_t)env * npid + i];
+  RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = io.qpos[(size_t)env * m.nq + i];
+  RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = io.qvel[(size_t)env * m.nv + i]; s[L.warm + i] = io.warm[(size_t)env * m.nv + i]; }
+  RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) s[L.ctrl + i] = io.ctrl[(size_t)env * m.nu + i];
+  RG_NOUNROLL for (int i = lane; i < npid; i += 32) s[L.pid + i] = io.pid[(size_t)env * npid + i];
   if (lane < 8 + RG_NPROF) RG_SI(c, lane) = 0;
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int j = lane; j < m.njnt; j += 32)
+  RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
     if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
   RG_PHASE_END
   for (int sub = 0; sub < nsub; sub++) {
@@ -114,19 +114,19 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     LANEVAR(int, badl);
     RG_PHASE_BEGIN
     int bad = 0;
-    for (int i = lane; i < m.nq; i += 32) { const float v = s[L.qpos + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
-    for (int i = lane; i < m.nv; i += 32) { const float v = s[L.qvel + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
+    RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) { const float v = s[L.qpos + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
+    RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) { const float v = s[L.qvel + i]; bad |= !(v == v) || fabsf(v) > 1e10f; }
     LV(badl) = bad;
     RG_PHASE_END
     if (RG_WARP_OR(badl)) {
       RG_PHASE_BEGIN
-      for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = m.qpos0[i];
-      for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = 0.0f; s[L.warm + i] = 0.0f; }
-      for (int i = lane; i < npid; i += 32) s[L.pid + i] = 0.0f;
+      RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = m.qpos0[i];
+      RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) { s[L.qvel + i] = 0.0f; s[L.warm + i] = 0.0f; }
+      RG_NOUNROLL for (int i = lane; i < npid; i += 32) s[L.pid + i] = 0.0f;
       if (lane == 0) RG_SI(c, RG_S_WARN) |= RG_WARN_BAD_STATE;
       RG_PHASE_END
       RG_PHASE_BEGIN
-      for (int j = lane; j < m.njnt; j += 32)
+      RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
         if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
       RG_PHASE_END
     }
@@ -135,22 +135,22 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   /* ---- store */
   if (!store) return;
   RG_PHASE_BEGIN
-  for (int j = lane; j < m.njnt; j += 32)
+  RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
     if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] += m.origin[a];
   RG_PHASE_END
   RG_PHASE_BEGIN
-  for (int i = lane; i < m.nq; i += 32) io.qpos[(size_t)env * m.nq + i] = s[L.qpos + i];
-  for (int i = lane; i < m.nv; i += 32) { io.qvel[(size_t)env * m.nv + i] = s[L.qvel + i]; io.warm[(size_t)env * m.nv + i] = s[L.warm + i]; }
-  for (int i = lane; i < npid; i += 32) io.pid[(size_t)env * npid + i] = s[L.pid + i];
+  RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) io.qpos[(size_t)env * m.nq + i] = s[L.qpos + i];
+  RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) { io.qvel[(size_t)env * m.nv + i] = s[L.qvel + i]; io.warm[(size_t)env * m.nv + i] = s[L.warm + i]; }
+  RG_NOUNROLL for (int i = lane; i < npid; i += 32) io.pid[(size_t)env * npid + i] = s[L.pid + i];
   if (lane == 0 && io.time) io.time[env] += c.timestep * (float)nsub;
-  if (io.site_xpos) for (int i = lane; i < 3 * m.nsite; i += 32) io.site_xpos[(size_t)env * 3 * m.nsite + i] = s[L.sxpos + i] + m.origin[i % 3];
-  if (io.body_xpos) for (int i = lane; i < 3 * m.nbody; i += 32) io.body_xpos[(size_t)env * 3 * m.nbody + i] = s[L.xpos + i] + m.origin[i % 3];
-  if (io.body_xquat) for (int i = lane; i < 4 * m.nbody; i += 32) io.body_xquat[(size_t)env * 4 * m.nbody + i] = s[L.xquat + i];
-  if (io.geom_xpos) for (int i = lane; i < 3 * m.ngeom; i += 32) io.geom_xpos[(size_t)env * 3 * m.ngeom + i] = s[L.gxpos + i] + m.origin[i % 3];
-  if (io.act_force) for (int i = lane; i < m.nu; i += 32) io.act_force[(size_t)env * m.nu + i] = s[L.aforce + i];
-  if (io.qacc) for (int i = lane; i < m.nv; i += 32) io.qacc[(size_t)env * m.nv + i] = s[L.qacc + i];
+  if (io.site_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.nsite; i += 32) io.site_xpos[(size_t)env * 3 * m.nsite + i] = s[L.sxpos + i] + m.origin[i % 3];
+  if (io.body_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.nbody; i += 32) io.body_xpos[(size_t)env * 3 * m.nbody + i] = s[L.xpos + i] + m.origin[i % 3];
+  if (io.body_xquat) RG_NOUNROLL for (int i = lane; i < 4 * m.nbody; i += 32) io.body_xquat[(size_t)env * 4 * m.nbody + i] = s[L.xquat + i];
+  if (io.geom_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.ngeom; i += 32) io.geom_xpos[(size_t)env * 3 * m.ngeom + i] = s[L.gxpos + i] + m.origin[i % 3];
+  if (io.act_force) RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) io.act_force[(size_t)env * m.nu + i] = s[L.aforce + i];
+  if (io.qacc) RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) io.qacc[(size_t)env * m.nv + i] = s[L.qacc + i];
   const int ncon = RG_SI(c, RG_S_NCON);
-  if (io.contact) for (int k = lane; k < RG_NCON; k += 32) {
+  if (io.contact) RG_NOUNROLL for (int k = lane; k < RG_NCON; k += 32) {
     float* o = io.contact + ((size_t)env * RG_NCON + k) * 4;
     const float* r = s + L.con + RG_CON_STRIDE * k;
     if (k < ncon) { o[0] = r[20]; o[1] = r[21]; o[2] = r[0]; o[3] = r[17]; } else { o[0] = o[1] = -1.0f; o[2] = 0.0f; o[3] = 0.0f; }
@@ -160,24 +160,24 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     float* g = io.dbg + (size_t)env * rg_dbg_size(m);
     const int nv = m.nv;
     int o = 0;
-    for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + RG_HR(nv, r_, c_)]; }
+    RG_NOUNROLL for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + RG_HR(nv, r_, c_)]; }
     o += nv * nv;
-    for (int i = lane; i < nv; i += 32) {
+    RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
       g[o + i] = s[L.bias + i]; g[o + nv + i] = 0.0f; g[o + 2 * nv + i] = 0.0f;   /* passive / actuator split is not kept */
       g[o + 3 * nv + i] = s[L.smooth + i]; g[o + 4 * nv + i] = s[L.qacc + i]; g[o + 5 * nv + i] = s[L.qfc + i];
     }
     o += 6 * nv;
-    for (int i = lane; i < m.ntendon; i += 32) g[o + i] = s[L.tlen + i];
+    RG_NOUNROLL for (int i = lane; i < m.ntendon; i += 32) g[o + i] = s[L.tlen + i];
     o += m.ntendon;
-    for (int i = lane; i < m.nu; i += 32) { g[o + i] = s[L.alen + i]; g[o + m.nu + i] = s[L.aforce + i]; }
+    RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) { g[o + i] = s[L.alen + i]; g[o + m.nu + i] = s[L.aforce + i]; }
     o += 2 * m.nu;
     if (lane == 0) { g[o] = (float)ncon; g[o + 1] = (float)RG_SI(c, RG_S_NEL); g[o + 2] = (float)RG_SI(c, RG_S_NITER); g[o + 3] = (float)RG_SI(c, RG_S_WARN); }
     o += 4;
-    for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
+    RG_NOUNROLL for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
     o += RG_NCON * RG_CON_STRIDE;
-    for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = rg_tendon_J(c, i / nv, i % nv);
+    RG_NOUNROLL for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = rg_tendon_J(c, i / nv, i % nv);
     o += m.ntendon * nv;
-    for (int i = lane; i < RG_NPROF; i += 32) g[o + i] = s[L.scal + 8 + i];
+    RG_NOUNROLL for (int i = lane; i < RG_NPROF; i += 32) g[o + i] = s[L.scal + 8 + i];
   }
   RG_PHASE_END
 }
