@@ -21,6 +21,7 @@
 #define RG_DEV static inline
 #define RG_DEV_NOINLINE static
 #define RG_NOUNROLL
+#define RG_UNROLL2
 #define RG_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define RG_PHASE_END }
 #define RG_LANE_DECL
@@ -42,6 +43,7 @@
 #define RG_DEV_NOINLINE __device__ __noinline__
 /* lane-strided loops run once or twice (n <= 64): unrolling them only bloats a kernel that is instruction-cache bound */
 #define RG_NOUNROLL _Pragma("unroll 1")
+#define RG_UNROLL2 _Pragma("unroll 2")
 #define RG_PHASE_BEGIN {
 #define RG_PHASE_END } __syncwarp();
 #define RG_LANE_DECL const int lane = threadIdx.x & 31;

@@ -411,7 +411,7 @@ RG_DEV float rg_tendon_J(const RgCtx c, int t, int d) {
   const int n = ((const int*)(RG_SCRATCH(c) + RG_CL(c).tJn))[t];
   const int* ji = (const int*)(RG_SCRATCH(c) + RG_CL(c).tJi) + RG_TJ * t;
   float v = 0.0f;
-  for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[RG_CL(c).tJv + RG_TJ * t + k];
+  RG_NOUNROLL for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[RG_CL(c).tJv + RG_TJ * t + k];
   return v;
 }
 RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {

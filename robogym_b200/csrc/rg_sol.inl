@@ -85,9 +85,9 @@ RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
     float acc0 = 0.0f, acc1 = 0.0f;
     const float* row = s + RG_CL(c).M + RG_TRI(r, 0);
     int q = 0;
-    for (; q + 1 <= r; q += 2) { acc0 += row[q] * s[x + nv - 1 - q]; acc1 += row[q + 1] * s[x + nv - 2 - q]; }
+    RG_UNROLL2 for (; q + 1 <= r; q += 2) { acc0 += row[q] * s[x + nv - 1 - q]; acc1 += row[q + 1] * s[x + nv - 2 - q]; }
     if (q <= r) acc0 += row[q] * s[x + nv - 1 - q];
-    for (q = r + 1; q < nv; q++) acc1 += s[RG_CL(c).M + RG_TRI(q, r)] * s[x + nv - 1 - q];
+    RG_UNROLL2 for (q = r + 1; q < nv; q++) acc1 += s[RG_CL(c).M + RG_TRI(q, r)] * s[x + nv - 1 - q];
     s[y + i] = acc0 + acc1;
   }
   RG_PHASE_END
@@ -108,7 +108,7 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
       acc = ri[j];
       float acc1 = 0.0f;
       int k = env[i] > env[j] ? env[i] : env[j];
-      for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
+      RG_UNROLL2 for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
       if (k < j) acc -= ri[k] * rj[k];
       acc += acc1;
     }
@@ -127,7 +127,7 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
         acc = ri[j];
         float acc1 = 0.0f;
         int k = env[i2] > env[j] ? env[i2] : env[j];
-        for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
+        RG_UNROLL2 for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
         if (k < j) acc -= ri[k] * rj[k];
         acc += acc1;
       }
@@ -340,7 +340,7 @@ RG_DEV float rg_el_Jx(const RgCtx c, int code, int x) {
   float acc = 0.0f;
   const int n = ((const int*)(s + RG_CL(c).tJn))[id];
   const int* ji = (const int*)(s + RG_CL(c).tJi) + RG_TJ * id;
-  for (int k = 0; k < n; k++) acc += s[RG_CL(c).tJv + RG_TJ * id + k] * s[x + ji[k]];
+  RG_NOUNROLL for (int k = 0; k < n; k++) acc += s[RG_CL(c).tJv + RG_TJ * id + k] * s[x + ji[k]];
   return side ? -acc : acc;
 }
 
@@ -415,7 +415,7 @@ RG_DEV_NOINLINE void rg_JT_force_phase(const RgCtx c, int out, int nel, int tl0,
       float col[6];
       if (dim == 0 || !rg_contact_col(c, r, d, dim, col)) continue;
       const float* F = s + L.cF + 6 * k;
-      for (int a = 0; a < dim; a++) acc += col[a] * F[a];
+      RG_NOUNROLL for (int a = 0; a < dim; a++) acc += col[a] * F[a];
     }
     s[out + d] = acc;
   }
@@ -445,7 +445,7 @@ RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_o
       const int d = list[i];
       rg_contact_col_list(c, r, d, (sgn >> i) & 1u ? 1.0f : -1.0f, dim, col);
       const float xd = s[xoff + d];
-      for (int a = 0; a < dim; a++) v[a] += col[a] * xd;
+      RG_NOUNROLL for (int a = 0; a < dim; a++) v[a] += col[a] * xd;
     }
     if (init) for (int a = 0; a < 6; a++) v[a] += s[L.cF + 6 * k + a];
     for (int a = 0; a < 6; a++) s[c_out + 6 * k + a] = v[a];
@@ -569,7 +569,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         float* tj = s + L.tileJ + 6 * lane;
         float* tw = s + L.tileWJ + 6 * lane;
         float w0 = W00 * col[0];
-        for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
+        RG_NOUNROLL for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
         tj[0] = col[0]; tw[0] = w0;
         for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
       }
@@ -582,7 +582,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         const float* tj = s + L.tileJ + 6 * i;
         const float* tw = s + L.tileWJ + 6 * j;
         float acc = 0.0f;
-        for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
+        RG_NOUNROLL for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
         if (tdof[i] >= tdof[j]) s[L.H + RG_HR(nv, tdof[i], tdof[j])] += acc;
       }
       RG_PHASE_END
@@ -732,7 +732,7 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int i = lane; i < nv; i += 32)
-    for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_HR(nv, i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
+    RG_NOUNROLL for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_HR(nv, i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
   RG_PHASE_BEGIN
