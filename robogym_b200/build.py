@@ -37,7 +37,10 @@ def build_profile():
 def build_variant(tag, defines):
     """Experimental build with extra -D flags (A/B measurements): librobogym_b200_<tag>.so."""
     out = os.path.join(HERE, "librobogym_b200_%s.so" % tag)
-    cmd = nvcc_cmd(tuple("-D" + d for d in defines))
+    flags = []
+    for d in defines:                      # "-..." entries are raw nvcc flags ("+" stands for a space), the rest are -D macros
+        flags += d.split() if d.startswith("-") else ["-D" + d]
+    cmd = nvcc_cmd(tuple(flags))
     cmd[cmd.index("-o") + 1] = out
     subprocess.check_call(cmd)
     return out
@@ -50,4 +53,4 @@ if __name__ == "__main__":
     for a in sys.argv[1:]:
         if a.startswith("--variant="):   # --variant=skew1:RG_SKEW=1
             tag, _, defs = a[len("--variant="):].partition(":")
-            print(build_variant(tag, [d for d in defs.split(",") if d]))
+            print(build_variant(tag, [d for d in defs.replace("+", " ").split(",") if d]))

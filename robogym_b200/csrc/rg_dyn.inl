@@ -230,7 +230,7 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     const int b = i / 10, k = i - 10 * b;
     float acc = 0.0f;
     const int e = b + m.body_subtreesize[b];
-    for (int bb = b; bb < e; bb++) acc += s[L.I10 + 10 * bb + k];
+    RG_NOUNROLL for (int bb = b; bb < e; bb++) acc += s[L.I10 + 10 * bb + k];
     s[L.crb + i] = acc;
   }
   RG_PHASE_END
@@ -271,7 +271,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
     float V[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
     if (!(m.opt_disableflags[0] & RG_DSBL_GRAVITY)) { A[3] = -m.opt_gravity[0]; A[4] = -m.opt_gravity[1]; A[5] = -m.opt_gravity[2]; }
-    for (int w = 0; w < m.nmaskw; w++) {
+    RG_NOUNROLL for (int w = 0; w < m.nmaskw; w++) {
       unsigned bits = (unsigned)m.body_dofmask[b * m.nmaskw + w];
       while (bits) {
         const int d = 32 * w + rg_ctz(bits);
@@ -297,7 +297,7 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
     const int b = i / 6, k = i - 6 * b;
     float acc = 0.0f;
     const int e = b + m.body_subtreesize[b];
-    for (int bb = b; bb < e; bb++) acc += s[L.crb + 10 * bb + k];
+    RG_NOUNROLL for (int bb = b; bb < e; bb++) acc += s[L.crb + 10 * bb + k];
     s[L.Sdot + 6 * b + k] = acc;
   }
   RG_PHASE_END
@@ -397,7 +397,7 @@ RG_DEV_NOINLINE float rg_wrap_geom(float* wp, const float* x0, const float* x1, 
 RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
   if (ba == bb) return;
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
-  for (int d = 0; d < m.nv; d++) {
+  RG_NOUNROLL for (int d = 0; d < m.nv; d++) {
     const int ina = rg_dof_in_body(m, ba, d), inb = rg_dof_in_body(m, bb, d);
     if (ina == inb) continue;
     float jp[3];
@@ -421,11 +421,11 @@ RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int t = lane; t < m.ntendon; t += 32) {
     float* J = s + L.H + t * nv;   /* dense scratch row in the (currently dead) H region, compressed below */
-    for (int k = 0; k < nv; k++) J[k] = 0.0f;
+    RG_NOUNROLL for (int k = 0; k < nv; k++) J[k] = 0.0f;
     const int adr = m.tendon_adr[t], num = m.tendon_num[t];
     float len = 0.0f, divisor = 1.0f;
     if (m.wrap_type[adr] == RG_WRAP_JOINT) {
-      for (int w = adr; w < adr + num; w++) {
+      RG_NOUNROLL for (int w = adr; w < adr + num; w++) {
         const int j = m.wrap_objid[w];
         len += m.wrap_prm[w] * s[L.qpos + m.jnt_qposadr[j]];
         J[m.jnt_dofadr[j]] += m.wrap_prm[w];
@@ -479,7 +479,7 @@ RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
     int nnz = 0;
     int* ji = (int*)(s + L.tJi) + RG_TJ * t;
     float* jv = s + L.tJv + RG_TJ * t;
-    for (int k = 0; k < nv; k++) {
+    RG_NOUNROLL for (int k = 0; k < nv; k++) {
       if (J[k] == 0.0f) continue;
       v += J[k] * s[L.qvel + k];
       if (nnz < RG_TJ) { ji[nnz] = k; jv[nnz] = J[k]; nnz++; }
@@ -542,10 +542,10 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
       if (m.jnt_stiffness[j] != 0.0f && (m.jnt_type[j] == RG_JNT_SLIDE || m.jnt_type[j] == RG_JNT_HINGE))
         passive -= m.jnt_stiffness[j] * (s[L.qpos + m.jnt_qposadr[j]] - m.qpos_spring[m.jnt_qposadr[j]]);
       passive -= m.dof_damping[d] * s[L.qvel + d];
-      for (int t = 0; t < m.ntendon; t++) passive += rg_tendon_J(c, t, d) * s[L.tmp + t];
+      RG_NOUNROLL for (int t = 0; t < m.ntendon; t++) passive += rg_tendon_J(c, t, d) * s[L.tmp + t];
     }
     float act = 0.0f;
-    for (int i = 0; i < m.nu; i++) {
+    RG_NOUNROLL for (int i = 0; i < m.nu; i++) {
       const float gear = m.actuator_gear[6 * i];
       const int id = m.actuator_trnid[i];
       if (m.actuator_trntype[i] == RG_TRN_JOINT) { if (m.jnt_dofadr[id] == d) act += gear * s[L.aforce + i]; }
@@ -553,7 +553,7 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
     }
     float applied = 0.0f;
     if (c.xfrc) {
-      for (int b = 1; b < m.nbody; b++) {
+      RG_NOUNROLL for (int b = 1; b < m.nbody; b++) {
         if (!rg_dof_in_body(m, b, d)) continue;
         const float* x = c.xfrc + 6 * b;
         if (x[0] == 0 && x[1] == 0 && x[2] == 0 && x[3] == 0 && x[4] == 0 && x[5] == 0) continue;

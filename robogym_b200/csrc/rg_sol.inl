@@ -120,7 +120,7 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
     const int i = j + lane;
     if (i == j) s[A + RG_TRI(j, j)] = inv;
     else if (i < n) s[A + RG_TRI(i, j)] = LV(sumv) * inv;
-    for (int i2 = i + 32; i2 < n; i2 += 32) {
+    RG_NOUNROLL for (int i2 = i + 32; i2 < n; i2 += 32) {
       float acc = 0.0f;
       if (env[i2] <= j) {
         const float* ri = s + A + RG_TRI(i2, 0); const float* rj = s + A + RG_TRI(j, 0);
@@ -145,7 +145,7 @@ RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, 
     RG_PHASE_BEGIN
     const float xj = s[x + j] * s[A + RG_TRI(j, j)];   /* diagonal slot = 1/L[j][j] */
     if (lane == 0) s[tmp + j] = xj;
-    for (int i = j + 1 + lane; i < n; i += 32)
+    RG_NOUNROLL for (int i = j + 1 + lane; i < n; i += 32)
       if (env[i] <= j) s[x + i] -= s[A + RG_TRI(i, j)] * xj;
     RG_PHASE_END
   }
@@ -153,7 +153,7 @@ RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, 
     RG_PHASE_BEGIN
     const float xj = s[tmp + j] * s[A + RG_TRI(j, j)];
     if (lane == 0) s[x + j] = xj;
-    for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + RG_TRI(j, i)] * xj;
+    RG_NOUNROLL for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + RG_TRI(j, i)] * xj;
     RG_PHASE_END
   }
 }
@@ -299,7 +299,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     unsigned char* list = (unsigned char*)(s + L.cdof + 4 * k);
     int nd = 0;
     unsigned sgn = 0u;
-    for (int w = 0; w < m.nmaskw && dim > 0; w++) {
+    RG_NOUNROLL for (int w = 0; w < m.nmaskw && dim > 0; w++) {
       const unsigned m1 = (unsigned)m.body_dofmask[b1 * m.nmaskw + w], m2 = (unsigned)m.body_dofmask[b2 * m.nmaskw + w];
       unsigned bits = m1 ^ m2;
       while (bits) {
@@ -313,12 +313,12 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     prm[4] = (float)nd; prm[5] = (float)(sgn & 0xffffu);
     /* velocity part of jar */
     float v[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < nd; i++) {
+    RG_NOUNROLL for (int i = 0; i < nd; i++) {
       float col[6];
       const int d = list[i];
       rg_contact_col_list(c, r, d, (sgn >> i) & 1u ? 1.0f : -1.0f, dim, col);
       const float qd = s[L.qvel + d];
-      for (int a = 0; a < dim; a++) v[a] += col[a] * qd;
+      RG_NOUNROLL for (int a = 0; a < dim; a++) v[a] += col[a] * qd;
     }
     float* cb = s + L.cF + 6 * k; /* staged here until the solver initialises cu */
     for (int a = 0; a < 6; a++) cb[a] = B * v[a];
@@ -440,7 +440,7 @@ RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_o
     const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
     const int nd = (int)s[L.cprm + 8 * k + 4];
     const unsigned sgn = (unsigned)s[L.cprm + 8 * k + 5];
-    for (int i = 0; i < nd; i++) {
+    RG_NOUNROLL for (int i = 0; i < nd; i++) {
       float col[6];
       const int d = list[i];
       rg_contact_col_list(c, r, d, (sgn >> i) & 1u ? 1.0f : -1.0f, dim, col);
