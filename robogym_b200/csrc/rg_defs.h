@@ -112,7 +112,11 @@ __device__ __forceinline__ void rg_stage_sync() {
 #endif                   /* single-row constraint elements (friction loss + limits) */
 #define RG_CON_STRIDE 24
 #define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
-#define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds) */
+#ifdef RG_PROFILE
+#define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds only) */
+#else
+#define RG_NPROF 0
+#endif
 #define RG_TRI(i, j) ((((i) * ((i) + 1)) >> 1) + (j))   /* packed lower triangle, i >= j */
 /* The solver's Hessian is stored with the dof order REVERSED (leaves of the kinematic tree first, roots and
  * free objects last): Cholesky then eliminates children before parents, so the tree-structured part
@@ -141,12 +145,13 @@ struct RgModel {
 #undef RG_I
 #undef RG_F
   const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
-  const int* dof_treeroot;     /* first dof of the kinematic tree a dof belongs to (Cholesky envelope) */
+  const int* dof_mrow;         /* [nv][3]: start of dof i's row in the tree-sparse mass matrix, dofs in its subtree, its depth */
   const float* mesh_nbr;       /* [nmeshadj][4]: neighbour vertex x,y,z + that vertex's own adjacency range (first | degree << 20, as int bits) */
   const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
   const float* mesh_ext;       /* [nmesh][6][4]: extreme vertices along +x,-x,+y,-y,+z,-z in the same x,y,z,range format (hill-climb starting points) */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
+  int nM;                      /* entries of the tree-sparse mass matrix: sum over dofs of (depth + 1) */
 };
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
@@ -188,13 +193,14 @@ struct RgModelDev {
 #undef RG_IB
 #undef RG_FB
   RgArr<int> body_subtreesize;
-  RgArr<int> dof_treeroot;
+  RgArr<int> dof_mrow;
   RgArr<unsigned short> pair_packed;
   int has_pairs;
   const float* mesh_nbr;
   const float* mesh_ext;
   float origin[3];
   int small_bytes;
+  int nM;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev

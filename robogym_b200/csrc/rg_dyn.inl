@@ -222,7 +222,6 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     I[8] = Ic[4] - mass * cm[0] * cm[2];
     I[9] = Ic[5] - mass * cm[1] * cm[2];
   }
-  RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.M + i] = 0.0f;
   RG_PHASE_END
   /* composite inertias: subtree(b) is the contiguous id range [b, b+size) */
   RG_PHASE_BEGIN
@@ -239,10 +238,11 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     float F[6];
     rg_inertia_mul(F, s + L.crb + 10 * m.dof_bodyid[i], s + L.S + 6 * i);
     int j = i;
-    while (j >= 0) {
+    float* row = s + L.M + m.dof_mrow[3 * i];   /* tree-sparse row: M(i,i), M(i,parent), M(i,grandparent), ... */
+    for (int k = 0; j >= 0; k++) {
       float v = rg_dot6(s + L.S + 6 * j, F);
       if (j == i) v += m.dof_armature[i];
-      s[L.M + RG_HR(nv, i, j)] = v;   /* packed in the solver's reversed dof order, so H starts as a straight copy */
+      row[k] = v;
       j = m.dof_parentid[j];
     }
   }

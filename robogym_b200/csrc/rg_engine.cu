@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
 #undef RG_IB
 #undef RG_FB
     RG_SETOFF(body_subtreesize)
-    RG_SETOFF(dof_treeroot)
+    RG_SETOFF(dof_mrow)
     RG_SETPTR(mesh_nbr)
     RG_SETPTR(mesh_ext)
     if (lane == 0) {
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       sm->pair_packed.off = args.m.pair_packed ? model_bytes + (int)((const char*)args.m.pair_packed - abase) : 0;
       sm->origin[0] = args.m.origin[0]; sm->origin[1] = args.m.origin[1]; sm->origin[2] = args.m.origin[2];
       sm->small_bytes = small_bytes;
+      sm->nM = args.m.nM;
     }
     for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
@@ -254,7 +255,7 @@ static void rg_wire_device_view(rg_model* mm) {
 #undef RG_I
 #undef RG_F
   RG_DEVPTR(body_subtreesize)
-  RG_DEVPTR(dof_treeroot)
+  RG_DEVPTR(dof_mrow)
   RG_DEVPTR(mesh_nbr)
   RG_DEVPTR(mesh_ext)
   if (mm->hm.view.pair_packed) RG_DEVPTR(pair_packed)

@@ -67,7 +67,7 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   dst = 0;
   for (size_t i = 0; i < first_big; i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
   dst = rg_align16(dst); const size_t off_subtree = dst; dst += 4 * (size_t)m.nbody;
-  dst = rg_align16(dst); const size_t off_treeroot = dst; dst += 4 * (size_t)m.nv;
+  dst = rg_align16(dst); const size_t off_mrow = dst; dst += 12 * (size_t)m.nv;
   dst = rg_align16(dst); const size_t off_pairs = dst; if (m.ngeom <= 256) dst += 2 * (size_t)m.npair;
   dst = rg_align16(dst);
   hm.small_bytes = dst;
@@ -96,19 +96,36 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
 #undef RG_I
 #undef RG_F
   int* subtree = (int*)(base + off_subtree);
-  int* treeroot = (int*)(base + off_treeroot);
+  int* mrow = (int*)(base + off_mrow);
   for (int b = 0; b < m.nbody; b++) subtree[b] = 1;
   for (int b = m.nbody - 1; b > 0; b--) subtree[m.body_parentid[b]] += subtree[b];
-  for (int d = 0; d < m.nv; d++) { int r = d; while (m.dof_parentid[r] >= 0) r = m.dof_parentid[r]; treeroot[d] = r; }
+  /* tree-sparse mass matrix (MuJoCo's qM layout): row i holds M(i,i), M(i,parent(i)), M(i,parent(parent(i))), ... */
+  {
+    int nM = 0;
+    for (int d = 0; d < m.nv; d++) {
+      const int par = m.dof_parentid[d];
+      if (par >= d) { err = "dofs are not numbered parent-first"; return false; }
+      mrow[3 * d + 2] = par >= 0 ? mrow[3 * par + 2] + 1 : 0;
+      mrow[3 * d] = nM;
+      mrow[3 * d + 1] = 1;
+      nM += mrow[3 * d + 2] + 1;
+    }
+    for (int d = m.nv - 1; d >= 0; d--) if (m.dof_parentid[d] >= 0) mrow[3 * m.dof_parentid[d] + 1] += mrow[3 * d + 1];
+    for (int d = 0; d < m.nv; d++) {   /* a dof's descendants must be the dofs right behind it */
+      const int par = m.dof_parentid[d];
+      if (par >= 0 && d >= par + mrow[3 * par + 1]) { err = "dof subtrees are not contiguous"; return false; }
+    }
+    m.nM = nM;
+  }
   /* depth-first numbering check: every body's parent must precede it and subtrees must be contiguous */
   for (int b = 1; b < m.nbody; b++) {
     const int par = m.body_parentid[b];
     if (par >= b || b >= par + subtree[par]) { err = "bodies are not numbered depth-first"; return false; }
   }
   m.body_subtreesize = subtree;
-  m.dof_treeroot = treeroot;
+  m.dof_mrow = mrow;
   hm.offsets.push_back(off_subtree);
-  hm.offsets.push_back(off_treeroot);
+  hm.offsets.push_back(off_mrow);
   /* hull neighbour table with inline coordinates + extreme-vertex starting points.  The 4th word of an entry is the
      neighbour's OWN adjacency range (first entry | degree << 20), so a hill-climb step is one dependent load level:
      the entries of the vertex it moves to are addressed without another lookup. */

@@ -73,22 +73,44 @@ RG_DEV void rg_contact_col_list(const RgCtx c, const float* r, int d, float sg, 
 }
 RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k == 3 ? r[15] : r[16]); }
 
-/* y = M x (dense, symmetric) */
+/* y = M x with the tree-sparse M: row i couples dof i with its ancestors (stored in row i) and with the dofs of its
+   subtree, which are the dofs right behind it (entry (d, i) sits depth(d) - depth(i) into row d) */
 RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
   RG_LANE_DECL
-  const int nv = RG_MDEREF(c.mref).nv;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const int nv = m.nv;
   float* s = RG_SCRATCH(c);
+  const float* M = s + RG_CL(c).M;
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
-    /* M is packed in reversed dof order: row r = nv-1-i, column q = nv-1-k */
-    const int r = nv - 1 - i;
-    float acc0 = 0.0f, acc1 = 0.0f;
-    const float* row = s + RG_CL(c).M + RG_TRI(r, 0);
-    int q = 0;
-    RG_UNROLL2 for (; q + 1 <= r; q += 2) { acc0 += row[q] * s[x + nv - 1 - q]; acc1 += row[q + 1] * s[x + nv - 2 - q]; }
-    if (q <= r) acc0 += row[q] * s[x + nv - 1 - q];
-    RG_UNROLL2 for (q = r + 1; q < nv; q++) acc1 += s[RG_CL(c).M + RG_TRI(q, r)] * s[x + nv - 1 - q];
-    s[y + i] = acc0 + acc1;
+    const int adr = m.dof_mrow[3 * i], nsub = m.dof_mrow[3 * i + 1], dep = m.dof_mrow[3 * i + 2];
+    float acc = 0.0f;
+    int j = i;
+    RG_NOUNROLL for (int k = 0; k <= dep; k++) { acc += M[adr + k] * s[x + j]; j = m.dof_parentid[j]; }
+    RG_NOUNROLL for (int d = i + 1; d < i + nsub; d++) acc += M[m.dof_mrow[3 * d] + m.dof_mrow[3 * d + 2] - dep] * s[x + d];
+    s[y + i] = acc;
+  }
+  RG_PHASE_END
+}
+
+/* dense H (packed, reversed dof order) <- tree-sparse M (+ diag) */
+RG_DEV void rg_H_from_M(const RgCtx c, const float* diag, float scale) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const RgLayout& L = RG_CL(c);
+  const int nv = m.nv;
+  float* s = RG_SCRATCH(c);
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = 0.0f;
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
+    const float* row = s + L.M + m.dof_mrow[3 * i];
+    int j = i;
+    RG_NOUNROLL for (int k = 0; j >= 0; k++) {
+      s[L.H + RG_HR(nv, i, j)] = row[k] + (k == 0 && diag ? scale * diag[i] : 0.0f);
+      j = m.dof_parentid[j];
+    }
   }
   RG_PHASE_END
 }
@@ -513,9 +535,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     const int refactor = !(have_factor && RG_SI(c, RG_S_SIG) == factor_sig);
 #endif
     if (refactor) {
-    RG_PHASE_BEGIN
-    RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = s[L.M + i];
-    RG_PHASE_END
+    rg_H_from_M(c, nullptr, 0.0f);
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       float add = 0.0f;
@@ -730,9 +750,8 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   const float h = c.timestep;
   int* env = (int*)(s + L.env);
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
+  rg_H_from_M(c, m.dof_damping + 0, h);
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int i = lane; i < nv; i += 32)
-    RG_NOUNROLL for (int j = 0; j <= i; j++) s[L.H + RG_HR(nv, i, j)] = s[L.M + RG_HR(nv, i, j)] + (i == j ? h * m.dof_damping[i] : 0.0f);
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
   RG_PHASE_BEGIN

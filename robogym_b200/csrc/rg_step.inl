@@ -38,12 +38,12 @@ static inline int rg_imax(int a, int b) { return a > b ? a : b; }
 static inline RgLayout rg_make_layout(const RgModel& m) {
   RgLayout L;
   int o = 0;
-#define RG_ALLOC(field, n) do { L.field = o; o += ((n) + 3) & ~3; } while (0)
+#define RG_ALLOC(field, n) do { L.field = o; o += (n); } while (0)   /* scalar 4-byte accesses only: no padding between arrays */
   RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
   RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
   RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
   const int ntri = (m.nv * (m.nv + 1)) >> 1;
-  RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, ntri);
+  RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nM);   /* M: tree-sparse rows (rg_host.h), H: dense packed lower triangle */
   /* H aliases the smooth-dynamics temporaries */
   const int h0 = o;
   RG_ALLOC(Sdot, 6 * rg_imax(m.nv, m.nbody)); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
@@ -160,7 +160,12 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     float* g = io.dbg + (size_t)env * rg_dbg_size(m);
     const int nv = m.nv;
     int o = 0;
-    RG_NOUNROLL for (int i = lane; i < nv * nv; i += 32) { const int r_ = i / nv, c_ = i - r_ * nv; g[o + i] = s[L.M + RG_HR(nv, r_, c_)]; }
+    RG_NOUNROLL for (int i = lane; i < nv * nv; i += 32) {   /* dense nv x nv from the tree-sparse rows */
+      const int r_ = i / nv, c_ = i - r_ * nv;
+      const int hi = r_ > c_ ? r_ : c_, lo = r_ > c_ ? c_ : r_;
+      const int anc = hi < lo + m.dof_mrow[3 * lo + 1];       /* lo is an ancestor of hi (or hi itself) */
+      g[o + i] = anc ? s[L.M + m.dof_mrow[3 * hi] + m.dof_mrow[3 * hi + 2] - m.dof_mrow[3 * lo + 2]] : 0.0f;
+    }
     o += nv * nv;
     RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
       g[o + i] = s[L.bias + i]; g[o + nv + i] = 0.0f; g[o + 2 * nv + i] = 0.0f;   /* passive / actuator split is not kept */

@@ -72,6 +72,9 @@ print(json.dumps(dict(nenv=N, ms_per_env_step=ms, env_steps_per_s=N / ms * 1e3, 
 # stage profile (only meaningful with RG_LIB=...librobogym_b200_prof.so)
 g = sim.dbg_view(0)
 print("dbg env0: ncon", g["ncon"], "nel", g["nel"], "niter", g["niter"])
+import os as _os
+if "prof" not in _os.environ.get("RG_LIB", ""):
+    raise SystemExit(0)          # the stage counters exist only in the -DRG_PROFILE build
 prof = sim.dbg.cpu().numpy()[:, -16:]
 names = ["kin", "massm", "bias", "tendon", "forces", "collide", "mkcon", "solve", "euler", "col:A-sphere", "col:B-obb", "col:C-narrow+write", "col:C-rounds", "-", "-", "col:loop"]
 tot = prof[:, :9].sum(1).mean()
