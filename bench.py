@@ -27,8 +27,8 @@ NENV_PER_GPU = 8192
 NSUB = 10
 ALGO_BYTES_PER_ENV_STEP = 1664       # 784 B read + 680 B written + ~200 B derived outputs
 # dram__bytes_read.sum + dram__bytes_write.sum of rg_step_kernel for one 8192-env launch, from the ncu --set full
-# capture summarised in profiles/r1h_ncu_metrics.csv (13.08 MB + 2.97 MB); re-measure when the kernel changes
-NCU_DRAM_BYTES_PER_LAUNCH = 14.16e6
+# capture summarised in profiles/r1i_ncu_metrics.csv (13.08 MB + 2.97 MB); re-measure when the kernel changes
+NCU_DRAM_BYTES_PER_LAUNCH = 17.06e6
 ACTION_SCALE = 0.3                   # relative random actions: ctrl += a * 0.3 * half-range, a ~ U(-1, 1)
 METRIC = "env-steps/sec dactyl/locked batch 8192 @1/2/4/8 B200 vs CPU mujoco-py"
 
@@ -358,7 +358,7 @@ def run_gpu_arm(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
             "gpu_launches": args.steps * world,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu, profiles/r1h_ncu_metrics.csv)",
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_metrics.csv)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
                          "note": "algorithmic 1664 B/env-step; the path is FP32-issue/latency bound, not HBM bound (DESIGN.md)"},
