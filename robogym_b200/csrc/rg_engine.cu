@@ -132,9 +132,13 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   const int total = args.nslots ? *args.nslots : args.io.nenv;
   const int iters = (total + stride - 1) / stride;   /* 0 for an empty subset */
   for (int it = 0; it < iters; it++) {
-    const int slot = it * stride + blockIdx.x * args.warps + warp;
+    /* the slot table is sorted by cost: walk the CTAs forwards in even iterations and backwards in odd ones, so that no
+       CTA collects the expensive end of every band (CTAs do not synchronise with each other: the slowest one is the
+       kernel time); padding slots replay the cheapest environment and discard the result */
+    const int pos = (it & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int slot = it * stride + pos * args.warps + warp;
     const int valid = slot < total;
-    const int e = args.order ? args.order[valid ? slot : total - 1] : (valid ? slot : total - 1);
+    const int e = args.order ? args.order[valid ? slot : 0] : (valid ? slot : 0);
     if (args.nover > 0) {
       const int lane = threadIdx.x & 31;
       for (int i = lane; i < (int)(sizeof(RgModelDev) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
