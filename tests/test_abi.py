@@ -41,3 +41,18 @@ def test_product_path_fails_loudly_without_gpu(locked_blob):
         pytest.skip("GPU present")
     with pytest.raises(engine.EngineError):
         engine.DeviceModel(locked_blob, 0)
+
+
+def test_scratch_budget_keeps_ten_environments_per_sm(locked_blob):
+    """dactyl/locked must keep fitting 10 environments per SM: 227 KB opt-in shared memory minus the static part, the
+    staged model arrays and the device model view, divided by 10 (rg_batch_size in rg_engine.cu).  Uses the CPU
+    emulation build's layout, which is the same rg_make_layout()."""
+    import pyemu
+    from robogym_b200 import modelblob
+
+    m = modelblob.unpack(locked_blob)
+    e = pyemu.EmuBatch(locked_blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    scratch = 4 * pyemu.lib().rge_scratch_floats(e.h)
+    small = pyemu.lib().rge_small_bytes(e.h)
+    fixed = 640 + ((small + 127) & ~127) + 64 + 1152           # model view (576 B today) + staged arrays + slack + static shared
+    assert (232448 - fixed) // scratch >= 10, (scratch, small)
