@@ -357,7 +357,7 @@ def run_gpu_arm(args):
                        "launch": info, "cubes_on_palm_at_end": on_palm, "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
-            "gpu_launches": args.steps * world,
+            "gpu_launches": 2 * args.steps * world,   # per step: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_metrics.csv)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
