@@ -1,4 +1,5 @@
-"""First-light check on a B200: teacher-forced parity of the CUDA engine vs the fp64 oracle on
+"""(Test tooling: compares the engine with the oracle -- lives under tests/ because only tests may load oracle/.)
+First-light check on a B200: teacher-forced parity of the CUDA engine vs the fp64 oracle on
 states sampled along an oracle rollout, then a throughput probe at batch 8192."""
 import json
 import os
@@ -7,7 +8,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 

@@ -1,4 +1,5 @@
-"""Free-running parity study (SURVEY.md 8(d) tiers T2/T3) on a B200: the CUDA engine and the fp64 oracle start
+"""(Test tooling: compares the engine with the oracle -- lives under tests/ because only tests may load oracle/.)
+Free-running parity study (SURVEY.md 8(d) tiers T2/T3) on a B200: the CUDA engine and the fp64 oracle start
 from identical states and receive identical action streams for 200 env-steps (2000 substeps); reports the
 divergence curve and statistical invariants.  Writes gpurun_out/parity_study.json."""
 import json
@@ -7,7 +8,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
