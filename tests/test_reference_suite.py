@@ -26,6 +26,10 @@ CASES = [
     ("robogym/tests/test_robot_env.py", None, 1),
     # test_remove_elem compares XML attribute order of the reference's own pure-Python composer under py3.12
     ("robogym/mujoco/test/test_mujoco_utils.py", "not remove_elem", 5),
+    ("robogym/envs/tests/test_wrapper_compositions.py", None, 1),
+    ("robogym/randomization/tests/test_randomization.py", None, 4),
+    # the other tests of this file reset the full Rubik's cube env, which needs the real pycuber package
+    ("robogym/wrappers/tests/test_randomizations.py", "randomize_obs_wrapper or replace_cube_obs_vision_wrapper", 2),
 ]
 
 
