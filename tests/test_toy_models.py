@@ -86,3 +86,43 @@ def test_cuda_matches_oracle_on_free_bodies(toy):
     assert np.median(eq) < 1e-4 and np.median(ev) < 2e-2
     # free-joint world positions come back un-shifted
     assert np.abs(sim.body_xpos[:, cm.name2id("body", "box")].cpu().numpy() - q[:, 0:3]).max() < 1e-5
+
+
+def _equilibrium_penetration(condim, mu=0.9, g=9.81, solref=(0.02, 1.0), solimp=(0.9, 0.95, 0.001, 0.5, 2.0)):
+    """Closed form of MuJoCo's soft-contact law for a free sphere at rest on a plane (documentation, 'Computation'):
+    reference acceleration aref = -b v - k d(r) r with k = 1 / (dmax^2 timeconst^2 dampratio^2), regulariser
+    R = (1 - d) / d * A with A = 1/m for a free body (A = (1 + mu^2)/m for the rows n +- mu t of a friction pyramid, which
+    then share R_py = 2 mu^2 R).  At rest the constraint force m g = sum_rows aref / R_row, which gives
+    |r| = g (1 - d) / (k d^2) for condim 1 and mu^2 (1 + mu^2) / 2 times that for a 4-row pyramid; d depends on |r|
+    through the solimp sigmoid, hence the fixed point."""
+    d0, d1, width, mid, power = solimp
+    k = 1.0 / (d1 ** 2 * solref[0] ** 2 * solref[1] ** 2)
+    scale = 1.0 if condim == 1 else mu * mu * (1.0 + mu * mu) / 2.0
+    r = 1e-4
+    for _ in range(200):
+        x = min(r / width, 1.0)
+        y = x ** power / mid ** (power - 1) if x <= mid else 1.0 - (1.0 - x) ** power / (1.0 - mid) ** (power - 1)
+        d = d0 + y * (d1 - d0)
+        r = scale * g * (1.0 - d) / (k * d * d)
+    return r
+
+
+@pytest.mark.parametrize("condim", [1, 3])
+def test_resting_sphere_sits_at_the_closed_form_penetration(condim):
+    """Contact impedance, regularisation, pyramid scaling, solver and integrator together reach the analytic fixed
+    point: fp64 oracle to 1e-8 m, the fp32 kernel logic (CPU emulation) to 2e-6 m."""
+    from toy_models import RESTING_SPHERE
+
+    cm = mjcf.compile_mjcf(RESTING_SPHERE.format(condim=condim))
+    blob = cm.blob()
+    want = 0.05 - _equilibrium_penetration(condim)
+    om, d = oracle_pair(blob)
+    for _ in range(4000):
+        d.step()
+    assert d.ncon[0] == 1 and np.abs(d.qvel).max() < 1e-9
+    assert abs(d.qpos[2] - want) < 1e-8, (d.qpos[2], want)
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0] = cm.m["qpos0"]
+    e.step(4000, 1)
+    assert int(e.warn[0]) == 0 and int(e.ncon[0]) == 1
+    assert abs(float(e.qpos[0, 2]) - want) < 2e-6, (float(e.qpos[0, 2]), want)

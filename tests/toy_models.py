@@ -37,3 +37,19 @@ FREE_BODIES = """
   </actuator>
 </mujoco>
 """
+
+# a sphere resting on a plane: the equilibrium penetration of MuJoCo's soft contact model has a closed form
+RESTING_SPHERE = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" iterations="50" tolerance="1e-12"/>
+  <size nuserdata="0" njmax="50" nconmax="10"/>
+  <worldbody>
+    <body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="{condim}" friction="0.9 0.005 0.0001"/></body>
+    <body name="ball" pos="0 0 0.0499">
+      <joint name="ball_free" type="free"/>
+      <geom name="ball" type="sphere" size="0.05" density="700" condim="{condim}" friction="0.9 0.005 0.0001"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
