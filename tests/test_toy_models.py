@@ -126,3 +126,35 @@ def test_resting_sphere_sits_at_the_closed_form_penetration(condim):
     e.step(4000, 1)
     assert int(e.warn[0]) == 0 and int(e.ncon[0]) == 1
     assert abs(float(e.qpos[0, 2]) - want) < 2e-6, (float(e.qpos[0, 2]), want)
+
+
+def test_dry_friction_stick_and_slip_have_the_closed_form_rates():
+    """frictionloss rows (MuJoCo 'Computation': a box constraint |f| <= frictionloss with the same soft regularisation):
+    below the threshold the slider creeps at v = u R / b with R = (1 - d0)/d0 / m and b = 2 / (dmax timeconst) -- the
+    constraint is soft, not rigid -- and above it accelerates at (u - frictionloss) / m."""
+    from toy_models import FRICTION_SLIDER
+
+    cm = mjcf.compile_mjcf(FRICTION_SLIDER)
+    blob = cm.blob()
+    m_, floss, d0, dmax, tc = 2.0, 1.5, 0.9, 0.95, 0.02
+    creep = lambda u: u * ((1 - d0) / d0 / m_) / (2.0 / (dmax * tc))
+    dims = {k: cm.m[k] for k in modelblob.DIMS}
+    for u, rate_tol in ((0.6, 1e-9), (-1.2, 1e-9)):
+        om, d = oracle_pair(blob)
+        d.ctrl[0] = u
+        for _ in range(2000):
+            d.step()
+        assert abs(d.qvel[0] - creep(u)) < rate_tol + 1e-6 * abs(creep(u)), (u, d.qvel[0], creep(u))
+        e = pyemu.EmuBatch(blob, dims, 1)
+        e.ctrl[0, 0] = u
+        e.step(2000, 1)
+        assert abs(float(e.qvel[0, 0]) - creep(u)) < 1e-5 * abs(creep(u)) + 1e-8
+    om, d = oracle_pair(blob)
+    d.ctrl[0] = 4.0
+    for _ in range(500):
+        d.step()
+    assert abs(d.qvel[0] - (4.0 - floss) / m_ * 500 * 0.002) < 1e-9
+    e = pyemu.EmuBatch(blob, dims, 1)
+    e.ctrl[0, 0] = 4.0
+    e.step(500, 1)
+    assert abs(float(e.qvel[0, 0]) - (4.0 - floss) / m_ * 1.0) < 1e-4

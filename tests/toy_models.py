@@ -53,3 +53,21 @@ RESTING_SPHERE = """
   </worldbody>
 </mujoco>
 """
+
+# a 2 kg slider with dry friction (frictionloss) pushed by a motor: stick / slip have closed forms
+FRICTION_SLIDER = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" iterations="50" tolerance="1e-12" gravity="0 0 0"/>
+  <size nuserdata="0" njmax="50" nconmax="10"/>
+  <worldbody>
+    <body name="cart" pos="0 0 0">
+      <joint name="x" type="slide" axis="1 0 0" frictionloss="1.5"/>
+      <geom name="cart" type="box" size="0.1 0.1 0.1" mass="2.0" contype="0" conaffinity="0"/>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor name="push" joint="x" gear="1" ctrllimited="true" ctrlrange="-10 10"/>
+  </actuator>
+</mujoco>
+"""
