@@ -158,3 +158,38 @@ def test_dry_friction_stick_and_slip_have_the_closed_form_rates():
     e.ctrl[0, 0] = 4.0
     e.step(500, 1)
     assert abs(float(e.qvel[0, 0]) - (4.0 - floss) / m_ * 1.0) < 1e-4
+
+
+def test_primitive_pairs_have_the_closed_form_penetration():
+    """Minkowski Portal Refinement (libccd's algorithm, tolerance 1e-6) on pairs whose answer is known:
+    sphere-sphere (r1 + r2 - |c|), capsule-sphere off the axis, sphere pressed into a box face.
+    MuJoCo reports dist = -depth along the normal pointing from geom1 to geom2."""
+    from toy_models import PRIMITIVE_PAIRS
+
+    cm = mjcf.compile_mjcf(PRIMITIVE_PAIRS)
+    blob = cm.blob()
+    gid = lambda n: cm.name2id("geom", n)
+    want = {
+        (gid("s1"), gid("s2")): (-(0.05 + 0.04 - 0.08), (1.0, 0.0, 0.0)),
+        (gid("c1"), gid("s3")): (-(0.03 + 0.03 - 0.05), (1.0, 0.0, 0.0)),          # sphere beside the capsule's cylinder part
+        (gid("b1"), gid("s4")): (-(0.05 + 0.04 - 0.085), (0.0, 0.0, 1.0)),         # sphere 5 mm into the +z face
+    }
+    om, d = oracle_pair(blob)
+    d.forward()
+    # MuJoCo puts the geom of lower type first in a pair (sphere < capsule < box): flip the expected normal accordingly
+    canon = lambda recs: {tuple(sorted((int(r[20]), int(r[21])))): (r, 1.0 if int(r[20]) < int(r[21]) else -1.0) for r in recs}
+    got = canon(d.contact.reshape(-1, 24)[:int(d.ncon[0])])
+    assert set(got) == set(want)
+    for key, (dist, n) in want.items():
+        r, sgn = got[key]
+        assert abs(r[0] - dist) < 2e-6, (key, r[0], dist)
+        assert np.abs(r[4:7] - sgn * np.array(n)).max() < 2e-3
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0] = cm.m["qpos0"]
+    e.forward()
+    con = e.dbg_view()["con"][:int(e.ncon[0])]
+    gote = canon(con)
+    assert set(gote) == set(want)
+    for key, (dist, n) in want.items():
+        r, sgn = gote[key]
+        assert abs(r[0] - dist) < 5e-6 and np.abs(r[4:7] - sgn * np.array(n)).max() < 5e-3

@@ -71,3 +71,22 @@ FRICTION_SLIDER = """
   </actuator>
 </mujoco>
 """
+
+# pairs of primitives held in known relative poses (no joints: everything is welded to the world, contacts are still
+# generated between geoms of different bodies) -- penetration depth and normal have closed forms
+PRIMITIVE_PAIRS = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" gravity="0 0 0"/>
+  <size nuserdata="0" njmax="100" nconmax="20"/>
+  <worldbody>
+    <body name="anchor" pos="0 0 0"><joint name="dummy" type="slide" axis="0 0 1"/><geom name="dummy" type="sphere" size="0.001" pos="5 5 5" mass="1" contype="0" conaffinity="0"/></body>
+    <body name="s1" pos="0 0 0"><geom name="s1" type="sphere" size="0.05" condim="1"/></body>
+    <body name="s2" pos="0.08 0 0"><joint name="j_s2" type="slide" axis="1 0 0"/><geom name="s2" type="sphere" size="0.04" mass="1" condim="1"/></body>
+    <body name="c1" pos="0 1 0"><geom name="c1" type="capsule" size="0.03 0.1" condim="1"/></body>
+    <body name="s3" pos="0.05 1 0.02"><joint name="j_s3" type="slide" axis="1 0 0"/><geom name="s3" type="sphere" size="0.03" mass="1" condim="1"/></body>
+    <body name="b1" pos="0 2 0"><geom name="b1" type="box" size="0.1 0.08 0.05" condim="1"/></body>
+    <body name="s4" pos="0.02 2.01 0.085"><joint name="j_s4" type="slide" axis="0 0 1"/><geom name="s4" type="sphere" size="0.04" mass="1" condim="1"/></body>
+  </worldbody>
+</mujoco>
+"""
