@@ -334,6 +334,8 @@ int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t 
     if (!strcmp(name, "body_pos")) /* keep the fp32 world shift */
       for (int b = 1; b < m.nbody; b++)
         if (m.body_parentid[b] == 0) for (int a = 0; a < 3; a++) d[3 * b + a] = (float)(s[3 * b + a] - (double)m.origin[a]);
+    if (!strcmp(name, "geom_pos")) for (int g = 0; g < m.ngeom; g++) if (m.geom_bodyid[g] == 0) for (int a = 0; a < 3; a++) d[3 * g + a] -= m.origin[a];
+    if (!strcmp(name, "site_pos")) for (int k = 0; k < m.nsite; k++) if (m.site_bodyid[k] == 0) for (int a = 0; a < 3; a++) d[3 * k + a] -= m.origin[a];
   }
   const size_t off = (const char*)hptr - mm->hm.arena.data();
   RG_CUDA(cudaSetDevice(mm->device));

@@ -184,6 +184,12 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   float* body_pos = (float*)m.body_pos;
   for (int b = 1; b < m.nbody; b++)
     if (m.body_parentid[b] == 0) for (int a = 0; a < 3; a++) body_pos[3 * b + a] = (float)(bp[3 * b + a] - (double)m.origin[a]);
+  /* the world body stays at the (shifted) origin, so geoms and sites attached to it directly are shifted themselves */
+  {
+    float* gp = (float*)m.geom_pos; float* sp = (float*)m.site_pos;
+    for (int g = 0; g < m.ngeom; g++) if (m.geom_bodyid[g] == 0) for (int a = 0; a < 3; a++) gp[3 * g + a] -= m.origin[a];
+    for (int k = 0; k < m.nsite; k++) if (m.site_bodyid[k] == 0) for (int a = 0; a < 3; a++) sp[3 * k + a] -= m.origin[a];
+  }
   m.small_bytes = (int)hm.small_bytes;
   if (m.nv > 32 * 8 || m.nmaskw > 8) { err = "model too large for the warp-per-env engine"; return false; }
   return true;

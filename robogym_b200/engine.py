@@ -169,13 +169,17 @@ class BatchedSim:
         v = t.as_tensor(np.asarray(values, dtype=np.float64) if not t.is_tensor(values) else values).to(t.float64).reshape(self.nenv, -1).clone()
         if v.shape[1] != m[name].size:
             raise EngineError(f"set_param({name}): expected {m[name].size} values per environment, got {v.shape[1]}")
-        if name == "body_pos":   # keep the engine's fp32 world shift for bodies attached to the world
+        if name in ("body_pos", "geom_pos", "site_pos"):
+            # keep the engine's fp32 world shift: bodies attached to the world, and geoms / sites attached to the world body
             o = (ctypes.c_float * 3)()
             _check(lib().rg_model_origin(self.model.h, o))
             rows = v.reshape(self.nenv, -1, 3)
-            root = t.as_tensor(np.asarray(m["body_parentid"]) == 0)
-            root[0] = False
-            rows[:, root] -= t.tensor(list(o), dtype=t.float64)
+            if name == "body_pos":
+                sel = t.as_tensor(np.asarray(m["body_parentid"]) == 0)
+                sel[0] = False
+            else:
+                sel = t.as_tensor(np.asarray(m["geom_bodyid" if name == "geom_pos" else "site_bodyid"]) == 0)
+            rows[:, sel] -= t.tensor(list(o), dtype=t.float64)
         dev = v.to(device=self.device, dtype=t.float32).contiguous()
         if not hasattr(self, "_params"):
             self._params = {}

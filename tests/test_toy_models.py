@@ -193,3 +193,39 @@ def test_primitive_pairs_have_the_closed_form_penetration():
     for key, (dist, n) in want.items():
         r, sgn = gote[key]
         assert abs(r[0] - dist) < 5e-6 and np.abs(r[4:7] - sgn * np.array(n)).max() < 5e-3
+
+
+def test_cylinder_wrapped_tendon_has_the_closed_form_length_and_moment_arm():
+    """Spatial tendon over a cylinder: length = two tangent segments + the arc between the tangent points; its
+    derivative w.r.t. the slider (the tendon Jacobian / moment arm) is the cosine between the slide axis and the last
+    segment.  Checked for the compile-time numpy geometry, the oracle and the emulated kernel at three slider positions."""
+    from toy_models import WRAPPED_TENDON
+
+    cm = mjcf.compile_mjcf(WRAPPED_TENDON)
+    blob = cm.blob()
+    R, c = 0.03, np.array([0.0, -0.01])
+
+    def analytic(xb):
+        p1, p2 = np.array([-0.1, 0.0]) - c, np.array([xb, 0.0]) - c
+        d1, d2 = np.linalg.norm(p1), np.linalg.norm(p2)
+        phi = np.arccos(np.dot(p1, p2) / (d1 * d2))                    # angle subtended at the axis (over the top)
+        arc = phi - np.arccos(R / d1) - np.arccos(R / d2)
+        assert arc > 0
+        return np.sqrt(d1 * d1 - R * R) + np.sqrt(d2 * d2 - R * R) + R * arc
+
+    dims = {k: cm.m[k] for k in modelblob.DIMS}
+    for q in (0.0, 0.05, -0.04):
+        xb = 0.1 + q
+        want = analytic(xb)
+        darm = (analytic(xb + 1e-6) - analytic(xb - 1e-6)) / 2e-6
+        L, J = mjcf.tendon_eval(cm.m, np.array([q]))
+        assert abs(L[0] - want) < 1e-12 and abs(J[0, 0] - darm) < 1e-6
+        om, d = oracle_pair(blob)
+        d.qpos[0] = q
+        d.forward()
+        assert abs(d.ten_length[0] - want) < 1e-12 and abs(d.ten_J[0] - darm) < 1e-6
+        e = pyemu.EmuBatch(blob, dims, 1)
+        e.qpos[0, 0] = q
+        e.forward()
+        g = e.dbg_view()
+        assert abs(float(g["tlen"][0]) - want) < 1e-6 and abs(float(g["tJ"][0, 0]) - darm) < 1e-5

@@ -90,3 +90,27 @@ PRIMITIVE_PAIRS = """
   </worldbody>
 </mujoco>
 """
+
+# a string from site a over a cylinder (axis z) to site b on a slider: the wrapped length is two tangents plus an arc
+WRAPPED_TENDON = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" gravity="0 0 0"/>
+  <size nuserdata="0" njmax="50" nconmax="10"/>
+  <worldbody>
+    <site name="a" pos="-0.1 0 0"/>
+    <body name="post" pos="0 -0.01 0">
+      <geom name="cyl" type="cylinder" size="0.03 0.1" contype="0" conaffinity="0"/>
+      <site name="side" pos="0 0.05 0"/>
+    </body>
+    <body name="cart" pos="0.1 0 0">
+      <joint name="x" type="slide" axis="1 0 0"/>
+      <geom name="cart" type="sphere" size="0.01" mass="1" contype="0" conaffinity="0"/>
+      <site name="b" pos="0 0 0"/>
+    </body>
+  </worldbody>
+  <tendon>
+    <spatial name="string"><site site="a"/><geom geom="cyl" sidesite="side"/><site site="b"/></spatial>
+  </tendon>
+</mujoco>
+"""
