@@ -256,12 +256,19 @@ RG_DEV_NOINLINE void rg_bias(const RgCtx c) {
   const float* qvel = s + L.qvel;
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) {
+    /* velocity the axis of dof d rides on: every ancestor dof EXCEPT the other rotational dofs of its own ball / free
+       joint -- their axes are fixed in the same body and turn together (MuJoCo's mj_comVel computes the three
+       cdof_dot of a ball joint from the velocity before any of them is added); a free joint's translations do count */
     float V[6] = {0, 0, 0, 0, 0, 0};
+    const int jd = m.dof_jntid[d], jt = m.jnt_type[jd], j0 = m.jnt_dofadr[jd];
     int a = m.dof_parentid[d];
     while (a >= 0) {
-      const float* Sa = s + L.S + 6 * a;
-      const float qa = qvel[a];
-      for (int k = 0; k < 6; k++) V[k] += Sa[k] * qa;
+      const int own_rot = a >= j0 && ((jt == RG_JNT_BALL) || (jt == RG_JNT_FREE && a >= j0 + 3));
+      if (!own_rot) {
+        const float* Sa = s + L.S + 6 * a;
+        const float qa = qvel[a];
+        for (int k = 0; k < 6; k++) V[k] += Sa[k] * qa;
+      }
       a = m.dof_parentid[a];
     }
     rg_cross_motion(s + L.Sdot + 6 * d, V, s + L.S + 6 * d);

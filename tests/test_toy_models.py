@@ -229,3 +229,61 @@ def test_cylinder_wrapped_tendon_has_the_closed_form_length_and_moment_arm():
         e.forward()
         g = e.dbg_view()
         assert abs(float(g["tlen"][0]) - want) < 1e-6 and abs(float(g["tJ"][0, 0]) - darm) < 1e-5
+
+
+def test_primitive_inertias_and_torque_free_rotation():
+    """Compiler: mass / principal inertia of box, capsule, cylinder, sphere from density (textbook formulas).
+    Dynamics: a torque-free asymmetric body keeps its world-frame angular momentum and kinetic energy (gyroscopic bias
+    terms + quaternion integration); fp64 oracle and fp32 kernel logic over 0.5 s of tumbling."""
+    from toy_models import SPINNING_BRICK
+
+    cm = mjcf.compile_mjcf(SPINNING_BRICK)
+    m = cm.m
+    bid = lambda n: cm.name2id("body", n)
+    I = m["body_inertia"].reshape(-1, 3)
+    a, b, c = 0.06, 0.04, 0.02
+    mb = 1000 * 8 * a * b * c
+    assert abs(m["body_mass"][bid("brick")] - mb) < 1e-12
+    assert np.allclose(sorted(I[bid("brick")]), sorted([mb / 3 * (b * b + c * c), mb / 3 * (a * a + c * c), mb / 3 * (a * a + b * b)]), rtol=1e-12)
+    r, h = 0.03, 0.08                       # capsule: cylinder of half-length h plus two hemispheres
+    mc, ms = 500 * np.pi * r * r * 2 * h, 500 * 4 / 3 * np.pi * r ** 3
+    assert abs(m["body_mass"][bid("caps")] - (mc + ms)) < 1e-12
+    Izz = 0.5 * mc * r * r + 0.4 * ms * r * r
+    Ixx = mc * (r * r / 4 + (2 * h) ** 2 / 12) + ms * (0.4 * r * r + h * h + 0.75 * h * r)
+    assert np.allclose(sorted(I[bid("caps")]), sorted([Ixx, Ixx, Izz]), rtol=1e-10)
+    mcy = 500 * np.pi * r * r * 2 * h
+    assert np.allclose(sorted(I[bid("cyl")]), sorted([mcy * (r * r / 4 + (2 * h) ** 2 / 12)] * 2 + [0.5 * mcy * r * r]), rtol=1e-12)
+    msp = 500 * 4 / 3 * np.pi * 0.05 ** 3
+    assert np.allclose(I[bid("ball")], 0.4 * msp * 0.05 ** 2, rtol=1e-12)
+
+    blob = cm.blob()
+    Ib = np.diag(I[bid("brick")])
+    iq = m["body_iquat"].reshape(-1, 4)[bid("brick")]
+
+    def momentum(qpos, qvel):
+        R = mjcf.quat2mat(mjcf.quat_mul(qpos[3:7], iq))       # principal axes in the world
+        w_world = mjcf.quat2mat(qpos[3:7]) @ qvel[3:6]         # free-joint angular velocity is expressed in the body frame
+        return R @ Ib @ R.T @ w_world, 0.5 * w_world @ (R @ Ib @ R.T) @ w_world
+
+    om, d = oracle_pair(blob)
+    d.qvel[3:6] = [3.0, 0.2, 5.0]                              # near the unstable middle axis: it tumbles
+    q0, v0 = d.qpos.copy(), d.qvel.copy()
+    L0, E0 = momentum(d.qpos[:7], d.qvel[:6])
+    for _ in range(500):
+        d.step()
+    L1, E1 = momentum(d.qpos[:7], d.qvel[:6])
+    assert np.abs(d.qpos[3:7] - q0[3:7]).max() > 0.3          # it really tumbled
+    assert np.abs(L1 - L0).max() < 2e-3 * np.linalg.norm(L0) and abs(E1 - E0) < 2e-3 * E0
+    # fp32 kernel logic: the same invariants over the same horizon (tumbling about the middle axis amplifies round-off
+    # exponentially, so the trajectories themselves are only compared over the first 50 steps)
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0], e.qvel[0] = q0, v0
+    e.step(50, 1)
+    om2, d2 = oracle_pair(blob)
+    d2.qpos[:], d2.qvel[:] = q0, v0
+    for _ in range(50):
+        d2.step()
+    assert np.abs(e.qpos[0, :7] - d2.qpos[:7]).max() < 2e-5 and np.abs(e.qvel[0, :6] - d2.qvel[:6]).max() < 2e-4
+    e.step(450, 1)
+    L2, E2 = momentum(e.qpos[0, :7].astype(float), e.qvel[0, :6].astype(float))
+    assert np.abs(L2 - L0).max() < 3e-3 * np.linalg.norm(L0) and abs(E2 - E0) < 3e-3 * E0

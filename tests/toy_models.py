@@ -114,3 +114,21 @@ WRAPPED_TENDON = """
   </tendon>
 </mujoco>
 """
+
+# torque-free spinning brick (no gravity, no contacts) and primitives whose mass / inertia have textbook formulas
+SPINNING_BRICK = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.001" gravity="0 0 0"/>
+  <size nuserdata="0" njmax="20" nconmax="5"/>
+  <worldbody>
+    <body name="brick" pos="0 0 1">
+      <joint name="free" type="free"/>
+      <geom name="brick" type="box" size="0.06 0.04 0.02" density="1000" contype="0" conaffinity="0"/>
+    </body>
+    <body name="caps" pos="1 0 1"><joint name="f2" type="free"/><geom name="caps" type="capsule" size="0.03 0.08" density="500" contype="0" conaffinity="0"/></body>
+    <body name="cyl" pos="2 0 1"><joint name="f3" type="free"/><geom name="cyl" type="cylinder" size="0.03 0.08" density="500" contype="0" conaffinity="0"/></body>
+    <body name="ball" pos="3 0 1"><joint name="f4" type="free"/><geom name="ball" type="sphere" size="0.05" density="500" contype="0" conaffinity="0"/></body>
+  </worldbody>
+</mujoco>
+"""
