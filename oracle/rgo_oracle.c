@@ -485,9 +485,18 @@ static void rgo_velocity(const rgo_model* m, rgo_data* d) {
     for (int k = 0; k < m->body_jntnum[b]; k++) {
       int j = m->body_jntadr[b] + k, da = m->jnt_dofadr[j];
       int nd = m->jnt_type[j] == JNT_FREE ? 6 : (m->jnt_type[j] == JNT_BALL ? 3 : 1);
-      /* axis derivative uses the velocity accumulated before this joint */
-      for (int a = 0; a < nd; a++) cross_motion(d->dof_Sdot + 6 * (da + a), V, d->dof_S + 6 * (da + a));
-      for (int a = 0; a < nd; a++)
+      /* axis derivative: the velocity accumulated before the joint's rotational dofs -- the three axes of a ball joint
+         turn together, so its own rotation does not enter; a free joint's translations come first and do count
+         (mj_comVel: cdof_dot = 0 for the translations, cvel += them, then the ball rule for the rotations) */
+      int a0 = 0;
+      if (m->jnt_type[j] == JNT_FREE) {
+        for (int a = 0; a < 3; a++) cross_motion(d->dof_Sdot + 6 * (da + a), V, d->dof_S + 6 * (da + a));
+        for (int a = 0; a < 3; a++)
+          for (int i = 0; i < 6; i++) V[i] += d->dof_S[6 * (da + a) + i] * d->qvel[da + a];
+        a0 = 3;
+      }
+      for (int a = a0; a < nd; a++) cross_motion(d->dof_Sdot + 6 * (da + a), V, d->dof_S + 6 * (da + a));
+      for (int a = a0; a < nd; a++)
         for (int i = 0; i < 6; i++) V[i] += d->dof_S[6 * (da + a) + i] * d->qvel[da + a];
     }
     memcpy(d->cvel + 6 * b, V, sizeof V);
