@@ -287,3 +287,37 @@ def test_primitive_inertias_and_torque_free_rotation():
     e.step(450, 1)
     L2, E2 = momentum(e.qpos[0, :7].astype(float), e.qvel[0, :6].astype(float))
     assert np.abs(L2 - L0).max() < 3e-3 * np.linalg.norm(L0) and abs(E2 - E0) < 3e-3 * E0
+
+
+@pytest.mark.parametrize("name,qtol,vtol", [("ball_chain", 1e-5, 2e-3), ("contacts", 2e-5, 2e-2)])
+def test_emulated_kernel_matches_oracle_on_feature_models(name, qtol, vtol):
+    """Teacher-forced 5-substep comparisons along an oracle rollout: fp32 kernel logic vs fp64 oracle on joint / geom /
+    contact kinds the dactyl models do not contain (every stage: M, bias, contact counts, state after the step)."""
+    from toy_models import MODELS
+
+    cm = mjcf.compile_mjcf(MODELS[name])
+    blob, m = cm.blob(), cm.m
+    om, d = oracle_pair(blob)
+    if name == "ball_chain":
+        d.qvel[:] = np.random.RandomState(0).uniform(-3, 3, m["nv"])
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    worst_q = worst_v = 0.0
+    same_ncon = 0
+    for it in range(20):
+        for _ in range(15):
+            d.step()
+        d.forward()
+        e.qpos[0], e.qvel[0], e.warm[0] = d.qpos, d.qvel, d.qacc_warmstart
+        e.forward()
+        g = e.dbg_view()
+        assert np.abs(g["M"].ravel() - d.M).max() < 1e-5 * np.abs(d.M).max()
+        assert np.abs(g["bias"] - d.qfrc_bias).max() < 1e-4 * max(1e-6, np.abs(d.qfrc_bias).max())
+        e.step(5, 1)
+        for _ in range(5):
+            d.step()
+        d.forward()
+        same_ncon += int(e.ncon[0]) == int(d.ncon[0])
+        worst_q = max(worst_q, float(np.abs(e.qpos[0] - d.qpos).max()))
+        worst_v = max(worst_v, float(np.abs(e.qvel[0] - d.qvel).max()))
+        assert int(e.warn[0]) == 0
+    assert worst_q < qtol and worst_v < vtol and same_ncon >= 18, (worst_q, worst_v, same_ncon)

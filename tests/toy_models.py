@@ -132,3 +132,30 @@ SPINNING_BRICK = """
   </worldbody>
 </mujoco>
 """
+
+# more joint / geom / contact kinds than any dactyl model has: ball joints inside a chain, joint springs, a limited slide,
+# ellipsoid inertia; capsule / cylinder / ellipsoid / box-on-box / sphere-on-sphere contacts with condim 3, 4 and 6
+MODELS = {}
+MODELS['ball_chain'] = """
+<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/>
+<size nuserdata="0" njmax="100" nconmax="20"/>
+<worldbody>
+ <body name="a" pos="0 0 1"><joint name="b1" type="ball" damping="0.01"/><geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.02" density="800" contype="0" conaffinity="0"/>
+  <body name="b" pos="0.2 0 0"><joint name="h1" type="hinge" axis="0 1 0" damping="0.01" stiffness="0.3" springref="0.2"/><geom type="box" size="0.08 0.02 0.03" pos="0.08 0 0" density="600" contype="0" conaffinity="0"/>
+   <body name="c" pos="0.16 0 0"><joint name="b2" type="ball"/><joint name="s1" type="slide" axis="1 0 0" damping="0.5" limited="true" range="-0.02 0.05"/><geom type="ellipsoid" size="0.04 0.02 0.03" density="700" contype="0" conaffinity="0"/></body>
+  </body>
+ </body>
+</worldbody></mujoco>"""
+MODELS['contacts'] = """
+<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/>
+<size nuserdata="0" njmax="200" nconmax="40"/>
+<worldbody>
+ <body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>
+ <body name="cap" pos="0 0 0.06" euler="0 1.4 0.3"><joint type="free"/><geom type="capsule" size="0.03 0.08" density="600" condim="4"/></body>
+ <body name="cyl" pos="0.3 0 0.05" euler="1.5 0.1 0"><joint type="free"/><geom type="cylinder" size="0.04 0.06" density="600" condim="3"/></body>
+ <body name="ell" pos="-0.3 0 0.05"><joint type="free"/><geom type="ellipsoid" size="0.05 0.03 0.04" density="600" condim="6"/></body>
+ <body name="bx" pos="0 0.3 0.04"><joint type="free"/><geom type="box" size="0.05 0.04 0.03" density="600" condim="3"/></body>
+ <body name="bx2" pos="0.02 0.31 0.105" euler="0 0 0.4"><joint type="free"/><geom type="box" size="0.03 0.03 0.03" density="600" condim="3"/></body>
+ <body name="sp" pos="0.01 -0.3 0.04"><joint type="free"/><geom type="sphere" size="0.04" density="600" condim="3"/></body>
+ <body name="sp2" pos="0.02 -0.29 0.115"><joint type="free"/><geom type="sphere" size="0.035" density="600" condim="3"/></body>
+</worldbody></mujoco>"""
