@@ -321,3 +321,29 @@ def test_emulated_kernel_matches_oracle_on_feature_models(name, qtol, vtol):
         worst_v = max(worst_v, float(np.abs(e.qvel[0] - d.qvel).max()))
         assert int(e.warn[0]) == 0
     assert worst_q < qtol and worst_v < vtol and same_ncon >= 18, (worst_q, worst_v, same_ncon)
+
+
+def test_emulated_kernel_matches_oracle_on_tendons_and_actuators():
+    from toy_models import MODELS
+
+    cm = mjcf.compile_mjcf(MODELS["tendons_actuators"])
+    blob, m = cm.blob(), cm.m
+    assert (m["ntendon"], m["nu"], m["nwrap"]) == (2, 4, 9)
+    om, d = oracle_pair(blob)
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    rng = np.random.RandomState(0)
+    for it in range(25):
+        d.ctrl[:] = rng.uniform(-1, 1, m["nu"])
+        for _ in range(15):
+            d.step()
+        d.forward()
+        e.qpos[0], e.qvel[0], e.ctrl[0], e.warm[0] = d.qpos, d.qvel, d.ctrl, d.qacc_warmstart
+        e.forward()
+        g = e.dbg_view()
+        assert np.abs(g["tlen"] - d.ten_length).max() < 2e-6 and np.abs(g["tJ"].ravel() - d.ten_J).max() < 2e-6
+        assert np.abs(g["aforce"] - d.actuator_force).max() < 1e-5 and np.abs(g["smooth"] - d.qfrc_smooth).max() < 2e-4
+        e.step(5, 1)
+        for _ in range(5):
+            d.step()
+        assert np.abs(e.qpos[0] - d.qpos).max() < 5e-6 and np.abs(e.qvel[0] - d.qvel).max() < 5e-4
+    assert int(e.warn[0]) == 0 and np.abs(d.qpos).max() > 0.3          # the arm really moved

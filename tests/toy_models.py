@@ -159,3 +159,32 @@ MODELS['contacts'] = """
  <body name="sp" pos="0.01 -0.3 0.04"><joint type="free"/><geom type="sphere" size="0.04" density="600" condim="3"/></body>
  <body name="sp2" pos="0.02 -0.29 0.115"><joint type="free"/><geom type="sphere" size="0.035" density="600" condim="3"/></body>
 </worldbody></mujoco>"""
+
+# tendons and actuators the dactyl models do not have: a spatial tendon over a wrapping sphere with a pulley, tendon spring /
+# damper / limits, a fixed tendon with limits, position / velocity / general actuators, a force-limited motor on a tendon
+MODELS["tendons_actuators"] = """
+<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/>
+<size nuserdata="0" njmax="100" nconmax="20"/>
+<worldbody>
+ <site name="anchor" pos="0 0 1.2"/>
+ <body name="l1" pos="0 0 1"><joint name="j1" type="hinge" axis="0 1 0" damping="0.05" armature="0.002" frictionloss="0.02" limited="true" range="-1.2 1.2"/>
+   <geom type="capsule" fromto="0 0 0 0.25 0 0" size="0.02" density="700" contype="0" conaffinity="0"/><site name="s1" pos="0.1 0 0.03"/>
+   <geom name="wrapsph" type="sphere" size="0.035" pos="0.25 0 0" contype="0" conaffinity="0" density="1"/><site name="side1" pos="0.25 0 0.08"/>
+  <body name="l2" pos="0.25 0 0"><joint name="j2" type="hinge" axis="0 1 0" damping="0.03" limited="true" range="-0.3 1.9"/>
+    <geom type="capsule" fromto="0 0 0 0.2 0 0" size="0.018" density="700" contype="0" conaffinity="0"/><site name="s2" pos="0.12 0 0.025"/>
+   <body name="l3" pos="0.2 0 0"><joint name="j3" type="hinge" axis="0 1 0" damping="0.02"/><joint name="j3s" type="slide" axis="1 0 0" damping="1.0" stiffness="50"/>
+     <geom type="box" size="0.05 0.02 0.02" pos="0.05 0 0" density="700" contype="0" conaffinity="0"/><site name="s3" pos="0.05 0 0.02"/></body>
+  </body>
+ </body>
+</worldbody>
+<tendon>
+ <fixed name="couple" limited="true" range="-0.5 0.8"><joint joint="j2" coef="1"/><joint joint="j3" coef="0.7"/></fixed>
+ <spatial name="flexor" stiffness="20" damping="0.5" limited="true" range="0 0.7"><site site="anchor"/><site site="s1"/><geom geom="wrapsph" sidesite="side1"/><site site="s2"/><pulley divisor="2"/><site site="s2"/><site site="s3"/></spatial>
+</tendon>
+<actuator>
+ <position name="p1" joint="j1" kp="8" ctrllimited="true" ctrlrange="-1 1"/>
+ <velocity name="v2" joint="j2" kv="0.5" ctrllimited="true" ctrlrange="-2 2"/>
+ <motor name="tm" tendon="flexor" gear="3" ctrllimited="true" ctrlrange="-1 1" forcelimited="true" forcerange="-2 2"/>
+ <general name="g3" joint="j3" gainprm="2 0 0" biasprm="0.1 -1.5 -0.05" ctrllimited="true" ctrlrange="-1 1"/>
+</actuator>
+</mujoco>"""
