@@ -347,3 +347,35 @@ def test_emulated_kernel_matches_oracle_on_tendons_and_actuators():
             d.step()
         assert np.abs(e.qpos[0] - d.qpos).max() < 5e-6 and np.abs(e.qvel[0] - d.qvel).max() < 5e-4
     assert int(e.warn[0]) == 0 and np.abs(d.qpos).max() > 0.3          # the arm really moved
+
+
+def test_free_floating_chain_conserves_linear_momentum():
+    """Internal motion of a floating free-root / ball / hinge chain cannot move its centre of mass: the COM velocity over
+    three consecutive windows is the same (oracle, 1e-4 relative), and the fp32 kernel logic follows the oracle."""
+    from toy_models import MODELS
+
+    cm = mjcf.compile_mjcf(MODELS["floating_chain"])
+    blob, m = cm.blob(), cm.m
+    mass = m["body_mass"]
+    com = lambda dd: (mass[:, None] * dd.xipos.reshape(-1, 3)).sum(0) / mass.sum()
+    om, d = oracle_pair(blob)
+    v0 = np.random.RandomState(1).uniform(-2, 2, m["nv"])
+    d.qvel[:] = v0
+    d.forward()
+    pts = [com(d)]
+    for n in (100, 100, 300):
+        for _ in range(n):
+            d.step()
+        d.forward()
+        pts.append(com(d))
+    v = [(pts[1] - pts[0]) / 0.1, (pts[2] - pts[1]) / 0.1, (pts[3] - pts[2]) / 0.3]
+    assert np.linalg.norm(v[0]) > 1.0
+    assert np.abs(v[1] - v[0]).max() < 1e-4 * np.linalg.norm(v[0]) and np.abs(v[2] - v[0]).max() < 1e-4 * np.linalg.norm(v[0])
+    om2, d2 = oracle_pair(blob)
+    d2.qvel[:] = v0
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0], e.qvel[0] = d2.qpos, d2.qvel
+    e.step(100, 1)
+    for _ in range(100):
+        d2.step()
+    assert np.abs(e.qpos[0] - d2.qpos).max() < 5e-6 and np.abs(e.qvel[0] - d2.qvel).max() < 1e-4

@@ -188,3 +188,18 @@ MODELS["tendons_actuators"] = """
  <general name="g3" joint="j3" gainprm="2 0 0" biasprm="0.1 -1.5 -0.05" ctrllimited="true" ctrlrange="-1 1"/>
 </actuator>
 </mujoco>"""
+
+# a free-floating articulated body (free root, ball shoulder, hinge elbow) in zero gravity: its centre of mass must move uniformly
+MODELS["floating_chain"] = """
+<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.001" gravity="0 0 0"/>
+<size nuserdata="0" njmax="50" nconmax="10"/>
+<worldbody>
+ <body name="base" pos="0 0 1"><joint name="root" type="free"/>
+   <geom type="box" size="0.08 0.05 0.03" density="900" contype="0" conaffinity="0"/>
+   <body name="arm" pos="0.08 0 0"><joint name="sh" type="ball"/>
+     <geom type="capsule" fromto="0 0 0 0.15 0 0" size="0.02" density="900" contype="0" conaffinity="0"/>
+     <body name="tip" pos="0.15 0 0"><joint name="el" type="hinge" axis="0 0 1"/>
+       <geom type="box" size="0.05 0.015 0.02" pos="0.05 0 0" density="900" contype="0" conaffinity="0"/></body>
+   </body>
+ </body>
+</worldbody></mujoco>"""
