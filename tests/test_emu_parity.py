@@ -83,3 +83,31 @@ def test_bad_state_resets_and_flags(locked_blob, setup):
     e.step(2, 0)
     assert e.warn[0] & 4
     assert np.isfinite(e.qpos).all() and np.isfinite(e.qvel).all()
+
+
+def test_external_force_and_per_env_timestep(locked_blob, locked_names, setup):
+    """data.xfrc_applied (RandomizedWindWrapper pushes the cube with it) and a per-environment opt.timestep
+    (RandomizedTimestepWrapper) -- kernel logic vs oracle, one env-step from identical states."""
+    m, dims, states, after, om = setup
+    cube = locked_names["body"].index("cube:middle")
+    st = states[3]
+    for xf, dt in (((0.3, -0.2, 0.5, 0.01, 0.0, -0.02), None), (None, 0.0065), ((0.0, 0.4, 0.0, 0.0, 0.03, 0.0), 0.0105)):
+        om2, d = oracle_pair(locked_blob)
+        d.qpos[:], d.qvel[:], d.ctrl[:] = st[0], st[1], st[2]
+        d.userdata[:60] = st[3]
+        d.qacc_warmstart[:] = st[4]
+        e = pyemu.EmuBatch(locked_blob, dims, 1)
+        load(e, 0, st)
+        if xf is not None:
+            d.xfrc_applied[6 * cube:6 * cube + 6] = xf
+            e.xfrc = np.zeros((1, dims["nbody"], 6), np.float32)
+            e.xfrc[0, cube] = xf
+        if dt is not None:
+            om2.field("opt_timestep")[0] = dt
+            e.timestep = np.full(1, dt, np.float32)
+        d.env_step(10)
+        e.step(10, 1)
+        iq, iv = live_indices(om, locked_names)
+        assert np.abs(e.qpos[0][iq] - d.qpos[iq]).max() < 2e-3 and np.abs(e.qvel[0][iv] - d.qvel[iv]).max() < 8e-2
+        # the push / the different step size must actually matter
+        assert np.abs(d.qpos[iq] - after[3][0][iq]).max() > 1e-4
