@@ -379,3 +379,24 @@ def test_free_floating_chain_conserves_linear_momentum():
     for _ in range(100):
         d2.step()
     assert np.abs(e.qpos[0] - d2.qpos).max() < 5e-6 and np.abs(e.qvel[0] - d2.qvel).max() < 1e-4
+
+
+def test_resting_box_shares_its_weight_between_four_corners():
+    """plane-box narrow phase (4 corner contacts) + the same closed form: each of the four condim-1 contacts carries
+    m g / 4, so the penetration solves k d(r) r = (g / 4) (1 - d) / d."""
+    from toy_models import RESTING_SPHERE
+
+    xml = RESTING_SPHERE.format(condim=1).replace('type="sphere" size="0.05"', 'type="box" size="0.05 0.04 0.05"')
+    cm = mjcf.compile_mjcf(xml)
+    blob = cm.blob()
+    want = 0.05 - _equilibrium_penetration(1, g=9.81 / 4.0)
+    om, d = oracle_pair(blob)
+    for _ in range(4000):
+        d.step()
+    assert d.ncon[0] == 4 and np.abs(d.qvel).max() < 1e-9
+    assert abs(d.qpos[2] - want) < 1e-8, (d.qpos[2], want)
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0] = cm.m["qpos0"]
+    e.step(4000, 1)
+    assert int(e.warn[0]) == 0 and int(e.ncon[0]) == 4
+    assert abs(float(e.qpos[0, 2]) - want) < 2e-6
