@@ -400,3 +400,19 @@ def test_resting_box_shares_its_weight_between_four_corners():
     e.step(4000, 1)
     assert int(e.warn[0]) == 0 and int(e.ncon[0]) == 4
     assert abs(float(e.qpos[0, 2]) - want) < 2e-6
+
+
+def test_joint_limit_holds_the_weight_at_the_closed_form_violation():
+    """Limit rows use the same soft law with A = dof_invweight0 = 1/m: the slider settles |r| below its lower limit."""
+    from toy_models import LIMITED_SLIDER
+
+    cm = mjcf.compile_mjcf(LIMITED_SLIDER)
+    blob = cm.blob()
+    want = -0.1 - _equilibrium_penetration(1)
+    om, d = oracle_pair(blob)
+    for _ in range(4000):
+        d.step()
+    assert abs(d.qvel[0]) < 1e-9 and abs(d.qpos[0] - want) < 1e-8, (d.qpos[0], want)
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
+    e.step(4000, 1)
+    assert int(e.warn[0]) == 0 and abs(float(e.qpos[0, 0]) - want) < 2e-6

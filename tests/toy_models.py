@@ -203,3 +203,18 @@ MODELS["floating_chain"] = """
    </body>
  </body>
 </worldbody></mujoco>"""
+
+# a 1.5 kg slider hanging on its lower joint limit under gravity
+LIMITED_SLIDER = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" iterations="50" tolerance="1e-12"/>
+  <size nuserdata="0" njmax="20" nconmax="5"/>
+  <worldbody>
+    <body name="w" pos="0 0 1">
+      <joint name="z" type="slide" axis="0 0 1" limited="true" range="-0.1 0.3"/>
+      <geom type="sphere" size="0.03" mass="1.5" contype="0" conaffinity="0"/>
+    </body>
+  </worldbody>
+</mujoco>
+"""
