@@ -104,6 +104,22 @@ class DeviceModel:
             self.h = None
 
 
+def world_shift_rows(t, v, name, m, origin):
+    """Subtract the engine's world origin, in place, from the rows of a per-environment body_pos / geom_pos / site_pos
+    tensor `v` ([nenv, 3 * count], any device) that live in world coordinates: bodies whose parent is the world, geoms
+    and sites attached to the world body itself."""
+    if name == "body_pos":
+        sel = np.asarray(m["body_parentid"]) == 0
+        sel[0] = False
+    else:
+        sel = np.asarray(m["geom_bodyid" if name == "geom_pos" else "site_bodyid"]) == 0
+    idx = t.as_tensor(np.nonzero(sel)[0], dtype=t.long, device=v.device)
+    if idx.numel():
+        rows = v.view(v.shape[0], -1, 3)
+        rows[:, idx] -= t.tensor(list(origin), dtype=v.dtype, device=v.device)
+    return v
+
+
 class BatchedSim:
     """nenv independent copies of one model, stepped by one fused kernel launch per env-step."""
 
@@ -173,13 +189,7 @@ class BatchedSim:
             # keep the engine's fp32 world shift: bodies attached to the world, and geoms / sites attached to the world body
             o = (ctypes.c_float * 3)()
             _check(lib().rg_model_origin(self.model.h, o))
-            rows = v.reshape(self.nenv, -1, 3)
-            if name == "body_pos":
-                sel = t.as_tensor(np.asarray(m["body_parentid"]) == 0)
-                sel[0] = False
-            else:
-                sel = t.as_tensor(np.asarray(m["geom_bodyid" if name == "geom_pos" else "site_bodyid"]) == 0)
-            rows[:, sel] -= t.tensor(list(o), dtype=t.float64)
+            world_shift_rows(t, v, name, m, list(o))
         dev = v.to(device=self.device, dtype=t.float32).contiguous()
         if not hasattr(self, "_params"):
             self._params = {}

@@ -56,3 +56,22 @@ def test_scratch_budget_keeps_ten_environments_per_sm(locked_blob):
     small = pyemu.lib().rge_small_bytes(e.h)
     fixed = 640 + ((small + 127) & ~127) + 64 + 1152           # model view (576 B today) + staged arrays + slack + static shared
     assert (232448 - fixed) // scratch >= 10, (scratch, small)
+
+
+def test_world_shift_of_per_environment_rows():
+    """BatchedSim.set_param keeps the engine's fp32 world shift for rows that live in world coordinates (host-side helper,
+    device-agnostic: the index and the origin are created on the rows' device)."""
+    import numpy as np
+    import torch
+
+    from robogym_b200.engine import world_shift_rows
+
+    m = dict(body_parentid=np.array([0, 0, 1, 0]), geom_bodyid=np.array([0, 1, 2]), site_bodyid=np.array([1, 1]))
+    v = torch.zeros(2, 12, dtype=torch.float64)
+    world_shift_rows(torch, v, "body_pos", m, [1.0, 2.0, 3.0])
+    assert v[1].view(4, 3).tolist() == [[0, 0, 0], [-1, -2, -3], [0, 0, 0], [-1, -2, -3]]      # world body itself stays
+    v = torch.ones(2, 9, dtype=torch.float32)
+    world_shift_rows(torch, v, "geom_pos", m, [1.0, 2.0, 3.0])
+    assert v[0].view(3, 3).tolist() == [[0, -1, -2], [1, 1, 1], [1, 1, 1]]
+    v = torch.ones(2, 6)
+    assert torch.equal(world_shift_rows(torch, v, "site_pos", m, [1.0, 2.0, 3.0]), torch.ones(2, 6))   # nothing on the world body
