@@ -416,3 +416,36 @@ def test_joint_limit_holds_the_weight_at_the_closed_form_violation():
     e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
     e.step(4000, 1)
     assert int(e.warn[0]) == 0 and abs(float(e.qpos[0, 0]) - want) < 2e-6
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_kinematic_trees(seed):
+    """Fuzz: random trees (branching, one or two joints per body of every type incl. free roots, random primitive geoms in
+    rotated frames, springs, limits, dry friction, armature, position / motor actuators) -- the kernel logic reproduces
+    the oracle's mass matrix, bias forces and 5-substep state to fp32 round-off on every one."""
+    from toy_models import random_tree_xml
+
+    rng = np.random.RandomState(seed)
+    cm = mjcf.compile_mjcf(random_tree_xml(rng, nbody=int(rng.randint(4, 10))))
+    blob, m = cm.blob(), cm.m
+    om, d = oracle_pair(blob)
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    d.qvel[:] = rng.uniform(-1, 1, m["nv"])
+    for it in range(5):
+        if m["nu"]:
+            d.ctrl[:] = rng.uniform(-1, 1, m["nu"])
+        for _ in range(20):
+            d.step()
+        d.forward()
+        e.qpos[0], e.qvel[0], e.warm[0] = d.qpos, d.qvel, d.qacc_warmstart
+        if m["nu"]:
+            e.ctrl[0] = d.ctrl
+        e.forward()
+        g = e.dbg_view()
+        assert np.abs(g["M"].ravel() - d.M).max() < 2e-6 * np.abs(d.M).max()
+        assert np.abs(g["bias"] - d.qfrc_bias).max() < 2e-5 * max(1e-6, np.abs(d.qfrc_bias).max())
+        e.step(5, 1)
+        for _ in range(5):
+            d.step()
+        assert np.abs(e.qpos[0] - d.qpos).max() < 5e-6 and np.abs(e.qvel[0] - d.qvel).max() < 2e-4
+    assert int(e.warn[0]) == 0

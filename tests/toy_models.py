@@ -218,3 +218,42 @@ LIMITED_SLIDER = """
   </worldbody>
 </mujoco>
 """
+
+
+import numpy as np  # noqa: E402
+
+
+def random_tree_xml(rng, nbody=8):
+    """random kinematic tree: every body hangs on 1-2 joints of random type, random primitive, random spring/damping/limits"""
+    bodies = {0: []}
+    parent = {}
+    for b in range(1, nbody + 1):
+        p = int(rng.randint(0, b)); parent[b] = p; bodies.setdefault(p, []).append(b); bodies.setdefault(b, [])
+    jn = [0]
+    acts = []
+    def body_xml(b, depth):
+        pos = rng.uniform(-0.15, 0.15, 3); pos[2] = abs(pos[2]) + (1.0 if parent[b] == 0 else 0.05)
+        s = '%s<body name="b%d" pos="%.4f %.4f %.4f">\n' % ('  ' * depth, b, *pos)
+        kinds = rng.choice(['hinge', 'slide', 'ball', 'hinge+slide', 'hinge+hinge', 'free'] if parent[b] == 0 else ['hinge', 'slide', 'ball', 'hinge+slide', 'hinge+hinge'])
+        for k in kinds.split('+'):
+            jn[0] += 1
+            name = 'j%d' % jn[0]
+            ax = rng.randn(3); ax /= np.linalg.norm(ax)
+            extra = ''
+            if k in ('hinge', 'slide'):
+                extra = ' axis="%.4f %.4f %.4f" damping="%.3f" armature="%.4f"' % (*ax, rng.uniform(0.01, 0.2), rng.uniform(0, 0.01))
+                if rng.rand() < 0.4: extra += ' stiffness="%.3f" springref="%.3f"' % (rng.uniform(0.5, 5), rng.uniform(-0.2, 0.2))
+                if rng.rand() < 0.4: extra += ' limited="true" range="%.3f %.3f"' % ((-0.3, 0.4) if k == 'hinge' else (-0.03, 0.05))
+                if rng.rand() < 0.3: extra += ' frictionloss="%.3f"' % rng.uniform(0.005, 0.05)
+                if rng.rand() < 0.5: acts.append('<%s joint="%s" %s ctrllimited="true" ctrlrange="-1 1"/>' % (('position', name, 'kp="%.2f"' % rng.uniform(1, 5)) if rng.rand() < 0.5 else ('motor', name, 'gear="%.2f"' % rng.uniform(0.2, 1))))
+            elif k == 'ball':
+                extra = ' damping="%.3f"' % rng.uniform(0.01, 0.1)
+            s += '%s  <joint name="%s" type="%s" pos="%.3f %.3f %.3f"%s/>\n' % ('  ' * depth, name, k, *(rng.uniform(-0.02, 0.02, 3) if k != 'free' else (0, 0, 0)), extra)
+        g = rng.choice(['box', 'capsule', 'sphere', 'ellipsoid', 'cylinder'])
+        size = {'box': '%.3f %.3f %.3f' % tuple(rng.uniform(0.02, 0.06, 3)), 'capsule': '%.3f %.3f' % tuple(rng.uniform(0.015, 0.05, 2)),
+                'sphere': '%.3f' % rng.uniform(0.02, 0.05), 'ellipsoid': '%.3f %.3f %.3f' % tuple(rng.uniform(0.02, 0.06, 3)), 'cylinder': '%.3f %.3f' % tuple(rng.uniform(0.015, 0.05, 2))}[g]
+        s += '%s  <geom type="%s" size="%s" pos="%.3f %.3f %.3f" euler="%.2f %.2f %.2f" density="%.0f" contype="0" conaffinity="0"/>\n' % ('  ' * depth, g, size, *rng.uniform(-0.03, 0.03, 3), *rng.uniform(-1, 1, 3), rng.uniform(300, 1500))
+        for c in bodies[b]: s += body_xml(c, depth + 1)
+        return s + '%s</body>\n' % ('  ' * depth)
+    wb = ''.join(body_xml(c, 2) for c in bodies[0])
+    return '<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="200" nconmax="10"/>\n<worldbody>\n%s</worldbody>\n<actuator>%s</actuator></mujoco>' % (wb, ''.join(acts))
