@@ -257,3 +257,14 @@ def random_tree_xml(rng, nbody=8):
         return s + '%s</body>\n' % ('  ' * depth)
     wb = ''.join(body_xml(c, 2) for c in bodies[0])
     return '<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="200" nconmax="10"/>\n<worldbody>\n%s</worldbody>\n<actuator>%s</actuator></mujoco>' % (wb, ''.join(acts))
+
+
+def pile_xml(rng, n=6):
+    s=''
+    for b in range(n):
+        g = rng.choice(['box','capsule','sphere','ellipsoid','cylinder'])
+        size = {'box': '%.3f %.3f %.3f' % tuple(rng.uniform(0.03, 0.06, 3)), 'capsule': '%.3f %.3f' % tuple(rng.uniform(0.02, 0.05, 2)),
+                'sphere': '%.3f' % rng.uniform(0.03, 0.05), 'ellipsoid': '%.3f %.3f %.3f' % tuple(rng.uniform(0.03, 0.06, 3)), 'cylinder': '%.3f %.3f' % tuple(rng.uniform(0.02, 0.05, 2))}[g]
+        pos = (rng.uniform(-0.06,0.06), rng.uniform(-0.06,0.06), 0.08+0.11*b)
+        s += '<body name="o%d" pos="%.3f %.3f %.3f" euler="%.2f %.2f %.2f"><joint type="free"/><geom type="%s" size="%s" density="%.0f" condim="%d" friction="%.2f 0.005 0.0001"/></body>\n' % (b, *pos, *rng.uniform(-1.5,1.5,3), g, size, rng.uniform(400,1200), int(rng.choice([1,3,4,6])), rng.uniform(0.3,1.0))
+    return '<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="400" nconmax="60"/><worldbody><body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>\n%s</worldbody></mujoco>' % s
