@@ -511,3 +511,33 @@ def test_random_conservative_trees_conserve_energy(seed):
     e1, k1 = energy()
     assert abs(k1 - k0) > 0.05 * max(k0, k1)                    # energy really moved between the two forms
     assert abs(e1 - e0) < 5e-3 * max(k0, k1)
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_random_convex_hull_piles(seed):
+    """Fuzz of the hull path: random lumpy point clouds (12-120 points) compiled to convex hulls, dropped on a box and a
+    plane.  The kernel's hill climb on the hull edge graph must find the same support points as the oracle's exhaustive
+    search: same contact counts, round-off agreement once resting, compiled mass properties shared by both."""
+    from toy_models import mesh_pile
+
+    rng = np.random.RandomState(seed)
+    xml, clouds = mesh_pile(rng)
+    cm = mjcf.compile_mjcf(xml, asset_loader=lambda p: clouds[p.split("/")[-1]])
+    blob, m = cm.blob(), cm.m
+    assert m["nmesh"] == 5 and (m["mesh_vertnum"] >= 4).all()
+    om, d = oracle_pair(blob)
+    e = pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    errs, same = [], 0
+    for it in range(25):
+        for _ in range(20):
+            d.step()
+        d.forward()
+        e.qpos[0], e.qvel[0], e.warm[0] = d.qpos, d.qvel, d.qacc_warmstart
+        e.step(5, 1)
+        for _ in range(5):
+            d.step()
+        d.forward()
+        same += int(e.ncon[0]) == int(d.ncon[0])
+        errs.append(float(np.abs(e.qpos[0] - d.qpos).max()))
+    assert int(e.warn[0]) == 0 and same >= 23
+    assert np.median(errs) < 2e-6 and max(errs) < 5e-3 and np.median(errs[-8:]) < 1e-6, errs

@@ -268,3 +268,18 @@ def pile_xml(rng, n=6):
         pos = (rng.uniform(-0.06,0.06), rng.uniform(-0.06,0.06), 0.08+0.11*b)
         s += '<body name="o%d" pos="%.3f %.3f %.3f" euler="%.2f %.2f %.2f"><joint type="free"/><geom type="%s" size="%s" density="%.0f" condim="%d" friction="%.2f 0.005 0.0001"/></body>\n' % (b, *pos, *rng.uniform(-1.5,1.5,3), g, size, rng.uniform(400,1200), int(rng.choice([1,3,4,6])), rng.uniform(0.3,1.0))
     return '<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="400" nconmax="60"/><worldbody><body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>\n%s</worldbody></mujoco>' % s
+
+
+def mesh_pile(rng, n=5):
+    clouds={}
+    assets=''; bodies=''
+    for b in range(n):
+        npts=int(rng.randint(12,120))
+        pts=rng.randn(npts,3); pts/=np.linalg.norm(pts,axis=1,keepdims=True)
+        pts*=rng.uniform(0.03,0.06,3)*rng.uniform(0.7,1.0,(npts,1))     # lumpy ellipsoid-ish hull
+        clouds['m%d.stl'%b]=pts
+        assets+='<mesh name="m%d" file="m%d.stl"/>'%(b,b)
+        pos=(rng.uniform(-0.05,0.05), rng.uniform(-0.05,0.05), 0.08+0.12*b)
+        bodies+='<body name="o%d" pos="%.3f %.3f %.3f" euler="%.2f %.2f %.2f"><joint type="free"/><geom type="mesh" mesh="m%d" density="%.0f" condim="%d"/></body>\n'%(b,*pos,*rng.uniform(-1.5,1.5,3),b,rng.uniform(400,1200),int(rng.choice([1,3,4])))
+    xml='<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="400" nconmax="60"/><asset>%s</asset><worldbody><body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>\n%s<body name="blk" pos="0 0 0.03"><geom type="box" size="0.08 0.08 0.03" condim="3"/></body></worldbody></mujoco>'%(assets,bodies)
+    return xml, clouds
