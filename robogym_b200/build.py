@@ -17,11 +17,27 @@ def nvcc_cmd(extra=()):
             "-Xcompiler", "-fPIC", "-shared", *extra, "-o", OUT, os.path.join(SRC, "rg_engine.cu")]
 
 
+def _fresh():
+    return os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS)
+
+
 def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
+    if not force and _fresh():
         return OUT
-    cmd = nvcc_cmd(("-Xptxas", "-v") if verbose else ())
-    subprocess.check_call(cmd)
+    # several ranks of one job may get here together (torchrun): one compiles, the others wait and then find it fresh
+    import fcntl
+
+    with open(OUT + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or not _fresh():
+                cmd = nvcc_cmd(("-Xptxas", "-v") if verbose else ())
+                tmp = OUT + ".tmp.%d" % os.getpid()
+                cmd[cmd.index("-o") + 1] = tmp
+                subprocess.check_call(cmd)
+                os.replace(tmp, OUT)          # readers never see a half-written library
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 
