@@ -41,10 +41,11 @@ def build(force=False, verbose=False):
     return OUT
 
 
-def build_profile():
-    """Same engine with per-stage clock64 counters in the RG_DBG dump (profiling only)."""
-    out = os.path.join(HERE, "librobogym_b200_prof.so")
-    cmd = nvcc_cmd(("-DRG_PROFILE",))
+def build_profile(level=1):
+    """Same engine with per-stage clock64 counters in the RG_DBG dump (profiling only); level 2 breaks the Newton solve
+    down instead of the collision stage."""
+    out = os.path.join(HERE, "librobogym_b200_prof%s.so" % ("" if level == 1 else str(level)))
+    cmd = nvcc_cmd(("-DRG_PROFILE=%d" % level,))
     cmd[cmd.index("-o") + 1] = out
     subprocess.check_call(cmd)
     return out
@@ -66,6 +67,7 @@ if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     if "--profile" in sys.argv:
         print(build_profile())
+        print(build_profile(2))
     for a in sys.argv[1:]:
         if a.startswith("--variant="):   # --variant=skew1:RG_SKEW=1
             tag, _, defs = a[len("--variant="):].partition(":")

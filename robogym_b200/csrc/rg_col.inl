@@ -10,16 +10,18 @@
 #include "rg_dyn.inl"
 
 #if defined(RG_EMU) && defined(RG_STATS)
+#include <stdio.h>
+#include <stdlib.h>
 static long long rg_stat_hist[2][64] = {{0}}; static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_stat_mpr_hit = 0, rg_stat_narrow = 0, rg_stat_maxsup = 0, rg_stat_cur = 0;
+/* solver / pipeline counters: forwards, newton iterations, refactorisations, line-search evaluations, triangular solves, broad-phase survivors, obb survivors, contacts, rows, mpr iterations */
+static long long rg_stat_x[16] = {0};
 #define RG_STAT(x) x
 #else
 #define RG_STAT(x)
 #endif
 struct RgGeomView {
   float pos[3], mat[9], size[3];
-  int type, vadr, vnum, mid;
-  int hint;              /* adjacency range of the last support vertex (hill-climb warm start), -1 = pick an extreme vertex */
-  float hv[3];           /* ... and its local coordinates */
+  int type, vadr, vnum;
   float halfmargin;
 };
 
@@ -33,11 +35,9 @@ RG_DEV void rg_geom_view(const RgCtx c, int g, float margin, RgGeomView& v) {
   rg_copy3(v.pos, RG_SCRATCH(c) + RG_CL(c).gxpos + 3 * g);
   rg_copy3(v.size, m.geom_size + 3 * g);
   v.type = m.geom_type[g];
-  v.hint = -1;
-  v.hv[0] = v.hv[1] = v.hv[2] = 0.0f;
   v.halfmargin = 0.5f * margin;
-  v.vadr = 0; v.vnum = 0; v.mid = 0;
-  if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.mid = mid; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
+  v.vadr = 0; v.vnum = 0;
+  if (v.type == RG_GEOM_MESH) { const int mid = m.geom_dataid[g]; v.vadr = m.mesh_vertadr[mid]; v.vnum = m.mesh_vertnum[mid]; }
 }
 
 /* support point of a primitive in its own frame */
@@ -68,113 +68,43 @@ RG_DEV void rg_support_prim(const RgGeomView& v, const float* dl, float* loc) {
   }
 }
 
-/* ---- hull support mapping: steepest-ascent hill climb on the convex hull's edge graph.  A vertex is known by its
- * adjacency range (first entry | degree << 20) in mesh_nbr; every entry carries the neighbour's coordinates AND the
- * neighbour's own range, so one climb step is ONE level of dependent loads, and the RG_CLIMB_W entries of a step are
- * fetched together (independent loads in flight) before any of them is compared. */
-#define RG_CLIMB_W 6
-struct RgClimb { int pk; float b[3], best; };
-
-RG_DEV void rg_climb_init(const RG_MODEL_T& m, const RgGeomView& v, const float* dl, RgClimb& st) {
-  if (v.hint >= 0) { st.pk = v.hint; rg_copy3(st.b, v.hv); }
-  else {
-    const float ax = fabsf(dl[0]), ay = fabsf(dl[1]), az = fabsf(dl[2]);
-    const int axis = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
-    float n4[4];
-    RG_LDG4(m.mesh_ext, 6 * v.mid + 2 * axis + (dl[axis] >= 0 ? 0 : 1), n4);
-    rg_copy3(st.b, n4); st.pk = rg_f2i(n4[3]);
-  }
-  st.best = st.b[0] * dl[0] + st.b[1] * dl[1] + st.b[2] * dl[2];
-}
-/* entries [base, base + RG_CLIMB_W) of the current vertex (clamped to its last entry: a repeated entry never wins the
-   strict comparison twice, so the visiting order -- and with it every tie-break -- is that of a plain loop) */
-RG_DEV void rg_climb_load(const RG_MODEL_T& m, int pk, int base, float n[RG_CLIMB_W][4]) {
-  const int a0 = pk & 0xFFFFF, last = (int)((unsigned)pk >> 20) - 1;
-#pragma unroll
-  for (int i = 0; i < RG_CLIMB_W; i++) { const int k = base + i < last ? base + i : last; RG_LDG4(m.mesh_nbr, a0 + k, n[i]); }
-}
-RG_DEV void rg_climb_eval(const float n[RG_CLIMB_W][4], const float* dl, RgClimb& st, int& nxt) {
-#pragma unroll
-  for (int i = 0; i < RG_CLIMB_W; i++) {
-    const float dd = n[i][0] * dl[0] + n[i][1] * dl[1] + n[i][2] * dl[2];
-    if (dd > st.best) { st.best = dd; nxt = rg_f2i(n[i][3]); st.b[0] = n[i][0]; st.b[1] = n[i][1]; st.b[2] = n[i][2]; }
+/* ---- hull support mapping: exhaustive scan of the hull's vertices (16-byte loads, no dependent chain).  In the
+ * convex-convex narrow phase the scan of one hull is shared by the RG_GRP lanes that work on the pair: lane `gl` looks
+ * at vertices gl, gl + RG_GRP, ... and the group's arg-max picks the winner (ties: the lower vertex id, which is what a
+ * plain first-maximum loop returns). */
+#define RG_GRP 8
+RG_DEV void rg_hull_scan(const RG_MODEL_T& m, const RgGeomView& v, const float* dl, int first, int stride, float& best, int& idx) {
+  best = -3.0e38f; idx = 0x7fffffff;
+  RG_STAT(rg_stat_climb += (v.vnum - first + stride - 1) / stride;)
+  RG_UNROLL4 for (int k = first; k < v.vnum; k += stride) {
+    float p[4];
+    RG_LDG4(m.mesh_vert4, v.vadr + k, p);
+    const float d = p[0] * dl[0] + p[1] * dl[1] + p[2] * dl[2];
+    if (d > best) { best = d; idx = k; }
   }
 }
-/* one step; returns 1 when the climb moved to a better neighbour */
-RG_DEV int rg_climb_step(const RG_MODEL_T& m, const float* dl, RgClimb& st) {
-  const int deg = (int)((unsigned)st.pk >> 20);
-  int nxt = st.pk;
-  for (int base = 0; base < deg; base += RG_CLIMB_W) {
-    float n[RG_CLIMB_W][4];
-    rg_climb_load(m, st.pk, base, n);
-    rg_climb_eval(n, dl, st, nxt);
-  }
-  const int moved = nxt != st.pk;
-  st.pk = nxt;
-  RG_STAT(rg_stat_climb += moved;)
-  return moved;
-}
-
 RG_DEV void rg_support_world(const RgGeomView& v, const float* loc, const float* dir, float* res) {
   rg_mulmat3(res, v.mat, loc);
   res[0] += v.pos[0] + dir[0] * v.halfmargin;
   res[1] += v.pos[1] + dir[1] * v.halfmargin;
   res[2] += v.pos[2] + dir[2] * v.halfmargin;
 }
-
-RG_DEV void rg_support(const RG_MODEL_T& m, RgGeomView& v, const float* dir, float* res) {
+/* one lane, whole hull (plane-convex pairs only: rare and cheap enough) */
+RG_DEV void rg_support(const RG_MODEL_T& m, const RgGeomView& v, const float* dir, float* res) {
   float dl[3], loc[3];
   RG_STAT(rg_stat_support++; rg_stat_cur++;)
   rg_mulmatT3(dl, v.mat, dir);
   if (v.type == RG_GEOM_MESH) {
-    RgClimb st;
-    rg_climb_init(m, v, dl, st);
-    for (int guard = 0; guard < v.vnum; guard++) if (!rg_climb_step(m, dl, st)) break;
-    v.hint = st.pk; rg_copy3(v.hv, st.b);
-    rg_copy3(loc, st.b);
+    float best; int idx;
+    rg_hull_scan(m, v, dl, 0, 1, best, idx);
+    float p[4];
+    RG_LDG4(m.mesh_vert4, v.vadr + idx, p);
+    rg_copy3(loc, p);
   } else rg_support_prim(v, dl, loc);
   rg_support_world(v, loc, dir, res);
 }
 
 struct RgSup { float v[3], v1[3], v2[3]; };
-
-/* support of the Minkowski difference o1 - o2.  For two hulls the two climbs advance together, so that the loads of
-   both are in flight at the same time (the narrow phase is a chain of dependent L2 round trips, not arithmetic). */
-RG_DEV void rg_mpr_support(const RG_MODEL_T& m, RgGeomView& o1, RgGeomView& o2, const float* dir, RgSup& sp) {
-  const float nd[3] = {-dir[0], -dir[1], -dir[2]};
-  if (o1.type == RG_GEOM_MESH && o2.type == RG_GEOM_MESH) {
-    float d1[3], d2[3];
-    RG_STAT(rg_stat_support += 2; rg_stat_cur += 2;)
-    rg_mulmatT3(d1, o1.mat, dir);
-    rg_mulmatT3(d2, o2.mat, nd);
-    RgClimb s1, s2;
-    rg_climb_init(m, o1, d1, s1);
-    rg_climb_init(m, o2, d2, s2);
-    int go1 = 1, go2 = 1;
-    for (int guard = 0; guard < o1.vnum + o2.vnum && (go1 | go2); guard++) {
-      const int deg1 = go1 ? (int)((unsigned)s1.pk >> 20) : 0, deg2 = go2 ? (int)((unsigned)s2.pk >> 20) : 0;
-      int n1 = s1.pk, n2 = s2.pk;
-      for (int base = 0; base < deg1 || base < deg2; base += RG_CLIMB_W) {
-        float e1[RG_CLIMB_W][4], e2[RG_CLIMB_W][4];
-        if (base < deg1) rg_climb_load(m, s1.pk, base, e1);
-        if (base < deg2) rg_climb_load(m, s2.pk, base, e2);
-        if (base < deg1) rg_climb_eval(e1, d1, s1, n1);
-        if (base < deg2) rg_climb_eval(e2, d2, s2, n2);
-      }
-      go1 = go1 && n1 != s1.pk; go2 = go2 && n2 != s2.pk;
-      RG_STAT(rg_stat_climb += go1 + go2;)
-      s1.pk = n1; s2.pk = n2;
-    }
-    o1.hint = s1.pk; rg_copy3(o1.hv, s1.b);
-    o2.hint = s2.pk; rg_copy3(o2.hv, s2.b);
-    rg_support_world(o1, s1.b, dir, sp.v1);
-    rg_support_world(o2, s2.b, nd, sp.v2);
-  } else {
-    rg_support(m, o1, dir, sp.v1);
-    rg_support(m, o2, nd, sp.v2);
-  }
-  rg_sub3(sp.v, sp.v1, sp.v2);
-}
 RG_DEV int rg_mpr_zero(float x) { return fabsf(x) < RG_EPS; }
 /* ---- Minkowski Portal Refinement (XenoCollide), written as ONE loop around the support call:
  * the portal lives in named registers (no indexed local arrays) and lanes that are in different
@@ -244,98 +174,102 @@ RG_DEV void rg_find_pos3(const float* v0, const float* c1, const float* c2, cons
     pos[i] = inv * (b[0] * (c1[i] + c2[i]) + b[1] * (p1.v1[i] + p1.v2[i]) + b[2] * (p2.v1[i] + p2.v2[i]) + b[3] * (p3.v1[i] + p3.v2[i]));
 }
 
-/* depth >= 0 with dir,pos when the inflated geoms intersect; -1 otherwise */
-/* The geom views are built HERE (not handed in by reference): a reference into the caller's frame would pin them in
-   local memory, and with ~28 KB of L1 beside the shared-memory scratch every access to them is an L2 round trip. */
-struct RgMprOut { float depth, dir[3], pos[3]; };
-RG_DEV_NOINLINE RgMprOut rg_mpr(const RgCtx c, int g1, int g2, float margin) {
-  const RG_MODEL_T& m = RG_MDEREF(c.mref);
-  const float tol = m.opt_mpr_tolerance[0];
-  const int maxiter = m.opt_mpr_iterations[0];
+/* ---- MPR as a resumable state machine.  The support evaluation sits OUTSIDE: the narrow phase runs RG_GRP lanes per
+ * pair, scans both hulls cooperatively, then every lane of the group advances its (identical) copy of this state with
+ * the new support point.  The sequence of operations per pair is the textbook one (discover portal -> refine until the
+ * origin is inside -> push the portal to the surface), identical to the oracle's three-loop formulation. */
+enum { RG_MPR_V1 = 0, RG_MPR_V2 = 1, RG_MPR_V3 = 2, RG_MPR_REFINE = 3, RG_MPR_PENETR = 4, RG_MPR_PRE = 5 /* trying the cached separating axis */, RG_MPR_DONE = 6, RG_MPR_IDLE = 7, RG_MPR_FINISHED = 8 };
+struct RgMpr {
   RgGeomView o1, o2;
-  rg_geom_view(c, g1, margin, o1);
-  rg_geom_view(c, g2, margin, o2);
-  RgMprOut out;
-  float* dir_out = out.dir; float* pos = out.pos;
-  dir_out[0] = dir_out[1] = dir_out[2] = 0.0f; pos[0] = pos[1] = pos[2] = 0.0f;
-  enum { S_V1 = 0, S_V2 = 1, S_V3 = 2, S_REFINE = 3, S_PENETR = 4, S_DONE = 5 };
-  RgSup P1, P2, P3, sp;
-  float v0[3], dir[3], va[3], vb[3];
-  float result = -1.0f;
-  rg_sub3(v0, o1.pos, o2.pos);
-  if (rg_mpr_zero(v0[0]) && rg_mpr_zero(v0[1]) && rg_mpr_zero(v0[2])) v0[0] = 1e-5f;
-  rg_scl3(dir, v0, -1.0f); rg_normalize3(dir);
-  int state = S_V1, pen_it = 0;
-  P1 = RgSup(); P2 = RgSup(); P3 = RgSup();
-  int it = 0;
-  for (; it < 200 + maxiter && state != S_DONE; it++) {
-    rg_mpr_support(m, o1, o2, dir, sp);
-    const float dot = rg_dot3(sp.v, dir);
-    if (state == S_V1) {
-      P1 = sp;
-      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
-      rg_cross(dir, v0, P1.v);
-      /* fp32: the parallel test must be scale-free (libccd compares the raw squared norm with DBL_EPSILON) */
-      if (rg_dot3(dir, dir) <= 1e-12f * rg_dot3(v0, v0) * rg_dot3(P1.v, P1.v)) {
-        const float n = sqrtf(rg_dot3(P1.v, P1.v));
-        for (int i = 0; i < 3; i++) pos[i] = 0.5f * (P1.v1[i] + P1.v2[i]);
-        if (n < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; result = 0.0f; }
-        else { rg_scl3(dir_out, P1.v, 1.0f / n); result = n; }
-        state = S_DONE;
-        continue;
-      }
-      rg_normalize3(dir);
-      state = S_V2;
-    } else if (state == S_V2) {
-      P2 = sp;
-      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
+  RgSup P1, P2, P3;
+  float v0[3], dir[3];
+  float depth, odir[3], opos[3];   /* result: depth >= 0 with direction and position when the inflated geoms intersect, -1 otherwise */
+  int state, pen_it, it, slot, pair;
+  float lastdot;                   /* support . dir of the last iteration (< 0: dir separates the geoms) */
+};
+RG_DEV void rg_mpr_begin(RgMpr& S) {
+  rg_sub3(S.v0, S.o1.pos, S.o2.pos);
+  if (rg_mpr_zero(S.v0[0]) && rg_mpr_zero(S.v0[1]) && rg_mpr_zero(S.v0[2])) S.v0[0] = 1e-5f;
+  rg_scl3(S.dir, S.v0, -1.0f); rg_normalize3(S.dir);
+  S.state = RG_MPR_V1; S.pen_it = 0; S.it = 0;
+  S.depth = -1.0f;
+  S.odir[0] = S.odir[1] = S.odir[2] = 0.0f; S.opos[0] = S.opos[1] = S.opos[2] = 0.0f;
+}
+/* consume the support point `sp` of the Minkowski difference in direction S.dir; leaves the next direction in S.dir */
+RG_DEV void rg_mpr_advance(RgMpr& S, const RgSup& sp, float tol, int maxiter) {
+  float va[3], vb[3];
+  RgSup& P1 = S.P1; RgSup& P2 = S.P2; RgSup& P3 = S.P3;
+  float* dir = S.dir; const float* v0 = S.v0;
+  const float dot = rg_dot3(sp.v, dir);
+  S.it++;
+  S.lastdot = dot;
+  if (S.state == RG_MPR_PRE) {
+    if (dot < 0 && !rg_mpr_zero(dot)) { S.state = RG_MPR_DONE; return; }   /* still separated along last time's axis */
+    rg_mpr_begin(S);
+    return;
+  }
+  if (S.state == RG_MPR_V1) {
+    P1 = sp;
+    if (dot < 0 || rg_mpr_zero(dot)) { S.state = RG_MPR_DONE; return; }
+    rg_cross(dir, v0, P1.v);
+    /* fp32: the parallel test must be scale-free (libccd compares the raw squared norm with DBL_EPSILON) */
+    if (rg_dot3(dir, dir) <= 1e-12f * rg_dot3(v0, v0) * rg_dot3(P1.v, P1.v)) {
+      const float n = sqrtf(rg_dot3(P1.v, P1.v));
+      for (int i = 0; i < 3; i++) S.opos[i] = 0.5f * (P1.v1[i] + P1.v2[i]);
+      if (n < RG_EPS) { S.odir[0] = S.odir[1] = S.odir[2] = 0; S.depth = 0.0f; }
+      else { rg_scl3(S.odir, P1.v, 1.0f / n); S.depth = n; }
+      S.state = RG_MPR_DONE;
+      return;
+    }
+    rg_normalize3(dir);
+    S.state = RG_MPR_V2;
+  } else if (S.state == RG_MPR_V2) {
+    P2 = sp;
+    if (dot < 0 || rg_mpr_zero(dot)) { S.state = RG_MPR_DONE; return; }
+    rg_sub3(va, P1.v, v0); rg_sub3(vb, P2.v, v0);
+    rg_cross(dir, va, vb); rg_normalize3(dir);
+    if (rg_dot3(dir, v0) > 0) { const RgSup t = P1; P1 = P2; P2 = t; rg_scl3(dir, dir, -1.0f); }
+    S.state = RG_MPR_V3;
+  } else if (S.state == RG_MPR_V3) {
+    P3 = sp;
+    if (dot < 0 || rg_mpr_zero(dot)) { S.state = RG_MPR_DONE; return; }
+    int cont = 0;
+    rg_cross(va, P1.v, P3.v);
+    if (rg_dot3(va, v0) < 0) { P2 = P3; cont = 1; }     /* triple products are ~1e-6: sign only */
+    if (!cont) {
+      rg_cross(va, P3.v, P2.v);
+      if (rg_dot3(va, v0) < 0) { P1 = P3; cont = 1; }
+    }
+    if (cont) {
       rg_sub3(va, P1.v, v0); rg_sub3(vb, P2.v, v0);
       rg_cross(dir, va, vb); rg_normalize3(dir);
-      if (rg_dot3(dir, v0) > 0) { const RgSup t = P1; P1 = P2; P2 = t; rg_scl3(dir, dir, -1.0f); }
-      state = S_V3;
-    } else if (state == S_V3) {
-      P3 = sp;
-      if (dot < 0 || rg_mpr_zero(dot)) { state = S_DONE; continue; }
-      int cont = 0;
-      rg_cross(va, P1.v, P3.v);
-      if (rg_dot3(va, v0) < 0) { P2 = P3; cont = 1; }     /* triple products are ~1e-6: sign only */
-      if (!cont) {
-        rg_cross(va, P3.v, P2.v);
-        if (rg_dot3(va, v0) < 0) { P1 = P3; cont = 1; }
-      }
-      if (cont) {
-        rg_sub3(va, P1.v, v0); rg_sub3(vb, P2.v, v0);
-        rg_cross(dir, va, vb); rg_normalize3(dir);
-      } else {
-        rg_portal_dir3(P1, P2, P3, dir);
-        const float d1 = rg_dot3(dir, P1.v);
-        state = (d1 > 0 || rg_mpr_zero(d1)) ? S_PENETR : S_REFINE;
-      }
-    } else if (state == S_REFINE) {
-      if (!(dot > 0 || rg_mpr_zero(dot)) || rg_reach_tol3(P1, P2, P3, sp, dir, tol)) { state = S_DONE; continue; }
-      rg_expand_portal3(P1, P2, P3, v0, sp);
+    } else {
       rg_portal_dir3(P1, P2, P3, dir);
       const float d1 = rg_dot3(dir, P1.v);
-      if (d1 > 0 || rg_mpr_zero(d1)) state = S_PENETR;
-    } else { /* S_PENETR */
-      if (rg_reach_tol3(P1, P2, P3, sp, dir, tol) || pen_it > maxiter) {
-        float w[3];
-        const float depth = sqrtf(rg_tri_closest(P1.v, P2.v, P3.v, w));
-        if (depth < RG_EPS) { dir_out[0] = dir_out[1] = dir_out[2] = 0; }
-        else rg_scl3(dir_out, w, 1.0f / depth);
-        rg_find_pos3(v0, o1.pos, o2.pos, P1, P2, P3, pos);
-        result = depth;
-        state = S_DONE;
-        continue;
-      }
-      rg_expand_portal3(P1, P2, P3, v0, sp);
-      rg_portal_dir3(P1, P2, P3, dir);
-      pen_it++;
+      S.state = (d1 > 0 || rg_mpr_zero(d1)) ? RG_MPR_PENETR : RG_MPR_REFINE;
     }
+  } else if (S.state == RG_MPR_REFINE) {
+    if (!(dot > 0 || rg_mpr_zero(dot)) || rg_reach_tol3(P1, P2, P3, sp, dir, tol)) { S.state = RG_MPR_DONE; return; }
+    rg_expand_portal3(P1, P2, P3, v0, sp);
+    rg_portal_dir3(P1, P2, P3, dir);
+    const float d1 = rg_dot3(dir, P1.v);
+    if (d1 > 0 || rg_mpr_zero(d1)) S.state = RG_MPR_PENETR;
+  } else { /* RG_MPR_PENETR */
+    if (rg_reach_tol3(P1, P2, P3, sp, dir, tol) || S.pen_it > maxiter) {
+      float w[3];
+      const float depth = sqrtf(rg_tri_closest(P1.v, P2.v, P3.v, w));
+      if (depth < RG_EPS) { S.odir[0] = S.odir[1] = S.odir[2] = 0; }
+      else rg_scl3(S.odir, w, 1.0f / depth);
+      rg_find_pos3(v0, S.o1.pos, S.o2.pos, P1, P2, P3, S.opos);
+      S.depth = depth;
+      S.state = RG_MPR_DONE;
+      return;
+    }
+    rg_expand_portal3(P1, P2, P3, v0, sp);
+    rg_portal_dir3(P1, P2, P3, dir);
+    S.pen_it++;
   }
-  RG_STAT(rg_stat_hist[result >= 0][it < 63 ? it : 63]++;)
-  out.depth = result;
-  return out;
+  if (S.it >= 200 + maxiter) S.state = RG_MPR_DONE;
 }
 
 RG_DEV void rg_make_frame(const float* n, float* t1, float* t2) {
@@ -383,11 +317,12 @@ RG_DEV_NOINLINE int rg_obb_overlap(const RgCtx c, int g1, int g2, float margin) 
   return 1;
 }
 
-RG_DEV_NOINLINE int rg_narrow(const RgCtx c, int g1, int g2, float margin, float* out) {
+/* plane against anything: one lane per pair; writes up to 4 (dist,pos,normal) records to out[7*i..]; returns count */
+RG_DEV_NOINLINE int rg_narrow_plane(const RgCtx c, int g1, int g2, float margin, float* out) {
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
   int cnt = 0;
-  if (t1 == RG_GEOM_PLANE) {
+  {
     RgGeomView pl, o;
     rg_geom_view(c, g1, 0.0f, pl);
     rg_geom_view(c, g2, 0.0f, o);
@@ -449,14 +384,7 @@ RG_DEV_NOINLINE int rg_narrow(const RgCtx c, int g1, int g2, float margin, float
     }
     return cnt;
   }
-  RG_STAT(rg_stat_mpr++; rg_stat_cur = 0;)
-  const RgMprOut r = rg_mpr(c, g1, g2, margin);
-  RG_STAT(if (rg_stat_cur > rg_stat_maxsup) rg_stat_maxsup = rg_stat_cur; if (r.depth >= 0) rg_stat_mpr_hit++;)
-  if (r.depth < 0 || rg_dot3(r.dir, r.dir) < 0.5f) return 0;
-  out[0] = margin - r.depth;
-  rg_copy3(out + 1, r.pos);
-  rg_copy3(out + 4, r.dir);
-  return 1;
+  return 0;
 }
 
 /* append the first `n` survivors (flag per lane) of list `src` to list `dst`, then drop them from `src` */
@@ -464,6 +392,128 @@ RG_DEV void rg_pair(const RG_MODEL_T& m, int k, int& g1, int& g2) {
   if (RG_HAS_PAIRS(m)) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
   else { g1 = RG_LDG(m.pair_geom1 + k); g2 = RG_LDG(m.pair_geom2 + k); }
 }
+/* Separating-axis cache: pairs that pass the bounding-box cull but do not touch (most of them: neighbouring finger links)
+ * stay separated along nearly the same axis from one substep to the next.  The axis MPR stopped with is remembered per
+ * pair and tried first next time: one support evaluation proves the separation instead of a portal search.  The test
+ * is the same "support . dir < 0" MPR itself exits on, so the outcome (no contact) is the one MPR would reach.
+ * Table: RG_NSEP / 2 sets x 2 ways, one word per entry = pair id (12 bits, 0xfff = empty) | axis in octahedral
+ * coordinates (2 x 10 bits); most recently written entry in way 0. */
+RG_DEV int rg_sep_set(int pair) { return 2 * ((int)(((unsigned)pair * 2654435761u) >> 16) & (RG_NSEP / 2 - 1)); }
+RG_DEV int rg_sep_pack(int pair, const float* d) {
+  const float inv = 1.0f / (fabsf(d[0]) + fabsf(d[1]) + fabsf(d[2]) + 1e-30f);
+  float px = d[0] * inv, py = d[1] * inv;
+  if (d[2] < 0.0f) { const float qx = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f), qy = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f); px = qx; py = qy; }
+  const int x = (int)(px * 511.0f + 511.5f), y = (int)(py * 511.0f + 511.5f);
+  return (pair & 0xfff) | (x << 12) | (y << 22);
+}
+RG_DEV void rg_sep_unpack(int w, float* d) {
+  const float px = (float)(((w >> 12) & 1023) - 511) * (1.0f / 511.0f), py = (float)(((w >> 22) & 1023) - 511) * (1.0f / 511.0f);
+  const float z = 1.0f - fabsf(px) - fabsf(py);
+  d[0] = px; d[1] = py; d[2] = z;
+  if (z < 0.0f) { d[0] = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f); d[1] = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f); }
+  rg_normalize3(d);
+}
+
+/* Convex-convex narrow phase of one batch of candidates: RG_GRP lanes per pair, 32 / RG_GRP pairs in flight.  Every loop
+ * trip is one MPR iteration of each pair in flight: the lanes of a group scan the two hulls together (support mapping),
+ * reduce to the winning vertices, and then each of them advances its copy of the pair's MPR state.  A group that finishes
+ * a pair takes the next one from the list, so the trip count is about (total iterations) / (pairs in flight) rather than
+ * the iteration count of the slowest pair times the number of rounds.
+ * `list[0..nconv)` = candidate slots to process; results go to stage[8 * slot ..] = {count, dist, pos[3], normal[3]}. */
+RG_DEV_NOINLINE void rg_mpr_batch(const RgCtx c, const int* cand2, const int* list, int nconv, float* stage) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const float tol = m.opt_mpr_tolerance[0];
+  const int maxiter = m.opt_mpr_iterations[0];
+  int* sep = (int*)(RG_SCRATCH(c) + RG_CL(c).sep);
+  LANEVAR(RgMpr, st);
+  LANEVAR(int, want); LANEVAR(int, wpos); LANEVAR(int, busy);
+  LANEVAR(float, b1); LANEVAR(int, i1); LANEVAR(float, b2); LANEVAR(int, i2);
+  int next = 0, wtot;
+  RG_PHASE_BEGIN
+  LV(st).state = RG_MPR_IDLE;
+  RG_PHASE_END
+  for (;;) {
+    RG_PHASE_BEGIN
+    LV(want) = LV(st).state == RG_MPR_IDLE ? 1 : 0;   /* all RG_GRP lanes of a group agree, so the scan counts groups x RG_GRP */
+    RG_PHASE_END
+    RG_WARP_SCAN(want, wpos, wtot);
+    RG_PHASE_BEGIN
+    RgMpr& S = LV(st);
+    if (S.state == RG_MPR_IDLE) {
+      const int idx = next + LV(wpos) / RG_GRP;
+      if (idx < nconv) {
+        S.slot = list[idx];
+        int g1, g2;
+        rg_pair(m, cand2[S.slot], g1, g2);
+        const float margin = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+        rg_geom_view(c, g1, margin, S.o1);
+        rg_geom_view(c, g2, margin, S.o2);
+        rg_mpr_begin(S);
+        S.pair = cand2[S.slot];
+        if (S.pair < 0xfff) {
+          const int* se = sep + rg_sep_set(S.pair);
+          const int w0 = se[0], w1 = se[1];
+          if ((w0 & 0xfff) == S.pair) { rg_sep_unpack(w0, S.dir); S.state = RG_MPR_PRE; }
+          else if ((w1 & 0xfff) == S.pair) { rg_sep_unpack(w1, S.dir); S.state = RG_MPR_PRE; }
+        }
+        RG_STAT(if ((lane & (RG_GRP - 1)) == 0) rg_stat_mpr++;)
+      } else S.state = RG_MPR_FINISHED;
+    }
+    LV(b1) = 0.0f; LV(i1) = 0; LV(b2) = 0.0f; LV(i2) = 0;
+    if (S.state < RG_MPR_DONE) {
+      /* this lane's share of both hull scans */
+      const int gl = lane & (RG_GRP - 1);
+      float d1[3], d2[3];
+      rg_mulmatT3(d1, S.o1.mat, S.dir);
+      rg_mulmatT3(d2, S.o2.mat, S.dir);
+      d2[0] = -d2[0]; d2[1] = -d2[1]; d2[2] = -d2[2];
+      if (S.o1.type == RG_GEOM_MESH) rg_hull_scan(m, S.o1, d1, gl, RG_GRP, LV(b1), LV(i1));
+      if (S.o2.type == RG_GEOM_MESH) rg_hull_scan(m, S.o2, d2, gl, RG_GRP, LV(b2), LV(i2));
+    }
+    LV(busy) = S.state < RG_MPR_DONE;
+    RG_PHASE_END
+    next += wtot / RG_GRP;
+    if (!RG_WARP_OR(busy)) break;
+    RG_STAT(rg_stat_x[4]++;)
+    RG_GROUP8_ARGMAX(b1, i1);
+    RG_GROUP8_ARGMAX(b2, i2);
+    RG_PHASE_BEGIN
+    RgMpr& S = LV(st);
+    if (S.state < RG_MPR_DONE) {
+      RgSup sp;
+      float dl[3], loc[3], nd[3] = {-S.dir[0], -S.dir[1], -S.dir[2]};
+      RG_STAT(if ((lane & (RG_GRP - 1)) == 0) { rg_stat_support += 2; rg_stat_x[9]++; })
+      if (S.o1.type == RG_GEOM_MESH) { float p[4]; RG_LDG4(m.mesh_vert4, S.o1.vadr + LV(i1), p); rg_copy3(loc, p); }
+      else { rg_mulmatT3(dl, S.o1.mat, S.dir); rg_support_prim(S.o1, dl, loc); }
+      rg_support_world(S.o1, loc, S.dir, sp.v1);
+      if (S.o2.type == RG_GEOM_MESH) { float p[4]; RG_LDG4(m.mesh_vert4, S.o2.vadr + LV(i2), p); rg_copy3(loc, p); }
+      else { rg_mulmatT3(dl, S.o2.mat, nd); rg_support_prim(S.o2, dl, loc); }
+      rg_support_world(S.o2, loc, nd, sp.v2);
+      rg_sub3(sp.v, sp.v1, sp.v2);
+      rg_mpr_advance(S, sp, tol, maxiter);
+      if (S.state == RG_MPR_DONE) {
+        RG_STAT(if ((lane & (RG_GRP - 1)) == 0) { rg_stat_hist[S.depth >= 0][S.it < 63 ? S.it : 63]++; if (S.depth >= 0) rg_stat_mpr_hit++; })
+        if ((lane & (RG_GRP - 1)) == 0) {
+          if (S.depth < 0 && S.lastdot < 0 && S.pair < 0xfff) {
+            int* se = sep + rg_sep_set(S.pair);
+            if ((se[0] & 0xfff) != S.pair) se[1] = se[0];
+            se[0] = rg_sep_pack(S.pair, S.dir);
+          }
+          float* o = stage + 8 * S.slot;
+          const int hit = S.depth >= 0 && rg_dot3(S.odir, S.odir) >= 0.5f;
+          o[0] = hit ? 1.0f : 0.0f;
+          o[1] = 2.0f * S.o1.halfmargin - S.depth;
+          rg_copy3(o + 2, S.opos);
+          rg_copy3(o + 5, S.odir);
+        }
+        S.state = RG_MPR_IDLE;
+      }
+    }
+    RG_PHASE_END
+  }
+}
+
 RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
@@ -475,7 +525,7 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
   RG_PROF_BEGIN
   while (enabled && (k0 < m.npair || n1 > 0 || n2 > 0)) {
     /* stage A: bounding spheres over the static pair list -> cand */
-    RG_PROF(c, 15)
+    RG_PROFC(c, 15)
     while (n1 < 32 && k0 < m.npair) {
       LANEVAR(int, pred); LANEVAR(int, pos);
       int tot;
@@ -506,9 +556,10 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
       if (LV(pred)) cand[n1 + LV(pos)] = k0 + lane;
       RG_PHASE_END
       n1 += tot;
+      RG_STAT(rg_stat_x[5] += tot;)
       k0 += 32;
     }
-    RG_PROF(c, 9)
+    RG_PROFC(c, 9)
     /* stage B: oriented bounding boxes on up to 32 candidates -> cand2 */
     if (n1 > 0 && n2 < 32) {
       const int n = n1 < 32 ? n1 : 32;
@@ -531,23 +582,48 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
       if (LV(keep) >= 0) cand[lane] = LV(keep);
       RG_PHASE_END
       n2 += tot;
+      RG_STAT(rg_stat_x[6] += tot;)
       n1 = n1 > 32 ? n1 - 32 : 0;
     }
-    RG_PROF(c, 10)
+    RG_PROFC(c, 10)
     /* stage C: narrow phase, one pair per lane, once a full warp of work is queued (or at the end) */
     if (n2 >= 32 || (n2 > 0 && k0 >= m.npair && n1 == 0)) {
       const int n = n2 < 32 ? n2 : 32;
       work += n;
-      LANEVAR(int, cnt); LANEVAR(int, cpos); LANEVAR(int, keep);
+      LANEVAR(int, cnt); LANEVAR(int, cpos); LANEVAR(int, keep); LANEVAR(int, conv); LANEVAR(int, vpos);
       LANEARR(float, cb, 28);
-      int tot;
+      int tot, nconv;
+      float* stage = s + L.stage;              /* [32][8] results of the convex-convex pairs */
+      int* clist = (int*)(s + L.stage) + 256;  /* their candidate slots */
+      /* convex-convex pairs: grouped MPR */
+      RG_PHASE_BEGIN
+      int cv = 0;
+      if (lane < n) {
+        int g1, g2;
+        rg_pair(m, cand2[lane], g1, g2);
+        cv = m.geom_type[g1] != RG_GEOM_PLANE;
+      }
+      LV(conv) = cv;
+      RG_PHASE_END
+      RG_WARP_SCAN(conv, vpos, nconv);
+      RG_PHASE_BEGIN
+      if (LV(conv)) clist[LV(vpos)] = lane;
+      RG_PHASE_END
+      if (nconv > 0) rg_mpr_batch(c, cand2, clist, nconv, stage);
+      /* planes: one lane per pair */
       RG_PHASE_BEGIN
       int cn = 0;
       if (lane < n) {
-        const int k = cand2[lane];
-        int g1, g2;
-        rg_pair(m, k, g1, g2);
-        cn = rg_narrow(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), &LA(cb, 0));
+        if (LV(conv)) {
+          const float* o = stage + 8 * lane;
+          cn = (int)o[0];
+          for (int q = 0; q < 7; q++) LA(cb, q) = o[1 + q];
+        } else {
+          const int k = cand2[lane];
+          int g1, g2;
+          rg_pair(m, k, g1, g2);
+          cn = rg_narrow_plane(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), &LA(cb, 0));
+        }
       }
       LV(cnt) = cn;
       LV(keep) = (lane + 32 < n2) ? cand2[lane + 32] : -1;
@@ -596,7 +672,7 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
           r[18] = (float)m.geom_bodyid[g1]; r[19] = (float)m.geom_bodyid[g2];
           r[20] = (float)g1; r[21] = (float)g2;
           r[22] = solref[0]; r[23] = solref[1];
-          for (int q = 0; q < 5; q++) s[L.cprm + 8 * idx + q] = solimp[q];   /* consumed by rg_make_constraints */
+          for (int q = 0; q < 5; q++) s[L.cprm + RG_CPRM * idx + q] = solimp[q];   /* consumed by rg_make_constraints */
         }
       }
       RG_PHASE_END
@@ -605,11 +681,12 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
       if (LV(keep) >= 0) cand2[lane] = LV(keep);
       RG_PHASE_END
       n2 = n2 > 32 ? n2 - 32 : 0;
-      RG_PROF(c, 12)
+      RG_PROFC(c, 12)
     }
-    RG_PROF(c, 11)
+    RG_PROFC(c, 11)
   }
   RG_PHASE_BEGIN
+  RG_STAT(if (lane == 0) rg_stat_x[7] += ncon;)
   if (lane == 0) { RG_SI(c, RG_S_NCON) = ncon; RG_SI(c, RG_S_WARN) |= warn; RG_SI(c, RG_S_WORK) += work; }
   RG_PHASE_END
 }

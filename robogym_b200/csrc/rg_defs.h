@@ -22,6 +22,7 @@
 #define RG_DEV_NOINLINE static
 #define RG_NOUNROLL
 #define RG_UNROLL2
+#define RG_UNROLL4
 #define RG_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define RG_PHASE_END }
 #define RG_LANE_DECL
@@ -44,6 +45,7 @@
 /* lane-strided loops run once or twice (n <= 64): unrolling them only bloats a kernel that is instruction-cache bound */
 #define RG_NOUNROLL _Pragma("unroll 1")
 #define RG_UNROLL2 _Pragma("unroll 2")
+#define RG_UNROLL4 _Pragma("unroll 4")
 #define RG_PHASE_BEGIN {
 #define RG_PHASE_END } __syncwarp();
 #define RG_LANE_DECL const int lane = threadIdx.x & 31;
@@ -111,6 +113,8 @@ __device__ __forceinline__ void rg_stage_sync() {
 #define RG_NEL 64
 #endif                   /* single-row constraint elements (friction loss + limits) */
 #define RG_CON_STRIDE 24
+#define RG_CPRM 6           /* per-contact solver parameters: D, dim, B, K*imp*r, number of dofs, their sign bits (solimp[5] is staged there by the collision stage) */
+#define RG_NSEP 64         /* words of the per-environment separating-axis cache (rg_mpr_batch) */
 #define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
 #ifdef RG_PROFILE
 #define RG_NPROF 16      /* per-stage cycle counters appended to the RG_DBG dump (-DRG_PROFILE builds only) */
@@ -146,12 +150,13 @@ struct RgModel {
 #undef RG_F
   const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
   const int* dof_mrow;         /* [nv][3]: start of dof i's row in the tree-sparse mass matrix, dofs in its subtree, its depth */
-  const float* mesh_nbr;       /* [nmeshadj][4]: neighbour vertex x,y,z + that vertex's own adjacency range (first | degree << 20, as int bits) */
+  const int* dof_lvl;          /* [2 nv + 2]: dof ids sorted by depth, then the start of every depth level (ndoflevel + 1 entries) */
+  const float* mesh_vert4;     /* [nmeshvert][4]: hull vertices padded to 16 bytes (one vector load each) */
   const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
-  const float* mesh_ext;       /* [nmesh][6][4]: extreme vertices along +x,-x,+y,-y,+z,-z in the same x,y,z,range format (hill-climb starting points) */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
   int nM;                      /* entries of the tree-sparse mass matrix: sum over dofs of (depth + 1) */
+  int ndoflevel;               /* depth levels of the dof tree */
 };
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
@@ -164,7 +169,7 @@ struct RgLayout {
   int tlen, tvel, tJn, tJi, tJv, alen, aforce;
   int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
   int el_i, el_D, el_floss, el_jar, el_jv, el_f;
-  int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof;
+  int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof, sep, stage;
   int total;
 };
 
@@ -194,13 +199,14 @@ struct RgModelDev {
 #undef RG_FB
   RgArr<int> body_subtreesize;
   RgArr<int> dof_mrow;
+  RgArr<int> dof_lvl;
   RgArr<unsigned short> pair_packed;
   int has_pairs;
-  const float* mesh_nbr;
-  const float* mesh_ext;
+  const float* mesh_vert4;
   float origin[3];
   int small_bytes;
   int nM;
+  int ndoflevel;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev
@@ -249,6 +255,17 @@ RG_DEV int rg_warp_excl_scan(int v, int* total) {
 #define RG_WARP_ISUM(x) rg_warp_isum(x)
 #define RG_WARP_BCAST(x, src) rg_warp_bcast(x, src)
 #define RG_WARP_SCAN(cnt, pos, total) pos = rg_warp_excl_scan(cnt, &(total))
+/* arg-max over each group of 8 consecutive lanes: every lane of a group ends up with the group's best value and the
+   index that goes with it (ties: the smaller index, so the answer does not depend on which lane held it) */
+RG_DEV void rg_group8_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+}
+#define RG_GROUP8_ARGMAX(v, i) rg_group8_argmax(v, i)
 #else
 /* ---- warp helpers (emulation: identical combination order) ---- */
 static inline float rg_emu_sum(const float* x) {
@@ -267,6 +284,14 @@ static inline int rg_emu_scan(const int* c, int* pos) { int s = 0; for (int l = 
 #define RG_WARP_ISUM(x) rg_emu_isum(x)
 #define RG_WARP_BCAST(x, src) (x[src])
 #define RG_WARP_SCAN(cnt, pos, total) total = rg_emu_scan(cnt, pos)
+static inline void rg_emu_group8_argmax(float* v, int* i) {
+  for (int g = 0; g < 32; g += 8) {
+    float bv = v[g]; int bi = i[g];
+    for (int l = g + 1; l < g + 8; l++) if (v[l] > bv || (v[l] == bv && i[l] < bi)) { bv = v[l]; bi = i[l]; }
+    for (int l = g; l < g + 8; l++) { v[l] = bv; i[l] = bi; }
+  }
+}
+#define RG_GROUP8_ARGMAX(v, i) rg_emu_group8_argmax(v, i)
 #endif
 
 /* ---- small vector math ---- */

@@ -42,6 +42,16 @@ enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4,
 #define RG_PROF_BEGIN
 #define RG_PROF(c, k)
 #endif
+/* -DRG_PROFILE=2: slots 9..15 break the Newton solve down instead of the collision stage */
+#if !defined(RG_EMU) && defined(RG_PROFILE) && RG_PROFILE == 2
+#define RG_PROFS_BEGIN RG_PROF_BEGIN
+#define RG_PROFS(c, k) RG_PROF(c, k)
+#define RG_PROFC(c, k)
+#else
+#define RG_PROFS_BEGIN
+#define RG_PROFS(c, k)
+#define RG_PROFC(c, k) RG_PROF(c, k)
+#endif
 
 /* Spatial vectors of a kinematic tree are expressed about that tree's own reference point (the
  * world position of its root body), not the world origin: in fp32 the parallel-axis terms m*c^2

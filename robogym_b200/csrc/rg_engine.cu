@@ -93,14 +93,15 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
 #undef RG_FB
     RG_SETOFF(body_subtreesize)
     RG_SETOFF(dof_mrow)
-    RG_SETPTR(mesh_nbr)
-    RG_SETPTR(mesh_ext)
+    RG_SETOFF(dof_lvl)
+    RG_SETPTR(mesh_vert4)
     if (lane == 0) {
       sm->has_pairs = args.m.pair_packed != nullptr;
       sm->pair_packed.off = args.m.pair_packed ? model_bytes + (int)((const char*)args.m.pair_packed - abase) : 0;
       sm->origin[0] = args.m.origin[0]; sm->origin[1] = args.m.origin[1]; sm->origin[2] = args.m.origin[2];
       sm->small_bytes = small_bytes;
       sm->nM = args.m.nM;
+      sm->ndoflevel = args.m.ndoflevel;
     }
     for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
@@ -216,9 +217,9 @@ __global__ void __launch_bounds__(1024) rg_subset_kernel(const uint8_t* __restri
   }
   if (t == 0) *count = base;
 }
-__global__ void rg_iota_kernel(int* order, int* cost, int nenv) {
+__global__ void rg_iota_kernel(int* order, int* cost, int* sep, int nenv) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < nenv) { order[e] = e; cost[e] = 0; }
+  if (e < nenv) { order[e] = e; cost[e] = 0; for (int i = 0; i < RG_NSEP; i++) sep[(size_t)e * RG_NSEP + i] = 0xfff; }
 }
 
 /* ------------------------------------------------------------------ host objects */
@@ -244,6 +245,7 @@ struct rg_batch {
   int* d_order = nullptr;  /* slot -> environment of the next launch */
   int* d_cost = nullptr;   /* work estimate written by the last launch */
   int* d_subset = nullptr; /* [nenv + 1] slot table of a subset launch, followed by its length */
+  int* d_sep = nullptr;    /* [nenv][RG_NSEP] separating-axis cache of the narrow phase (speeds it up; results do not depend on it) */
   int balance = 1;
 };
 
@@ -260,8 +262,8 @@ static void rg_wire_device_view(rg_model* mm) {
 #undef RG_F
   RG_DEVPTR(body_subtreesize)
   RG_DEVPTR(dof_mrow)
-  RG_DEVPTR(mesh_nbr)
-  RG_DEVPTR(mesh_ext)
+  RG_DEVPTR(dof_lvl)
+  RG_DEVPTR(mesh_vert4)
   if (mm->hm.view.pair_packed) RG_DEVPTR(pair_packed)
 #undef RG_DEVPTR
 }
@@ -406,7 +408,8 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   cudaError_t e = cudaMalloc((void**)&b->d_order, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_subset, sizeof(int) * ((size_t)nenv + 1));
-  if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, nenv); e = cudaDeviceSynchronize(); }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_sep, sizeof(int) * (size_t)nenv * RG_NSEP);
+  if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, b->d_sep, nenv); e = cudaDeviceSynchronize(); }
   if (e != cudaSuccess) { std::string msg = std::string("rg_batch_create: CUDA: ") + cudaGetErrorString(e); rg_batch_destroy(b); return rg_fail(-2, msg); }
   *out = b;
   return 0;
@@ -416,6 +419,7 @@ void rg_batch_destroy(rg_batch* b) {
   if (b->d_order) cudaFree(b->d_order);
   if (b->d_cost) cudaFree(b->d_cost);
   if (b->d_subset) cudaFree(b->d_subset);
+  if (b->d_sep) cudaFree(b->d_sep);
   delete b;
 }
 
@@ -493,6 +497,7 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   io.site_xpos = (float*)b->ptr[RG_FIELD_SITE_XPOS]; io.body_xpos = (float*)b->ptr[RG_FIELD_BODY_XPOS]; io.body_xquat = (float*)b->ptr[RG_FIELD_BODY_XQUAT];
   io.geom_xpos = (float*)b->ptr[RG_FIELD_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_FIELD_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_FIELD_QACC];
   io.cost = b->balance ? b->d_cost : nullptr;
+  io.sep = b->d_sep;
   io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;
 }

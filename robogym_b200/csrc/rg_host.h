@@ -68,12 +68,12 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   for (size_t i = 0; i < first_big; i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
   dst = rg_align16(dst); const size_t off_subtree = dst; dst += 4 * (size_t)m.nbody;
   dst = rg_align16(dst); const size_t off_mrow = dst; dst += 12 * (size_t)m.nv;
+  dst = rg_align16(dst); const size_t off_dlvl = dst; dst += 4 * (2 * (size_t)m.nv + 2);
   dst = rg_align16(dst); const size_t off_pairs = dst; if (m.ngeom <= 256) dst += 2 * (size_t)m.npair;
   dst = rg_align16(dst);
   hm.small_bytes = dst;
   for (size_t i = first_big; i < names.size(); i++) { dst = rg_align16(dst); dstoff[i] = dst; dst += 4 * counts[i]; }
-  dst = rg_align16(dst); const size_t off_nbr = dst; dst += 16 * (size_t)m.nmeshadj;
-  dst = rg_align16(dst); const size_t off_ext = dst; dst += 16 * 6 * (size_t)m.nmesh;
+  dst = rg_align16(dst); const size_t off_v4 = dst; dst += 16 * (size_t)m.nmeshvert;
   dst = rg_align16(dst);
   hm.arena.assign(dst, 0);
   char* base = hm.arena.data();
@@ -116,6 +116,19 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
       if (par >= 0 && d >= par + mrow[3 * par + 1]) { err = "dof subtrees are not contiguous"; return false; }
     }
     m.nM = nM;
+    /* dofs sorted by depth (stable): dlvl[0..nv) = dof ids, dlvl[nv + l] = start of level l; the tree-sparse
+       factorisation walks these levels leaves-first, the back substitution roots-first */
+    int* dlvl = (int*)(base + off_dlvl);
+    int maxd = 0;
+    for (int d = 0; d < m.nv; d++) if (mrow[3 * d + 2] > maxd) maxd = mrow[3 * d + 2];
+    int pos = 0;
+    for (int l = 0; l <= maxd; l++) {
+      dlvl[m.nv + l] = pos;
+      for (int d = 0; d < m.nv; d++) if (mrow[3 * d + 2] == l) dlvl[pos++] = d;
+    }
+    dlvl[m.nv + maxd + 1] = pos;
+    m.ndoflevel = m.nv > 0 ? maxd + 1 : 0;
+    m.dof_lvl = dlvl;
   }
   /* depth-first numbering check: every body's parent must precede it and subtrees must be contiguous */
   for (int b = 1; b < m.nbody; b++) {
@@ -126,50 +139,18 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   m.dof_mrow = mrow;
   hm.offsets.push_back(off_subtree);
   hm.offsets.push_back(off_mrow);
-  /* hull neighbour table with inline coordinates + extreme-vertex starting points.  The 4th word of an entry is the
-     neighbour's OWN adjacency range (first entry | degree << 20), so a hill-climb step is one dependent load level:
-     the entries of the vertex it moves to are addressed without another lookup. */
-  float* nbr = (float*)(base + off_nbr);
-  float* ext = (float*)(base + off_ext);
-  if (m.nmeshadj >= (1 << 20)) { err = "hull adjacency too large for the packed neighbour table"; return false; }
-  for (int i = 0; i < m.nmesh; i++) {
-    const int va = m.mesh_vertadr[i], vn = m.mesh_vertnum[i];
-    const float* v = m.mesh_vert + 3 * va;
-    auto packed = [&](int k) {
-      const int a0 = m.mesh_adjadr[va + k], deg = m.mesh_adjadr[va + k + 1] - a0;
-      return (int)((unsigned)a0 | ((unsigned)(deg > 4095 ? 4095 : deg) << 20));
-    };
-    for (int k = 0; k < vn; k++) {
-      if (m.mesh_adjadr[va + k + 1] - m.mesh_adjadr[va + k] > 4095) { err = "hull vertex degree too large"; return false; }
-      for (int a = m.mesh_adjadr[va + k]; a < m.mesh_adjadr[va + k + 1]; a++) {
-        const int nb = m.mesh_adj[a];
-        const int pk = packed(nb);
-        nbr[4 * a] = v[3 * nb]; nbr[4 * a + 1] = v[3 * nb + 1]; nbr[4 * a + 2] = v[3 * nb + 2];
-        memcpy(&nbr[4 * a + 3], &pk, 4);
-      }
-    }
-    for (int ax = 0; ax < 3; ax++) {
-      int hi = 0, lo = 0;
-      for (int k = 1; k < vn; k++) { if (v[3 * k + ax] > v[3 * hi + ax]) hi = k; if (v[3 * k + ax] < v[3 * lo + ax]) lo = k; }
-      const int sel[2] = {hi, lo};
-      for (int q = 0; q < 2; q++) {
-        float* e = ext + 4 * (6 * i + 2 * ax + q);
-        const int pk = packed(sel[q]);
-        e[0] = v[3 * sel[q]]; e[1] = v[3 * sel[q] + 1]; e[2] = v[3 * sel[q] + 2];
-        memcpy(&e[3], &pk, 4);
-      }
-    }
-  }
-  m.mesh_nbr = nbr;
-  m.mesh_ext = ext;
+  hm.offsets.push_back(off_dlvl);
+  /* hull vertices padded to float4: the narrow phase scans a hull's vertices with one 16-byte load each */
+  float* v4 = (float*)(base + off_v4);
+  for (int k = 0; k < m.nmeshvert; k++) { v4[4 * k] = m.mesh_vert[3 * k]; v4[4 * k + 1] = m.mesh_vert[3 * k + 1]; v4[4 * k + 2] = m.mesh_vert[3 * k + 2]; v4[4 * k + 3] = 0.0f; }
+  m.mesh_vert4 = v4;
   m.pair_packed = nullptr;
   if (m.ngeom <= 256) {
     unsigned short* pk = (unsigned short*)(base + off_pairs);
     for (int k = 0; k < m.npair; k++) pk[k] = (unsigned short)(m.pair_geom1[k] | (m.pair_geom2[k] << 8));
     m.pair_packed = pk;
   }
-  hm.offsets.push_back(off_nbr);
-  hm.offsets.push_back(off_ext);
+  hm.offsets.push_back(off_v4);
   /* fp32 conditioning: translate the world so the scene sits near the origin */
   double o[3] = {0, 0, 0};
   int cnt = 0;

@@ -11,6 +11,12 @@
 #pragma once
 #include "rg_col.inl"
 
+#ifndef RG_NEWTON_TOL
+#define RG_NEWTON_TOL 1e-6f   /* fp32: below ~1e-6 the scaled cost differences are rounding noise */
+#endif
+#ifndef RG_LS_TOL
+#define RG_LS_TOL 1e-6f
+#endif
 #define RG_MINIMP 0.0001f
 #define RG_MAXIMP 0.9999f
 
@@ -301,7 +307,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     float* r = s + L.con + RG_CON_STRIDE * k;
-    float* prm = s + L.cprm + 8 * k;
+    float* prm = s + L.cprm + RG_CPRM * k;
     int dim = (int)r[17];
     if ((flags & (RG_DSBL_CONTACT | RG_DSBL_CONSTRAINT)) || !(r[0] < r[13])) dim = 0; /* inactive: outside includemargin */
     const int b1 = (int)r[18], b2 = (int)r[19];
@@ -391,7 +397,7 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
   }
   RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     const float* r = s + L.con + RG_CON_STRIDE * k;
-    const float* prm = s + L.cprm + 8 * k;
+    const float* prm = s + L.cprm + RG_CPRM * k;
     const float* u = s + L.cu + 6 * k;
     const int dim = (int)prm[1];
     const float D = prm[0];
@@ -433,7 +439,7 @@ RG_DEV_NOINLINE void rg_JT_force_phase(const RgCtx c, int out, int nel, int tl0,
     }
     for (int k = 0; k < ncon; k++) {
       const float* r = s + L.con + RG_CON_STRIDE * k;
-      const int dim = (int)s[L.cprm + 8 * k + 1];
+      const int dim = (int)s[L.cprm + RG_CPRM * k + 1];
       float col[6];
       if (dim == 0 || !rg_contact_col(c, r, d, dim, col)) continue;
       const float* F = s + L.cF + 6 * k;
@@ -457,11 +463,11 @@ RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_o
   }
   RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
     const float* r = s + L.con + RG_CON_STRIDE * k;
-    const int dim = (int)s[L.cprm + 8 * k + 1];
+    const int dim = (int)s[L.cprm + RG_CPRM * k + 1];
     float v[6] = {0, 0, 0, 0, 0, 0};
     const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
-    const int nd = (int)s[L.cprm + 8 * k + 4];
-    const unsigned sgn = (unsigned)s[L.cprm + 8 * k + 5];
+    const int nd = (int)s[L.cprm + RG_CPRM * k + 4];
+    const unsigned sgn = (unsigned)s[L.cprm + RG_CPRM * k + 5];
     RG_NOUNROLL for (int i = 0; i < nd; i++) {
       float col[6];
       const int d = list[i];
@@ -488,6 +494,8 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   for (int e = 0; e < nel; e++) printf(" %d/%d/%d", el_i[e] & 3, (el_i[e] >> 2) & 1, el_i[e] >> 3);
   printf("\n");
 #endif
+  RG_STAT(rg_stat_x[0]++; rg_stat_x[8] += nel;)
+  RG_PROFS_BEGIN
   /* start from the previous solution (warm start) */
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
@@ -496,7 +504,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   rg_J_mul_phase(c, L.qacc, L.el_jar, L.cu, nel, ncon, 1);
   float cost_con = rg_solver_update(c, nel, ncon);
   const float scale = 1.0f / (m.opt_meaninertia[0] * (float)(nv > 1 ? nv : 1));
-  const float tol = fmaxf(m.opt_tolerance[0], 1e-6f); /* fp32: below ~1e-6 the cost differences are rounding noise */
+  const float tol = fmaxf(m.opt_tolerance[0], RG_NEWTON_TOL); /* fp32: below ~1e-6 the cost differences are rounding noise */
   int iter = 0, have_factor = 0, factor_sig = 0;
   float cost;
   {
@@ -508,6 +516,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     RG_PHASE_END
     cost = RG_WARP_SUM(gp) + cost_con;
   }
+  RG_PROFS(c, 9)
   int active = 1;
   for (;;) {
   const int go = active && iter < m.opt_iterations[0];
@@ -527,14 +536,17 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     LV(gn) = a;
     RG_PHASE_END
     const float gnorm = sqrtf(RG_WARP_SUM(gn));
-    if (scale * gnorm < tol) break;
+    RG_PROFS(c, 10)
+    if (scale * gnorm < tol) { RG_STAT(rg_stat_x[10]++;) break; }
     /* Hessian H = M + J' diag(D active) J: rebuilt and refactored only when the active set changed */
 #ifdef RG_NO_REUSE
     const int refactor = 1;
 #else
     const int refactor = !(have_factor && RG_SI(c, RG_S_SIG) == factor_sig);
 #endif
+    RG_STAT(rg_stat_x[1]++;)
     if (refactor) {
+    RG_STAT(rg_stat_x[2]++;)
     rg_H_from_M(c, nullptr, 0.0f);
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
@@ -560,7 +572,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     }
     for (int k = 0; k < ncon; k++) {
       const float* r = s + L.con + RG_CON_STRIDE * k;
-      const float* prm = s + L.cprm + 8 * k;
+      const float* prm = s + L.cprm + RG_CPRM * k;
       const int dim = (int)prm[1];
       if (dim == 0) continue;
       /* W = sum over active pyramid rows of D c c^T, c = e0 +- mu e_a */
@@ -615,7 +627,9 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       env[i] = e;
     }
     RG_PHASE_END
+    RG_PROFS(c, 11)
     rg_cholesky(c, L.H, env);
+    RG_PROFS(c, 12)
     have_factor = 1; factor_sig = RG_SI(c, RG_S_SIG);
     }
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
@@ -623,6 +637,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #endif
     rg_chol_solve(c, L.H, env, L.search, L.tmp);
     rg_reverse_phase(c, L.search);
+    RG_PROFS(c, 13)
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
     { /* finite-difference check of the Newton direction: g(q + eps*s) should be ~ (1-eps) g(q) when the active set holds */
       static float q0[256], g0v[256], ma0[256], jar0[256], cu0[6 * RG_NCON], f0[256], cf0[6 * RG_NCON], qfc0[256];
@@ -665,6 +680,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     float alpha = 0.0f, lo = 0.0f, hi = -1.0f, g0 = 0.0f;
     for (int ls = 0; ls < 12; ls++) {
       LANEVAR(float, pg); LANEVAR(float, ph);
+      RG_STAT(rg_stat_x[3]++;)
       RG_PHASE_BEGIN
       float g = 0.0f, h = 0.0f;
       RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
@@ -678,7 +694,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       }
       RG_NOUNROLL for (int k = lane; k < ncon; k += 32) {
         const float* r = s + L.con + RG_CON_STRIDE * k;
-        const float* prm = s + L.cprm + 8 * k;
+        const float* prm = s + L.cprm + RG_CPRM * k;
         const float* u = s + L.cu + 6 * k;
         const float* w = s + L.cw + 6 * k;
         const int dim = (int)prm[1];
@@ -698,7 +714,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       const float h = RG_WARP_SUM(ph) + 2.0f * q2;
       if (ls == 0) { g0 = g; if (!(g0 < 0.0f)) break; }
       else {
-        if (fabsf(g) <= 1e-6f * fabsf(g0)) break;
+        if (fabsf(g) <= RG_LS_TOL * fabsf(g0)) break;
         if (g < 0.0f) lo = alpha; else hi = alpha;
         if (hi >= 0.0f && hi - lo <= 1e-7f * hi) break;
       }
@@ -706,7 +722,8 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       if (hi >= 0.0f && (a2 <= lo || a2 >= hi)) a2 = 0.5f * (lo + hi);
       alpha = a2;
     }
-    if (!(alpha > 0.0f)) break;
+    RG_PROFS(c, 14)
+    if (!(alpha > 0.0f)) { RG_STAT(rg_stat_x[11]++;) break; }
     /* take the step */
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) { s[L.qacc + d] += alpha * s[L.search + d]; s[L.Ma + d] += alpha * s[L.Mv + d]; }
@@ -725,12 +742,14 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       newcost = RG_WARP_SUM(gp) + cost_con;
     }
     const float improvement = scale * (cost - newcost);
+    RG_PROFS(c, 15)
+    RG_STAT(if (getenv("RG_TRACE") && rg_stat_x[0] % 97 == 0) printf("  fw %lld it %d g %.3g alpha %.4g impr %.3g refac %d nel %d ncon %d\n", rg_stat_x[0], iter, scale * gnorm, alpha, improvement, refactor, nel, ncon);)
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
     printf("  it %d cost %.9g new %.9g impr %.3g alpha %.6g gnorm %.3g refactor %d sig %d\n", iter, cost, newcost, improvement, alpha, gnorm, refactor, RG_SI(c, RG_S_SIG));
 #endif
     cost = newcost;
     /* fp32: cost differences below ~2 ulp of the cost itself are rounding noise, not progress */
-    if (improvement < tol + 2.4e-7f * fabsf(cost) * scale) { iter++; break; }
+    if (improvement < tol + 2.4e-7f * fabsf(cost) * scale) { RG_STAT(rg_stat_x[12]++;) iter++; break; }
     done = 0;
   } while (0);
   if (done) active = 0; else iter++;
@@ -742,28 +761,86 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   RG_PHASE_END
 }
 
+/* ---------------------------------------------------------------- tree-sparse factorisation of M + diag */
+/* M couples a dof only with its ancestors and descendants, so M + diag = L' D L with L as sparse as M (the layout MuJoCo
+ * calls qLD).  F (nM floats, rows like M) receives D(i) in slot 0 of row i and the UNSCALED couplings D(i) L(i, a) behind
+ * it; invD (nv floats) the reciprocals of D.  Work is organised by depth level, leaves first: entry (i, a) subtracts the
+ * contributions of the dofs in the subtree of i, all of which are deeper and therefore final ("pull" form: lanes never
+ * write the same slot, no atomics, fixed summation order). */
+RG_DEV_NOINLINE void rg_sparse_factor(const RgCtx c, int F, int invD, const float* diag, float scale) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  float* s = RG_SCRATCH(c);
+  const float* M = s + RG_CL(c).M;
+  const int nv = m.nv;
+  const int* order = m.dof_lvl + 0;
+  const int* start = m.dof_lvl + nv;
+  for (int lvl = m.ndoflevel - 1; lvl >= 0; lvl--) {
+    const int l0 = start[lvl], cnt = start[lvl + 1] - l0, w = lvl + 1;
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int it = lane; it < cnt * w; it += 32) {
+      const int q = it / w, e = it - q * w;
+      const int i = order[l0 + q];
+      const int adr = m.dof_mrow[3 * i], nsub = m.dof_mrow[3 * i + 1];
+      float acc = M[adr + e] + (e == 0 && diag ? scale * diag[i] : 0.0f);
+      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++) {
+        const int ak = m.dof_mrow[3 * k], dk = m.dof_mrow[3 * k + 2] - lvl;   /* column i sits dk entries into row k */
+        acc -= s[F + ak + dk] * s[F + ak + dk + e] * s[invD + k];
+      }
+      s[F + adr + e] = acc;
+      if (e == 0) s[invD + i] = 1.0f / acc;
+    }
+    RG_PHASE_END
+  }
+}
+/* x <- (M + diag)^-1 x with the factor above */
+RG_DEV_NOINLINE void rg_sparse_solve(const RgCtx c, int F, int invD, int x) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  float* s = RG_SCRATCH(c);
+  const int nv = m.nv;
+  const int* order = m.dof_lvl + 0;
+  const int* start = m.dof_lvl + nv;
+  /* x <- L^-T x: a dof collects from its subtree (deeper levels are final) */
+  for (int lvl = m.ndoflevel - 2; lvl >= 0; lvl--) {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
+      const int i = order[q];
+      const int nsub = m.dof_mrow[3 * i + 1];
+      float acc = s[x + i];
+      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++)
+        acc -= s[F + m.dof_mrow[3 * k] + m.dof_mrow[3 * k + 2] - lvl] * s[invD + k] * s[x + k];
+      s[x + i] = acc;
+    }
+    RG_PHASE_END
+  }
+  /* x <- D^-1 x, then x <- L^-1 x: a dof collects from its ancestors (shallower levels are final) */
+  for (int lvl = 0; lvl < m.ndoflevel; lvl++) {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
+      const int i = order[q];
+      const int adr = m.dof_mrow[3 * i];
+      float acc = s[x + i];
+      int a = m.dof_parentid[i];
+      RG_NOUNROLL for (int e = 1; e <= lvl; e++) { acc -= s[F + adr + e] * s[x + a]; a = m.dof_parentid[a]; }
+      s[x + i] = acc * s[invD + i];
+    }
+    RG_PHASE_END
+  }
+}
+
 /* ---------------------------------------------------------------- S15 semi-implicit Euler */
 RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   const float h = c.timestep;
-  int* env = (int*)(s + L.env);
-  /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint */
-  rg_H_from_M(c, m.dof_damping + 0, h);
+  /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint; the dense Hessian region is free here and holds the factor */
+  rg_sparse_factor(c, L.H, L.tmp, m.dof_damping + 0, h);
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + (nv - 1 - d)] = s[L.smooth + d] + s[L.qfc + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + d] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
-  RG_PHASE_BEGIN
-  RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
-    int e = 0;
-    while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
-    env[i] = e;
-  }
-  RG_PHASE_END
-  rg_cholesky(c, L.H, env);
-  rg_chol_solve(c, L.H, env, L.search, L.tmp);
-  rg_reverse_phase(c, L.search);
+  rg_sparse_solve(c, L.H, L.tmp, L.search);
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
   RG_PHASE_END

@@ -18,6 +18,7 @@ struct RgBatchIO {
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
   float* contact;           /* [nenv][RG_NCON][4] = geom1, geom2, dist, dim */
   int* ncon; int* warn;
+  int* sep;                 /* [nenv][RG_NSEP] separating-axis cache carried from launch to launch (engine-internal, may be nullptr) */
   int* cost;                /* [nenv] work estimate of this launch (engine-internal, see rg_order_kernel) */
   float* dbg;               /* [nenv][rg_dbg_size] stage dump for the parity tests */
 };
@@ -53,17 +54,20 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
   RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
   RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, RG_TJ * m.ntendon); RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
-  RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, 8 * RG_NCON);
+  RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, RG_CPRM * RG_NCON);
   RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
   RG_ALLOC(el_jar, RG_NEL); RG_ALLOC(el_jv, RG_NEL); RG_ALLOC(el_f, RG_NEL);
   RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(scal, 8 + RG_NPROF);
   RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, 4 * RG_NCON);
+  RG_ALLOC(sep, RG_NSEP);   /* lives across the substeps of a launch, so it cannot share storage */
 #undef RG_ALLOC
   /* lifetimes that never overlap share storage: local frames (kinematics only) sit in the contact
      solver vectors, the broad-phase candidate lists in the row work arrays */
   if (((3 * m.nbody + 3) & ~3) + 4 * m.nbody <= 12 * RG_NCON) { L.lpos = L.cu; L.lquat = L.cu + ((3 * m.nbody + 3) & ~3); }
   else { L.lpos = o; o += (3 * m.nbody + 3) & ~3; L.lquat = o; o += 4 * m.nbody; }
   L.cand = L.el_jv; L.cand2 = L.el_f;
+  /* narrow-phase staging (32 x 8 results + 32 slots): in the contact solver vectors, which are idle during collision */
+  if (18 * RG_NCON >= 288) L.stage = L.cu; else { L.stage = o; o += 288; }
   L.total = o;
   return L;
 }
@@ -102,6 +106,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) s[L.ctrl + i] = io.ctrl[(size_t)env * m.nu + i];
   RG_NOUNROLL for (int i = lane; i < npid; i += 32) s[L.pid + i] = io.pid[(size_t)env * npid + i];
   if (lane < 8 + RG_NPROF) RG_SI(c, lane) = 0;
+  RG_NOUNROLL for (int i = lane; i < RG_NSEP; i += 32) ((int*)(s + L.sep))[i] = io.sep ? io.sep[(size_t)env * RG_NSEP + i] : 0xfff;
   RG_PHASE_END
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
@@ -143,6 +148,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) { io.qvel[(size_t)env * m.nv + i] = s[L.qvel + i]; io.warm[(size_t)env * m.nv + i] = s[L.warm + i]; }
   RG_NOUNROLL for (int i = lane; i < npid; i += 32) io.pid[(size_t)env * npid + i] = s[L.pid + i];
   if (lane == 0 && io.time) io.time[env] += c.timestep * (float)nsub;
+  if (io.sep) RG_NOUNROLL for (int i = lane; i < RG_NSEP; i += 32) io.sep[(size_t)env * RG_NSEP + i] = ((const int*)(s + L.sep))[i];
   if (io.site_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.nsite; i += 32) io.site_xpos[(size_t)env * 3 * m.nsite + i] = s[L.sxpos + i] + m.origin[i % 3];
   if (io.body_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.nbody; i += 32) io.body_xpos[(size_t)env * 3 * m.nbody + i] = s[L.xpos + i] + m.origin[i % 3];
   if (io.body_xquat) RG_NOUNROLL for (int i = lane; i < 4 * m.nbody; i += 32) io.body_xquat[(size_t)env * 4 * m.nbody + i] = s[L.xquat + i];

@@ -12,7 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; };
+struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; std::vector<int> sep; };
 
 extern "C" {
 
@@ -25,7 +25,7 @@ void* rge_create(const void* blob, size_t len) {
   return h;
 }
 #ifdef RG_STATS
-void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; for (int i = 0; i < 128; i++) out[8 + i] = rg_stat_hist[i / 64][i % 64]; }
+void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; for (int i = 0; i < 128; i++) out[8 + i] = rg_stat_hist[i / 64][i % 64]; for (int i = 0; i < 16; i++) out[136 + i] = rg_stat_x[i]; }
 #endif
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
 int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view); }
@@ -60,6 +60,8 @@ void rge_step(void* hv, int nenv, float* qpos, float* qvel, float* ctrl, float* 
   io.nenv = nenv; io.qpos = qpos; io.qvel = qvel; io.ctrl = ctrl; io.pid = pid; io.warm = warm; io.time = time; io.xfrc = xfrc;
   io.timestep = timestep; io.site_xpos = site_xpos; io.body_xpos = body_xpos; io.body_xquat = body_xquat; io.geom_xpos = geom_xpos;
   io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg; io.cost = nullptr;
+  if (h->sep.size() != (size_t)nenv * RG_NSEP) h->sep.assign((size_t)nenv * RG_NSEP, 0xfff);   /* like the engine's per-batch buffer */
+  io.sep = h->sep.data();
   for (int env = 0; env < nenv; env++) rg_env_step(&h->hm.view, h->L, h->scratch.data(), 0, io, env, nsub, final_forward, 1);
 }
 }

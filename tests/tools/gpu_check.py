@@ -78,6 +78,8 @@ if "prof" not in _os.environ.get("RG_LIB", ""):
     raise SystemExit(0)          # the stage counters exist only in the -DRG_PROFILE build
 prof = sim.dbg.cpu().numpy()[:, -16:]
 names = ["kin", "massm", "bias", "tendon", "forces", "collide", "mkcon", "solve", "euler", "col:A-sphere", "col:B-obb", "col:C-narrow+write", "col:C-rounds", "-", "-", "col:loop"]
+if "prof2" in _os.environ.get("RG_LIB", ""):
+    names = names[:9] + ["sol:init", "sol:gradient", "sol:H-assembly", "sol:cholesky", "sol:tri-solves", "sol:linesearch", "sol:step+update"]
 tot = prof[:, :9].sum(1).mean()
 print("stage cycles per env-step (mean over envs, lane0 clock64):")
 for i, nme in enumerate(names):
