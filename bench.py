@@ -26,10 +26,6 @@ sys.path.insert(0, ROOT)
 NENV_PER_GPU = 8192
 NSUB = 10
 ALGO_BYTES_PER_ENV_STEP = 1664       # 784 B read + 680 B written + ~200 B derived outputs
-# dram__bytes_read.sum + dram__bytes_write.sum of rg_step_kernel for one 8192-env launch, from the ncu --set full
-# capture summarised in profiles/r1i_ncu_metrics.csv (13.08 MB + 2.97 MB); re-measure when the kernel changes
-NCU_DRAM_BYTES_PER_LAUNCH = 17.06e6
-ACTION_SCALE = 0.3                   # relative random actions: ctrl += a * 0.3 * half-range, a ~ U(-1, 1)
 METRIC = "env-steps/sec dactyl/locked batch 8192 @1/2/4/8 B200 vs CPU mujoco-py"
 
 
@@ -242,6 +238,74 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------- GPU arm
+def newest_profile_metrics():
+    """Per-launch counters of rg_step_kernel from the newest ncu capture committed under profiles/ (8192 envs, one launch):
+    DRAM bytes and warp instructions.  None when no capture is there."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.csv")), key=lambda f: (os.path.basename(f).split("_")[0][:2], os.path.getmtime(f)))
+    for f in reversed(files):
+        try:
+            d = {r[0]: (r[1], float(r[2].replace(",", ""))) for r in csv.reader(open(f)) if len(r) == 3 and r[0] != "metric"}
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+            return {"file": os.path.relpath(f, ROOT), "dram_bytes": rd[1] * unit.get(rd[0], 1.0) + wr[1] * unit.get(wr[0], 1.0),
+                    "warp_inst": d["smsp__inst_executed.sum"][1]}
+        except Exception:
+            continue
+    return None
+
+
+class Workload:
+    """SURVEY.md 8(d) cfg 2: a ~ U(-1,1)^20, ctrl = clip(P qpos_hand + a * range / 2, ctrlrange) (relative actions,
+    robogym/robot/robot_interface.py:247-278), held for the 10 substeps of an env-step; an environment whose cube left
+    the palm is reset (CubeEnv._reset style: settled hand, cube position jitter N(0, 0.005^2), uniform random cube
+    orientation) before the next step, so dropped cubes do not make steps cheaper."""
+
+    def __init__(self, sim, model, names, dev, gen):
+        import torch
+
+        from robogym_b200.batched_env import ShadowHandCubeFacade
+
+        self.torch, self.sim, self.gen, self.dev = torch, sim, gen, dev
+        self.facade = ShadowHandCubeFacade(model.host, names, dev)
+        m = model.host
+        self.nu = m["nu"]
+        N = sim.nenv
+        lo, hi = self.facade.ctrl_lo, self.facade.ctrl_hi
+        sim.ctrl.copy_((0.5 * (lo + hi)).repeat(N, 1))
+        for _ in range(20):                              # locked.py:200-205: settle with zero actions
+            sim.step()
+        self.q0, self.c0 = sim.qpos.clone(), sim.ctrl.clone()
+        self.n_resets = 0
+        self.reset(torch.ones(N, dtype=torch.bool, device=dev))
+
+    def reset(self, mask):
+        t, sim = self.torch, self.sim
+        N = sim.nenv
+        q = self.q0.clone()
+        q[:, 0:3] += 0.005 * t.randn(N, 3, device=self.dev, generator=self.gen)
+        quat = t.randn(N, 4, device=self.dev, generator=self.gen)
+        q[:, 3:7] = quat / quat.norm(dim=1, keepdim=True)
+        mk = mask.unsqueeze(1)
+        sim.qpos.copy_(t.where(mk, q, sim.qpos))
+        sim.qvel.mul_((~mk).to(sim.qvel.dtype))
+        sim.pid.mul_((~mk).to(sim.pid.dtype))
+        sim.qacc_warmstart.mul_((~mk).to(sim.qvel.dtype))
+        sim.ctrl.copy_(t.where(mk, self.c0, sim.ctrl))
+
+    def next_ctrl(self):
+        t, sim = self.torch, self.sim
+        a = t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1
+        return self.facade.denormalize_position_control(a, sim.qpos, relative_action=True)
+
+    def auto_reset(self):
+        dropped = ~self.facade.on_palm(self.sim.site_xpos)
+        self.reset(dropped)
+        return dropped
+
+
 def run_gpu_arm(args):
     import numpy as np
     import torch
@@ -261,33 +325,23 @@ def run_gpu_arm(args):
     torch.cuda.set_device(dev)
     build.build()
     blob = load_blob()
+    names = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.names.json")))
     model = engine.DeviceModel(blob, local)
-    N = NENV_PER_GPU                                  # weak scaling: 8192 envs per GPU
+    strong = args.scaling == "strong"
+    N = NENV_PER_GPU // world if strong else NENV_PER_GPU      # weak: 8192 envs per GPU; strong: 8192 per box
     lo_env, hi_env = shard_range(N * world, rank, world)
     sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"))
     m = model.host
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
-    cr = torch.tensor(m["actuator_ctrlrange"].reshape(-1, 2), dtype=torch.float32, device=dev)
-    lo, hi = cr[:, 0].contiguous(), cr[:, 1].contiguous()
-    half = 0.5 * (hi - lo)
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank_seed(1234, rank))
-
-    def new_ctrl(cur):
-        a = torch.rand(N, nu, device=dev, generator=gen) * 2 - 1
-        return torch.minimum(torch.maximum(cur + ACTION_SCALE * a * half, lo), hi)
-
-    # setup (untimed): settle 20 env-steps at mid-range targets, then perturb the cube pose per env
-    sim.ctrl.copy_((0.5 * (lo + hi)).repeat(N, 1))
-    for _ in range(20):
-        sim.step()
-    sim.qpos[:, 0:3] += 0.005 * torch.randn(N, 3, device=dev, generator=gen)
-    quat = torch.randn(N, 4, device=dev, generator=gen)
-    sim.qpos[:, 3:7] = quat / quat.norm(dim=1, keepdim=True)
+    wl = Workload(sim, model, names, dev, gen)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
-    for _ in range(max(args.warmup, 3)):
-        sim.ctrl.copy_(new_ctrl(sim.ctrl))
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
+        sim.ctrl.copy_(wl.next_ctrl())
         sim.step()
+        wl.auto_reset()
     torch.cuda.synchronize()
 
     # ---- timed region 1: device-resident (kernel) throughput
@@ -298,13 +352,19 @@ def run_gpu_arm(args):
         dist.barrier()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    resets = torch.zeros((), dtype=torch.int64, device=dev)
+    ncon_sum = torch.zeros((), dtype=torch.float64, device=dev)
+    warn = torch.zeros((), dtype=torch.int32, device=dev)
     for k in range(args.steps):
-        nxt = new_ctrl(sim.ctrl)
+        nxt = wl.next_ctrl()
         flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
         sim.ctrl.copy_(nxt)
         ev[k][0].record()
         sim.step()
         ev[k][1].record()
+        ncon_sum += sim.ncon.double().mean()
+        warn |= sim.warn.max()
+        resets += wl.auto_reset().sum()                 # in-loop auto-reset (untimed torch ops, like the action sampling)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -313,16 +373,19 @@ def run_gpu_arm(args):
     t_dev = max_over_ranks(sum(step_ms) / 1e3, dist, dev)
     total_steps = sum_over_ranks(float(N * args.steps), dist, dev)
     value = total_steps / t_dev
-    on_palm = float((sim.site_xpos[:, model_site(model, "cube:center"), 2] > 0.04).float().mean().item())
-    warn = int(sim.warn.max().item())
+    on_palm = float(wl.facade.on_palm(sim.site_xpos).float().mean().item())
+    warn = int(warn.item())
 
     # ---- timed region 2: end to end through the public API with host buffers
     h_ctrl = torch.empty(N, nu, dtype=torch.float32).pin_memory()
     h_q = torch.empty(N, nq, dtype=torch.float32).pin_memory()
     h_v = torch.empty(N, nv, dtype=torch.float32).pin_memory()
-    h_ctrl.copy_(sim.ctrl)
+    h_q.copy_(sim.qpos)
     rng = np.random.RandomState(rank_seed(99, rank) % (2 ** 31))
-    lo_h, hi_h, half_h = lo.cpu().numpy(), hi.cpu().numpy(), half.cpu().numpy()
+    P = wl.facade.P.cpu().numpy()
+    hidx = wl.facade.hand_qpos_idx.cpu().numpy()
+    lo_h, hi_h = wl.facade.ctrl_lo.cpu().numpy(), wl.facade.ctrl_hi.cpu().numpy()
+    half_h = 0.5 * (hi_h - lo_h)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -330,7 +393,8 @@ def run_gpu_arm(args):
     acts = [(rng.uniform(-1, 1, (N, nu)).astype(np.float32)) for _ in range(args.steps)]
     e0.record()
     for k in range(args.steps):
-        np.clip(h_ctrl.numpy() + ACTION_SCALE * acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
+        # the host computes this step's control from the observation it read back last step
+        np.clip(h_q.numpy()[:, hidx] @ P.T + acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
         sim.ctrl.copy_(h_ctrl, non_blocking=True)       # H2D of this step's inputs
         sim.step()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
@@ -346,22 +410,35 @@ def run_gpu_arm(args):
         kernel_s = statistics.mean(step_ms) / 1e3
         achieved = ALGO_BYTES_PER_ENV_STEP * N / kernel_s / 1e9
         info = sim.launch_info()
+        prof = newest_profile_metrics()
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": prof["dram_bytes"] * N / NENV_PER_GPU if prof else None,
+                "traffic_unit": "bytes per launch (dram__bytes_read+write of rg_step_kernel, ncu --set full; %s)" % (prof["file"] if prof else "no capture"),
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
+                "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
+                "note": "algorithmic 1664 B/env-step; the path is instruction-issue bound, not HBM bound (DESIGN.md): see fp32_issue_frac"}
+        if prof:
+            # SURVEY 8(d) asks for both fractions: warp instructions issued per second against 148 SMs x 4 schedulers x clock
+            inst_per_env_step = prof["warp_inst"] / NENV_PER_GPU
+            per_gpu = value / world
+            roof["fp32_issue_frac"] = inst_per_env_step * per_gpu / (148 * 4 * sm_mhz * 1e6)
+            roof["warp_inst_per_env_step"] = inst_per_env_step
         line = {
-            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "dactyl/locked (BASELINE.json configs[1]): ShadowHand + locked cube, nq38/nv36/nu20, batch 8192 per GPU, "
-                                   "10 substeps of 0.008 s + forward per env-step, relative random actions (ctrl += 0.3*a*half-range)",
+            "config": {"workload": "dactyl/locked (BASELINE.json configs[1], SURVEY 8(d) cfg 2): ShadowHand + locked cube, nq38/nv36/nu20, batch %d per GPU, "
+                                   "10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): ctrl = clip(P qpos + a*range/2), "
+                                   "auto-reset of environments whose cube left the palm" % N,
                        "envs_per_gpu": N, "substeps": NSUB, "physics_substeps_per_s": value * NSUB,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
-                       "launch": info, "cubes_on_palm_at_end": on_palm, "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
+                       "launch": info, "cubes_on_palm_at_end": on_palm, "resets_in_timed_region_rank0": int(resets.item()),
+                       "mean_contacts": float(ncon_sum.item()) / args.steps, "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
             "gpu_launches": 2 * args.steps * world,   # per step: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch)
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch (ncu, profiles/r1i_ncu_metrics.csv)",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
-                         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
-                         "note": "algorithmic 1664 B/env-step; the path is FP32-issue/latency bound, not HBM bound (DESIGN.md)"},
+            "roofline": roof,
         }
         if world == 1:
             try:
@@ -383,8 +460,9 @@ def model_site(model, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 8192 envs per GPU; strong: 8192 envs per box")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

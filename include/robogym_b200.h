@@ -24,7 +24,9 @@
  * Conventions: every function returns 0 on success or a negative code and sets a thread-local
  * message readable with rg_last_error(); no exceptions or callbacks cross the ABI.  All device
  * work is stream-ordered and asynchronous on the stream the caller passes (a cudaStream_t as
- * void*); the library never synchronises and never allocates or frees the bound tensors.
+ * void*).  The set-up calls (rg_model_load, rg_batch_create[_ex]) allocate engine-internal buffers and may synchronise with
+ * the device; the stepping calls (rg_step, rg_step_subset, rg_forward, rg_reset, rg_model_set_field_async) never do, and
+ * nothing ever allocates or frees the bound tensors.
  * State layout: row-major [nenv][n] float32 (int32 for ncon/warn); one environment per row.
  */
 #ifndef ROBOGYM_B200_H
@@ -54,26 +56,49 @@ enum rg_field {
   RG_FIELD_GEOM_XPOS = 11, /* [nenv][ngeom*3]     out    (optional) */
   RG_FIELD_ACT_FORCE = 12, /* [nenv][nu]          out    (optional) */
   RG_FIELD_QACC = 13,      /* [nenv][nv]          out    (optional) */
-  RG_FIELD_CONTACT = 14,   /* [nenv][RG_MAX_CONTACTS][4] out (optional): geom1, geom2, dist, condim */
+  RG_FIELD_CONTACT = 14,   /* [nenv][contact capacity][4] out (optional): geom1, geom2, dist, condim (rg_batch_capacity) */
   RG_FIELD_NCON = 15,      /* [nenv] int32        out    (optional) */
-  RG_FIELD_WARN = 16,      /* [nenv] int32        in/out (optional): bit0 contact buffer full, bit1 row buffer full, bit2 bad state -> reset */
-  RG_FIELD_DBG = 17,       /* [nenv][rg_dbg_size] out    (optional): stage dump used by the parity tests */
-  RG_NFIELDS = 18
+  RG_FIELD_WARN = 16,      /* [nenv] int32        in/out (optional): bit0 contact buffer full, bit1 row buffer full, bit2 bad state -> reset,
+                              bit3 MPR, bit4 tendon Jacobian too dense, bit5 a contact touched more dofs than the batch allows (dropped) */
+  RG_FIELD_DBG = 17,       /* [nenv][rg_batch_dbg_size] out (optional): stage dump used by the parity tests */
+  RG_FIELD_BODY_XVEL = 18, /* [nenv][nbody*6]     out    (optional): angular, linear velocity of every body frame in world axes
+                              = data.get_body_xvelr / get_body_xvelp (robogym/robot/ur16e/mujoco/joint_controlled_arm.py:32,
+                              robogym/envs/rearrange/simulation/base.py:465-472) */
+  RG_NFIELDS = 19
 };
-#define RG_MAX_CONTACTS 32
+#define RG_MAX_CONTACTS 32   /* DEFAULT contact capacity of a batch (rg_batch_create); rg_batch_create_ex picks another */
 #define RG_MAX_PARAM_OVERRIDES 16
 
 int rg_model_load(const void* blob, size_t len, int device, rg_model** out);
 void rg_model_destroy(rg_model* m);
 /* value of a dimension of rg_model_fields.h (nq, nv, nu, nbody, ...) or -1 */
 int rg_model_dim(const rg_model* m, const char* name);
-/* overwrite a model array (host float64 / int32 values, `count` elements) and re-upload it */
+/* id of a named object, as mjModel.body_name2id / joint_name2id / geom_name2id / site_name2id / actuator_name2id /
+ * tendon_name2id / sensor_name2id do (robogym reaches them through sim.model); objtype is "body", "joint",
+ * "geom", "site", "actuator", "tendon", "mesh", "sensor" or "equality".  -1 when the name is unknown or the blob was
+ * packed without its name tables. */
+int rg_model_name2id(const rg_model* m, const char* objtype, const char* name);
+const char* rg_model_id2name(const rg_model* m, const char* objtype, int id);   /* NULL when out of range; "" for an unnamed object */
+/* overwrite a model array (host float64 / int32 values, `count` elements) and re-upload it.  The upload is ordered on
+ * `stream` (set_field: the legacy default stream): launches queued before it keep the old values.  The host buffers may be
+ * reused as soon as the call returns.  Do not call it from two threads for the same model at once. */
 int rg_model_set_field(rg_model* m, const char* name, const void* data, size_t count);
+int rg_model_set_field_async(rg_model* m, const char* name, const void* data, size_t count, void* stream);
 /* floats per environment of the RG_FIELD_DBG dump; bytes of shared memory per environment (one warp) */
 int rg_dbg_size(const rg_model* m);
 int rg_scratch_bytes(const rg_model* m);
 
 int rg_batch_create(const rg_model* m, int nenv, rg_batch** out);
+/* The same with explicit capacities per environment (0 = default): contacts kept (the reference compiles nconmax=100,
+ * robogym/assets/xmls/robot/shadowhand/assets.xml:6), single-row constraint elements = friction-loss + limit rows
+ * (reference njmax=500 counts these plus the contact rows, assets.xml:5), dofs one contact may touch (<= 32).  Larger
+ * capacities mean more shared memory per environment, i.e. fewer environments resident per SM; overflow at run time sets
+ * a warning bit (RG_FIELD_WARN) and drops the surplus, like mj_warning does. */
+int rg_batch_create_ex(const rg_model* m, int nenv, int contact_capacity, int row_capacity, int dofs_per_contact, rg_batch** out);
+int rg_batch_capacity(const rg_batch* b, int* contacts, int* rows, int* dofs_per_contact);
+/* floats per environment of this batch's RG_FIELD_DBG dump; shared-memory bytes per environment */
+int rg_batch_dbg_size(const rg_batch* b);
+int rg_batch_scratch_bytes(const rg_batch* b);
 void rg_batch_destroy(rg_batch* b);
 int rg_batch_bind(rg_batch* b, int field, void* device_ptr);
 /* Per-environment override of a float model array (domain randomisation, SURVEY 5.6: robogym's wrappers write

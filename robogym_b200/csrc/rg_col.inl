@@ -72,7 +72,6 @@ RG_DEV void rg_support_prim(const RgGeomView& v, const float* dl, float* loc) {
  * convex-convex narrow phase the scan of one hull is shared by the RG_GRP lanes that work on the pair: lane `gl` looks
  * at vertices gl, gl + RG_GRP, ... and the group's arg-max picks the winner (ties: the lower vertex id, which is what a
  * plain first-maximum loop returns). */
-#define RG_GRP 8
 RG_DEV void rg_hull_scan(const RG_MODEL_T& m, const RgGeomView& v, const float* dl, int first, int stride, float& best, int& idx) {
   best = -3.0e38f; idx = 0x7fffffff;
   RG_STAT(rg_stat_climb += (v.vnum - first + stride - 1) / stride;)
@@ -81,6 +80,25 @@ RG_DEV void rg_hull_scan(const RG_MODEL_T& m, const RgGeomView& v, const float* 
     RG_LDG4(m.mesh_vert4, v.vadr + k, p);
     const float d = p[0] * dl[0] + p[1] * dl[1] + p[2] * dl[2];
     if (d > best) { best = d; idx = k; }
+  }
+}
+/* both hulls of a pair in one loop, so that the loads of the two scans are in flight together (the scan is a chain of
+   L2 round trips, not arithmetic); same visiting order per hull as rg_hull_scan */
+RG_DEV void rg_hull_scan2(const RG_MODEL_T& m, const RgGeomView& v1, const float* d1, const RgGeomView& v2, const float* d2, int first, int stride,
+                          float& best1, int& idx1, float& best2, int& idx2) {
+  best1 = best2 = -3.0e38f; idx1 = idx2 = 0x7fffffff;
+  const int n1 = v1.type == RG_GEOM_MESH ? v1.vnum : 0, n2 = v2.type == RG_GEOM_MESH ? v2.vnum : 0;
+  const int n = n1 > n2 ? n1 : n2;
+  RG_STAT(rg_stat_climb += (n1 - first + stride - 1) / stride + (n2 - first + stride - 1) / stride;)
+  RG_UNROLL4 for (int k = first; k < n; k += stride) {
+    float p[4], q[4];
+    const int k1 = k < n1 ? k : 0, k2 = k < n2 ? k : 0;     /* clamped: a repeated vertex 0 never wins the strict comparison */
+    RG_LDG4(m.mesh_vert4, v1.vadr + k1, p);
+    RG_LDG4(m.mesh_vert4, v2.vadr + k2, q);
+    const float e1 = p[0] * d1[0] + p[1] * d1[1] + p[2] * d1[2];
+    const float e2 = q[0] * d2[0] + q[1] * d2[1] + q[2] * d2[2];
+    if (k < n1 && e1 > best1) { best1 = e1; idx1 = k; }
+    if (k < n2 && e2 > best2) { best2 = e2; idx2 = k; }
   }
 }
 RG_DEV void rg_support_world(const RgGeomView& v, const float* loc, const float* dir, float* res) {
@@ -468,16 +486,15 @@ RG_DEV_NOINLINE void rg_mpr_batch(const RgCtx c, const int* cand2, const int* li
       rg_mulmatT3(d1, S.o1.mat, S.dir);
       rg_mulmatT3(d2, S.o2.mat, S.dir);
       d2[0] = -d2[0]; d2[1] = -d2[1]; d2[2] = -d2[2];
-      if (S.o1.type == RG_GEOM_MESH) rg_hull_scan(m, S.o1, d1, gl, RG_GRP, LV(b1), LV(i1));
-      if (S.o2.type == RG_GEOM_MESH) rg_hull_scan(m, S.o2, d2, gl, RG_GRP, LV(b2), LV(i2));
+      rg_hull_scan2(m, S.o1, d1, S.o2, d2, gl, RG_GRP, LV(b1), LV(i1), LV(b2), LV(i2));
     }
     LV(busy) = S.state < RG_MPR_DONE;
     RG_PHASE_END
     next += wtot / RG_GRP;
     if (!RG_WARP_OR(busy)) break;
     RG_STAT(rg_stat_x[4]++;)
-    RG_GROUP8_ARGMAX(b1, i1);
-    RG_GROUP8_ARGMAX(b2, i2);
+    RG_GROUP_ARGMAX(b1, i1);
+    RG_GROUP_ARGMAX(b2, i2);
     RG_PHASE_BEGIN
     RgMpr& S = LV(st);
     if (S.state < RG_MPR_DONE) {
@@ -520,7 +537,7 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
   int* cand = (int*)(s + L.cand);
   int* cand2 = (int*)(s + L.cand2);
   int ncon = 0, n1 = 0, n2 = 0, k0 = 0, warn = 0, work = 0;
-  const int cap = (m.nconmax > 0 && m.nconmax < RG_NCON) ? m.nconmax : RG_NCON;
+  const int cap = (m.nconmax > 0 && m.nconmax < L.ncon) ? m.nconmax : L.ncon;
   const int enabled = !(m.opt_disableflags[0] & (RG_DSBL_CONTACT | RG_DSBL_CONSTRAINT));
   RG_PROF_BEGIN
   while (enabled && (k0 < m.npair || n1 > 0 || n2 > 0)) {

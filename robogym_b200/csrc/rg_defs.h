@@ -103,17 +103,24 @@ __device__ __forceinline__ void rg_stage_sync() {
 
 #define RG_MINVAL 1e-15f
 #define RG_EPS 1.1920929e-07f
+/* Capacities are RUN-TIME parameters of a batch (rg_batch_create_ex): contacts kept per environment, single-row constraint
+ * elements (friction loss + limits), dofs one contact may touch.  The defaults below are what the dactyl/locked model
+ * needs in practice; the reference's own sizes (nconmax=100, njmax=500, assets.xml:5-6) are available at the price of
+ * fewer resident environments per SM.  Overflow sets a warning bit, it never corrupts memory. */
 #ifndef RG_NCON
 #define RG_NCON 32
-#endif                   /* contacts kept per environment (reference nconmax=100, assets.xml:6); overflow sets a warning bit */
+#endif
 #ifndef RG_COST_ITER
 #define RG_COST_ITER 3   /* weight of one Newton iteration against one narrow-phase pair in the work estimate (rg_order_kernel) */
 #endif
 #ifndef RG_NEL
 #define RG_NEL 64
-#endif                   /* single-row constraint elements (friction loss + limits) */
+#endif
 #define RG_CON_STRIDE 24
 #define RG_CPRM 6           /* per-contact solver parameters: D, dim, B, K*imp*r, number of dofs, their sign bits (solimp[5] is staged there by the collision stage) */
+#ifndef RG_GRP
+#define RG_GRP 8           /* lanes that share one pair in the convex-convex narrow phase (rg_mpr_batch) */
+#endif
 #define RG_NSEP 64         /* words of the per-environment separating-axis cache (rg_mpr_batch) */
 #define RG_TJ 8           /* max non-zeros of one tendon's Jacobian row */
 #ifdef RG_PROFILE
@@ -126,7 +133,9 @@ __device__ __forceinline__ void rg_stage_sync() {
  * free objects last): Cholesky then eliminates children before parents, so the tree-structured part
  * of the matrix produces no fill-in and the envelope of most rows is a handful of entries. */
 #define RG_HR(nv, i, j) ((i) <= (j) ? RG_TRI((nv) - 1 - (i), (nv) - 1 - (j)) : RG_TRI((nv) - 1 - (j), (nv) - 1 - (i)))
-#define RG_TILE 16       /* max dofs touched by one contact */
+#ifndef RG_TILE
+#define RG_TILE 16       /* default for the dofs one contact may touch (<= 32: their signs travel in one word) */
+#endif
 
 enum { RG_JNT_FREE = 0, RG_JNT_BALL = 1, RG_JNT_SLIDE = 2, RG_JNT_HINGE = 3 };
 enum { RG_GEOM_PLANE = 0, RG_GEOM_SPHERE = 2, RG_GEOM_CAPSULE = 3, RG_GEOM_ELLIPSOID = 4, RG_GEOM_CYLINDER = 5, RG_GEOM_BOX = 6, RG_GEOM_MESH = 7 };
@@ -137,7 +146,7 @@ enum { RG_DSBL_CONSTRAINT = 1, RG_DSBL_EQUALITY = 2, RG_DSBL_FRICTIONLOSS = 4, R
        RG_DSBL_PASSIVE = 32, RG_DSBL_GRAVITY = 64, RG_DSBL_CLAMPCTRL = 128, RG_DSBL_WARMSTART = 256,
        RG_DSBL_ACTUATION = 1024, RG_DSBL_REFSAFE = 2048 };
 enum { RG_EL_FLOSS = 0, RG_EL_JLIMIT = 1, RG_EL_TLIMIT = 2 };
-enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8, RG_WARN_TENDON_NNZ = 16 };
+enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8, RG_WARN_TENDON_NNZ = 16, RG_WARN_DOFS_FULL = 32 };
 
 /* Device view of the compiled model: fp32 / int32 copies of every rg_model_fields.h array. */
 struct RgModel {
@@ -170,6 +179,7 @@ struct RgLayout {
   int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
   int el_i, el_D, el_floss, el_jar, el_jv, el_f;
   int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof, sep, stage;
+  int ncon, nel, tile;               /* capacities: contacts, single-row elements, dofs per contact */
   int total;
 };
 
@@ -255,17 +265,17 @@ RG_DEV int rg_warp_excl_scan(int v, int* total) {
 #define RG_WARP_ISUM(x) rg_warp_isum(x)
 #define RG_WARP_BCAST(x, src) rg_warp_bcast(x, src)
 #define RG_WARP_SCAN(cnt, pos, total) pos = rg_warp_excl_scan(cnt, &(total))
-/* arg-max over each group of 8 consecutive lanes: every lane of a group ends up with the group's best value and the
+/* arg-max over each group of RG_GRP consecutive lanes: every lane of a group ends up with the group's best value and the
    index that goes with it (ties: the smaller index, so the answer does not depend on which lane held it) */
-RG_DEV void rg_group8_argmax(float& v, int& i) {
+RG_DEV void rg_group_argmax(float& v, int& i) {
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
+  for (int o = RG_GRP / 2; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, v, o);
     const int oi = __shfl_xor_sync(0xffffffffu, i, o);
     if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
   }
 }
-#define RG_GROUP8_ARGMAX(v, i) rg_group8_argmax(v, i)
+#define RG_GROUP_ARGMAX(v, i) rg_group_argmax(v, i)
 #else
 /* ---- warp helpers (emulation: identical combination order) ---- */
 static inline float rg_emu_sum(const float* x) {
@@ -284,14 +294,14 @@ static inline int rg_emu_scan(const int* c, int* pos) { int s = 0; for (int l = 
 #define RG_WARP_ISUM(x) rg_emu_isum(x)
 #define RG_WARP_BCAST(x, src) (x[src])
 #define RG_WARP_SCAN(cnt, pos, total) total = rg_emu_scan(cnt, pos)
-static inline void rg_emu_group8_argmax(float* v, int* i) {
-  for (int g = 0; g < 32; g += 8) {
+static inline void rg_emu_group_argmax(float* v, int* i) {
+  for (int g = 0; g < 32; g += RG_GRP) {
     float bv = v[g]; int bi = i[g];
-    for (int l = g + 1; l < g + 8; l++) if (v[l] > bv || (v[l] == bv && i[l] < bi)) { bv = v[l]; bi = i[l]; }
-    for (int l = g; l < g + 8; l++) { v[l] = bv; i[l] = bi; }
+    for (int l = g + 1; l < g + RG_GRP; l++) if (v[l] > bv || (v[l] == bv && i[l] < bi)) { bv = v[l]; bi = i[l]; }
+    for (int l = g; l < g + RG_GRP; l++) { v[l] = bv; i[l] = bi; }
   }
 }
-#define RG_GROUP8_ARGMAX(v, i) rg_emu_group8_argmax(v, i)
+#define RG_GROUP_ARGMAX(v, i) rg_emu_group_argmax(v, i)
 #endif
 
 /* ---- small vector math ---- */
@@ -351,6 +361,7 @@ RG_DEV void rg_mulmatT3(float* r, const float* m, const float* v) {
   r[0] = x; r[1] = y; r[2] = z;
 }
 RG_DEV int rg_f2i(float f) { int i; memcpy(&i, &f, 4); return i; }
+RG_DEV float rg_i2f(int i) { float f; memcpy(&f, &i, 4); return f; }
 RG_DEV float rg_clamp(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 RG_DEV int rg_dof_in_body(const RG_MODEL_T& m, int body, int dof) {
   return ((unsigned)m.body_dofmask[body * m.nmaskw + (dof >> 5)] >> (dof & 31)) & 1u;

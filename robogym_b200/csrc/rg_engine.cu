@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
 
   const int warp = threadIdx.x >> 5;
   if (warp >= args.warps) return;
-  float* s = scratch0 + (size_t)warp * args.L.total;
+  float* s = scratch0 + (size_t)warp * args.L.total;   /* L.total is a multiple of 4 floats: every per-warp area stays 16-byte aligned */
   /* with per-env overrides every warp keeps its own model view + a copy of this env's rows after the scratch */
   RgModelDev* wm = sm;
   float* wover = nullptr;
@@ -162,6 +162,7 @@ __global__ void rg_reset_kernel(RgModel m, RgBatchIO io, const uint8_t* mask) {
   for (int i = threadIdx.x; i < m.nv; i += blockDim.x) { io.qvel[(size_t)env * m.nv + i] = 0.0f; io.warm[(size_t)env * m.nv + i] = 0.0f; }
   for (int i = threadIdx.x; i < m.nu; i += blockDim.x) io.ctrl[(size_t)env * m.nu + i] = 0.0f;
   for (int i = threadIdx.x; i < 3 * m.nu; i += blockDim.x) io.pid[(size_t)env * 3 * m.nu + i] = 0.0f;
+  if (io.xfrc) for (int i = threadIdx.x; i < 6 * m.nbody; i += blockDim.x) ((float*)io.xfrc)[(size_t)env * 6 * m.nbody + i] = 0.0f;   /* mj_resetData clears xfrc_applied too */
   if (threadIdx.x == 0) { if (io.time) io.time[env] = 0.0f; if (io.warn) io.warn[env] = 0; }
 }
 
@@ -245,6 +246,7 @@ struct rg_batch {
   int* d_order = nullptr;  /* slot -> environment of the next launch */
   int* d_cost = nullptr;   /* work estimate written by the last launch */
   int* d_subset = nullptr; /* [nenv + 1] slot table of a subset launch, followed by its length */
+  RgLayout L;              /* scratch layout for this batch's capacities */
   int* d_sep = nullptr;    /* [nenv][RG_NSEP] separating-axis cache of the narrow phase (speeds it up; results do not depend on it) */
   int balance = 1;
 };
@@ -306,7 +308,23 @@ int rg_model_dim(const rg_model* m, const char* name) {
   return -1;
 }
 
-int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t count) {
+int rg_model_name2id(const rg_model* m, const char* objtype, const char* name) {
+  if (!m || !objtype || !name) return -1;
+  auto it = m->hm.names.find(objtype);
+  if (it == m->hm.names.end()) return -1;
+  for (size_t i = 0; i < it->second.size(); i++) if (it->second[i] == name) return (int)i;
+  return -1;
+}
+const char* rg_model_id2name(const rg_model* m, const char* objtype, int id) {
+  if (!m || !objtype) return nullptr;
+  auto it = m->hm.names.find(objtype);
+  if (it == m->hm.names.end() || id < 0 || (size_t)id >= it->second.size()) return nullptr;
+  return it->second[(size_t)id].c_str();
+}
+
+int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t count) { return rg_model_set_field_async(mm, name, data, count, nullptr); }
+
+int rg_model_set_field_async(rg_model* mm, const char* name, const void* data, size_t count, void* stream) {
   if (!mm || !name || !data) return rg_fail(-1, "rg_model_set_field: null argument");
   RgModel& m = mm->hm.view;
 #define RG_DIM(n) const int n = m.n; (void)n;
@@ -341,11 +359,13 @@ int rg_model_set_field(rg_model* mm, const char* name, const void* data, size_t 
   }
   const size_t off = (const char*)hptr - mm->hm.arena.data();
   RG_CUDA(cudaSetDevice(mm->device));
-  RG_CUDA(cudaMemcpy(mm->d_arena + off, hptr, 4 * n, cudaMemcpyHostToDevice));
+  /* stream-ordered: launches already queued on `stream` still see the old values, later ones the new; the host copy is
+     pageable, so the runtime stages it before returning and `data` / the host arena may change right away */
+  RG_CUDA(cudaMemcpyAsync(mm->d_arena + off, hptr, 4 * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return 0;
 }
 
-int rg_dbg_size(const rg_model* m) { return m ? ::rg_dbg_size(m->hm.view) : -1; }
+int rg_dbg_size(const rg_model* m) { return m ? ::rg_dbg_size(m->hm.view, m->L.ncon) : -1; }
 int rg_scratch_bytes(const rg_model* m) { return m ? 4 * m->L.total : -1; }
 
 /* launch geometry: warps per CTA, dynamic shared memory, CTA count (re-run when the override set changes) */
@@ -362,7 +382,7 @@ static int rg_batch_size(rg_batch* b) {
   const int model_bytes = RG_MODEL_DEV_BYTES;
   const int fixed = model_bytes + (int)((m->hm.small_bytes + 127) & ~(size_t)127) + 64;
   /* with per-env parameter overrides every warp also holds its own model view + this env's rows */
-  const int per_warp = 4 * m->L.total + (b->nover > 0 ? model_bytes + 4 * b->over_floats : 0);
+  const int per_warp = 4 * b->L.total + (b->nover > 0 ? model_bytes + 4 * b->over_floats : 0);
   int warps = (maxsmem - fixed) / per_warp;
   if (warps < 1) return rg_fail(-3, "rg_batch: model scratch does not fit in shared memory");
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
@@ -395,11 +415,14 @@ static int rg_batch_size(rg_batch* b) {
   return 0;
 }
 
-int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
-  if (!m || !out || nenv <= 0) return rg_fail(-1, "rg_batch_create: bad argument");
+int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) { return rg_batch_create_ex(m, nenv, 0, 0, 0, out); }
+
+int rg_batch_create_ex(const rg_model* m, int nenv, int contact_capacity, int row_capacity, int dofs_per_contact, rg_batch** out) {
+  if (!m || !out || nenv <= 0 || contact_capacity < 0 || row_capacity < 0 || dofs_per_contact < 0) return rg_fail(-1, "rg_batch_create: bad argument");
   rg_batch* b = new rg_batch();
   b->model = m;
   b->nenv = nenv;
+  b->L = rg_make_layout(m->hm.view, contact_capacity ? contact_capacity : RG_NCON, row_capacity ? row_capacity : RG_NEL, dofs_per_contact ? dofs_per_contact : RG_TILE);
   for (int i = 0; i < RG_NFIELDS; i++) b->ptr[i] = nullptr;
   const int rc = rg_batch_size(b);
   if (rc) { delete b; return rc; }
@@ -409,7 +432,7 @@ int rg_batch_create(const rg_model* m, int nenv, rg_batch** out) {
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_subset, sizeof(int) * ((size_t)nenv + 1));
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_sep, sizeof(int) * (size_t)nenv * RG_NSEP);
-  if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, b->d_sep, nenv); e = cudaDeviceSynchronize(); }
+  if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, b->d_sep, nenv); e = cudaDeviceSynchronize(); }   /* set-up call: may synchronise (the stepping calls never do) */
   if (e != cudaSuccess) { std::string msg = std::string("rg_batch_create: CUDA: ") + cudaGetErrorString(e); rg_batch_destroy(b); return rg_fail(-2, msg); }
   *out = b;
   return 0;
@@ -479,6 +502,16 @@ int rg_batch_bind_param(rg_batch* b, const char* name, void* p) {
   return rg_batch_size(b);
 }
 
+int rg_batch_capacity(const rg_batch* b, int* contacts, int* rows, int* dofs_per_contact) {
+  if (!b) return -1;
+  if (contacts) *contacts = b->L.ncon;
+  if (rows) *rows = b->L.nel;
+  if (dofs_per_contact) *dofs_per_contact = b->L.tile;
+  return 0;
+}
+int rg_batch_dbg_size(const rg_batch* b) { return b ? ::rg_dbg_size(b->model->hm.view, b->L.ncon) : -1; }
+int rg_batch_scratch_bytes(const rg_batch* b) { return b ? 4 * b->L.total : -1; }
+
 int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
   if (!b) return -1;
   if (ctas) *ctas = b->ctas;
@@ -498,6 +531,7 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   io.geom_xpos = (float*)b->ptr[RG_FIELD_GEOM_XPOS]; io.act_force = (float*)b->ptr[RG_FIELD_ACT_FORCE]; io.qacc = (float*)b->ptr[RG_FIELD_QACC];
   io.cost = b->balance ? b->d_cost : nullptr;
   io.sep = b->d_sep;
+  io.body_xvel = (float*)b->ptr[RG_FIELD_BODY_XVEL];
   io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;
 }
@@ -508,7 +542,7 @@ static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_
   const int rc = rg_fill_io(b, args.io);
   if (rc) return rc;
   args.m = b->model->dev;
-  args.L = b->model->L;
+  args.L = b->L;
   args.arena = b->model->d_arena;
   args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
   args.nover = b->nover;

@@ -8,6 +8,7 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -18,6 +19,7 @@ struct RgHostModel {
   RgModel view;                 /* pointers into `arena` (host) */
   std::vector<size_t> offsets;  /* byte offset of every RgModel pointer field, in struct order */
   size_t small_bytes = 0;
+  std::map<std::string, std::vector<std::string>> names;   /* objtype -> names ("" = unnamed), from the blob's RGNAMES1 section */
 };
 
 static inline size_t rg_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -59,6 +61,34 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
 #undef RG_I
 #undef RG_F
   if (src > len) { err = "model blob truncated"; return false; }
+  /* optional name tables behind the arrays (mjModel.*_name2id): RGNAMES1, ntypes, then type\0 count name\0 ... */
+  hm.names.clear();
+  {
+    size_t q = (src + 7) & ~(size_t)7;
+    if (q + 12 <= len && !memcmp(p + q, "RGNAMES1", 8)) {
+      int nt;
+      memcpy(&nt, p + q + 8, 4);
+      q += 12;
+      for (int t = 0; t < nt && q < len; t++) {
+        const size_t tl = strnlen(p + q, len - q);
+        if (q + tl + 5 > len) { err = "model blob: bad name section"; return false; }
+        std::string typ(p + q, tl);
+        q += tl + 1;
+        int cnt;
+        memcpy(&cnt, p + q, 4);
+        q += 4;
+        std::vector<std::string>& v = hm.names[typ];
+        for (int i = 0; i < cnt; i++) {
+          if (q >= len) { err = "model blob: bad name section"; return false; }
+          const size_t nl = strnlen(p + q, len - q);
+          v.emplace_back(p + q, nl);
+          q += nl + 1;
+        }
+      }
+    }
+  }
+  /* features the compiler can describe but this engine does not simulate: refuse them instead of stepping wrong physics */
+  if (m.nmocap > 0) { err = "model uses mocap bodies: not supported by this engine"; return false; }
   /* derived arrays appended to the small section would disturb the order; put them right after the blob fields
      but account for them in small_bytes by placing them BEFORE the first big field. */
   size_t first_big = names.size();
@@ -95,6 +125,8 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
+  if (m.opt_cone[0] != 0) { err = "model uses elliptic friction cones (option cone=elliptic): not supported by this engine (pyramidal only)"; return false; }
+  for (int e = 0; e < m.neq; e++) if (m.eq_active[e]) { err = "model has active equality constraints: not supported by this engine"; return false; }
   int* subtree = (int*)(base + off_subtree);
   int* mrow = (int*)(base + off_mrow);
   for (int b = 0; b < m.nbody; b++) subtree[b] = 1;

@@ -121,7 +121,9 @@ RG_DEV void rg_H_from_M(const RgCtx c, const float* diag, float scale) {
   RG_PHASE_END
 }
 
-/* in-place envelope Cholesky of the lower triangle of A (row stride nv); env[i] = first nonzero column */
+/* in-place envelope Cholesky of the lower triangle of A (packed rows); env[i] = first nonzero column of row i.
+ * Row n (one past the matrix) carries the right-hand side: treating it as one more row of the matrix makes the factorisation
+ * deliver the forward substitution y = L^-1 b in that row for free (the same dot products, one more lane). */
 RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
@@ -131,30 +133,32 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
     RG_PHASE_BEGIN
     const int i = j + lane;
     float acc = 0.0f;
-    if (i < n && env[i] <= j) {
+    const int ei = i < n ? env[i] : 0;
+    if (i <= n && ei <= j) {
       const float* ri = s + A + RG_TRI(i, 0); const float* rj = s + A + RG_TRI(j, 0);
       acc = ri[j];
       float acc1 = 0.0f;
-      int k = env[i] > env[j] ? env[i] : env[j];
+      int k = ei > env[j] ? ei : env[j];
       RG_UNROLL2 for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
       if (k < j) acc -= ri[k] * rj[k];
       acc += acc1;
     }
     LV(sumv) = acc;
     RG_PHASE_END
-    /* the diagonal slot keeps 1/L[j][j]: the factor is only ever used to solve (rg_chol_solve) */
+    /* the diagonal slot keeps 1/L[j][j]: the factor is only ever used to solve (rg_chol_back) */
     const float inv = RG_RSQRT(fmaxf(RG_WARP_BCAST(sumv, 0), 1e-20f));
     RG_PHASE_BEGIN
     const int i = j + lane;
     if (i == j) s[A + RG_TRI(j, j)] = inv;
-    else if (i < n) s[A + RG_TRI(i, j)] = LV(sumv) * inv;
-    RG_NOUNROLL for (int i2 = i + 32; i2 < n; i2 += 32) {
+    else if (i <= n) s[A + RG_TRI(i, j)] = LV(sumv) * inv;
+    RG_NOUNROLL for (int i2 = i + 32; i2 <= n; i2 += 32) {
       float acc = 0.0f;
-      if (env[i2] <= j) {
+      const int e2 = i2 < n ? env[i2] : 0;
+      if (e2 <= j) {
         const float* ri = s + A + RG_TRI(i2, 0); const float* rj = s + A + RG_TRI(j, 0);
         acc = ri[j];
         float acc1 = 0.0f;
-        int k = env[i2] > env[j] ? env[i2] : env[j];
+        int k = e2 > env[j] ? e2 : env[j];
         RG_UNROLL2 for (; k + 1 < j; k += 2) { acc -= ri[k] * rj[k]; acc1 -= ri[k + 1] * rj[k + 1]; }
         if (k < j) acc -= ri[k] * rj[k];
         acc += acc1;
@@ -164,36 +168,37 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
     RG_PHASE_END
   }
 }
-/* x <- (L L^T)^-1 x ; uses `tmp` as staging */
-RG_DEV_NOINLINE void rg_chol_solve(const RgCtx c, int A, const int* env, int x, int tmp) {
+/* y <- L^-1 y for the right-hand side sitting in row n of A (only needed when a factor is REUSED: rg_cholesky does it
+   on the fly) */
+RG_DEV_NOINLINE void rg_chol_forward(const RgCtx c, int A, const int* env) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
+  const int x = A + RG_TRI(n, 0);
   for (int j = 0; j < n; j++) {
     RG_PHASE_BEGIN
     const float xj = s[x + j] * s[A + RG_TRI(j, j)];   /* diagonal slot = 1/L[j][j] */
-    if (lane == 0) s[tmp + j] = xj;
     RG_NOUNROLL for (int i = j + 1 + lane; i < n; i += 32)
       if (env[i] <= j) s[x + i] -= s[A + RG_TRI(i, j)] * xj;
     RG_PHASE_END
-  }
-  for (int j = n - 1; j >= 0; j--) {
-    RG_PHASE_BEGIN
-    const float xj = s[tmp + j] * s[A + RG_TRI(j, j)];
-    if (lane == 0) s[x + j] = xj;
-    RG_NOUNROLL for (int i = env[j] + lane; i < j; i += 32) s[tmp + i] -= s[A + RG_TRI(j, i)] * xj;
+    RG_PHASE_BEGIN   /* only now: the other lanes have read the old value */
+    if (lane == 0) s[x + j] *= s[A + RG_TRI(j, j)];
     RG_PHASE_END
   }
 }
-
-/* x <- reversed x (solver dof order <-> model dof order) */
-RG_DEV void rg_reverse_phase(const RgCtx c, int x) {
+/* out[n - 1 - j] <- (L^-T y)[j] with y in row n of A (row n is consumed): the solution leaves in model dof order */
+RG_DEV_NOINLINE void rg_chol_back(const RgCtx c, int A, const int* env, int out) {
   RG_LANE_DECL
   const int n = RG_MDEREF(c.mref).nv;
   float* s = RG_SCRATCH(c);
-  RG_PHASE_BEGIN
-  RG_NOUNROLL for (int d = lane; d < n / 2; d += 32) { const float a = s[x + d], b = s[x + n - 1 - d]; s[x + d] = b; s[x + n - 1 - d] = a; }
-  RG_PHASE_END
+  const int x = A + RG_TRI(n, 0);
+  for (int j = n - 1; j >= 0; j--) {
+    RG_PHASE_BEGIN
+    const float xj = s[x + j] * s[A + RG_TRI(j, j)];
+    if (lane == 0) s[out + (n - 1 - j)] = xj;
+    RG_NOUNROLL for (int i = env[j] + lane; i < j; i += 32) s[x + i] -= s[A + RG_TRI(j, i)] * xj;
+    RG_PHASE_END
+  }
 }
 
 /* ---------------------------------------------------------------- S8/S9 constraint elements */
@@ -220,7 +225,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     RG_PHASE_BEGIN
     const int d = base + lane;
     const int e = nel + LV(pos);
-    if (LV(cnt) && e < RG_NEL) {
+    if (LV(cnt) && e < L.nel) {
       float R, aref, B, KI;
       rg_row_params(c, m.dof_solref + 2 * d, m.dof_solimp + 5 * d, 0.0f, 0.0f, s[L.qvel + d], m.dof_invweight0[d], 1, &R, &aref, &B, &KI);
       el_i[e] = RG_EL_FLOSS + 8 * d;
@@ -253,7 +258,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
       int e = nel + LV(pos);
       for (int side = 0; side < 2; side++) {
         const float dist = side == 0 ? q - m.jnt_range[2 * j] : m.jnt_range[2 * j + 1] - q;
-        if (!(dist < m.jnt_margin[j]) || e >= RG_NEL) continue;
+        if (!(dist < m.jnt_margin[j]) || e >= L.nel) continue;
         const float sg = side == 0 ? 1.0f : -1.0f;
         float R, aref, B, KI;
         rg_row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, m.jnt_margin[j], sg * s[L.qvel + d], m.dof_invweight0[d], 0, &R, &aref, &B, &KI);
@@ -266,7 +271,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     RG_PHASE_END
     nel += tot;
   }
-  const int tl0 = nel < RG_NEL ? nel : RG_NEL;
+  const int tl0 = nel < L.nel ? nel : L.nel;
   /* tendon limits */
   for (int base = 0; on && !(flags & RG_DSBL_LIMIT) && base < m.ntendon; base += 32) {
     LANEVAR(int, cnt); LANEVAR(int, pos);
@@ -289,7 +294,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
       int e = nel + LV(pos);
       for (int side = 0; side < 2; side++) {
         const float dist = side == 0 ? len - m.tendon_range[2 * t] : m.tendon_range[2 * t + 1] - len;
-        if (!(dist < m.tendon_margin[t]) || e >= RG_NEL) continue;
+        if (!(dist < m.tendon_margin[t]) || e >= L.nel) continue;
         const float sg = side == 0 ? 1.0f : -1.0f;
         float R, aref, B, KI;
         rg_row_params(c, m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, dist, m.tendon_margin[t], sg * s[L.tvel + t], m.tendon_invweight0[t], 0, &R, &aref, &B, &KI);
@@ -301,7 +306,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     RG_PHASE_END
     nel += tot;
   }
-  if (nel > RG_NEL) { nel = RG_NEL; warn |= RG_WARN_ROWS_FULL; }
+  if (nel > L.nel) { nel = L.nel; warn |= RG_WARN_ROWS_FULL; }
   /* contacts: per-contact solver parameters; cu = B * (Jc qvel) + [K imp (dist-margin)] on the normal row */
   const int ncon = RG_SI(c, RG_S_NCON);
   RG_PHASE_BEGIN
@@ -324,7 +329,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     }
     prm[0] = 1.0f / R; prm[1] = (float)dim; prm[2] = B; prm[3] = KI;
     /* list of the dofs this contact touches (symmetric difference of the two bodies' ancestor sets) */
-    unsigned char* list = (unsigned char*)(s + L.cdof + 4 * k);
+    unsigned char* list = (unsigned char*)(s + L.cdof + ((L.tile + 3) >> 2) * k);
     int nd = 0;
     unsigned sgn = 0u;
     RG_NOUNROLL for (int w = 0; w < m.nmaskw && dim > 0; w++) {
@@ -333,12 +338,12 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
       while (bits) {
         const int bit = rg_ctz(bits);
         bits &= bits - 1;
-        if (nd < 16) { list[nd] = (unsigned char)(32 * w + bit); if ((m2 >> bit) & 1u) sgn |= 1u << nd; nd++; }
-        else { dim = 0; RG_SI(c, RG_S_WARN) |= RG_WARN_ROWS_FULL; } /* more than 16 dofs: not representable -> contact dropped, flagged */
+        if (nd < L.tile) { list[nd] = (unsigned char)(32 * w + bit); if ((m2 >> bit) & 1u) sgn |= 1u << nd; nd++; }
+        else { dim = 0; RG_SI(c, RG_S_WARN) |= RG_WARN_DOFS_FULL; } /* touches more dofs than the batch's per-contact capacity: dropped, flagged */
       }
     }
     if (dim == 0) { prm[1] = 0.0f; nd = 0; }
-    prm[4] = (float)nd; prm[5] = (float)(sgn & 0xffffu);
+    prm[4] = (float)nd; prm[5] = rg_i2f((int)sgn);   /* sign bits travel as raw bits */
     /* velocity part of jar */
     float v[6] = {0, 0, 0, 0, 0, 0};
     RG_NOUNROLL for (int i = 0; i < nd; i++) {
@@ -465,9 +470,9 @@ RG_DEV_NOINLINE void rg_J_mul_phase(const RgCtx c, int xoff, int el_out, int c_o
     const float* r = s + L.con + RG_CON_STRIDE * k;
     const int dim = (int)s[L.cprm + RG_CPRM * k + 1];
     float v[6] = {0, 0, 0, 0, 0, 0};
-    const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
+    const unsigned char* list = (const unsigned char*)(s + L.cdof + ((L.tile + 3) >> 2) * k);
     const int nd = (int)s[L.cprm + RG_CPRM * k + 4];
-    const unsigned sgn = (unsigned)s[L.cprm + RG_CPRM * k + 5];
+    const unsigned sgn = (unsigned)rg_f2i(s[L.cprm + RG_CPRM * k + 5]);
     RG_NOUNROLL for (int i = 0; i < nd; i++) {
       float col[6];
       const int d = list[i];
@@ -530,7 +535,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     float a = 0.0f;
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
-      s[L.search + (nv - 1 - d)] = -g;   /* right-hand side in the solver's reversed dof order */
+      s[L.search + d] = -g;
       a += g * g;
     }
     LV(gn) = a;
@@ -589,9 +594,9 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       if (!anyact) continue;
       /* tile: columns of Jc for the dofs this contact touches, and W Jc */
       int* tdof = (int*)(s + L.tileDof);
-      const unsigned char* list = (const unsigned char*)(s + L.cdof + 4 * k);
+      const unsigned char* list = (const unsigned char*)(s + L.cdof + ((L.tile + 3) >> 2) * k);
       int nd = (int)prm[4];
-      const unsigned sgn = (unsigned)prm[5];
+      const unsigned sgn = (unsigned)rg_f2i(prm[5]);
       RG_PHASE_BEGIN
       if (lane < nd) {
         float col[6] = {0, 0, 0, 0, 0, 0};
@@ -606,7 +611,6 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
       }
       RG_PHASE_END
-      if (nd > RG_TILE) nd = RG_TILE;
       RG_PHASE_BEGIN
       RG_NOUNROLL for (int p = lane; p < nd * nd; p += 32) {
         const int i = p / nd, j = p - i * nd;
@@ -628,19 +632,26 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     }
     RG_PHASE_END
     RG_PROFS(c, 11)
+    RG_PHASE_BEGIN   /* right-hand side -> row nv of H, in the solver's reversed dof order */
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.H + RG_TRI(nv, nv - 1 - d)] = s[L.search + d];
+    RG_PHASE_END
     rg_cholesky(c, L.H, env);
     RG_PROFS(c, 12)
     have_factor = 1; factor_sig = RG_SI(c, RG_S_SIG);
+    } else {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.H + RG_TRI(nv, nv - 1 - d)] = s[L.search + d];
+    RG_PHASE_END
+    rg_chol_forward(c, L.H, env);
     }
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
     { double cs = 0; for (int i = 0; i < (nv * (nv + 1)) / 2; i++) cs += s[L.H + i] * (1 + (i % 7)); int es = 0; for (int i = 0; i < nv; i++) es += env[i] * (i + 1); printf("    L checksum %.9g env %d\n", cs, es); }
 #endif
-    rg_chol_solve(c, L.H, env, L.search, L.tmp);
-    rg_reverse_phase(c, L.search);
+    rg_chol_back(c, L.H, env, L.search);
     RG_PROFS(c, 13)
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
     { /* finite-difference check of the Newton direction: g(q + eps*s) should be ~ (1-eps) g(q) when the active set holds */
-      static float q0[256], g0v[256], ma0[256], jar0[256], cu0[6 * RG_NCON], f0[256], cf0[6 * RG_NCON], qfc0[256];
+      static float q0[256], g0v[256], ma0[256], jar0[256], cu0[6 * 512], f0[256], cf0[6 * 512], qfc0[256];
       for (int d = 0; d < nv; d++) { q0[d] = s[L.qacc + d]; ma0[d] = s[L.Ma + d]; qfc0[d] = s[L.qfc + d]; g0v[d] = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d]; }
       for (int e = 0; e < nel; e++) { jar0[e] = s[L.el_jar + e]; f0[e] = s[L.el_f + e]; }
       for (int i = 0; i < 6 * ncon; i++) { cu0[i] = s[L.cu + i]; cf0[i] = s[L.cF + i]; }

@@ -16,7 +16,8 @@ struct RgBatchIO {
   const float* timestep;    /* [nenv] per-env opt.timestep override or nullptr */
   /* derived outputs (any may be nullptr) */
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
-  float* contact;           /* [nenv][RG_NCON][4] = geom1, geom2, dist, dim */
+  float* body_xvel;         /* [nenv][nbody][6]: angular then linear velocity of the body frame, world axes (data.get_body_xvelr / get_body_xvelp) */
+  float* contact;           /* [nenv][contact capacity][4] = geom1, geom2, dist, dim */
   int* ncon; int* warn;
   int* sep;                 /* [nenv][RG_NSEP] separating-axis cache carried from launch to launch (engine-internal, may be nullptr) */
   int* cost;                /* [nenv] work estimate of this launch (engine-internal, see rg_order_kernel) */
@@ -29,21 +30,26 @@ struct RgBatchIO {
 #define RG_HD __host__ __device__ static inline
 #endif
 template <class MT>
-RG_HD int rg_dbg_size(const MT& m) {
-  return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + RG_NCON * RG_CON_STRIDE + m.ntendon * m.nv + RG_NPROF;
+RG_HD int rg_dbg_size(const MT& m, int ncon_cap) {
+  return m.nv * m.nv + 6 * m.nv + m.ntendon + 2 * m.nu + 4 + ncon_cap * RG_CON_STRIDE + m.ntendon * m.nv + RG_NPROF;
 }
 
 static inline int rg_imax(int a, int b) { return a > b ? a : b; }
 
 /* host: compute the per-warp scratch layout for a model */
-static inline RgLayout rg_make_layout(const RgModel& m) {
+static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int nel = RG_NEL, int tile = RG_TILE) {
   RgLayout L;
   int o = 0;
+  if (tile > 32) tile = 32;
+  if (tile > m.nv) tile = m.nv > 0 ? m.nv : 1;
+  if (ncon < 1) ncon = 1;
+  if (nel < 1) nel = 1;
+  L.ncon = ncon; L.nel = nel; L.tile = tile;
 #define RG_ALLOC(field, n) do { L.field = o; o += (n); } while (0)   /* scalar 4-byte accesses only: no padding between arrays */
   RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
   RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
   RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
-  const int ntri = (m.nv * (m.nv + 1)) >> 1;
+  const int ntri = ((m.nv + 1) * (m.nv + 2)) >> 1;   /* packed lower triangle of H plus one extra row (the right-hand side rides along in the factorisation) */
   RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nM);   /* M: tree-sparse rows (rg_host.h), H: dense packed lower triangle */
   /* H aliases the smooth-dynamics temporaries */
   const int h0 = o;
@@ -54,21 +60,22 @@ static inline RgLayout rg_make_layout(const RgModel& m) {
   RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
   RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, RG_TJ * m.ntendon); RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
-  RG_ALLOC(con, RG_NCON * RG_CON_STRIDE); RG_ALLOC(cu, 6 * RG_NCON); RG_ALLOC(cw, 6 * RG_NCON); RG_ALLOC(cF, 6 * RG_NCON); RG_ALLOC(cprm, RG_CPRM * RG_NCON);
-  RG_ALLOC(el_i, RG_NEL); RG_ALLOC(el_D, RG_NEL); RG_ALLOC(el_floss, RG_NEL);
-  RG_ALLOC(el_jar, RG_NEL); RG_ALLOC(el_jv, RG_NEL); RG_ALLOC(el_f, RG_NEL);
-  RG_ALLOC(tileJ, 6 * RG_TILE); RG_ALLOC(tileWJ, 6 * RG_TILE); RG_ALLOC(tileDof, RG_TILE); RG_ALLOC(scal, 8 + RG_NPROF);
-  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, 4 * RG_NCON);
+  RG_ALLOC(con, ncon * RG_CON_STRIDE); RG_ALLOC(cu, 6 * ncon); RG_ALLOC(cw, 6 * ncon); RG_ALLOC(cF, 6 * ncon); RG_ALLOC(cprm, RG_CPRM * ncon);
+  const int nel64 = nel < 64 ? 64 : nel;   /* el_jv / el_f double as the broad-phase candidate lists (64 entries) */
+  RG_ALLOC(el_i, nel); RG_ALLOC(el_D, nel); RG_ALLOC(el_floss, nel);
+  RG_ALLOC(el_jar, nel); RG_ALLOC(el_jv, nel64); RG_ALLOC(el_f, nel64);
+  RG_ALLOC(tileJ, 6 * tile); RG_ALLOC(tileWJ, 6 * tile); RG_ALLOC(tileDof, tile); RG_ALLOC(scal, 8 + RG_NPROF);
+  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, ((tile + 3) >> 2) * ncon);   /* dof ids as bytes */
   RG_ALLOC(sep, RG_NSEP);   /* lives across the substeps of a launch, so it cannot share storage */
 #undef RG_ALLOC
   /* lifetimes that never overlap share storage: local frames (kinematics only) sit in the contact
      solver vectors, the broad-phase candidate lists in the row work arrays */
-  if (((3 * m.nbody + 3) & ~3) + 4 * m.nbody <= 12 * RG_NCON) { L.lpos = L.cu; L.lquat = L.cu + ((3 * m.nbody + 3) & ~3); }
+  if (((3 * m.nbody + 3) & ~3) + 4 * m.nbody <= 12 * ncon) { L.lpos = L.cu; L.lquat = L.cu + ((3 * m.nbody + 3) & ~3); }
   else { L.lpos = o; o += (3 * m.nbody + 3) & ~3; L.lquat = o; o += 4 * m.nbody; }
   L.cand = L.el_jv; L.cand2 = L.el_f;
   /* narrow-phase staging (32 x 8 results + 32 slots): in the contact solver vectors, which are idle during collision */
-  if (18 * RG_NCON >= 288) L.stage = L.cu; else { L.stage = o; o += 288; }
-  L.total = o;
+  if (18 * ncon >= 288) L.stage = L.cu; else { L.stage = o; o += 288; }
+  L.total = (o + 3) & ~3;   /* per-warp areas (and the per-warp model views behind them) stay 16-byte aligned */
   return L;
 }
 
@@ -153,17 +160,36 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   if (io.body_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.nbody; i += 32) io.body_xpos[(size_t)env * 3 * m.nbody + i] = s[L.xpos + i] + m.origin[i % 3];
   if (io.body_xquat) RG_NOUNROLL for (int i = lane; i < 4 * m.nbody; i += 32) io.body_xquat[(size_t)env * 4 * m.nbody + i] = s[L.xquat + i];
   if (io.geom_xpos) RG_NOUNROLL for (int i = lane; i < 3 * m.ngeom; i += 32) io.geom_xpos[(size_t)env * 3 * m.ngeom + i] = s[L.gxpos + i] + m.origin[i % 3];
+  if (io.body_xvel) RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
+    /* mj_objectVelocity(body, world axes): spatial velocity about the tree's reference point, moved to the body origin */
+    float V[6] = {0, 0, 0, 0, 0, 0};
+    RG_NOUNROLL for (int w = 0; w < m.nmaskw; w++) {
+      unsigned bits = (unsigned)m.body_dofmask[b * m.nmaskw + w];
+      while (bits) {
+        const int d = 32 * w + rg_ctz(bits);
+        bits &= bits - 1;
+        const float qd = s[L.qvel + d];
+        const float* Sd = s + L.S + 6 * d;
+        for (int k = 0; k < 6; k++) V[k] += Sd[k] * qd;
+      }
+    }
+    float rel[3], t[3];
+    rg_sub3(rel, s + L.xpos + 3 * b, rg_body_ref(c, b));
+    rg_cross(t, V, rel);
+    float* o = io.body_xvel + ((size_t)env * m.nbody + b) * 6;
+    o[0] = V[0]; o[1] = V[1]; o[2] = V[2]; o[3] = V[3] + t[0]; o[4] = V[4] + t[1]; o[5] = V[5] + t[2];
+  }
   if (io.act_force) RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) io.act_force[(size_t)env * m.nu + i] = s[L.aforce + i];
   if (io.qacc) RG_NOUNROLL for (int i = lane; i < m.nv; i += 32) io.qacc[(size_t)env * m.nv + i] = s[L.qacc + i];
   const int ncon = RG_SI(c, RG_S_NCON);
-  if (io.contact) RG_NOUNROLL for (int k = lane; k < RG_NCON; k += 32) {
-    float* o = io.contact + ((size_t)env * RG_NCON + k) * 4;
+  if (io.contact) RG_NOUNROLL for (int k = lane; k < L.ncon; k += 32) {
+    float* o = io.contact + ((size_t)env * L.ncon + k) * 4;
     const float* r = s + L.con + RG_CON_STRIDE * k;
     if (k < ncon) { o[0] = r[20]; o[1] = r[21]; o[2] = r[0]; o[3] = r[17]; } else { o[0] = o[1] = -1.0f; o[2] = 0.0f; o[3] = 0.0f; }
   }
   if (lane == 0) { if (io.ncon) io.ncon[env] = ncon; if (io.warn) io.warn[env] |= RG_SI(c, RG_S_WARN); if (io.cost) io.cost[env] = RG_SI(c, RG_S_WORK); }
   if (io.dbg) {
-    float* g = io.dbg + (size_t)env * rg_dbg_size(m);
+    float* g = io.dbg + (size_t)env * rg_dbg_size(m, L.ncon);
     const int nv = m.nv;
     int o = 0;
     RG_NOUNROLL for (int i = lane; i < nv * nv; i += 32) {   /* dense nv x nv from the tree-sparse rows */
@@ -184,8 +210,8 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
     o += 2 * m.nu;
     if (lane == 0) { g[o] = (float)ncon; g[o + 1] = (float)RG_SI(c, RG_S_NEL); g[o + 2] = (float)RG_SI(c, RG_S_NITER); g[o + 3] = (float)RG_SI(c, RG_S_WARN); }
     o += 4;
-    RG_NOUNROLL for (int i = lane; i < RG_NCON * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
-    o += RG_NCON * RG_CON_STRIDE;
+    RG_NOUNROLL for (int i = lane; i < L.ncon * RG_CON_STRIDE; i += 32) g[o + i] = s[L.con + i];
+    o += L.ncon * RG_CON_STRIDE;
     RG_NOUNROLL for (int i = lane; i < m.ntendon * nv; i += 32) g[o + i] = rg_tendon_J(c, i / nv, i % nv);
     o += m.ntendon * nv;
     RG_NOUNROLL for (int i = lane; i < RG_NPROF; i += 32) g[o + i] = s[L.scal + 8 + i];

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librobogym_b200.so"))  
 
 # enum rg_field (include/robogym_b200.h)
 (QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,
- ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG) = range(18)
+ ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG, BODY_XVEL) = range(19)
 MAX_CONTACTS = 32
 CON_STRIDE = 24
 
@@ -47,9 +47,17 @@ def lib():
         L.rg_model_destroy.argtypes = [vp]
         L.rg_model_dim.argtypes = [vp, ctypes.c_char_p]
         L.rg_model_set_field.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t]
+        L.rg_model_set_field_async.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_size_t, vp]
+        L.rg_model_name2id.argtypes = [vp, ctypes.c_char_p, ctypes.c_char_p]
+        L.rg_model_id2name.argtypes = [vp, ctypes.c_char_p, ci]
+        L.rg_model_id2name.restype = ctypes.c_char_p
         L.rg_dbg_size.argtypes = [vp]
         L.rg_scratch_bytes.argtypes = [vp]
         L.rg_batch_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
+        L.rg_batch_create_ex.argtypes = [vp, ci, ci, ci, ci, ctypes.POINTER(vp)]
+        L.rg_batch_capacity.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        L.rg_batch_dbg_size.argtypes = [vp]
+        L.rg_batch_scratch_bytes.argtypes = [vp]
         L.rg_batch_destroy.argtypes = [vp]
         L.rg_batch_bind.argtypes = [vp, ci, vp]
         L.rg_batch_bind_param.argtypes = [vp, ctypes.c_char_p, vp]
@@ -83,12 +91,25 @@ class DeviceModel:
     def dim(self, name):
         return self.host[name]
 
-    def set_field(self, name, values):
-        """Overwrite a model array (randomisers write e.g. geom_friction, dof_damping, opt_gravity)."""
+    def set_field(self, name, values, stream=None):
+        """Overwrite a model array (randomisers write e.g. geom_friction, dof_damping, opt_gravity).  The upload is ordered
+        on `stream` (a raw cudaStream_t; default: torch's current stream on the model's device when torch is loaded)."""
         arr = self.host[name]
         arr[...] = np.asarray(values, dtype=arr.dtype).reshape(arr.shape)
         buf = np.ascontiguousarray(arr)
-        _check(lib().rg_model_set_field(self.h, name.encode(), buf.ctypes.data, buf.size))
+        if stream is None:
+            import sys
+
+            t = sys.modules.get("torch")
+            stream = t.cuda.current_stream(self.device).cuda_stream if t is not None and t.cuda.is_available() else 0
+        _check(lib().rg_model_set_field_async(self.h, name.encode(), buf.ctypes.data, buf.size, ctypes.c_void_p(stream)))
+
+    def name2id(self, objtype, name):
+        """mjModel.<objtype>_name2id through the C ABI (the blob carries its name tables)."""
+        i = lib().rg_model_name2id(self.h, objtype.encode(), name.encode())
+        if i < 0:
+            raise ValueError(f'No "{objtype}" with name {name} exists.')
+        return i
 
     @property
     def dbg_size(self):
@@ -123,7 +144,10 @@ def world_shift_rows(t, v, name, m, origin):
 class BatchedSim:
     """nenv independent copies of one model, stepped by one fused kernel launch per env-step."""
 
-    def __init__(self, model, nenv, n_substeps=10, outputs=("site_xpos", "act_force", "ncon", "warn"), debug=False):
+    def __init__(self, model, nenv, n_substeps=10, outputs=("site_xpos", "act_force", "ncon", "warn"), debug=False,
+                 contact_capacity=0, row_capacity=0, dofs_per_contact=0):
+        """Capacities per environment (0 = engine default 32 / 64 / 16, see include/robogym_b200.h: rg_batch_create_ex); the
+        reference's compiled sizes are nconmax=100 / njmax=500 (assets.xml:5-6)."""
         import torch
 
         if not torch.cuda.is_available():
@@ -144,16 +168,19 @@ class BatchedSim:
         self.qacc_warmstart = torch.zeros(n, m["nv"], **f32)
         self.time = torch.zeros(n, **f32)
         h = ctypes.c_void_p()
-        _check(lib().rg_batch_create(model.h, n, ctypes.byref(h)))
+        _check(lib().rg_batch_create_ex(model.h, n, int(contact_capacity), int(row_capacity), int(dofs_per_contact), ctypes.byref(h)))
         self.h = h
+        c1, c2, c3 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib().rg_batch_capacity(h, ctypes.byref(c1), ctypes.byref(c2), ctypes.byref(c3))
+        self.contact_capacity, self.row_capacity, self.dofs_per_contact = c1.value, c2.value, c3.value
         self._bound = {}
         for fid, t in ((QPOS, self.qpos), (QVEL, self.qvel), (CTRL, self.ctrl), (PID, self.pid),
                        (WARMSTART, self.qacc_warmstart), (TIME, self.time)):
             self._bind(fid, t)
         shapes = dict(site_xpos=(SITE_XPOS, (n, m["nsite"], 3), f32), body_xpos=(BODY_XPOS, (n, m["nbody"], 3), f32),
                       body_xquat=(BODY_XQUAT, (n, m["nbody"], 4), f32), geom_xpos=(GEOM_XPOS, (n, m["ngeom"], 3), f32),
-                      act_force=(ACT_FORCE, (n, m["nu"]), f32), qacc=(QACC, (n, m["nv"]), f32),
-                      contact=(CONTACT, (n, MAX_CONTACTS, 4), f32), ncon=(NCON, (n,), i32), warn=(WARN, (n,), i32))
+                      body_xvel=(BODY_XVEL, (n, m["nbody"], 6), f32), act_force=(ACT_FORCE, (n, m["nu"]), f32), qacc=(QACC, (n, m["nv"]), f32),
+                      contact=(CONTACT, (n, self.contact_capacity, 4), f32), ncon=(NCON, (n,), i32), warn=(WARN, (n,), i32))
         for name in outputs:
             fid, shape, kw = shapes[name]
             t = torch.zeros(*shape, **kw)
@@ -161,7 +188,7 @@ class BatchedSim:
             self._bind(fid, t)
         self.dbg = None
         if debug:
-            self.dbg = torch.zeros(n, model.dbg_size, **f32)
+            self.dbg = torch.zeros(n, lib().rg_batch_dbg_size(self.h), **f32)
             self._bind(DBG, self.dbg)
         self.xfrc_applied = None
         self.timestep = None
@@ -177,12 +204,17 @@ class BatchedSim:
         self._bind(XFRC, self.xfrc_applied)
         return self.xfrc_applied
 
-    def set_param(self, name, values):
+    def set_param(self, name, values, idx=None):
         """Per-environment override of a float model array (domain randomisation): `values` is [nenv, count]
-        (float64/float32 host array or tensor).  The device copy is created on first use and updated in place."""
+        (float64/float32 host array or tensor), or [len(idx), count] for the rows `idx` of an array that is already bound.
+        The device copy is created on first use and updated in place; rows in world coordinates get the engine's fp32 world
+        shift on EVERY write."""
         t = self.torch
         m = self.model.host
-        v = t.as_tensor(np.asarray(values, dtype=np.float64) if not t.is_tensor(values) else values).to(t.float64).reshape(self.nenv, -1).clone()
+        rows = self.nenv if idx is None else len(idx)
+        v = t.as_tensor(np.asarray(values, dtype=np.float64) if not t.is_tensor(values) else values).to(t.float64).reshape(rows, -1).clone()
+        if idx is not None and name not in getattr(self, "_params", {}):
+            raise EngineError(f"set_param({name}, idx=...): bind the full array first")
         if v.shape[1] != m[name].size:
             raise EngineError(f"set_param({name}): expected {m[name].size} values per environment, got {v.shape[1]}")
         if name in ("body_pos", "geom_pos", "site_pos"):
@@ -193,7 +225,9 @@ class BatchedSim:
         dev = v.to(device=self.device, dtype=t.float32).contiguous()
         if not hasattr(self, "_params"):
             self._params = {}
-        if name in self._params:
+        if idx is not None:
+            self._params[name][idx] = dev
+        elif name in self._params:
             self._params[name].copy_(dev)
         else:
             self._params[name] = dev
@@ -240,7 +274,8 @@ class BatchedSim:
     def launch_info(self):
         a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         lib().rg_batch_launch_info(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        return dict(ctas=a.value, warps_per_cta=b.value, smem_bytes=c.value)
+        return dict(ctas=a.value, warps_per_cta=b.value, smem_bytes=c.value, scratch_bytes_per_env=lib().rg_batch_scratch_bytes(self.h),
+                    contact_capacity=self.contact_capacity, row_capacity=self.row_capacity, dofs_per_contact=self.dofs_per_contact)
 
     def dbg_view(self, env=0):
         """Decode the stage dump of one environment (tests)."""
@@ -256,7 +291,8 @@ class BatchedSim:
         out["alen"] = g[o:o + nu]; o += nu
         out["aforce"] = g[o:o + nu]; o += nu
         out["ncon"], out["nel"], out["niter"], out["warn"] = [int(x) for x in g[o:o + 4]]; o += 4
-        out["con"] = g[o:o + MAX_CONTACTS * CON_STRIDE].reshape(MAX_CONTACTS, CON_STRIDE); o += MAX_CONTACTS * CON_STRIDE
+        K = self.contact_capacity
+        out["con"] = g[o:o + K * CON_STRIDE].reshape(K, CON_STRIDE); o += K * CON_STRIDE
         out["tJ"] = g[o:o + nt * nv].reshape(nt, nv)
         return out
 

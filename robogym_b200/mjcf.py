@@ -291,7 +291,7 @@ class CompiledModel:
         self.xml = xml
 
     def blob(self):
-        return modelblob.pack(self.m)
+        return modelblob.pack(self.m, self.names)
 
     @classmethod
     def from_blob(cls, blob, names, xml=""):

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FIELDS_H = os.path.join(_HERE, "..", "include", "rg_model_fields.h")
 MAGIC = b"RGMODEL1"
+NAMES_MAGIC = b"RGNAMES1"   # optional trailing section: the name tables behind rg_model_name2id (mjModel.*_name2id)
 
 _pat = re.compile(r"^\s*RG_(DIM|IB|FB|I|F)\(\s*(\w+)\s*(?:,\s*(.+?)\s*)?\)\s*(?:/\*.*)?$")
 
@@ -41,8 +42,8 @@ def _count(expr, dims):
     return int(eval(expr, {"__builtins__": {}}, dict(dims)))
 
 
-def pack(model):
-    """model: dict name -> int (dims) / ndarray (arrays). Returns bytes."""
+def pack(model, names=None):
+    """model: dict name -> int (dims) / ndarray (arrays); names: optional dict objtype -> [name | None].  Returns bytes."""
     dims = {d: int(model[d]) for d in DIMS}
     out = bytearray()
     out += MAGIC
@@ -62,7 +63,41 @@ def pack(model):
             out += arr.astype("<f8").tobytes()
     while len(out) % 8:
         out += b"\0"
+    if names:
+        # RGNAMES1, int32 ntypes, then per type: type name, NUL, int32 count, count NUL-terminated names ("" = unnamed)
+        out += NAMES_MAGIC
+        out += struct.pack("<i", len(names))
+        for typ in sorted(names):
+            out += typ.encode() + b"\0"
+            out += struct.pack("<i", len(names[typ]))
+            for n in names[typ]:
+                out += (n or "").encode() + b"\0"
     return bytes(out)
+
+
+def unpack_names(blob):
+    """The name tables of a blob (dict objtype -> [name | None]) or None when the blob carries none."""
+    blob = bytes(blob)
+    k = blob.find(NAMES_MAGIC)
+    if k < 0:
+        return None
+    off = k + len(NAMES_MAGIC)
+    (nt,) = struct.unpack_from("<i", blob, off)
+    off += 4
+    out = {}
+    for _ in range(nt):
+        e = blob.index(b"\0", off)
+        typ = blob[off:e].decode()
+        off = e + 1
+        (cnt,) = struct.unpack_from("<i", blob, off)
+        off += 4
+        lst = []
+        for _ in range(cnt):
+            e = blob.index(b"\0", off)
+            lst.append(blob[off:e].decode() or None)
+            off = e + 1
+        out[typ] = lst
+    return out
 
 
 def unpack(blob):

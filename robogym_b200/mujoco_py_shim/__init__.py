@@ -280,6 +280,12 @@ class MjSim:
         if out["warn"] and _callbacks["warning"] is not None:
             if out["warn"] & 1:
                 _callbacks["warning"](b"Pre-allocated contact buffer is full. Increase nconmax above %d." % 32)
+            if out["warn"] & 2:
+                _callbacks["warning"](b"Pre-allocated constraint buffer is full. Increase njmax above %d." % 64)
+            if out["warn"] & 32:
+                _callbacks["warning"](b"A contact touched more degrees of freedom than the engine batch allows and was dropped.")
+            if out["warn"] & 16:
+                _callbacks["warning"](b"A tendon Jacobian row has more non-zeros than the engine keeps.")
             if out["warn"] & 4:
                 _callbacks["warning"](b"Nan, Inf or huge value in QACC at DOF 0. The simulation is unstable. Time = %.4f." % d.time)
 

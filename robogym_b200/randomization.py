@@ -248,10 +248,8 @@ class LockedRandomizer:
                 else:
                     full[idx] = rows
                 sim.set_param(name, full)
-            elif idx is None:
-                cur.copy_(rows.to(cur.dtype))
             else:
-                cur[idx] = rows.to(cur.dtype)
+                sim.set_param(name, rows, idx=idx)     # through set_param: world-attached body / geom / site rows keep the fp32 world shift
 
     # ------------------------------------------------------------ per-step randomisation
     def timestep_state(self, n):

@@ -17,11 +17,12 @@ def lib():
     if _lib is None:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
         L = ctypes.CDLL(_LIB)
-        L.rge_create.restype = ctypes.c_void_p
-        L.rge_create.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+        L.rge_create_ex.restype = ctypes.c_void_p
+        L.rge_create_ex.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.rge_destroy.argtypes = [ctypes.c_void_p]
-        for f in ("rge_dbg_size", "rge_scratch_floats", "rge_small_bytes"):
+        for f in ("rge_dbg_size", "rge_scratch_floats", "rge_small_bytes", "rge_ncon"):
             getattr(L, f).argtypes = [ctypes.c_void_p]
+        L.rge_name2id.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.rge_model_field.restype = ctypes.c_void_p
         L.rge_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
         L.rge_step.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 18 + [ctypes.c_int, ctypes.c_int]
@@ -36,10 +37,11 @@ def _p(a):
 class EmuBatch:
     """Same state layout as robogym_b200.engine.Batch, backed by the emulation library."""
 
-    def __init__(self, blob, dims, nenv):
-        self.h = lib().rge_create(bytes(blob), len(blob))
+    def __init__(self, blob, dims, nenv, contact_capacity=0, row_capacity=0, dofs_per_contact=0):
+        self.h = lib().rge_create_ex(bytes(blob), len(blob), contact_capacity, row_capacity, dofs_per_contact)
         if not self.h:
             raise RuntimeError("rge_create failed")
+        self.ncon_cap = lib().rge_ncon(self.h)
         self.nenv = nenv
         self.d = dims
         f = np.float32
@@ -57,7 +59,7 @@ class EmuBatch:
         self.geom_xpos = np.zeros((nenv, dims["ngeom"], 3), f)
         self.act_force = np.zeros((nenv, dims["nu"]), f)
         self.qacc = np.zeros((nenv, dims["nv"]), f)
-        self.contact = np.zeros((nenv, NCON, 4), f)
+        self.contact = np.zeros((nenv, self.ncon_cap, 4), f)
         self.ncon = np.zeros(nenv, np.int32)
         self.warn = np.zeros(nenv, np.int32)
         self.dbg = np.zeros((nenv, lib().rge_dbg_size(self.h)), f)
@@ -90,7 +92,7 @@ class EmuBatch:
         out["alen"] = g[o:o + nu]; o += nu
         out["aforce"] = g[o:o + nu]; o += nu
         out["ncon"], out["nel"], out["niter"], out["warn"] = [int(x) for x in g[o:o + 4]]; o += 4
-        out["con"] = g[o:o + NCON * CON_STRIDE].reshape(NCON, CON_STRIDE); o += NCON * CON_STRIDE
+        out["con"] = g[o:o + self.ncon_cap * CON_STRIDE].reshape(self.ncon_cap, CON_STRIDE); o += self.ncon_cap * CON_STRIDE
         out["tJ"] = g[o:o + nt * nv].reshape(nt, nv)
         return out
 

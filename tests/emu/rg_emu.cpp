@@ -16,19 +16,29 @@ struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; std::
 
 extern "C" {
 
-void* rge_create(const void* blob, size_t len) {
+void* rge_create_ex(const void* blob, size_t len, int ncon, int nel, int tile) {
   RgeHandle* h = new RgeHandle();
   std::string err;
   if (!rg_host_load(blob, len, h->hm, err)) { fprintf(stderr, "rge_create: %s\n", err.c_str()); delete h; return nullptr; }
-  h->L = rg_make_layout(h->hm.view);
+  h->L = rg_make_layout(h->hm.view, ncon ? ncon : RG_NCON, nel ? nel : RG_NEL, tile ? tile : RG_TILE);
   h->scratch.assign(h->L.total, 0.0f);
   return h;
+}
+void* rge_create(const void* blob, size_t len) { return rge_create_ex(blob, len, 0, 0, 0); }
+int rge_ncon(void* hv) { return ((RgeHandle*)hv)->L.ncon; }
+/* the blob's name tables as parsed by the shared host loader (what rg_model_name2id serves) */
+int rge_name2id(void* hv, const char* typ, const char* name) {
+  RgeHandle* h = (RgeHandle*)hv;
+  auto it = h->hm.names.find(typ);
+  if (it == h->hm.names.end()) return -1;
+  for (size_t i = 0; i < it->second.size(); i++) if (it->second[i] == name) return (int)i;
+  return -1;
 }
 #ifdef RG_STATS
 void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; for (int i = 0; i < 128; i++) out[8 + i] = rg_stat_hist[i / 64][i % 64]; for (int i = 0; i < 16; i++) out[136 + i] = rg_stat_x[i]; }
 #endif
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
-int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view); }
+int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view, ((RgeHandle*)hv)->L.ncon); }
 int rge_scratch_floats(void* hv) { return ((RgeHandle*)hv)->L.total; }
 int rge_small_bytes(void* hv) { return (int)((RgeHandle*)hv)->hm.small_bytes; }
 /* writable pointer to a model array (float32/int32 copy) so tests can edit parameters */
@@ -59,7 +69,7 @@ void rge_step(void* hv, int nenv, float* qpos, float* qvel, float* ctrl, float* 
   RgBatchIO io;
   io.nenv = nenv; io.qpos = qpos; io.qvel = qvel; io.ctrl = ctrl; io.pid = pid; io.warm = warm; io.time = time; io.xfrc = xfrc;
   io.timestep = timestep; io.site_xpos = site_xpos; io.body_xpos = body_xpos; io.body_xquat = body_xquat; io.geom_xpos = geom_xpos;
-  io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg; io.cost = nullptr;
+  io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg; io.cost = nullptr; io.body_xvel = nullptr;
   if (h->sep.size() != (size_t)nenv * RG_NSEP) h->sep.assign((size_t)nenv * RG_NSEP, 0xfff);   /* like the engine's per-batch buffer */
   io.sep = h->sep.data();
   for (int env = 0; env < nenv; env++) rg_env_step(&h->hm.view, h->L, h->scratch.data(), 0, io, env, nsub, final_forward, 1);

@@ -31,6 +31,73 @@ def test_library_exports_every_declared_symbol():
     assert lib.rg_last_error() is not None
 
 
+def test_name_tables_travel_in_the_blob(locked_blob, locked_names):
+    """rg_model_name2id is served from the RGNAMES1 section of the blob: the Python packer and the C++ host loader
+    (shared with the CUDA engine; reached here through the emulation build) agree with the names sidecar."""
+    import pyemu
+    from robogym_b200 import modelblob
+
+    names = modelblob.unpack_names(locked_blob)
+    assert names["joint"] == locked_names["joint"] and names["site"] == locked_names["site"]
+    m = modelblob.unpack(locked_blob)
+    e = pyemu.EmuBatch(locked_blob, {k: m[k] for k in modelblob.DIMS}, 1)
+    L = pyemu.lib()
+    for typ in ("body", "joint", "geom", "site", "actuator", "tendon"):
+        for i, n in enumerate(locked_names[typ]):
+            if n is not None:
+                assert L.rge_name2id(e.h, typ.encode(), n.encode()) == locked_names[typ].index(n)
+    assert L.rge_name2id(e.h, b"joint", b"no such joint") == -1
+    assert L.rge_name2id(e.h, b"no such type", b"x") == -1
+
+
+def test_unsupported_features_are_refused(locked_blob):
+    """A model with elliptic cones, active equality constraints or mocap bodies must not load (it used to step
+    with silently wrong physics)."""
+    import pyemu
+    from robogym_b200 import modelblob
+
+    names = modelblob.unpack_names(locked_blob)
+    for edit in (lambda m: m["opt_cone"].__setitem__(0, 1), lambda m: m.__setitem__("nmocap", 1)):
+        m = modelblob.unpack(locked_blob)
+        edit(m)
+        with pytest.raises(RuntimeError):
+            pyemu.EmuBatch(modelblob.pack(m, names), {k: m[k] for k in modelblob.DIMS}, 1)
+
+
+@pytest.mark.gpu
+def test_new_entry_points_on_the_device(locked_blob, locked_names):
+    """rg_model_name2id / rg_model_set_field_async / rg_batch_create_ex / RG_FIELD_BODY_XVEL through ctypes on a GPU."""
+    import numpy as np
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+    model = engine.DeviceModel(locked_blob, 0)
+    assert model.name2id("joint", "robot0:WRJ1") == locked_names["joint"].index("robot0:WRJ1")
+    assert model.name2id("site", "cube:center") == locked_names["site"].index("cube:center")
+    with pytest.raises(ValueError):
+        model.name2id("geom", "nope")
+    sim = engine.BatchedSim(model, 4, 10, outputs=("site_xpos", "body_xpos", "body_xvel", "ncon", "warn", "contact"), contact_capacity=100, row_capacity=128)
+    assert (sim.contact_capacity, sim.row_capacity) == (100, 128) and sim.contact.shape == (4, 100, 4)
+    g0 = model.host["opt_gravity"].copy()
+    # stream-ordered parameter edit: the step queued BEFORE the edit falls with gravity, the one after it does not
+    sim.step()
+    z1 = sim.body_xpos[:, locked_names["body"].index("target:middle"), 2].clone()
+    v1 = sim.body_xvel[:, locked_names["body"].index("target:middle"), 5].clone()
+    model.set_field("opt_gravity", [0.0, 0.0, 0.0])
+    sim.step()
+    torch.cuda.synchronize()
+    v2 = sim.body_xvel[:, locked_names["body"].index("target:middle"), 5]
+    # free-falling target cube: v_z = -g t after the first env-step (0.08 s), unchanged by the second (gravity off)
+    assert torch.allclose(v1, torch.full_like(v1, g0[2] * 0.08), rtol=2e-3)
+    assert torch.allclose(v2, v1, atol=1e-4)
+    # linear velocity output equals the finite difference of the body position
+    z2 = sim.body_xpos[:, locked_names["body"].index("target:middle"), 2]
+    assert torch.allclose((z2 - z1) / 0.08, v2, rtol=5e-3)
+    model.set_field("opt_gravity", g0)
+
+
 def test_product_path_fails_loudly_without_gpu(locked_blob):
     """No CPU fallback: on a box without CUDA the engine raises instead of routing elsewhere."""
     import torch

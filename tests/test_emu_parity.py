@@ -63,6 +63,25 @@ def test_teacher_forced_env_step(locked_blob, locked_names, setup):
     assert np.mean(eq < 1e-3) > 0.7          # chaotic contact switching limits the tail, see DESIGN.md
 
 
+def test_teacher_forced_contract_workload(locked_blob, locked_names, setup):
+    """The GPU test's thresholds on the kernel logic in CPU emulation: 512 states from 8 seeds of the SURVEY 8(d) workload
+    (full-range relative actions): >= 90 % within 1e-3 in qpos, >= 95 % with the oracle's contact count."""
+    from helpers import contract_states
+
+    m, dims, _, _, _ = setup
+    sts, after, om = contract_states(locked_blob, range(100, 108), 64)
+    e = pyemu.EmuBatch(locked_blob, dims, len(sts))
+    for k, st in enumerate(sts):
+        load(e, k, st)
+    e.step(10, 1)
+    iq, iv = live_indices(om, locked_names)
+    eq, ev = step_errors(e.qpos, e.qvel, after, iq, iv)
+    assert e.warn.max() == 0
+    assert np.median(eq) < 2e-5 and np.median(ev) < 1e-3
+    assert np.mean(eq < 1e-3) >= 0.90
+    assert np.mean(e.ncon == np.array([a[2] for a in after])) >= 0.95
+
+
 def test_result_is_independent_of_batch_slot(locked_blob, setup):
     """Determinism: the same state in different batch slots gives bitwise identical results."""
     m, dims, states, after, om = setup

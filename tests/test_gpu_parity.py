@@ -4,7 +4,7 @@ plus size-independent properties at BASELINE.json's full batch (8192)."""
 import numpy as np
 import pytest
 
-from helpers import live_indices, oracle_pair, rollout_states, step_errors
+from helpers import contract_states, live_indices, oracle_pair, rollout_states, step_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -40,11 +40,12 @@ def test_native_library_is_loaded(gpu):
     assert "librobogym_b200" in maps
 
 
-def test_teacher_forced_env_step_vs_oracle(gpu, states, locked_names):
-    """10 x mj_step + forward from identical states.  Tolerances (fp32 vs fp64, contact-rich):
-    median |dq| < 2e-4 (rad / m), median |dv| < 5e-3, >= 70 % of states within 1e-3 in qpos."""
+def test_teacher_forced_env_step_vs_oracle(gpu, locked_blob, locked_names):
+    """10 x mj_step + forward from identical states: 512 states from 8 seeds of the SURVEY 8(d) workload (full-range
+    relative actions).  Tolerances (fp32 vs fp64, contact-rich): median |dq| < 2e-4 (rad / m), median |dv| < 5e-3,
+    >= 90 % of the states within 1e-3 in qpos, >= 95 % with the oracle's contact count."""
     torch, engine, model = gpu
-    sts, after, om = states
+    sts, after, om = contract_states(locked_blob, range(200, 208), 64)
     sim = engine.BatchedSim(model, len(sts), 10, outputs=("site_xpos", "ncon", "warn"))
     put(torch, sim, sts)
     sim.step()
@@ -53,9 +54,9 @@ def test_teacher_forced_env_step_vs_oracle(gpu, states, locked_names):
     eq, ev = step_errors(sim.qpos.cpu().numpy(), sim.qvel.cpu().numpy(), after, iq, iv)
     assert int(sim.warn.max()) == 0
     assert np.median(eq) < 2e-4 and np.median(ev) < 5e-3
-    assert np.mean(eq < 1e-3) > 0.7
+    assert np.mean(eq < 1e-3) >= 0.90, np.mean(eq < 1e-3)
     ncon = sim.ncon.cpu().numpy()
-    assert np.mean(ncon == np.array([a[2] for a in after])) > 0.7
+    assert np.mean(ncon == np.array([a[2] for a in after])) >= 0.95
 
 
 def test_stagewise_forward_vs_oracle(gpu, states, locked_blob):

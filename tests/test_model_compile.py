@@ -11,7 +11,7 @@ HAVE_REF = os.path.isdir("/root/reference/robogym")
 
 def test_blob_roundtrip(locked_blob):
     m = modelblob.unpack(locked_blob)
-    assert modelblob.pack(m) == locked_blob
+    assert modelblob.pack(m, modelblob.unpack_names(locked_blob)) == locked_blob
     assert m["nq"] == 38 and m["nv"] == 36 and m["npair"] == 1243
 
 

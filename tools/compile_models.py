@@ -36,5 +36,40 @@ def main():
         print(name, {k: cm.m[k] for k in ("nq", "nv", "nu", "nbody", "ngeom", "npair", "nmeshvert")}, len(cm.blob()), "bytes")
 
 
+def full_perpendicular():
+    """BASELINE.json configs[2]: the reference itself builds dactyl/full_perpendicular (Rubik's cube, nq170/nv168) on the
+    mujoco_py shim (robogym/envs/dactyl/full_perpendicular.py:92-154); the compiled model is taken from that MjSim."""
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    for p in (os.path.join(root, "tests", "stubs"), ref.REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import robogym_b200.mujoco_py_shim as shim
+
+    shim.install()
+    from oracle_engine import OracleEngine
+
+    shim.set_engine_factory(OracleEngine)
+    try:
+        from robogym.envs.dactyl.full_perpendicular import make_simple_env
+
+        env = make_simple_env(starting_seed=0)
+        cm = env.mujoco_simulation.mj_sim.model._cm
+        name = "dactyl_full_perpendicular"
+        with open(os.path.join(OUT, name + ".rgm"), "wb") as f:
+            f.write(cm.blob())
+        with open(os.path.join(OUT, name + ".names.json"), "w") as f:
+            json.dump(cm.names, f)
+        print(name, {k: cm.m[k] for k in ("nq", "nv", "nu", "nbody", "ngeom", "npair", "nmeshvert")}, len(cm.blob()), "bytes")
+    finally:
+        shim.set_engine_factory(None)
+
+
 if __name__ == "__main__":
-    main()
+    if "--full-only" in sys.argv:
+        full_perpendicular()
+    else:
+        main()
+        import subprocess
+
+        # fresh interpreter: the composer above imported robogym under a mujoco_py stub, the env needs the shim
+        subprocess.check_call([sys.executable, os.path.abspath(__file__), "--full-only"])
