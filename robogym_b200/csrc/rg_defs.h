@@ -132,7 +132,7 @@ __device__ __forceinline__ void rg_stage_sync() {
 /* The solver's Hessian is stored with the dof order REVERSED (leaves of the kinematic tree first, roots and
  * free objects last): Cholesky then eliminates children before parents, so the tree-structured part
  * of the matrix produces no fill-in and the envelope of most rows is a handful of entries. */
-#define RG_HR(nv, i, j) ((i) <= (j) ? RG_TRI((nv) - 1 - (i), (nv) - 1 - (j)) : RG_TRI((nv) - 1 - (j), (nv) - 1 - (i)))
+#define RG_HS(a, b) ((a) >= (b) ? RG_TRI(a, b) : RG_TRI(b, a))   /* a, b = solver positions (dof_sidx) */
 #ifndef RG_TILE
 #define RG_TILE 16       /* default for the dofs one contact may touch (<= 32: their signs travel in one word) */
 #endif
@@ -160,12 +160,15 @@ struct RgModel {
   const int* body_subtreesize; /* bodies are numbered depth-first: subtree(b) = [b, b+size) */
   const int* dof_mrow;         /* [nv][3]: start of dof i's row in the tree-sparse mass matrix, dofs in its subtree, its depth */
   const int* dof_lvl;          /* [2 nv + 2]: dof ids sorted by depth, then the start of every depth level (ndoflevel + 1 entries) */
+  const int* dof_xlvl;         /* the same lists restricted to the dofs that stay out of the constraint solver */
+  const int* dof_sidx;         /* [2 nv]: solver position of every dof (or -1), then the dof at every solver position */
   const float* mesh_vert4;     /* [nmeshvert][4]: hull vertices padded to 16 bytes (one vector load each) */
   const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
   int small_bytes;             /* leading part of the arena that is staged into shared memory */
   int nM;                      /* entries of the tree-sparse mass matrix: sum over dofs of (depth + 1) */
   int ndoflevel;               /* depth levels of the dof tree */
+  int ns;                      /* dofs in the constraint solver (<= nv) */
 };
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
@@ -210,6 +213,8 @@ struct RgModelDev {
   RgArr<int> body_subtreesize;
   RgArr<int> dof_mrow;
   RgArr<int> dof_lvl;
+  RgArr<int> dof_xlvl;
+  RgArr<int> dof_sidx;
   RgArr<unsigned short> pair_packed;
   int has_pairs;
   const float* mesh_vert4;
@@ -217,6 +222,7 @@ struct RgModelDev {
   int small_bytes;
   int nM;
   int ndoflevel;
+  int ns;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev

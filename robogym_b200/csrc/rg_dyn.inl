@@ -414,12 +414,20 @@ RG_DEV_NOINLINE float rg_wrap_geom(float* wp, const float* x0, const float* x1, 
 RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx c, float* J, int ba, const float* pa, int bb, const float* pb, const float* dir, float scale) {
   if (ba == bb) return;
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
-  RG_NOUNROLL for (int d = 0; d < m.nv; d++) {
-    const int ina = rg_dof_in_body(m, ba, d), inb = rg_dof_in_body(m, bb, d);
-    if (ina == inb) continue;
-    float jp[3];
-    rg_jacp_world(c, d, inb ? pb : pa, jp);
-    J[d] += (inb ? scale : -scale) * rg_dot3(jp, dir);
+  /* only the dofs that move exactly one of the two bodies contribute: walk the set bits of the symmetric difference of their
+     ancestor masks instead of testing every dof */
+  RG_NOUNROLL for (int w = 0; w < m.nmaskw; w++) {
+    const unsigned ma = (unsigned)m.body_dofmask[ba * m.nmaskw + w], mb = (unsigned)m.body_dofmask[bb * m.nmaskw + w];
+    unsigned bits = ma ^ mb;
+    while (bits) {
+      const int bit = rg_ctz(bits);
+      bits &= bits - 1;
+      const int d = 32 * w + bit;
+      const int inb = (mb >> bit) & 1u;
+      float jp[3];
+      rg_jacp_world(c, d, inb ? pb : pa, jp);
+      J[d] += (inb ? scale : -scale) * rg_dot3(jp, dir);
+    }
   }
 }
 

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     RG_SETOFF(body_subtreesize)
     RG_SETOFF(dof_mrow)
     RG_SETOFF(dof_lvl)
+    RG_SETOFF(dof_xlvl)
+    RG_SETOFF(dof_sidx)
     RG_SETPTR(mesh_vert4)
     if (lane == 0) {
       sm->has_pairs = args.m.pair_packed != nullptr;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       sm->small_bytes = small_bytes;
       sm->nM = args.m.nM;
       sm->ndoflevel = args.m.ndoflevel;
+      sm->ns = args.m.ns;
     }
     for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
@@ -265,6 +268,8 @@ static void rg_wire_device_view(rg_model* mm) {
   RG_DEVPTR(body_subtreesize)
   RG_DEVPTR(dof_mrow)
   RG_DEVPTR(dof_lvl)
+  RG_DEVPTR(dof_xlvl)
+  RG_DEVPTR(dof_sidx)
   RG_DEVPTR(mesh_vert4)
   if (mm->hm.view.pair_packed) RG_DEVPTR(pair_packed)
 #undef RG_DEVPTR

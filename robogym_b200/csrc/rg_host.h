@@ -99,6 +99,8 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   dst = rg_align16(dst); const size_t off_subtree = dst; dst += 4 * (size_t)m.nbody;
   dst = rg_align16(dst); const size_t off_mrow = dst; dst += 12 * (size_t)m.nv;
   dst = rg_align16(dst); const size_t off_dlvl = dst; dst += 4 * (2 * (size_t)m.nv + 2);
+  dst = rg_align16(dst); const size_t off_xlvl = dst; dst += 4 * (2 * (size_t)m.nv + 2);
+  dst = rg_align16(dst); const size_t off_sidx = dst; dst += 4 * (2 * (size_t)m.nv);
   dst = rg_align16(dst); const size_t off_pairs = dst; if (m.ngeom <= 256) dst += 2 * (size_t)m.npair;
   dst = rg_align16(dst);
   hm.small_bytes = dst;
@@ -161,6 +163,38 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
     dlvl[m.nv + maxd + 1] = pos;
     m.ndoflevel = m.nv > 0 ? maxd + 1 : 0;
     m.dof_lvl = dlvl;
+    /* Kinematic trees that no constraint row can ever touch (no friction loss, no limited joint, no tendon, no geom in a
+       collision pair -- e.g. the collision-free target cube of the dactyl scenes, robogym/envs/dactyl/locked.py:89-96) stay
+       out of the constraint solver: their acceleration is M^-1 qfrc_smooth exactly (tree-sparse solve), and the dense
+       Hessian is built over the remaining `ns` dofs only.  sidx[d] = position of dof d in the solver's order (reversed:
+       leaves first) or -1; sidx[nv + k] = dof at solver position k. */
+    std::vector<char> tree_con(m.nbody, 0);
+    auto mark_body = [&](int b) { tree_con[m.body_rootid[b]] = 1; };
+    for (int d = 0; d < m.nv; d++) if (m.dof_frictionloss[d] > 0.0f) mark_body(m.dof_bodyid[d]);
+    for (int j = 0; j < m.njnt; j++) if (m.jnt_limited[j]) mark_body(m.jnt_bodyid[j]);
+    for (int k = 0; k < m.npair; k++) { mark_body(m.geom_bodyid[m.pair_geom1[k]]); mark_body(m.geom_bodyid[m.pair_geom2[k]]); }
+    for (int t = 0; t < m.ntendon; t++)
+      for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) {
+        if (m.wrap_type[w] == RG_WRAP_JOINT) mark_body(m.jnt_bodyid[m.wrap_objid[w]]);
+        else if (m.wrap_type[w] == RG_WRAP_SITE) mark_body(m.site_bodyid[m.wrap_objid[w]]);
+        else if (m.wrap_type[w] == RG_WRAP_SPHERE || m.wrap_type[w] == RG_WRAP_CYLINDER) mark_body(m.geom_bodyid[m.wrap_objid[w]]);
+      }
+    int* sidx = (int*)(base + off_sidx);
+    int ns = 0;
+    for (int d = m.nv - 1; d >= 0; d--) {
+      if (tree_con[m.body_rootid[m.dof_bodyid[d]]]) { sidx[d] = ns; sidx[m.nv + ns] = d; ns++; }
+      else sidx[d] = -1;
+    }
+    m.ns = ns;
+    m.dof_sidx = sidx;
+    int* xlvl = (int*)(base + off_xlvl);
+    pos = 0;
+    for (int l = 0; l <= maxd; l++) {
+      xlvl[m.nv + l] = pos;
+      for (int d = 0; d < m.nv; d++) if (mrow[3 * d + 2] == l && sidx[d] < 0) xlvl[pos++] = d;
+    }
+    xlvl[m.nv + maxd + 1] = pos;
+    m.dof_xlvl = xlvl;
   }
   /* depth-first numbering check: every body's parent must precede it and subtrees must be contiguous */
   for (int b = 1; b < m.nbody; b++) {
@@ -172,6 +206,8 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   hm.offsets.push_back(off_subtree);
   hm.offsets.push_back(off_mrow);
   hm.offsets.push_back(off_dlvl);
+  hm.offsets.push_back(off_xlvl);
+  hm.offsets.push_back(off_sidx);
   /* hull vertices padded to float4: the narrow phase scans a hull's vertices with one 16-byte load each */
   float* v4 = (float*)(base + off_v4);
   for (int k = 0; k < m.nmeshvert; k++) { v4[4 * k] = m.mesh_vert[3 * k]; v4[4 * k + 1] = m.mesh_vert[3 * k + 1]; v4[4 * k + 2] = m.mesh_vert[3 * k + 2]; v4[4 * k + 3] = 0.0f; }

@@ -99,22 +99,24 @@ RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
   RG_PHASE_END
 }
 
-/* dense H (packed, reversed dof order) <- tree-sparse M (+ diag) */
-RG_DEV void rg_H_from_M(const RgCtx c, const float* diag, float scale) {
+/* dense H (packed lower triangle over the solver's dofs, leaves first) <- tree-sparse M */
+RG_DEV void rg_H_from_M(const RgCtx c) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(c.mref);
   const RgLayout& L = RG_CL(c);
-  const int nv = m.nv;
+  const int nv = m.nv, ns = m.ns;
   float* s = RG_SCRATCH(c);
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int i = lane; i < ((nv * (nv + 1)) >> 1); i += 32) s[L.H + i] = 0.0f;
+  RG_NOUNROLL for (int i = lane; i < ((ns * (ns + 1)) >> 1); i += 32) s[L.H + i] = 0.0f;
   RG_PHASE_END
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
+    const int si = m.dof_sidx[i];
+    if (si < 0) continue;
     const float* row = s + L.M + m.dof_mrow[3 * i];
     int j = i;
     RG_NOUNROLL for (int k = 0; j >= 0; k++) {
-      s[L.H + RG_HR(nv, i, j)] = row[k] + (k == 0 && diag ? scale * diag[i] : 0.0f);
+      s[L.H + RG_TRI(m.dof_sidx[j], si)] = row[k];     /* an ancestor sits later in the solver's order */
       j = m.dof_parentid[j];
     }
   }
@@ -126,7 +128,7 @@ RG_DEV void rg_H_from_M(const RgCtx c, const float* diag, float scale) {
  * deliver the forward substitution y = L^-1 b in that row for free (the same dot products, one more lane). */
 RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
   RG_LANE_DECL
-  const int n = RG_MDEREF(c.mref).nv;
+  const int n = RG_MDEREF(c.mref).ns;
   float* s = RG_SCRATCH(c);
   for (int j = 0; j < n; j++) {
     LANEVAR(float, sumv);
@@ -172,7 +174,7 @@ RG_DEV_NOINLINE void rg_cholesky(const RgCtx c, int A, const int* env) {
    on the fly) */
 RG_DEV_NOINLINE void rg_chol_forward(const RgCtx c, int A, const int* env) {
   RG_LANE_DECL
-  const int n = RG_MDEREF(c.mref).nv;
+  const int n = RG_MDEREF(c.mref).ns;
   float* s = RG_SCRATCH(c);
   const int x = A + RG_TRI(n, 0);
   for (int j = 0; j < n; j++) {
@@ -186,17 +188,87 @@ RG_DEV_NOINLINE void rg_chol_forward(const RgCtx c, int A, const int* env) {
     RG_PHASE_END
   }
 }
-/* out[n - 1 - j] <- (L^-T y)[j] with y in row n of A (row n is consumed): the solution leaves in model dof order */
+/* out[dof at solver position j] <- (L^-T y)[j] with y in row n of A (row n is consumed): the solution leaves in model dof order */
 RG_DEV_NOINLINE void rg_chol_back(const RgCtx c, int A, const int* env, int out) {
   RG_LANE_DECL
-  const int n = RG_MDEREF(c.mref).nv;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const int n = m.ns;
+  const int* sdof = m.dof_sidx + m.nv;
   float* s = RG_SCRATCH(c);
   const int x = A + RG_TRI(n, 0);
   for (int j = n - 1; j >= 0; j--) {
     RG_PHASE_BEGIN
     const float xj = s[x + j] * s[A + RG_TRI(j, j)];
-    if (lane == 0) s[out + (n - 1 - j)] = xj;
+    if (lane == 0) s[out + sdof[j]] = xj;
     RG_NOUNROLL for (int i = env[j] + lane; i < j; i += 32) s[x + i] -= s[A + RG_TRI(j, i)] * xj;
+    RG_PHASE_END
+  }
+}
+
+/* ---------------------------------------------------------------- tree-sparse factorisation of M + diag */
+/* M couples a dof only with its ancestors and descendants, so M + diag = L' D L with L as sparse as M (the layout MuJoCo
+ * calls qLD).  F (nM floats, rows like M) receives D(i) in slot 0 of row i and the UNSCALED couplings D(i) L(i, a) behind
+ * it; invD (nv floats) the reciprocals of D.  Work is organised by depth level, leaves first: entry (i, a) subtracts the
+ * contributions of the dofs in the subtree of i, all of which are deeper and therefore final ("pull" form: lanes never
+ * write the same slot, no atomics, fixed summation order). */
+RG_DEV_NOINLINE void rg_sparse_factor(const RgCtx c, int F, int invD, const float* diag, float scale, const int* lvl) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  float* s = RG_SCRATCH(c);
+  const float* M = s + RG_CL(c).M;
+  const int nv = m.nv;
+  const int* order = lvl;          /* dof ids by depth level (all dofs, or the trees outside the constraint solver) */
+  const int* start = lvl + nv;
+  for (int lvl = m.ndoflevel - 1; lvl >= 0; lvl--) {
+    const int l0 = start[lvl], cnt = start[lvl + 1] - l0, w = lvl + 1;
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int it = lane; it < cnt * w; it += 32) {
+      const int q = it / w, e = it - q * w;
+      const int i = order[l0 + q];
+      const int adr = m.dof_mrow[3 * i], nsub = m.dof_mrow[3 * i + 1];
+      float acc = M[adr + e] + (e == 0 && diag ? scale * diag[i] : 0.0f);
+      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++) {
+        const int ak = m.dof_mrow[3 * k], dk = m.dof_mrow[3 * k + 2] - lvl;   /* column i sits dk entries into row k */
+        acc -= s[F + ak + dk] * s[F + ak + dk + e] * s[invD + k];
+      }
+      s[F + adr + e] = acc;
+      if (e == 0) s[invD + i] = 1.0f / acc;
+    }
+    RG_PHASE_END
+  }
+}
+/* x <- (M + diag)^-1 x with the factor above */
+RG_DEV_NOINLINE void rg_sparse_solve(const RgCtx c, int F, int invD, int x, const int* lvl) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  float* s = RG_SCRATCH(c);
+  const int nv = m.nv;
+  const int* order = lvl;          /* dof ids by depth level (all dofs, or the trees outside the constraint solver) */
+  const int* start = lvl + nv;
+  /* x <- L^-T x: a dof collects from its subtree (deeper levels are final) */
+  for (int lvl = m.ndoflevel - 2; lvl >= 0; lvl--) {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
+      const int i = order[q];
+      const int nsub = m.dof_mrow[3 * i + 1];
+      float acc = s[x + i];
+      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++)
+        acc -= s[F + m.dof_mrow[3 * k] + m.dof_mrow[3 * k + 2] - lvl] * s[invD + k] * s[x + k];
+      s[x + i] = acc;
+    }
+    RG_PHASE_END
+  }
+  /* x <- D^-1 x, then x <- L^-1 x: a dof collects from its ancestors (shallower levels are final) */
+  for (int lvl = 0; lvl < m.ndoflevel; lvl++) {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
+      const int i = order[q];
+      const int adr = m.dof_mrow[3 * i];
+      float acc = s[x + i];
+      int a = m.dof_parentid[i];
+      RG_NOUNROLL for (int e = 1; e <= lvl; e++) { acc -= s[F + adr + e] * s[x + a]; a = m.dof_parentid[a]; }
+      s[x + i] = acc * s[invD + i];
+    }
     RG_PHASE_END
   }
 }
@@ -501,9 +573,23 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #endif
   RG_STAT(rg_stat_x[0]++; rg_stat_x[8] += nel;)
   RG_PROFS_BEGIN
+  const int ns = m.ns;
+  const int* sidx = m.dof_sidx + 0;
+  /* trees no constraint can touch: qacc = M^-1 qfrc_smooth, exactly, by the tree-sparse factorisation (the Hessian region
+     is still free); they take no part in the iteration below (their search direction stays zero) */
+  if (ns < nv) {
+    rg_sparse_factor(c, L.H, L.tmp, nullptr, 0.0f, m.dof_xlvl + 0);
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + d] = s[L.smooth + d];
+    RG_PHASE_END
+    rg_sparse_solve(c, L.H, L.tmp, L.search, m.dof_xlvl + 0);
+  }
   /* start from the previous solution (warm start) */
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
+  RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
+    if (sidx[d] < 0) { s[L.qacc + d] = s[L.search + d]; s[L.search + d] = 0.0f; }
+    else s[L.qacc + d] = (m.opt_disableflags[0] & RG_DSBL_WARMSTART) ? 0.0f : s[L.warm + d];
+  }
   RG_PHASE_END
   rg_matvec_phase(c, L.Ma, L.qacc);
   rg_J_mul_phase(c, L.qacc, L.el_jar, L.cu, nel, ncon, 1);
@@ -534,6 +620,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     RG_PHASE_BEGIN
     float a = 0.0f;
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
+      if (sidx[d] < 0) continue;
       const float g = s[L.Ma + d] - s[L.smooth + d] - s[L.qfc + d];
       s[L.search + d] = -g;
       a += g * g;
@@ -552,14 +639,14 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     RG_STAT(rg_stat_x[1]++;)
     if (refactor) {
     RG_STAT(rg_stat_x[2]++;)
-    rg_H_from_M(c, nullptr, 0.0f);
+    rg_H_from_M(c);
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       float add = 0.0f;
       const int e0 = eldof[3 * d];
       if (e0 >= 0) { const float rf = s[L.el_floss + e0] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
       for (int q = 1; q < 3; q++) { const int e = eldof[3 * d + q]; if (e >= 0 && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
-      s[L.H + RG_HR(nv, d, d)] += add;
+      if (add != 0.0f) s[L.H + RG_TRI(sidx[d], sidx[d])] += add;
     }
     RG_PHASE_END
     for (int e = tl0; e < nel; e++) {
@@ -571,7 +658,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       RG_PHASE_BEGIN
       RG_NOUNROLL for (int p = lane; p < tn * tn; p += 32) {
         const int a = p / tn, b = p - a * tn;
-        if (tji[a] >= tji[b]) s[L.H + RG_HR(nv, tji[a], tji[b])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
+        if (tji[a] >= tji[b]) s[L.H + RG_HS(sidx[tji[a]], sidx[tji[b]])] += D * s[L.tJv + RG_TJ * t + a] * s[L.tJv + RG_TJ * t + b];
       }
       RG_PHASE_END
     }
@@ -619,13 +706,13 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         const float* tw = s + L.tileWJ + 6 * j;
         float acc = 0.0f;
         RG_NOUNROLL for (int a = 0; a < dim; a++) acc += tj[a] * tw[a];
-        if (tdof[i] >= tdof[j]) s[L.H + RG_HR(nv, tdof[i], tdof[j])] += acc;
+        if (tdof[i] >= tdof[j]) s[L.H + RG_HS(sidx[tdof[i]], sidx[tdof[j]])] += acc;
       }
       RG_PHASE_END
     }
     /* envelope, factor, Newton direction */
     RG_PHASE_BEGIN
-    RG_NOUNROLL for (int i = lane; i < nv; i += 32) {
+    RG_NOUNROLL for (int i = lane; i < ns; i += 32) {
       int e = 0;
       while (e < i && s[L.H + RG_TRI(i, e)] == 0.0f) e++;
       env[i] = e;
@@ -633,19 +720,19 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     RG_PHASE_END
     RG_PROFS(c, 11)
     RG_PHASE_BEGIN   /* right-hand side -> row nv of H, in the solver's reversed dof order */
-    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.H + RG_TRI(nv, nv - 1 - d)] = s[L.search + d];
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) if (sidx[d] >= 0) s[L.H + RG_TRI(ns, sidx[d])] = s[L.search + d];
     RG_PHASE_END
     rg_cholesky(c, L.H, env);
     RG_PROFS(c, 12)
     have_factor = 1; factor_sig = RG_SI(c, RG_S_SIG);
     } else {
     RG_PHASE_BEGIN
-    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.H + RG_TRI(nv, nv - 1 - d)] = s[L.search + d];
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) if (sidx[d] >= 0) s[L.H + RG_TRI(ns, sidx[d])] = s[L.search + d];
     RG_PHASE_END
     rg_chol_forward(c, L.H, env);
     }
 #if defined(RG_EMU) && defined(RG_DEBUG_NEWTON)
-    { double cs = 0; for (int i = 0; i < (nv * (nv + 1)) / 2; i++) cs += s[L.H + i] * (1 + (i % 7)); int es = 0; for (int i = 0; i < nv; i++) es += env[i] * (i + 1); printf("    L checksum %.9g env %d\n", cs, es); }
+    { double cs = 0; for (int i = 0; i < (ns * (ns + 1)) / 2; i++) cs += s[L.H + i] * (1 + (i % 7)); int es = 0; for (int i = 0; i < ns; i++) es += env[i] * (i + 1); printf("    L checksum %.9g env %d\n", cs, es); }
 #endif
     rg_chol_back(c, L.H, env, L.search);
     RG_PROFS(c, 13)
@@ -772,74 +859,6 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   RG_PHASE_END
 }
 
-/* ---------------------------------------------------------------- tree-sparse factorisation of M + diag */
-/* M couples a dof only with its ancestors and descendants, so M + diag = L' D L with L as sparse as M (the layout MuJoCo
- * calls qLD).  F (nM floats, rows like M) receives D(i) in slot 0 of row i and the UNSCALED couplings D(i) L(i, a) behind
- * it; invD (nv floats) the reciprocals of D.  Work is organised by depth level, leaves first: entry (i, a) subtracts the
- * contributions of the dofs in the subtree of i, all of which are deeper and therefore final ("pull" form: lanes never
- * write the same slot, no atomics, fixed summation order). */
-RG_DEV_NOINLINE void rg_sparse_factor(const RgCtx c, int F, int invD, const float* diag, float scale) {
-  RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref);
-  float* s = RG_SCRATCH(c);
-  const float* M = s + RG_CL(c).M;
-  const int nv = m.nv;
-  const int* order = m.dof_lvl + 0;
-  const int* start = m.dof_lvl + nv;
-  for (int lvl = m.ndoflevel - 1; lvl >= 0; lvl--) {
-    const int l0 = start[lvl], cnt = start[lvl + 1] - l0, w = lvl + 1;
-    RG_PHASE_BEGIN
-    RG_NOUNROLL for (int it = lane; it < cnt * w; it += 32) {
-      const int q = it / w, e = it - q * w;
-      const int i = order[l0 + q];
-      const int adr = m.dof_mrow[3 * i], nsub = m.dof_mrow[3 * i + 1];
-      float acc = M[adr + e] + (e == 0 && diag ? scale * diag[i] : 0.0f);
-      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++) {
-        const int ak = m.dof_mrow[3 * k], dk = m.dof_mrow[3 * k + 2] - lvl;   /* column i sits dk entries into row k */
-        acc -= s[F + ak + dk] * s[F + ak + dk + e] * s[invD + k];
-      }
-      s[F + adr + e] = acc;
-      if (e == 0) s[invD + i] = 1.0f / acc;
-    }
-    RG_PHASE_END
-  }
-}
-/* x <- (M + diag)^-1 x with the factor above */
-RG_DEV_NOINLINE void rg_sparse_solve(const RgCtx c, int F, int invD, int x) {
-  RG_LANE_DECL
-  const RG_MODEL_T& m = RG_MDEREF(c.mref);
-  float* s = RG_SCRATCH(c);
-  const int nv = m.nv;
-  const int* order = m.dof_lvl + 0;
-  const int* start = m.dof_lvl + nv;
-  /* x <- L^-T x: a dof collects from its subtree (deeper levels are final) */
-  for (int lvl = m.ndoflevel - 2; lvl >= 0; lvl--) {
-    RG_PHASE_BEGIN
-    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
-      const int i = order[q];
-      const int nsub = m.dof_mrow[3 * i + 1];
-      float acc = s[x + i];
-      RG_NOUNROLL for (int k = i + 1; k < i + nsub; k++)
-        acc -= s[F + m.dof_mrow[3 * k] + m.dof_mrow[3 * k + 2] - lvl] * s[invD + k] * s[x + k];
-      s[x + i] = acc;
-    }
-    RG_PHASE_END
-  }
-  /* x <- D^-1 x, then x <- L^-1 x: a dof collects from its ancestors (shallower levels are final) */
-  for (int lvl = 0; lvl < m.ndoflevel; lvl++) {
-    RG_PHASE_BEGIN
-    RG_NOUNROLL for (int q = start[lvl] + lane; q < start[lvl + 1]; q += 32) {
-      const int i = order[q];
-      const int adr = m.dof_mrow[3 * i];
-      float acc = s[x + i];
-      int a = m.dof_parentid[i];
-      RG_NOUNROLL for (int e = 1; e <= lvl; e++) { acc -= s[F + adr + e] * s[x + a]; a = m.dof_parentid[a]; }
-      s[x + i] = acc * s[invD + i];
-    }
-    RG_PHASE_END
-  }
-}
-
 /* ---------------------------------------------------------------- S15 semi-implicit Euler */
 RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   RG_LANE_DECL
@@ -847,11 +866,11 @@ RG_DEV_NOINLINE void rg_euler(const RgCtx c) {
   const int nv = m.nv;
   const float h = c.timestep;
   /* (M + h B) qacc_damped = qfrc_smooth + qfrc_constraint; the dense Hessian region is free here and holds the factor */
-  rg_sparse_factor(c, L.H, L.tmp, m.dof_damping + 0, h);
+  rg_sparse_factor(c, L.H, L.tmp, m.dof_damping + 0, h, m.dof_lvl + 0);
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.search + d] = s[L.smooth + d] + s[L.qfc + d];
   RG_PHASE_END
-  rg_sparse_solve(c, L.H, L.tmp, L.search);
+  rg_sparse_solve(c, L.H, L.tmp, L.search, m.dof_lvl + 0);
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.qvel + d] += h * s[L.search + d];
   RG_PHASE_END

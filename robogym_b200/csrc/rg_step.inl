@@ -49,13 +49,13 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
   RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
   RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
-  const int ntri = ((m.nv + 1) * (m.nv + 2)) >> 1;   /* packed lower triangle of H plus one extra row (the right-hand side rides along in the factorisation) */
+  const int ntri = ((m.ns + 1) * (m.ns + 2)) >> 1;   /* packed lower triangle of H plus one extra row (the right-hand side rides along in the factorisation) */
   RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nM);   /* M: tree-sparse rows (rg_host.h), H: dense packed lower triangle */
   /* H aliases the smooth-dynamics temporaries */
   const int h0 = o;
   RG_ALLOC(Sdot, 6 * rg_imax(m.nv, m.nbody)); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
   L.H = h0;
-  o = h0 + rg_imax(rg_imax(o - h0, (ntri + 3) & ~3), (m.ntendon * m.nv + 3) & ~3);
+  o = h0 + rg_imax(rg_imax(rg_imax(o - h0, (ntri + 3) & ~3), (m.ntendon * m.nv + 3) & ~3), (m.nM + 3) & ~3);   /* also the tree-sparse factor (Euler, solver-free trees) */
   RG_ALLOC(bias, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
   RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));

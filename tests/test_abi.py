@@ -121,7 +121,7 @@ def test_scratch_budget_keeps_ten_environments_per_sm(locked_blob):
     e = pyemu.EmuBatch(locked_blob, {k: m[k] for k in modelblob.DIMS}, 1)
     scratch = 4 * pyemu.lib().rge_scratch_floats(e.h)
     small = pyemu.lib().rge_small_bytes(e.h)
-    fixed = 640 + ((small + 127) & ~127) + 64 + 1152           # model view (576 B today) + staged arrays + slack + static shared
+    fixed = 768 + ((small + 127) & ~127) + 64 + 256            # model view (<= 768 B) + staged arrays + slack + static shared (128 B today)
     assert (232448 - fixed) // scratch >= 10, (scratch, small)
 
 

@@ -238,3 +238,77 @@ def test_cuda_env_with_domain_randomisation():
     w = env.sim.warn
     assert float(((w & 4) != 0).float().mean()) < 0.05
     assert float(env.fac.on_palm(env.sim.site_xpos).float().mean()) > 0.8
+
+
+@pytest.mark.gpu
+def test_cuda_env_matches_oracle_env_teacher_forced(locked_blob, locked_names):
+    """Rows f1/f2 of SURVEY 8(f) on the GPU tier, as parity rather than smoke: the batched environment on the CUDA engine
+    beside the same environment on the fp64 oracle simulator, 60 env-steps, teacher-forced (before every step the CUDA side
+    receives the oracle side's simulator state and bookkeeping; both get the same action and the same new goals).
+    Observations, the reward terms, done flags and tracker statistics must agree: qpos-derived quantities to 2e-3
+    (one env-step of fp32 vs fp64 contact dynamics), discrete outcomes exactly except at a decision threshold."""
+    import torch
+
+    from robogym_b200.locked_env import STATE_FIELDS, make_cuda_env
+
+    n, steps = 16, 60
+    kw = dict(max_timesteps_per_goal=12, successes_needed=3, auto_reset=False, success_threshold=0.6)
+    ref = cpu_env(locked_blob, locked_names, n, seed=5, pool_size=n, **kw)
+    env = make_cuda_env(n, seed=5, pool_size=n, **kw)
+    ref.reset()
+    env.reset()
+    rng = np.random.RandomState(0)
+    book = ("goal_quat", "prev_dist", "t", "steps_since_last_goal", "consecutive_success", "successes_so_far", "goals_so_far", "success_pending", "first_drop")
+    worst = dict(qpos=0.0, reward=0.0)
+    mism = 0
+    for k in range(steps):
+        for f in STATE_FIELDS:                       # teacher forcing: oracle state -> CUDA engine
+            getattr(env.sim, f).copy_(getattr(ref.sim, f).to(device=env.device, dtype=getattr(env.sim, f).dtype))
+        for f in book:
+            getattr(env, f).copy_(getattr(ref, f).to(device=env.device, dtype=getattr(env, f).dtype))
+        a = rng.uniform(-1, 1, (n, 20))
+        g = ref.sample_goals(n)
+        o1, r1, d1, i1 = ref.step(torch.as_tensor(a), new_goals=g)
+        o2, r2, d2, i2 = env.step(torch.as_tensor(a, dtype=torch.float32, device=env.device), new_goals=g.to(env.device, torch.float32))
+        for key in ("cube_pos", "cube_quat", "hand_angle", "fingertip_pos", "qpos"):
+            worst["qpos"] = max(worst["qpos"], float((o2[key].cpu().double() - o1[key]).abs().max()))
+        near = (i1["goal_dist"] - ref.success_threshold).abs() < 5e-3          # a success decided within fp32 noise of the threshold
+        worst["reward"] = max(worst["reward"], float((r2.cpu().double() - r1)[~near].abs().max()) if (~near).any() else 0.0)
+        same = (d2.cpu() == d1) & (i2["goal_achieved"].cpu() == i1["goal_achieved"]) & (i2["fell_down"].cpu() == i1["fell_down"]) & \
+               (i2["successes_so_far"].cpu() == i1["successes_so_far"]) & (i2["goals_so_far"].cpu() == i1["goals_so_far"])
+        mism += int((~same & ~near).sum())
+        assert float((i2["goal_dist"].cpu().double() - i1["goal_dist"]).abs().max()) < 2e-2
+    assert int(env.sim.warn.max()) == 0
+    assert worst["qpos"] < 2e-2, worst            # worst single environment-step over 960 (contact-mode switches included)
+    assert worst["reward"] < 2e-2, worst
+    assert mism == 0
+    assert int(ref.successes_so_far.sum()) > 0 and int(ref.goals_so_far.max()) > 1          # the run did exercise successes and goal switches
+
+
+@pytest.mark.gpu
+def test_randomised_env_with_reference_capacities_never_overflows():
+    """the randomised stack (friction up to 5x, joint limits, gains, timesteps) used to fill the 32-contact /
+    64-row buffers.  With run-time capacities at the reference's sizes for contacts (nconmax=100, assets.xml:6) and 160
+    single-row elements, 200 env-steps at 2048 environments must not set the contact-full / rows-full bits at all."""
+    import torch
+
+    from robogym_b200 import engine
+    from robogym_b200.locked_env import BatchedLockedEnv
+    import json
+
+    here = os.path.join(os.path.dirname(HERE), "robogym_b200")
+    blob = open(os.path.join(here, "assets", "dactyl_locked.rgm"), "rb").read()
+    names = json.load(open(os.path.join(here, "assets", "dactyl_locked.names.json")))
+    model = engine.DeviceModel(blob, 0)
+    dev = torch.device("cuda", 0)
+    factory = lambda n: engine.BatchedSim(model, n, 10, outputs=("site_xpos", "act_force", "ncon", "warn"), contact_capacity=100, row_capacity=160, dofs_per_contact=24)
+    env = BatchedLockedEnv(factory, model.host, names, 2048, dev, seed=3, pool_size=512, randomize=True)
+    env.reset()
+    gen = torch.Generator(device=dev); gen.manual_seed(0)
+    worst = 0
+    for k in range(200):
+        env.step(torch.rand(2048, 20, device=dev, generator=gen) * 2 - 1)
+        worst = max(worst, int(env.sim.ncon.max()))
+    w = env.sim.warn
+    assert int((w & 3).max()) == 0 and int((w & 32).max()) == 0, (int(w.max()), worst)
+    assert worst <= 100
