@@ -57,8 +57,8 @@ def sum_over_ranks(x, dist, device):
     return float(t.item())
 
 
-def load_blob():
-    with open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.rgm"), "rb") as f:
+def load_blob(asset="dactyl_locked"):
+    with open(os.path.join(ROOT, "robogym_b200", "assets", asset + ".rgm"), "rb") as f:
         return f.read()
 
 
@@ -119,24 +119,56 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- CPU arm (oracle port of the reference path)
+class _CpuEnv:
+    """One dactyl/locked environment on the fp64 CPU port, driven with the GPU arm's workload (SURVEY 8(d) cfg 2: relative
+    full-range actions, reset when the cube leaves the palm)."""
+
+    def __init__(self, blob, seed):
+        import numpy as np
+
+        from oracle import pyoracle
+        from robogym_b200 import modelblob
+
+        self.np = np
+        self.om = pyoracle.OracleModel(blob)
+        self.d = pyoracle.OracleData(self.om)
+        m = modelblob.unpack(blob)
+        self.P = control_matrix(m)
+        self.cr = self.om.field("actuator_ctrlrange").reshape(-1, 2)
+        self.site = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.names.json")))["site"].index("cube:center")
+        self.rng = np.random.RandomState(seed)
+        self.d.ctrl[:] = self.cr.mean(1)
+        for _ in range(20):
+            self.d.env_step(NSUB)
+        self.q0, self.c0 = self.d.qpos.copy(), self.d.ctrl.copy()
+        self.reset()
+
+    def reset(self):
+        d, np = self.d, self.np
+        d.qpos[:] = self.q0
+        d.qpos[0:3] += 0.005 * self.rng.randn(3)
+        q = self.rng.randn(4)
+        d.qpos[3:7] = q / np.linalg.norm(q)
+        d.qvel[:] = 0
+        d.userdata[:] = 0
+        d.qacc_warmstart[:] = 0
+        d.ctrl[:] = self.c0
+
+    def step(self):
+        d, np, cr = self.d, self.np, self.cr
+        a = self.rng.uniform(-1, 1, len(cr))
+        d.ctrl[:] = np.clip(self.P @ d.qpos + a * (cr[:, 1] - cr[:, 0]) / 2, cr[:, 0], cr[:, 1])
+        d.env_step(NSUB)
+        if d.site_xpos.reshape(-1, 3)[self.site, 2] <= 0.04:
+            self.reset()
+
+
 def _cpu_worker(args):
     blob, seed, n_steps = args
-    import numpy as np
-
-    from oracle import pyoracle
-
-    om = pyoracle.OracleModel(blob)
-    d = pyoracle.OracleData(om)
-    cr = om.field("actuator_ctrlrange").reshape(-1, 2)
-    rng = np.random.RandomState(seed)
-    d.ctrl[:] = cr.mean(1)
-    for _ in range(5):
-        d.env_step(NSUB)
+    env = _CpuEnv(blob, seed)
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        a = rng.uniform(-1, 1, len(cr))
-        d.ctrl[:] = np.clip(d.ctrl + ACTION_SCALE * a * (cr[:, 1] - cr[:, 0]) / 2, cr[:, 0], cr[:, 1])
-        d.env_step(NSUB)
+        env.step()
     return time.perf_counter() - t0
 
 
@@ -149,7 +181,9 @@ def cpu_baseline(blob, seconds=10.0):
     n = max(20, int(seconds / (probe / 20)))
     t = _cpu_worker((blob, 2, n))
     return {"value": n / t, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{n} env-steps (x{NSUB} substeps) of one dactyl/locked env, relative random actions, fp64 CPU port (oracle/)"}
+            "sample": f"{n} env-steps (x{NSUB} substeps) of one dactyl/locked env, the GPU arm's workload (relative full-range actions, reset on drop), "
+                      "fp64 CPU port of the reference path (oracle/: dense, scalar, written for clarity -- NOT mujoco-py, which is not installable here); "
+                      "one otherwise idle core: under full load the per-core rate is lower (see --impl reference: value / cores)"}
 
 
 _REF = {}
@@ -157,27 +191,13 @@ _REF = {}
 
 def _ref_init(blob, base_seed):
     """Pool initializer: one persistent oracle environment per worker process (model loaded and settled once)."""
-    import numpy as np
-
-    from oracle import pyoracle
-
-    om = pyoracle.OracleModel(blob)
-    d = pyoracle.OracleData(om)
-    cr = om.field("actuator_ctrlrange").reshape(-1, 2)
-    d.ctrl[:] = cr.mean(1)
-    for _ in range(20):
-        d.env_step(NSUB)
-    _REF.update(om=om, d=d, cr=cr, rng=np.random.RandomState(base_seed + os.getpid()))
+    _REF.update(env=_CpuEnv(blob, base_seed + os.getpid()))
 
 
 def _ref_step(n_steps):
-    import numpy as np
-
-    d, cr, rng = _REF["d"], _REF["cr"], _REF["rng"]
+    env = _REF["env"]
     for _ in range(n_steps):
-        a = rng.uniform(-1, 1, len(cr))
-        d.ctrl[:] = np.clip(d.ctrl + ACTION_SCALE * a * (cr[:, 1] - cr[:, 0]) / 2, cr[:, 0], cr[:, 1])
-        d.env_step(NSUB)
+        env.step()
     return n_steps
 
 
@@ -226,13 +246,14 @@ def run_reference_arm(args):
         dt = time.perf_counter() - t0
     value = cores * per_step * args.steps / dt
     sample = (f"each bench step = {cores} persistent worker processes x {per_step} env-steps of one dactyl/locked env each "
-              f"(fp64 CPU port of the reference path; 10 substeps + forward per env-step)")
+              f"(fp64 CPU port of the reference path -- dense, scalar, unoptimised, NOT mujoco-py; 10 substeps + forward per env-step; "
+              f"per-core rate under this full load: {value / cores:.0f} env-steps/s)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "dactyl/locked (BASELINE.json configs[1]): ShadowHand + locked cube, 10 substeps of 0.008 s + forward per env-step, "
-                                   "relative random actions (ctrl += 0.3*a*half-range); CPU arm = bounded sample of that workload"},
-            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": CONFIGS["locked"]["label"] + ", 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
+                                   "ctrl = clip(P qpos + a*range/2), reset of environments whose cube left the palm; CPU arm = bounded sample of that workload"},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "per_core_under_load": value / cores, "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -257,24 +278,52 @@ def newest_profile_metrics():
     return None
 
 
+CONFIGS = {
+    # BASELINE.json configs[1] (the headline) and configs[2]; capacities per environment = (contacts, single-row elements, dofs per contact), 0 = engine default
+    "locked": dict(asset="dactyl_locked", nenv=8192, caps=(0, 0, 0),
+                   label="dactyl/locked (BASELINE.json configs[1], SURVEY 8(d) cfg 2): ShadowHand + locked cube, nq38/nv36/nu20"),
+    "full_perpendicular": dict(asset="dactyl_full_perpendicular", nenv=4096, caps=(64, 256, 32),
+                               label="dactyl/full_perpendicular (BASELINE.json configs[2], SURVEY 8(d) cfg 3 without per-env parameter randomisation): "
+                                     "ShadowHand + Rubik's cube (26 cubelets, 6 face drivers), nq170/nv168/nu20"),
+}
+
+
+def control_matrix(m):
+    """ctrl = P qpos for the position actuators (joint -> 1, fixed tendon -> its joint coefficients): what
+    robot/shadow_hand/hand_interface.py:245-266 tabulates, read off the compiled transmissions."""
+    import numpy as np
+
+    P = np.zeros((m["nu"], m["nq"]))
+    for i in range(m["nu"]):
+        tid = int(m["actuator_trnid"][i])
+        if m["actuator_trntype"][i] == 0:
+            P[i, m["jnt_qposadr"][tid]] = 1.0
+        else:
+            for w in range(m["tendon_adr"][tid], m["tendon_adr"][tid] + m["tendon_num"][tid]):
+                P[i, m["jnt_qposadr"][int(m["wrap_objid"][w])]] = m["wrap_prm"][w]
+    return P
+
+
 class Workload:
     """SURVEY.md 8(d) cfg 2: a ~ U(-1,1)^20, ctrl = clip(P qpos_hand + a * range / 2, ctrlrange) (relative actions,
     robogym/robot/robot_interface.py:247-278), held for the 10 substeps of an env-step; an environment whose cube left
     the palm is reset (CubeEnv._reset style: settled hand, cube position jitter N(0, 0.005^2), uniform random cube
-    orientation) before the next step, so dropped cubes do not make steps cheaper."""
+    orientation) before the next step, so dropped cubes do not make steps cheaper.  Both dactyl scenes start their qpos
+    with the cube's three slide joints and its ball joint."""
 
     def __init__(self, sim, model, names, dev, gen):
         import torch
 
-        from robogym_b200.batched_env import ShadowHandCubeFacade
-
         self.torch, self.sim, self.gen, self.dev = torch, sim, gen, dev
-        self.facade = ShadowHandCubeFacade(model.host, names, dev)
         m = model.host
         self.nu = m["nu"]
         N = sim.nenv
-        lo, hi = self.facade.ctrl_lo, self.facade.ctrl_hi
-        sim.ctrl.copy_((0.5 * (lo + hi)).repeat(N, 1))
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.P = torch.tensor(control_matrix(m), **f32)
+        cr = m["actuator_ctrlrange"].reshape(-1, 2)
+        self.ctrl_lo, self.ctrl_hi = torch.tensor(cr[:, 0], **f32), torch.tensor(cr[:, 1], **f32)
+        self.cube_site = names["site"].index("cube:center")
+        sim.ctrl.copy_((0.5 * (self.ctrl_lo + self.ctrl_hi)).repeat(N, 1))
         for _ in range(20):                              # locked.py:200-205: settle with zero actions
             sim.step()
         self.q0, self.c0 = sim.qpos.clone(), sim.ctrl.clone()
@@ -298,10 +347,14 @@ class Workload:
     def next_ctrl(self):
         t, sim = self.torch, self.sim
         a = t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1
-        return self.facade.denormalize_position_control(a, sim.qpos, relative_action=True)
+        center = sim.qpos @ self.P.T
+        return t.minimum(t.maximum(center + a * 0.5 * (self.ctrl_hi - self.ctrl_lo), self.ctrl_lo), self.ctrl_hi)
+
+    def on_palm(self):
+        return self.sim.site_xpos[:, self.cube_site, 2] > 0.04      # envs/dactyl/common/cube_utils.py:17-23
 
     def auto_reset(self):
-        dropped = ~self.facade.on_palm(self.sim.site_xpos)
+        dropped = ~self.on_palm()
         self.reset(dropped)
         return dropped
 
@@ -324,13 +377,16 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     build.build()
-    blob = load_blob()
-    names = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", "dactyl_locked.names.json")))
+    cfg = CONFIGS[args.config]
+    blob = load_blob(cfg["asset"])
+    names = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", cfg["asset"] + ".names.json")))
     model = engine.DeviceModel(blob, local)
     strong = args.scaling == "strong"
-    N = NENV_PER_GPU // world if strong else NENV_PER_GPU      # weak: 8192 envs per GPU; strong: 8192 per box
+    NBOX = cfg["nenv"]
+    N = NBOX // world if strong else NBOX                      # weak: the config's batch per GPU; strong: per box
     lo_env, hi_env = shard_range(N * world, rank, world)
-    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"))
+    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"), contact_capacity=cfg["caps"][0],
+                            row_capacity=cfg["caps"][1], dofs_per_contact=cfg["caps"][2])
     m = model.host
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
     gen = torch.Generator(device=dev)
@@ -373,7 +429,7 @@ def run_gpu_arm(args):
     t_dev = max_over_ranks(sum(step_ms) / 1e3, dist, dev)
     total_steps = sum_over_ranks(float(N * args.steps), dist, dev)
     value = total_steps / t_dev
-    on_palm = float(wl.facade.on_palm(sim.site_xpos).float().mean().item())
+    on_palm = float(wl.on_palm().float().mean().item())
     warn = int(warn.item())
 
     # ---- timed region 2: end to end through the public API with host buffers
@@ -382,9 +438,8 @@ def run_gpu_arm(args):
     h_v = torch.empty(N, nv, dtype=torch.float32).pin_memory()
     h_q.copy_(sim.qpos)
     rng = np.random.RandomState(rank_seed(99, rank) % (2 ** 31))
-    P = wl.facade.P.cpu().numpy()
-    hidx = wl.facade.hand_qpos_idx.cpu().numpy()
-    lo_h, hi_h = wl.facade.ctrl_lo.cpu().numpy(), wl.facade.ctrl_hi.cpu().numpy()
+    P = wl.P.cpu().numpy()
+    lo_h, hi_h = wl.ctrl_lo.cpu().numpy(), wl.ctrl_hi.cpu().numpy()
     half_h = 0.5 * (hi_h - lo_h)
     if dist is not None:
         dist.barrier()
@@ -394,7 +449,7 @@ def run_gpu_arm(args):
     e0.record()
     for k in range(args.steps):
         # the host computes this step's control from the observation it read back last step
-        np.clip(h_q.numpy()[:, hidx] @ P.T + acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
+        np.clip(h_q.numpy() @ P.T + acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
         sim.ctrl.copy_(h_ctrl, non_blocking=True)       # H2D of this step's inputs
         sim.step()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
@@ -410,10 +465,10 @@ def run_gpu_arm(args):
         kernel_s = statistics.mean(step_ms) / 1e3
         achieved = ALGO_BYTES_PER_ENV_STEP * N / kernel_s / 1e9
         info = sim.launch_info()
-        prof = newest_profile_metrics()
+        prof = newest_profile_metrics() if args.config == "locked" else None
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": prof["dram_bytes"] * N / NENV_PER_GPU if prof else None,
+                "traffic": prof["dram_bytes"] * N / NENV_PER_GPU if prof else None,   # the capture is one 8192-env launch
                 "traffic_unit": "bytes per launch (dram__bytes_read+write of rg_step_kernel, ncu --set full; %s)" % (prof["file"] if prof else "no capture"),
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * N,
                 "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback 6.65 TB/s",
@@ -428,9 +483,8 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "dactyl/locked (BASELINE.json configs[1], SURVEY 8(d) cfg 2): ShadowHand + locked cube, nq38/nv36/nu20, batch %d per GPU, "
-                                   "10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): ctrl = clip(P qpos + a*range/2), "
-                                   "auto-reset of environments whose cube left the palm" % N,
+            "config": {"workload": cfg["label"] + ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
+                                   "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N,
                        "envs_per_gpu": N, "substeps": NSUB, "physics_substeps_per_s": value * NSUB,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "launch": info, "cubes_on_palm_at_end": on_palm, "resets_in_timed_region_rank0": int(resets.item()),
@@ -464,6 +518,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 8192 envs per GPU; strong: 8192 envs per box")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

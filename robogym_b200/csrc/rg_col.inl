@@ -82,6 +82,9 @@ RG_DEV void rg_hull_scan(const RG_MODEL_T& m, const RgGeomView& v, const float* 
     if (d > best) { best = d; idx = k; }
   }
 }
+#ifndef RG_SCAN_UNROLL
+#define RG_SCAN_UNROLL RG_UNROLL4   /* loads in flight per lane and hull (8 measured slower: 223 k vs 228 k env-steps/s, code size) */
+#endif
 /* both hulls of a pair in one loop, so that the loads of the two scans are in flight together (the scan is a chain of
    L2 round trips, not arithmetic); same visiting order per hull as rg_hull_scan */
 RG_DEV void rg_hull_scan2(const RG_MODEL_T& m, const RgGeomView& v1, const float* d1, const RgGeomView& v2, const float* d2, int first, int stride,
@@ -90,7 +93,7 @@ RG_DEV void rg_hull_scan2(const RG_MODEL_T& m, const RgGeomView& v1, const float
   const int n1 = v1.type == RG_GEOM_MESH ? v1.vnum : 0, n2 = v2.type == RG_GEOM_MESH ? v2.vnum : 0;
   const int n = n1 > n2 ? n1 : n2;
   RG_STAT(rg_stat_climb += (n1 - first + stride - 1) / stride + (n2 - first + stride - 1) / stride;)
-  RG_UNROLL4 for (int k = first; k < n; k += stride) {
+  RG_SCAN_UNROLL for (int k = first; k < n; k += stride) {
     float p[4], q[4];
     const int k1 = k < n1 ? k : 0, k2 = k < n2 ? k : 0;     /* clamped: a repeated vertex 0 never wins the strict comparison */
     RG_LDG4(m.mesh_vert4, v1.vadr + k1, p);
@@ -491,7 +494,11 @@ RG_DEV_NOINLINE void rg_mpr_batch(const RgCtx c, const int* cand2, const int* li
     LV(busy) = S.state < RG_MPR_DONE;
     RG_PHASE_END
     next += wtot / RG_GRP;
+#ifdef RG_MPR_CTA_TRIPS
+    if (!RG_CTA_ANY(RG_WARP_OR(busy))) break;   /* every warp of the CTA runs the same number of trips (one barrier per trip) */
+#else
     if (!RG_WARP_OR(busy)) break;
+#endif
     RG_STAT(rg_stat_x[4]++;)
     RG_GROUP_ARGMAX(b1, i1);
     RG_GROUP_ARGMAX(b2, i2);

@@ -23,6 +23,7 @@
 #define RG_NOUNROLL
 #define RG_UNROLL2
 #define RG_UNROLL4
+#define RG_UNROLL8
 #define RG_PHASE_BEGIN for (int lane = 0; lane < 32; ++lane) {
 #define RG_PHASE_END }
 #define RG_LANE_DECL
@@ -46,6 +47,7 @@
 #define RG_NOUNROLL _Pragma("unroll 1")
 #define RG_UNROLL2 _Pragma("unroll 2")
 #define RG_UNROLL4 _Pragma("unroll 4")
+#define RG_UNROLL8 _Pragma("unroll 8")
 #define RG_PHASE_BEGIN {
 #define RG_PHASE_END } __syncwarp();
 #define RG_LANE_DECL const int lane = threadIdx.x & 31;
@@ -68,7 +70,10 @@ extern __shared__ __align__(128) unsigned char rg_smem_raw[];
 #define RG_SKEW 0
 #endif
 #if RG_SKEW == 0
-#define RG_CTA_SYNC() __syncthreads()
+/* Only the warps that hold an environment in this round take part (the last round of a launch is usually partial): named
+ * barrier 1 over rg_bar_threads threads; barrier 0 (__syncthreads) stays for the round boundaries in rg_step_kernel. */
+__shared__ int rg_bar_threads;
+#define RG_CTA_SYNC() asm volatile("bar.sync 1, %0;" ::"r"(rg_bar_threads) : "memory")
 #else
 /* Skewed variant: a warp may run up to RG_SKEW stages ahead of the slowest warp of its CTA.  Stage boundary k is an
  * mbarrier (ring of RG_SKEW+1): arrive on boundary k, then wait for boundary k-RG_SKEW.  A warp passes boundary k+R-1

@@ -44,6 +44,7 @@ struct RgKernelArgs {
   const float* over_ptr[RG_MAX_PARAM_OVERRIDES]; /* [nenv][cnt] in global memory */
   const int* order;   /* [nenv] slot -> environment (work-sorted, see rg_order_kernel) or nullptr = identity */
   const int* nslots;  /* device: number of slots of a subset launch (rg_step_subset) or nullptr = every environment */
+  int* counter;       /* device: next unassigned slot of this launch (zeroed before the launch) */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,7 +122,6 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   __syncthreads();
 
   const int warp = threadIdx.x >> 5;
-  if (warp >= args.warps) return;
   float* s = scratch0 + (size_t)warp * args.L.total;   /* L.total is a multiple of 4 floats: every per-warp area stays 16-byte aligned */
   /* with per-env overrides every warp keeps its own model view + a copy of this env's rows after the scratch */
   RgModelDev* wm = sm;
@@ -131,18 +131,23 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     wm = (RgModelDev*)base;
     wover = (float*)(base + model_bytes);
   }
-  /* every warp of the CTA runs the same number of iterations (the stage barriers need all of them) */
-  const int stride = gridDim.x * args.warps;
+  /* Rounds: the CTA takes the next `warps` slots of the (cost-sorted) slot table from a device-wide counter, one slot per
+     warp, and its warps walk the step in lock-step.  CTAs that finish early simply take more rounds (no static striding,
+     no tail), and a partial last round runs with fewer warps instead of padding (the stage barriers count only the warps
+     that hold an environment). */
+  __shared__ int sh_slot0;
   const int total = args.nslots ? *args.nslots : args.io.nenv;
-  const int iters = (total + stride - 1) / stride;   /* 0 for an empty subset */
-  for (int it = 0; it < iters; it++) {
-    /* the slot table is sorted by cost: walk the CTAs forwards in even iterations and backwards in odd ones, so that no
-       CTA collects the expensive end of every band (CTAs do not synchronise with each other: the slowest one is the
-       kernel time); padding slots replay the cheapest environment and discard the result */
-    const int pos = (it & 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-    const int slot = it * stride + pos * args.warps + warp;
-    const int valid = slot < total;
-    const int e = args.order ? args.order[valid ? slot : 0] : (valid ? slot : 0);
+  for (;;) {
+    __syncthreads();                                   /* everybody is done with the previous round (and with sh_slot0) */
+    if (threadIdx.x == 0) sh_slot0 = atomicAdd(args.counter, args.warps);
+    __syncthreads();
+    const int slot0 = sh_slot0;
+    if (slot0 >= total) break;
+    const int nact = total - slot0 < args.warps ? total - slot0 : args.warps;
+    if (threadIdx.x == 0) rg_bar_threads = 32 * nact;
+    __syncthreads();
+    if (warp >= nact) continue;
+    const int e = args.order ? args.order[slot0 + warp] : slot0 + warp;
     if (args.nover > 0) {
       const int lane = threadIdx.x & 31;
       for (int i = lane; i < (int)(sizeof(RgModelDev) / 4); i += 32) ((int*)wm)[i] = ((const int*)sm)[i];
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       if (lane < args.nover) *(int*)((char*)wm + args.over_off[lane]) = (int)((unsigned char*)(wover + args.over_dst[lane]) - rg_smem_raw);
       __syncwarp();
     }
-    rg_env_step((int)((unsigned char*)wm - rg_smem_raw), args.L, s, (int)(s - (float*)rg_smem_raw), args.io, e, args.nsub, args.final_forward, valid);
+    rg_env_step((int)((unsigned char*)wm - rg_smem_raw), args.L, s, (int)(s - (float*)rg_smem_raw), args.io, e, args.nsub, args.final_forward, 1);
   }
 }
 
@@ -181,7 +186,8 @@ __global__ void __launch_bounds__(1024) rg_order_kernel(const int* __restrict__ 
   const int t = threadIdx.x;
   bin[t] = 0;
   __syncthreads();
-  for (int e = t; e < nenv; e += 1024) atomicAdd(&bin[min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1);
+  /* most expensive first: rounds are handed out in slot order, so the launch ends with the cheap environments (short tail) */
+  for (int e = t; e < nenv; e += 1024) atomicAdd(&bin[RG_ORDER_BINS - 1 - min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1);
   __syncthreads();
   /* exclusive scan of the 1024 bins */
   const int v = bin[t];
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(1024) rg_order_kernel(const int* __restrict__ 
   __syncthreads();
   bin[t] = x - v + (t >= 32 ? wsum[(t >> 5) - 1] : 0);
   __syncthreads();
-  for (int e = t; e < nenv; e += 1024) order[atomicAdd(&bin[min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1)] = e;
+  for (int e = t; e < nenv; e += 1024) order[atomicAdd(&bin[RG_ORDER_BINS - 1 - min(max(cost[e], 0), RG_ORDER_BINS - 1)], 1)] = e;
 }
 /* slot table of a subset launch: the selected environments in ascending order (one CTA, ballot + scan compaction) */
 __global__ void __launch_bounds__(1024) rg_subset_kernel(const uint8_t* __restrict__ mask, int* __restrict__ order, int* __restrict__ count, int nenv) {
@@ -250,6 +256,7 @@ struct rg_batch {
   int* d_cost = nullptr;   /* work estimate written by the last launch */
   int* d_subset = nullptr; /* [nenv + 1] slot table of a subset launch, followed by its length */
   RgLayout L;              /* scratch layout for this batch's capacities */
+  int* d_counter = nullptr; /* slot counter of the launch in flight */
   int* d_sep = nullptr;    /* [nenv][RG_NSEP] separating-axis cache of the narrow phase (speeds it up; results do not depend on it) */
   int balance = 1;
 };
@@ -391,19 +398,8 @@ static int rg_batch_size(rg_batch* b) {
   int warps = (maxsmem - fixed) / per_warp;
   if (warps < 1) return rg_fail(-3, "rg_batch: model scratch does not fit in shared memory");
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
-  /* every warp of a CTA runs the same number of environments (stage barriers), so pick the warp count
-     that wastes the fewest padded slots: maximise padding-efficiency x warps^0.9 */
-  {
-    int best = warps;
-    double best_score = -1.0;
-    for (int w = warps; w >= 1; w--) {
-      int c = (nenv + w - 1) / w; if (c > sms) c = sms;
-      const long long slots = (long long)((nenv + (long long)c * w - 1) / ((long long)c * w)) * c * w;
-      const double score = (double)nenv / (double)slots * pow((double)w, 0.9);
-      if (score > best_score + 1e-9) { best_score = score; best = w; }
-    }
-    warps = best;
-  }
+  /* rounds are handed out dynamically and a partial round runs with fewer warps, so more resident warps never cost padding */
+  if (warps > nenv) warps = nenv;
   const char* wenv = getenv("RG_WARPS_PER_CTA");
   if (wenv && atoi(wenv) > 0 && atoi(wenv) <= RG_MAX_WARPS && per_warp * atoi(wenv) + fixed <= maxsmem) warps = atoi(wenv);
   b->warps = warps;
@@ -436,6 +432,7 @@ int rg_batch_create_ex(const rg_model* m, int nenv, int contact_capacity, int ro
   cudaError_t e = cudaMalloc((void**)&b->d_order, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_subset, sizeof(int) * ((size_t)nenv + 1));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_counter, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_sep, sizeof(int) * (size_t)nenv * RG_NSEP);
   if (e == cudaSuccess) { rg_iota_kernel<<<(nenv + 255) / 256, 256>>>(b->d_order, b->d_cost, b->d_sep, nenv); e = cudaDeviceSynchronize(); }   /* set-up call: may synchronise (the stepping calls never do) */
   if (e != cudaSuccess) { std::string msg = std::string("rg_batch_create: CUDA: ") + cudaGetErrorString(e); rg_batch_destroy(b); return rg_fail(-2, msg); }
@@ -448,6 +445,7 @@ void rg_batch_destroy(rg_batch* b) {
   if (b->d_cost) cudaFree(b->d_cost);
   if (b->d_subset) cudaFree(b->d_subset);
   if (b->d_sep) cudaFree(b->d_sep);
+  if (b->d_counter) cudaFree(b->d_counter);
   delete b;
 }
 
@@ -563,6 +561,8 @@ static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_
     args.nslots = b->d_subset + b->nenv;
     args.io.cost = nullptr;
   }
+  args.counter = b->d_counter;
+  RG_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(int), (cudaStream_t)stream));
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());
   if (!mask && b->balance && nsub > 0) {

@@ -79,16 +79,31 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   return L;
 }
 
-/* mj_forward: everything but the integrator */
+/* mj_forward: everything but the integrator.  RG_SYNC_LEVEL picks which stage boundaries are CTA barriers (lock-step keeps
+   the warps of a CTA in the same code): 2 = every stage (default), 1 = only before the big stages (collision, constraint
+   rows, solver), 0 = before collision and the solver only. */
+#ifndef RG_SYNC_LEVEL
+#define RG_SYNC_LEVEL 2
+#endif
+#if RG_SYNC_LEVEL >= 2
+#define RG_SYNC_SMALL() RG_CTA_SYNC()
+#else
+#define RG_SYNC_SMALL()
+#endif
+#if RG_SYNC_LEVEL >= 1
+#define RG_SYNC_MID() RG_CTA_SYNC()
+#else
+#define RG_SYNC_MID()
+#endif
 RG_DEV_NOINLINE void rg_forward(const RgCtx c) {
   RG_PROF_BEGIN
-  RG_CTA_SYNC(); rg_kinematics(c); RG_PROF(c, 0)
-  RG_CTA_SYNC(); rg_massmatrix(c); RG_PROF(c, 1)
-  RG_CTA_SYNC(); rg_bias(c); RG_PROF(c, 2)
-  RG_CTA_SYNC(); rg_tendon(c); RG_PROF(c, 3)
-  RG_CTA_SYNC(); rg_forces(c); RG_PROF(c, 4)
+  RG_SYNC_SMALL(); rg_kinematics(c); RG_PROF(c, 0)
+  RG_SYNC_SMALL(); rg_massmatrix(c); RG_PROF(c, 1)
+  RG_SYNC_SMALL(); rg_bias(c); RG_PROF(c, 2)
+  RG_SYNC_SMALL(); rg_tendon(c); RG_PROF(c, 3)
+  RG_SYNC_SMALL(); rg_forces(c); RG_PROF(c, 4)
   RG_CTA_SYNC(); rg_collision(c); RG_PROF(c, 5)
-  RG_CTA_SYNC(); rg_make_constraints(c); RG_PROF(c, 6)
+  RG_SYNC_MID(); rg_make_constraints(c); RG_PROF(c, 6)
   RG_CTA_SYNC(); rg_solve(c); RG_PROF(c, 7)
 }
 
@@ -121,7 +136,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   RG_PHASE_END
   for (int sub = 0; sub < nsub; sub++) {
     rg_forward(c);
-    { RG_PROF_BEGIN RG_CTA_SYNC(); rg_euler(c); RG_PROF(c, 8) }
+    { RG_PROF_BEGIN RG_SYNC_SMALL(); rg_euler(c); RG_PROF(c, 8) }
     /* mj_checkPos / mj_checkVel: reset on a bad state, like mj_step does */
     LANEVAR(int, badl);
     RG_PHASE_BEGIN

@@ -58,16 +58,55 @@ for k, c in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     print("%-22s %6.2f%% %6.2f%% %5.1f  %s" % ("%s:%d" % k, 100 * c["samples"] / tot["samples"], 100 * c["instr"] / max(tot["instr"], 1),
                                               c["thr"] / max(c["instr"], 1), ", ".join("%s %.0f%%" % (s[6:], 100 * c[s] / max(c["samples"], 1)) for s in st)))
 
-# ---- per-function view (function = nearest preceding definition line in the same file)
+# ---- per-function view: function (or struct) = nearest preceding definition line in the same file that the PRODUCT build
+# compiles -- definitions inside preprocessor branches that are off in that build (RG_EMU, RG_SKEW > 0, RG_PROFILE, RG_STATS)
+# are skipped, so a sample can no longer be credited to code that is not in the binary
 import os
+MACROS = {"RG_SKEW": 0, "RG_SYNC_LEVEL": 2}          # defined in the product build; RG_EMU / RG_PROFILE / RG_STATS / RG_DEBUG_NEWTON are not
+
+
+def cond_true(expr):
+    e = re.sub(r"defined\s*\(?\s*(\w+)\s*\)?", lambda m: "True" if m.group(1) in MACROS else "False", expr)
+    e = e.replace("&&", " and ").replace("||", " or ")
+    e = re.sub(r"!(?!=)", " not ", e)
+    e = re.sub(r"\b([A-Z_][A-Z0-9_]*)\b", lambda m: str(MACROS.get(m.group(1), 0)) if m.group(1) not in ("True", "False") else m.group(1), e)
+    try:
+        return bool(eval(e, {"__builtins__": {}}, {}))
+    except Exception:
+        return True
+
+
 defs = {}
 root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "robogym_b200", "csrc")
 for f in os.listdir(root):
     L = []
+    stack = []          # (this branch active, some branch of this #if already taken)
     for n, line in enumerate(open(os.path.join(root, f)), 1):
-        m = re.match(r"^(?:template.*\n)?(?:RG_DEV_NOINLINE|RG_DEV|RG_HD|static inline|__global__|__device__)\b.*?\b(rg_\w+)\s*\(", line)
+        t = line.strip()
+        if t.startswith("#"):
+            d = t[1:].strip()
+            if d.startswith("ifdef"):
+                a = d.split()[1] in MACROS; stack.append([a, a])
+            elif d.startswith("ifndef"):
+                a = d.split()[1] not in MACROS; stack.append([a, a])
+            elif d.startswith("if"):
+                a = cond_true(d[2:]); stack.append([a, a])
+            elif d.startswith("elif") and stack:
+                a = (not stack[-1][1]) and cond_true(d[4:]); stack[-1] = [a, stack[-1][1] or a]
+            elif d.startswith("else") and stack:
+                stack[-1] = [not stack[-1][1], True]
+            elif d.startswith("endif") and stack:
+                stack.pop()
+            continue
+        if not all(a for a, _ in stack):
+            continue
+        m = re.match(r"^(?:RG_DEV_NOINLINE|RG_DEV|RG_HD|static inline|__global__|__device__)\b.*?\b(rg_\w+)\s*\(", line)
         if m:
             L.append((n, m.group(1)))
+            continue
+        m = re.match(r"^(?:template\s*<[^>]*>\s*)?struct\s+(\w+)\s*\{", line)
+        if m:
+            L.append((n, "struct " + m.group(1)))
     defs[f] = L
 fagg = collections.defaultdict(lambda: collections.Counter())
 for (f, ln), c in agg.items():
