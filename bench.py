@@ -282,7 +282,7 @@ CONFIGS = {
     # BASELINE.json configs[1] (the headline) and configs[2]; capacities per environment = (contacts, single-row elements, dofs per contact), 0 = engine default
     "locked": dict(asset="dactyl_locked", nenv=8192, caps=(0, 0, 0),
                    label="dactyl/locked (BASELINE.json configs[1], SURVEY 8(d) cfg 2): ShadowHand + locked cube, nq38/nv36/nu20"),
-    "full_perpendicular": dict(asset="dactyl_full_perpendicular", nenv=4096, caps=(64, 256, 32),
+    "full_perpendicular": dict(asset="dactyl_full_perpendicular", nenv=4096, caps=(96, 288, 32),
                                label="dactyl/full_perpendicular (BASELINE.json configs[2], SURVEY 8(d) cfg 3 without per-env parameter randomisation): "
                                      "ShadowHand + Rubik's cube (26 cubelets, 6 face drivers), nq170/nv168/nu20"),
 }

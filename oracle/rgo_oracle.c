@@ -32,7 +32,7 @@ enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_USER = 3 };
 enum { DSBL_CONSTRAINT = 1, DSBL_EQUALITY = 2, DSBL_FRICTIONLOSS = 4, DSBL_LIMIT = 8, DSBL_CONTACT = 16,
        DSBL_PASSIVE = 32, DSBL_GRAVITY = 64, DSBL_CLAMPCTRL = 128, DSBL_WARMSTART = 256,
        DSBL_ACTUATION = 1024, DSBL_REFSAFE = 2048 };
-enum { ROW_EQUALITY = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CONTACT = 3 };
+enum { ROW_EQUALITY = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CONTACT = 3, ROW_CONTACT_ELL = 4 /* first row of an elliptic-cone contact: dim rows follow each other */, ROW_CONTACT_ELLF = 5 /* its friction rows */ };
 
 /* ------------------------------------------------------------------ model */
 struct rgo_model {

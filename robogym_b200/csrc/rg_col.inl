@@ -15,6 +15,19 @@
 static long long rg_stat_hist[2][64] = {{0}}; static long long rg_stat_support = 0, rg_stat_climb = 0, rg_stat_mpr = 0, rg_stat_mpr_hit = 0, rg_stat_narrow = 0, rg_stat_maxsup = 0, rg_stat_cur = 0;
 /* solver / pipeline counters: forwards, newton iterations, refactorisations, line-search evaluations, triangular solves, broad-phase survivors, obb survivors, contacts, rows, mpr iterations */
 static long long rg_stat_x[16] = {0};
+static long long rg_stat_iterhist[16] = {0};
+static long long rg_stat_fliphist[16] = {0};
+static unsigned char rg_stat_act[2048], rg_stat_prev[2048];
+static void rg_stat_flips(int have_factor) {
+  if (have_factor) {
+    int fl = 0, flc = 0;
+    for (int q = 0; q < 512; q++) fl += rg_stat_act[q] != rg_stat_prev[q];
+    for (int q = 512; q < 2048; q++) flc += rg_stat_act[q] != rg_stat_prev[q];
+    rg_stat_fliphist[fl + flc < 15 ? fl + flc : 15]++;
+    rg_stat_x[13] += fl; rg_stat_x[14] += flc; rg_stat_x[15]++;
+  }
+  memcpy(rg_stat_prev, rg_stat_act, sizeof rg_stat_act);
+}
 #define RG_STAT(x) x
 #else
 #define RG_STAT(x)
@@ -80,28 +93,6 @@ RG_DEV void rg_hull_scan(const RG_MODEL_T& m, const RgGeomView& v, const float* 
     RG_LDG4(m.mesh_vert4, v.vadr + k, p);
     const float d = p[0] * dl[0] + p[1] * dl[1] + p[2] * dl[2];
     if (d > best) { best = d; idx = k; }
-  }
-}
-#ifndef RG_SCAN_UNROLL
-#define RG_SCAN_UNROLL RG_UNROLL4   /* loads in flight per lane and hull (8 measured slower: 223 k vs 228 k env-steps/s, code size) */
-#endif
-/* both hulls of a pair in one loop, so that the loads of the two scans are in flight together (the scan is a chain of
-   L2 round trips, not arithmetic); same visiting order per hull as rg_hull_scan */
-RG_DEV void rg_hull_scan2(const RG_MODEL_T& m, const RgGeomView& v1, const float* d1, const RgGeomView& v2, const float* d2, int first, int stride,
-                          float& best1, int& idx1, float& best2, int& idx2) {
-  best1 = best2 = -3.0e38f; idx1 = idx2 = 0x7fffffff;
-  const int n1 = v1.type == RG_GEOM_MESH ? v1.vnum : 0, n2 = v2.type == RG_GEOM_MESH ? v2.vnum : 0;
-  const int n = n1 > n2 ? n1 : n2;
-  RG_STAT(rg_stat_climb += (n1 - first + stride - 1) / stride + (n2 - first + stride - 1) / stride;)
-  RG_SCAN_UNROLL for (int k = first; k < n; k += stride) {
-    float p[4], q[4];
-    const int k1 = k < n1 ? k : 0, k2 = k < n2 ? k : 0;     /* clamped: a repeated vertex 0 never wins the strict comparison */
-    RG_LDG4(m.mesh_vert4, v1.vadr + k1, p);
-    RG_LDG4(m.mesh_vert4, v2.vadr + k2, q);
-    const float e1 = p[0] * d1[0] + p[1] * d1[1] + p[2] * d1[2];
-    const float e2 = q[0] * d2[0] + q[1] * d2[1] + q[2] * d2[2];
-    if (k < n1 && e1 > best1) { best1 = e1; idx1 = k; }
-    if (k < n2 && e2 > best2) { best2 = e2; idx2 = k; }
   }
 }
 RG_DEV void rg_support_world(const RgGeomView& v, const float* loc, const float* dir, float* res) {
@@ -408,6 +399,137 @@ RG_DEV_NOINLINE int rg_narrow_plane(const RgCtx c, int g1, int g2, float margin,
   return 0;
 }
 
+/* ---- box-box: separating-axis test over the 15 candidate axes, then a contact manifold (same construction as the oracle's
+ * box_box, oracle/rgo_collision.inc): face contact = the opposing face of the other box clipped against the reference
+ * face's side planes, every vertex within `margin` of the reference face is a contact (at most 4: the extreme ones along
+ * the face's two tangents); edge-edge contact = the closest points of the two edges.  The 1-point MPR answer cannot hold a
+ * block flat on a table or on another block (robogym/envs/rearrange/holdouts/tests/test_stability.py:215-261).  One lane
+ * per pair; out[7*i..] = dist, pos[3], normal[3] (from box 1 to box 2); returns the number of contacts. */
+RG_DEV_NOINLINE int rg_box_box(const RgCtx c, int g1, int g2, float margin, float* out) {
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  RgGeomView va, vb;
+  rg_geom_view(c, g1, 0.0f, va);
+  rg_geom_view(c, g2, 0.0f, vb);
+  const float* pa = va.pos; const float* pb = vb.pos; const float* a = va.size; const float* b = vb.size;
+  float A[3][3], B[3][3], d[3], C[3][3], AC[3][3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { A[i][k] = va.mat[3 * k + i]; B[i][k] = vb.mat[3 * k + i]; }
+  rg_sub3(d, pb, pa);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { C[i][j] = rg_dot3(A[i], B[j]); AC[i][j] = fabsf(C[i][j]); }
+  float best = -3.0e38f, bestn[3] = {0, 0, 0};
+  int code = -1;
+  for (int i = 0; i < 3; i++) {
+    const float t = rg_dot3(A[i], d), s = fabsf(t) - (a[i] + b[0] * AC[i][0] + b[1] * AC[i][1] + b[2] * AC[i][2]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = i; for (int k = 0; k < 3; k++) bestn[k] = t < 0 ? -A[i][k] : A[i][k]; }
+  }
+  for (int j = 0; j < 3; j++) {
+    const float t = rg_dot3(B[j], d), s = fabsf(t) - (b[j] + a[0] * AC[0][j] + a[1] * AC[1][j] + a[2] * AC[2][j]);
+    if (s > margin) return 0;
+    if (s > best) { best = s; code = 3 + j; for (int k = 0; k < 3; k++) bestn[k] = t < 0 ? -B[j][k] : B[j][k]; }
+  }
+  float beste = -3.0e38f, en[3] = {0, 0, 0};
+  int ecode = -1;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float Lx[3];
+      rg_cross(Lx, A[i], B[j]);
+      const float len = sqrtf(rg_dot3(Lx, Lx));
+      if (len < 1e-6f) continue;
+      for (int k = 0; k < 3; k++) Lx[k] /= len;
+      const float t = rg_dot3(Lx, d);
+      float ra = 0.0f, rb = 0.0f;
+      for (int k = 0; k < 3; k++) { ra += a[k] * fabsf(rg_dot3(Lx, A[k])); rb += b[k] * fabsf(rg_dot3(Lx, B[k])); }
+      const float s = fabsf(t) - (ra + rb);
+      if (s > margin) return 0;
+      if (s > beste) { beste = s; ecode = 6 + 3 * i + j; for (int k = 0; k < 3; k++) en[k] = t < 0 ? -Lx[k] : Lx[k]; }
+    }
+  if (ecode >= 0 && beste > best + 1e-6f) {
+    const int i = (ecode - 6) / 3, j = (ecode - 6) % 3;
+    float ea[3], eb[3];
+    rg_copy3(ea, pa); rg_copy3(eb, pb);
+    for (int k = 0; k < 3; k++) {
+      if (k != i) rg_addscl3(ea, A[k], rg_dot3(en, A[k]) > 0 ? a[k] : -a[k]);
+      if (k != j) rg_addscl3(eb, B[k], rg_dot3(en, B[k]) > 0 ? -b[k] : b[k]);
+    }
+    float w[3];
+    rg_sub3(w, ea, eb);
+    const float uv = C[i][j], uw = rg_dot3(A[i], w), vw = rg_dot3(B[j], w), den = 1.0f - uv * uv;
+    float sa = den > 1e-12f ? (uv * vw - uw) / den : 0.0f, tb = den > 1e-12f ? (vw - uv * uw) / den : 0.0f;
+    sa = rg_clamp(sa, -a[i], a[i]); tb = rg_clamp(tb, -b[j], b[j]);
+    out[0] = beste;
+    for (int k = 0; k < 3; k++) { out[1 + k] = 0.5f * (ea[k] + sa * A[i][k] + eb[k] + tb * B[j][k]); out[4 + k] = en[k]; }
+    return 1;
+  }
+  const int refA = code < 3, ax = refA ? code : code - 3;
+  const float* pr = refA ? pa : pb; const float* pi = refA ? pb : pa;
+  const float* hr = refA ? a : b; const float* hi = refA ? b : a;
+  float (*Rr)[3] = refA ? A : B; float (*Ri)[3] = refA ? B : A;
+  float nr[3];
+  for (int k = 0; k < 3; k++) nr[k] = refA ? bestn[k] : -bestn[k];
+  int iax = 0; float mind = 3.0e38f, isg = 1.0f;
+  for (int k = 0; k < 3; k++) { const float t = rg_dot3(Ri[k], nr); if (-fabsf(t) < mind) { mind = -fabsf(t); iax = k; isg = t > 0 ? -1.0f : 1.0f; } }
+  const int i1 = (iax + 1) % 3, i2 = (iax + 2) % 3, r1 = (ax + 1) % 3, r2 = (ax + 2) % 3;
+  float poly[16][3], tmp[16][3], fc[3];
+  rg_copy3(fc, pi); rg_addscl3(fc, Ri[iax], isg * hi[iax]);
+  for (int q = 0; q < 4; q++) {
+    rg_copy3(poly[q], fc);
+    rg_addscl3(poly[q], Ri[i1], (q == 0 || q == 3) ? hi[i1] : -hi[i1]);
+    rg_addscl3(poly[q], Ri[i2], (q < 2) ? hi[i2] : -hi[i2]);
+  }
+  int np = 4;
+  for (int side = 0; side < 4 && np > 0; side++) {
+    const int r = side < 2 ? r1 : r2;
+    const float sg = (side & 1) ? -1.0f : 1.0f;
+    int nn = 0;
+    for (int q = 0; q < np; q++) {
+      const float* P = poly[q]; const float* Q = poly[(q + 1) % np];
+      float dp[3], dq[3];
+      rg_sub3(dp, P, pr); rg_sub3(dq, Q, pr);
+      const float fp = sg * rg_dot3(dp, Rr[r]) - hr[r], fq = sg * rg_dot3(dq, Rr[r]) - hr[r];
+      const int inp = fp <= 1e-6f, inq = fq <= 1e-6f;   /* a vertex within a micron of the plane counts as inside (see the oracle) */
+      if (inp) { rg_copy3(tmp[nn], P); nn++; }
+      if (inp != inq) {
+        const float t = fp / (fp - fq);
+        for (int k = 0; k < 3; k++) tmp[nn][k] = P[k] + t * (Q[k] - P[k]);
+        nn++;
+      }
+    }
+    np = nn;
+    for (int q = 0; q < np; q++) rg_copy3(poly[q], tmp[q]);
+  }
+  float dist[16], u[16], v[16];
+  int keep[16], nk = 0;
+  for (int q = 0; q < np; q++) {
+    float dq[3];
+    rg_sub3(dq, poly[q], pr);
+    dist[q] = rg_dot3(dq, nr) - hr[ax];
+    u[q] = rg_dot3(dq, Rr[r1]); v[q] = rg_dot3(dq, Rr[r2]);
+    if (dist[q] <= margin) keep[nk++] = q;
+  }
+  if (nk > 4) {
+    int sel[4] = {keep[0], keep[0], keep[0], keep[0]};
+    for (int k = 0; k < nk; k++) {
+      const int q = keep[k];
+      /* extremes along two skewed directions: the edges of the usual polygons (axis-aligned or 45-degree rectangles)
+         are never perpendicular to them, so every extreme is a single vertex and rounding cannot pick another one */
+      const float k1 = u[q] + 0.31f * v[q], k2 = v[q] - 0.31f * u[q];
+      if (k1 < u[sel[0]] + 0.31f * v[sel[0]]) sel[0] = q;
+      if (k1 > u[sel[1]] + 0.31f * v[sel[1]]) sel[1] = q;
+      if (k2 < v[sel[2]] - 0.31f * u[sel[2]]) sel[2] = q;
+      if (k2 > v[sel[3]] - 0.31f * u[sel[3]]) sel[3] = q;
+    }
+    nk = 0;
+    for (int k = 0; k < 4; k++) { int dup = 0; for (int l = 0; l < nk; l++) dup |= keep[l] == sel[k]; if (!dup) keep[nk++] = sel[k]; }
+  }
+  for (int k = 0; k < nk; k++) {
+    const int q = keep[k];
+    float* o = out + 7 * k;
+    o[0] = dist[q];
+    for (int cc = 0; cc < 3; cc++) { o[1 + cc] = poly[q][cc] - 0.5f * dist[q] * nr[cc]; o[4 + cc] = bestn[cc]; }
+  }
+  return nk;
+}
+
 /* append the first `n` survivors (flag per lane) of list `src` to list `dst`, then drop them from `src` */
 RG_DEV void rg_pair(const RG_MODEL_T& m, int k, int& g1, int& g2) {
   if (RG_HAS_PAIRS(m)) { const unsigned p = m.pair_packed[k]; g1 = (int)(p & 255u); g2 = (int)(p >> 8); }
@@ -489,7 +611,10 @@ RG_DEV_NOINLINE void rg_mpr_batch(const RgCtx c, const int* cand2, const int* li
       rg_mulmatT3(d1, S.o1.mat, S.dir);
       rg_mulmatT3(d2, S.o2.mat, S.dir);
       d2[0] = -d2[0]; d2[1] = -d2[1]; d2[2] = -d2[2];
-      rg_hull_scan2(m, S.o1, d1, S.o2, d2, gl, RG_GRP, LV(b1), LV(i1), LV(b2), LV(i2));
+      /* one hull after the other: a fused loop over both (more loads in flight) measured SLOWER (2.17 M vs 1.84 M cycles per
+         env-step in the narrow phase): a box on one side makes half of its loads useless, and the body gets bigger */
+      if (S.o1.type == RG_GEOM_MESH) rg_hull_scan(m, S.o1, d1, gl, RG_GRP, LV(b1), LV(i1));
+      if (S.o2.type == RG_GEOM_MESH) rg_hull_scan(m, S.o2, d2, gl, RG_GRP, LV(b2), LV(i2));
     }
     LV(busy) = S.state < RG_MPR_DONE;
     RG_PHASE_END
@@ -625,7 +750,11 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
       if (lane < n) {
         int g1, g2;
         rg_pair(m, cand2[lane], g1, g2);
+#ifdef RG_NO_BOXBOX   /* A/B measurement only: box-box pairs through MPR (1 point) */
         cv = m.geom_type[g1] != RG_GEOM_PLANE;
+#else
+        cv = m.geom_type[g1] != RG_GEOM_PLANE && !(m.geom_type[g1] == RG_GEOM_BOX && m.geom_type[g2] == RG_GEOM_BOX);
+#endif
       }
       LV(conv) = cv;
       RG_PHASE_END
@@ -646,7 +775,8 @@ RG_DEV_NOINLINE void rg_collision(const RgCtx c) {
           const int k = cand2[lane];
           int g1, g2;
           rg_pair(m, k, g1, g2);
-          cn = rg_narrow_plane(c, g1, g2, fmaxf(m.geom_margin[g1], m.geom_margin[g2]), &LA(cb, 0));
+          const float mg = fmaxf(m.geom_margin[g1], m.geom_margin[g2]);
+          cn = m.geom_type[g1] == RG_GEOM_PLANE ? rg_narrow_plane(c, g1, g2, mg, &LA(cb, 0)) : rg_box_box(c, g1, g2, mg, &LA(cb, 0));
         }
       }
       LV(cnt) = cn;

@@ -32,7 +32,8 @@ struct RgCtx {
 
 #define RG_SI(c, k) (((int*)(RG_SCRATCH(c) + RG_CL(c).scal))[k])
 enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4, RG_S_SIG = 5 /* signature of the solver's active set, see rg_solver_update */,
-       RG_S_WORK = 6 /* work estimate of this launch (Newton iterations, narrow-phase pairs): orders the next launch */ };
+       RG_S_WORK = 6 /* work estimate of this launch (Newton iterations, narrow-phase pairs): orders the next launch */,
+       RG_S_CONE = 7 /* some elliptic contact sits in the middle zone of its cone: its Hessian block moves with every step */ };
 
 /* optional per-stage cycle counters (lane 0 of each warp), dumped at the end of RG_DBG */
 #if !defined(RG_EMU) && defined(RG_PROFILE)

@@ -525,7 +525,8 @@ int rg_batch_launch_info(const rg_batch* b, int* ctas, int* warps, int* smem) {
 
 static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   for (int f = RG_FIELD_QPOS; f <= RG_FIELD_WARMSTART; f++)
-    if (!b->ptr[f]) return rg_fail(-1, "rg_step: qpos, qvel, ctrl, pid and warmstart must be bound");
+    if (!b->ptr[f] && !((f == RG_FIELD_CTRL || f == RG_FIELD_PID) && b->model->hm.view.nu == 0))   /* a model without actuators has no ctrl / PID rows */
+      return rg_fail(-1, "rg_step: qpos, qvel, ctrl, pid and warmstart must be bound");
   io.nenv = b->nenv;
   io.qpos = (float*)b->ptr[RG_FIELD_QPOS]; io.qvel = (float*)b->ptr[RG_FIELD_QVEL]; io.ctrl = (float*)b->ptr[RG_FIELD_CTRL];
   io.pid = (float*)b->ptr[RG_FIELD_PID]; io.warm = (float*)b->ptr[RG_FIELD_WARMSTART]; io.time = (float*)b->ptr[RG_FIELD_TIME];

@@ -127,7 +127,6 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
-  if (m.opt_cone[0] != 0) { err = "model uses elliptic friction cones (option cone=elliptic): not supported by this engine (pyramidal only)"; return false; }
   for (int e = 0; e < m.neq; e++) if (m.eq_active[e]) { err = "model has active equality constraints: not supported by this engine"; return false; }
   int* subtree = (int*)(base + off_subtree);
   int* mrow = (int*)(base + off_mrow);

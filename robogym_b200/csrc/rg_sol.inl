@@ -79,6 +79,79 @@ RG_DEV void rg_contact_col_list(const RgCtx c, const float* r, int d, float sg, 
 }
 RG_DEV float rg_contact_mu(const float* r, int k) { return k <= 2 ? r[14] : (k == 3 ? r[15] : r[16]); }
 
+/* ---- elliptic friction cones (option cone="elliptic", robogym/assets/xmls/robot/ur16e/base.xml:4).  Kept out of line: the
+ * pyramidal models (dactyl) must not pay for this code in their Newton loop's instruction footprint.  One contact has dim
+ * rows (normal + friction directions) with D_0 = 1/R_normal and D_k = D_0 friction_k^2 / mu^2, mu = friction_0 / sqrt(impratio).
+ * With N = mu u_0, U_k = friction_k u_k, T = |U| (coordinates in which the force cone is circular with coefficient mu) the
+ * cost has three zones: top (N >= mu T: nothing), bottom (mu N + T <= 0: every row quadratic) and the middle zone
+ * 1/2 Dm (N - mu T)^2, Dm = D_0 / (mu^2 (1 + mu^2)) = half the squared length of the projection onto the cone's boundary. */
+RG_DEV float rg_cone_mu(const RG_MODEL_T& m, const float* r) { return fmaxf(r[14] * sqrtf(1.0f / m.opt_impratio[0]), 1e-5f); }
+/* zone (0 top, 1 bottom, 2 middle), cost and force F = -gradient at u */
+RG_DEV_NOINLINE int rg_cone_eval(const float* r, float mu, int dim, float D0, const float* u, float* cost, float* F) {
+  float U[6] = {0, 0, 0, 0, 0, 0}, T2 = 0.0f;
+  const float N = u[0] * mu;
+  for (int k = 1; k < 6; k++) if (k < dim) { U[k] = u[k] * rg_contact_mu(r, k); T2 += U[k] * U[k]; }
+  const float T = sqrtf(T2);
+  for (int k = 0; k < 6; k++) F[k] = 0.0f;
+  *cost = 0.0f;
+  if (N >= mu * T) return 0;
+  if (mu * N + T <= 0.0f) {
+    float cst = 0.0f;
+    for (int k = 0; k < 6; k++) if (k < dim) {
+      const float fk = k == 0 ? mu : rg_contact_mu(r, k);
+      const float Dk = D0 * fk * fk / (mu * mu);
+      F[k] = -Dk * u[k]; cst += 0.5f * Dk * u[k] * u[k];
+    }
+    *cost = cst;
+    return 1;
+  }
+  const float Dm = D0 / (mu * mu * (1.0f + mu * mu)), NT = N - mu * T;
+  *cost = 0.5f * Dm * NT * NT;
+  F[0] = -Dm * NT * mu;
+  const float q = Dm * NT * mu / T;
+  for (int k = 1; k < 6; k++) if (k < dim) F[k] = q * rg_contact_mu(r, k) * U[k];
+  return 2;
+}
+/* first and second derivative of the cone cost along u + alpha w */
+RG_DEV_NOINLINE void rg_cone_ray(const float* r, float mu, int dim, float D0, const float* u, const float* w, float alpha, float* g, float* h) {
+  float U[6], V[6], T2 = 0.0f, UV = 0.0f, VV = 0.0f;
+  const float N = (u[0] + alpha * w[0]) * mu, Nd = w[0] * mu;
+  for (int k = 1; k < 6; k++) if (k < dim) {
+    const float fk = rg_contact_mu(r, k);
+    U[k] = (u[k] + alpha * w[k]) * fk; V[k] = w[k] * fk;
+    T2 += U[k] * U[k]; UV += U[k] * V[k]; VV += V[k] * V[k];
+  }
+  const float T = sqrtf(T2);
+  if (N >= mu * T) return;
+  if (mu * N + T <= 0.0f) {
+    for (int k = 0; k < 6; k++) if (k < dim) {
+      const float fk = k == 0 ? mu : rg_contact_mu(r, k);
+      const float Dk = D0 * fk * fk / (mu * mu);
+      *g += Dk * (u[k] + alpha * w[k]) * w[k]; *h += Dk * w[k] * w[k];
+    }
+    return;
+  }
+  const float Dm = D0 / (mu * mu * (1.0f + mu * mu)), NT = N - mu * T;
+  const float Td = UV / T, Tdd = (VV - Td * Td) / T;
+  const float NTd = Nd - mu * Td;
+  *g += Dm * NT * NTd;
+  *h += Dm * (NTd * NTd - NT * mu * Tdd);
+}
+/* dim x dim Hessian block of the middle zone at u (row-major W[6][6], only [0, dim) x [0, dim) is written) */
+RG_DEV_NOINLINE void rg_cone_hessian(const float* r, float mu, int dim, float D0, const float* u, float W[6][6]) {
+  float U[6] = {0, 0, 0, 0, 0, 0}, f[6] = {0, 0, 0, 0, 0, 0}, T2 = 0.0f;
+  const float N = u[0] * mu;
+  for (int k = 1; k < 6; k++) if (k < dim) { f[k] = rg_contact_mu(r, k); U[k] = u[k] * f[k]; T2 += U[k] * U[k]; }
+  const float T = sqrtf(T2), iT = 1.0f / T;
+  const float Dm = D0 / (mu * mu * (1.0f + mu * mu)), NT = N - mu * T;
+  W[0][0] = Dm * mu * mu;
+  for (int k = 1; k < 6; k++) if (k < dim) {
+    W[0][k] = W[k][0] = -Dm * mu * mu * f[k] * U[k] * iT;
+    for (int l = 1; l < 6; l++) if (l < dim)
+      W[k][l] = Dm * mu * f[k] * f[l] * (mu * U[k] * U[l] * iT * iT - NT * ((k == l ? iT : 0.0f) - U[k] * U[l] * iT * iT * iT));
+  }
+}
+
 /* y = M x with the tree-sparse M: row i couples dof i with its ancestors (stored in row i) and with the dofs of its
    subtree, which are the dofs right behind it (entry (d, i) sits depth(d) - depth(i) into row d) */
 RG_DEV_NOINLINE void rg_matvec_phase(const RgCtx c, int y, int x) {
@@ -393,8 +466,9 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     /* first row's diagApprox: tran + mu^2 tran (dim>1) or tran */
     const float mu0 = r[14];
     const float solimp[5] = {prm[0], prm[1], prm[2], prm[3], prm[4]};   /* staged there by rg_collision */
-    rg_row_params(c, r + 22, solimp, r[0], r[13], 0.0f, dim > 1 ? tran + mu0 * mu0 * tran : tran, 0, &R, &aref, &B, &KI);
-    if (dim > 1) {
+    const int elliptic = m.opt_cone[0] == 1;
+    rg_row_params(c, r + 22, solimp, r[0], r[13], 0.0f, (dim > 1 && !elliptic) ? tran + mu0 * mu0 * tran : tran, 0, &R, &aref, &B, &KI);
+    if (dim > 1 && !elliptic) {   /* pyramid edges share R = 2 mu^2 R_normal; an elliptic contact keeps D_0 = 1 / R_normal here */
       float mu = mu0 * sqrtf(1.0f / m.opt_impratio[0]);
       if (mu < 1e-5f) mu = 1e-5f;
       R = fmaxf(1e-12f, 2.0f * mu * mu * R);
@@ -456,9 +530,12 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
   RG_LANE_DECL
   const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
-  LANEVAR(float, part); LANEVAR(int, sigp);
+  LANEVAR(float, part); LANEVAR(int, sigp); LANEVAR(int, conep);
+  const int elliptic = RG_MDEREF(c.mref).opt_cone[0] == 1;
+  RG_STAT(memset(rg_stat_act, 0, sizeof rg_stat_act);)
   RG_PHASE_BEGIN
   float cost = 0.0f;
+  int cone = 0;
   unsigned sig = 0u;   /* which rows are in their quadratic zone: decides whether H must be rebuilt */
   RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
     const float jar = s[L.el_jar + e], D = s[L.el_D + e];
@@ -467,8 +544,8 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
       const float fl = s[L.el_floss + e], rf = fl / D;
       if (jar <= -rf) { f = fl; cost += -0.5f * rf * fl - fl * jar; }
       else if (jar >= rf) { f = -fl; cost += -0.5f * rf * fl + fl * jar; }
-      else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); }
-    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); }
+      else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); RG_STAT(rg_stat_act[e] = 1;) }
+    } else if (jar < 0.0f) { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); RG_STAT(rg_stat_act[e] = 1;) }
     else f = 0.0f;
     s[L.el_f + e] = f;
   }
@@ -480,19 +557,28 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
     const float D = prm[0];
     float F[6] = {0, 0, 0, 0, 0, 0};
     if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; sig += rg_mix((unsigned)(1000 + 16 * k)); } }
+    else if (elliptic) {
+      float cc;
+      const int zone = rg_cone_eval(r, rg_cone_mu(RG_MDEREF(c.mref), r), dim, D, u, &cc, F);
+      cost += cc;
+      if (zone) sig += rg_mix((unsigned)(1000 + 16 * k + zone));
+      if (zone == 2) cone = 1;
+    }
     else for (int a = 1; a < dim; a++) {
       const float mu = rg_contact_mu(r, a);
       const float jp = u[0] + mu * u[a], jm = u[0] - mu * u[a];
-      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a)); }
-      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a + 1)); }
+      if (jp < 0.0f) { const float f = -D * jp; F[0] += f; F[a] += mu * f; cost += 0.5f * D * jp * jp; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a)); RG_STAT(rg_stat_act[512 + 16 * k + 2 * a] = 1;) }
+      if (jm < 0.0f) { const float f = -D * jm; F[0] += f; F[a] -= mu * f; cost += 0.5f * D * jm * jm; sig += rg_mix((unsigned)(1000 + 16 * k + 2 * a + 1)); RG_STAT(rg_stat_act[512 + 16 * k + 2 * a + 1] = 1;) }
     }
     float* cf = s + L.cF + 6 * k;
     for (int a = 0; a < 6; a++) cf[a] = F[a];
   }
   LV(part) = cost;
   LV(sigp) = (int)(sig & 0x00ffffffu);
+  LV(conep) = cone;
   RG_PHASE_END
   RG_SI(c, RG_S_SIG) = RG_WARP_ISUM(sigp);
+  if (elliptic) RG_SI(c, RG_S_CONE) = RG_WARP_OR(conep);
   return RG_WARP_SUM(part);
 }
 
@@ -634,11 +720,11 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
 #ifdef RG_NO_REUSE
     const int refactor = 1;
 #else
-    const int refactor = !(have_factor && RG_SI(c, RG_S_SIG) == factor_sig);
+    const int refactor = !(have_factor && RG_SI(c, RG_S_SIG) == factor_sig) || RG_SI(c, RG_S_CONE);
 #endif
     RG_STAT(rg_stat_x[1]++;)
     if (refactor) {
-    RG_STAT(rg_stat_x[2]++;)
+    RG_STAT(rg_stat_x[2]++; rg_stat_flips(have_factor);)
     rg_H_from_M(c);
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
@@ -671,8 +757,19 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       const float* u = s + L.cu + 6 * k;
       const float D = prm[0];
       float W00 = 0.0f, W0a[6] = {0, 0, 0, 0, 0, 0}, Waa[6] = {0, 0, 0, 0, 0, 0};
-      int anyact = 0;
+      int anyact = 0, zone = 0;
       if (dim == 1) { if (u[0] < 0.0f) { W00 = D; anyact = 1; } }
+      else if (m.opt_cone[0] == 1) {
+        /* elliptic cone: nothing in the top zone, diag(D_k) in the bottom zone (fits the arrow form below), a dense block in
+           the middle zone (handled separately) */
+        float cc, F[6];
+        const float mu = rg_cone_mu(m, r);
+        zone = rg_cone_eval(r, mu, dim, D, u, &cc, F);
+        if (zone == 1) {
+          W00 = D; anyact = 1;
+          for (int a = 1; a < 6; a++) if (a < dim) { const float fa = rg_contact_mu(r, a); Waa[a] = D * fa * fa / (mu * mu); }
+        } else if (zone == 2) anyact = 1;
+      }
       else for (int a = 1; a < dim; a++) {
         const float mu = rg_contact_mu(r, a);
         if (u[0] + mu * u[a] < 0.0f) { W00 += D; W0a[a] += D * mu; Waa[a] += D * mu * mu; anyact = 1; }
@@ -692,10 +789,20 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         tdof[lane] = d;
         float* tj = s + L.tileJ + 6 * lane;
         float* tw = s + L.tileWJ + 6 * lane;
+        if (zone == 2) {
+          float W[6][6];
+          rg_cone_hessian(r, rg_cone_mu(m, r), dim, D, u, W);
+          for (int a = 0; a < 6; a++) {
+            float w = 0.0f;
+            for (int b = 0; b < 6; b++) if (a < dim && b < dim) w += W[a][b] * col[b];
+            tj[a] = a < dim ? col[a] : 0.0f; tw[a] = w;
+          }
+        } else {
         float w0 = W00 * col[0];
         RG_NOUNROLL for (int a = 1; a < dim; a++) w0 += W0a[a] * col[a];
         tj[0] = col[0]; tw[0] = w0;
         for (int a = 1; a < 6; a++) { tj[a] = a < dim ? col[a] : 0.0f; tw[a] = a < dim ? W0a[a] * col[0] + Waa[a] * col[a] : 0.0f; }
+        }
       }
       RG_PHASE_END
       RG_PHASE_BEGIN
@@ -798,6 +905,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
         const int dim = (int)prm[1];
         const float D = prm[0];
         if (dim == 1) { const float x = u[0] + alpha * w[0]; if (x < 0.0f) { g += D * x * w[0]; h += D * w[0] * w[0]; } }
+        else if (m.opt_cone[0] == 1) rg_cone_ray(r, rg_cone_mu(m, r), dim, D, u, w, alpha, &g, &h);
         else for (int a = 1; a < dim; a++) {
           const float mu = rg_contact_mu(r, a);
           const float xp = u[0] + alpha * w[0] + mu * (u[a] + alpha * w[a]), vp = w[0] + mu * w[a];
@@ -855,6 +963,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
   rg_JT_force_phase(c, L.qfc, nel, tl0, ncon);
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[L.warm + d] = s[L.qacc + d];
+  RG_STAT(if (lane == 0) rg_stat_iterhist[iter < 15 ? iter : 15]++;)
   if (lane == 0) { RG_SI(c, RG_S_NITER) = iter; RG_SI(c, RG_S_WORK) += RG_COST_ITER * iter; }
   RG_PHASE_END
 }

@@ -35,7 +35,7 @@ int rge_name2id(void* hv, const char* typ, const char* name) {
   return -1;
 }
 #ifdef RG_STATS
-void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; for (int i = 0; i < 128; i++) out[8 + i] = rg_stat_hist[i / 64][i % 64]; for (int i = 0; i < 16; i++) out[136 + i] = rg_stat_x[i]; }
+void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_climb; out[2] = rg_stat_mpr; out[3] = rg_stat_mpr_hit; out[4] = rg_stat_maxsup; for (int i = 0; i < 128; i++) out[8 + i] = rg_stat_hist[i / 64][i % 64]; for (int i = 0; i < 16; i++) out[136 + i] = rg_stat_x[i]; for (int i = 0; i < 16; i++) out[152 + i] = rg_stat_iterhist[i]; for (int i = 0; i < 16; i++) out[168 + i] = rg_stat_fliphist[i]; }
 #endif
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
 int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view, ((RgeHandle*)hv)->L.ncon); }

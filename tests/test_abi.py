@@ -51,13 +51,13 @@ def test_name_tables_travel_in_the_blob(locked_blob, locked_names):
 
 
 def test_unsupported_features_are_refused(locked_blob):
-    """A model with elliptic cones, active equality constraints or mocap bodies must not load (it used to step
-    with silently wrong physics)."""
+    """A model with active equality constraints or mocap bodies must not load (it used to step with silently
+    wrong physics; elliptic cones are simulated since round 2)."""
     import pyemu
     from robogym_b200 import modelblob
 
     names = modelblob.unpack_names(locked_blob)
-    for edit in (lambda m: m["opt_cone"].__setitem__(0, 1), lambda m: m.__setitem__("nmocap", 1)):
+    for edit in (lambda m: m.__setitem__("nmocap", 1),):
         m = modelblob.unpack(locked_blob)
         edit(m)
         with pytest.raises(RuntimeError):

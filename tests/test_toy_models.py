@@ -541,3 +541,100 @@ def test_random_convex_hull_piles(seed):
         errs.append(float(np.abs(e.qpos[0] - d.qpos).max()))
     assert int(e.warn[0]) == 0 and same >= 23
     assert np.median(errs) < 2e-6 and max(errs) < 5e-3 and np.median(errs[-8:]) < 1e-6, errs
+
+
+# ---------------------------------------------------------------------------------------------- elliptic friction cones
+# (option cone="elliptic" impratio=10: robogym/assets/xmls/robot/ur16e/base.xml:4, the rearrange scenes)
+ELLIPTIC = 'iterations="50" cone="elliptic" impratio="10"'
+
+
+@pytest.mark.parametrize("condim", [3, 4, 6])
+def test_elliptic_cone_resting_sphere_sits_at_the_closed_form_penetration(condim):
+    """At rest only the normal row of an elliptic contact carries force, with D = 1/R_normal: the equilibrium is the
+    condim-1 closed form whatever the friction dimensions are (a pyramid would sit mu^2 (1 + mu^2) / 2 times deeper)."""
+    from toy_models import RESTING_SPHERE
+
+    cm = mjcf.compile_mjcf(RESTING_SPHERE.format(condim=condim).replace('iterations="50"', ELLIPTIC))
+    assert cm.m["opt_cone"][0] == 1 and cm.m["opt_impratio"][0] == 10
+    blob = cm.blob()
+    want = 0.05 - _equilibrium_penetration(1)
+    om, d = oracle_pair(blob)
+    for _ in range(4000):
+        d.step()
+    assert d.ncon[0] == 1 and np.abs(d.qvel).max() < 1e-9
+    assert abs(d.qpos[2] - want) < 1e-8, (d.qpos[2], want)
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, 1)
+    e.qpos[0] = cm.m["qpos0"]
+    e.step(4000, 1)
+    assert int(e.warn[0]) == 0 and int(e.ncon[0]) == 1
+    assert abs(float(e.qpos[0, 2]) - want) < 2e-6, (float(e.qpos[0, 2]), want)
+
+
+def test_elliptic_cone_sliding_force_lies_on_the_cone():
+    """A box sliding on a plane: every contact is in the middle zone of its cone, where the force is the projection onto the
+    cone's boundary -- tangential / normal force = the friction coefficient exactly, opposing the sliding direction."""
+    from toy_models import RESTING_SPHERE
+
+    xml = RESTING_SPHERE.format(condim=3).replace('iterations="50"', ELLIPTIC).replace('type="sphere" size="0.05"', 'type="box" size="0.05 0.05 0.05"')
+    cm = mjcf.compile_mjcf(xml)
+    om, d = oracle_pair(cm.blob())
+    for _ in range(2000):
+        d.step()
+    d.qvel[0] = 1.0
+    for _ in range(20):
+        d.step()
+    nefc = int(d.nefc[0])
+    typ, f = d.efc_type[:nefc], d.efc_force[:nefc]
+    rows = [i for i in range(nefc) if typ[i] == 4]
+    assert len(rows) >= 2 and d.qvel[0] > 0.5      # the sliding box leans on its leading edge
+    for i in rows:
+        assert f[i] > 0
+        assert abs(np.hypot(f[i + 1], f[i + 2]) / f[i] - 0.9) < 1e-9          # on the cone: |f_t| = mu f_n
+    # the net friction force opposes the motion (contact frames differ per corner, so sum in world coordinates)
+    assert d.qacc[0] < -5.0                        # ~ -mu g (soft cone: a little less)
+
+
+def _elliptic_pile():
+    cm = mjcf.compile_mjcf(FREE_BODIES.replace('iterations="20"', 'iterations="20" cone="elliptic" impratio="3"'))
+    return cm, cm.blob()
+
+
+def test_emulated_kernel_matches_oracle_on_an_elliptic_pile():
+    """FREE_BODIES (box, ball, brick with condim 3/4, plane and box-box contacts) with elliptic cones: the kernel logic in CPU
+    emulation against the oracle, teacher-forced over a rollout that goes through the impacts and into resting contact
+    (all three cone zones, dense middle-zone Hessian blocks)."""
+    cm, blob = _elliptic_pile()
+    states, after, om = rollout(blob, 60)
+    e = pyemu.EmuBatch(blob, {k: cm.m[k] for k in modelblob.DIMS}, len(states))
+    for k, st in enumerate(states):
+        e.qpos[k], e.qvel[k], e.ctrl[k], e.pid[k], e.warm[k] = st
+    e.step(5, 1)
+    eq = np.array([np.abs(e.qpos[k] - after[k][0]).max() for k in range(len(states))])
+    ev = np.array([np.abs(e.qvel[k] - after[k][1]).max() for k in range(len(states))])
+    assert e.warn.max() == 0
+    assert np.median(eq) < 1e-5 and np.mean(eq < 1e-3) > 0.85 and np.median(ev) < 2e-2
+    assert np.mean(e.ncon == np.array([a[2] for a in after])) > 0.8
+    assert max(a[2] for a in after) >= 5
+
+
+@pytest.mark.gpu
+def test_cuda_matches_oracle_on_an_elliptic_pile():
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+    cm, blob = _elliptic_pile()
+    states, after, om = rollout(blob, 60)
+    model = engine.DeviceModel(blob, 0)
+    sim = engine.BatchedSim(model, len(states), 5, outputs=("ncon", "warn"))
+    f = lambda i: torch.tensor(np.stack([s[i] for s in states]), dtype=torch.float32, device=sim.device)
+    sim.qpos.copy_(f(0)); sim.qvel.copy_(f(1)); sim.ctrl.copy_(f(2)); sim.qacc_warmstart.copy_(f(4))
+    sim.step()
+    torch.cuda.synchronize()
+    q, v = sim.qpos.cpu().numpy(), sim.qvel.cpu().numpy()
+    eq = np.array([np.abs(q[k] - after[k][0]).max() for k in range(len(states))])
+    ev = np.array([np.abs(v[k] - after[k][1]).max() for k in range(len(states))])
+    assert int(sim.warn.max()) == 0
+    assert np.median(eq) < 1e-5 and np.mean(eq < 1e-3) > 0.85 and np.median(ev) < 2e-2
+    assert np.mean(sim.ncon.cpu().numpy() == np.array([a[2] for a in after])) > 0.8

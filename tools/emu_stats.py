@@ -56,7 +56,7 @@ def main():
     e.qpos[:, 0:3] += 0.005 * rng.randn(nenv, 3)
     q = rng.randn(nenv, 4)
     e.qpos[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
-    buf = (ctypes.c_longlong * 160)()
+    buf = (ctypes.c_longlong * 192)()
     L.rge_stats(buf)
     base = np.array(buf[:])
     for _ in range(steps):
@@ -76,6 +76,10 @@ def main():
     h = s[8:136].reshape(2, 64)
     print("mpr iteration histogram (miss):", h[0][:24])
     print("mpr iteration histogram (hit): ", h[1][:40])
+    ih = s[152:168]
+    fh = s[168:184]
+    print("rows whose active state flipped between consecutive refactorisations of a solve, histogram:", fh, " single-row flips/refactor %.2f, contact-edge flips/refactor %.2f" % (x[13] / max(x[15], 1), x[14] / max(x[15], 1)))
+    print("newton iterations per solve, histogram:", ih[:12], " P(>=5) = %.3f, P(>=6) = %.3f" % (ih[5:].sum() / ih.sum(), ih[6:].sum() / ih.sum()))
 
 
 if __name__ == "__main__":

@@ -49,6 +49,21 @@ def main():
         dims=dict(nq=38, nv=36, nu=20, nbody=31, ngeom=65, ntendon=12, npair=1243),
     )
     json.dump(exp, open(os.path.join(OUT, "locked_expectations.json"), "w"), indent=1)
+    # the reference's recorded real-MuJoCo state of four stacked blocks (the only settled multi-body fixture of its kind in
+    # the repo: robogym/envs/rearrange/holdouts/states/physics_tests/block_stacking4/) with the scene constants that its
+    # stability test runs it under (holdouts/tests/test_stability.py:215-261, holdouts/configs/physics_tests/*.jsonnet,
+    # materials/painted_wood.jsonnet + base.libsonnet, assets/xmls/primitives/box.xml, robot/ur16e/base.xml:3-22)
+    st = np.load(os.path.join(ref.REF, "robogym/envs/rearrange/holdouts/states/physics_tests/block_stacking4/initial_state_4_blocks_stacked.npz"))
+    stack = dict(
+        obj_pos=st["obj_pos"].tolist(), obj_quat=st["obj_quat"].tolist(),
+        block_half_size=0.025, density=720.0, friction=[0.85, 0.25, 0.001], condim=6, margin=0.00005, solref=[-4000.0, -200.0],
+        joint_damping=0.01, joint_armature=0.001,
+        table=dict(pos=[1.4508, 0.773, 0.453], half_size=[0.6075, 0.7655, 0.03324], solimp=[0.99, 0.999, 0.001], solref=[-50000.0, -100.0]),
+        option=dict(timestep=0.002, substeps=20, cone="elliptic", impratio=10),
+        stability=dict(env_steps=50, max_linear_speed=0.3, note="test_stability.py:215-230: block_stacking4 must stay below 0.3 m/s for 50 env-steps"),
+        doc_resting_z=dict(value=0.51167315, block_half_size=0.0254, source="docs/env_param_interface.md:32-38 (default material, blocks env)"),
+    )
+    json.dump(stack, open(os.path.join(OUT, "block_stack4.json"), "w"), indent=1)
     print("wrote", os.listdir(OUT))
 
 
