@@ -385,8 +385,11 @@ def run_gpu_arm(args):
     NBOX = cfg["nenv"]
     N = NBOX // world if strong else NBOX                      # weak: the config's batch per GPU; strong: per box
     lo_env, hi_env = shard_range(N * world, rank, world)
-    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"), contact_capacity=cfg["caps"][0],
-                            row_capacity=cfg["caps"][1], dofs_per_contact=cfg["caps"][2])
+    caps = cfg["caps"]
+    if os.environ.get("RG_BENCH_CAPS"):        # experiments: "contacts,rows,dofs" (0 = engine default)
+        caps = tuple(int(x) for x in os.environ["RG_BENCH_CAPS"].split(","))
+    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"), contact_capacity=caps[0],
+                            row_capacity=caps[1], dofs_per_contact=caps[2])
     m = model.host
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
     gen = torch.Generator(device=dev)
@@ -411,6 +414,7 @@ def run_gpu_arm(args):
     resets = torch.zeros((), dtype=torch.int64, device=dev)
     ncon_sum = torch.zeros((), dtype=torch.float64, device=dev)
     warn = torch.zeros((), dtype=torch.int32, device=dev)
+    ncon_max = torch.zeros((), dtype=torch.int32, device=dev)
     for k in range(args.steps):
         nxt = wl.next_ctrl()
         flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
@@ -419,6 +423,7 @@ def run_gpu_arm(args):
         sim.step()
         ev[k][1].record()
         ncon_sum += sim.ncon.double().mean()
+        ncon_max = torch.maximum(ncon_max, sim.ncon.max())
         warn |= sim.warn.max()
         resets += wl.auto_reset().sum()                 # in-loop auto-reset (untimed torch ops, like the action sampling)
     torch.cuda.synchronize()
@@ -488,7 +493,7 @@ def run_gpu_arm(args):
                        "envs_per_gpu": N, "substeps": NSUB, "physics_substeps_per_s": value * NSUB,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "launch": info, "cubes_on_palm_at_end": on_palm, "resets_in_timed_region_rank0": int(resets.item()),
-                       "mean_contacts": float(ncon_sum.item()) / args.steps, "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
+                       "mean_contacts": float(ncon_sum.item()) / args.steps, "max_contacts": int(ncon_max.item()), "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
             "gpu_launches": 2 * args.steps * world,   # per step: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch)

@@ -22,7 +22,7 @@
 #include "rg_host.h"
 
 #ifndef RG_MAX_WARPS
-#define RG_MAX_WARPS 10
+#define RG_MAX_WARPS 12   /* 168 registers x 384 threads fit the register file; shared memory decides how many are used */
 #endif
 
 static thread_local std::string g_err;

@@ -53,7 +53,11 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nM);   /* M: tree-sparse rows (rg_host.h), H: dense packed lower triangle */
   /* H aliases the smooth-dynamics temporaries */
   const int h0 = o;
-  RG_ALLOC(Sdot, 6 * rg_imax(m.nv, m.nbody)); RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody);
+  /* body inertias (I10, crb) live from the mass-matrix stage to the bias stage only: they sit in the contact records, which
+     are rewritten by the collision stage afterwards (when those are big enough) */
+  const int inertia_in_con = 20 * m.nbody <= ncon * RG_CON_STRIDE;
+  RG_ALLOC(Sdot, 6 * rg_imax(m.nv, m.nbody));
+  if (!inertia_in_con) { RG_ALLOC(I10, 10 * m.nbody); RG_ALLOC(crb, 10 * m.nbody); }
   L.H = h0;
   o = h0 + rg_imax(rg_imax(rg_imax(o - h0, (ntri + 3) & ~3), (m.ntendon * m.nv + 3) & ~3), (m.nM + 3) & ~3);   /* also the tree-sparse factor (Euler, solver-free trees) */
   RG_ALLOC(bias, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
@@ -64,7 +68,12 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   const int nel64 = nel < 64 ? 64 : nel;   /* el_jv / el_f double as the broad-phase candidate lists (64 entries) */
   RG_ALLOC(el_i, nel); RG_ALLOC(el_D, nel); RG_ALLOC(el_floss, nel);
   RG_ALLOC(el_jar, nel); RG_ALLOC(el_jv, nel64); RG_ALLOC(el_f, nel64);
-  RG_ALLOC(tileJ, 6 * tile); RG_ALLOC(tileWJ, 6 * tile); RG_ALLOC(tileDof, tile); RG_ALLOC(scal, 8 + RG_NPROF);
+  /* the Hessian tiles of one contact are built while cw / el_jv are dead (they are written after the factorisation) */
+  const int tile_in_cw = 12 * tile <= 6 * ncon && tile <= nel64;
+  if (tile_in_cw) { L.tileJ = L.cw; L.tileWJ = L.cw + 6 * tile; L.tileDof = L.el_jv; }
+  else { RG_ALLOC(tileJ, 6 * tile); RG_ALLOC(tileWJ, 6 * tile); RG_ALLOC(tileDof, tile); }
+  RG_ALLOC(scal, 8 + RG_NPROF);
+  if (inertia_in_con) { L.I10 = L.con; L.crb = L.con + 10 * m.nbody; }
   RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, ((tile + 3) >> 2) * ncon);   /* dof ids as bytes */
   RG_ALLOC(sep, RG_NSEP);   /* lives across the substeps of a launch, so it cannot share storage */
 #undef RG_ALLOC

@@ -93,3 +93,114 @@ def test_cuda_matches_oracle(full):
     sim.step()
     torch.cuda.synchronize()
     check(sim.qpos.cpu().numpy(), sim.ncon.cpu().numpy(), sim.warn.cpu().numpy(), after)
+
+
+def _randomised_rows(m, n, seed=5):
+    """Per-environment parameter rows in the spirit of full_perpendicular.py:425-440 (the subset of that wrapper stack that
+    is plain array scaling: robot / cube friction, gravity, robot damping, Kp, and a per-env timestep), drawn with the
+    wrappers' distributions (randomizations.py:72-306: log-uniform factors, gravity +- 0.4 m/s^2 per axis)."""
+    rng = np.random.RandomState(seed)
+    rows = {}
+    fr = np.tile(m["geom_friction"].reshape(1, -1, 3), (n, 1, 1))
+    fr *= np.exp(rng.uniform(np.log(0.7), np.log(1.3), (n, 1, 1)))
+    rows["geom_friction"] = fr.reshape(n, -1)
+    rows["opt_gravity"] = m["opt_gravity"].reshape(1, 3) + rng.uniform(-0.4, 0.4, (n, 3))
+    rows["dof_damping"] = m["dof_damping"].reshape(1, -1) * np.exp(rng.uniform(np.log(1 / 1.5), np.log(1.5), (n, m["nv"])))
+    gp = np.tile(m["actuator_gainprm"].reshape(1, -1, 10), (n, 1, 1))
+    gp[:, :, 0] *= np.exp(rng.uniform(np.log(0.5), np.log(2.0), (n, m["nu"])))
+    rows["actuator_gainprm"] = gp.reshape(n, -1)
+    ts = m["opt_timestep"][0] * rng.uniform(0.85, 1.15, n)
+    return rows, ts
+
+
+def _oracle_step_with_rows(blob, m, states, rows, ts, nsub=10):
+    """One env-step per state on the oracle, each under its own parameter row."""
+    after = []
+    for k, st in enumerate(states):
+        om, d = oracle_pair(blob)
+        for name, v in rows.items():
+            om.field(name)[:] = v[k]
+        om.field("opt_timestep")[0] = ts[k]
+        d.qpos[:], d.qvel[:], d.ctrl[:] = st[0], st[1], st[2]
+        d.userdata[:3 * m["nu"]] = st[3]
+        d.qacc_warmstart[:] = st[4]
+        d.env_step(nsub)
+        after.append((d.qpos.copy(), d.qvel.copy(), int(d.ncon[0])))
+    return after
+
+
+def test_kernel_logic_with_per_env_parameters_in_emulation(full):
+    """The per-environment timestep path on the full cube (parameter ROWS exist only in the CUDA engine: the emulation has one
+    model): each state stepped under its own opt.timestep."""
+    import pyemu
+    from robogym_b200 import modelblob
+
+    blob, m, states, after, = full
+    n = 6
+    _, ts = _randomised_rows(m, n)
+    want = _oracle_step_with_rows(blob, m, states[:n], {}, ts)
+    dims = {k: m[k] for k in modelblob.DIMS}
+    e = pyemu.EmuBatch(blob, dims, n, **CAPS)
+    e.timestep = ts.astype(np.float32)
+    for k, st in enumerate(states[:n]):
+        e.qpos[k], e.qvel[k], e.ctrl[k], e.pid[k], e.warm[k] = st
+    e.step(10, 1)
+    check(e.qpos, e.ncon, e.warn, want)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_oracle_with_per_env_parameters(full):
+    """cfg 3 with per-environment parameters (friction, gravity, damping, Kp rows through rg_batch_bind_param + a per-env
+    timestep), every environment against an oracle that carries the same parameters."""
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+    blob, m, states, after = full
+    n = len(states)
+    rows, ts = _randomised_rows(m, n)
+    want = _oracle_step_with_rows(blob, m, states, rows, ts)
+    model = engine.DeviceModel(blob, 0)
+    sim = engine.BatchedSim(model, n, 10, outputs=("site_xpos", "ncon", "warn"), **CAPS)
+    for name, v in rows.items():
+        sim.set_param(name, v)
+    sim.enable_per_env_timestep().copy_(torch.tensor(ts, dtype=torch.float32, device=sim.device))
+    f = lambda i: torch.tensor(np.stack([s[i] for s in states]), dtype=torch.float32, device=sim.device)
+    sim.qpos.copy_(f(0)); sim.qvel.copy_(f(1)); sim.ctrl.copy_(f(2)); sim.pid.copy_(f(3)); sim.qacc_warmstart.copy_(f(4))
+    sim.step()
+    torch.cuda.synchronize()
+    check(sim.qpos.cpu().numpy(), sim.ncon.cpu().numpy(), sim.warn.cpu().numpy(), want)
+    # and the parameters did matter: the same states without them land elsewhere
+    base = np.array([a[0] for a in after])
+    assert np.abs(np.array([w[0] for w in want]) - base).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_cuda_full_cube_at_batch_4096(full):
+    """BASELINE.json configs[2] at its batch size (4096), per-environment parameters on: the 16 teacher-forcing states tiled over
+    the batch must reproduce the small-batch result bit for bit in every slot (size-independent property), with no warning
+    bits, and the slots that hold oracle states still agree with the oracle."""
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+    blob, m, states, after = full
+    n, N = len(states), 4096
+    rows, ts = _randomised_rows(m, n)
+    want = _oracle_step_with_rows(blob, m, states, rows, ts)
+    model = engine.DeviceModel(blob, 0)
+    sim = engine.BatchedSim(model, N, 10, outputs=("site_xpos", "ncon", "warn"), **CAPS)
+    idx = np.arange(N) % n
+    for name, v in rows.items():
+        sim.set_param(name, v[idx])
+    sim.enable_per_env_timestep().copy_(torch.tensor(ts[idx], dtype=torch.float32, device=sim.device))
+    f = lambda i: torch.tensor(np.stack([states[k][i] for k in idx]), dtype=torch.float32, device=sim.device)
+    sim.qpos.copy_(f(0)); sim.qvel.copy_(f(1)); sim.ctrl.copy_(f(2)); sim.pid.copy_(f(3)); sim.qacc_warmstart.copy_(f(4))
+    sim.step()
+    torch.cuda.synchronize()
+    q = sim.qpos.cpu().numpy()
+    assert int(sim.warn.max()) == 0
+    assert np.array_equal(q.reshape(N // n, n, -1), np.broadcast_to(q[:n], (N // n, n, q.shape[1])))
+    check(q[:n], sim.ncon.cpu().numpy()[:n], sim.warn.cpu().numpy()[:n], want)
