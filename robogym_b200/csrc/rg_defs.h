@@ -179,13 +179,13 @@ struct RgModel {
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
 struct RgLayout {
   int qpos, qvel, ctrl, pid, warm;
-  int lpos, lquat, xpos, xquat, xipos, gxpos, sxpos;
+  int lpos, lquat, xpos, xquat, gxpos, sxpos;
   int S, M, H;                       /* packed lower triangles; H aliases the block {Sdot,I10,crb} that is dead by then */
   int Sdot, I10, crb;
   int bias, smooth, qacc, Ma, search, Mv, qfc, tmp;
   int tlen, tvel, tJn, tJi, tJv, alen, aforce;
   int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
-  int el_i, el_D, el_floss, el_jar, el_jv, el_f;
+  int el_i, el_D, el_jar, el_jv, el_f;
   int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof, sep, stage;
   int ncon, nel, tile;               /* capacities: contacts, single-row elements, dofs per contact */
   int total;

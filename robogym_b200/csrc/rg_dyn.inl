@@ -59,6 +59,13 @@ enum { RG_S_NCON = 0, RG_S_NEL = 1, RG_S_WARN = 2, RG_S_NITER = 3, RG_S_TL0 = 4,
  * would otherwise swamp the link inertias of anything that drifts far away (a dropped cube). */
 RG_DEV const float* rg_body_ref(const RgCtx c, int body) { return RG_SCRATCH(c) + RG_CL(c).xpos + 3 * RG_MDEREF(c.mref).body_rootid[body]; }
 RG_DEV const float* rg_dof_ref(const RgCtx c, int dof) { return rg_body_ref(c, RG_MDEREF(c.mref).dof_bodyid[dof]); }
+/* world position of a body's centre of mass (recomputed where needed: two uses per step do not earn it a scratch array) */
+RG_DEV void rg_body_xipos(const RgCtx c, int b, float* out) {
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  float t[3];
+  rg_rot(t, RG_SCRATCH(c) + RG_CL(c).xquat + 4 * b, m.body_ipos + 3 * b);
+  rg_add3(out, RG_SCRATCH(c) + RG_CL(c).xpos + 3 * b, t);
+}
 /* translational Jacobian column of dof d at world point p */
 RG_DEV void rg_jacp_world(const RgCtx c, int d, const float* p, float* jp) {
   float rel[3];
@@ -143,9 +150,6 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
     rg_copy3(s + L.xpos + 3 * b, p);
     float* xq = s + L.xquat + 4 * b;
     xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
-    float t[3];
-    rg_rot(t, q, m.body_ipos + 3 * b);
-    rg_add3(s + L.xipos + 3 * b, p, t);
   }
   RG_PHASE_END
   /* geom / site positions, motion axes */
@@ -215,7 +219,8 @@ RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
     const float* di = m.body_inertia + 3 * b;
     const float mass = m.body_mass[b];
     float cm[3];
-    rg_sub3(cm, s + L.xipos + 3 * b, rg_body_ref(c, b));
+    rg_body_xipos(c, b, cm);
+    rg_sub3(cm, cm, rg_body_ref(c, b));
     float Ic[6]; /* xx yy zz xy xz yz */
     Ic[0] = R[0] * R[0] * di[0] + R[1] * R[1] * di[1] + R[2] * R[2] * di[2];
     Ic[1] = R[3] * R[3] * di[0] + R[4] * R[4] * di[1] + R[5] * R[5] * di[2];
@@ -435,7 +440,7 @@ RG_DEV_NOINLINE void rg_tendon_seg_jac(const RgCtx c, float* J, int ba, const fl
 /* entry (t, d) of the sparse tendon Jacobian */
 RG_DEV float rg_tendon_J(const RgCtx c, int t, int d) {
   const int n = ((const int*)(RG_SCRATCH(c) + RG_CL(c).tJn))[t];
-  const int* ji = (const int*)(RG_SCRATCH(c) + RG_CL(c).tJi) + RG_TJ * t;
+  const unsigned char* ji = (const unsigned char*)(RG_SCRATCH(c) + RG_CL(c).tJi) + RG_TJ * t;
   float v = 0.0f;
   RG_NOUNROLL for (int k = 0; k < n; k++) if (ji[k] == d) v = RG_SCRATCH(c)[RG_CL(c).tJv + RG_TJ * t + k];
   return v;
@@ -503,12 +508,12 @@ RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
     s[L.tlen + t] = len;
     float v = 0.0f;
     int nnz = 0;
-    int* ji = (int*)(s + L.tJi) + RG_TJ * t;
+    unsigned char* ji = (unsigned char*)(s + L.tJi) + RG_TJ * t;
     float* jv = s + L.tJv + RG_TJ * t;
     RG_NOUNROLL for (int k = 0; k < nv; k++) {
       if (J[k] == 0.0f) continue;
       v += J[k] * s[L.qvel + k];
-      if (nnz < RG_TJ) { ji[nnz] = k; jv[nnz] = J[k]; nnz++; }
+      if (nnz < RG_TJ) { ji[nnz] = (unsigned char)k; jv[nnz] = J[k]; nnz++; }
       else RG_SI(c, RG_S_WARN) |= RG_WARN_TENDON_NNZ;
     }
     ((int*)(s + L.tJn))[t] = nnz;
@@ -584,7 +589,9 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
         const float* x = c.xfrc + 6 * b;
         if (x[0] == 0 && x[1] == 0 && x[2] == 0 && x[3] == 0 && x[4] == 0 && x[5] == 0) continue;
         float jp[3];
-        rg_jacp_world(c, d, s + L.xipos + 3 * b, jp);
+        float xi[3];
+        rg_body_xipos(c, b, xi);
+        rg_jacp_world(c, d, xi, jp);
         applied += rg_dot3(jp, x) + rg_dot3(s + L.S + 6 * d, x + 3);
       }
     }

@@ -355,7 +355,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
   int* eldof = (int*)(s + L.eldof);
   int nel = 0, warn = 0;
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int i = lane; i < 3 * nv; i += 32) eldof[i] = -1;
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) eldof[i] = 0x3fffffff;   /* three empty 10-bit slots */
   RG_PHASE_END
   const int on = !(flags & RG_DSBL_CONSTRAINT);
   /* dof friction loss: one element per dof with frictionloss > 0 */
@@ -374,8 +374,8 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
       float R, aref, B, KI;
       rg_row_params(c, m.dof_solref + 2 * d, m.dof_solimp + 5 * d, 0.0f, 0.0f, s[L.qvel + d], m.dof_invweight0[d], 1, &R, &aref, &B, &KI);
       el_i[e] = RG_EL_FLOSS + 8 * d;
-      s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = m.dof_frictionloss[d];
-      eldof[3 * d] = e;
+      s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref;
+      eldof[d] = (eldof[d] & ~0x3ff) | e;
     }
     RG_PHASE_END
     nel += tot;
@@ -408,8 +408,8 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
         float R, aref, B, KI;
         rg_row_params(c, m.jnt_solref + 2 * j, m.jnt_solimp + 5 * j, dist, m.jnt_margin[j], sg * s[L.qvel + d], m.dof_invweight0[d], 0, &R, &aref, &B, &KI);
         el_i[e] = RG_EL_JLIMIT + 4 * side + 8 * d;
-        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = 0.0f;
-        eldof[3 * d + 1 + side] = e;
+        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref;
+        eldof[d] = (eldof[d] & ~(0x3ff << (10 + 10 * side))) | (e << (10 + 10 * side));
         e++;
       }
     }
@@ -444,7 +444,7 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
         float R, aref, B, KI;
         rg_row_params(c, m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, dist, m.tendon_margin[t], sg * s[L.tvel + t], m.tendon_invweight0[t], 0, &R, &aref, &B, &KI);
         el_i[e] = RG_EL_TLIMIT + 4 * side + 8 * t;
-        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref; s[L.el_floss + e] = 0.0f;
+        s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref;
         e++;
       }
     }
@@ -518,7 +518,7 @@ RG_DEV float rg_el_Jx(const RgCtx c, int code, int x) {
   if (type == RG_EL_JLIMIT) return side ? -s[x + id] : s[x + id];
   float acc = 0.0f;
   const int n = ((const int*)(s + RG_CL(c).tJn))[id];
-  const int* ji = (const int*)(s + RG_CL(c).tJi) + RG_TJ * id;
+  const unsigned char* ji = (const unsigned char*)(s + RG_CL(c).tJi) + RG_TJ * id;
   RG_NOUNROLL for (int k = 0; k < n; k++) acc += s[RG_CL(c).tJv + RG_TJ * id + k] * s[x + ji[k]];
   return side ? -acc : acc;
 }
@@ -531,7 +531,8 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
   const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int* el_i = (const int*)(s + L.el_i);
   LANEVAR(float, part); LANEVAR(int, sigp); LANEVAR(int, conep);
-  const int elliptic = RG_MDEREF(c.mref).opt_cone[0] == 1;
+  const RG_MODEL_T& m = RG_MDEREF(c.mref);
+  const int elliptic = m.opt_cone[0] == 1;
   RG_STAT(memset(rg_stat_act, 0, sizeof rg_stat_act);)
   RG_PHASE_BEGIN
   float cost = 0.0f;
@@ -541,7 +542,7 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
     const float jar = s[L.el_jar + e], D = s[L.el_D + e];
     float f;
     if ((el_i[e] & 3) == RG_EL_FLOSS) {
-      const float fl = s[L.el_floss + e], rf = fl / D;
+      const float fl = m.dof_frictionloss[el_i[e] >> 3], rf = fl / D;
       if (jar <= -rf) { f = fl; cost += -0.5f * rf * fl - fl * jar; }
       else if (jar >= rf) { f = -fl; cost += -0.5f * rf * fl + fl * jar; }
       else { f = -D * jar; cost += 0.5f * D * jar * jar; sig += rg_mix((unsigned)(e + 1)); RG_STAT(rg_stat_act[e] = 1;) }
@@ -559,7 +560,7 @@ RG_DEV_NOINLINE float rg_solver_update(const RgCtx c, int nel, int ncon) {
     if (dim == 1) { if (u[0] < 0.0f) { F[0] = -D * u[0]; cost += 0.5f * D * u[0] * u[0]; sig += rg_mix((unsigned)(1000 + 16 * k)); } }
     else if (elliptic) {
       float cc;
-      const int zone = rg_cone_eval(r, rg_cone_mu(RG_MDEREF(c.mref), r), dim, D, u, &cc, F);
+      const int zone = rg_cone_eval(r, rg_cone_mu(m, r), dim, D, u, &cc, F);
       cost += cc;
       if (zone) sig += rg_mix((unsigned)(1000 + 16 * k + zone));
       if (zone == 2) cone = 1;
@@ -591,10 +592,10 @@ RG_DEV_NOINLINE void rg_JT_force_phase(const RgCtx c, int out, int nel, int tl0,
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int d = lane; d < m.nv; d += 32) {
     float acc = 0.0f;
-    const int e0 = eldof[3 * d], e1 = eldof[3 * d + 1], e2 = eldof[3 * d + 2];
-    if (e0 >= 0) acc += s[L.el_f + e0];
-    if (e1 >= 0) acc += s[L.el_f + e1];
-    if (e2 >= 0) acc -= s[L.el_f + e2];
+    const int ew = eldof[d], e0 = ew & 0x3ff, e1 = (ew >> 10) & 0x3ff, e2 = (ew >> 20) & 0x3ff;   /* 0x3ff = none */
+    if (e0 != 0x3ff) acc += s[L.el_f + e0];
+    if (e1 != 0x3ff) acc += s[L.el_f + e1];
+    if (e2 != 0x3ff) acc -= s[L.el_f + e2];
     for (int e = tl0; e < nel; e++) {
       const int code = el_i[e];
       const float f = s[L.el_f + e];
@@ -729,9 +730,9 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
     RG_PHASE_BEGIN
     RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
       float add = 0.0f;
-      const int e0 = eldof[3 * d];
-      if (e0 >= 0) { const float rf = s[L.el_floss + e0] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
-      for (int q = 1; q < 3; q++) { const int e = eldof[3 * d + q]; if (e >= 0 && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
+      const int ew = eldof[d], e0 = ew & 0x3ff;
+      if (e0 != 0x3ff) { const float rf = m.dof_frictionloss[d] / s[L.el_D + e0]; if (fabsf(s[L.el_jar + e0]) < rf) add += s[L.el_D + e0]; }
+      for (int q = 1; q < 3; q++) { const int e = (ew >> (10 * q)) & 0x3ff; if (e != 0x3ff && s[L.el_jar + e] < 0.0f) add += s[L.el_D + e]; }
       if (add != 0.0f) s[L.H + RG_TRI(sidx[d], sidx[d])] += add;
     }
     RG_PHASE_END
@@ -740,7 +741,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       const int t = el_i[e] >> 3;
       const float D = s[L.el_D + e];
       const int tn = ((const int*)(s + L.tJn))[t];
-      const int* tji = (const int*)(s + L.tJi) + RG_TJ * t;
+      const unsigned char* tji = (const unsigned char*)(s + L.tJi) + RG_TJ * t;
       RG_PHASE_BEGIN
       RG_NOUNROLL for (int p = lane; p < tn * tn; p += 32) {
         const int a = p / tn, b = p - a * tn;
@@ -891,7 +892,7 @@ RG_DEV_NOINLINE void rg_solve(const RgCtx c) {
       RG_NOUNROLL for (int e = lane; e < nel; e += 32) {
         const float jv = s[L.el_jv + e], x = s[L.el_jar + e] + alpha * jv, D = s[L.el_D + e];
         if ((el_i[e] & 3) == RG_EL_FLOSS) {
-          const float fl = s[L.el_floss + e], rf = fl / D;
+          const float fl = m.dof_frictionloss[el_i[e] >> 3], rf = fl / D;
           if (x <= -rf) g -= fl * jv;
           else if (x >= rf) g += fl * jv;
           else { g += D * x * jv; h += D * jv * jv; }

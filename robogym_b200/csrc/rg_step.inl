@@ -44,11 +44,12 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   if (tile > m.nv) tile = m.nv > 0 ? m.nv : 1;
   if (ncon < 1) ncon = 1;
   if (nel < 1) nel = 1;
+  if (nel > 1022) nel = 1022;   /* element ids travel in 10 bits (eldof) */
   L.ncon = ncon; L.nel = nel; L.tile = tile;
 #define RG_ALLOC(field, n) do { L.field = o; o += (n); } while (0)   /* scalar 4-byte accesses only: no padding between arrays */
   RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
   RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
-  RG_ALLOC(xipos, 3 * m.nbody); RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
+  RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
   const int ntri = ((m.ns + 1) * (m.ns + 2)) >> 1;   /* packed lower triangle of H plus one extra row (the right-hand side rides along in the factorisation) */
   RG_ALLOC(S, 6 * m.nv); RG_ALLOC(M, m.nM);   /* M: tree-sparse rows (rg_host.h), H: dense packed lower triangle */
   /* H aliases the smooth-dynamics temporaries */
@@ -63,10 +64,10 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   RG_ALLOC(bias, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
   RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
-  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, RG_TJ * m.ntendon); RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
+  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, (RG_TJ * m.ntendon + 3) >> 2);   /* dof ids as bytes */ RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
   RG_ALLOC(con, ncon * RG_CON_STRIDE); RG_ALLOC(cu, 6 * ncon); RG_ALLOC(cw, 6 * ncon); RG_ALLOC(cF, 6 * ncon); RG_ALLOC(cprm, RG_CPRM * ncon);
   const int nel64 = nel < 64 ? 64 : nel;   /* el_jv / el_f double as the broad-phase candidate lists (64 entries) */
-  RG_ALLOC(el_i, nel); RG_ALLOC(el_D, nel); RG_ALLOC(el_floss, nel);
+  RG_ALLOC(el_i, nel); RG_ALLOC(el_D, nel);
   RG_ALLOC(el_jar, nel); RG_ALLOC(el_jv, nel64); RG_ALLOC(el_f, nel64);
   /* the Hessian tiles of one contact are built while cw / el_jv are dead (they are written after the factorisation) */
   const int tile_in_cw = 12 * tile <= 6 * ncon && tile <= nel64;
@@ -74,7 +75,7 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   else { RG_ALLOC(tileJ, 6 * tile); RG_ALLOC(tileWJ, 6 * tile); RG_ALLOC(tileDof, tile); }
   RG_ALLOC(scal, 8 + RG_NPROF);
   if (inertia_in_con) { L.I10 = L.con; L.crb = L.con + 10 * m.nbody; }
-  RG_ALLOC(eldof, 3 * m.nv); RG_ALLOC(env, m.nv); RG_ALLOC(cdof, ((tile + 3) >> 2) * ncon);   /* dof ids as bytes */
+  RG_ALLOC(eldof, m.nv); RG_ALLOC(env, m.nv);   /* eldof: the (up to) three single-dof elements of a dof, 10 bits each */ RG_ALLOC(cdof, ((tile + 3) >> 2) * ncon);   /* dof ids as bytes */
   RG_ALLOC(sep, RG_NSEP);   /* lives across the substeps of a launch, so it cannot share storage */
 #undef RG_ALLOC
   /* lifetimes that never overlap share storage: local frames (kinematics only) sit in the contact
