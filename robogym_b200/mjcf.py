@@ -306,304 +306,319 @@ class CompiledModel:
 
 
 # ----------------------------------------------------------------------------------------------
-def compile_mjcf(xml_string, asset_loader=None):
-    """Compile an MJCF document (string) into a CompiledModel."""
-    root = ET.fromstring(xml_string)
-    if root.tag != "mujoco":
+class _Ctx:
+    """State shared by the passes of compile_mjcf: every name one pass leaves for a later one is an attribute."""
+
+
+def _pass_document(c):
+    """parse the document root, compiler / option / size / default sections"""
+    c.root = ET.fromstring(c.xml_string)
+    if c.root.tag != "mujoco":
         raise ValueError("root element must be <mujoco>")
 
-    # ---- compiler / option / size
+
+def _pass_compiler_option_size(c):
+    """<compiler>, <option> (+ flags), <size>, <default> classes"""
     comp = {}
-    for e in root.findall("compiler"):
+    for e in c.root.findall("compiler"):
         comp.update(e.attrib)
-    angle_scale = 1.0 if comp.get("angle", "degree") == "radian" else np.pi / 180.0
+    c.angle_scale = 1.0 if comp.get("angle", "degree") == "radian" else np.pi / 180.0
     if comp.get("coordinate", "local") != "local":
         raise NotImplementedError("only coordinate=local is supported")
-    eulerseq = comp.get("eulerseq", "xyz")
-    meshdir = comp.get("meshdir", "")
-    boundmass = float(comp.get("boundmass", 0))
-    boundinertia = float(comp.get("boundinertia", 0))
-    inertiafromgeom = comp.get("inertiafromgeom", "auto")
-    settotalmass = float(comp.get("settotalmass", -1))
+    c.eulerseq = comp.get("eulerseq", "xyz")
+    c.meshdir = comp.get("meshdir", "")
+    c.boundmass = float(comp.get("boundmass", 0))
+    c.boundinertia = float(comp.get("boundinertia", 0))
+    c.inertiafromgeom = comp.get("inertiafromgeom", "auto")
+    c.settotalmass = float(comp.get("settotalmass", -1))
 
-    opt = {}
-    flags = {}
-    for e in root.findall("option"):
-        opt.update(e.attrib)
+    c.opt = {}
+    c.flags = {}
+    for e in c.root.findall("option"):
+        c.opt.update(e.attrib)
         for fl in e.findall("flag"):
-            flags.update(fl.attrib)
-    size_attrs = {}
-    for e in root.findall("size"):
-        size_attrs.update(e.attrib)
+            c.flags.update(fl.attrib)
+    c.size_attrs = {}
+    for e in c.root.findall("size"):
+        c.size_attrs.update(e.attrib)
 
-    defaults = _Defaults()
-    for e in root.findall("default"):
-        defaults.add(e, parent=None)
+    c.defaults = _Defaults()
+    for e in c.root.findall("default"):
+        c.defaults.add(e, parent=None)
 
-    # ---- assets: meshes
-    mesh_names, mesh_verts, mesh_faces, mesh_center = [], [], [], []
-    mesh_props = []
-    used_meshes = {g.get("mesh") for wb in root.findall("worldbody") for g in wb.iter("geom") if g.get("mesh")}
-    for asset in root.findall("asset"):
+
+def _pass_assets(c):
+    """<asset><mesh>: load STL / MSH files, scale, convex hulls, volume / centre / inertia of every hull"""
+    c.mesh_names, c.mesh_verts, c.mesh_faces, c.mesh_center = [], [], [], []
+    c.mesh_props = []
+    used_meshes = {g.get("mesh") for wb in c.root.findall("worldbody") for g in wb.iter("geom") if g.get("mesh")}
+    for asset in c.root.findall("asset"):
         for me in asset.findall("mesh"):
-            a = defaults.resolve("mesh", me, None)
+            a = c.defaults.resolve("mesh", me, None)
             name = a.get("name")
             fname = a["file"]
             if name is None:
                 name = os.path.splitext(os.path.basename(fname))[0]
             if name not in used_meshes:
                 continue  # unreferenced assets do not affect the physics; keep the blob small
-            path = fname if os.path.isabs(fname) else os.path.join(meshdir, fname)
-            if asset_loader is not None:
-                raw = asset_loader(path)
+            path = fname if os.path.isabs(fname) else os.path.join(c.meshdir, fname)
+            if c.asset_loader is not None:
+                c.raw = c.asset_loader(path)
             elif path.lower().endswith(".stl"):
-                raw = load_stl(path)
+                c.raw = load_stl(path)
             elif path.lower().endswith(".msh"):
-                raw = load_msh(path)
+                c.raw = load_msh(path)
             else:
                 raise NotImplementedError(f"mesh format of {path}")
             scale = _vec(a.get("scale", "1 1 1"), 3)
-            raw = raw * scale
-            verts, faces = convex_hull(raw)
+            c.raw = c.raw * scale
+            verts, faces = convex_hull(c.raw)
             vol, cen, inertia = polyhedron_mass_props(verts, faces)
             verts = verts - cen
-            mesh_names.append(name)
-            mesh_verts.append(verts)
-            mesh_faces.append(faces)
-            mesh_center.append(cen)
-            mesh_props.append((vol, inertia))
+            c.mesh_names.append(name)
+            c.mesh_verts.append(verts)
+            c.mesh_faces.append(faces)
+            c.mesh_center.append(cen)
+            c.mesh_props.append((vol, inertia))
 
-    # ---- kinematic tree (document-order DFS over merged <worldbody> sections)
-    B = dict(name=[], parent=[], pos=[], quat=[], inertial=[], childclass=[], mocap=[])
-    J = []  # joint dicts
-    G = []  # geom dicts
-    S = []  # site dicts
+
+def _pass_kinematic_tree(c):
+    """bodies in document-order DFS over the merged <worldbody> sections: parents, frames, joints / geoms / sites per body"""
+    c.B = dict(name=[], parent=[], pos=[], quat=[], inertial=[], childclass=[], mocap=[])
+    c.J = []  # joint dicts
+    c.G = []  # geom dicts
+    c.S = []  # site dicts
 
     def add_body(elem, parent, childclass):
         a = elem.attrib
-        bid = len(B["name"])
+        bid = len(c.B["name"])
         cc = a.get("childclass", childclass)
-        B["name"].append(a.get("name"))
-        B["parent"].append(parent)
-        B["pos"].append(_vec(a.get("pos", "0 0 0"), 3))
-        B["quat"].append(_frame_quat(a, angle_scale, eulerseq))
-        B["childclass"].append(cc)
-        B["mocap"].append(a.get("mocap", "false") == "true")
+        c.B["name"].append(a.get("name"))
+        c.B["parent"].append(parent)
+        c.B["pos"].append(_vec(a.get("pos", "0 0 0"), 3))
+        c.B["quat"].append(_frame_quat(a, c.angle_scale, c.eulerseq))
+        c.B["childclass"].append(cc)
+        c.B["mocap"].append(a.get("mocap", "false") == "true")
         inertial = elem.find("inertial")
-        B["inertial"].append(dict(inertial.attrib) if inertial is not None else None)
-        add_body_content(elem, bid, cc)
+        c.B["inertial"].append(dict(inertial.attrib) if inertial is not None else None)
+        c.add_body_content(elem, bid, cc)
         return bid
 
     def add_body_content(elem, bid, cc):
         for ch in elem:
             if ch.tag == "joint":
-                ja = defaults.resolve("joint", ch, cc)
+                ja = c.defaults.resolve("joint", ch, cc)
                 ja["_body"] = bid
-                J.append(ja)
+                c.J.append(ja)
             elif ch.tag == "freejoint":
                 ja = dict(ch.attrib)
                 ja.update(type="free", _body=bid)
-                J.append(ja)
+                c.J.append(ja)
             elif ch.tag == "geom":
-                ga = defaults.resolve("geom", ch, cc)
+                ga = c.defaults.resolve("geom", ch, cc)
                 ga["_body"] = bid
-                G.append(ga)
+                c.G.append(ga)
             elif ch.tag == "site":
-                sa = defaults.resolve("site", ch, cc)
+                sa = c.defaults.resolve("site", ch, cc)
                 sa["_body"] = bid
-                S.append(sa)
+                c.S.append(sa)
         for ch in elem:
             if ch.tag == "body":
                 add_body(ch, bid, cc)
+    c.add_body_content = add_body_content
 
     # world body
-    B["name"].append("world")
-    B["parent"].append(0)
-    B["pos"].append(np.zeros(3))
-    B["quat"].append(np.array([1.0, 0, 0, 0]))
-    B["inertial"].append(None)
-    B["childclass"].append(None)
-    B["mocap"].append(False)
-    for wb in root.findall("worldbody"):
-        add_body_content(wb, 0, wb.get("childclass"))
+    c.B["name"].append("world")
+    c.B["parent"].append(0)
+    c.B["pos"].append(np.zeros(3))
+    c.B["quat"].append(np.array([1.0, 0, 0, 0]))
+    c.B["inertial"].append(None)
+    c.B["childclass"].append(None)
+    c.B["mocap"].append(False)
+    for wb in c.root.findall("worldbody"):
+        c.add_body_content(wb, 0, wb.get("childclass"))
 
-    nbody = len(B["name"])
+    c.nbody = len(c.B["name"])
     # MuJoCo numbers joints/geoms/sites grouped by body id
-    J.sort(key=lambda d: d["_body"])
-    G.sort(key=lambda d: d["_body"])
-    S.sort(key=lambda d: d["_body"])
-    njnt, ngeom, nsite = len(J), len(G), len(S)
+    c.J.sort(key=lambda d: d["_body"])
+    c.G.sort(key=lambda d: d["_body"])
+    c.S.sort(key=lambda d: d["_body"])
+    c.njnt, c.ngeom, c.nsite = len(c.J), len(c.G), len(c.S)
 
-    m = {}
-    names = dict(body=list(B["name"]), joint=[j.get("name") for j in J], geom=[g.get("name") for g in G],
-                 site=[s.get("name") for s in S], mesh=mesh_names)
+    c.m = {}
+    c.names = dict(body=list(c.B["name"]), joint=[j.get("name") for j in c.J], geom=[g.get("name") for g in c.G],
+                 site=[s.get("name") for s in c.S], mesh=c.mesh_names)
 
-    # ---- joints / dofs
+
+def _pass_joints_dofs(c):
+    """joints and degrees of freedom: types, axes, limits, springs, armature / damping / frictionloss, qpos0, dof ancestry masks"""
     jtype_map = dict(free=JNT_FREE, ball=JNT_BALL, slide=JNT_SLIDE, hinge=JNT_HINGE)
-    jnt_type = np.zeros(njnt, int)
-    jnt_qposadr = np.zeros(njnt, int)
-    jnt_dofadr = np.zeros(njnt, int)
-    jnt_bodyid = np.zeros(njnt, int)
-    jnt_limited = np.zeros(njnt, int)
-    jnt_pos = np.zeros((njnt, 3))
-    jnt_axis = np.zeros((njnt, 3))
-    jnt_stiffness = np.zeros(njnt)
-    jnt_range = np.zeros((njnt, 2))
-    jnt_margin = np.zeros(njnt)
-    jnt_solref = np.zeros((njnt, 2))
-    jnt_solimp = np.zeros((njnt, 5))
-    qpos0, qpos_spring = [], []
-    dof_bodyid, dof_jntid, dof_armature, dof_damping, dof_frictionloss = [], [], [], [], []
-    dof_solref, dof_solimp = [], []
-    nq = nv = 0
-    for i, ja in enumerate(J):
+    c.jnt_type = np.zeros(c.njnt, int)
+    c.jnt_qposadr = np.zeros(c.njnt, int)
+    c.jnt_dofadr = np.zeros(c.njnt, int)
+    c.jnt_bodyid = np.zeros(c.njnt, int)
+    c.jnt_limited = np.zeros(c.njnt, int)
+    c.jnt_pos = np.zeros((c.njnt, 3))
+    c.jnt_axis = np.zeros((c.njnt, 3))
+    c.jnt_stiffness = np.zeros(c.njnt)
+    c.jnt_range = np.zeros((c.njnt, 2))
+    c.jnt_margin = np.zeros(c.njnt)
+    c.jnt_solref = np.zeros((c.njnt, 2))
+    c.jnt_solimp = np.zeros((c.njnt, 5))
+    c.qpos0, c.qpos_spring = [], []
+    c.dof_bodyid, c.dof_jntid, c.dof_armature, c.dof_damping, c.dof_frictionloss = [], [], [], [], []
+    c.dof_solref, c.dof_solimp = [], []
+    c.nq = c.nv = 0
+    for i, ja in enumerate(c.J):
         t = jtype_map[ja.get("type", "hinge")]
-        jnt_type[i] = t
-        jnt_bodyid[i] = ja["_body"]
-        jnt_qposadr[i] = nq
-        jnt_dofadr[i] = nv
-        jnt_pos[i] = _vec(ja.get("pos", "0 0 0"), 3)
+        c.jnt_type[i] = t
+        c.jnt_bodyid[i] = ja["_body"]
+        c.jnt_qposadr[i] = c.nq
+        c.jnt_dofadr[i] = c.nv
+        c.jnt_pos[i] = _vec(ja.get("pos", "0 0 0"), 3)
         ax = _vec(ja.get("axis", "0 0 1"), 3)
-        jnt_axis[i] = ax / max(np.linalg.norm(ax), MINVAL)
+        c.jnt_axis[i] = ax / max(np.linalg.norm(ax), MINVAL)
         limited = ja.get("limited", "false") == "true"
-        jnt_limited[i] = int(limited)
+        c.jnt_limited[i] = int(limited)
         rng = _vec(ja.get("range", "0 0"), 2)
         if t in (JNT_HINGE, JNT_BALL):
-            rng = rng * angle_scale
-        jnt_range[i] = rng
-        jnt_stiffness[i] = float(ja.get("stiffness", 0))
-        jnt_margin[i] = float(ja.get("margin", 0))
-        jnt_solref[i] = _vec(ja.get("solreflimit", DEFAULT_SOLREF), 2)
-        jnt_solimp[i] = _solimp(ja.get("solimplimit"))
+            rng = rng * c.angle_scale
+        c.jnt_range[i] = rng
+        c.jnt_stiffness[i] = float(ja.get("stiffness", 0))
+        c.jnt_margin[i] = float(ja.get("margin", 0))
+        c.jnt_solref[i] = _vec(ja.get("solreflimit", DEFAULT_SOLREF), 2)
+        c.jnt_solimp[i] = _solimp(ja.get("solimplimit"))
         ref = float(ja.get("ref", 0))
         sref = float(ja.get("springref", 0))
         if t == JNT_HINGE:
-            ref *= angle_scale
-            sref *= angle_scale
+            ref *= c.angle_scale
+            sref *= c.angle_scale
         nqi, nvi = {JNT_FREE: (7, 6), JNT_BALL: (4, 3), JNT_SLIDE: (1, 1), JNT_HINGE: (1, 1)}[t]
         if t == JNT_FREE:
             # qpos0 of a free joint is the body's pose in the world (filled after frames are known)
-            qpos0 += [None] * 7
-            qpos_spring += [None] * 7
+            c.qpos0 += [None] * 7
+            c.qpos_spring += [None] * 7
         elif t == JNT_BALL:
-            qpos0 += [1.0, 0, 0, 0]
-            qpos_spring += [1.0, 0, 0, 0]
+            c.qpos0 += [1.0, 0, 0, 0]
+            c.qpos_spring += [1.0, 0, 0, 0]
         else:
-            qpos0.append(ref)
-            qpos_spring.append(sref)
+            c.qpos0.append(ref)
+            c.qpos_spring.append(sref)
         for _ in range(nvi):
-            dof_bodyid.append(ja["_body"])
-            dof_jntid.append(i)
-            dof_armature.append(float(ja.get("armature", 0)))
-            dof_damping.append(float(ja.get("damping", 0)))
-            dof_frictionloss.append(float(ja.get("frictionloss", 0)))
-            dof_solref.append(_vec(ja.get("solreffriction", DEFAULT_SOLREF), 2))
-            dof_solimp.append(_solimp(ja.get("solimpfriction")))
-        nq += nqi
-        nv += nvi
+            c.dof_bodyid.append(ja["_body"])
+            c.dof_jntid.append(i)
+            c.dof_armature.append(float(ja.get("armature", 0)))
+            c.dof_damping.append(float(ja.get("damping", 0)))
+            c.dof_frictionloss.append(float(ja.get("frictionloss", 0)))
+            c.dof_solref.append(_vec(ja.get("solreffriction", DEFAULT_SOLREF), 2))
+            c.dof_solimp.append(_solimp(ja.get("solimpfriction")))
+        c.nq += nqi
+        c.nv += nvi
 
-    body_jntadr = -np.ones(nbody, int)
-    body_jntnum = np.zeros(nbody, int)
-    body_dofadr = -np.ones(nbody, int)
-    body_dofnum = np.zeros(nbody, int)
-    for i in range(njnt):
-        b = jnt_bodyid[i]
-        if body_jntadr[b] < 0:
-            body_jntadr[b] = i
-            body_dofadr[b] = jnt_dofadr[i]
-        body_jntnum[b] += 1
-        body_dofnum[b] += {JNT_FREE: 6, JNT_BALL: 3}.get(jnt_type[i], 1)
+    c.body_jntadr = -np.ones(c.nbody, int)
+    c.body_jntnum = np.zeros(c.nbody, int)
+    c.body_dofadr = -np.ones(c.nbody, int)
+    c.body_dofnum = np.zeros(c.nbody, int)
+    for i in range(c.njnt):
+        b = c.jnt_bodyid[i]
+        if c.body_jntadr[b] < 0:
+            c.body_jntadr[b] = i
+            c.body_dofadr[b] = c.jnt_dofadr[i]
+        c.body_jntnum[b] += 1
+        c.body_dofnum[b] += {JNT_FREE: 6, JNT_BALL: 3}.get(c.jnt_type[i], 1)
 
-    parent = np.array(B["parent"], int)
-    body_pos = np.array(B["pos"], float)
-    body_quat = np.array(B["quat"], float)
+    c.parent = np.array(c.B["parent"], int)
+    c.body_pos = np.array(c.B["pos"], float)
+    c.body_quat = np.array(c.B["quat"], float)
     # free-joint bodies: qpos0 is the body frame (must be children of world)
-    for i in range(njnt):
-        if jnt_type[i] == JNT_FREE:
-            b = jnt_bodyid[i]
-            a = jnt_qposadr[i]
-            vals = list(body_pos[b]) + list(body_quat[b])
-            qpos0[a:a + 7] = vals
-            qpos_spring[a:a + 7] = vals
-    qpos0 = np.array(qpos0, float)
-    qpos_spring = np.array(qpos_spring, float)
+    for i in range(c.njnt):
+        if c.jnt_type[i] == JNT_FREE:
+            b = c.jnt_bodyid[i]
+            a = c.jnt_qposadr[i]
+            vals = list(c.body_pos[b]) + list(c.body_quat[b])
+            c.qpos0[a:a + 7] = vals
+            c.qpos_spring[a:a + 7] = vals
+    c.qpos0 = np.array(c.qpos0, float)
+    c.qpos_spring = np.array(c.qpos_spring, float)
 
     # dof parent chain
-    dof_parentid = -np.ones(nv, int)
-    last_dof_of_body = -np.ones(nbody, int)  # last dof on path from root up to and including body
-    for b in range(1, nbody):
-        last = last_dof_of_body[parent[b]]
-        if body_dofnum[b] > 0:
-            for d in range(body_dofadr[b], body_dofadr[b] + body_dofnum[b]):
-                dof_parentid[d] = last
+    c.dof_parentid = -np.ones(c.nv, int)
+    last_dof_of_body = -np.ones(c.nbody, int)  # last dof on path from root up to and including body
+    for b in range(1, c.nbody):
+        last = last_dof_of_body[c.parent[b]]
+        if c.body_dofnum[b] > 0:
+            for d in range(c.body_dofadr[b], c.body_dofadr[b] + c.body_dofnum[b]):
+                c.dof_parentid[d] = last
                 last = d
         last_dof_of_body[b] = last
 
     # levels, roots, weld ids
-    level = np.zeros(nbody, int)
-    rootid = np.zeros(nbody, int)
-    weldid = np.zeros(nbody, int)
-    for b in range(1, nbody):
-        level[b] = level[parent[b]] + 1
-        rootid[b] = b if parent[b] == 0 else rootid[parent[b]]
-        weldid[b] = b if body_jntnum[b] > 0 else weldid[parent[b]]
-    order = np.array(sorted(range(nbody), key=lambda b: (level[b], b)), int)
-    nlevel = int(level.max()) + 1
-    level_adr = np.zeros(nlevel + 1, int)
-    for b in range(nbody):
-        level_adr[level[b] + 1] += 1
-    level_adr = np.cumsum(level_adr)
+    c.level = np.zeros(c.nbody, int)
+    c.rootid = np.zeros(c.nbody, int)
+    c.weldid = np.zeros(c.nbody, int)
+    for b in range(1, c.nbody):
+        c.level[b] = c.level[c.parent[b]] + 1
+        c.rootid[b] = b if c.parent[b] == 0 else c.rootid[c.parent[b]]
+        c.weldid[b] = b if c.body_jntnum[b] > 0 else c.weldid[c.parent[b]]
+    c.order = np.array(sorted(range(c.nbody), key=lambda b: (c.level[b], b)), int)
+    c.nlevel = int(c.level.max()) + 1
+    c.level_adr = np.zeros(c.nlevel + 1, int)
+    for b in range(c.nbody):
+        c.level_adr[c.level[b] + 1] += 1
+    c.level_adr = np.cumsum(c.level_adr)
 
-    nmaskw = max(1, (nv + 31) // 32)
-    dofmask = np.zeros((nbody, nmaskw), np.uint32)
-    for b in range(1, nbody):
-        dofmask[b] = dofmask[parent[b]]
-        for d in range(body_dofadr[b], body_dofadr[b] + body_dofnum[b]) if body_dofnum[b] else []:
-            dofmask[b, d // 32] |= np.uint32(1 << (d % 32))
+    c.nmaskw = max(1, (c.nv + 31) // 32)
+    c.dofmask = np.zeros((c.nbody, c.nmaskw), np.uint32)
+    for b in range(1, c.nbody):
+        c.dofmask[b] = c.dofmask[c.parent[b]]
+        for d in range(c.body_dofadr[b], c.body_dofadr[b] + c.body_dofnum[b]) if c.body_dofnum[b] else []:
+            c.dofmask[b, d // 32] |= np.uint32(1 << (d % 32))
 
-    mocapid = -np.ones(nbody, int)
-    nmocap = 0
-    for b in range(nbody):
-        if B["mocap"][b]:
-            mocapid[b] = nmocap
-            nmocap += 1
+    c.mocapid = -np.ones(c.nbody, int)
+    c.nmocap = 0
+    for b in range(c.nbody):
+        if c.B["mocap"][b]:
+            c.mocapid[b] = c.nmocap
+            c.nmocap += 1
 
-    # ---- geoms
-    geom_type = np.zeros(ngeom, int)
-    geom_bodyid = np.zeros(ngeom, int)
-    geom_dataid = -np.ones(ngeom, int)
-    geom_contype = np.zeros(ngeom, int)
-    geom_conaffinity = np.zeros(ngeom, int)
-    geom_condim = np.zeros(ngeom, int)
-    geom_priority = np.zeros(ngeom, int)
-    geom_size = np.zeros((ngeom, 3))
-    geom_pos = np.zeros((ngeom, 3))
-    geom_quat = np.zeros((ngeom, 4))
-    geom_rbound = np.zeros(ngeom)
-    geom_aabb = np.zeros((ngeom, 6))
-    geom_friction = np.zeros((ngeom, 3))
-    geom_margin = np.zeros(ngeom)
-    geom_gap = np.zeros(ngeom)
-    geom_solmix = np.zeros(ngeom)
-    geom_solref = np.zeros((ngeom, 2))
-    geom_solimp = np.zeros((ngeom, 5))
-    geom_mass = np.zeros(ngeom)
-    geom_inertia = np.zeros((ngeom, 3, 3))  # about geom centre, in geom frame
-    body_geomadr = -np.ones(nbody, int)
-    body_geomnum = np.zeros(nbody, int)
-    for i, ga in enumerate(G):
+
+def _pass_geoms(c):
+    """geoms: types, sizes (fromto), frames, contact parameters, bounding spheres and boxes, mass properties"""
+    c.geom_type = np.zeros(c.ngeom, int)
+    c.geom_bodyid = np.zeros(c.ngeom, int)
+    c.geom_dataid = -np.ones(c.ngeom, int)
+    c.geom_contype = np.zeros(c.ngeom, int)
+    c.geom_conaffinity = np.zeros(c.ngeom, int)
+    c.geom_condim = np.zeros(c.ngeom, int)
+    c.geom_priority = np.zeros(c.ngeom, int)
+    c.geom_size = np.zeros((c.ngeom, 3))
+    c.geom_pos = np.zeros((c.ngeom, 3))
+    c.geom_quat = np.zeros((c.ngeom, 4))
+    c.geom_rbound = np.zeros(c.ngeom)
+    c.geom_aabb = np.zeros((c.ngeom, 6))
+    c.geom_friction = np.zeros((c.ngeom, 3))
+    c.geom_margin = np.zeros(c.ngeom)
+    c.geom_gap = np.zeros(c.ngeom)
+    c.geom_solmix = np.zeros(c.ngeom)
+    c.geom_solref = np.zeros((c.ngeom, 2))
+    c.geom_solimp = np.zeros((c.ngeom, 5))
+    c.geom_mass = np.zeros(c.ngeom)
+    c.geom_inertia = np.zeros((c.ngeom, 3, 3))  # about geom centre, in geom frame
+    c.body_geomadr = -np.ones(c.nbody, int)
+    c.body_geomnum = np.zeros(c.nbody, int)
+    for i, ga in enumerate(c.G):
         b = ga["_body"]
-        if body_geomadr[b] < 0:
-            body_geomadr[b] = i
-        body_geomnum[b] += 1
-        geom_bodyid[i] = b
+        if c.body_geomadr[b] < 0:
+            c.body_geomadr[b] = i
+        c.body_geomnum[b] += 1
+        c.geom_bodyid[i] = b
         if "mesh" in ga and "type" not in ga:
             ga["type"] = "mesh"
         t = GEOM_TYPES[ga.get("type", "sphere")]
-        geom_type[i] = t
+        c.geom_type[i] = t
         size = _vec(ga.get("size", "0 0 0"), 3)
         pos = _vec(ga.get("pos", "0 0 0"), 3)
-        quat = _frame_quat(ga, angle_scale, eulerseq)
+        quat = _frame_quat(ga, c.angle_scale, c.eulerseq)
         if "fromto" in ga and t in (GEOM_CAPSULE, GEOM_CYLINDER, GEOM_BOX, GEOM_ELLIPSOID):
             ft = _vec(ga["fromto"], 6)
             pos = 0.5 * (ft[:3] + ft[3:])
@@ -614,338 +629,353 @@ def compile_mjcf(xml_string, asset_loader=None):
             else:
                 size = np.array([size[0], size[0], half])
         if t == GEOM_MESH:
-            mid = mesh_names.index(ga["mesh"])
-            geom_dataid[i] = mid
+            c.mid = c.mesh_names.index(ga["mesh"])
+            c.geom_dataid[i] = c.mid
             # mesh vertices were recentred on the hull centroid: shift the geom frame to match
-            pos = pos + quat2mat(quat) @ mesh_center[mid]
-            size = np.abs(mesh_verts[mid]).max(axis=0)
-            geom_rbound[i] = np.linalg.norm(mesh_verts[mid], axis=1).max()
+            pos = pos + quat2mat(quat) @ c.mesh_center[c.mid]
+            size = np.abs(c.mesh_verts[c.mid]).max(axis=0)
+            c.geom_rbound[i] = np.linalg.norm(c.mesh_verts[c.mid], axis=1).max()
         elif t == GEOM_SPHERE:
-            geom_rbound[i] = size[0]
+            c.geom_rbound[i] = size[0]
         elif t == GEOM_CAPSULE:
-            geom_rbound[i] = size[0] + size[1]
+            c.geom_rbound[i] = size[0] + size[1]
         elif t == GEOM_CYLINDER:
-            geom_rbound[i] = np.hypot(size[0], size[1])
+            c.geom_rbound[i] = np.hypot(size[0], size[1])
         elif t in (GEOM_BOX, GEOM_ELLIPSOID):
-            geom_rbound[i] = np.linalg.norm(size) if t == GEOM_BOX else size.max()
+            c.geom_rbound[i] = np.linalg.norm(size) if t == GEOM_BOX else size.max()
         if t == GEOM_MESH:
-            vmin, vmax = mesh_verts[mid].min(axis=0), mesh_verts[mid].max(axis=0)
-            geom_aabb[i] = np.concatenate([0.5 * (vmin + vmax), 0.5 * (vmax - vmin)])
+            vmin, vmax = c.mesh_verts[c.mid].min(axis=0), c.mesh_verts[c.mid].max(axis=0)
+            c.geom_aabb[i] = np.concatenate([0.5 * (vmin + vmax), 0.5 * (vmax - vmin)])
         elif t == GEOM_SPHERE:
-            geom_aabb[i, 3:] = size[0]
+            c.geom_aabb[i, 3:] = size[0]
         elif t == GEOM_CAPSULE:
-            geom_aabb[i, 3:] = [size[0], size[0], size[0] + size[1]]
+            c.geom_aabb[i, 3:] = [size[0], size[0], size[0] + size[1]]
         elif t == GEOM_CYLINDER:
-            geom_aabb[i, 3:] = [size[0], size[0], size[1]]
+            c.geom_aabb[i, 3:] = [size[0], size[0], size[1]]
         elif t in (GEOM_BOX, GEOM_ELLIPSOID):
-            geom_aabb[i, 3:] = size
-        geom_size[i] = size
-        geom_pos[i] = pos
-        geom_quat[i] = quat
-        geom_contype[i] = int(ga.get("contype", 1))
-        geom_conaffinity[i] = int(ga.get("conaffinity", 1))
-        geom_condim[i] = int(ga.get("condim", 3))
-        geom_priority[i] = int(ga.get("priority", 0))
-        geom_friction[i] = _vec(ga.get("friction", "1 0.005 0.0001"), 3)
-        geom_margin[i] = float(ga.get("margin", 0))
-        geom_gap[i] = float(ga.get("gap", 0))
-        geom_solmix[i] = float(ga.get("solmix", 1))
-        geom_solref[i] = _vec(ga.get("solref", DEFAULT_SOLREF), 2)
-        geom_solimp[i] = _solimp(ga.get("solimp"))
+            c.geom_aabb[i, 3:] = size
+        c.geom_size[i] = size
+        c.geom_pos[i] = pos
+        c.geom_quat[i] = quat
+        c.geom_contype[i] = int(ga.get("contype", 1))
+        c.geom_conaffinity[i] = int(ga.get("conaffinity", 1))
+        c.geom_condim[i] = int(ga.get("condim", 3))
+        c.geom_priority[i] = int(ga.get("priority", 0))
+        c.geom_friction[i] = _vec(ga.get("friction", "1 0.005 0.0001"), 3)
+        c.geom_margin[i] = float(ga.get("margin", 0))
+        c.geom_gap[i] = float(ga.get("gap", 0))
+        c.geom_solmix[i] = float(ga.get("solmix", 1))
+        c.geom_solref[i] = _vec(ga.get("solref", DEFAULT_SOLREF), 2)
+        c.geom_solimp[i] = _solimp(ga.get("solimp"))
         # mass / inertia (used only if the body has no <inertial>)
-        vol, I = _geom_volume_inertia(t, size, mesh_props[geom_dataid[i]] if t == GEOM_MESH else None)
+        vol, I = _geom_volume_inertia(t, size, c.mesh_props[c.geom_dataid[i]] if t == GEOM_MESH else None)
         if "mass" in ga:
             mass = float(ga["mass"])
         else:
             mass = float(ga.get("density", 1000)) * vol
-        geom_mass[i] = mass
-        geom_inertia[i] = I * (mass / vol if vol > 0 else 0.0)
+        c.geom_mass[i] = mass
+        c.geom_inertia[i] = I * (mass / vol if vol > 0 else 0.0)
 
-    # ---- body inertial properties
-    body_mass = np.zeros(nbody)
-    body_ipos = np.zeros((nbody, 3))
-    body_iquat = np.tile(np.array([1.0, 0, 0, 0]), (nbody, 1))
-    body_inertia = np.zeros((nbody, 3))
-    for b in range(1, nbody):
-        ia = B["inertial"][b]
-        use_geoms = (inertiafromgeom == "true") or (inertiafromgeom == "auto" and ia is None)
+
+def _pass_body_inertial_properties(c):
+    """body inertial frames: explicit <inertial> or accumulated from geoms (inertiafromgeom), bounds, totals"""
+    c.body_mass = np.zeros(c.nbody)
+    c.body_ipos = np.zeros((c.nbody, 3))
+    c.body_iquat = np.tile(np.array([1.0, 0, 0, 0]), (c.nbody, 1))
+    c.body_inertia = np.zeros((c.nbody, 3))
+    for b in range(1, c.nbody):
+        ia = c.B["inertial"][b]
+        use_geoms = (c.inertiafromgeom == "true") or (c.inertiafromgeom == "auto" and ia is None)
         if not use_geoms and ia is not None:
-            body_mass[b] = float(ia["mass"])
-            body_ipos[b] = _vec(ia.get("pos", "0 0 0"), 3)
-            iq = _frame_quat(ia, angle_scale, eulerseq)
+            c.body_mass[b] = float(ia["mass"])
+            c.body_ipos[b] = _vec(ia.get("pos", "0 0 0"), 3)
+            iq = _frame_quat(ia, c.angle_scale, c.eulerseq)
             if "fullinertia" in ia:
                 f = _vec(ia["fullinertia"], 6)
                 full = np.array([[f[0], f[3], f[4]], [f[3], f[1], f[5]], [f[4], f[5], f[2]]])
                 w, v = _eig_frame(full)
-                body_inertia[b] = w
+                c.body_inertia[b] = w
                 iq = quat_mul(iq, mat2quat(v))
             else:
-                body_inertia[b] = _vec(ia["diaginertia"], 3)
-            body_iquat[b] = quat_normalize(iq)
-        elif body_geomnum[b] > 0:
-            gs = range(body_geomadr[b], body_geomadr[b] + body_geomnum[b])
-            mtot = sum(geom_mass[g] for g in gs)
+                c.body_inertia[b] = _vec(ia["diaginertia"], 3)
+            c.body_iquat[b] = quat_normalize(iq)
+        elif c.body_geomnum[b] > 0:
+            gs = range(c.body_geomadr[b], c.body_geomadr[b] + c.body_geomnum[b])
+            mtot = sum(c.geom_mass[g] for g in gs)
             if mtot > 0:
-                com = sum(geom_mass[g] * geom_pos[g] for g in gs) / mtot
+                com = sum(c.geom_mass[g] * c.geom_pos[g] for g in gs) / mtot
                 I = np.zeros((3, 3))
                 for g in gs:
-                    R = quat2mat(geom_quat[g])
-                    d = geom_pos[g] - com
-                    I += R @ geom_inertia[g] @ R.T + geom_mass[g] * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+                    R = quat2mat(c.geom_quat[g])
+                    d = c.geom_pos[g] - com
+                    I += R @ c.geom_inertia[g] @ R.T + c.geom_mass[g] * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
                 w, v = _eig_frame(I)
-                body_mass[b] = mtot
-                body_ipos[b] = com
-                body_inertia[b] = w
-                body_iquat[b] = mat2quat(v)
-        if body_mass[b] > 0 or body_inertia[b].any():
-            body_mass[b] = max(body_mass[b], boundmass)
-            body_inertia[b] = np.maximum(body_inertia[b], boundinertia)
-    if settotalmass > 0:
-        s = settotalmass / body_mass.sum()
-        body_mass *= s
-        body_inertia *= s
-    subtreemass = body_mass.copy()
-    for b in range(nbody - 1, 0, -1):
-        subtreemass[parent[b]] += subtreemass[b]
+                c.body_mass[b] = mtot
+                c.body_ipos[b] = com
+                c.body_inertia[b] = w
+                c.body_iquat[b] = mat2quat(v)
+        if c.body_mass[b] > 0 or c.body_inertia[b].any():
+            c.body_mass[b] = max(c.body_mass[b], c.boundmass)
+            c.body_inertia[b] = np.maximum(c.body_inertia[b], c.boundinertia)
+    if c.settotalmass > 0:
+        s = c.settotalmass / c.body_mass.sum()
+        c.body_mass *= s
+        c.body_inertia *= s
+    c.subtreemass = c.body_mass.copy()
+    for b in range(c.nbody - 1, 0, -1):
+        c.subtreemass[c.parent[b]] += c.subtreemass[b]
 
-    # ---- sites
-    site_bodyid = np.array([s["_body"] for s in S], int).reshape(-1)
-    site_pos = np.zeros((nsite, 3))
-    site_quat = np.zeros((nsite, 4))
-    for i, sa in enumerate(S):
+
+def _pass_sites(c):
+    """sites"""
+    c.site_bodyid = np.array([s["_body"] for s in c.S], int).reshape(-1)
+    c.site_pos = np.zeros((c.nsite, 3))
+    c.site_quat = np.zeros((c.nsite, 4))
+    for i, sa in enumerate(c.S):
         pos = _vec(sa.get("pos", "0 0 0"), 3)
-        quat = _frame_quat(sa, angle_scale, eulerseq)
+        quat = _frame_quat(sa, c.angle_scale, c.eulerseq)
         if "fromto" in sa:
             ft = _vec(sa["fromto"], 6)
             pos = 0.5 * (ft[:3] + ft[3:])
             quat = z2quat(ft[:3] - ft[3:])
-        site_pos[i] = pos
-        site_quat[i] = quat
+        c.site_pos[i] = pos
+        c.site_quat[i] = quat
 
-    # ---- collision pair list (static filtering; MuJoCo's mj_collision body/geom filters)
-    disableflags = 0
-    for k, v in flags.items():
+
+def _pass_collision_pair_list(c):
+    """candidate geom pairs after the static filters of mj_collision (contype / conaffinity, same or welded body, parent-child, <exclude>)"""
+    c.disableflags = 0
+    for k, v in c.flags.items():
         if k in DSBL and v == "disable":
-            disableflags |= DSBL[k]
+            c.disableflags |= DSBL[k]
     excludes = set()
-    for ce in root.findall("contact"):
+    for ce in c.root.findall("contact"):
         for ex in ce.findall("exclude"):
-            b1 = names["body"].index(ex.get("body1"))
-            b2 = names["body"].index(ex.get("body2"))
+            b1 = c.names["body"].index(ex.get("body1"))
+            b2 = c.names["body"].index(ex.get("body2"))
             excludes.add((min(b1, b2), max(b1, b2)))
         if ce.findall("pair"):
             raise NotImplementedError("explicit <contact><pair> is not used by the robogym configs")
-    pair1, pair2 = [], []
-    filterparent = not (disableflags & DSBL["filterparent"])
-    for g1 in range(ngeom):
-        for g2 in range(g1 + 1, ngeom):
-            b1, b2 = geom_bodyid[g1], geom_bodyid[g2]
+    c.pair1, c.pair2 = [], []
+    filterparent = not (c.disableflags & DSBL["filterparent"])
+    for g1 in range(c.ngeom):
+        for g2 in range(g1 + 1, c.ngeom):
+            b1, b2 = c.geom_bodyid[g1], c.geom_bodyid[g2]
             if b1 == b2:
                 continue
-            w1, w2 = weldid[b1], weldid[b2]
+            w1, w2 = c.weldid[b1], c.weldid[b2]
             if w1 == w2:
                 continue  # welded together (incl. both static)
             if (min(b1, b2), max(b1, b2)) in excludes:
                 continue
             if filterparent and w1 != 0 and w2 != 0:
-                if weldid[parent[w1]] == w2 or weldid[parent[w2]] == w1:
+                if c.weldid[c.parent[w1]] == w2 or c.weldid[c.parent[w2]] == w1:
                     continue
-            if not ((geom_contype[g1] & geom_conaffinity[g2]) or (geom_contype[g2] & geom_conaffinity[g1])):
+            if not ((c.geom_contype[g1] & c.geom_conaffinity[g2]) or (c.geom_contype[g2] & c.geom_conaffinity[g1])):
                 continue
-            t1, t2 = geom_type[g1], geom_type[g2]
+            t1, t2 = c.geom_type[g1], c.geom_type[g2]
             if t1 == GEOM_PLANE and t2 == GEOM_PLANE:
                 continue
             # order so that type1 <= type2 (collision function table is upper-triangular)
             if t1 > t2:
-                pair1.append(g2)
-                pair2.append(g1)
+                c.pair1.append(g2)
+                c.pair2.append(g1)
             else:
-                pair1.append(g1)
-                pair2.append(g2)
+                c.pair1.append(g1)
+                c.pair2.append(g2)
 
-    # ---- tendons
-    T = []
-    W_type, W_obj, W_prm = [], [], []
-    for te in root.findall("tendon"):
+
+def _pass_tendons(c):
+    """fixed and spatial tendons (wrap paths with pulleys, cylinders / spheres and side sites), limits, springs"""
+    c.T = []
+    c.W_type, c.W_obj, c.W_prm = [], [], []
+    for te in c.root.findall("tendon"):
         for t in te:
             if t.tag not in ("fixed", "spatial"):
                 continue
-            ta = defaults.resolve("tendon", t, None)
-            adr = len(W_type)
+            ta = c.defaults.resolve("tendon", t, None)
+            c.adr = len(c.W_type)
             for w in t:
                 if w.tag == "joint":
-                    W_type.append(WRAP_JOINT)
-                    W_obj.append(names["joint"].index(w.get("joint")))
-                    W_prm.append(float(w.get("coef", 1)))
+                    c.W_type.append(WRAP_JOINT)
+                    c.W_obj.append(c.names["joint"].index(w.get("joint")))
+                    c.W_prm.append(float(w.get("coef", 1)))
                 elif w.tag == "site":
-                    W_type.append(WRAP_SITE)
-                    W_obj.append(names["site"].index(w.get("site")))
-                    W_prm.append(-1)
+                    c.W_type.append(WRAP_SITE)
+                    c.W_obj.append(c.names["site"].index(w.get("site")))
+                    c.W_prm.append(-1)
                 elif w.tag == "geom":
-                    g = names["geom"].index(w.get("geom"))
-                    if geom_type[g] == GEOM_SPHERE:
-                        W_type.append(WRAP_SPHERE)
-                    elif geom_type[g] == GEOM_CYLINDER:
-                        W_type.append(WRAP_CYLINDER)
+                    g = c.names["geom"].index(w.get("geom"))
+                    if c.geom_type[g] == GEOM_SPHERE:
+                        c.W_type.append(WRAP_SPHERE)
+                    elif c.geom_type[g] == GEOM_CYLINDER:
+                        c.W_type.append(WRAP_CYLINDER)
                     else:
                         raise ValueError("tendon can only wrap spheres and cylinders")
-                    W_obj.append(g)
+                    c.W_obj.append(g)
                     ss = w.get("sidesite")
-                    W_prm.append(names["site"].index(ss) if ss is not None else -1)
+                    c.W_prm.append(c.names["site"].index(ss) if ss is not None else -1)
                 elif w.tag == "pulley":
-                    W_type.append(WRAP_PULLEY)
-                    W_obj.append(-1)
-                    W_prm.append(float(w.get("divisor")))
-            ta["_adr"] = adr
-            ta["_num"] = len(W_type) - adr
-            T.append(ta)
-    ntendon = len(T)
-    names["tendon"] = [t.get("name") for t in T]
-    tendon_range = np.zeros((ntendon, 2))
-    tendon_limited = np.zeros(ntendon, int)
-    tendon_margin = np.zeros(ntendon)
-    tendon_stiffness = np.zeros(ntendon)
-    tendon_damping = np.zeros(ntendon)
-    tendon_frictionloss = np.zeros(ntendon)
-    tendon_lengthspring = np.zeros(ntendon)
-    tendon_solref_lim = np.zeros((ntendon, 2))
-    tendon_solimp_lim = np.zeros((ntendon, 5))
-    for i, ta in enumerate(T):
-        tendon_limited[i] = int(ta.get("limited", "false") == "true")
-        tendon_range[i] = _vec(ta.get("range", "0 0"), 2)
-        tendon_margin[i] = float(ta.get("margin", 0))
-        tendon_stiffness[i] = float(ta.get("stiffness", 0))
-        tendon_damping[i] = float(ta.get("damping", 0))
-        tendon_frictionloss[i] = float(ta.get("frictionloss", 0))
-        tendon_lengthspring[i] = float(ta.get("springlength", -1))
-        tendon_solref_lim[i] = _vec(ta.get("solreflimit", DEFAULT_SOLREF), 2)
-        tendon_solimp_lim[i] = _solimp(ta.get("solimplimit"))
+                    c.W_type.append(WRAP_PULLEY)
+                    c.W_obj.append(-1)
+                    c.W_prm.append(float(w.get("divisor")))
+            ta["_adr"] = c.adr
+            ta["_num"] = len(c.W_type) - c.adr
+            c.T.append(ta)
+    c.ntendon = len(c.T)
+    c.names["tendon"] = [t.get("name") for t in c.T]
+    c.tendon_range = np.zeros((c.ntendon, 2))
+    c.tendon_limited = np.zeros(c.ntendon, int)
+    c.tendon_margin = np.zeros(c.ntendon)
+    c.tendon_stiffness = np.zeros(c.ntendon)
+    c.tendon_damping = np.zeros(c.ntendon)
+    c.tendon_frictionloss = np.zeros(c.ntendon)
+    c.tendon_lengthspring = np.zeros(c.ntendon)
+    c.tendon_solref_lim = np.zeros((c.ntendon, 2))
+    c.tendon_solimp_lim = np.zeros((c.ntendon, 5))
+    for i, ta in enumerate(c.T):
+        c.tendon_limited[i] = int(ta.get("limited", "false") == "true")
+        c.tendon_range[i] = _vec(ta.get("range", "0 0"), 2)
+        c.tendon_margin[i] = float(ta.get("margin", 0))
+        c.tendon_stiffness[i] = float(ta.get("stiffness", 0))
+        c.tendon_damping[i] = float(ta.get("damping", 0))
+        c.tendon_frictionloss[i] = float(ta.get("frictionloss", 0))
+        c.tendon_lengthspring[i] = float(ta.get("springlength", -1))
+        c.tendon_solref_lim[i] = _vec(ta.get("solreflimit", DEFAULT_SOLREF), 2)
+        c.tendon_solimp_lim[i] = _solimp(ta.get("solimplimit"))
 
-    # ---- actuators
+
+def _pass_actuators(c):
+    """actuators (general / motor / position / velocity): transmission, gain / bias types and parameters, ranges"""
     A = []
-    for ae in root.findall("actuator"):
+    for ae in c.root.findall("actuator"):
         for a in ae:
-            aa = defaults.resolve("general", a, None)
+            aa = c.defaults.resolve("general", a, None)
             aa["_tag"] = a.tag
             A.append(aa)
-    nu = len(A)
-    names["actuator"] = [a.get("name") for a in A]
-    act_trntype = np.zeros(nu, int)
-    act_trnid = np.zeros(nu, int)
-    act_gaintype = np.zeros(nu, int)
-    act_biastype = np.zeros(nu, int)
-    act_ctrllimited = np.zeros(nu, int)
-    act_forcelimited = np.zeros(nu, int)
-    act_gainprm = np.zeros((nu, 10))
-    act_biasprm = np.zeros((nu, 10))
-    act_ctrlrange = np.zeros((nu, 2))
-    act_forcerange = np.zeros((nu, 2))
-    act_gear = np.zeros((nu, 6))
-    act_user0 = np.zeros(nu)
+    c.nu = len(A)
+    c.names["actuator"] = [a.get("name") for a in A]
+    c.act_trntype = np.zeros(c.nu, int)
+    c.act_trnid = np.zeros(c.nu, int)
+    c.act_gaintype = np.zeros(c.nu, int)
+    c.act_biastype = np.zeros(c.nu, int)
+    c.act_ctrllimited = np.zeros(c.nu, int)
+    c.act_forcelimited = np.zeros(c.nu, int)
+    c.act_gainprm = np.zeros((c.nu, 10))
+    c.act_biasprm = np.zeros((c.nu, 10))
+    c.act_ctrlrange = np.zeros((c.nu, 2))
+    c.act_forcerange = np.zeros((c.nu, 2))
+    c.act_gear = np.zeros((c.nu, 6))
+    c.act_user0 = np.zeros(c.nu)
     gmap = dict(fixed=GAIN_FIXED, muscle=GAIN_MUSCLE, user=GAIN_USER)
     bmap = dict(none=BIAS_NONE, affine=BIAS_AFFINE, muscle=BIAS_MUSCLE, user=BIAS_USER)
     for i, aa in enumerate(A):
         if "joint" in aa:
-            act_trntype[i] = TRN_JOINT
-            act_trnid[i] = names["joint"].index(aa["joint"])
+            c.act_trntype[i] = TRN_JOINT
+            c.act_trnid[i] = c.names["joint"].index(aa["joint"])
         elif "tendon" in aa:
-            act_trntype[i] = TRN_TENDON
-            act_trnid[i] = names["tendon"].index(aa["tendon"])
+            c.act_trntype[i] = TRN_TENDON
+            c.act_trnid[i] = c.names["tendon"].index(aa["tendon"])
         else:
             raise NotImplementedError("actuator transmission must be joint or tendon")
-        act_gainprm[i, 0] = 1.0
+        c.act_gainprm[i, 0] = 1.0
         tag = aa["_tag"]
         if tag == "general":
-            act_gaintype[i] = gmap[aa.get("gaintype", "fixed")]
-            act_biastype[i] = bmap[aa.get("biastype", "none")]
+            c.act_gaintype[i] = gmap[aa.get("gaintype", "fixed")]
+            c.act_biastype[i] = bmap[aa.get("biastype", "none")]
             if "gainprm" in aa:
-                act_gainprm[i] = _vec(aa["gainprm"], 10)
+                c.act_gainprm[i] = _vec(aa["gainprm"], 10)
             if "biasprm" in aa:
-                act_biasprm[i] = _vec(aa["biasprm"], 10)
+                c.act_biasprm[i] = _vec(aa["biasprm"], 10)
         elif tag == "motor":
             pass
         elif tag == "position":
             kp = float(aa.get("kp", 1))
-            act_gainprm[i, 0] = kp
-            act_biastype[i] = BIAS_AFFINE
-            act_biasprm[i, 1] = -kp
+            c.act_gainprm[i, 0] = kp
+            c.act_biastype[i] = BIAS_AFFINE
+            c.act_biasprm[i, 1] = -kp
         elif tag == "velocity":
             kv = float(aa.get("kv", 1))
-            act_gainprm[i, 0] = kv
-            act_biastype[i] = BIAS_AFFINE
-            act_biasprm[i, 2] = -kv
+            c.act_gainprm[i, 0] = kv
+            c.act_biastype[i] = BIAS_AFFINE
+            c.act_biasprm[i, 2] = -kv
         else:
             raise NotImplementedError(f"actuator <{tag}>")
-        act_ctrllimited[i] = int(aa.get("ctrllimited", "false") == "true")
-        act_forcelimited[i] = int(aa.get("forcelimited", "false") == "true")
-        act_ctrlrange[i] = _vec(aa.get("ctrlrange", "0 0"), 2)
-        act_forcerange[i] = _vec(aa.get("forcerange", "0 0"), 2)
-        act_gear[i] = _vec(aa.get("gear", "1 0 0 0 0 0"), 6)
+        c.act_ctrllimited[i] = int(aa.get("ctrllimited", "false") == "true")
+        c.act_forcelimited[i] = int(aa.get("forcelimited", "false") == "true")
+        c.act_ctrlrange[i] = _vec(aa.get("ctrlrange", "0 0"), 2)
+        c.act_forcerange[i] = _vec(aa.get("forcerange", "0 0"), 2)
+        c.act_gear[i] = _vec(aa.get("gear", "1 0 0 0 0 0"), 6)
         if "user" in aa:
-            act_user0[i] = _vec(aa["user"])[0]
+            c.act_user0[i] = _vec(aa["user"])[0]
 
-    # ---- equality (weld / joint), sensors: parsed for the rearrange rows
+
+def _pass_equality(c):
+    """equality constraints (weld / joint), mocap ids and sensors: parsed so that the loader can refuse what it cannot simulate"""
     E = []
-    for ee in root.findall("equality"):
+    for ee in c.root.findall("equality"):
         for e in ee:
-            ea = defaults.resolve("equality", e, None)
+            ea = c.defaults.resolve("equality", e, None)
             ea["_tag"] = e.tag
             E.append(ea)
-    neq = len(E)
-    names["equality"] = [e.get("name") for e in E]
-    eq_type = np.zeros(neq, int)
-    eq_obj1 = np.zeros(neq, int)
-    eq_obj2 = -np.ones(neq, int)
-    eq_active = np.ones(neq, int)
-    eq_data = np.zeros((neq, 7))
-    eq_solref = np.zeros((neq, 2))
-    eq_solimp = np.zeros((neq, 5))
+    c.neq = len(E)
+    c.names["equality"] = [e.get("name") for e in E]
+    c.eq_type = np.zeros(c.neq, int)
+    c.eq_obj1 = np.zeros(c.neq, int)
+    c.eq_obj2 = -np.ones(c.neq, int)
+    c.eq_active = np.ones(c.neq, int)
+    c.eq_data = np.zeros((c.neq, 7))
+    c.eq_solref = np.zeros((c.neq, 2))
+    c.eq_solimp = np.zeros((c.neq, 5))
     for i, ea in enumerate(E):
         tag = ea["_tag"]
-        eq_active[i] = int(ea.get("active", "true") == "true")
-        eq_solref[i] = _vec(ea.get("solref", DEFAULT_SOLREF), 2)
-        eq_solimp[i] = _solimp(ea.get("solimp"))
+        c.eq_active[i] = int(ea.get("active", "true") == "true")
+        c.eq_solref[i] = _vec(ea.get("solref", DEFAULT_SOLREF), 2)
+        c.eq_solimp[i] = _solimp(ea.get("solimp"))
         if tag == "weld":
-            eq_type[i] = EQ_WELD
-            eq_obj1[i] = names["body"].index(ea["body1"])
-            eq_obj2[i] = names["body"].index(ea["body2"]) if "body2" in ea else 0
-            eq_data[i, 3] = 1.0  # relpose filled by setconst (relative pose at qpos0)
+            c.eq_type[i] = EQ_WELD
+            c.eq_obj1[i] = c.names["body"].index(ea["body1"])
+            c.eq_obj2[i] = c.names["body"].index(ea["body2"]) if "body2" in ea else 0
+            c.eq_data[i, 3] = 1.0  # relpose filled by setconst (relative pose at qpos0)
         elif tag == "joint":
-            eq_type[i] = EQ_JOINT
-            eq_obj1[i] = names["joint"].index(ea["joint1"])
-            eq_obj2[i] = names["joint"].index(ea["joint2"]) if "joint2" in ea else -1
-            eq_data[i, :5] = _vec(ea.get("polycoef", "0 1 0 0 0"), 5)
+            c.eq_type[i] = EQ_JOINT
+            c.eq_obj1[i] = c.names["joint"].index(ea["joint1"])
+            c.eq_obj2[i] = c.names["joint"].index(ea["joint2"]) if "joint2" in ea else -1
+            c.eq_data[i, :5] = _vec(ea.get("polycoef", "0 1 0 0 0"), 5)
         else:
             raise NotImplementedError(f"equality <{tag}>")
 
     SENS = []
-    for se in root.findall("sensor"):
+    for se in c.root.findall("sensor"):
         for s in se:
             SENS.append(s)
-    nsensor = len(SENS)
-    names["sensor"] = [s.get("name") for s in SENS]
-    sensor_type = np.zeros(nsensor, int)
-    sensor_objid = np.zeros(nsensor, int)
-    sensor_adr = np.zeros(nsensor, int)
-    sensor_dim = np.zeros(nsensor, int)
-    adr = 0
+    c.nsensor = len(SENS)
+    c.names["sensor"] = [s.get("name") for s in SENS]
+    c.sensor_type = np.zeros(c.nsensor, int)
+    c.sensor_objid = np.zeros(c.nsensor, int)
+    c.sensor_adr = np.zeros(c.nsensor, int)
+    c.sensor_dim = np.zeros(c.nsensor, int)
+    c.adr = 0
     for i, s in enumerate(SENS):
         if s.tag == "touch":
-            sensor_type[i], sensor_dim[i] = SENS_TOUCH, 1
-            sensor_objid[i] = names["site"].index(s.get("site"))
+            c.sensor_type[i], c.sensor_dim[i] = SENS_TOUCH, 1
+            c.sensor_objid[i] = c.names["site"].index(s.get("site"))
         elif s.tag == "jointpos":
-            sensor_type[i], sensor_dim[i] = SENS_JOINTPOS, 1
-            sensor_objid[i] = names["joint"].index(s.get("joint"))
+            c.sensor_type[i], c.sensor_dim[i] = SENS_JOINTPOS, 1
+            c.sensor_objid[i] = c.names["joint"].index(s.get("joint"))
         elif s.tag in ("force", "torque"):
-            sensor_type[i], sensor_dim[i] = (SENS_FORCE if s.tag == "force" else SENS_TORQUE), 3
-            sensor_objid[i] = names["site"].index(s.get("site"))
+            c.sensor_type[i], c.sensor_dim[i] = (SENS_FORCE if s.tag == "force" else SENS_TORQUE), 3
+            c.sensor_objid[i] = c.names["site"].index(s.get("site"))
         else:
             raise NotImplementedError(f"sensor <{s.tag}>")
-        sensor_adr[i] = adr
-        adr += sensor_dim[i]
+        c.sensor_adr[i] = c.adr
+        c.adr += c.sensor_dim[i]
 
-    # ---- mesh tables
-    nmesh = len(mesh_names)
+
+def _pass_mesh_tables_and_model(c):
+    """hull vertex / adjacency / face tables, then the model dict (dims, options, every array of rg_model_fields.h), the
+    CompiledModel and the constants of mj_setConst"""
+    nmesh = len(c.mesh_names)
     mesh_vertadr = np.zeros(nmesh, int)
     mesh_vertnum = np.zeros(nmesh, int)
     mesh_faceadr = np.zeros(nmesh, int)
@@ -953,98 +983,110 @@ def compile_mjcf(xml_string, asset_loader=None):
     adj_lists = []
     va = fa = 0
     for i in range(nmesh):
-        nvert = len(mesh_verts[i])
+        nvert = len(c.mesh_verts[i])
         mesh_vertadr[i], mesh_vertnum[i] = va, nvert
-        mesh_faceadr[i], mesh_facenum[i] = fa, len(mesh_faces[i])
+        mesh_faceadr[i], mesh_facenum[i] = fa, len(c.mesh_faces[i])
         nb = [set() for _ in range(nvert)]
-        for f in mesh_faces[i]:
+        for f in c.mesh_faces[i]:
             for a, b in ((0, 1), (1, 2), (2, 0)):
                 nb[f[a]].add(int(f[b]))
                 nb[f[b]].add(int(f[a]))
         adj_lists += [sorted(s) for s in nb]
         va += nvert
-        fa += len(mesh_faces[i])
+        fa += len(c.mesh_faces[i])
     adjadr = np.zeros(va + 1, int)
     for i, l in enumerate(adj_lists):
         adjadr[i + 1] = adjadr[i] + len(l)
     mesh_adj = np.array([x for l in adj_lists for x in l], int)
-    mesh_vert = np.concatenate(mesh_verts) if nmesh else np.zeros((0, 3))
-    mesh_face = np.concatenate(mesh_faces) if nmesh else np.zeros((0, 3), int)
+    mesh_vert = np.concatenate(c.mesh_verts) if nmesh else np.zeros((0, 3))
+    mesh_face = np.concatenate(c.mesh_faces) if nmesh else np.zeros((0, 3), int)
 
-    cone = dict(pyramidal=0, elliptic=1)[opt.get("cone", "pyramidal")]
-    if opt.get("solver", "Newton") != "Newton":
+    cone = dict(pyramidal=0, elliptic=1)[c.opt.get("cone", "pyramidal")]
+    if c.opt.get("solver", "Newton") != "Newton":
         raise NotImplementedError("only the Newton solver (MuJoCo's default) is implemented")
-    if opt.get("integrator", "Euler") != "Euler":
+    if c.opt.get("integrator", "Euler") != "Euler":
         import warnings
 
         # only robogym's pendulum test asset asks for RK4 (assets/xmls/test/inverted_pendulum); every env of the
         # five BASELINE configs uses MuJoCo's default Euler.  Integrate with Euler and say so.
-        warnings.warn(f"integrator={opt.get('integrator')} is not implemented; using semi-implicit Euler")
+        warnings.warn(f"integrator={c.opt.get('integrator')} is not implemented; using semi-implicit Euler")
 
-    m.update(
-        nq=nq, nv=nv, nu=nu, nbody=nbody, njnt=njnt, ngeom=ngeom, nsite=nsite, ntendon=ntendon,
-        nwrap=len(W_type), nmesh=nmesh, nmeshvert=len(mesh_vert), nmeshadj=len(mesh_adj),
-        nmeshface=len(mesh_face), npair=len(pair1), nlevel=nlevel, nmaskw=nmaskw,
-        nuserdata=int(size_attrs.get("nuserdata", 0)), nconmax=int(size_attrs.get("nconmax", -1)),
-        njmax=int(size_attrs.get("njmax", -1)), neq=neq, nmocap=nmocap, nsensor=nsensor, nsensordata=adr,
-        opt_timestep=[float(opt.get("timestep", 0.002))],
-        opt_gravity=_vec(opt.get("gravity", "0 0 -9.81"), 3),
-        opt_tolerance=[float(opt.get("tolerance", 1e-8))],
-        opt_impratio=[float(opt.get("impratio", 1))],
-        opt_mpr_tolerance=[float(opt.get("mpr_tolerance", 1e-6))],
+    c.m.update(
+        nq=c.nq, nv=c.nv, nu=c.nu, nbody=c.nbody, njnt=c.njnt, ngeom=c.ngeom, nsite=c.nsite, ntendon=c.ntendon,
+        nwrap=len(c.W_type), nmesh=nmesh, nmeshvert=len(mesh_vert), nmeshadj=len(mesh_adj),
+        nmeshface=len(mesh_face), npair=len(c.pair1), nlevel=c.nlevel, nmaskw=c.nmaskw,
+        nuserdata=int(c.size_attrs.get("nuserdata", 0)), nconmax=int(c.size_attrs.get("nconmax", -1)),
+        njmax=int(c.size_attrs.get("njmax", -1)), neq=c.neq, nmocap=c.nmocap, nsensor=c.nsensor, nsensordata=c.adr,
+        opt_timestep=[float(c.opt.get("timestep", 0.002))],
+        opt_gravity=_vec(c.opt.get("gravity", "0 0 -9.81"), 3),
+        opt_tolerance=[float(c.opt.get("tolerance", 1e-8))],
+        opt_impratio=[float(c.opt.get("impratio", 1))],
+        opt_mpr_tolerance=[float(c.opt.get("mpr_tolerance", 1e-6))],
         opt_ls_tolerance=[0.01],
         opt_meaninertia=[1.0],
-        opt_iterations=[int(opt.get("iterations", 100))],
+        opt_iterations=[int(c.opt.get("iterations", 100))],
         opt_ls_iterations=[50],
-        opt_mpr_iterations=[int(opt.get("mpr_iterations", 50))],
-        opt_cone=[cone], opt_disableflags=[disableflags], opt_pid=[0],
-        body_parentid=parent, body_rootid=rootid, body_weldid=weldid, body_mocapid=mocapid,
-        body_jntadr=body_jntadr, body_jntnum=body_jntnum, body_dofadr=body_dofadr,
-        body_dofnum=body_dofnum, body_geomadr=body_geomadr, body_geomnum=body_geomnum,
-        body_level=level, body_order=order, level_adr=level_adr,
-        body_dofmask=dofmask.view(np.int32), body_pos=body_pos, body_quat=body_quat,
-        body_ipos=body_ipos, body_iquat=body_iquat, body_mass=body_mass,
-        body_subtreemass=subtreemass, body_inertia=body_inertia,
-        body_invweight0=np.zeros((nbody, 2)),
-        jnt_type=jnt_type, jnt_qposadr=jnt_qposadr, jnt_dofadr=jnt_dofadr, jnt_bodyid=jnt_bodyid,
-        jnt_limited=jnt_limited, jnt_pos=jnt_pos, jnt_axis=jnt_axis, jnt_stiffness=jnt_stiffness,
-        jnt_range=jnt_range, jnt_margin=jnt_margin, jnt_solref=jnt_solref, jnt_solimp=jnt_solimp,
-        dof_bodyid=np.array(dof_bodyid, int), dof_jntid=np.array(dof_jntid, int),
-        dof_parentid=dof_parentid, dof_armature=np.array(dof_armature),
-        dof_damping=np.array(dof_damping), dof_frictionloss=np.array(dof_frictionloss),
-        dof_invweight0=np.zeros(nv), dof_solref=np.array(dof_solref).reshape(nv, 2),
-        dof_solimp=np.array(dof_solimp).reshape(nv, 5), qpos0=qpos0, qpos_spring=qpos_spring,
-        geom_type=geom_type, geom_bodyid=geom_bodyid, geom_dataid=geom_dataid,
-        geom_contype=geom_contype, geom_conaffinity=geom_conaffinity, geom_condim=geom_condim,
-        geom_priority=geom_priority, geom_size=geom_size, geom_pos=geom_pos, geom_quat=geom_quat,
-        geom_rbound=geom_rbound, geom_aabb=geom_aabb, geom_friction=geom_friction, geom_margin=geom_margin,
-        geom_gap=geom_gap, geom_solmix=geom_solmix, geom_solref=geom_solref, geom_solimp=geom_solimp,
-        site_bodyid=site_bodyid, site_pos=site_pos, site_quat=site_quat,
+        opt_mpr_iterations=[int(c.opt.get("mpr_iterations", 50))],
+        opt_cone=[cone], opt_disableflags=[c.disableflags], opt_pid=[0],
+        body_parentid=c.parent, body_rootid=c.rootid, body_weldid=c.weldid, body_mocapid=c.mocapid,
+        body_jntadr=c.body_jntadr, body_jntnum=c.body_jntnum, body_dofadr=c.body_dofadr,
+        body_dofnum=c.body_dofnum, body_geomadr=c.body_geomadr, body_geomnum=c.body_geomnum,
+        body_level=c.level, body_order=c.order, level_adr=c.level_adr,
+        body_dofmask=c.dofmask.view(np.int32), body_pos=c.body_pos, body_quat=c.body_quat,
+        body_ipos=c.body_ipos, body_iquat=c.body_iquat, body_mass=c.body_mass,
+        body_subtreemass=c.subtreemass, body_inertia=c.body_inertia,
+        body_invweight0=np.zeros((c.nbody, 2)),
+        jnt_type=c.jnt_type, jnt_qposadr=c.jnt_qposadr, jnt_dofadr=c.jnt_dofadr, jnt_bodyid=c.jnt_bodyid,
+        jnt_limited=c.jnt_limited, jnt_pos=c.jnt_pos, jnt_axis=c.jnt_axis, jnt_stiffness=c.jnt_stiffness,
+        jnt_range=c.jnt_range, jnt_margin=c.jnt_margin, jnt_solref=c.jnt_solref, jnt_solimp=c.jnt_solimp,
+        dof_bodyid=np.array(c.dof_bodyid, int), dof_jntid=np.array(c.dof_jntid, int),
+        dof_parentid=c.dof_parentid, dof_armature=np.array(c.dof_armature),
+        dof_damping=np.array(c.dof_damping), dof_frictionloss=np.array(c.dof_frictionloss),
+        dof_invweight0=np.zeros(c.nv), dof_solref=np.array(c.dof_solref).reshape(c.nv, 2),
+        dof_solimp=np.array(c.dof_solimp).reshape(c.nv, 5), qpos0=c.qpos0, qpos_spring=c.qpos_spring,
+        geom_type=c.geom_type, geom_bodyid=c.geom_bodyid, geom_dataid=c.geom_dataid,
+        geom_contype=c.geom_contype, geom_conaffinity=c.geom_conaffinity, geom_condim=c.geom_condim,
+        geom_priority=c.geom_priority, geom_size=c.geom_size, geom_pos=c.geom_pos, geom_quat=c.geom_quat,
+        geom_rbound=c.geom_rbound, geom_aabb=c.geom_aabb, geom_friction=c.geom_friction, geom_margin=c.geom_margin,
+        geom_gap=c.geom_gap, geom_solmix=c.geom_solmix, geom_solref=c.geom_solref, geom_solimp=c.geom_solimp,
+        site_bodyid=c.site_bodyid, site_pos=c.site_pos, site_quat=c.site_quat,
         mesh_vertadr=mesh_vertadr, mesh_vertnum=mesh_vertnum, mesh_faceadr=mesh_faceadr,
         mesh_facenum=mesh_facenum, mesh_vert=mesh_vert, mesh_adjadr=adjadr, mesh_adj=mesh_adj,
-        mesh_face=mesh_face, pair_geom1=np.array(pair1, int), pair_geom2=np.array(pair2, int),
-        tendon_adr=np.array([t["_adr"] for t in T], int), tendon_num=np.array([t["_num"] for t in T], int),
-        tendon_limited=tendon_limited, tendon_range=tendon_range, tendon_margin=tendon_margin,
-        tendon_stiffness=tendon_stiffness, tendon_damping=tendon_damping,
-        tendon_frictionloss=tendon_frictionloss, tendon_lengthspring=tendon_lengthspring,
-        tendon_length0=np.zeros(ntendon), tendon_invweight0=np.zeros(ntendon),
-        tendon_solref_lim=tendon_solref_lim, tendon_solimp_lim=tendon_solimp_lim,
-        wrap_type=np.array(W_type, int), wrap_objid=np.array(W_obj, int), wrap_prm=np.array(W_prm, float),
-        actuator_trntype=act_trntype, actuator_trnid=act_trnid, actuator_gaintype=act_gaintype,
-        actuator_biastype=act_biastype, actuator_ctrllimited=act_ctrllimited,
-        actuator_forcelimited=act_forcelimited, actuator_gainprm=act_gainprm,
-        actuator_biasprm=act_biasprm, actuator_ctrlrange=act_ctrlrange,
-        actuator_forcerange=act_forcerange, actuator_gear=act_gear, actuator_user0=act_user0,
-        eq_type=eq_type, eq_obj1id=eq_obj1, eq_obj2id=eq_obj2, eq_active=eq_active, eq_data=eq_data,
-        eq_solref=eq_solref, eq_solimp=eq_solimp,
-        sensor_type=sensor_type, sensor_objid=sensor_objid, sensor_adr=sensor_adr, sensor_dim=sensor_dim,
+        mesh_face=mesh_face, pair_geom1=np.array(c.pair1, int), pair_geom2=np.array(c.pair2, int),
+        tendon_adr=np.array([t["_adr"] for t in c.T], int), tendon_num=np.array([t["_num"] for t in c.T], int),
+        tendon_limited=c.tendon_limited, tendon_range=c.tendon_range, tendon_margin=c.tendon_margin,
+        tendon_stiffness=c.tendon_stiffness, tendon_damping=c.tendon_damping,
+        tendon_frictionloss=c.tendon_frictionloss, tendon_lengthspring=c.tendon_lengthspring,
+        tendon_length0=np.zeros(c.ntendon), tendon_invweight0=np.zeros(c.ntendon),
+        tendon_solref_lim=c.tendon_solref_lim, tendon_solimp_lim=c.tendon_solimp_lim,
+        wrap_type=np.array(c.W_type, int), wrap_objid=np.array(c.W_obj, int), wrap_prm=np.array(c.W_prm, float),
+        actuator_trntype=c.act_trntype, actuator_trnid=c.act_trnid, actuator_gaintype=c.act_gaintype,
+        actuator_biastype=c.act_biastype, actuator_ctrllimited=c.act_ctrllimited,
+        actuator_forcelimited=c.act_forcelimited, actuator_gainprm=c.act_gainprm,
+        actuator_biasprm=c.act_biasprm, actuator_ctrlrange=c.act_ctrlrange,
+        actuator_forcerange=c.act_forcerange, actuator_gear=c.act_gear, actuator_user0=c.act_user0,
+        eq_type=c.eq_type, eq_obj1id=c.eq_obj1, eq_obj2id=c.eq_obj2, eq_active=c.eq_active, eq_data=c.eq_data,
+        eq_solref=c.eq_solref, eq_solimp=c.eq_solimp,
+        sensor_type=c.sensor_type, sensor_objid=c.sensor_objid, sensor_adr=c.sensor_adr, sensor_dim=c.sensor_dim,
     )
-    for k, v in list(m.items()):
+    for k, v in list(c.m.items()):
         if not isinstance(v, (int, np.integer)):
-            m[k] = np.ascontiguousarray(np.asarray(v)).reshape(-1)
-    cm = CompiledModel(m, names, xml_string)
-    set_const(m)
-    return cm
+            c.m[k] = np.ascontiguousarray(np.asarray(v)).reshape(-1)
+    c.cm = CompiledModel(c.m, c.names, c.xml_string)
+    set_const(c.m)
+
+
+_PASSES = (_pass_document, _pass_compiler_option_size, _pass_assets, _pass_kinematic_tree, _pass_joints_dofs, _pass_geoms, _pass_body_inertial_properties, _pass_sites, _pass_collision_pair_list, _pass_tendons, _pass_actuators, _pass_equality, _pass_mesh_tables_and_model)
+
+
+def compile_mjcf(xml_string, asset_loader=None):
+    """Compile an MJCF document (string) into a CompiledModel: one pass per section of the document, in the order the
+    later passes need (tests/test_model_compile.py exercises the passes one by one)."""
+    c = _Ctx()
+    c.xml_string, c.asset_loader = xml_string, asset_loader
+    for p in _PASSES:
+        p(c)
+    return c.cm
 
 
 def _solimp(s):

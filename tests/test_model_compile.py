@@ -80,3 +80,26 @@ def test_committed_blob_is_reproducible(locked_blob):
     cm = mjcf.compile_mjcf(ref.locked_xml())
     cm.m["opt_pid"][0] = 1
     assert cm.blob() == locked_blob
+
+
+def test_compiler_passes_one_by_one():
+    """compile_mjcf is a sequence of passes over one context (mjcf._PASSES): run them one at a time on a small document and
+    check what each leaves behind for the next."""
+    from robogym_b200 import mjcf
+    from toy_models import FREE_BODIES
+
+    c = mjcf._Ctx()
+    c.xml_string, c.asset_loader = FREE_BODIES, None
+    seen = {}
+    for p in mjcf._PASSES:
+        p(c)
+        seen[p.__name__] = set(vars(c))
+    assert [p.__name__ for p in mjcf._PASSES][:4] == ["_pass_document", "_pass_compiler_option_size", "_pass_assets", "_pass_kinematic_tree"]
+    assert "root" in seen["_pass_document"] and "angle_scale" in seen["_pass_compiler_option_size"]
+    assert "nbody" in seen["_pass_kinematic_tree"] and "nbody" not in seen["_pass_assets"]
+    assert c.nbody == 7 and (c.nq, c.nv) == (23, 20)                     # world, floor, box, ball, brick, arm, fore; 3 free joints + 2 hinges
+    assert "pair1" in seen["_pass_collision_pair_list"] and "pair1" not in seen["_pass_sites"]
+    assert len(c.pair1) == len(c.pair2) > 0
+    assert "act_gainprm" in seen["_pass_actuators"] and c.nu == 2
+    assert "cm" in seen["_pass_mesh_tables_and_model"]
+    assert c.cm.blob() == mjcf.compile_mjcf(FREE_BODIES).blob()
