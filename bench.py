@@ -384,6 +384,8 @@ def run_gpu_arm(args):
     strong = args.scaling == "strong"
     NBOX = cfg["nenv"]
     N = NBOX // world if strong else NBOX                      # weak: the config's batch per GPU; strong: per box
+    if os.environ.get("RG_BENCH_NENV"):                        # experiments only
+        N = int(os.environ["RG_BENCH_NENV"])
     lo_env, hi_env = shard_range(N * world, rank, world)
     caps = cfg["caps"]
     if os.environ.get("RG_BENCH_CAPS"):        # experiments: "contacts,rows,dofs" (0 = engine default)

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
   const int total = args.nslots ? *args.nslots : args.io.nenv;
   for (;;) {
     __syncthreads();                                   /* everybody is done with the previous round (and with sh_slot0) */
-    if (threadIdx.x == 0) sh_slot0 = atomicAdd(args.counter, args.warps);
+    if (threadIdx.x == 0) sh_slot0 = atomicAdd(args.counter, args.warps);   /* (shrinking tail chunks measured worse: a round's length hardly depends on its warp count) */
     __syncthreads();
     const int slot0 = sh_slot0;
     if (slot0 >= total) break;
@@ -400,6 +400,9 @@ static int rg_batch_size(rg_batch* b) {
   if (warps > RG_MAX_WARPS) warps = RG_MAX_WARPS;
   /* rounds are handed out dynamically and a partial round runs with fewer warps, so more resident warps never cost padding */
   if (warps > nenv) warps = nenv;
+  /* a batch smaller than one full round is spread over all SMs (fewer warps per CTA) rather than packed into few of them:
+     a round lasts as long as its slowest environment, and fewer resident warps make every one of them faster */
+  if (nenv < sms * warps) { const int even = (nenv + sms - 1) / sms; if (even < warps) warps = even; }
   const char* wenv = getenv("RG_WARPS_PER_CTA");
   if (wenv && atoi(wenv) > 0 && atoi(wenv) <= RG_MAX_WARPS && per_warp * atoi(wenv) + fixed <= maxsmem) warps = atoi(wenv);
   b->warps = warps;
