@@ -64,7 +64,11 @@ enum rg_field {
   RG_FIELD_BODY_XVEL = 18, /* [nenv][nbody*6]     out    (optional): angular, linear velocity of every body frame in world axes
                               = data.get_body_xvelr / get_body_xvelp (robogym/robot/ur16e/mujoco/joint_controlled_arm.py:32,
                               robogym/envs/rearrange/simulation/base.py:465-472) */
-  RG_NFIELDS = 19
+  RG_FIELD_MOCAP_POS = 19, /* [nenv][nmocap*3]    in     (optional): data.mocap_pos (world coordinates); unbound = the mocap bodies' model pose.
+                              robogym moves the UR16e tool centre point by a mocap body welded to it
+                              (robogym/robot/control/tcp/mocap_solver.py:41-46, robogym/assets/xmls/robot/ur16e/tcp_mocap.xml:2) */
+  RG_FIELD_MOCAP_QUAT = 20,/* [nenv][nmocap*4]    in     (optional): data.mocap_quat */
+  RG_NFIELDS = 21
 };
 #define RG_MAX_CONTACTS 32   /* DEFAULT contact capacity of a batch (rg_batch_create); rg_batch_create_ex picks another */
 #define RG_MAX_PARAM_OVERRIDES 16

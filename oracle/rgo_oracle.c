@@ -32,6 +32,7 @@ enum { BIAS_NONE = 0, BIAS_AFFINE = 1, BIAS_USER = 3 };
 enum { DSBL_CONSTRAINT = 1, DSBL_EQUALITY = 2, DSBL_FRICTIONLOSS = 4, DSBL_LIMIT = 8, DSBL_CONTACT = 16,
        DSBL_PASSIVE = 32, DSBL_GRAVITY = 64, DSBL_CLAMPCTRL = 128, DSBL_WARMSTART = 256,
        DSBL_ACTUATION = 1024, DSBL_REFSAFE = 2048 };
+enum { EQ_CONNECT = 0, EQ_WELD = 1, EQ_JOINT = 2 };
 enum { ROW_EQUALITY = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CONTACT = 3, ROW_CONTACT_ELL = 4 /* first row of an elliptic-cone contact: dim rows follow each other */, ROW_CONTACT_ELLF = 5 /* its friction rows */ };
 
 /* ------------------------------------------------------------------ model */
@@ -129,7 +130,8 @@ void* rgo_model_field(rgo_model* m, const char* name, int* count, int* is_int) {
   F(efc_aref, MAXEFC) F(efc_D, MAXEFC) F(efc_R, MAXEFC) F(efc_force, MAXEFC) F(efc_pos, MAXEFC)                \
   F(efc_margin, MAXEFC) F(efc_floss, MAXEFC) F(efc_vel, MAXEFC) F(efc_diagApprox, MAXEFC)                     \
   F(efc_solref, MAXEFC * 2) F(efc_solimp, MAXEFC * 5) F(efc_jar, MAXEFC) F(sensordata, nsensordata + 1)        \
-  F(body_I10, nbody * 10) F(wrap_xpos, nwrap * 6 + 6) F(solver_stat, 8) F(contact_solimp, MAXCON * 5)
+  F(body_I10, nbody * 10) F(wrap_xpos, nwrap * 6 + 6) F(solver_stat, 8) F(contact_solimp, MAXCON * 5)         \
+  F(mocap_pos, nmocap * 3) F(mocap_quat, nmocap * 4)
 
 struct rgo_data {
 #define F(n, c) double* n;
@@ -206,6 +208,13 @@ void rgo_reset(const rgo_model* m, rgo_data* d) {
   d->time[0] = 0;
   d->ncon = d->nefc = 0;
   d->warning = 0;
+  /* mocap bodies start at their model pose (mj_resetData; robogym then moves them through data.mocap_pos / mocap_quat,
+     robogym/robot/control/tcp/mocap_solver.py:41-46 via gym's mocap_set_action / reset_mocap2body_xpos) */
+  for (int b = 0; b < m->nbody; b++)
+    if (m->body_mocapid[b] >= 0) {
+      memcpy(d->mocap_pos + 3 * m->body_mocapid[b], m->body_pos + 3 * b, 3 * sizeof(double));
+      memcpy(d->mocap_quat + 4 * m->body_mocapid[b], m->body_quat + 4 * b, 4 * sizeof(double));
+    }
 }
 
 /* ------------------------------------------------------------------ small math */
@@ -284,6 +293,10 @@ static void rgo_kinematics(const rgo_model* m, rgo_data* d) {
     rotvec(t, xquat + 4 * p, m->body_pos + 3 * b);
     add3(pos, xpos + 3 * p, t);
     quat_mul(quat, xquat + 4 * p, m->body_quat + 4 * b);
+    if (m->body_mocapid[b] >= 0) {   /* mocap body (child of the world, no joints): pose comes from the data */
+      copy3(pos, d->mocap_pos + 3 * m->body_mocapid[b]);
+      memcpy(quat, d->mocap_quat + 4 * m->body_mocapid[b], 4 * sizeof(double));
+    }
     for (int k = 0; k < m->body_jntnum[b]; k++) {
       int j = m->body_jntadr[b] + k, qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
       int type = m->jnt_type[j];

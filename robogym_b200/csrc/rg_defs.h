@@ -151,6 +151,7 @@ enum { RG_DSBL_CONSTRAINT = 1, RG_DSBL_EQUALITY = 2, RG_DSBL_FRICTIONLOSS = 4, R
        RG_DSBL_PASSIVE = 32, RG_DSBL_GRAVITY = 64, RG_DSBL_CLAMPCTRL = 128, RG_DSBL_WARMSTART = 256,
        RG_DSBL_ACTUATION = 1024, RG_DSBL_REFSAFE = 2048 };
 enum { RG_EL_FLOSS = 0, RG_EL_JLIMIT = 1, RG_EL_TLIMIT = 2 };
+enum { RG_EQ_CONNECT = 0, RG_EQ_WELD = 1, RG_EQ_JOINT = 2 };
 enum { RG_WARN_CONTACT_FULL = 1, RG_WARN_ROWS_FULL = 2, RG_WARN_BAD_STATE = 4, RG_WARN_MPR = 8, RG_WARN_TENDON_NNZ = 16, RG_WARN_DOFS_FULL = 32 };
 
 /* Device view of the compiled model: fp32 / int32 copies of every rg_model_fields.h array. */
@@ -167,6 +168,7 @@ struct RgModel {
   const int* dof_lvl;          /* [2 nv + 2]: dof ids sorted by depth, then the start of every depth level (ndoflevel + 1 entries) */
   const int* dof_xlvl;         /* the same lists restricted to the dofs that stay out of the constraint solver */
   const int* dof_sidx;         /* [2 nv]: solver position of every dof (or -1), then the dof at every solver position */
+  const int* eqrow;            /* [neqrow]: equality id * 8 + row (weld: 6 rows, joint coupling: 1); row k is "virtual tendon" ntendon + k */
   const float* mesh_vert4;     /* [nmeshvert][4]: hull vertices padded to 16 bytes (one vector load each) */
   const unsigned short* pair_packed; /* [npair] geom1 | geom2 << 8 when ngeom <= 256 (staged in shared memory), else nullptr */
   float origin[3];             /* world translation applied at load so coordinates stay small in fp32 */
@@ -174,6 +176,7 @@ struct RgModel {
   int nM;                      /* entries of the tree-sparse mass matrix: sum over dofs of (depth + 1) */
   int ndoflevel;               /* depth levels of the dof tree */
   int ns;                      /* dofs in the constraint solver (<= nv) */
+  int neqrow;                  /* rows of the active equality constraints */
 };
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
@@ -187,6 +190,7 @@ struct RgLayout {
   int con, cu, cw, cF, cprm;         /* contacts + per-contact solver state */
   int el_i, el_D, el_jar, el_jv, el_f;
   int tileJ, tileWJ, tileDof, cand, cand2, scal, eldof, env, cdof, sep, stage;
+  int mocap;                         /* [nmocap][7] pose of the mocap bodies (data.mocap_pos / mocap_quat) */
   int ncon, nel, tile;               /* capacities: contacts, single-row elements, dofs per contact */
   int total;
 };
@@ -220,6 +224,7 @@ struct RgModelDev {
   RgArr<int> dof_lvl;
   RgArr<int> dof_xlvl;
   RgArr<int> dof_sidx;
+  RgArr<int> eqrow;
   RgArr<unsigned short> pair_packed;
   int has_pairs;
   const float* mesh_vert4;
@@ -228,6 +233,7 @@ struct RgModelDev {
   int nM;
   int ndoflevel;
   int ns;
+  int neqrow;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev

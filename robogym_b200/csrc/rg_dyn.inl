@@ -124,6 +124,11 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
     float quat[4] = {m.body_quat[4 * b], m.body_quat[4 * b + 1], m.body_quat[4 * b + 2], m.body_quat[4 * b + 3]};
     const int ja = m.body_jntadr[b], jn = m.body_jntnum[b];
     for (int k = 0; k < jn; k++) rg_apply_joint(RG_MREF(m), s + L.qpos, ja + k, pos, quat);
+    if (m.body_mocapid[b] >= 0) {   /* mocap body (child of the world, no joints): its pose is data, not model */
+      const float* mp = s + L.mocap + 7 * m.body_mocapid[b];
+      rg_copy3(pos, mp);
+      quat[0] = mp[3]; quat[1] = mp[4]; quat[2] = mp[5]; quat[3] = mp[6];
+    }
     rg_copy3(s + L.lpos + 3 * b, pos);
     float* lq = s + L.lquat + 4 * b;
     lq[0] = quat[0]; lq[1] = quat[1]; lq[2] = quat[2]; lq[3] = quat[3];
@@ -518,6 +523,78 @@ RG_DEV_NOINLINE void rg_tendon(const RgCtx c) {
     }
     ((int*)(s + L.tJn))[t] = nnz;
     s[L.tvel + t] = v;
+  }
+  RG_PHASE_END
+}
+
+/* Equality constraints (weld, joint coupling; robogym/assets/xmls/robot/ur16e/base.xml:52-54, gripper_actuators.xml:2-4): every
+ * row becomes a "virtual tendon" behind the real ones -- residual in tlen, its rate in tvel, sparse Jacobian row in tJ* -- so the
+ * constraint builder and the solver handle it with the tendon-limit machinery (rg_make_constraints).  One lane per constraint.
+ * Weld (mj_instantiateEquality, mjEQ_WELD): body 2 keeps the pose eq_data relative to body 1; residual = position error in
+ * world axes, then the vector part of conj(q2) q1 relquat; d/dt of that = 1/2 vec(conj(q2) [0, w1 - w2] q1 relquat). */
+RG_DEV_NOINLINE void rg_equality(const RgCtx c) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
+  const int nt = m.ntendon;
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int r0 = lane; r0 < m.neqrow; r0 += 32) {
+    const int code = m.eqrow[r0];
+    if (code & 7) continue;               /* the lane of a constraint's first row does all of its rows */
+    const int e = code >> 3, t0 = nt + r0;
+    const float* data = m.eq_data + 7 * e;
+    int* tJn = (int*)(s + L.tJn);
+    unsigned char* ji = (unsigned char*)(s + L.tJi) + RG_TJ * t0;
+    float* jv = s + L.tJv + RG_TJ * t0;
+    if (m.eq_type[e] == RG_EQ_JOINT) {
+      const int j1 = m.eq_obj1id[e], j2 = m.eq_obj2id[e];
+      const int a1 = m.jnt_qposadr[j1], d1 = m.jnt_dofadr[j1];
+      float cpos = s[L.qpos + a1] - m.qpos0[a1] - data[0], vel = s[L.qvel + d1];
+      int n = 1;
+      ji[0] = (unsigned char)d1; jv[0] = 1.0f;
+      if (j2 >= 0) {
+        const int a2 = m.jnt_qposadr[j2], d2 = m.jnt_dofadr[j2];
+        const float dif = s[L.qpos + a2] - m.qpos0[a2];
+        cpos -= dif * (data[1] + dif * (data[2] + dif * (data[3] + dif * data[4])));
+        const float deriv = data[1] + dif * (2.0f * data[2] + dif * (3.0f * data[3] + dif * 4.0f * data[4]));
+        ji[1] = (unsigned char)d2; jv[1] = -deriv; n = 2;
+        vel -= deriv * s[L.qvel + d2];
+      }
+      tJn[t0] = n; s[L.tlen + t0] = cpos; s[L.tvel + t0] = vel;
+      continue;
+    }
+    const int b1 = m.eq_obj1id[e], b2 = m.eq_obj2id[e];
+    float p0[3], cpos[6], q[4], qc[4], qe[4], vel[6] = {0, 0, 0, 0, 0, 0};
+    const float* p1 = s + L.xpos + 3 * b2;
+    rg_rot(p0, s + L.xquat + 4 * b1, data);
+    rg_add3(p0, p0, s + L.xpos + 3 * b1);
+    rg_sub3(cpos, p0, p1);
+    rg_quat_mul(q, s + L.xquat + 4 * b1, data + 3);
+    const float* q2 = s + L.xquat + 4 * b2;
+    qc[0] = q2[0]; qc[1] = -q2[1]; qc[2] = -q2[2]; qc[3] = -q2[3];
+    rg_quat_mul(qe, qc, q);
+    cpos[3] = qe[1]; cpos[4] = qe[2]; cpos[5] = qe[3];
+    int n = 0;
+    RG_NOUNROLL for (int w = 0; w < m.nmaskw; w++) {
+      const unsigned m1 = (unsigned)m.body_dofmask[b1 * m.nmaskw + w], m2 = (unsigned)m.body_dofmask[b2 * m.nmaskw + w];
+      unsigned bits = m1 | m2;
+      while (bits && n < RG_TJ) {
+        const int bit = rg_ctz(bits);
+        bits &= bits - 1;
+        const int d = 32 * w + bit;
+        const float* S = s + L.S + 6 * d;
+        float col[6] = {0, 0, 0, 0, 0, 0}, ang[3] = {0, 0, 0}, jp[3];
+        if ((m1 >> bit) & 1u) { rg_jacp_world(c, d, p0, jp); rg_add3(col, col, jp); rg_add3(ang, ang, S); }
+        if ((m2 >> bit) & 1u) { rg_jacp_world(c, d, p1, jp); rg_sub3(col, col, jp); rg_sub3(ang, ang, S); }
+        float wq[4] = {0.0f, ang[0], ang[1], ang[2]}, t1[4], t2[4];
+        rg_quat_mul(t1, qc, wq);
+        rg_quat_mul(t2, t1, q);
+        col[3] = 0.5f * t2[1]; col[4] = 0.5f * t2[2]; col[5] = 0.5f * t2[3];
+        const float qd = s[L.qvel + d];
+        for (int k = 0; k < 6; k++) { ji[RG_TJ * k + n] = (unsigned char)d; jv[RG_TJ * k + n] = col[k]; vel[k] += col[k] * qd; }
+        n++;
+      }
+    }
+    for (int k = 0; k < 6; k++) { tJn[t0 + k] = n; s[L.tlen + t0 + k] = cpos[k]; s[L.tvel + t0 + k] = vel[k]; }
   }
   RG_PHASE_END
 }

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     RG_SETOFF(dof_lvl)
     RG_SETOFF(dof_xlvl)
     RG_SETOFF(dof_sidx)
+    RG_SETOFF(eqrow)
     RG_SETPTR(mesh_vert4)
     if (lane == 0) {
       sm->has_pairs = args.m.pair_packed != nullptr;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       sm->nM = args.m.nM;
       sm->ndoflevel = args.m.ndoflevel;
       sm->ns = args.m.ns;
+      sm->neqrow = args.m.neqrow;
     }
     for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
@@ -277,6 +279,7 @@ static void rg_wire_device_view(rg_model* mm) {
   RG_DEVPTR(dof_lvl)
   RG_DEVPTR(dof_xlvl)
   RG_DEVPTR(dof_sidx)
+  RG_DEVPTR(eqrow)
   RG_DEVPTR(mesh_vert4)
   if (mm->hm.view.pair_packed) RG_DEVPTR(pair_packed)
 #undef RG_DEVPTR
@@ -539,6 +542,7 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   io.cost = b->balance ? b->d_cost : nullptr;
   io.sep = b->d_sep;
   io.body_xvel = (float*)b->ptr[RG_FIELD_BODY_XVEL];
+  io.mocap_pos = (const float*)b->ptr[RG_FIELD_MOCAP_POS]; io.mocap_quat = (const float*)b->ptr[RG_FIELD_MOCAP_QUAT];
   io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;
 }

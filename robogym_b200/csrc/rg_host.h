@@ -87,8 +87,6 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
       }
     }
   }
-  /* features the compiler can describe but this engine does not simulate: refuse them instead of stepping wrong physics */
-  if (m.nmocap > 0) { err = "model uses mocap bodies: not supported by this engine"; return false; }
   /* derived arrays appended to the small section would disturb the order; put them right after the blob fields
      but account for them in small_bytes by placing them BEFORE the first big field. */
   size_t first_big = names.size();
@@ -101,6 +99,7 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   dst = rg_align16(dst); const size_t off_dlvl = dst; dst += 4 * (2 * (size_t)m.nv + 2);
   dst = rg_align16(dst); const size_t off_xlvl = dst; dst += 4 * (2 * (size_t)m.nv + 2);
   dst = rg_align16(dst); const size_t off_sidx = dst; dst += 4 * (2 * (size_t)m.nv);
+  dst = rg_align16(dst); const size_t off_eqrow = dst; dst += 4 * (6 * (size_t)m.neq + 1);
   dst = rg_align16(dst); const size_t off_pairs = dst; if (m.ngeom <= 256) dst += 2 * (size_t)m.npair;
   dst = rg_align16(dst);
   hm.small_bytes = dst;
@@ -127,7 +126,25 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
-  for (int e = 0; e < m.neq; e++) if (m.eq_active[e]) { err = "model has active equality constraints: not supported by this engine"; return false; }
+  /* rows of the equality constraints (weld: 3 position + 3 orientation rows, joint coupling: 1) -- of all of them: eq_active is
+     read at run time, robogym switches welds off and on (robogym/envs/rearrange/common/base.py:452).  Constraint types the
+     compiler can describe but this engine does not simulate are refused instead of stepping wrong physics */
+  {
+    int* eqrow = (int*)(base + off_eqrow);
+    int n = 0;
+    for (int e = 0; e < m.neq; e++) {
+      if (m.eq_type[e] == RG_EQ_WELD) {
+        const int b1 = m.eq_obj1id[e], b2 = m.eq_obj2id[e];
+        int nd = 0;
+        for (int w = 0; w < m.nmaskw; w++) nd += __builtin_popcount((unsigned)(m.body_dofmask[b1 * m.nmaskw + w] | m.body_dofmask[b2 * m.nmaskw + w]));
+        if (nd > RG_TJ) { err = "weld constraint touches more than RG_TJ dofs: not supported by this engine"; return false; }
+        for (int k = 0; k < 6; k++) eqrow[n++] = 8 * e + k;
+      } else if (m.eq_type[e] == RG_EQ_JOINT) eqrow[n++] = 8 * e;
+      else { err = "equality constraint type other than weld / joint: not supported by this engine"; return false; }
+    }
+    m.neqrow = n;
+    m.eqrow = eqrow;
+  }
   int* subtree = (int*)(base + off_subtree);
   int* mrow = (int*)(base + off_mrow);
   for (int b = 0; b < m.nbody; b++) subtree[b] = 1;
@@ -178,6 +195,10 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
         else if (m.wrap_type[w] == RG_WRAP_SITE) mark_body(m.site_bodyid[m.wrap_objid[w]]);
         else if (m.wrap_type[w] == RG_WRAP_SPHERE || m.wrap_type[w] == RG_WRAP_CYLINDER) mark_body(m.geom_bodyid[m.wrap_objid[w]]);
       }
+    for (int e = 0; e < m.neq; e++) {
+      if (m.eq_type[e] == RG_EQ_WELD) { mark_body(m.eq_obj1id[e]); mark_body(m.eq_obj2id[e]); }
+      else { mark_body(m.jnt_bodyid[m.eq_obj1id[e]]); if (m.eq_obj2id[e] >= 0) mark_body(m.jnt_bodyid[m.eq_obj2id[e]]); }
+    }
     int* sidx = (int*)(base + off_sidx);
     int ns = 0;
     for (int d = m.nv - 1; d >= 0; d--) {
@@ -207,6 +228,7 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
   hm.offsets.push_back(off_dlvl);
   hm.offsets.push_back(off_xlvl);
   hm.offsets.push_back(off_sidx);
+  hm.offsets.push_back(off_eqrow);
   /* hull vertices padded to float4: the narrow phase scans a hull's vertices with one 16-byte load each */
   float* v4 = (float*)(base + off_v4);
   for (int k = 0; k < m.nmeshvert; k++) { v4[4 * k] = m.mesh_vert[3 * k]; v4[4 * k + 1] = m.mesh_vert[3 * k + 1]; v4[4 * k + 2] = m.mesh_vert[3 * k + 2]; v4[4 * k + 3] = 0.0f; }

@@ -417,18 +417,23 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     nel += tot;
   }
   const int tl0 = nel < L.nel ? nel : L.nel;
-  /* tendon limits */
-  for (int base = 0; on && !(flags & RG_DSBL_LIMIT) && base < m.ntendon; base += 32) {
+  /* tendon limits, then the equality rows: every row of a weld / joint coupling is a "virtual tendon" (rg_equality) whose
+     residual must be zero -- the quadratic penalty 1/2 D jar^2 of an always-active row is exactly the sum of the two one-sided
+     penalties of a lower and an upper limit at the same place, so an equality row is a pair of limit rows that are both there */
+  const int nt = m.ntendon, nvt = nt + m.neqrow;
+  for (int base = 0; on && base < nvt; base += 32) {
     LANEVAR(int, cnt); LANEVAR(int, pos);
     int tot;
     RG_PHASE_BEGIN
     const int t = base + lane;
     int cn = 0;
-    if (t < m.ntendon && m.tendon_limited[t]) {
-      const float len = s[L.tlen + t];
-      if (len - m.tendon_range[2 * t] < m.tendon_margin[t]) cn++;
-      if (m.tendon_range[2 * t + 1] - len < m.tendon_margin[t]) cn++;
-    }
+    if (t < nt) {
+      if (m.tendon_limited[t] && !(flags & RG_DSBL_LIMIT)) {
+        const float len = s[L.tlen + t];
+        if (len - m.tendon_range[2 * t] < m.tendon_margin[t]) cn++;
+        if (m.tendon_range[2 * t + 1] - len < m.tendon_margin[t]) cn++;
+      }
+    } else if (t < nvt && !(flags & RG_DSBL_EQUALITY) && m.eq_active[m.eqrow[t - nt] >> 3]) cn = 2;
     LV(cnt) = cn;
     RG_PHASE_END
     RG_WARP_SCAN(cnt, pos, tot);
@@ -437,12 +442,27 @@ RG_DEV_NOINLINE void rg_make_constraints(const RgCtx c) {
     if (LV(cnt)) {
       const float len = s[L.tlen + t];
       int e = nel + LV(pos);
+      const float* solref = m.tendon_solref_lim + 2 * (t < nt ? t : 0);
+      const float* solimp = m.tendon_solimp_lim + 5 * (t < nt ? t : 0);
+      float lo = 0.0f, hi = 0.0f, margin = 0.0f, invw = 0.0f;
+      if (t < nt) { lo = m.tendon_range[2 * t]; hi = m.tendon_range[2 * t + 1]; margin = m.tendon_margin[t]; invw = m.tendon_invweight0[t]; }
+      else {
+        const int q = m.eqrow[t - nt] >> 3, k = m.eqrow[t - nt] & 7;
+        solref = m.eq_solref + 2 * q; solimp = m.eq_solimp + 5 * q;
+        if (m.eq_type[q] == RG_EQ_WELD) {
+          const int b1 = m.eq_obj1id[q], b2 = m.eq_obj2id[q], o = k < 3 ? 0 : 1;
+          invw = m.body_invweight0[2 * b1 + o] + m.body_invweight0[2 * b2 + o];
+        } else {
+          invw = m.dof_invweight0[m.jnt_dofadr[m.eq_obj1id[q]]];
+          if (m.eq_obj2id[q] >= 0) invw += m.dof_invweight0[m.jnt_dofadr[m.eq_obj2id[q]]];
+        }
+      }
       for (int side = 0; side < 2; side++) {
-        const float dist = side == 0 ? len - m.tendon_range[2 * t] : m.tendon_range[2 * t + 1] - len;
-        if (!(dist < m.tendon_margin[t]) || e >= L.nel) continue;
+        const float dist = side == 0 ? len - lo : hi - len;
+        if ((t < nt && !(dist < margin)) || e >= L.nel) continue;
         const float sg = side == 0 ? 1.0f : -1.0f;
         float R, aref, B, KI;
-        rg_row_params(c, m.tendon_solref_lim + 2 * t, m.tendon_solimp_lim + 5 * t, dist, m.tendon_margin[t], sg * s[L.tvel + t], m.tendon_invweight0[t], 0, &R, &aref, &B, &KI);
+        rg_row_params(c, solref, solimp, dist, margin, sg * s[L.tvel + t], invw, 0, &R, &aref, &B, &KI);
         el_i[e] = RG_EL_TLIMIT + 4 * side + 8 * t;
         s[L.el_D + e] = 1.0f / R; s[L.el_jar + e] = -aref;
         e++;

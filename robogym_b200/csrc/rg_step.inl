@@ -14,6 +14,8 @@ struct RgBatchIO {
   float* qpos; float* qvel; float* ctrl; float* pid; float* warm; float* time;
   const float* xfrc;        /* [nenv][nbody*6] or nullptr */
   const float* timestep;    /* [nenv] per-env opt.timestep override or nullptr */
+  const float* mocap_pos;   /* [nenv][nmocap*3] data.mocap_pos or nullptr (then the mocap bodies keep their model pose) */
+  const float* mocap_quat;  /* [nenv][nmocap*4] data.mocap_quat or nullptr */
   /* derived outputs (any may be nullptr) */
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
   float* body_xvel;         /* [nenv][nbody][6]: angular then linear velocity of the body frame, world axes (data.get_body_xvelr / get_body_xvelp) */
@@ -64,7 +66,9 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   RG_ALLOC(bias, m.nv); RG_ALLOC(smooth, m.nv); RG_ALLOC(qacc, m.nv);
   RG_ALLOC(Ma, m.nv); RG_ALLOC(search, m.nv); RG_ALLOC(Mv, m.nv); RG_ALLOC(qfc, m.nv);
   RG_ALLOC(tmp, rg_imax(m.nv, m.ntendon));
-  RG_ALLOC(tlen, m.ntendon); RG_ALLOC(tvel, m.ntendon); RG_ALLOC(tJn, m.ntendon); RG_ALLOC(tJi, (RG_TJ * m.ntendon + 3) >> 2);   /* dof ids as bytes */ RG_ALLOC(tJv, RG_TJ * m.ntendon); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
+  const int nvt = m.ntendon + m.neqrow;   /* equality rows ride behind the tendons as "virtual tendons" (rg_equality) */
+  RG_ALLOC(tlen, nvt); RG_ALLOC(tvel, nvt); RG_ALLOC(tJn, nvt); RG_ALLOC(tJi, (RG_TJ * nvt + 3) >> 2);   /* dof ids as bytes */ RG_ALLOC(tJv, RG_TJ * nvt); RG_ALLOC(alen, m.nu); RG_ALLOC(aforce, m.nu);
+  RG_ALLOC(mocap, 7 * m.nmocap);
   RG_ALLOC(con, ncon * RG_CON_STRIDE); RG_ALLOC(cu, 6 * ncon); RG_ALLOC(cw, 6 * ncon); RG_ALLOC(cF, 6 * ncon); RG_ALLOC(cprm, RG_CPRM * ncon);
   const int nel64 = nel < 64 ? 64 : nel;   /* el_jv / el_f double as the broad-phase candidate lists (64 entries) */
   RG_ALLOC(el_i, nel); RG_ALLOC(el_D, nel);
@@ -110,7 +114,7 @@ RG_DEV_NOINLINE void rg_forward(const RgCtx c) {
   RG_SYNC_SMALL(); rg_kinematics(c); RG_PROF(c, 0)
   RG_SYNC_SMALL(); rg_massmatrix(c); RG_PROF(c, 1)
   RG_SYNC_SMALL(); rg_bias(c); RG_PROF(c, 2)
-  RG_SYNC_SMALL(); rg_tendon(c); RG_PROF(c, 3)
+  RG_SYNC_SMALL(); rg_tendon(c); if (RG_MDEREF(c.mref).neqrow) rg_equality(c); RG_PROF(c, 3)
   RG_SYNC_SMALL(); rg_forces(c); RG_PROF(c, 4)
   RG_CTA_SYNC(); rg_collision(c); RG_PROF(c, 5)
   RG_SYNC_MID(); rg_make_constraints(c); RG_PROF(c, 6)
@@ -143,6 +147,14 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
     if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
+  /* mocap poses: data.mocap_pos / mocap_quat of this environment, or the model pose of the mocap bodies */
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
+    const int k = m.body_mocapid[b];
+    if (k < 0) continue;
+    float* mp = s + L.mocap + 7 * k;
+    for (int a = 0; a < 3; a++) mp[a] = io.mocap_pos ? io.mocap_pos[((size_t)env * m.nmocap + k) * 3 + a] - m.origin[a] : m.body_pos[3 * b + a];
+    for (int a = 0; a < 4; a++) mp[3 + a] = io.mocap_quat ? io.mocap_quat[((size_t)env * m.nmocap + k) * 4 + a] : m.body_quat[4 * b + a];
+  }
   RG_PHASE_END
   for (int sub = 0; sub < nsub; sub++) {
     rg_forward(c);

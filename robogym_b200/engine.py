@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librobogym_b200.so"))  
 
 # enum rg_field (include/robogym_b200.h)
 (QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,
- ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG, BODY_XVEL) = range(19)
+ ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG, BODY_XVEL, MOCAP_POS, MOCAP_QUAT) = range(21)
 MAX_CONTACTS = 32
 CON_STRIDE = 24
 
@@ -192,6 +192,16 @@ class BatchedSim:
             self._bind(DBG, self.dbg)
         self.xfrc_applied = None
         self.timestep = None
+        # data.mocap_pos / mocap_quat (world coordinates), one row per environment, initialised like mj_resetData does: the
+        # model pose of the mocap bodies (robogym/robot/control/tcp/mocap_solver.py:41-46 then writes them every step)
+        self.mocap_pos = self.mocap_quat = None
+        if m["nmocap"]:
+            ids = [b for b in range(m["nbody"]) if m["body_mocapid"][b] >= 0]
+            ids.sort(key=lambda b: m["body_mocapid"][b])
+            self.mocap_pos = torch.tensor(m["body_pos"].reshape(-1, 3)[ids], **f32).repeat(n, 1, 1).contiguous()
+            self.mocap_quat = torch.tensor(m["body_quat"].reshape(-1, 4)[ids], **f32).repeat(n, 1, 1).contiguous()
+            self._bind(MOCAP_POS, self.mocap_pos)
+            self._bind(MOCAP_QUAT, self.mocap_quat)
 
     def _bind(self, fid, t):
         assert t.is_contiguous()

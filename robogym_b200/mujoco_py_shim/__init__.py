@@ -49,7 +49,7 @@ class CudaEngine:
 
         self.cm = cm
         self.model = engine.DeviceModel(cm.blob(), 0)
-        self.sim = engine.BatchedSim(self.model, 1, 1, outputs=("site_xpos", "body_xpos", "body_xquat", "geom_xpos", "act_force", "qacc", "contact", "ncon", "warn"))
+        self.sim = engine.BatchedSim(self.model, 1, 1, outputs=("site_xpos", "body_xpos", "body_xquat", "body_xvel", "geom_xpos", "act_force", "qacc", "contact", "ncon", "warn"))
         self.sim.enable_xfrc()
 
     def push_model(self, name, arr):
@@ -62,6 +62,12 @@ class CudaEngine:
         self.sim.pid.copy_(f(pid)); self.sim.qacc_warmstart.copy_(f(warm))
         self.sim.xfrc_applied.copy_(f(xfrc).reshape(self.sim.xfrc_applied.shape))
 
+    def push_mocap(self, pos, quat):
+        if self.sim.mocap_pos is not None:
+            t = self.sim.torch
+            self.sim.mocap_pos.copy_(t.as_tensor(np.asarray(pos, dtype=np.float32)).to(self.sim.device).reshape(self.sim.mocap_pos.shape))
+            self.sim.mocap_quat.copy_(t.as_tensor(np.asarray(quat, dtype=np.float32)).to(self.sim.device).reshape(self.sim.mocap_quat.shape))
+
     def run(self, nsub, final_forward):
         self.sim.step(nsub, final_forward)
 
@@ -72,7 +78,7 @@ class CudaEngine:
         con = g(s.contact)[:ncon]
         return dict(qpos=g(s.qpos), qvel=g(s.qvel), pid=g(s.pid), warm=g(s.qacc_warmstart), site_xpos=g(s.site_xpos),
                     body_xpos=g(s.body_xpos), body_xquat=g(s.body_xquat), geom_xpos=g(s.geom_xpos), act_force=g(s.act_force),
-                    qacc=g(s.qacc), ncon=ncon, contact=con, warn=int(s.warn[0].item()))
+                    qacc=g(s.qacc), ncon=ncon, contact=con, warn=int(s.warn[0].item()), body_xvel=g(s.body_xvel))
 
 
 def _default_factory(cm):
@@ -195,6 +201,11 @@ class PyMjData:
         self.geom_xpos = np.zeros((m["ngeom"], 3))
         self.actuator_force = np.zeros(m["nu"])
         self.sensordata = np.zeros(m["nsensordata"])
+        self.body_xvelp = np.zeros((m["nbody"], 3))
+        self.body_xvelr = np.zeros((m["nbody"], 3))
+        mocap = sorted((int(k), b) for b, k in enumerate(m["body_mocapid"]) if k >= 0)
+        self.mocap_pos = np.array([m["body_pos"].reshape(-1, 3)[b] for _, b in mocap], dtype=np.float64).reshape(-1, 3)
+        self.mocap_quat = np.array([m["body_quat"].reshape(-1, 4)[b] for _, b in mocap], dtype=np.float64).reshape(-1, 4)
         self.time = 0.0
         self.ncon = 0
         self.contact = [_Contact() for _ in range(32)]
@@ -205,6 +216,19 @@ class PyMjData:
     def get_body_xquat(self, name): return self.body_xquat[self._model._name2id("body", name)]
     def get_body_xmat(self, name): return mjcf.quat2mat(self.get_body_xquat(name))
     def get_geom_xpos(self, name): return self.geom_xpos[self._model._name2id("geom", name)]
+    def get_body_xvelp(self, name): return self.body_xvelp[self._model._name2id("body", name)]
+    def get_body_xvelr(self, name): return self.body_xvelr[self._model._name2id("body", name)]
+
+    def _mocapid(self, name):
+        k = int(self._model._m["body_mocapid"][self._model._name2id("body", name)])
+        if k < 0:
+            raise ValueError(f'Body "{name}" is not a mocap body.')
+        return k
+
+    def get_mocap_pos(self, name): return self.mocap_pos[self._mocapid(name)]
+    def get_mocap_quat(self, name): return self.mocap_quat[self._mocapid(name)]
+    def set_mocap_pos(self, name, value): self.mocap_pos[self._mocapid(name)] = value
+    def set_mocap_quat(self, name, value): self.mocap_quat[self._mocapid(name)] = value
 
     def get_joint_qpos(self, name):
         a = self._model.get_joint_qpos_addr(name)
@@ -261,6 +285,8 @@ class MjSim:
         d = self._rg_data
         nu = m["nu"]
         self._rg_engine.push_state(d.qpos, d.qvel, d.ctrl, d.userdata[:3 * nu], d.qacc_warmstart, d.xfrc_applied)
+        if len(d.mocap_pos):
+            self._rg_engine.push_mocap(d.mocap_pos, d.mocap_quat)
 
     def _pull(self, nsub):
         d, m = self._rg_data, self._rg_model._m
@@ -270,6 +296,9 @@ class MjSim:
         d.site_xpos[:] = out["site_xpos"].reshape(-1, 3); d.body_xpos[:] = out["body_xpos"].reshape(-1, 3)
         d.body_xquat[:] = out["body_xquat"].reshape(-1, 4); d.geom_xpos[:] = out["geom_xpos"].reshape(-1, 3)
         d.actuator_force[:] = out["act_force"]
+        if "body_xvel" in out:     # [nbody][6]: angular, then linear velocity of the body frame in world axes
+            xv = np.asarray(out["body_xvel"]).reshape(-1, 6)
+            d.body_xvelr[:] = xv[:, :3]; d.body_xvelp[:] = xv[:, 3:]
         d.ncon = out["ncon"]
         while len(d.contact) < d.ncon:
             d.contact.append(_Contact())
@@ -303,6 +332,9 @@ class MjSim:
         d, m = self._rg_data, self._rg_model._m
         d.qpos[:] = m["qpos0"]; d.qvel[:] = 0; d.ctrl[:] = 0; d.qacc[:] = 0; d.qacc_warmstart[:] = 0
         d.userdata[:] = 0; d.xfrc_applied[:] = 0; d.time = 0.0; d.ncon = 0
+        for b, k in enumerate(m["body_mocapid"]):
+            if k >= 0:
+                d.mocap_pos[k] = m["body_pos"].reshape(-1, 3)[b]; d.mocap_quat[k] = m["body_quat"].reshape(-1, 4)[b]
 
     def set_constants(self):
         """mj_setConst after model edits (robogym/mujoco/simulation_interface.py:197-201)."""

@@ -25,6 +25,7 @@ def lib():
         L.rge_name2id.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.rge_model_field.restype = ctypes.c_void_p
         L.rge_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+        L.rge_set_mocap.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.rge_step.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 18 + [ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
@@ -63,6 +64,8 @@ class EmuBatch:
         self.ncon = np.zeros(nenv, np.int32)
         self.warn = np.zeros(nenv, np.int32)
         self.dbg = np.zeros((nenv, lib().rge_dbg_size(self.h)), f)
+        self.mocap_pos = np.zeros((nenv, dims.get("nmocap", 0), 3), f) if dims.get("nmocap", 0) else None
+        self.mocap_quat = np.zeros((nenv, dims.get("nmocap", 0), 4), f) if dims.get("nmocap", 0) else None
 
     def model_field(self, name, dtype):
         n = ctypes.c_int()
@@ -71,6 +74,7 @@ class EmuBatch:
         return np.frombuffer((ct * n.value).from_address(p), dtype=dtype)
 
     def step(self, nsub, final_forward=1):
+        lib().rge_set_mocap(self.h, _p(self.mocap_pos), _p(self.mocap_quat))
         lib().rge_step(self.h, self.nenv, _p(self.qpos), _p(self.qvel), _p(self.ctrl), _p(self.pid), _p(self.warm), _p(self.time),
                        _p(self.xfrc), _p(self.timestep), _p(self.site_xpos), _p(self.body_xpos), _p(self.body_xquat),
                        _p(self.geom_xpos), _p(self.act_force), _p(self.qacc), _p(self.contact), _p(self.ncon), _p(self.warn),

@@ -51,17 +51,34 @@ def test_name_tables_travel_in_the_blob(locked_blob, locked_names):
 
 
 def test_unsupported_features_are_refused(locked_blob):
-    """A model with active equality constraints or mocap bodies must not load (it used to step with silently
-    wrong physics; elliptic cones are simulated since round 2)."""
+    """What the compiler can describe but the engine does not simulate must not load (such models used to step
+    with silently wrong physics).  Elliptic cones, welds, joint couplings and mocap bodies are simulated since round 2; a
+    connect constraint, or a weld between bodies with more than RG_TJ = 8 dofs between them, is still refused."""
+    import numpy as np
+
     import pyemu
     from robogym_b200 import modelblob
 
     names = modelblob.unpack_names(locked_blob)
-    for edit in (lambda m: m.__setitem__("nmocap", 1),):
+
+    def add_eq(m, typ, b1, b2):
+        m["neq"] = 1
+        m["eq_type"], m["eq_obj1id"], m["eq_obj2id"], m["eq_active"] = (np.array([v], np.int32) for v in (typ, b1, b2, 1))
+        m["eq_data"] = np.array([0, 0, 0, 1, 0, 0, 0.0])
+        m["eq_solref"], m["eq_solimp"] = np.array([0.02, 1.0]), np.array([0.9, 0.95, 0.001, 0.5, 2.0])
+
+    tip = names["body"].index("robot0:ffdistal")
+    for edit, ok in ((lambda m: add_eq(m, 0, 0, tip), False),                                  # connect
+                     (lambda m: add_eq(m, 1, 0, tip), True),                                   # weld world <-> fingertip: 6 dofs
+                     (lambda m: add_eq(m, 1, names["body"].index("robot0:thdistal"), tip), False)):   # thumb tip <-> fingertip: 11 dofs
         m = modelblob.unpack(locked_blob)
         edit(m)
-        with pytest.raises(RuntimeError):
-            pyemu.EmuBatch(modelblob.pack(m, names), {k: m[k] for k in modelblob.DIMS}, 1)
+        blob = modelblob.pack(m, names)
+        if ok:
+            pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
+        else:
+            with pytest.raises(RuntimeError):
+                pyemu.EmuBatch(blob, {k: m[k] for k in modelblob.DIMS}, 1)
 
 
 @pytest.mark.gpu

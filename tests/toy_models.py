@@ -283,3 +283,57 @@ def mesh_pile(rng, n=5):
         bodies+='<body name="o%d" pos="%.3f %.3f %.3f" euler="%.2f %.2f %.2f"><joint type="free"/><geom type="mesh" mesh="m%d" density="%.0f" condim="%d"/></body>\n'%(b,*pos,*rng.uniform(-1.5,1.5,3),b,rng.uniform(400,1200),int(rng.choice([1,3,4])))
     xml='<mujoco><compiler angle="radian" coordinate="local"/><option timestep="0.002"/><size nuserdata="0" njmax="400" nconmax="60"/><asset>%s</asset><worldbody><body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>\n%s<body name="blk" pos="0 0 0.03"><geom type="box" size="0.08 0.08 0.03" condim="3"/></body></worldbody></mujoco>'%(assets,bodies)
     return xml, clouds
+
+# A 3-link arm whose tip is dragged by a mocap body through a weld (the UR16e tool-centre-point scheme of
+# robogym/assets/xmls/robot/ur16e/base.xml:52-54 + tcp_mocap.xml), a two-finger gripper whose fingers are coupled by a joint
+# equality with a direct (negative) solref (gripper_actuators.xml:2-4), and a free brick hanging from a second mocap body.
+MOCAP_ARM = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" iterations="30" tolerance="1e-10"/>
+  <size nuserdata="0" njmax="200" nconmax="20"/>
+  <worldbody>
+    <body name="mocap" mocap="true" pos="0.45 0.0 0.55">
+      <geom name="mocap_viz" type="box" size="0.005 0.005 0.005" contype="0" conaffinity="0"/>
+    </body>
+    <body name="hook" mocap="true" pos="-0.3 0.2 0.6"/>
+    <body name="floor" pos="0 0 0"><geom name="floor" type="plane" size="2 2 1" condim="3"/></body>
+    <body name="base" pos="0 0 0.5">
+      <joint name="yaw" type="hinge" axis="0 0 1" damping="0.5" armature="0.01"/>
+      <geom name="g_base" type="capsule" fromto="0 0 0 0.2 0 0" size="0.025" density="600" contype="0" conaffinity="0"/>
+      <body name="upper" pos="0.2 0 0">
+        <joint name="shoulder" type="hinge" axis="0 1 0" damping="0.5" armature="0.01" limited="true" range="-2 2"/>
+        <geom name="g_upper" type="capsule" fromto="0 0 0 0.15 0 0" size="0.02" density="600" contype="0" conaffinity="0"/>
+        <body name="fore" pos="0.15 0 0">
+          <joint name="elbow" type="hinge" axis="0 1 0" damping="0.3" armature="0.01"/>
+          <joint name="roll" type="hinge" axis="1 0 0" damping="0.1" armature="0.005"/>
+          <geom name="g_fore" type="capsule" fromto="0 0 0 0.1 0 0" size="0.015" density="600" contype="0" conaffinity="0"/>
+          <body name="tcp" pos="0.1 0 0">
+            <geom name="g_palm" type="box" size="0.01 0.03 0.01" density="600" contype="0" conaffinity="0"/>
+            <body name="finger_r" pos="0.02 -0.02 0">
+              <joint name="r_slide" type="slide" axis="0 1 0" damping="2" armature="0.001" limited="true" range="-0.005 0.02"/>
+              <geom name="g_fr" type="box" size="0.015 0.003 0.008" density="600" contype="0" conaffinity="0"/>
+            </body>
+            <body name="finger_l" pos="0.02 0.02 0">
+              <joint name="l_slide" type="slide" axis="0 -1 0" damping="2" armature="0.001"/>
+              <geom name="g_fl" type="box" size="0.015 0.003 0.008" density="600" contype="0" conaffinity="0"/>
+            </body>
+          </body>
+        </body>
+      </body>
+    </body>
+    <body name="brick" pos="-0.3 0.2 0.6">
+      <joint name="brick_free" type="free"/>
+      <geom name="brick" type="box" size="0.03 0.02 0.01" density="900" condim="3"/>
+    </body>
+  </worldbody>
+  <equality>
+    <weld name="mocap_weld" body1="mocap" body2="tcp" solimp="0.9 0.95 0.001" solref="0.02 1"/>
+    <weld name="hook_weld" body1="hook" body2="brick"/>
+    <joint name="coupling" joint1="r_slide" joint2="l_slide" polycoef="0 1 0 0 0" solref="-50000 -100"/>
+  </equality>
+  <actuator>
+    <position name="a_grip" joint="r_slide" kp="200" ctrllimited="true" ctrlrange="0 0.02"/>
+  </actuator>
+</mujoco>
+"""
