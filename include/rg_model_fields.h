@@ -135,8 +135,10 @@ RG_F(geom_solmix, ngeom)
 RG_F(geom_solref, ngeom * 2)
 RG_F(geom_solimp, ngeom * 5)
 RG_I(site_bodyid, nsite)
+RG_I(site_type, nsite)       /* mjtGeom of the site's volume (touch sensors test contact points against it) */
 RG_F(site_pos, nsite * 3)
 RG_F(site_quat, nsite * 4)
+RG_F(site_size, nsite * 3)
 RG_I(mesh_vertadr, nmesh)
 RG_I(mesh_vertnum, nmesh)
 RG_I(mesh_faceadr, nmesh)
@@ -183,7 +185,7 @@ RG_F(eq_data, neq * 7)
 RG_F(eq_solref, neq * 2)
 RG_F(eq_solimp, neq * 5)
 
-/* ---- sensors (touch/jointpos/force/torque; ids only) ---- */
+/* ---- sensors (mjtSensor: 0 touch, 8 jointpos are computed; 4 force / 5 torque are described only and read 0) ---- */
 RG_I(sensor_type, nsensor)
 RG_I(sensor_objid, nsensor)
 RG_I(sensor_adr, nsensor)

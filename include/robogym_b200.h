@@ -68,7 +68,10 @@ enum rg_field {
                               robogym moves the UR16e tool centre point by a mocap body welded to it
                               (robogym/robot/control/tcp/mocap_solver.py:41-46, robogym/assets/xmls/robot/ur16e/tcp_mocap.xml:2) */
   RG_FIELD_MOCAP_QUAT = 20,/* [nenv][nmocap*4]    in     (optional): data.mocap_quat */
-  RG_NFIELDS = 21
+  RG_FIELD_SENSORDATA = 21,/* [nenv][nsensordata] out    (optional): data.sensordata after the launch's last forward pass -- joint positions and
+                              touch sensors (robogym/assets/xmls/robot/shadowhand/assets.xml:135-142); force / torque sensors
+                              (robogym/assets/xmls/robot/ur16e/base.xml:48-49) are described in the model but read 0 */
+  RG_NFIELDS = 22
 };
 #define RG_MAX_CONTACTS 32   /* DEFAULT contact capacity of a batch (rg_batch_create); rg_batch_create_ex picks another */
 #define RG_MAX_PARAM_OVERRIDES 16

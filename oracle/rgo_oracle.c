@@ -893,6 +893,68 @@ static void rgo_euler(const rgo_model* m, rgo_data* d) {
 /* ------------------------------------------------------------------ drivers */
 static int bad(double x) { return !(x == x) || fabs(x) > 1e10; }
 
+/* ------------------------------------------------------------------ S14 sensors */
+/* smallest non-negative root of a t^2 + 2 b t + c = 0 (both roots in xx), or -1 */
+static double ray_quad(double a, double b, double c, double xx[2]) {
+  double det = b * b - a * c;
+  if (det < MINVAL || a < MINVAL) { xx[0] = xx[1] = -1; return -1; }
+  det = sqrt(det);
+  xx[0] = (-b - det) / a; xx[1] = (-b + det) / a;
+  if (xx[0] >= 0) return xx[0];
+  if (xx[1] >= 0) return xx[1];
+  return -1;
+}
+/* distance along the ray pnt + t vec to a sphere / capsule volume at (pos, mat), -1 = miss (a point inside always hits) */
+static double ray_site(const double* pos, const double* mat, const double* size, const double* pnt, const double* vec, int type) {
+  double dif[3], lp[3], lv[3], xx[2], x = -1;
+  sub3(dif, pnt, pos);
+  mulmatT3(lp, mat, dif);
+  mulmatT3(lv, mat, vec);
+  if (type == GEOM_SPHERE) return ray_quad(dot3(lv, lv), dot3(lv, lp), dot3(lp, lp) - size[0] * size[0], xx);
+  if (type != GEOM_CAPSULE) return -1;
+  double sol = ray_quad(lv[0] * lv[0] + lv[1] * lv[1], lv[0] * lp[0] + lv[1] * lp[1], lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0], xx);
+  if (sol >= 0 && fabs(lp[2] + sol * lv[2]) <= size[1]) x = sol;
+  for (int cap = 0; cap < 2; cap++) {
+    double zc = cap == 0 ? size[1] : -size[1], q[3] = {lp[0], lp[1], lp[2] - zc};
+    ray_quad(dot3(lv, lv), dot3(lv, q), dot3(q, q) - size[0] * size[0], xx);
+    for (int i = 0; i < 2; i++) {
+      if (xx[i] < 0) continue;
+      double z = lp[2] + xx[i] * lv[2];
+      if ((cap == 0 ? z >= size[1] : z <= -size[1]) && (x < 0 || xx[i] < x)) x = xx[i];
+    }
+  }
+  return x;
+}
+/* data.sensordata after mj_forward: joint positions and touch sensors (the 5 fingertip pads of the hand,
+   robogym/assets/xmls/robot/shadowhand/assets.xml:135-142: normal forces of the contacts on the site's body whose point --
+   or the ray from it along the contact normal -- lies in the site's volume).  Force / torque sensors (base.xml:48-49) read 0. */
+static void rgo_sensors(const rgo_model* m, rgo_data* d) {
+  for (int i = 0; i < m->nsensor; i++) {
+    int adr = m->sensor_adr[i], obj = m->sensor_objid[i];
+    for (int k = 0; k < m->sensor_dim[i]; k++) d->sensordata[adr + k] = 0;
+    if (m->sensor_type[i] == 8) d->sensordata[adr] = d->qpos[m->jnt_qposadr[obj]];
+    if (m->sensor_type[i] != 0) continue;
+    int body = m->site_bodyid[obj];
+    for (int c = 0; c < d->ncon; c++) {
+      const double* con = d->contact + RGO_CON_STRIDE * c;
+      int b1 = m->geom_bodyid[(int)con[20]], b2 = m->geom_bodyid[(int)con[21]];
+      if (body != b1 && body != b2) continue;
+      double f = 0;
+      int rows = 0;
+      for (int r = 0; r < d->nefc; r++) {
+        if (d->efc_id[r] != c) continue;
+        if (d->efc_type[r] == ROW_CONTACT) { f += d->efc_force[r]; rows++; }
+        else if (d->efc_type[r] == ROW_CONTACT_ELL) { f = d->efc_force[r]; rows++; }
+      }
+      if (!rows || f <= 0) continue;
+      double ray[3] = {con[4], con[5], con[6]};
+      if (body == b2) scl3(ray, ray, -1);
+      if (ray_site(d->site_xpos + 3 * obj, d->site_xmat + 9 * obj, m->site_size + 3 * obj, con + 1, ray, m->site_type[obj]) >= 0)
+        d->sensordata[adr] += f;
+    }
+  }
+}
+
 void rgo_forward(const rgo_model* m, rgo_data* d) {
   rgo_kinematics(m, d);
   rgo_inertia(m, d);
@@ -906,6 +968,7 @@ void rgo_forward(const rgo_model* m, rgo_data* d) {
   rgo_actuation(m, d);
   rgo_smooth(m, d);
   rgo_constraint(m, d);
+  rgo_sensors(m, d);
 }
 
 void rgo_step(const rgo_model* m, rgo_data* d) {

@@ -542,6 +542,7 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   io.cost = b->balance ? b->d_cost : nullptr;
   io.sep = b->d_sep;
   io.body_xvel = (float*)b->ptr[RG_FIELD_BODY_XVEL];
+  io.sensordata = (float*)b->ptr[RG_FIELD_SENSORDATA];
   io.mocap_pos = (const float*)b->ptr[RG_FIELD_MOCAP_POS]; io.mocap_quat = (const float*)b->ptr[RG_FIELD_MOCAP_QUAT];
   io.contact = (float*)b->ptr[RG_FIELD_CONTACT]; io.ncon = (int*)b->ptr[RG_FIELD_NCON]; io.warn = (int*)b->ptr[RG_FIELD_WARN]; io.dbg = (float*)b->ptr[RG_FIELD_DBG];
   return 0;

@@ -18,6 +18,7 @@ struct RgBatchIO {
   const float* mocap_quat;  /* [nenv][nmocap*4] data.mocap_quat or nullptr */
   /* derived outputs (any may be nullptr) */
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
+  float* sensordata;        /* [nenv][nsensordata] data.sensordata after the last forward pass (joint positions, touch; force / torque read 0) */
   float* body_xvel;         /* [nenv][nbody][6]: angular then linear velocity of the body frame, world axes (data.get_body_xvelr / get_body_xvelp) */
   float* contact;           /* [nenv][contact capacity][4] = geom1, geom2, dist, dim */
   int* ncon; int* warn;
@@ -121,6 +122,71 @@ RG_DEV_NOINLINE void rg_forward(const RgCtx c) {
   RG_CTA_SYNC(); rg_solve(c); RG_PROF(c, 7)
 }
 
+/* ---- S14 sensors (evaluated once per launch, after the last forward pass, when RG_FIELD_SENSORDATA is bound) */
+/* smallest non-negative root of a t^2 + 2 b t + c = 0 (both roots in xx), or -1 */
+RG_DEV float rg_ray_quad(float a, float b, float c, float* xx) {
+  float det = b * b - a * c;
+  if (det < 1e-15f || a < 1e-15f) { xx[0] = xx[1] = -1.0f; return -1.0f; }
+  det = sqrtf(det);
+  xx[0] = (-b - det) / a; xx[1] = (-b + det) / a;
+  if (xx[0] >= 0.0f) return xx[0];
+  if (xx[1] >= 0.0f) return xx[1];
+  return -1.0f;
+}
+/* distance along the ray pnt + t vec to a sphere / capsule site volume, -1 = miss (a point inside always hits) */
+RG_DEV_NOINLINE float rg_ray_site(const float* pos, const float* quat, const float* size, const float* pnt, const float* vec, int type) {
+  float mat[9], dif[3], lp[3], lv[3], xx[2], x = -1.0f;
+  rg_quat2mat(mat, quat);
+  rg_sub3(dif, pnt, pos);
+  rg_mulmatT3(lp, mat, dif);
+  rg_mulmatT3(lv, mat, vec);
+  if (type == RG_GEOM_SPHERE) return rg_ray_quad(rg_dot3(lv, lv), rg_dot3(lv, lp), rg_dot3(lp, lp) - size[0] * size[0], xx);
+  if (type != RG_GEOM_CAPSULE) return -1.0f;
+  const float sol = rg_ray_quad(lv[0] * lv[0] + lv[1] * lv[1], lv[0] * lp[0] + lv[1] * lp[1], lp[0] * lp[0] + lp[1] * lp[1] - size[0] * size[0], xx);
+  if (sol >= 0.0f && fabsf(lp[2] + sol * lv[2]) <= size[1]) x = sol;
+  for (int cap = 0; cap < 2; cap++) {
+    const float zc = cap == 0 ? size[1] : -size[1];
+    const float q[3] = {lp[0], lp[1], lp[2] - zc};
+    rg_ray_quad(rg_dot3(lv, lv), rg_dot3(lv, q), rg_dot3(q, q) - size[0] * size[0], xx);
+    for (int i = 0; i < 2; i++) {
+      if (xx[i] < 0.0f) continue;
+      const float z = lp[2] + xx[i] * lv[2];
+      if ((cap == 0 ? z >= size[1] : z <= -size[1]) && (x < 0.0f || xx[i] < x)) x = xx[i];
+    }
+  }
+  return x;
+}
+/* one lane per sensor: joint position, or the normal forces of the contacts on the site's body whose point (or the ray from it
+   along the contact normal) lies in the site's volume (mjSENS_TOUCH; robogym/assets/xmls/robot/shadowhand/assets.xml:135-142) */
+RG_DEV_NOINLINE void rg_sensors(const RgCtx c, float* out) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
+  const int ncon = RG_SI(c, RG_S_NCON);
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int i = lane; i < m.nsensor; i += 32) {
+    const int adr = m.sensor_adr[i], obj = m.sensor_objid[i], type = m.sensor_type[i];
+    for (int k = 0; k < m.sensor_dim[i]; k++) out[adr + k] = 0.0f;
+    if (type == 8) { const int j = obj, qa = m.jnt_qposadr[j]; out[adr] = s[L.qpos + qa]; }
+    if (type != 0) continue;
+    const int body = m.site_bodyid[obj];
+    float sq[4], total = 0.0f;
+    rg_quat_mul(sq, s + L.xquat + 4 * body, m.site_quat + 4 * obj);
+    rg_quat_norm(sq);
+    RG_NOUNROLL for (int k = 0; k < ncon; k++) {
+      const float* r = s + L.con + RG_CON_STRIDE * k;
+      const int b1 = (int)r[18], b2 = (int)r[19];
+      if ((body != b1 && body != b2) || (int)s[L.cprm + RG_CPRM * k + 1] == 0) continue;
+      const float f = s[L.cF + 6 * k];
+      if (!(f > 0.0f)) continue;
+      float ray[3] = {r[4], r[5], r[6]};
+      if (body == b2) rg_scl3(ray, ray, -1.0f);
+      if (rg_ray_site(s + L.sxpos + 3 * obj, sq, m.site_size + 3 * obj, r + 1, ray, m.site_type[obj]) >= 0.0f) total += f;
+    }
+    out[adr] = total;
+  }
+  RG_PHASE_END
+}
+
 /* `store` == 0: a padding iteration that keeps this warp in step with its CTA (same barriers), results discarded */
 RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, int soff, const RgBatchIO& io, int env, int nsub, int final_forward, int store) {
   RG_LANE_DECL
@@ -183,6 +249,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   for (int f = 0; f < final_forward; f++) rg_forward(c);   /* robogym steps, then observes: sim.forward() runs again in RobotEnv._observe_sync */
   /* ---- store */
   if (!store) return;
+  if (io.sensordata && m.nsensor > 0) rg_sensors(c, io.sensordata + (size_t)env * m.nsensordata);
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
     if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] += m.origin[a];

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("RG_LIB", os.path.join(_HERE, "librobogym_b200.so"))  
 
 # enum rg_field (include/robogym_b200.h)
 (QPOS, QVEL, CTRL, PID, WARMSTART, TIME, XFRC, TIMESTEP, SITE_XPOS, BODY_XPOS, BODY_XQUAT, GEOM_XPOS,
- ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG, BODY_XVEL, MOCAP_POS, MOCAP_QUAT) = range(21)
+ ACT_FORCE, QACC, CONTACT, NCON, WARN, DBG, BODY_XVEL, MOCAP_POS, MOCAP_QUAT, SENSORDATA) = range(22)
 MAX_CONTACTS = 32
 CON_STRIDE = 24
 
@@ -180,7 +180,7 @@ class BatchedSim:
         shapes = dict(site_xpos=(SITE_XPOS, (n, m["nsite"], 3), f32), body_xpos=(BODY_XPOS, (n, m["nbody"], 3), f32),
                       body_xquat=(BODY_XQUAT, (n, m["nbody"], 4), f32), geom_xpos=(GEOM_XPOS, (n, m["ngeom"], 3), f32),
                       body_xvel=(BODY_XVEL, (n, m["nbody"], 6), f32), act_force=(ACT_FORCE, (n, m["nu"]), f32), qacc=(QACC, (n, m["nv"]), f32),
-                      contact=(CONTACT, (n, self.contact_capacity, 4), f32), ncon=(NCON, (n,), i32), warn=(WARN, (n,), i32))
+                      contact=(CONTACT, (n, self.contact_capacity, 4), f32), sensordata=(SENSORDATA, (n, m["nsensordata"]), f32), ncon=(NCON, (n,), i32), warn=(WARN, (n,), i32))
         for name in outputs:
             fid, shape, kw = shapes[name]
             t = torch.zeros(*shape, **kw)

@@ -731,13 +731,19 @@ def _pass_sites(c):
     c.site_bodyid = np.array([s["_body"] for s in c.S], int).reshape(-1)
     c.site_pos = np.zeros((c.nsite, 3))
     c.site_quat = np.zeros((c.nsite, 4))
+    c.site_type = np.zeros(c.nsite, int)
+    c.site_size = np.zeros((c.nsite, 3))
     for i, sa in enumerate(c.S):
+        c.site_type[i] = GEOM_TYPES[sa.get("type", "sphere")]
+        sz = _vec(sa.get("size", "0.005"))
+        c.site_size[i, :len(sz)] = sz[:3]
         pos = _vec(sa.get("pos", "0 0 0"), 3)
         quat = _frame_quat(sa, c.angle_scale, c.eulerseq)
         if "fromto" in sa:
             ft = _vec(sa["fromto"], 6)
             pos = 0.5 * (ft[:3] + ft[3:])
             quat = z2quat(ft[:3] - ft[3:])
+            c.site_size[i, 1] = 0.5 * np.linalg.norm(ft[:3] - ft[3:])
         c.site_pos[i] = pos
         c.site_quat[i] = quat
 
@@ -1049,7 +1055,7 @@ def _pass_mesh_tables_and_model(c):
         geom_priority=c.geom_priority, geom_size=c.geom_size, geom_pos=c.geom_pos, geom_quat=c.geom_quat,
         geom_rbound=c.geom_rbound, geom_aabb=c.geom_aabb, geom_friction=c.geom_friction, geom_margin=c.geom_margin,
         geom_gap=c.geom_gap, geom_solmix=c.geom_solmix, geom_solref=c.geom_solref, geom_solimp=c.geom_solimp,
-        site_bodyid=c.site_bodyid, site_pos=c.site_pos, site_quat=c.site_quat,
+        site_bodyid=c.site_bodyid, site_type=c.site_type, site_pos=c.site_pos, site_quat=c.site_quat, site_size=c.site_size,
         mesh_vertadr=mesh_vertadr, mesh_vertnum=mesh_vertnum, mesh_faceadr=mesh_faceadr,
         mesh_facenum=mesh_facenum, mesh_vert=mesh_vert, mesh_adjadr=adjadr, mesh_adj=mesh_adj,
         mesh_face=mesh_face, pair_geom1=np.array(c.pair1, int), pair_geom2=np.array(c.pair2, int),

@@ -49,7 +49,7 @@ class CudaEngine:
 
         self.cm = cm
         self.model = engine.DeviceModel(cm.blob(), 0)
-        self.sim = engine.BatchedSim(self.model, 1, 1, outputs=("site_xpos", "body_xpos", "body_xquat", "body_xvel", "geom_xpos", "act_force", "qacc", "contact", "ncon", "warn"))
+        self.sim = engine.BatchedSim(self.model, 1, 1, outputs=("site_xpos", "body_xpos", "body_xquat", "body_xvel", "geom_xpos", "act_force", "qacc", "contact", "ncon", "warn", "sensordata"))
         self.sim.enable_xfrc()
 
     def push_model(self, name, arr):
@@ -59,7 +59,9 @@ class CudaEngine:
         t = self.sim.torch
         f = lambda a: t.as_tensor(np.asarray(a, dtype=np.float32)).to(self.sim.device).reshape(1, -1)
         self.sim.qpos.copy_(f(qpos)); self.sim.qvel.copy_(f(qvel)); self.sim.ctrl.copy_(f(ctrl))
-        self.sim.pid.copy_(f(pid)); self.sim.qacc_warmstart.copy_(f(warm))
+        if np.size(pid) == self.sim.pid.numel():      # a model without room for the PID state in userdata does not use the PID path
+            self.sim.pid.copy_(f(pid))
+        self.sim.qacc_warmstart.copy_(f(warm))
         self.sim.xfrc_applied.copy_(f(xfrc).reshape(self.sim.xfrc_applied.shape))
 
     def push_mocap(self, pos, quat):
@@ -78,7 +80,7 @@ class CudaEngine:
         con = g(s.contact)[:ncon]
         return dict(qpos=g(s.qpos), qvel=g(s.qvel), pid=g(s.pid), warm=g(s.qacc_warmstart), site_xpos=g(s.site_xpos),
                     body_xpos=g(s.body_xpos), body_xquat=g(s.body_xquat), geom_xpos=g(s.geom_xpos), act_force=g(s.act_force),
-                    qacc=g(s.qacc), ncon=ncon, contact=con, warn=int(s.warn[0].item()), body_xvel=g(s.body_xvel))
+                    qacc=g(s.qacc), ncon=ncon, contact=con, warn=int(s.warn[0].item()), body_xvel=g(s.body_xvel), sensordata=g(s.sensordata))
 
 
 def _default_factory(cm):
@@ -110,7 +112,7 @@ class _Opt:
 
 _SHAPES = dict(body_pos=3, body_quat=4, body_ipos=3, body_iquat=4, body_inertia=3, body_invweight0=2, jnt_pos=3, jnt_axis=3, jnt_range=2,
                jnt_solref=2, jnt_solimp=5, geom_size=3, geom_pos=3, geom_quat=4, geom_friction=3, geom_solref=2, geom_solimp=5,
-               site_pos=3, site_quat=4, tendon_range=2, actuator_gainprm=10, actuator_biasprm=10, actuator_ctrlrange=2,
+               site_pos=3, site_quat=4, site_size=3, tendon_range=2, actuator_gainprm=10, actuator_biasprm=10, actuator_ctrlrange=2,
                actuator_forcerange=2, actuator_gear=6, eq_data=7, eq_solref=2, eq_solimp=5, dof_solref=2, dof_solimp=5)
 _OBJ = dict(body="body", joint="joint", geom="geom", site="site", tendon="tendon", actuator="actuator", mesh="mesh", sensor="sensor")
 
@@ -292,13 +294,16 @@ class MjSim:
         d, m = self._rg_data, self._rg_model._m
         out = self._rg_engine.pull()
         d.qpos[:] = out["qpos"]; d.qvel[:] = out["qvel"]; d.qacc[:] = out["qacc"]; d.qacc_warmstart[:] = out["warm"]
-        d.userdata[:3 * m["nu"]] = out["pid"]
+        if len(d.userdata) >= 3 * m["nu"]:
+            d.userdata[:3 * m["nu"]] = out["pid"]
         d.site_xpos[:] = out["site_xpos"].reshape(-1, 3); d.body_xpos[:] = out["body_xpos"].reshape(-1, 3)
         d.body_xquat[:] = out["body_xquat"].reshape(-1, 4); d.geom_xpos[:] = out["geom_xpos"].reshape(-1, 3)
         d.actuator_force[:] = out["act_force"]
         if "body_xvel" in out:     # [nbody][6]: angular, then linear velocity of the body frame in world axes
             xv = np.asarray(out["body_xvel"]).reshape(-1, 6)
             d.body_xvelr[:] = xv[:, :3]; d.body_xvelp[:] = xv[:, 3:]
+        if "sensordata" in out:
+            d.sensordata[:] = out["sensordata"]
         d.ncon = out["ncon"]
         while len(d.contact) < d.ncon:
             d.contact.append(_Contact())

@@ -25,6 +25,7 @@ def lib():
         L.rge_name2id.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.rge_model_field.restype = ctypes.c_void_p
         L.rge_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+        L.rge_set_sensordata.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.rge_set_mocap.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.rge_step.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 18 + [ctypes.c_int, ctypes.c_int]
         _lib = L
@@ -64,6 +65,7 @@ class EmuBatch:
         self.ncon = np.zeros(nenv, np.int32)
         self.warn = np.zeros(nenv, np.int32)
         self.dbg = np.zeros((nenv, lib().rge_dbg_size(self.h)), f)
+        self.sensordata = np.zeros((nenv, dims.get("nsensordata", 0)), f)
         self.mocap_pos = np.zeros((nenv, dims.get("nmocap", 0), 3), f) if dims.get("nmocap", 0) else None
         self.mocap_quat = np.zeros((nenv, dims.get("nmocap", 0), 4), f) if dims.get("nmocap", 0) else None
 
@@ -75,6 +77,7 @@ class EmuBatch:
 
     def step(self, nsub, final_forward=1):
         lib().rge_set_mocap(self.h, _p(self.mocap_pos), _p(self.mocap_quat))
+        lib().rge_set_sensordata(self.h, _p(self.sensordata) if self.sensordata.size else None)
         lib().rge_step(self.h, self.nenv, _p(self.qpos), _p(self.qvel), _p(self.ctrl), _p(self.pid), _p(self.warm), _p(self.time),
                        _p(self.xfrc), _p(self.timestep), _p(self.site_xpos), _p(self.body_xpos), _p(self.body_xquat),
                        _p(self.geom_xpos), _p(self.act_force), _p(self.qacc), _p(self.contact), _p(self.ncon), _p(self.warn),

@@ -12,7 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; std::vector<int> sep; const float* mocap_pos = nullptr; const float* mocap_quat = nullptr; };
+struct RgeHandle { RgHostModel hm; RgLayout L; std::vector<float> scratch; std::vector<int> sep; const float* mocap_pos = nullptr; const float* mocap_quat = nullptr; float* sensordata = nullptr; };
 
 extern "C" {
 
@@ -39,6 +39,7 @@ void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_clim
 #endif
 /* data.mocap_pos / mocap_quat rows ([nenv][nmocap*3], [nenv][nmocap*4]) used by the following rge_step calls (or null) */
 void rge_set_mocap(void* hv, const float* pos, const float* quat) { ((RgeHandle*)hv)->mocap_pos = pos; ((RgeHandle*)hv)->mocap_quat = quat; }
+void rge_set_sensordata(void* hv, float* out) { ((RgeHandle*)hv)->sensordata = out; }   /* [nenv][nsensordata] or null */
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
 int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view, ((RgeHandle*)hv)->L.ncon); }
 int rge_scratch_floats(void* hv) { return ((RgeHandle*)hv)->L.total; }
@@ -71,7 +72,7 @@ void rge_step(void* hv, int nenv, float* qpos, float* qvel, float* ctrl, float* 
   RgBatchIO io;
   io.nenv = nenv; io.qpos = qpos; io.qvel = qvel; io.ctrl = ctrl; io.pid = pid; io.warm = warm; io.time = time; io.xfrc = xfrc;
   io.timestep = timestep; io.site_xpos = site_xpos; io.body_xpos = body_xpos; io.body_xquat = body_xquat; io.geom_xpos = geom_xpos;
-  io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg; io.cost = nullptr; io.body_xvel = nullptr; io.mocap_pos = h->mocap_pos; io.mocap_quat = h->mocap_quat;
+  io.act_force = act_force; io.qacc = qacc; io.contact = contact; io.ncon = ncon; io.warn = warn; io.dbg = dbg; io.cost = nullptr; io.body_xvel = nullptr; io.mocap_pos = h->mocap_pos; io.mocap_quat = h->mocap_quat; io.sensordata = h->sensordata;
   if (h->sep.size() != (size_t)nenv * RG_NSEP) h->sep.assign((size_t)nenv * RG_NSEP, 0xfff);   /* like the engine's per-batch buffer */
   io.sep = h->sep.data();
   for (int env = 0; env < nenv; env++) rg_env_step(&h->hm.view, h->L, h->scratch.data(), 0, io, env, nsub, final_forward, 1);

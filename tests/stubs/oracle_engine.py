@@ -39,4 +39,5 @@ class OracleEngine:
         xvel = np.concatenate([cv[:, :3], cv[:, 3:] + np.cross(cv[:, :3], xp)], axis=1)
         return dict(qpos=d.qpos.copy(), qvel=d.qvel.copy(), pid=d.userdata[:3 * self.nu].copy(), warm=d.qacc_warmstart.copy(),
                     site_xpos=d.site_xpos.copy(), body_xpos=d.xpos.copy(), body_xquat=xq, geom_xpos=d.geom_xpos.copy(),
-                    act_force=d.actuator_force.copy(), qacc=d.qacc.copy(), ncon=ncon, contact=contact, warn=int(d.warning[0]), body_xvel=xvel)
+                    act_force=d.actuator_force.copy(), qacc=d.qacc.copy(), ncon=ncon, contact=contact, warn=int(d.warning[0]), body_xvel=xvel,
+                    sensordata=d.sensordata[:self.cm.m["nsensordata"]].copy())
