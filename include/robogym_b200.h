@@ -20,6 +20,7 @@
  *                         (robogym/mujoco/simulation_interface.py:176-189; robogym/robot_env.py:837).
  *   rg_forward         <- SimulationInterface.forward() (simulation_interface.py:203-207).
  *   rg_reset           <- SimulationInterface.reset() = mj_resetData (simulation_interface.py:191-195).
+ *   rg_set_const       <- SimulationInterface.set_constants() = mj_setConst (simulation_interface.py:197-201).
  *
  * Conventions: every function returns 0 on success or a negative code and sets a thread-local
  * message readable with rg_last_error(); no exceptions or callbacks cross the ABI.  All device
@@ -132,6 +133,14 @@ int rg_forward(rg_batch* b, void* stream);
  * nothing (the launch covers only the selected environments).  What a Python loop over MjSim objects does when it
  * calls sim.forward()/sim.step() on some environments only (goal switches, resets). */
 int rg_step_subset(rg_batch* b, const uint8_t* mask_device, int nsub, int final_forward, void* stream);
+/* mj_setConst per environment (SimulationInterface.set_constants, robogym/mujoco/simulation_interface.py:197-201, which the
+ * reference calls after its randomisers edited masses, inertias, armatures ...): recomputes, from each selected environment's
+ * own parameter view at qpos0, the constants MuJoCo derives from the model -- dof_invweight0, body_invweight0,
+ * tendon_invweight0, tendon_length0, body_subtreemass, opt_meaninertia -- and writes them into that environment's row of the
+ * arrays bound with rg_batch_bind_param under those names (constants that are not bound per environment are not written:
+ * the shared model is immutable while launches may be in flight; at least one must be bound).  One launch, asynchronous on
+ * `stream`; mask as in rg_step_subset, NULL = every environment. */
+int rg_set_const(rg_batch* b, const uint8_t* mask_device, void* stream);
 /* mj_resetData for the environments whose mask byte is non-zero (mask == NULL: all) */
 int rg_reset(rg_batch* b, const uint8_t* mask_device, void* stream);
 

@@ -45,6 +45,8 @@ struct RgKernelArgs {
   const int* order;   /* [nenv] slot -> environment (work-sorted, see rg_order_kernel) or nullptr = identity */
   const int* nslots;  /* device: number of slots of a subset launch (rg_step_subset) or nullptr = every environment */
   int* counter;       /* device: next unassigned slot of this launch (zeroed before the launch) */
+  int setconst[6];    /* nsub < 0 = an rg_set_const launch: override slots of dof_invweight0, body_invweight0, tendon_invweight0,
+                         tendon_length0, body_subtreemass, opt_meaninertia (-1 = not bound per environment, not written) */
 };
 
 __device__ __forceinline__ uint32_t rg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,6 +162,13 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       __syncwarp();
       if (lane < args.nover) *(int*)((char*)wm + args.over_off[lane]) = (int)((unsigned char*)(wover + args.over_dst[lane]) - rg_smem_raw);
       __syncwarp();
+    }
+    if (args.nsub < 0) {
+      RgSetConstOut o;
+      float** op = (float**)&o;
+      for (int k = 0; k < 6; k++) op[k] = args.setconst[k] >= 0 ? (float*)args.over_ptr[args.setconst[k]] + (size_t)e * args.over_cnt[args.setconst[k]] : nullptr;
+      rg_env_setconst((int)((unsigned char*)wm - rg_smem_raw), args.L, s, (int)(s - (float*)rg_smem_raw), o);
+      continue;
     }
     rg_env_step((int)((unsigned char*)wm - rg_smem_raw), args.L, s, (int)(s - (float*)rg_smem_raw), args.io, e, args.nsub, args.final_forward, 1);
   }
@@ -548,9 +557,21 @@ static int rg_fill_io(const rg_batch* b, RgBatchIO& io) {
   return 0;
 }
 
-static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_forward, void* stream) {
+static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_forward, void* stream, bool setconst = false) {
   if (!b || nsub < 0 || final_forward < 0 || final_forward > 4) return rg_fail(-1, "rg_step: bad argument");
   RgKernelArgs args;
+  if (setconst) {
+    /* mj_setConst writes into the per-environment rows the caller bound with rg_batch_bind_param: only bound constants exist
+       per environment (the shared model is immutable while steps may be in flight) */
+    static const char* names[6] = {"dof_invweight0", "body_invweight0", "tendon_invweight0", "tendon_length0", "body_subtreemass", "opt_meaninertia"};
+    int any = 0;
+    for (int k = 0; k < 6; k++) {
+      args.setconst[k] = -1;
+      for (int i = 0; i < b->nover; i++) if (b->over_name[i] == names[k]) { args.setconst[k] = i; any = 1; }
+    }
+    if (!any) return rg_fail(-3, "rg_set_const: bind at least one of dof_invweight0 / body_invweight0 / tendon_invweight0 / tendon_length0 / body_subtreemass / opt_meaninertia per environment first (rg_batch_bind_param)");
+    nsub = -1;
+  }
   const int rc = rg_fill_io(b, args.io);
   if (rc) return rc;
   args.m = b->model->dev;
@@ -574,7 +595,7 @@ static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_
   RG_CUDA(cudaMemsetAsync(b->d_counter, 0, sizeof(int), (cudaStream_t)stream));
   rg_step_kernel<<<b->ctas, RG_MAX_WARPS * 32 < b->warps * 32 ? RG_MAX_WARPS * 32 : b->warps * 32, b->smem, (cudaStream_t)stream>>>(args);
   RG_CUDA(cudaGetLastError());
-  if (!mask && b->balance && nsub > 0) {
+  if (!mask && b->balance && nsub > 0) {   /* (not after rg_set_const: it leaves no cost) */
     rg_order_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(b->d_cost, b->d_order, b->nenv);
     RG_CUDA(cudaGetLastError());
   }
@@ -586,6 +607,7 @@ int rg_step_subset(rg_batch* b, const uint8_t* mask, int nsub, int final_forward
   return rg_launch_step(b, mask, nsub, final_forward, stream);
 }
 int rg_forward(rg_batch* b, void* stream) { return rg_step(b, 0, 1, stream); }
+int rg_set_const(rg_batch* b, const uint8_t* mask, void* stream) { return rg_launch_step(b, mask, 0, 0, stream, true); }
 
 int rg_reset(rg_batch* b, const uint8_t* mask, void* stream) {
   if (!b) return rg_fail(-1, "rg_reset: bad argument");

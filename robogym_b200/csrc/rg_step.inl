@@ -322,3 +322,126 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   }
   RG_PHASE_END
 }
+
+/* ---- mj_setConst for one environment (SimulationInterface.set_constants, robogym/mujoco/simulation_interface.py:197-201, after
+ * the randomisers edited masses / inertias / armatures, robogym/wrappers/randomizations.py:72-306): the constants MuJoCo derives
+ * from the model at qpos0, recomputed from THIS environment's parameter view and written to its rows of the per-environment
+ * arrays (each pointer may be null).  A^-1 = M(qpos0)^-1 by the tree-sparse factorisation:
+ *   dof_invweight0[i]   = A^-1(i, i), averaged over the 3 rotations / 3 translations of a ball or free joint
+ *   body_invweight0[b]  = tr(Jp A^-1 Jp') / 3, tr(Jr A^-1 Jr') / 3 with the Jacobians at the body's centre of mass (0 for bodies
+ *                         welded to the world)
+ *   tendon_invweight0[t]= J_t A^-1 J_t',   tendon_length0[t] = length at qpos0
+ *   body_subtreemass[b] = mass of b and its descendants,   opt_meaninertia = mean diag M(qpos0) */
+struct RgSetConstOut { float* dof_invweight0; float* body_invweight0; float* tendon_invweight0; float* tendon_length0; float* body_subtreemass; float* opt_meaninertia; };
+
+RG_DEV_NOINLINE void rg_env_setconst(RgMRef mr, const RgLayout& L_in, float* s_in, int soff, const RgSetConstOut& o) {
+  RG_LANE_DECL
+  const RG_MODEL_T& m = RG_MDEREF(mr);
+#ifdef RG_EMU
+  const RgCtx c = {mr, &L_in, s_in, nullptr, m.opt_timestep[0]};
+#else
+  const RgCtx c = {mr, soff, nullptr, m.opt_timestep[0]};
+#endif
+  const RgLayout& L = RG_CL(c);
+  float* s = RG_SCRATCH(c);
+  const int nv = m.nv;
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = m.qpos0[i];
+  RG_NOUNROLL for (int i = lane; i < nv; i += 32) s[L.qvel + i] = 0.0f;
+  if (lane < 8 + RG_NPROF) RG_SI(c, lane) = 0;
+  RG_PHASE_END
+  RG_PHASE_BEGIN
+  RG_NOUNROLL for (int j = lane; j < m.njnt; j += 32)
+    if (m.jnt_type[j] == RG_JNT_FREE) for (int a = 0; a < 3; a++) s[L.qpos + m.jnt_qposadr[j] + a] -= m.origin[a];
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
+    const int k = m.body_mocapid[b];
+    if (k < 0) continue;
+    for (int a = 0; a < 3; a++) s[L.mocap + 7 * k + a] = m.body_pos[3 * b + a];
+    for (int a = 0; a < 4; a++) s[L.mocap + 7 * k + 3 + a] = m.body_quat[4 * b + a];
+  }
+  RG_PHASE_END
+  rg_kinematics(c);
+  rg_massmatrix(c);
+  if (m.ntendon > 0) rg_tendon(c);
+  const int F = L.H, invD = L.Mv, x = L.search, rhs = L.qfc, diag = L.Ma;
+  rg_sparse_factor(c, F, invD, nullptr, 0.0f, m.dof_lvl + 0);
+  /* diagonal of the inverse, one unit vector at a time */
+  for (int i = 0; i < nv; i++) {
+    RG_PHASE_BEGIN
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) s[x + d] = d == i ? 1.0f : 0.0f;
+    RG_PHASE_END
+    rg_sparse_solve(c, F, invD, x, m.dof_lvl + 0);
+    RG_PHASE_BEGIN
+    if (lane == 0) s[diag + i] = s[x + i];
+    RG_PHASE_END
+  }
+  RG_PHASE_BEGIN
+  if (o.dof_invweight0) RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
+    const int j = m.dof_jntid[d], type = m.jnt_type[j], a = m.jnt_dofadr[j];
+    float v = s[diag + d];
+    if (type == RG_JNT_BALL || type == RG_JNT_FREE) {
+      const int g = a + 3 * ((d - a) / 3);
+      v = (s[diag + g] + s[diag + g + 1] + s[diag + g + 2]) * (1.0f / 3.0f);
+    }
+    o.dof_invweight0[d] = v;
+  }
+  if (o.body_subtreemass) RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
+    float acc = 0.0f;
+    RG_NOUNROLL for (int k = b; k < b + m.body_subtreesize[b]; k++) acc += m.body_mass[k];
+    o.body_subtreemass[b] = acc;
+  }
+  if (o.tendon_length0) RG_NOUNROLL for (int t = lane; t < m.ntendon; t += 32) o.tendon_length0[t] = s[L.tlen + t];
+  RG_PHASE_END
+  if (o.opt_meaninertia) {
+    LANEVAR(float, part);
+    RG_PHASE_BEGIN
+    float a = 0.0f;
+    RG_NOUNROLL for (int d = lane; d < nv; d += 32) a += s[L.M + m.dof_mrow[3 * d]];
+    LV(part) = a;
+    RG_PHASE_END
+    const float tot = RG_WARP_SUM(part);
+    RG_PHASE_BEGIN
+    if (lane == 0) o.opt_meaninertia[0] = tot / (float)(nv > 0 ? nv : 1);
+    RG_PHASE_END
+  }
+  /* rows of the body Jacobians and of the tendon Jacobian: y = A^-1 r, then r . y */
+  const int nrow = (o.body_invweight0 ? 6 * m.nbody : 0) + (o.tendon_invweight0 ? m.ntendon : 0);
+  float tr = 0.0f;
+  for (int q = 0; q < nrow; q++) {
+    const int isbody = o.body_invweight0 && q < 6 * m.nbody;
+    const int b = isbody ? q / 6 : 0, a = isbody ? q - 6 * b : 0, t = isbody ? 0 : q - (o.body_invweight0 ? 6 * m.nbody : 0);
+    const int skip = isbody && (b == 0 || m.body_weldid[b] == 0);
+    if (!skip) {
+      LANEVAR(float, part);
+      RG_PHASE_BEGIN
+      float com[3] = {0, 0, 0};
+      if (isbody) rg_body_xipos(c, b, com);
+      RG_NOUNROLL for (int d = lane; d < nv; d += 32) {
+        float v = 0.0f;
+        if (!isbody) v = rg_tendon_J(c, t, d);
+        else if (rg_dof_in_body(m, b, d)) {
+          if (a < 3) { float jp[3]; rg_jacp_world(c, d, com, jp); v = jp[a]; }
+          else v = s[L.S + 6 * d + a - 3];
+        }
+        s[rhs + d] = v; s[x + d] = v;
+      }
+      RG_PHASE_END
+      rg_sparse_solve(c, F, invD, x, m.dof_lvl + 0);
+      RG_PHASE_BEGIN
+      float acc = 0.0f;
+      RG_NOUNROLL for (int d = lane; d < nv; d += 32) acc += s[rhs + d] * s[x + d];
+      LV(part) = acc;
+      RG_PHASE_END
+      tr += RG_WARP_SUM(part);
+    }
+    if (!isbody || a == 2 || a == 5) {
+      RG_PHASE_BEGIN
+      if (lane == 0) {
+        if (isbody) o.body_invweight0[2 * b + (a == 5)] = skip ? 0.0f : fmaxf(tr * (1.0f / 3.0f), RG_MINVAL);
+        else o.tendon_invweight0[t] = fmaxf(tr, RG_MINVAL);
+      }
+      RG_PHASE_END
+      tr = 0.0f;
+    }
+  }
+}

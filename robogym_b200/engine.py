@@ -68,6 +68,7 @@ def lib():
         L.rg_step_subset.argtypes = [vp, vp, ci, ci, vp]
         L.rg_forward.argtypes = [vp, vp]
         L.rg_reset.argtypes = [vp, vp, vp]
+        L.rg_set_const.argtypes = [vp, vp, vp]
         _lib = L
     return _lib
 
@@ -276,6 +277,26 @@ class BatchedSim:
             mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
             mp = ctypes.c_void_p(mask.data_ptr())
         _check(lib().rg_reset(self.h, mp, self._stream()))
+
+    SET_CONST_FIELDS = ("dof_invweight0", "body_invweight0", "tendon_invweight0", "tendon_length0", "body_subtreemass", "opt_meaninertia")
+
+    def set_const(self, mask=None, fields=("dof_invweight0", "body_invweight0", "tendon_invweight0", "opt_meaninertia")):
+        """SimulationInterface.set_constants() for every (or the masked) environment: mj_setConst from each environment's own
+        parameters (set_param), on the device, written into per-environment rows of `fields` (bound here on first use with the
+        model's values).  Returns the dict of those tensors."""
+        m = self.model.host
+        for name in fields:
+            if name not in self.SET_CONST_FIELDS:
+                raise EngineError(f"set_const: {name} is not a constant mj_setConst derives")
+            if name not in getattr(self, "_params", {}) and m[name].size:
+                self.set_param(name, np.repeat(np.asarray(m[name], dtype=np.float64).reshape(1, -1), self.nenv, axis=0))
+        mp = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+            mp = ctypes.c_void_p(mask.data_ptr())
+            self._keep_mask = mask
+        _check(lib().rg_set_const(self.h, mp, self._stream()))
+        return {k: self._params[k] for k in fields if k in self._params}
 
     def set_balance(self, on):
         """Work-ordered scheduling on/off (include/robogym_b200.h: rg_batch_set_balance); results do not depend on it."""

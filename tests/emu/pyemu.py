@@ -25,6 +25,7 @@ def lib():
         L.rge_name2id.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.rge_model_field.restype = ctypes.c_void_p
         L.rge_model_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+        L.rge_set_const.argtypes = [ctypes.c_void_p] + [ctypes.c_void_p] * 6
         L.rge_set_sensordata.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.rge_set_mocap.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.rge_step.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 18 + [ctypes.c_int, ctypes.c_int]
@@ -85,6 +86,15 @@ class EmuBatch:
 
     def forward(self):
         self.step(0, 1)
+
+    def set_const(self):
+        """mj_setConst of the (edited) model through the kernel code: dict of float32 arrays"""
+        d = self.d
+        out = dict(dof_invweight0=np.zeros(d["nv"], np.float32), body_invweight0=np.zeros(2 * d["nbody"], np.float32),
+                   tendon_invweight0=np.zeros(d["ntendon"], np.float32), tendon_length0=np.zeros(d["ntendon"], np.float32),
+                   body_subtreemass=np.zeros(d["nbody"], np.float32), opt_meaninertia=np.zeros(1, np.float32))
+        lib().rge_set_const(self.h, *[_p(out[k]) if out[k].size else None for k in ("dof_invweight0", "body_invweight0", "tendon_invweight0", "tendon_length0", "body_subtreemass", "opt_meaninertia")])
+        return out
 
     def dbg_view(self, env=0):
         d = self.d

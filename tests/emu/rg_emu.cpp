@@ -40,6 +40,12 @@ void rge_stats(long long* out) { out[0] = rg_stat_support; out[1] = rg_stat_clim
 /* data.mocap_pos / mocap_quat rows ([nenv][nmocap*3], [nenv][nmocap*4]) used by the following rge_step calls (or null) */
 void rge_set_mocap(void* hv, const float* pos, const float* quat) { ((RgeHandle*)hv)->mocap_pos = pos; ((RgeHandle*)hv)->mocap_quat = quat; }
 void rge_set_sensordata(void* hv, float* out) { ((RgeHandle*)hv)->sensordata = out; }   /* [nenv][nsensordata] or null */
+/* mj_setConst of the (edited) model: any output may be null */
+void rge_set_const(void* hv, float* dof_invweight0, float* body_invweight0, float* tendon_invweight0, float* tendon_length0, float* body_subtreemass, float* opt_meaninertia) {
+  RgeHandle* h = (RgeHandle*)hv;
+  RgSetConstOut o = {dof_invweight0, body_invweight0, tendon_invweight0, tendon_length0, body_subtreemass, opt_meaninertia};
+  rg_env_setconst(&h->hm.view, h->L, h->scratch.data(), 0, o);
+}
 void rge_destroy(void* hv) { delete (RgeHandle*)hv; }
 int rge_dbg_size(void* hv) { return rg_dbg_size(((RgeHandle*)hv)->hm.view, ((RgeHandle*)hv)->L.ncon); }
 int rge_scratch_floats(void* hv) { return ((RgeHandle*)hv)->L.total; }
