@@ -4,8 +4,8 @@
 One "step" = one SimulationInterface.step() for every environment of the batch
 (robogym/mujoco/simulation_interface.py:176-189: 10 x mj_step + mj_forward), i.e. one launch of
 the fused rg_step kernel per rank.  `value` = whole-job env-steps/s with inputs resident in HBM;
-`e2e` = the same through the public API (robogym_b200.engine.BatchedSim) with HOST buffers: pinned
-ctrl -> device, step, qpos/qvel -> pinned host, every step, inside the timed region.
+`e2e` = the same through the public API (robogym_b200.engine.BatchedSim + the batched facade's action -> control law)
+with HOST buffers: pinned actions -> device, control law, step, qpos/qvel -> pinned host, every step, inside the timed region.
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -344,11 +344,16 @@ class Workload:
         sim.qacc_warmstart.mul_((~mk).to(sim.qvel.dtype))
         sim.ctrl.copy_(t.where(mk, self.c0, sim.ctrl))
 
-    def next_ctrl(self):
+    def ctrl_from_action(self, a):
+        """Robot.denormalize_position_control with relative actions (robogym/robot/robot_interface.py:247-278) on the device:
+        the formula of robogym_b200.batched_env.ShadowHandCubeFacade.denormalize_position_control"""
         t, sim = self.torch, self.sim
-        a = t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1
         center = sim.qpos @ self.P.T
         return t.minimum(t.maximum(center + a * 0.5 * (self.ctrl_hi - self.ctrl_lo), self.ctrl_lo), self.ctrl_hi)
+
+    def next_ctrl(self):
+        t, sim = self.torch, self.sim
+        return self.ctrl_from_action(t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1)
 
     def on_palm(self):
         return self.sim.site_xpos[:, self.cube_site, 2] > 0.04      # envs/dactyl/common/cube_utils.py:17-23
@@ -439,25 +444,26 @@ def run_gpu_arm(args):
     on_palm = float(wl.on_palm().float().mean().item())
     warn = int(warn.item())
 
-    # ---- timed region 2: end to end through the public API with host buffers
-    h_ctrl = torch.empty(N, nu, dtype=torch.float32).pin_memory()
+    # ---- timed region 2: end to end through the public API with host buffers: every step the policy's ACTIONS come from
+    # pinned host memory (H2D), the batched facade turns them into controls on the device (what RobotEnv.step does per
+    # environment on the host, robot_interface.py:247-278), the step runs, and the observation (qpos, qvel) is read back (D2H)
+    # and waited for, because the next action depends on it
+    h_act = [torch.empty(N, nu, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d_act = torch.empty(N, nu, dtype=torch.float32, device=dev)
     h_q = torch.empty(N, nq, dtype=torch.float32).pin_memory()
     h_v = torch.empty(N, nv, dtype=torch.float32).pin_memory()
-    h_q.copy_(sim.qpos)
     rng = np.random.RandomState(rank_seed(99, rank) % (2 ** 31))
-    P = wl.P.cpu().numpy()
-    lo_h, hi_h = wl.ctrl_lo.cpu().numpy(), wl.ctrl_hi.cpu().numpy()
-    half_h = 0.5 * (hi_h - lo_h)
+    acts = [(rng.uniform(-1, 1, (N, nu)).astype(np.float32)) for _ in range(args.steps)]
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    acts = [(rng.uniform(-1, 1, (N, nu)).astype(np.float32)) for _ in range(args.steps)]
     e0.record()
     for k in range(args.steps):
-        # the host computes this step's control from the observation it read back last step
-        np.clip(h_q.numpy() @ P.T + acts[k] * half_h, lo_h, hi_h, out=h_ctrl.numpy())
-        sim.ctrl.copy_(h_ctrl, non_blocking=True)       # H2D of this step's inputs
+        buf = h_act[k & 1]
+        buf.numpy()[:] = acts[k]                        # the policy's output lands in pinned host memory
+        d_act.copy_(buf, non_blocking=True)             # H2D of this step's inputs
+        sim.ctrl.copy_(wl.ctrl_from_action(d_act))
         sim.step()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
         h_v.copy_(sim.qvel, non_blocking=True)

@@ -202,7 +202,7 @@ class BatchedLockedEnv:
                  successes_needed=50, max_timesteps_per_goal=400, min_timesteps_per_goal=0, success_threshold=0.4,
                  success_reward=5.0, stop_on_fall=True, drop_reward=-20.0, reset_initial_steps=20,
                  n_random_initial_steps=10, cube_position_wiggle_std=0.005, auto_reset=True, observe_forwards=None,
-                 randomize=False):
+                 randomize=False, action_latency=None):
         import torch
 
         self.torch = torch
@@ -260,6 +260,14 @@ class BatchedLockedEnv:
         self.success_pending = z(torch.bool)        # MultiGoalTracker._success_and_no_goal_reset
         self.first_drop = z(torch.long)             # StopOnFallWrapper.first_drop
         self.episodes = 0
+        # RandomizedActionLatency (robogym/wrappers/randomizations.py:516-556; first entry of locked.py:265-277's stack, so it is
+        # on whenever the stack is): every action COORDINATE is delayed by 0..max_delay env-steps, drawn per episode
+        if action_latency is None:
+            action_latency = 1 if randomize else 0
+        self.max_delay = int(action_latency)
+        nu = int(model["nu"])
+        self.action_history = torch.zeros(n, self.max_delay + 1, nu, dtype=dtype, device=device)
+        self.action_delay = torch.zeros(n, nu, dtype=torch.long, device=device)
 
     # ---------------------------------------------------------------- goals
     def sample_goals(self, n):
@@ -308,6 +316,9 @@ class BatchedLockedEnv:
             self.wind_state["hit_prob"][idx] = ws["hit_prob"]
             self.timestep[idx] = self.randomizer.timestep0
             self.xfrc[idx] = 0
+        if self.max_delay > 0:                      # RandomizedActionLatency.reset
+            self.action_history[idx] = 0
+            self.action_delay[idx] = self.rand.randint(self.max_delay + 1, k * self.action_delay.shape[1]).reshape(k, -1)
         self.t[idx] = 0
         self.successes_so_far[idx] = 0
         self.goals_so_far[idx] = 0
@@ -338,6 +349,9 @@ class BatchedLockedEnv:
         qg[:, self.fac.cube_pos_idx] = torch.tensor([0.0, 0.0, -0.025], dtype=s.qpos.dtype, device=self.device)
         obs["qpos_goal"] = qg
         obs["is_goal_achieved"] = (self.goal_distance() < self.success_threshold).to(s.qpos.dtype)
+        if self.max_delay > 0:
+            obs["action_history"] = self.action_history[:, :-1].clone()
+            obs["action_delay"] = self.action_delay.clone()
         return obs
 
     # ---------------------------------------------------------------- step
@@ -349,6 +363,13 @@ class BatchedLockedEnv:
         torch = self.torch
         s = self.sim
         a = torch.clamp(torch.as_tensor(action, dtype=s.qpos.dtype, device=self.device), -1.0, 1.0)
+        if self.max_delay > 0:
+            # RandomizedActionLatency.step.  The reference shifts its history with a tuple assignment whose right-hand side is
+            # a VIEW (randomizations.py:546-549): history[0] = action is visible to the shift that follows, so the result is
+            # [a, a, old[1], old[2], ...] -- a delay of d >= 1 returns the action of d - 1 steps ago (and the default
+            # max_delay = 1 delays nothing).  Reproduced as is: this is a drop-in, not a correction.
+            self.action_history = torch.cat([a.unsqueeze(1), a.unsqueeze(1), self.action_history[:, 1:-1]], dim=1)
+            a = torch.gather(self.action_history, 1, self.action_delay.unsqueeze(1)).squeeze(1)
         cr = None
         if self.randomizer is not None:
             cr = s._params["actuator_ctrlrange"].reshape(self.nenv, -1, 2)

@@ -319,3 +319,44 @@ def test_randomised_env_with_reference_capacities_never_overflows():
     w = env.sim.warn
     assert int((w & 3).max()) == 0 and int((w & 32).max()) == 0, (int(w.max()), worst)
     assert worst <= 100
+
+
+@needs_reference
+def test_action_latency_matches_the_reference_wrapper(ref_modules, locked_blob, locked_names):
+    """RandomizedActionLatency (robogym/wrappers/randomizations.py:516-556, first entry of the locked.py:265-277 stack): with
+    the same per-coordinate delays, the batched environment hands the simulation the same delayed actions and reports the
+    same action_history / action_delay observations as the reference wrapper around the reference env."""
+    import torch
+
+    from robogym.envs.dactyl.locked import make_simple_env
+    from robogym.wrappers import randomizations as rz
+
+    inner = make_simple_env(starting_seed=3)
+    performed = []
+    real_step = inner.step
+
+    def spy(action):
+        performed.append(np.array(action, copy=True))
+        return real_step(action)
+
+    inner.step = spy
+    w = rz.RandomizedActionLatency(inner, max_delay=2)
+    obs = w.reset()
+    b = cpu_env(locked_blob, locked_names, 2, stop_on_fall=False, auto_reset=False, action_latency=2)
+    b.reset()
+    assert b.action_delay.shape == (2, 20) and int(b.action_delay.max()) <= 2 and int(b.action_delay.min()) >= 0
+    b.action_delay[0] = torch.tensor(np.asarray(w._action_delay))
+    b.action_delay[1] = 0
+    sent = []
+    orig = b.fac.denormalize_position_control
+    b.fac.denormalize_position_control = lambda a, *args, **kw: (sent.append(a.clone()), orig(a, *args, **kw))[1]
+    rng = np.random.RandomState(0)
+    for k in range(6):
+        a = rng.uniform(-1, 1, 20)
+        obs, _, _, _ = w.step(a)
+        mo, _, _, _ = b.step(np.stack([a, a]))
+        assert np.abs(sent[-1][0].numpy() - performed[-1]).max() < 1e-6, k          # env 0: the wrapper's delays
+        assert np.abs(sent[-1][1].numpy() - a).max() < 1e-6                           # env 1: no delay
+        assert np.abs(mo["action_history"][0].numpy() - np.asarray(obs["action_history"])).max() < 1e-6
+        assert np.array_equal(mo["action_delay"][0].numpy(), np.asarray(obs["action_delay"]))
+    assert len(set(np.asarray(w._action_delay))) > 1, "the fixture drew a single delay: nothing was exercised"
