@@ -21,14 +21,14 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "robogym_b2
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("dactyl_locked", ref.locked_xml), ("dactyl_reach", ref.reach_xml)):
+    for name, fn in (("dactyl_locked", ref.locked_xml), ("dactyl_reach", ref.reach_xml), ("rearrange_blocks5", ref.rearrange_blocks_xml)):
         try:
             xml = fn()
         except Exception as e:  # reach needs extra assets
             print(f"skip {name}: {e}")
             continue
         cm = mjcf.compile_mjcf(xml)
-        cm.m["opt_pid"][0] = 1  # the dactyl sims call enable_pid() right after build (cube_env.py:157-160)
+        cm.m["opt_pid"][0] = 1  # the sims call enable_pid() right after build (cube_env.py:157-160, ur16e/mujoco/simulation/base.py:29)
         with open(os.path.join(OUT, name + ".rgm"), "wb") as f:
             f.write(cm.blob())
         with open(os.path.join(OUT, name + ".names.json"), "w") as f:

@@ -91,3 +91,40 @@ def reach_xml():
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "locked"
     sys.stdout.write({"locked": locked_xml, "reach": reach_xml}[which]())
+
+
+def rearrange_blocks_xml(num_objects=5, object_size=0.0254, mujoco_timestep=0.002):
+    """BASELINE.json configs[3] (rearrange/blocks): repeats, call for call, RearrangeSimulationInterface.make_xml +
+    ArmSimulationInterface.make_robot_xml for TCP control through the mocap weld (robogym/envs/rearrange/simulation/
+    base.py:279-322, robogym/robot/ur16e/mujoco/simulation/base.py:73-110) with make_blocks_and_targets' block / target
+    documents (robogym/envs/rearrange/common/utils.py:195-241, 284-291) and the default material
+    (robogym/envs/rearrange/materials/default.jsonnet: geom condim 6, margin 5e-5; joint damping 0.01, armature 0.001)."""
+    import copy
+
+    X = mujoco_xml_cls()
+    xml = (X.parse("robot/ur16e/base.xml")
+           .set_objects_attr(tag="option", timestep=mujoco_timestep)
+           .set_objects_attr(tag="size", njmax=2000, nconmax=500, nuserdata=2000, nuser_actuator=16)
+           .add_default_compiler_directive())
+    material = dict(geom=dict(condim="6", margin=0.00005), joint=dict(damping="0.01", armature="0.001"))
+    for i in range(num_objects):
+        name = f"object{i}"
+        obj = X.from_string(f"""
+        <mujoco>
+          <worldbody>
+            <body name="{name}" pos="0.0 0.0 0.0">
+              <geom type="box" rgba="0.0 0.0 0.0 0.0" material="block_mat"/>
+              <joint name="{name}:joint" type="free"/>
+            </body>
+          </worldbody>
+        </mujoco>
+        """).set_objects_attr(tag="geom", size=[object_size] * 3)
+        target = (copy.deepcopy(obj).remove_objects_by_tag("joint")
+                  .add_name_prefix("target:", exclude_attribs=["material", "mesh", "class"])
+                  .set_objects_attr(tag="geom", contype=0, conaffinity=0))
+        obj.set_objects_attrs(material)
+        xml.append(obj)
+        xml.append(target)
+    xml.append(X.parse("robot/ur16e/jointspec/ur16e_mocap_class.xml"))
+    xml.append(X.parse("robot/ur16e/gripper_actuators.xml"))
+    return xml.xml_string()
