@@ -186,6 +186,46 @@ def cpu_baseline(blob, seconds=10.0):
                       "one otherwise idle core: under full load the per-core rate is lower (see --impl reference: value / cores)"}
 
 
+def cpu_baseline_rearrange(blob, names, seconds=10.0):
+    """Single-thread timing of the fp64 CPU port on the rearrange/blocks workload (one environment, bounded sample)."""
+    import numpy as np
+
+    from oracle import pyoracle
+
+    pyoracle.build()
+    om = pyoracle.OracleModel(blob)
+    d = pyoracle.OracleData(om)
+    jn = names["joint"]
+    d.qpos[:6] = np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0])
+    for i in range(5):
+        a = int(om.field("jnt_qposadr")[jn.index("object%d:joint" % i)])
+        d.qpos[a:a + 3] = [1.2 + 0.13 * (i % 3), 0.5 + 0.16 * (i // 3), 0.453 + 0.03324 + 0.0254 + 0.001]
+    d.forward()
+    tcp = names["body"].index("robot0:gripper_tcp")
+    om.field("eq_data")[:7] = [0, 0, 0, 1, 0, 0, 0]
+    p0 = d.xpos[3 * tcp:3 * tcp + 3].copy()
+    d.mocap_pos[:3] = p0
+    d.mocap_quat[:4] = d.xquat[4 * tcp:4 * tcp + 4]
+    lo, hi = om.field("actuator_ctrlrange")[:2]
+    rng = np.random.RandomState(0)
+
+    def run(n):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            a = rng.uniform(-1, 1, 4)
+            d.mocap_pos[:3] = np.clip(d.mocap_pos[:3] + 0.01 * a[:3], p0 + [-0.15, -0.05, -0.055], p0 + [0.25, 0.45, 0.10])
+            d.ctrl[0] = lo + (hi - lo) * 0.5 * (a[3] + 1)
+            d.env_step(20)
+        return time.perf_counter() - t0
+
+    probe = run(10)
+    n = max(10, int(seconds / (probe / 10)))
+    t = run(n)
+    return {"value": n / t, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n} env-steps (x20 substeps) of one rearrange/blocks env, the GPU arm's workload, fp64 CPU port of the reference path "
+                      "(oracle/: dense, scalar -- NOT mujoco-py); one otherwise idle core"}
+
+
 _REF = {}
 
 
@@ -285,6 +325,10 @@ CONFIGS = {
     "full_perpendicular": dict(asset="dactyl_full_perpendicular", nenv=4096, caps=(96, 288, 32),
                                label="dactyl/full_perpendicular (BASELINE.json configs[2], SURVEY 8(d) cfg 3 without per-env parameter randomisation): "
                                      "ShadowHand + Rubik's cube (26 cubelets, 6 face drivers), nq170/nv168/nu20"),
+    # BASELINE.json configs[3]: the reference's UR16e + Robotiq 2f-85 + table world with 5 blocks (tools/compose_reference_xml.py)
+    "rearrange_blocks": dict(asset="rearrange_blocks5", nenv=2048, caps=(64, 128, 16), nsub=20, workload="rearrange",
+                             label="rearrange/blocks (BASELINE.json configs[3]): UR16e + Robotiq 2f-85 driven through the mocap weld, 5 free "
+                                   "blocks (condim 6, elliptic cones, impratio 10) on the table, nq43/nv38/nu1"),
 }
 
 
@@ -352,8 +396,18 @@ class Workload:
         return t.minimum(t.maximum(center + a * 0.5 * (self.ctrl_hi - self.ctrl_lo), self.ctrl_lo), self.ctrl_hi)
 
     def next_ctrl(self):
+        return self.ctrl_from_action(self.sample_action())
+
+    @property
+    def action_dim(self):
+        return self.nu
+
+    def sample_action(self):
         t, sim = self.torch, self.sim
-        return self.ctrl_from_action(t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1)
+        return t.rand(sim.nenv, self.nu, device=self.dev, generator=self.gen) * 2 - 1
+
+    def apply_action(self, a):
+        self.sim.ctrl.copy_(self.ctrl_from_action(a))
 
     def on_palm(self):
         return self.sim.site_xpos[:, self.cube_site, 2] > 0.04      # envs/dactyl/common/cube_utils.py:17-23
@@ -362,6 +416,85 @@ class Workload:
         dropped = ~self.on_palm()
         self.reset(dropped)
         return dropped
+
+
+class RearrangeWorkload:
+    """BASELINE.json configs[3]: TCP control through the mocap weld.  Action a ~ U(-1,1)^4: the mocap target moves by
+    a[:3] * 0.01 m per env-step inside a box over the table (what gym's mocap_set_action does with MocapSolver's scaled action,
+    robogym/robot/control/tcp/mocap_solver.py:52-53), a[3] picks the gripper's position target in its control range; 20 substeps
+    of 0.002 s + forward per env-step (RearrangeSimulationInterface.build defaults, simulation/base.py:262-265).  Reset as
+    the reference does it: arm at TABLETOP_EXPERIMENT_INITIAL_POS (robot/ur16e/arm_interface.py:27), reset_mocap_welds +
+    reset_mocap2body_xpos, blocks dropped on random free spots of the table; an environment that lost a block over the
+    table's edge is reset before the next step."""
+
+    action_dim = 4
+
+    def __init__(self, sim, model, names, dev, gen):
+        import numpy as np
+        import torch
+
+        self.torch, self.sim, self.gen, self.dev = torch, sim, gen, dev
+        m = model.host
+        N = sim.nenv
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.tcp = names["body"].index("robot0:gripper_tcp")
+        self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(5)]
+        cr = m["actuator_ctrlrange"].reshape(-1, 2)
+        self.ctrl_lo, self.ctrl_hi = torch.tensor(cr[:, 0], **f32), torch.tensor(cr[:, 1], **f32)
+        eq = np.array(m["eq_data"], dtype=np.float64).reshape(-1, 7)
+        eq[0] = [0, 0, 0, 1, 0, 0, 0]                               # gym reset_mocap_welds
+        model.set_field("eq_data", eq.reshape(-1))
+        q0 = torch.tensor(m["qpos0"], **f32).repeat(N, 1)
+        q0[:, :6] = torch.tensor(np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0]), **f32)
+        for k, a in enumerate(self.blocks):                          # parked far apart for the pose query below
+            q0[:, a:a + 3] = torch.tensor([1.1 + 0.15 * k, 1.2, 0.53], **f32)
+        sim.qpos.copy_(q0)
+        sim.forward()
+        self.tcp_pos0 = sim.body_xpos[:, self.tcp].clone()
+        self.tcp_quat0 = sim.body_xquat[:, self.tcp].clone()
+        self.q0 = q0
+        self.lo = self.tcp_pos0[0] + torch.tensor([-0.15, -0.05, -0.055], **f32)
+        self.hi = self.tcp_pos0[0] + torch.tensor([0.25, 0.45, 0.10], **f32)
+        self.reset(torch.ones(N, dtype=torch.bool, device=dev))
+
+    def reset(self, mask):
+        t, sim = self.torch, self.sim
+        N = sim.nenv
+        q = self.q0.clone()
+        # blocks on a jittered 3 x 2 grid of the table area in front of the arm (one cell stays empty), random yaw
+        cells = t.argsort(t.rand(N, 6, device=self.dev, generator=self.gen), dim=1)[:, :5]
+        cx = 1.20 + 0.13 * (cells % 3).to(q.dtype) + 0.02 * (t.rand(N, 5, device=self.dev, generator=self.gen) - 0.5)
+        cy = 0.50 + 0.16 * (cells // 3).to(q.dtype) + 0.02 * (t.rand(N, 5, device=self.dev, generator=self.gen) - 0.5)
+        yaw = 3.14159 * t.rand(N, 5, device=self.dev, generator=self.gen)
+        for k, a in enumerate(self.blocks):
+            q[:, a] = cx[:, k]; q[:, a + 1] = cy[:, k]; q[:, a + 2] = 0.453 + 0.03324 + 0.0254 + 0.001
+            q[:, a + 3] = t.cos(0.5 * yaw[:, k]); q[:, a + 4] = 0.0; q[:, a + 5] = 0.0; q[:, a + 6] = t.sin(0.5 * yaw[:, k])
+        mk = mask.unsqueeze(1)
+        sim.qpos.copy_(t.where(mk, q, sim.qpos))
+        sim.qvel.mul_((~mk).to(sim.qvel.dtype))
+        sim.pid.mul_((~mk).to(sim.pid.dtype))
+        sim.qacc_warmstart.mul_((~mk).to(sim.qvel.dtype))
+        sim.ctrl.copy_(t.where(mk, self.ctrl_hi.expand_as(sim.ctrl), sim.ctrl))
+        sim.mocap_pos[:, 0].copy_(t.where(mk, self.tcp_pos0, sim.mocap_pos[:, 0]))       # reset_mocap2body_xpos
+        sim.mocap_quat[:, 0].copy_(t.where(mk, self.tcp_quat0, sim.mocap_quat[:, 0]))
+
+    def apply_action(self, a):
+        t, sim = self.torch, self.sim
+        sim.mocap_pos[:, 0].copy_(t.minimum(t.maximum(sim.mocap_pos[:, 0] + 0.01 * a[:, :3], self.lo), self.hi))
+        sim.ctrl.copy_(self.ctrl_lo + (self.ctrl_hi - self.ctrl_lo) * (0.5 * (a[:, 3:4] + 1.0)))
+
+    def sample_action(self):
+        return self.torch.rand(self.sim.nenv, 4, device=self.dev, generator=self.gen) * 2 - 1
+
+    def on_palm(self):
+        """healthy = every block still on (or above) the table"""
+        z = self.torch.stack([self.sim.qpos[:, a + 2] for a in self.blocks], dim=1)
+        return (z > 0.45).all(dim=1)
+
+    def auto_reset(self):
+        lost = ~self.on_palm()
+        self.reset(lost)
+        return lost
 
 
 def run_gpu_arm(args):
@@ -395,17 +528,20 @@ def run_gpu_arm(args):
     caps = cfg["caps"]
     if os.environ.get("RG_BENCH_CAPS"):        # experiments: "contacts,rows,dofs" (0 = engine default)
         caps = tuple(int(x) for x in os.environ["RG_BENCH_CAPS"].split(","))
-    sim = engine.BatchedSim(model, N, NSUB, outputs=("site_xpos", "act_force", "ncon", "warn"), contact_capacity=caps[0],
-                            row_capacity=caps[1], dofs_per_contact=caps[2])
+    nsub = cfg.get("nsub", NSUB)
+    rearrange = cfg.get("workload") == "rearrange"
+    sim = engine.BatchedSim(model, N, nsub, outputs=("site_xpos", "act_force", "ncon", "warn") + (("body_xpos", "body_xquat") if rearrange else ()),
+                            contact_capacity=caps[0], row_capacity=caps[1], dofs_per_contact=caps[2])
     m = model.host
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank_seed(1234, rank))
-    wl = Workload(sim, model, names, dev, gen)
+    wl = (RearrangeWorkload if rearrange else Workload)(sim, model, names, dev, gen)
+    nact = wl.action_dim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
-        sim.ctrl.copy_(wl.next_ctrl())
+        wl.apply_action(wl.sample_action())
         sim.step()
         wl.auto_reset()
     torch.cuda.synchronize()
@@ -423,9 +559,9 @@ def run_gpu_arm(args):
     warn = torch.zeros((), dtype=torch.int32, device=dev)
     ncon_max = torch.zeros((), dtype=torch.int32, device=dev)
     for k in range(args.steps):
-        nxt = wl.next_ctrl()
+        nxt = wl.sample_action()
         flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
-        sim.ctrl.copy_(nxt)
+        wl.apply_action(nxt)
         ev[k][0].record()
         sim.step()
         ev[k][1].record()
@@ -448,12 +584,12 @@ def run_gpu_arm(args):
     # pinned host memory (H2D), the batched facade turns them into controls on the device (what RobotEnv.step does per
     # environment on the host, robot_interface.py:247-278), the step runs, and the observation (qpos, qvel) is read back (D2H)
     # and waited for, because the next action depends on it
-    h_act = [torch.empty(N, nu, dtype=torch.float32).pin_memory() for _ in range(2)]
-    d_act = torch.empty(N, nu, dtype=torch.float32, device=dev)
+    h_act = [torch.empty(N, nact, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d_act = torch.empty(N, nact, dtype=torch.float32, device=dev)
     h_q = torch.empty(N, nq, dtype=torch.float32).pin_memory()
     h_v = torch.empty(N, nv, dtype=torch.float32).pin_memory()
     rng = np.random.RandomState(rank_seed(99, rank) % (2 ** 31))
-    acts = [(rng.uniform(-1, 1, (N, nu)).astype(np.float32)) for _ in range(args.steps)]
+    acts = [(rng.uniform(-1, 1, (N, nact)).astype(np.float32)) for _ in range(args.steps)]
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -464,7 +600,7 @@ def run_gpu_arm(args):
         buf.numpy()[:] = acts[k]                        # the policy's output lands in pinned host memory
         flush.zero_()                                   # same cold L2 as the device-timed region (0.05 ms of memset, inside the timing)
         d_act.copy_(buf, non_blocking=True)             # H2D of this step's inputs
-        sim.ctrl.copy_(wl.ctrl_from_action(d_act))
+        wl.apply_action(d_act)
         sim.step()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
         h_v.copy_(sim.qvel, non_blocking=True)
@@ -498,20 +634,25 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["label"] + ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
-                                   "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N,
-                       "envs_per_gpu": N, "substeps": NSUB, "physics_substeps_per_s": value * NSUB,
+            "config": {"workload": cfg["label"] + (", batch %d per GPU, 20 substeps of 0.002 s + forward per env-step, a~U(-1,1)^4: mocap target += 0.01 a[:3] "
+                                                   "(clipped to a box over the table), gripper target from a[3]; auto-reset of environments that lost a block" % N if rearrange else
+                                                   ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
+                                                   "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N),
+                       "envs_per_gpu": N, "substeps": nsub, "physics_substeps_per_s": value * nsub,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "launch": info, "cubes_on_palm_at_end": on_palm, "resets_in_timed_region_rank0": int(resets.item()),
                        "mean_contacts": float(ncon_sum.item()) / args.steps, "max_contacts": int(ncon_max.item()), "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nu * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nact * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
             "gpu_launches": 2 * args.steps * world,   # per step: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch)
             "roofline": roof,
         }
         if world == 1:
             try:
-                line["cpu_baseline"] = cpu_baseline(blob, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
+                if rearrange:
+                    line["cpu_baseline"] = cpu_baseline_rearrange(blob, names, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
+                else:
+                    line["cpu_baseline"] = cpu_baseline(blob, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "env-steps/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
@@ -533,7 +674,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 8192 envs per GPU; strong: 8192 envs per box")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]")
+    ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]; rearrange_blocks = configs[3]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
