@@ -197,9 +197,10 @@ def cpu_baseline_rearrange(blob, names, seconds=10.0):
     d = pyoracle.OracleData(om)
     jn = names["joint"]
     d.qpos[:6] = np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0])
-    for i in range(5):
+    nobj = sum(1 for n in jn if n and n.startswith("object") and n.endswith(":joint"))
+    for i in range(nobj):
         a = int(om.field("jnt_qposadr")[jn.index("object%d:joint" % i)])
-        d.qpos[a:a + 3] = [1.2 + 0.13 * (i % 3), 0.5 + 0.16 * (i // 3), 0.453 + 0.03324 + 0.0254 + 0.001]
+        d.qpos[a:a + 3] = [1.25 + 0.27 * (i % 3), 0.32 + 0.36 * (i // 3), 0.60] if nobj > 5 else [1.2 + 0.13 * (i % 3), 0.5 + 0.16 * (i // 3), 0.453 + 0.03324 + 0.0254 + 0.001]
     d.forward()
     tcp = names["body"].index("robot0:gripper_tcp")
     om.field("eq_data")[:7] = [0, 0, 0, 1, 0, 0, 0]
@@ -222,7 +223,7 @@ def cpu_baseline_rearrange(blob, names, seconds=10.0):
     n = max(10, int(seconds / (probe / 10)))
     t = run(n)
     return {"value": n / t, "unit": "env-steps/s", "cores": 1, "kind": "port",
-            "sample": f"{n} env-steps (x20 substeps) of one rearrange/blocks env, the GPU arm's workload, fp64 CPU port of the reference path "
+            "sample": f"{n} env-steps (x20 substeps) of one rearrange env with {nobj} objects, the GPU arm's workload, fp64 CPU port of the reference path "
                       "(oracle/: dense, scalar -- NOT mujoco-py); one otherwise idle core"}
 
 
@@ -326,9 +327,13 @@ CONFIGS = {
                                label="dactyl/full_perpendicular (BASELINE.json configs[2], SURVEY 8(d) cfg 3 without per-env parameter randomisation): "
                                      "ShadowHand + Rubik's cube (26 cubelets, 6 face drivers), nq170/nv168/nu20"),
     # BASELINE.json configs[3]: the reference's UR16e + Robotiq 2f-85 + table world with 5 blocks (tools/compose_reference_xml.py)
-    "rearrange_blocks": dict(asset="rearrange_blocks5", nenv=2048, caps=(64, 128, 16), nsub=20, workload="rearrange",
+    "rearrange_blocks": dict(asset="rearrange_blocks5", nenv=2048, caps=(64, 128, 16), nsub=20, workload="rearrange", nobj=5, grid=(3, 6, 1.20, 0.50, 0.13, 0.16),
                              label="rearrange/blocks (BASELINE.json configs[3]): UR16e + Robotiq 2f-85 driven through the mocap weld, 5 free "
                                    "blocks (condim 6, elliptic cones, impratio 10) on the table, nq43/nv38/nu1"),
+    # BASELINE.json configs[4]: the same world with 8 YCB objects (unions of 1..29 convex meshes each; one fixed draw of the eight)
+    "rearrange_ycb": dict(asset="rearrange_ycb8", nenv=1024, caps=(64, 128, 16), nsub=20, workload="rearrange", nobj=8, grid=(3, 9, 1.25, 0.32, 0.27, 0.36),
+                          label="rearrange/ycb (BASELINE.json configs[4]): UR16e + Robotiq 2f-85 driven through the mocap weld, 8 YCB mesh objects "
+                                "(cracker box, banana, mug, power drill, hammer, soup can, scissors, apple: 59 convex parts) on the table, nq64/nv56/nu1"),
 }
 
 
@@ -429,7 +434,7 @@ class RearrangeWorkload:
 
     action_dim = 4
 
-    def __init__(self, sim, model, names, dev, gen):
+    def __init__(self, sim, model, names, dev, gen, nobj=5, grid=(3, 6, 1.20, 0.50, 0.13, 0.16)):
         import numpy as np
         import torch
 
@@ -437,8 +442,24 @@ class RearrangeWorkload:
         m = model.host
         N = sim.nenv
         f32 = dict(dtype=torch.float32, device=dev)
+        self.nobj, self.grid = nobj, grid
         self.tcp = names["body"].index("robot0:gripper_tcp")
-        self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(5)]
+        self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(nobj)]
+        # resting height of every object: the table top minus the lowest point of its geoms in the body frame
+        rest = []
+        for i in range(nobj):
+            b = names["body"].index("object%d" % i)
+            zmin = 0.0
+            for g in range(m["ngeom"]):
+                if m["geom_bodyid"][g] != b:
+                    continue
+                if m["geom_dataid"][g] >= 0:
+                    a, n = int(m["mesh_vertadr"][m["geom_dataid"][g]]), int(m["mesh_vertnum"][m["geom_dataid"][g]])
+                    zmin = min(zmin, float((m["mesh_vert"].reshape(-1, 3)[a:a + n, 2] + m["geom_pos"].reshape(-1, 3)[g, 2]).min()))
+                else:
+                    zmin = min(zmin, float(m["geom_pos"].reshape(-1, 3)[g, 2] - m["geom_size"].reshape(-1, 3)[g, 2]))
+            rest.append(0.453 + 0.03324 - zmin + 0.001)
+        self.rest = torch.tensor(rest, **f32)
         cr = m["actuator_ctrlrange"].reshape(-1, 2)
         self.ctrl_lo, self.ctrl_hi = torch.tensor(cr[:, 0], **f32), torch.tensor(cr[:, 1], **f32)
         eq = np.array(m["eq_data"], dtype=np.float64).reshape(-1, 7)
@@ -447,7 +468,7 @@ class RearrangeWorkload:
         q0 = torch.tensor(m["qpos0"], **f32).repeat(N, 1)
         q0[:, :6] = torch.tensor(np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0]), **f32)
         for k, a in enumerate(self.blocks):                          # parked far apart for the pose query below
-            q0[:, a:a + 3] = torch.tensor([1.1 + 0.15 * k, 1.2, 0.53], **f32)
+            q0[:, a:a + 3] = torch.tensor([1.0 + 0.25 * (k % 4), 1.1 + 0.3 * (k // 4), 0.75], **f32)
         sim.qpos.copy_(q0)
         sim.forward()
         self.tcp_pos0 = sim.body_xpos[:, self.tcp].clone()
@@ -461,13 +482,15 @@ class RearrangeWorkload:
         t, sim = self.torch, self.sim
         N = sim.nenv
         q = self.q0.clone()
-        # blocks on a jittered 3 x 2 grid of the table area in front of the arm (one cell stays empty), random yaw
-        cells = t.argsort(t.rand(N, 6, device=self.dev, generator=self.gen), dim=1)[:, :5]
-        cx = 1.20 + 0.13 * (cells % 3).to(q.dtype) + 0.02 * (t.rand(N, 5, device=self.dev, generator=self.gen) - 0.5)
-        cy = 0.50 + 0.16 * (cells // 3).to(q.dtype) + 0.02 * (t.rand(N, 5, device=self.dev, generator=self.gen) - 0.5)
-        yaw = 3.14159 * t.rand(N, 5, device=self.dev, generator=self.gen)
+        # objects on a jittered grid of the table area in front of the arm (one cell stays empty), random yaw
+        ncol, ncell, x0, y0, dx, dy = self.grid
+        no = self.nobj
+        cells = t.argsort(t.rand(N, ncell, device=self.dev, generator=self.gen), dim=1)[:, :no]
+        cx = x0 + dx * (cells % ncol).to(q.dtype) + 0.02 * (t.rand(N, no, device=self.dev, generator=self.gen) - 0.5)
+        cy = y0 + dy * (cells // ncol).to(q.dtype) + 0.02 * (t.rand(N, no, device=self.dev, generator=self.gen) - 0.5)
+        yaw = 3.14159 * t.rand(N, no, device=self.dev, generator=self.gen)
         for k, a in enumerate(self.blocks):
-            q[:, a] = cx[:, k]; q[:, a + 1] = cy[:, k]; q[:, a + 2] = 0.453 + 0.03324 + 0.0254 + 0.001
+            q[:, a] = cx[:, k]; q[:, a + 1] = cy[:, k]; q[:, a + 2] = self.rest[k]
             q[:, a + 3] = t.cos(0.5 * yaw[:, k]); q[:, a + 4] = 0.0; q[:, a + 5] = 0.0; q[:, a + 6] = t.sin(0.5 * yaw[:, k])
         mk = mask.unsqueeze(1)
         sim.qpos.copy_(t.where(mk, q, sim.qpos))
@@ -536,7 +559,7 @@ def run_gpu_arm(args):
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank_seed(1234, rank))
-    wl = (RearrangeWorkload if rearrange else Workload)(sim, model, names, dev, gen)
+    wl = RearrangeWorkload(sim, model, names, dev, gen, cfg["nobj"], cfg["grid"]) if rearrange else Workload(sim, model, names, dev, gen)
     nact = wl.action_dim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     warmup = max(args.warmup, 3)
@@ -635,7 +658,7 @@ def run_gpu_arm(args):
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["label"] + (", batch %d per GPU, 20 substeps of 0.002 s + forward per env-step, a~U(-1,1)^4: mocap target += 0.01 a[:3] "
-                                                   "(clipped to a box over the table), gripper target from a[3]; auto-reset of environments that lost a block" % N if rearrange else
+                                                   "(clipped to a box over the table), gripper target from a[3]; auto-reset of environments that lost an object" % N if rearrange else
                                                    ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
                                                    "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N),
                        "envs_per_gpu": N, "substeps": nsub, "physics_substeps_per_s": value * nsub,
@@ -674,7 +697,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 8192 envs per GPU; strong: 8192 envs per box")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]; rearrange_blocks = configs[3]")
+    ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]; rearrange_blocks = configs[3]; rearrange_ycb = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -21,7 +21,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "robogym_b2
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("dactyl_locked", ref.locked_xml), ("dactyl_reach", ref.reach_xml), ("rearrange_blocks5", ref.rearrange_blocks_xml)):
+    for name, fn in (("dactyl_locked", ref.locked_xml), ("dactyl_reach", ref.reach_xml), ("rearrange_blocks5", ref.rearrange_blocks_xml), ("rearrange_ycb8", ref.rearrange_ycb_xml)):
         try:
             xml = fn()
         except Exception as e:  # reach needs extra assets

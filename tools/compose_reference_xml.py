@@ -128,3 +128,65 @@ def rearrange_blocks_xml(num_objects=5, object_size=0.0254, mujoco_timestep=0.00
     xml.append(X.parse("robot/ur16e/jointspec/ur16e_mocap_class.xml"))
     xml.append(X.parse("robot/ur16e/gripper_actuators.xml"))
     return xml.xml_string()
+
+
+YCB_SCENE = ("003_cracker_box", "011_banana", "025_mug", "035_power_drill", "048_hammer", "005_tomato_soup_can", "037_scissors", "013_apple")
+
+
+def rearrange_ycb_xml(mesh_dirs=YCB_SCENE, mujoco_timestep=0.002):
+    """BASELINE.json configs[4] (rearrange/ycb, num_objects=8): like rearrange_blocks_xml, with make_mesh_object's documents
+    (robogym/envs/rearrange/common/utils.py:250-281) -- one free body per object holding one mesh geom per STL part of the
+    object's YCB directory (find_meshes_by_dirname, utils.py:997-1021), shifted so that the combined centre of mass sits at the
+    body origin -- plus make_target's copy and the default material.  The reference takes the centre of mass from
+    trimesh.util.concatenate(...).center_mass; here it is the volume-weighted mean of the parts' centres of mass
+    (mjcf.polyhedron_mass_props on the raw triangles), the same integral for closed, consistently oriented parts.
+    One fixed choice of eight objects (the env draws them at random per reset, envs/rearrange/ycb.py:75-95)."""
+    import copy
+    import glob
+
+    import numpy as np
+
+    from robogym_b200 import mjcf
+
+    X = mujoco_xml_cls()
+    xml = (X.parse("robot/ur16e/base.xml")
+           .set_objects_attr(tag="option", timestep=mujoco_timestep)
+           .set_objects_attr(tag="size", njmax=2000, nconmax=500, nuserdata=2000, nuser_actuator=16)
+           .add_default_compiler_directive())
+    material = dict(geom=dict(condim="6", margin=0.00005), joint=dict(damping="0.01", armature="0.001"))
+    stl_root = os.path.join(REF, "robogym", "assets", "stls")
+    for i, d in enumerate(mesh_dirs):
+        name = f"object{i}"
+        files = sorted(glob.glob(os.path.join(stl_root, "ycb", d, "*.stl")))
+        vol, mom = 0.0, np.zeros(3)
+        for f in files:
+            verts = mjcf.load_stl(f)                              # three vertices per triangle, in order
+            v, com, _ = mjcf.polyhedron_mass_props(verts, np.arange(len(verts)).reshape(-1, 3))
+            vol += v
+            mom += v * np.asarray(com)
+        pos = " ".join(map(str, (-mom / vol).tolist()))
+        rel = [os.path.relpath(f, stl_root) for f in files]
+        assets = "\n".join(f'<mesh file="{f}" name="{name}-{k}" scale="1.0 1.0 1.0" />' for k, f in enumerate(rel))
+        geoms = "\n".join(f'<geom type="mesh" mesh="{name}-{k}" pos="{pos}"/>' for k in range(len(rel)))
+        obj = X.from_string(f"""
+        <mujoco>
+          <asset>
+            {assets}
+          </asset>
+          <worldbody>
+            <body name="{name}" pos="0.0 0.0 0.0">
+              {geoms}
+              <joint name="{name}:joint" type="free"/>
+            </body>
+          </worldbody>
+        </mujoco>
+        """)
+        target = (copy.deepcopy(obj).remove_objects_by_tag("joint")
+                  .add_name_prefix("target:", exclude_attribs=["material", "mesh", "class"])
+                  .set_objects_attr(tag="geom", contype=0, conaffinity=0))
+        obj.set_objects_attrs(material)
+        xml.append(obj)
+        xml.append(target)
+    xml.append(X.parse("robot/ur16e/jointspec/ur16e_mocap_class.xml"))
+    xml.append(X.parse("robot/ur16e/gripper_actuators.xml"))
+    return xml.xml_string()
