@@ -133,6 +133,29 @@ class PyMjModel:
         self.mat_rgba = np.ones((1, 4))
         self.geom_matid = np.zeros(n["ngeom"], dtype=np.int32)
         self.geom_group = np.zeros(n["ngeom"], dtype=np.int32)
+        # cameras / lights / headlight: rendering only (robogym/envs/rearrange/simulation/base.py:187-189,781-803 saves and
+        # randomises them); kept as writable arrays with the XML's values so that code runs, never sent to the engine
+        import types
+        import xml.etree.ElementTree as ET
+
+        cams, lights = [], []
+        try:
+            root = ET.fromstring(cm.xml) if getattr(cm, "xml", None) else None
+        except ET.ParseError:
+            root = None
+        if root is not None:
+            cams, lights = list(root.iter("camera")), list(root.iter("light"))
+        vec = lambda e, k, d: np.array([float(x) for x in e.get(k, d).split()], dtype=np.float64)
+        self.cam_fovy = np.array([float(c.get("fovy", "45")) for c in cams], dtype=np.float64)
+        self.cam_pos = np.array([vec(c, "pos", "0 0 0") for c in cams], dtype=np.float64).reshape(-1, 3)
+        self.cam_quat = np.array([vec(c, "quat", "1 0 0 0") for c in cams], dtype=np.float64).reshape(-1, 4)
+        self.camera_names = tuple(c.get("name", "") for c in cams)
+        self.light_pos = np.array([vec(l, "pos", "0 0 0") for l in lights], dtype=np.float64).reshape(-1, 3)
+        self.light_dir = np.array([vec(l, "dir", "0 0 -1") for l in lights], dtype=np.float64).reshape(-1, 3)
+        self.light_castshadow = np.array([l.get("castshadow", "true") == "true" for l in lights], dtype=np.float64)
+        self.light_ambient = np.array([vec(l, "ambient", "0 0 0") for l in lights], dtype=np.float64).reshape(-1, 3)
+        self.light_diffuse = np.array([vec(l, "diffuse", "0.7 0.7 0.7") for l in lights], dtype=np.float64).reshape(-1, 3)
+        self.vis = types.SimpleNamespace(headlight=types.SimpleNamespace(ambient=np.full(3, 0.1), diffuse=np.full(3, 0.4), specular=np.full(3, 0.5)))
 
     def __getattr__(self, k):
         m = self.__dict__.get("_m")
@@ -177,6 +200,11 @@ class PyMjModel:
 
     def get_xml(self):
         return self._cm.xml
+
+    def camera_name2id(self, name):
+        if name not in self.camera_names:
+            raise ValueError(f'No "camera" with name {name} exists.')
+        return self.camera_names.index(name)
 
 
 class _Contact:

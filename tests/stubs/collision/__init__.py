@@ -1,20 +1,21 @@
-"""import-only stub (test infrastructure): the real package is not installed and is not on the step path.
-robogym's rearrange placement code imports Poly / Vector / collide from it; object placement is outside this round's
-scope, so they refuse to run."""
+"""Stand-in for the `collision` package (not installed in this image; test infrastructure).  robogym's rearrange placement code
+uses exactly Vector(x, y), Poly.from_box(center, width, height) and collide(a, b) on such axis-aligned rectangles
+(robogym/envs/rearrange/common/utils.py:600-620), for which the separating-axis test is an interval-overlap test."""
 
 
-class _Unsupported:
-    def __init__(self, *a, **k):
-        raise NotImplementedError("the `collision` package is not installed (rearrange placement is out of scope)")
+class Vector:
+    def __init__(self, x, y):
+        self.x, self.y = float(x), float(y)
 
 
-class Poly(_Unsupported):
-    pass
+class Poly:
+    def __init__(self, center, width, height):
+        self.pos, self.w, self.h = center, float(width), float(height)
+
+    @classmethod
+    def from_box(cls, center, width, height):
+        return cls(center, width, height)
 
 
-class Vector(_Unsupported):
-    pass
-
-
-def collide(*a, **k):
-    raise NotImplementedError("the `collision` package is not installed (rearrange placement is out of scope)")
+def collide(a, b):
+    return abs(a.pos.x - b.pos.x) * 2.0 < a.w + b.w and abs(a.pos.y - b.pos.y) * 2.0 < a.h + b.h
