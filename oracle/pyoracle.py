@@ -1,7 +1,8 @@
 """ctypes front end of the CPU ORACLE (oracle/rgo_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
-import this module (see oracle/rgo_oracle.h).  PARITY UNPINNED vs mujoco-py (not installable).
+import this module (see oracle/rgo_oracle.h).  PARITY UNPINNED vs mujoco-py (not installable) except for the one documented real-MuJoCo
+output the reference holds (block height 0.51167315, tests/test_rearrange_reset_pin.py).
 """
 import ctypes
 import os

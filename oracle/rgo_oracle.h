@@ -8,15 +8,22 @@
  * cymj.set_pid_control (robogym/mujoco/simulation_interface.py:86-88; parameter
  * layout robogym/mujoco/constants.py:34-53).
  *
- * PARITY UNPINNED: the arithmetic of this path lives in mujoco-py==2.0.2.13 /
- * MuJoCo 2.0 (robogym setup.py:16), which is not vendored in /root/reference and is
- * not installable in the build container.  This file restates MuJoCo's published
- * pipeline (kinematics -> tendons -> CRB mass matrix -> collision -> constraint
- * rows with solref/solimp impedance -> Newton solver on the pyramidal-cone
- * convex problem -> semi-implicit Euler with implicit joint damping) from its
- * documentation.  It is pinned only against the reference-owned fixtures listed
- * in SURVEY.md section 8(c) (pure-numpy forward kinematics, cube mass, joint
- * order, closed-loop PID tracking, resting behaviour), see tests/.
+ * PARITY: the arithmetic of this path lives in mujoco-py==2.0.2.13 / MuJoCo 2.0
+ * (robogym setup.py:16), which is not vendored in /root/reference and is not installable
+ * in the build container, so no mujoco-py trajectory exists to compare against: PARITY
+ * UNPINNED for everything except what follows.  This file restates MuJoCo's published
+ * pipeline (kinematics -> tendons -> CRB mass matrix -> collision -> constraint rows with
+ * solref/solimp impedance -> Newton solver on the pyramidal / elliptic cone convex problem
+ * -> semi-implicit Euler with implicit joint damping) from its documentation.  Pinned:
+ *   - ONE real-MuJoCo output, the only one the reference repository holds for a simulated
+ *     quantity: the block heights 0.51167315 that its documentation prints for
+ *     rearrange/blocks_train after env.reset() (docs/env_param_interface.md:32-38).  The
+ *     unmodified reference environment, run on the mujoco_py shim with this oracle as the
+ *     engine, reports exactly that number after its 4000 mj_steps of object stabilisation
+ *     (tests/test_rearrange_reset_pin.py, tools/make_rearrange_reset_fixture.py);
+ *   - the reference-owned fixtures listed in SURVEY.md section 8(c) (pure-numpy forward
+ *     kinematics, cube mass, joint order, closed-loop PID tracking, resting behaviour, the
+ *     recorded four-block stack), see tests/.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.
