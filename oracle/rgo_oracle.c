@@ -83,6 +83,14 @@ rgo_model* rgo_model_load(const void* blob, size_t len) {
 #undef RG_I
 #undef RG_F
   if (off > len) { free(m->storage); free(m); return NULL; }
+  /* the cascaded-PI user controller (actuator_user[0] = 1, robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/
+     joint_actuations.xml:4) is defined in mujoco-py's mjpid.pyx, which the reference tree does not contain: refused, like the
+     engine does, rather than driven by the PID law */
+  for (int i = 0; i < m->nu; i++)
+    if (m->actuator_user0[i] == 1.0 && m->actuator_biastype[i] == BIAS_USER) {
+      fprintf(stderr, "rgo_model_load: cascaded-PI actuators (actuator_user[0] = 1): control law not available\n");
+      free(m->storage); free(m); return NULL;
+    }
   return m;
 }
 

@@ -143,8 +143,11 @@ class PyMjModel:
             root = ET.fromstring(cm.xml) if getattr(cm, "xml", None) else None
         except ET.ParseError:
             root = None
+        self.nuser_actuator = 0
         if root is not None:
             cams, lights = list(root.iter("camera")), list(root.iter("light"))
+            for sz in root.iter("size"):             # mjModel.nuser_actuator: width of actuator_user (only column 0 is carried)
+                self.nuser_actuator = int(sz.get("nuser_actuator", self.nuser_actuator))
         vec = lambda e, k, d: np.array([float(x) for x in e.get(k, d).split()], dtype=np.float64)
         self.cam_fovy = np.array([float(c.get("fovy", "45")) for c in cams], dtype=np.float64)
         self.cam_pos = np.array([vec(c, "pos", "0 0 0") for c in cams], dtype=np.float64).reshape(-1, 3)

@@ -15,3 +15,21 @@ if os.environ.get("RG_SHIM_ENGINE", "oracle") == "oracle":
     from oracle_engine import OracleEngine  # noqa: E402
 
     shim.set_engine_factory(OracleEngine)
+
+# The UR16e's default joint calibration drives the arm with mujoco-py's cascaded-PI controller, whose law (mjpid.pyx) is not
+# in the reference tree; the engines refuse such models.  The reference ships a second calibration, "pid"
+# (robogym/robot/robot_interface.py:61-63), which uses the PID controller this repository implements: the rearrange test files
+# are run with that as the default.
+if os.environ.get("RG_REFSUITE_ARM_CALIBRATION", "pid") == "pid":
+    import attr  # noqa: E402
+    import robogym.robot.ur16e.mujoco.simulation.base as _arm_sim  # noqa: E402
+
+    _orig_make_robot_xml = _arm_sim.ArmSimulationInterface.make_robot_xml.__func__
+
+    def _make_robot_xml(cls, xml, robot_control_params):
+        # the one place the calibration is read (robogym/robot/ur16e/mujoco/simulation/base.py:97)
+        if robot_control_params.arm_joint_calibration_path != "pid":
+            robot_control_params = attr.evolve(robot_control_params, arm_joint_calibration_path="pid")
+        return _orig_make_robot_xml(cls, xml, robot_control_params)
+
+    _arm_sim.ArmSimulationInterface.make_robot_xml = classmethod(_make_robot_xml)

@@ -53,7 +53,8 @@ def test_name_tables_travel_in_the_blob(locked_blob, locked_names):
 def test_unsupported_features_are_refused(locked_blob):
     """What the compiler can describe but the engine does not simulate must not load (such models used to step
     with silently wrong physics).  Elliptic cones, welds, joint couplings and mocap bodies are simulated since round 2; a
-    connect constraint, or a weld between bodies with more than RG_TJ = 8 dofs between them, is still refused."""
+    connect constraint, a weld between bodies with more than RG_TJ = 8 dofs between them, or an actuator driven by mujoco-py's
+    cascaded-PI controller (actuator_user[0] = 1; its law is not in the reference tree) is still refused."""
     import numpy as np
 
     import pyemu
@@ -70,7 +71,8 @@ def test_unsupported_features_are_refused(locked_blob):
     tip = names["body"].index("robot0:ffdistal")
     for edit, ok in ((lambda m: add_eq(m, 0, 0, tip), False),                                  # connect
                      (lambda m: add_eq(m, 1, 0, tip), True),                                   # weld world <-> fingertip: 6 dofs
-                     (lambda m: add_eq(m, 1, names["body"].index("robot0:thdistal"), tip), False)):   # thumb tip <-> fingertip: 11 dofs
+                     (lambda m: add_eq(m, 1, names["body"].index("robot0:thdistal"), tip), False),    # thumb tip <-> fingertip: 11 dofs
+                     (lambda m: m["actuator_user0"].__setitem__(0, 1.0), False)):                       # mujoco-py's cascaded-PI controller
         m = modelblob.unpack(locked_blob)
         edit(m)
         blob = modelblob.pack(m, names)
