@@ -112,7 +112,7 @@ class _Opt:
 
 _SHAPES = dict(body_pos=3, body_quat=4, body_ipos=3, body_iquat=4, body_inertia=3, body_invweight0=2, jnt_pos=3, jnt_axis=3, jnt_range=2,
                jnt_solref=2, jnt_solimp=5, geom_size=3, geom_pos=3, geom_quat=4, geom_friction=3, geom_solref=2, geom_solimp=5,
-               site_pos=3, site_quat=4, site_size=3, tendon_range=2, actuator_gainprm=10, actuator_biasprm=10, actuator_ctrlrange=2,
+               site_pos=3, site_quat=4, site_size=3, mesh_vert=3, mesh_face=3, tendon_range=2, actuator_gainprm=10, actuator_biasprm=10, actuator_ctrlrange=2,
                actuator_forcerange=2, actuator_gear=6, eq_data=7, eq_solref=2, eq_solimp=5, dof_solref=2, dof_solimp=5)
 _OBJ = dict(body="body", joint="joint", geom="geom", site="site", tendon="tendon", actuator="actuator", mesh="mesh", sensor="sensor")
 
