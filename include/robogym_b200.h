@@ -46,7 +46,9 @@ enum rg_field {
   RG_FIELD_QPOS = 0,       /* [nenv][nq]          in/out */
   RG_FIELD_QVEL = 1,       /* [nenv][nv]          in/out */
   RG_FIELD_CTRL = 2,       /* [nenv][nu]          in     */
-  RG_FIELD_PID = 3,        /* [nenv][3*nu]        in/out : mujoco-py PID state (integral, last error, last derivative) */
+  RG_FIELD_PID = 3,        /* [nenv][npid]        in/out : mujoco-py controller state in userdata; npid = rg_model_dim(m, "npid") = 3*nu
+                              (PID: integral, last error, last derivative) or 6*nu when the model has a cascaded-PI actuator
+                              (actuator user="1": + velocity-loop integral, smoothed set-point, step-taken flag) */
   RG_FIELD_WARMSTART = 4,  /* [nenv][nv]          in/out : qacc_warmstart */
   RG_FIELD_TIME = 5,       /* [nenv]              in/out (optional) */
   RG_FIELD_XFRC = 6,       /* [nenv][nbody*6]     in     (optional) : data.xfrc_applied */

@@ -45,6 +45,8 @@ def lib():
         for f in ("rgo_reset", "rgo_forward", "rgo_step"):
             getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         L.rgo_env_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.rgo_pid_stride.argtypes = [ctypes.c_void_p]
+        L.rgo_set_casc_gravcomp.argtypes = [ctypes.c_int]
         L.rgo_tendon_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_void_p] * 3
         _lib = L
     return _lib

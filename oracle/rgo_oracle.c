@@ -83,14 +83,6 @@ rgo_model* rgo_model_load(const void* blob, size_t len) {
 #undef RG_I
 #undef RG_F
   if (off > len) { free(m->storage); free(m); return NULL; }
-  /* the cascaded-PI user controller (actuator_user[0] = 1, robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/
-     joint_actuations.xml:4) is defined in mujoco-py's mjpid.pyx, which the reference tree does not contain: refused, like the
-     engine does, rather than driven by the PID law */
-  for (int i = 0; i < m->nu; i++)
-    if (m->actuator_user0[i] == 1.0 && m->actuator_biastype[i] == BIAS_USER) {
-      fprintf(stderr, "rgo_model_load: cascaded-PI actuators (actuator_user[0] = 1): control law not available\n");
-      free(m->storage); free(m); return NULL;
-    }
   return m;
 }
 
@@ -785,20 +777,66 @@ static void rgo_passive(const rgo_model* m, rgo_data* d) {
 /* ------------------------------------------------------------------ S11 actuation */
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
+/* userdata floats per actuator: mujoco-py's PID keeps 3 (integral, last error, last derivative); a model with a cascaded-PI
+ * actuator (actuator_user[0] = 1) keeps 6 for every actuator (position-loop integral, last error, last derivative,
+ * velocity-loop integral, smoothed set-point, "a step has been taken" flag). */
+static int rgo_casc_gravcomp = 1;
+void rgo_set_casc_gravcomp(int on) { rgo_casc_gravcomp = on; }   /* experiment switch (tests/tools) */
+int rgo_pid_stride(const rgo_model* m) {
+  static int env_read = 0;
+  if (!env_read) { const char* e = getenv("RGO_CASC_GRAVCOMP"); if (e) rgo_set_casc_gravcomp(atoi(e)); env_read = 1; }
+  for (int i = 0; i < m->nu; i++)
+    if (m->actuator_user0[i] == 1.0 && m->actuator_biastype[i] == BIAS_USER) return 6;
+  return 3;
+}
+
 /* mujoco-py's PID bias callback (mjpid.pyx, pinned by robogym/mujoco/constants.py:34-53 and
  * SURVEY.md Appendix D).  State per actuator in userdata: integral, last error, last derivative. */
-static double pid_bias(const rgo_model* m, rgo_data* d, int id) {
+static double pid_bias(const rgo_model* m, rgo_data* d, int id, int stride) {
   const double* g = m->actuator_gainprm + 10 * id;
   double dt = m->opt_timestep[0];
   double Kp = g[0], Ti = g[1], imax = g[2], Td = g[3], smooth = g[4], deadband = g[5];
   double err = d->ctrl[id] - d->actuator_length[id];
   if (fabs(err) < deadband) err = 0;
-  double* ud = d->userdata + 3 * id;
+  double* ud = d->userdata + stride * id;
   double integ = clampd(ud[0] + err * dt, -imax, imax);
   double deriv = (err - ud[1]) / dt;
   deriv = (1.0 - smooth) * ud[2] + smooth * deriv;
   double f = Kp * (err + (Ti != 0 ? integ / Ti : 0.0) + Td * deriv);
   ud[0] = integ; ud[1] = err; ud[2] = deriv;
+  double lo = m->actuator_forcerange[2 * id], hi = m->actuator_forcerange[2 * id + 1];
+  if (lo != 0 || hi != 0) f = clampd(f, lo, hi);
+  return f;
+}
+
+/* mujoco-py's cascaded-PI bias callback (mjpid.pyx, selected by actuator_user[0] = 1: the UR16e's default joint calibration,
+ * robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/joint_actuations.xml:4-10).  mjpid.pyx is not in the
+ * reference tree: this is its published law restated, pinned by the reference's impulse-response
+ * fixture robogym/envs/rearrange/tests/test_rearrange_sim.py:135-230 (tests/test_reference_suite.py).
+ *   gainprm = Kp_x Ti_x clamp_x Td_x dsmooth_x | Kp_v Ti_v clamp_v | ema max_vel
+ *   set-point: exponential moving average of ctrl (taken over as is until the first step has been integrated),
+ *   position PID loop -> desired velocity, clamped to max_vel (Kp_x = 0: ctrl is the desired velocity),
+ *   velocity PI loop -> force, plus the joint's bias force (gravity / Coriolis compensation), clamped to forcerange. */
+static double cascaded_pi_bias(const rgo_model* m, rgo_data* d, int id, int stride) {
+  const double* g = m->actuator_gainprm + 10 * id;
+  double dt = m->opt_timestep[0];
+  double* ud = d->userdata + stride * id;
+  double ema = ud[5] != 0 ? g[8] * ud[4] + (1.0 - g[8]) * d->ctrl[id] : d->ctrl[id];
+  ud[4] = ema;
+  double des_vel = d->ctrl[id];
+  if (g[0] != 0) {
+    double err = ema - d->actuator_length[id];
+    double integ = clampd(ud[0] + err * dt, -g[2], g[2]);
+    double deriv = (1.0 - g[4]) * ud[2] + g[4] * (err - ud[1]) / dt;
+    des_vel = g[0] * (err + (g[1] != 0 ? integ / g[1] : 0.0) + g[3] * deriv);
+    ud[0] = integ; ud[1] = err; ud[2] = deriv;
+  }
+  des_vel = clampd(des_vel, -g[9], g[9]);
+  double errv = des_vel - d->actuator_velocity[id];
+  double integv = clampd(ud[3] + errv * dt, -g[7], g[7]);
+  ud[3] = integv;
+  double f = g[5] * (errv + (g[6] != 0 ? integv / g[6] : 0.0));
+  if (rgo_casc_gravcomp && m->actuator_trntype[id] == TRN_JOINT) f += d->qfrc_bias[m->jnt_dofadr[m->actuator_trnid[id]]];
   double lo = m->actuator_forcerange[2 * id], hi = m->actuator_forcerange[2 * id + 1];
   if (lo != 0 || hi != 0) f = clampd(f, lo, hi);
   return f;
@@ -821,7 +859,8 @@ static void rgo_actuation(const rgo_model* m, rgo_data* d) {
     const double* bp = m->actuator_biasprm + 10 * i;
     if (m->actuator_biastype[i] == BIAS_AFFINE) bias = bp[0] + bp[1] * d->actuator_length[i] + bp[2] * v;
     else if (m->actuator_biastype[i] == BIAS_USER && m->opt_pid[0]) {
-      if (3 * i + 3 <= m->nuserdata) bias = pid_bias(m, d, i);
+      int stride = rgo_pid_stride(m);
+      if (stride * (i + 1) <= m->nuserdata) bias = m->actuator_user0[i] == 1.0 ? cascaded_pi_bias(m, d, i, stride) : pid_bias(m, d, i, stride);
     }
     double f = gain * ctrl + bias;
     if (m->actuator_forcelimited[i]) f = clampd(f, m->actuator_forcerange[2 * i], m->actuator_forcerange[2 * i + 1]);
@@ -895,6 +934,8 @@ static void rgo_euler(const rgo_model* m, rgo_data* d) {
     }
   }
   d->time[0] += h;
+  if (rgo_pid_stride(m) == 6)   /* cascaded-PI "a step has been taken" flag (mjpid.pyx: d.time > 0) */
+    for (int i = 0; i < m->nu; i++) if (6 * (i + 1) <= m->nuserdata) d->userdata[6 * i + 5] = 1;
   free(qacc);
 }
 

@@ -57,6 +57,8 @@ void rgo_forward(const rgo_model* m, rgo_data* d);    /* mj_forward (PID callbac
 void rgo_step(const rgo_model* m, rgo_data* d);       /* mj_step */
 /* SimulationInterface.step(): nsub x mj_step then mj_forward */
 void rgo_env_step(const rgo_model* m, rgo_data* d, int nsub);
+int rgo_pid_stride(const rgo_model* m);               /* userdata floats per actuator: 3 (PID) or 6 (model with a cascaded-PI actuator) */
+void rgo_set_casc_gravcomp(int on);                   /* experiment switch for tests/tools: bias-force compensation of the cascaded-PI law */
 /* spatial-tendon constants for mj_setConst: lengths and dense Jacobian at qpos */
 void rgo_tendon_eval(const rgo_model* m, rgo_data* d, const double* qpos, double* length, double* J);
 

@@ -177,6 +177,7 @@ struct RgModel {
   int ndoflevel;               /* depth levels of the dof tree */
   int ns;                      /* dofs in the constraint solver (<= nv) */
   int neqrow;                  /* rows of the active equality constraints */
+  int pidw;                    /* floats of controller state per actuator: 3 (PID), 6 when the model has a cascaded-PI actuator */
 };
 
 /* Offsets (in floats) of the per-warp scratch arrays; computed once on the host (rg_make_layout). */
@@ -234,6 +235,7 @@ struct RgModelDev {
   int ndoflevel;
   int ns;
   int neqrow;
+  int pidw;
   RgLayout L;                  /* per-warp scratch layout, kept next to the model so it is read with LDS too */
 };
 #define RG_MODEL_T RgModelDev

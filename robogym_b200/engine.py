@@ -165,7 +165,7 @@ class BatchedSim:
         self.qpos = torch.tensor(m["qpos0"], **f32).repeat(n, 1).contiguous()
         self.qvel = torch.zeros(n, m["nv"], **f32)
         self.ctrl = torch.zeros(n, m["nu"], **f32)
-        self.pid = torch.zeros(n, 3 * m["nu"], **f32)
+        self.pid = torch.zeros(n, modelblob.pid_stride(m) * m["nu"], **f32)
         self.qacc_warmstart = torch.zeros(n, m["nv"], **f32)
         self.time = torch.zeros(n, **f32)
         h = ctypes.c_void_p()

@@ -121,3 +121,13 @@ def unpack(blob):
             model[name] = np.frombuffer(blob, dtype="<f8", count=n, offset=off).copy()
             off += 8 * n
     return model
+
+
+def pid_stride(m):
+    """Floats of controller state per actuator in `userdata` / RG_FIELD_PID: 3 for mujoco-py's PID (integral, last error, last
+    derivative); 6 for every actuator of a model that has a cascaded-PI actuator (actuator_user[0] = 1: position-loop integral,
+    last error, last derivative, velocity-loop integral, smoothed set-point, "a step has been taken" flag)."""
+    import numpy as np
+
+    casc = (np.asarray(m["actuator_user0"]).reshape(-1) == 1.0) & (np.asarray(m["actuator_biastype"]).reshape(-1) == 3)
+    return 6 if m["nu"] and bool(casc.any()) else 3

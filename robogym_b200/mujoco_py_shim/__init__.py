@@ -317,7 +317,7 @@ class MjSim:
                 self._rg_pushed[k] = np.array(cur, copy=True)
         d = self._rg_data
         nu = m["nu"]
-        self._rg_engine.push_state(d.qpos, d.qvel, d.ctrl, d.userdata[:3 * nu], d.qacc_warmstart, d.xfrc_applied)
+        self._rg_engine.push_state(d.qpos, d.qvel, d.ctrl, d.userdata[:modelblob.pid_stride(m) * nu], d.qacc_warmstart, d.xfrc_applied)
         if len(d.mocap_pos):
             self._rg_engine.push_mocap(d.mocap_pos, d.mocap_quat)
 
@@ -325,8 +325,9 @@ class MjSim:
         d, m = self._rg_data, self._rg_model._m
         out = self._rg_engine.pull()
         d.qpos[:] = out["qpos"]; d.qvel[:] = out["qvel"]; d.qacc[:] = out["qacc"]; d.qacc_warmstart[:] = out["warm"]
-        if len(d.userdata) >= 3 * m["nu"]:
-            d.userdata[:3 * m["nu"]] = out["pid"]
+        npid = modelblob.pid_stride(m) * m["nu"]
+        if len(d.userdata) >= npid:
+            d.userdata[:npid] = out["pid"]
         d.site_xpos[:] = out["site_xpos"].reshape(-1, 3); d.body_xpos[:] = out["body_xpos"].reshape(-1, 3)
         d.body_xquat[:] = out["body_xquat"].reshape(-1, 4); d.geom_xpos[:] = out["geom_xpos"].reshape(-1, 3)
         d.actuator_force[:] = out["act_force"]
@@ -401,7 +402,7 @@ class _Cymj:
     def set_pid_control(model, data):
         """robogym/mujoco/simulation_interface.py:86-88.  Zeroes the PID state and enables the PID bias path."""
         m = model._m
-        if m["nuserdata"] < 3 * m["nu"]:
+        if m["nuserdata"] < modelblob.pid_stride(m) * m["nu"]:
             raise MujocoException("nuserdata is too small for the PID controller state")
         data.userdata[:] = 0
         m["opt_pid"][0] = 1

@@ -20,7 +20,7 @@ def lib():
         L.rge_create_ex.restype = ctypes.c_void_p
         L.rge_create_ex.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.rge_destroy.argtypes = [ctypes.c_void_p]
-        for f in ("rge_dbg_size", "rge_scratch_floats", "rge_small_bytes", "rge_ncon"):
+        for f in ("rge_dbg_size", "rge_scratch_floats", "rge_small_bytes", "rge_ncon", "rge_pidw"):
             getattr(L, f).argtypes = [ctypes.c_void_p]
         L.rge_name2id.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_char_p]
         L.rge_model_field.restype = ctypes.c_void_p
@@ -51,7 +51,7 @@ class EmuBatch:
         self.qpos = np.zeros((nenv, dims["nq"]), f)
         self.qvel = np.zeros((nenv, dims["nv"]), f)
         self.ctrl = np.zeros((nenv, dims["nu"]), f)
-        self.pid = np.zeros((nenv, 3 * dims["nu"]), f)
+        self.pid = np.zeros((nenv, lib().rge_pidw(self.h) * dims["nu"]), f)
         self.warm = np.zeros((nenv, dims["nv"]), f)
         self.time = np.zeros(nenv, f)
         self.xfrc = None

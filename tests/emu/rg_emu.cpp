@@ -26,6 +26,7 @@ void* rge_create_ex(const void* blob, size_t len, int ncon, int nel, int tile) {
 }
 void* rge_create(const void* blob, size_t len) { return rge_create_ex(blob, len, 0, 0, 0); }
 int rge_ncon(void* hv) { return ((RgeHandle*)hv)->L.ncon; }
+int rge_pidw(void* hv) { return ((RgeHandle*)hv)->hm.view.pidw; }
 /* the blob's name tables as parsed by the shared host loader (what rg_model_name2id serves) */
 int rge_name2id(void* hv, const char* typ, const char* name) {
   RgeHandle* h = (RgeHandle*)hv;

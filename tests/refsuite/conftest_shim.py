@@ -16,11 +16,10 @@ if os.environ.get("RG_SHIM_ENGINE", "oracle") == "oracle":
 
     shim.set_engine_factory(OracleEngine)
 
-# The UR16e's default joint calibration drives the arm with mujoco-py's cascaded-PI controller, whose law (mjpid.pyx) is not
-# in the reference tree; the engines refuse such models.  The reference ships a second calibration, "pid"
-# (robogym/robot/robot_interface.py:61-63), which uses the PID controller this repository implements: the rearrange test files
-# are run with that as the default.
-if os.environ.get("RG_REFSUITE_ARM_CALIBRATION", "pid") == "pid":
+# The UR16e's default joint calibration drives the arm with mujoco-py's cascaded-PI controller (robogym/robot/robot_interface.py:61-63):
+# the reference's tests run with that default, untouched.  RG_REFSUITE_ARM_CALIBRATION=pid forces the reference's second calibration
+# (plain PID) instead -- used once by tests/test_reference_suite.py to show that the impulse-response fixture tells the two apart.
+if os.environ.get("RG_REFSUITE_ARM_CALIBRATION", "default") == "pid":
     import attr  # noqa: E402
     import robogym.robot.ur16e.mujoco.simulation.base as _arm_sim  # noqa: E402
 

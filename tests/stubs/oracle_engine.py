@@ -3,6 +3,7 @@ Lets the CPU-only tier drive unmodified robogym envs through the shim (the produ
 import numpy as np
 
 from oracle import pyoracle
+from robogym_b200 import modelblob
 
 
 class OracleEngine:
@@ -11,13 +12,14 @@ class OracleEngine:
         self.om = pyoracle.OracleModel(cm.blob())
         self.d = pyoracle.OracleData(self.om)
         self.nu = cm.m["nu"]
+        self.npid = modelblob.pid_stride(cm.m) * self.nu
 
     def push_model(self, name, arr):
         self.om.field(name)[:] = np.asarray(arr).reshape(-1)
 
     def push_state(self, qpos, qvel, ctrl, pid, warm, xfrc):
         d = self.d
-        d.qpos[:] = qpos; d.qvel[:] = qvel; d.ctrl[:] = ctrl; d.userdata[:3 * self.nu] = pid
+        d.qpos[:] = qpos; d.qvel[:] = qvel; d.ctrl[:] = ctrl; d.userdata[:self.npid] = pid
         d.qacc_warmstart[:] = warm; d.xfrc_applied[:] = np.asarray(xfrc).reshape(-1)
 
     def push_mocap(self, pos, quat):
@@ -37,7 +39,7 @@ class OracleEngine:
         xq = d.xquat.copy()
         cv, xp = d.cvel.reshape(-1, 6), d.xpos.reshape(-1, 3)          # [w, v at the world origin] -> velocity of the body frame
         xvel = np.concatenate([cv[:, :3], cv[:, 3:] + np.cross(cv[:, :3], xp)], axis=1)
-        return dict(qpos=d.qpos.copy(), qvel=d.qvel.copy(), pid=d.userdata[:3 * self.nu].copy(), warm=d.qacc_warmstart.copy(),
+        return dict(qpos=d.qpos.copy(), qvel=d.qvel.copy(), pid=d.userdata[:self.npid].copy(), warm=d.qacc_warmstart.copy(),
                     site_xpos=d.site_xpos.copy(), body_xpos=d.xpos.copy(), body_xquat=xq, geom_xpos=d.geom_xpos.copy(),
                     act_force=d.actuator_force.copy(), qacc=d.qacc.copy(), ncon=ncon, contact=contact, warn=int(d.warning[0]), body_xvel=xvel,
                     sensordata=d.sensordata[:self.cm.m["nsensordata"]].copy())

@@ -72,7 +72,7 @@ def test_unsupported_features_are_refused(locked_blob):
     for edit, ok in ((lambda m: add_eq(m, 0, 0, tip), False),                                  # connect
                      (lambda m: add_eq(m, 1, 0, tip), True),                                   # weld world <-> fingertip: 6 dofs
                      (lambda m: add_eq(m, 1, names["body"].index("robot0:thdistal"), tip), False),    # thumb tip <-> fingertip: 11 dofs
-                     (lambda m: m["actuator_user0"].__setitem__(0, 1.0), False)):                       # mujoco-py's cascaded-PI controller
+                     (lambda m: m["actuator_user0"].__setitem__(0, 1.0), True)):                        # mujoco-py's cascaded-PI controller
         m = modelblob.unpack(locked_blob)
         edit(m)
         blob = modelblob.pack(m, names)

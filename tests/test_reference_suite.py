@@ -30,19 +30,20 @@ CASES = [
     ("robogym/randomization/tests/test_randomization.py", None, 4),
     # the other tests of this file reset the full Rubik's cube env, which needs the real pycuber package
     ("robogym/wrappers/tests/test_randomizations.py", "randomize_obs_wrapper or replace_cube_obs_vision_wrapper", 2),
-    # ---- rearrange (BASELINE configs[3]): the reference's environments on the shim, dual-sim MOCAP_IK controller included.
-    # Run with the reference's "pid" arm calibration (tests/refsuite/conftest_shim.py): the default "cascaded_pi" controller's
-    # law is not in the reference tree and the engines refuse such models.  Not selected:
-    # rendering (hide_geoms), and test_mocap_ik_impulse_response, whose expected displacements belong to the cascaded-PI arm.
+    # ---- rearrange (BASELINE configs[3]): the reference's environments on the shim, dual-sim MOCAP_IK controller included, with
+    # the reference's default arm calibration: mujoco-py's cascaded-PI controller (restated in oracle / kernel, tests/test_cascaded_pi.py).
+    # test_mocap_ik_impulse_response holds the reference's recorded numbers for that controller + the mocap weld + the two-sim
+    # loop (tool displacement 0.036 / 0.0363 / 0.022 / 0.022 +- 1e-3, 90 % rise within 5 / 12 steps): it PINS the restated law.
+    # Not selected: rendering (hide_geoms).
     ("robogym/envs/rearrange/tests/test_robot_polymorphism.py", None, 7),
     ("robogym/envs/rearrange/tests/test_placement.py", "not ycb", 4),
-    ("robogym/envs/rearrange/tests/test_rearrange_sim.py", "not impulse and not hide_geoms", 6),
+    ("robogym/envs/rearrange/tests/test_rearrange_sim.py", "not hide_geoms", 10),
     ("robogym/envs/rearrange/tests/test_multi_goals_env.py", None, 6),
     ("robogym/envs/rearrange/tests/test_object_creation.py", None, 3),
     ("robogym/envs/rearrange/tests/test_goal_generation.py", None, 6),
     # Also green on the shim but too slow for this tier with the dense fp64 oracle as the engine (run by hand, same command):
     # test_placement.py -k ycb (8 tests, 32 YCB objects = 200 dofs: 20 min), test_object_rotation.py (12 tests, 6 min),
-    # test_rearrange_envs.py (20 of 30: the rest need the holdout configs' full Jsonnet, numpy < 2 (`np.Inf`), or the cascaded-PI arm).
+    # test_rearrange_envs.py (the rest need the holdout configs' full Jsonnet or numpy < 2 (`np.Inf`)).
 ]
 
 
@@ -57,3 +58,13 @@ def test_reference_test_file_passes_on_the_shim(path, kexpr, npass, tmp_path):
     tail = out.stdout[-2000:] + out.stderr[-1000:]
     assert out.returncode == 0, tail
     assert f"{npass} passed" in out.stdout, tail
+
+
+def test_impulse_response_fixture_tells_the_controllers_apart(tmp_path):
+    """The same reference fixture run with the reference's OTHER calibration (plain PID) fails: the recorded displacements
+    belong to the cascaded-PI law, so passing them (above) is evidence for the restatement, not a loose threshold."""
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "refsuite"), RG_SHIM_ENGINE="oracle", RG_REFSUITE_ARM_CALIBRATION="pid")
+    cmd = [sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-p", "conftest_shim", f"--rootdir={tmp_path}",
+           os.path.join(REF, "robogym/envs/rearrange/tests/test_rearrange_sim.py"), "-k", "impulse"]
+    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode != 0 and " failed" in out.stdout, out.stdout[-2000:]

@@ -337,3 +337,40 @@ MOCAP_ARM = """
   </actuator>
 </mujoco>
 """
+
+
+# A 3-joint arm driven the way the UR16e's default calibration drives its joints: mujoco-py's cascaded-PI user controller
+# (user="1", 10 gain parameters; robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/joint_actuations.xml:4-10)
+# on light joints (cascaded_pi/ur16e_ik_class.xml: damping / armature / frictionloss 0.01), plus a plain-PID gripper actuator
+# (gripper_actuators.xml:7) in the same model, so both user controllers share one userdata block.
+CASCADED_ARM = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.001" iterations="30" tolerance="1e-10"/>
+  <size nuserdata="100" njmax="200" nconmax="20" nuser_actuator="16"/>
+  <worldbody>
+    <body name="base" pos="0 0 0.5">
+      <joint name="J1" type="hinge" axis="0 0 1" damping="0.01" armature="0.01" frictionloss="0.01"/>
+      <geom name="g_base" type="capsule" fromto="0 0 0 0.3 0 0" size="0.04" density="800" contype="0" conaffinity="0"/>
+      <body name="upper" pos="0.3 0 0">
+        <joint name="J2" type="hinge" axis="0 1 0" damping="0.01" armature="0.01" frictionloss="0.01" limited="true" range="-3 3"/>
+        <geom name="g_upper" type="capsule" fromto="0 0 0 0.25 0 0" size="0.03" density="800" contype="0" conaffinity="0"/>
+        <body name="fore" pos="0.25 0 0">
+          <joint name="J3" type="hinge" axis="0 1 0" damping="0.01" armature="0.01" frictionloss="0.01"/>
+          <geom name="g_fore" type="capsule" fromto="0 0 0 0.2 0 0" size="0.02" density="800" contype="0" conaffinity="0"/>
+          <body name="finger" pos="0.2 0 0">
+            <joint name="grip" type="slide" axis="0 1 0" damping="2" armature="0.001" limited="true" range="-0.045 0.001"/>
+            <geom name="g_finger" type="box" size="0.03 0.02 0.03" density="2000" contype="0" conaffinity="0"/>
+          </body>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <actuator>
+    <general gaintype="user" biastype="user" name="A1" joint="J1" ctrlrange="-6.1959 6.1959" forcerange="-330 330" gainprm="12 0 0 0 0 70 .05 1.0 .97 2.094" user="1"/>
+    <general gaintype="user" biastype="user" name="A2" joint="J2" ctrlrange="-2.8 2.8" forcerange="-150 150" gainprm="12 0.5 0.05 0.01 0.3 10 .10 1.5 .97 3.142" user="1"/>
+    <general gaintype="user" biastype="user" name="A3" joint="J3" ctrlrange="-6.1959 6.1959" forcerange="-56 56" gainprm="12 0 0 0 0 20 0 0 .97 3.142" user="1"/>
+    <general gaintype="user" biastype="user" name="AG" joint="grip" ctrllimited="true" ctrlrange="-.04473 0" forcelimited="true" forcerange="-230 230" gainprm="2000 1000.0 .2 0.005 0.1 0.00"/>
+  </actuator>
+</mujoco>
+"""

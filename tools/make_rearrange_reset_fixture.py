@@ -1,7 +1,7 @@
 """Generate tests/golden/rearrange_reset.json + robogym_b200/assets/rearrange_blocks5_env.rgm (build container only).
 
-Runs the UNMODIFIED reference environment `robogym.envs.rearrange.blocks_train.make_env` (dual-sim MOCAP_IK controller, PID arm
-calibration) on the mujoco_py shim with the fp64 oracle as the engine -- exactly the example of the reference's documentation
+Runs the UNMODIFIED reference environment `robogym.envs.rearrange.blocks_train.make_env` (dual-sim MOCAP_IK controller, the default
+cascaded-PI arm calibration) on the mujoco_py shim with the fp64 oracle as the engine -- exactly the example of the reference's documentation
 (docs/env_param_interface.md:12-38), whose printed observation holds the only real-MuJoCo numbers of this scene:
 block heights 0.51167315.  `stabilize_objects` (robogym/envs/rearrange/common/utils.py:76-92: object damping 1e-3, then 100
 env-steps = 2000 mj_steps + a forward after every 20) is where that number is produced, so the fixture is the simulator state
@@ -24,6 +24,7 @@ for p in (os.path.join(ROOT, "tests", "stubs"), REF, ROOT):
 
 def main():
     import robogym_b200.mujoco_py_shim as shim
+    from robogym_b200 import modelblob
 
     shim.install()
     from oracle_engine import OracleEngine
@@ -41,7 +42,7 @@ def main():
         sim.set_object_damping(1e-3)
         nu = m.nu
         cap.update(blob=m._cm.blob(), names=m._cm.names, nsub=int(sim.mj_sim.nsubsteps), nsteps=int(n_steps),
-                   qpos=d.qpos.copy(), qvel=d.qvel.copy(), ctrl=d.ctrl.copy(), pid=d.userdata[:3 * nu].copy(), warm=d.qacc_warmstart.copy(),
+                   qpos=d.qpos.copy(), qvel=d.qvel.copy(), ctrl=d.ctrl.copy(), pid=d.userdata[:modelblob.pid_stride(m._m) * nu].copy(), warm=d.qacc_warmstart.copy(),
                    mocap_pos=d.mocap_pos.copy(), mocap_quat=d.mocap_quat.copy(),
                    obj_qposadr=[int(m.get_joint_qpos_addr(f"object{i}:joint")[0]) for i in range(sim.num_objects)])
         sim.set_object_damping(damping)          # hand the simulation back untouched, then let the reference do its thing
@@ -51,8 +52,7 @@ def main():
     base.stabilize_objects = spy
     from robogym.envs.rearrange.blocks_train import make_env
 
-    env = make_env(parameters={"simulation_params": {"num_objects": 5, "max_num_objects": 8},
-                               "robot_control_params": {"arm_joint_calibration_path": "pid"}})
+    env = make_env(parameters={"simulation_params": {"num_objects": 5, "max_num_objects": 8}})
     obs = env.reset()
     z_obs = [float(obs["obj_pos"][i][2]) for i in range(5)]
     out = {k: np.asarray(cap[k]).tolist() for k in ("qpos", "qvel", "ctrl", "pid", "warm", "mocap_pos", "mocap_quat", "qpos_after")}
