@@ -185,7 +185,7 @@ RG_F(eq_data, neq * 7)
 RG_F(eq_solref, neq * 2)
 RG_F(eq_solimp, neq * 5)
 
-/* ---- sensors (mjtSensor: 0 touch, 8 jointpos are computed; 4 force / 5 torque are described only and read 0) ---- */
+/* ---- sensors (mjtSensor: 0 touch, 4 force, 5 torque, 8 jointpos) ---- */
 RG_I(sensor_type, nsensor)
 RG_I(sensor_objid, nsensor)
 RG_I(sensor_adr, nsensor)

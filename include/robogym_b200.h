@@ -73,7 +73,8 @@ enum rg_field {
   RG_FIELD_MOCAP_QUAT = 20,/* [nenv][nmocap*4]    in     (optional): data.mocap_quat */
   RG_FIELD_SENSORDATA = 21,/* [nenv][nsensordata] out    (optional): data.sensordata after the launch's last forward pass -- joint positions and
                               touch sensors (robogym/assets/xmls/robot/shadowhand/assets.xml:135-142); force / torque sensors
-                              (robogym/assets/xmls/robot/ur16e/base.xml:48-49) are described in the model but read 0 */
+                              (robogym/assets/xmls/robot/ur16e/base.xml:48-49): wrench between the site's body and its parent
+                              (cfrc_int of mj_rnePostConstraint), site frame */
   RG_NFIELDS = 22
 };
 #define RG_MAX_CONTACTS 32   /* DEFAULT contact capacity of a batch (rg_batch_create); rg_batch_create_ex picks another */

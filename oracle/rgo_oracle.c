@@ -974,14 +974,88 @@ static double ray_site(const double* pos, const double* mat, const double* size,
   }
   return x;
 }
-/* data.sensordata after mj_forward: joint positions and touch sensors (the 5 fingertip pads of the hand,
+/* force (normal, 2 tangential) and torque (torsional, 2 rolling) of contact c in its own frame, from the solver's rows */
+static void contact_wrench(const rgo_model* m, const rgo_data* d, int c, double* F) {
+  const double* con = d->contact + RGO_CON_STRIDE * c;
+  for (int k = 0; k < 6; k++) F[k] = 0;
+  int seen = 0;
+  for (int r = 0; r < d->nefc; r++) {
+    if (d->efc_id[r] != c) continue;
+    if (d->efc_type[r] == ROW_CONTACT_ELL || d->efc_type[r] == ROW_CONTACT_ELLF) F[seen++] = d->efc_force[r];
+    else if (d->efc_type[r] == ROW_CONTACT) {
+      int dim = (int)con[19];
+      if (dim == 1) { F[0] = d->efc_force[r]; continue; }
+      int k = 1 + seen / 2, sgn = seen & 1;          /* pyramid edges: direction k, + then - */
+      double mu = con[14 + k - 1];
+      F[0] += d->efc_force[r];
+      F[k] += (sgn == 0 ? mu : -mu) * d->efc_force[r];
+      seen++;
+    }
+  }
+}
+
+/* mj_rnePostConstraint for one body: the wrench its parent transmits to the subtree rooted at `body`
+   (cfrc_int = sum over the subtree of I a + v x* I v - external wrench, with xfrc_applied and the contact forces as the
+   external part; a(world) = -gravity), as [torque about the world origin, force] in world axes */
+static void subtree_wrench(const rgo_model* m, const rgo_data* d, int body, double* W) {
+  int nb = m->nbody;
+  double* A = (double*)calloc((size_t)6 * nb, sizeof(double));
+  char* in = (char*)calloc(nb, 1);
+  if (!(m->opt_disableflags[0] & DSBL_GRAVITY)) { A[3] = -m->opt_gravity[0]; A[4] = -m->opt_gravity[1]; A[5] = -m->opt_gravity[2]; }
+  for (int k = 0; k < 6; k++) W[k] = 0;
+  for (int b = 1; b < nb; b++) {
+    double* Ab = A + 6 * b;
+    memcpy(Ab, A + 6 * m->body_parentid[b], 6 * sizeof(double));
+    for (int k = 0; k < m->body_dofnum[b]; k++) {
+      int dof = m->body_dofadr[b] + k;
+      for (int i = 0; i < 6; i++) Ab[i] += d->dof_Sdot[6 * dof + i] * d->qvel[dof] + d->dof_S[6 * dof + i] * d->qacc[dof];
+    }
+    in[b] = b == body || in[m->body_parentid[b]];
+    if (!in[b]) continue;
+    double F[6], H[6], G[6];
+    inertia_mul(F, d->body_I10 + 10 * b, Ab);
+    inertia_mul(H, d->body_I10 + 10 * b, d->cvel + 6 * b);
+    cross_force(G, d->cvel + 6 * b, H);
+    for (int i = 0; i < 6; i++) W[i] += F[i] + G[i];
+    const double* x = d->xfrc_applied + 6 * b;   /* force, torque at the body's centre of mass */
+    double t[3];
+    cross3(t, d->xipos + 3 * b, x);
+    for (int i = 0; i < 3; i++) { W[i] -= x[3 + i] + t[i]; W[3 + i] -= x[i]; }
+  }
+  for (int c = 0; c < d->ncon; c++) {
+    const double* con = d->contact + RGO_CON_STRIDE * c;
+    int b1 = m->geom_bodyid[(int)con[20]], b2 = m->geom_bodyid[(int)con[21]];
+    if (in[b1] == in[b2]) continue;              /* outside, or internal to the subtree */
+    double F[6], f[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, t[3];
+    contact_wrench(m, d, c, F);
+    for (int k = 0; k < 3; k++)
+      for (int i = 0; i < 3; i++) { f[i] += F[k] * con[4 + 3 * k + i]; tq[i] += F[3 + k] * con[4 + 3 * k + i]; }
+    double sgn = in[b2] ? 1 : -1;                /* the contact force acts on geom2's body, its opposite on geom1's */
+    cross3(t, con + 1, f);
+    for (int i = 0; i < 3; i++) { W[i] -= sgn * (tq[i] + t[i]); W[3 + i] -= sgn * f[i]; }
+  }
+  free(A); free(in);
+}
+
+/* data.sensordata after mj_forward: joint positions, touch sensors (the 5 fingertip pads of the hand,
    robogym/assets/xmls/robot/shadowhand/assets.xml:135-142: normal forces of the contacts on the site's body whose point --
-   or the ray from it along the contact normal -- lies in the site's volume).  Force / torque sensors (base.xml:48-49) read 0. */
+   or the ray from it along the contact normal -- lies in the site's volume), and the force / torque sensors of the UR16e's
+   tool flange (robogym/assets/xmls/robot/ur16e/base.xml:48-49, read by robogym/robot/ur16e/mujoco/joint_controlled_arm.py:35-45):
+   the wrench between the site's body and its parent, in the site's frame, the torque taken about the site. */
 static void rgo_sensors(const rgo_model* m, rgo_data* d) {
   for (int i = 0; i < m->nsensor; i++) {
     int adr = m->sensor_adr[i], obj = m->sensor_objid[i];
     for (int k = 0; k < m->sensor_dim[i]; k++) d->sensordata[adr + k] = 0;
     if (m->sensor_type[i] == 8) d->sensordata[adr] = d->qpos[m->jnt_qposadr[obj]];
+    if (m->sensor_type[i] == 4 || m->sensor_type[i] == 5) {
+      double W[6], t[3];
+      subtree_wrench(m, d, m->site_bodyid[obj], W);
+      if (m->sensor_type[i] == 5) {            /* torque about the site instead of the world origin */
+        cross3(t, d->site_xpos + 3 * obj, W + 3);
+        for (int k = 0; k < 3; k++) W[k] -= t[k];
+      }
+      mulmatT3(d->sensordata + adr, d->site_xmat + 9 * obj, m->sensor_type[i] == 4 ? W + 3 : W);
+    }
     if (m->sensor_type[i] != 0) continue;
     int body = m->site_bodyid[obj];
     for (int c = 0; c < d->ncon; c++) {

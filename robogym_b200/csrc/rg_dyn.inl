@@ -211,38 +211,41 @@ RG_DEV_NOINLINE void rg_kinematics(const RgCtx c) {
 }
 
 /* ---------------------------------------------------------------- S2/S5 inertias + mass matrix */
+/* spatial inertia of body b about its tree's reference point, world axes: mass, m c, then the 6 second moments (xx yy zz xy xz yz) */
+RG_DEV void rg_body_inertia10(const RgCtx c, int b, float* I) {
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
+  float q[4], R[9];
+  rg_quat_mul(q, s + L.xquat + 4 * b, m.body_iquat + 4 * b);
+  rg_quat2mat(R, q);
+  const float* di = m.body_inertia + 3 * b;
+  const float mass = m.body_mass[b];
+  float cm[3];
+  rg_body_xipos(c, b, cm);
+  rg_sub3(cm, cm, rg_body_ref(c, b));
+  float Ic[6]; /* xx yy zz xy xz yz */
+  Ic[0] = R[0] * R[0] * di[0] + R[1] * R[1] * di[1] + R[2] * R[2] * di[2];
+  Ic[1] = R[3] * R[3] * di[0] + R[4] * R[4] * di[1] + R[5] * R[5] * di[2];
+  Ic[2] = R[6] * R[6] * di[0] + R[7] * R[7] * di[1] + R[8] * R[8] * di[2];
+  Ic[3] = R[0] * R[3] * di[0] + R[1] * R[4] * di[1] + R[2] * R[5] * di[2];
+  Ic[4] = R[0] * R[6] * di[0] + R[1] * R[7] * di[1] + R[2] * R[8] * di[2];
+  Ic[5] = R[3] * R[6] * di[0] + R[4] * R[7] * di[1] + R[5] * R[8] * di[2];
+  const float cc = rg_dot3(cm, cm);
+  I[0] = mass;
+  I[1] = mass * cm[0]; I[2] = mass * cm[1]; I[3] = mass * cm[2];
+  I[4] = Ic[0] + mass * (cc - cm[0] * cm[0]);
+  I[5] = Ic[1] + mass * (cc - cm[1] * cm[1]);
+  I[6] = Ic[2] + mass * (cc - cm[2] * cm[2]);
+  I[7] = Ic[3] - mass * cm[0] * cm[1];
+  I[8] = Ic[4] - mass * cm[0] * cm[2];
+  I[9] = Ic[5] - mass * cm[1] * cm[2];
+}
+
 RG_DEV_NOINLINE void rg_massmatrix(const RgCtx c) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
   const int nv = m.nv;
   RG_PHASE_BEGIN
-  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) {
-    float* I = s + L.I10 + 10 * b;
-    float q[4], R[9];
-    rg_quat_mul(q, s + L.xquat + 4 * b, m.body_iquat + 4 * b);
-    rg_quat2mat(R, q);
-    const float* di = m.body_inertia + 3 * b;
-    const float mass = m.body_mass[b];
-    float cm[3];
-    rg_body_xipos(c, b, cm);
-    rg_sub3(cm, cm, rg_body_ref(c, b));
-    float Ic[6]; /* xx yy zz xy xz yz */
-    Ic[0] = R[0] * R[0] * di[0] + R[1] * R[1] * di[1] + R[2] * R[2] * di[2];
-    Ic[1] = R[3] * R[3] * di[0] + R[4] * R[4] * di[1] + R[5] * R[5] * di[2];
-    Ic[2] = R[6] * R[6] * di[0] + R[7] * R[7] * di[1] + R[8] * R[8] * di[2];
-    Ic[3] = R[0] * R[3] * di[0] + R[1] * R[4] * di[1] + R[2] * R[5] * di[2];
-    Ic[4] = R[0] * R[6] * di[0] + R[1] * R[7] * di[1] + R[2] * R[8] * di[2];
-    Ic[5] = R[3] * R[6] * di[0] + R[4] * R[7] * di[1] + R[5] * R[8] * di[2];
-    const float cc = rg_dot3(cm, cm);
-    I[0] = mass;
-    I[1] = mass * cm[0]; I[2] = mass * cm[1]; I[3] = mass * cm[2];
-    I[4] = Ic[0] + mass * (cc - cm[0] * cm[0]);
-    I[5] = Ic[1] + mass * (cc - cm[1] * cm[1]);
-    I[6] = Ic[2] + mass * (cc - cm[2] * cm[2]);
-    I[7] = Ic[3] - mass * cm[0] * cm[1];
-    I[8] = Ic[4] - mass * cm[0] * cm[2];
-    I[9] = Ic[5] - mass * cm[1] * cm[2];
-  }
+  RG_NOUNROLL for (int b = lane; b < m.nbody; b += 32) rg_body_inertia10(c, b, s + L.I10 + 10 * b);
   RG_PHASE_END
   /* composite inertias: subtree(b) is the contiguous id range [b, b+size) */
   RG_PHASE_BEGIN

@@ -18,7 +18,7 @@ struct RgBatchIO {
   const float* mocap_quat;  /* [nenv][nmocap*4] data.mocap_quat or nullptr */
   /* derived outputs (any may be nullptr) */
   float* site_xpos; float* body_xpos; float* body_xquat; float* geom_xpos; float* act_force; float* qacc;
-  float* sensordata;        /* [nenv][nsensordata] data.sensordata after the last forward pass (joint positions, touch; force / torque read 0) */
+  float* sensordata;        /* [nenv][nsensordata] data.sensordata after the last forward pass (joint positions, touch, force / torque) */
   float* body_xvel;         /* [nenv][nbody][6]: angular then linear velocity of the body frame, world axes (data.get_body_xvelr / get_body_xvelp) */
   float* contact;           /* [nenv][contact capacity][4] = geom1, geom2, dist, dim */
   int* ncon; int* warn;
@@ -158,6 +158,70 @@ RG_DEV_NOINLINE float rg_ray_site(const float* pos, const float* quat, const flo
 }
 /* one lane per sensor: joint position, or the normal forces of the contacts on the site's body whose point (or the ray from it
    along the contact normal) lies in the site's volume (mjSENS_TOUCH; robogym/assets/xmls/robot/shadowhand/assets.xml:135-142) */
+/* mj_rnePostConstraint for one body: the wrench its parent transmits to the subtree rooted at `body` (cfrc_int: sum over the
+   subtree of I a + v x* I v minus the external wrench -- xfrc_applied and the contact forces; the world accelerates with
+   -gravity), as [torque about the tree's reference point, force] in world axes.  One lane walks the subtree: it runs once
+   per launch, for the two sensors of the UR16e tool flange (robogym/assets/xmls/robot/ur16e/base.xml:48-49). */
+RG_DEV_NOINLINE void rg_subtree_wrench(const RgCtx c, int body, float* W) {
+  const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
+  const int end = body + m.body_subtreesize[body];
+  const float* ref = rg_body_ref(c, body);
+  for (int k = 0; k < 6; k++) W[k] = 0.0f;
+  RG_NOUNROLL for (int b = body; b < end; b++) {
+    float V[6] = {0, 0, 0, 0, 0, 0}, Vs[6] = {0, 0, 0, 0, 0, 0}, A[6] = {0, 0, 0, 0, 0, 0};
+    if (!(m.opt_disableflags[0] & RG_DSBL_GRAVITY)) { A[3] = -m.opt_gravity[0]; A[4] = -m.opt_gravity[1]; A[5] = -m.opt_gravity[2]; }
+    int rot0 = -1, rot1 = -1;   /* rotational dofs of the ball / free joint being walked: their axes turn with the velocity before them */
+    RG_NOUNROLL for (int w = 0; w < m.nmaskw; w++) {
+      unsigned bits = (unsigned)m.body_dofmask[b * m.nmaskw + w];
+      while (bits) {           /* ascending dof ids = root to leaf */
+        const int d = 32 * w + rg_ctz(bits);
+        bits &= bits - 1;
+        if (d >= rot1) {
+          const int j = m.dof_jntid[d], jt = m.jnt_type[j], j0 = m.jnt_dofadr[j];
+          if (jt == RG_JNT_BALL) { rot0 = j0; rot1 = j0 + 3; }
+          else if (jt == RG_JNT_FREE) { rot0 = j0 + 3; rot1 = j0 + 6; }
+          else rot0 = rot1 = -1;
+        }
+        if (d == rot0) for (int k = 0; k < 6; k++) Vs[k] = V[k];
+        const float* Sd = s + L.S + 6 * d;
+        float Sp[6];
+        rg_cross_motion(Sp, (d >= rot0 && d < rot1) ? Vs : V, Sd);
+        const float qd = s[L.qvel + d], qa = s[L.qacc + d];
+        for (int k = 0; k < 6; k++) { A[k] += Sp[k] * qd + Sd[k] * qa; V[k] += Sd[k] * qd; }
+      }
+    }
+    float I[10], F[6], H[6], G[6];
+    rg_body_inertia10(c, b, I);
+    rg_inertia_mul(F, I, A);
+    rg_inertia_mul(H, I, V);
+    rg_cross_force(G, V, H);
+    for (int k = 0; k < 6; k++) W[k] += F[k] + G[k];
+    if (c.xfrc) {              /* xfrc_applied: force, torque at the body's centre of mass */
+      const float* x = c.xfrc + 6 * b;
+      float xi[3], t[3];
+      rg_body_xipos(c, b, xi);
+      rg_sub3(xi, xi, ref);
+      rg_cross(t, xi, x);
+      for (int k = 0; k < 3; k++) { W[k] -= x[3 + k] + t[k]; W[3 + k] -= x[k]; }
+    }
+  }
+  const int ncon = RG_SI(c, RG_S_NCON);
+  RG_NOUNROLL for (int k = 0; k < ncon; k++) {
+    const float* r = s + L.con + RG_CON_STRIDE * k;
+    const int b1 = (int)r[18], b2 = (int)r[19], dim = (int)s[L.cprm + RG_CPRM * k + 1];
+    const int in1 = b1 >= body && b1 < end, in2 = b2 >= body && b2 < end;
+    if (in1 == in2 || dim == 0) continue;        /* outside, internal to the subtree, or not in the solver */
+    const float* F = s + L.cF + 6 * k;
+    float f[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, p[3], t[3];
+    for (int a = 0; a < 3 && a < dim; a++) for (int i = 0; i < 3; i++) f[i] += F[a] * r[4 + 3 * a + i];
+    for (int a = 3; a < dim; a++) for (int i = 0; i < 3; i++) tq[i] += F[a] * r[4 + 3 * (a - 3) + i];
+    const float sgn = in2 ? 1.0f : -1.0f;        /* the contact force acts on geom2's body, its opposite on geom1's */
+    rg_sub3(p, r + 1, ref);
+    rg_cross(t, p, f);
+    for (int i = 0; i < 3; i++) { W[i] -= sgn * (tq[i] + t[i]); W[3 + i] -= sgn * f[i]; }
+  }
+}
+
 RG_DEV_NOINLINE void rg_sensors(const RgCtx c, float* out) {
   RG_LANE_DECL
   const RG_MODEL_T& m = RG_MDEREF(c.mref); const RgLayout& L = RG_CL(c); float* s = RG_SCRATCH(c);
@@ -167,6 +231,21 @@ RG_DEV_NOINLINE void rg_sensors(const RgCtx c, float* out) {
     const int adr = m.sensor_adr[i], obj = m.sensor_objid[i], type = m.sensor_type[i];
     for (int k = 0; k < m.sensor_dim[i]; k++) out[adr + k] = 0.0f;
     if (type == 8) { const int j = obj, qa = m.jnt_qposadr[j]; out[adr] = s[L.qpos + qa]; }
+    if (type == 4 || type == 5) {   /* mjSENS_FORCE / mjSENS_TORQUE: the wrench between the site's body and its parent, in the site's frame */
+      const int body = m.site_bodyid[obj];
+      float W[6], sq[4], R[9], t[3], rel[3];
+      rg_subtree_wrench(c, body, W);
+      if (type == 5) {             /* torque about the site */
+        rg_sub3(rel, s + L.sxpos + 3 * obj, rg_body_ref(c, body));
+        rg_cross(t, rel, W + 3);
+        for (int k = 0; k < 3; k++) W[k] -= t[k];
+      }
+      rg_quat_mul(sq, s + L.xquat + 4 * body, m.site_quat + 4 * obj);
+      rg_quat_norm(sq);
+      rg_quat2mat(R, sq);
+      const float* v = type == 4 ? W + 3 : W;
+      for (int k = 0; k < 3; k++) out[adr + k] = R[k] * v[0] + R[3 + k] * v[1] + R[6 + k] * v[2];
+    }
     if (type != 0) continue;
     const int body = m.site_bodyid[obj];
     float sq[4], total = 0.0f;

@@ -1,7 +1,6 @@
 """data.sensordata (SURVEY 8a' S14 / 8b): joint-position and touch sensors.  The hand has five fingertip touch pads
 (robogym/assets/xmls/robot/shadowhand/assets.xml:135-142, capsule sites chain.xml:65,242); the UR16e scene adds joint
-position sensors (robogym/assets/xmls/robot/ur16e/base.xml:41-46).  Force / torque sensors are described in the model
-but read 0 (documented in include/robogym_b200.h)."""
+position sensors (robogym/assets/xmls/robot/ur16e/base.xml:41-46).  Force / torque sensors: tests/test_force_torque_sensors.py."""
 import numpy as np
 import pytest
 
