@@ -227,6 +227,46 @@ def cpu_baseline_rearrange(blob, names, seconds=10.0):
                       "(oracle/: dense, scalar -- NOT mujoco-py); one otherwise idle core"}
 
 
+def cpu_baseline_rearrange_tcp(blob, solver_blob, seconds=10.0):
+    """Single-thread timing of the fp64 CPU port on the dual-simulation rearrange loop: the same controller class on oracle-backed
+    stand-ins of its two simulations (tests/stubs/oracle_generic_sim.py: checker infrastructure, used here as the CPU arm only)."""
+    import numpy as np
+    import torch
+
+    from oracle import pyoracle
+
+    pyoracle.build()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "stubs"))
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    main, solver = OracleGenericSim(blob, 1, 40), OracleGenericSim(solver_blob, 1, 40)
+    ctl = BatchedTcpArmController(main, solver, max_position_change=0.1)
+    arm = np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0])
+    main.qpos[0, ctl.arm_qadr_main] = torch.tensor(arm)
+    main.ctrl[0, ctl.arm_act_main] = torch.tensor(arm)
+    jn = main.model.names["joint"]
+    for i in range(5):
+        a = int(main.model.host["jnt_qposadr"][jn.index("object%d:joint" % i)])
+        main.qpos[0, a:a + 3] = torch.tensor([1.2 + 0.13 * (i % 3), 0.5 + 0.16 * (i // 3), 0.453 + 0.03324 + 0.0254 + 0.001])
+    main.forward()
+    ctl.reset()
+    rng = np.random.RandomState(0)
+
+    def run(n):
+        t0 = time.perf_counter()
+        for _ in range(n):
+            ctl.step(torch.tensor(rng.uniform(-1, 1, (1, 6)).astype(np.float32)))
+        return time.perf_counter() - t0
+
+    probe = run(5)
+    n = max(5, int(seconds / (probe / 5)))
+    t = run(n)
+    return {"value": n / t, "unit": "env-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{n} env-steps (solver arm: forward + 40 substeps; main scene: 40 substeps + 2 forwards) of one rearrange env with 5 blocks, the GPU arm's "
+                      "workload, fp64 CPU port of the reference path (oracle/: dense, scalar -- NOT mujoco-py); one otherwise idle core"}
+
+
 _REF = {}
 
 
@@ -330,6 +370,12 @@ CONFIGS = {
     "rearrange_blocks": dict(asset="rearrange_blocks5", nenv=2048, caps=(64, 128, 16), nsub=20, workload="rearrange", nobj=5, grid=(3, 6, 1.20, 0.50, 0.13, 0.16),
                              label="rearrange/blocks (BASELINE.json configs[3]): UR16e + Robotiq 2f-85 driven through the mocap weld, 5 free "
                                    "blocks (condim 6, elliptic cones, impratio 10) on the table, nq43/nv38/nu1"),
+    # BASELINE.json configs[3] with the reference's own two-simulation control loop and 6-D tool actions
+    "rearrange_blocks_tcp": dict(asset="rearrange_blocks5_tcp", solver_asset="rearrange_solver_arm", nenv=2048, caps=(64, 160, 16), nsub=40, workload="rearrange_tcp", nobj=5,
+                                 grid=(3, 6, 1.20, 0.50, 0.13, 0.16),
+                                 label="rearrange/blocks (BASELINE.json configs[3], SURVEY 8(d) cfg 4): UR16e + Robotiq 2f-85 under the reference's dual-simulation "
+                                       "MOCAP_IK controller (solver arm with mocap weld nq8 -> joint targets -> main scene with cascaded-PI joint controllers, "
+                                       "5 free blocks, condim 6, elliptic cones, impratio 10), nq43/nv38/nu7"),
     # BASELINE.json configs[4]: the same world with 8 YCB objects (unions of 1..29 convex meshes each; one fixed draw of the eight)
     "rearrange_ycb": dict(asset="rearrange_ycb8", nenv=1024, caps=(64, 128, 16), nsub=20, workload="rearrange", nobj=8, grid=(3, 9, 1.25, 0.32, 0.27, 0.36),
                           label="rearrange/ycb (BASELINE.json configs[4]): UR16e + Robotiq 2f-85 driven through the mocap weld, 8 YCB mesh objects "
@@ -422,6 +468,9 @@ class Workload:
         self.reset(dropped)
         return dropped
 
+    def step_timed(self):
+        self.sim.step()
+
 
 class RearrangeWorkload:
     """BASELINE.json configs[3]: TCP control through the mocap weld.  Action a ~ U(-1,1)^4: the mocap target moves by
@@ -478,7 +527,8 @@ class RearrangeWorkload:
         self.hi = self.tcp_pos0[0] + torch.tensor([0.25, 0.45, 0.10], **f32)
         self.reset(torch.ones(N, dtype=torch.bool, device=dev))
 
-    def reset(self, mask):
+    def reset_blocks(self, mask):
+        """arm at its start pose, objects re-placed, velocities / controller state / warm start cleared -- for the masked environments"""
         t, sim = self.torch, self.sim
         N = sim.nenv
         q = self.q0.clone()
@@ -497,6 +547,11 @@ class RearrangeWorkload:
         sim.qvel.mul_((~mk).to(sim.qvel.dtype))
         sim.pid.mul_((~mk).to(sim.pid.dtype))
         sim.qacc_warmstart.mul_((~mk).to(sim.qvel.dtype))
+
+    def reset(self, mask):
+        t, sim = self.torch, self.sim
+        self.reset_blocks(mask)
+        mk = mask.unsqueeze(1)
         sim.ctrl.copy_(t.where(mk, self.ctrl_hi.expand_as(sim.ctrl), sim.ctrl))
         sim.mocap_pos[:, 0].copy_(t.where(mk, self.tcp_pos0, sim.mocap_pos[:, 0]))       # reset_mocap2body_xpos
         sim.mocap_quat[:, 0].copy_(t.where(mk, self.tcp_quat0, sim.mocap_quat[:, 0]))
@@ -509,6 +564,9 @@ class RearrangeWorkload:
     def sample_action(self):
         return self.torch.rand(self.sim.nenv, 4, device=self.dev, generator=self.gen) * 2 - 1
 
+    def step_timed(self):
+        self.sim.step()
+
     def on_palm(self):
         """healthy = every block still on (or above) the table"""
         z = self.torch.stack([self.sim.qpos[:, a + 2] for a in self.blocks], dim=1)
@@ -518,6 +576,60 @@ class RearrangeWorkload:
         lost = ~self.on_palm()
         self.reset(lost)
         return lost
+
+
+class RearrangeTcpWorkload(RearrangeWorkload):
+    """BASELINE.json configs[3] with the reference's own control loop: a ~ U(-1,1)^6 = tool translation (3) +
+    roll / yaw (2) + gripper (1) (ControlMode.TCP_ROLL_YAW, TcpSolverMode.MOCAP_IK, free_dof_tcp_arm.py:161-178).  TWO simulations
+    per environment, as robogym/robot/composite/ur_gripper_arm.py:104-150 builds them: the solver arm (mocap weld, 40 substeps of
+    0.001 s) turns the tool action into joint angles, the main scene (arm joints under mujoco-py's cascaded-PI controllers, 5
+    blocks, 40 substeps + 2 forwards) tracks them -- robogym_b200.rearrange_arm.BatchedTcpArmController, two launches per
+    env-step with the hand-off on the device."""
+
+    action_dim = 6
+
+    def __init__(self, sim, model, names, dev, gen, nobj, grid, solver_sim):
+        import numpy as np
+        import torch
+
+        from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+        self.torch, self.sim, self.gen, self.dev = torch, sim, gen, dev
+        self.solver = solver_sim
+        m = model.host
+        N = sim.nenv
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.nobj, self.grid = nobj, grid
+        self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(nobj)]
+        self.rest = torch.full((nobj,), 0.453 + 0.03324 + 0.0254 + 0.001, **f32)
+        self.ctl = BatchedTcpArmController(sim, solver_sim, max_position_change=0.1, reset_controller_error=True)
+        q0 = torch.tensor(m["qpos0"], **f32).repeat(N, 1)
+        q0[:, self.ctl.arm_qadr_main] = torch.tensor(np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0]), **f32)   # TABLETOP_EXPERIMENT_INITIAL_POS
+        self.q0 = q0
+        self.ctrl0 = torch.zeros(N, m["nu"], **f32)
+        self.ctrl0[:, self.ctl.arm_act_main] = q0[:, self.ctl.arm_qadr_main]
+        self.pending = None
+        self.reset(torch.ones(N, dtype=torch.bool, device=dev))
+        self.ctl.reset()
+
+    def reset(self, mask):
+        t, sim, sol = self.torch, self.sim, self.solver
+        RearrangeWorkload.reset_blocks(self, mask)
+        mk = mask.unsqueeze(1)
+        sim.ctrl.copy_(t.where(mk, self.ctrl0, sim.ctrl))
+        # the helper arm restarts with the main arm (JointControlledTcpArm.reset): joints re-synced every step anyway
+        keep = (~mk).to(sol.qvel.dtype)
+        sol.qvel.mul_(keep); sol.pid.mul_(keep); sol.qacc_warmstart.mul_(keep)
+        sol.qpos[:, self.ctl.arm_qadr_solver] = t.where(mk, sim.qpos[:, self.ctl.arm_qadr_main], sol.qpos[:, self.ctl.arm_qadr_solver])
+
+    def apply_action(self, a):
+        self.pending = a
+
+    def step_timed(self):
+        self.ctl.step(self.pending)
+
+    def sample_action(self):
+        return self.torch.rand(self.sim.nenv, 6, device=self.dev, generator=self.gen) * 2 - 1
 
 
 def run_gpu_arm(args):
@@ -552,20 +664,27 @@ def run_gpu_arm(args):
     if os.environ.get("RG_BENCH_CAPS"):        # experiments: "contacts,rows,dofs" (0 = engine default)
         caps = tuple(int(x) for x in os.environ["RG_BENCH_CAPS"].split(","))
     nsub = cfg.get("nsub", NSUB)
-    rearrange = cfg.get("workload") == "rearrange"
+    rearrange = cfg.get("workload") in ("rearrange", "rearrange_tcp")
+    tcp = cfg.get("workload") == "rearrange_tcp"
     sim = engine.BatchedSim(model, N, nsub, outputs=("site_xpos", "act_force", "ncon", "warn") + (("body_xpos", "body_xquat") if rearrange else ()),
                             contact_capacity=caps[0], row_capacity=caps[1], dofs_per_contact=caps[2])
     m = model.host
     nu, nq, nv = m["nu"], m["nq"], m["nv"]
     gen = torch.Generator(device=dev)
     gen.manual_seed(rank_seed(1234, rank))
-    wl = RearrangeWorkload(sim, model, names, dev, gen, cfg["nobj"], cfg["grid"]) if rearrange else Workload(sim, model, names, dev, gen)
+    solver = None
+    if tcp:
+        solver_model = engine.DeviceModel(load_blob(cfg["solver_asset"]), local)
+        solver = engine.BatchedSim(solver_model, N, nsub, outputs=("body_xpos", "body_xquat", "warn"))
+        wl = RearrangeTcpWorkload(sim, model, names, dev, gen, cfg["nobj"], cfg["grid"], solver)
+    else:
+        wl = RearrangeWorkload(sim, model, names, dev, gen, cfg["nobj"], cfg["grid"]) if rearrange else Workload(sim, model, names, dev, gen)
     nact = wl.action_dim
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
         wl.apply_action(wl.sample_action())
-        sim.step()
+        wl.step_timed()
         wl.auto_reset()
     torch.cuda.synchronize()
 
@@ -586,11 +705,11 @@ def run_gpu_arm(args):
         flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
         wl.apply_action(nxt)
         ev[k][0].record()
-        sim.step()
+        wl.step_timed()                                 # one launch (two for the dual-simulation rearrange loop, hand-off included)
         ev[k][1].record()
         ncon_sum += sim.ncon.double().mean()
         ncon_max = torch.maximum(ncon_max, sim.ncon.max())
-        warn |= sim.warn.max()
+        warn |= sim.warn.max() if solver is None else torch.maximum(sim.warn.max(), solver.warn.max())
         resets += wl.auto_reset().sum()                 # in-loop auto-reset (untimed torch ops, like the action sampling)
     torch.cuda.synchronize()
     if dist is not None:
@@ -624,7 +743,7 @@ def run_gpu_arm(args):
         flush.zero_()                                   # same cold L2 as the device-timed region (0.05 ms of memset, inside the timing)
         d_act.copy_(buf, non_blocking=True)             # H2D of this step's inputs
         wl.apply_action(d_act)
-        sim.step()
+        wl.step_timed()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
         h_v.copy_(sim.qvel, non_blocking=True)
         wl.auto_reset()                                 # the environment loop restarts dropped cubes (else steps get cheaper)
@@ -657,7 +776,9 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["label"] + (", batch %d per GPU, 20 substeps of 0.002 s + forward per env-step, a~U(-1,1)^4: mocap target += 0.01 a[:3] "
+            "config": {"workload": cfg["label"] + (", batch %d per GPU, per env-step: solver arm forward + 40 substeps of 0.001 s, main scene 40 substeps + 2 forwards, "
+                                                   "a~U(-1,1)^6 relative tool actions (max_position_change 0.1, arm_reset_controller_error); auto-reset of environments that lost an object" % N if tcp else
+                                                   ", batch %d per GPU, 20 substeps of 0.002 s + forward per env-step, a~U(-1,1)^4: mocap target += 0.01 a[:3] "
                                                    "(clipped to a box over the table), gripper target from a[3]; auto-reset of environments that lost an object" % N if rearrange else
                                                    ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
                                                    "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N),
@@ -667,12 +788,16 @@ def run_gpu_arm(args):
                        "mean_contacts": float(ncon_sum.item()) / args.steps, "max_contacts": int(ncon_max.item()), "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": N * nact * 4, "d2h_bytes_per_step": N * (nq + nv) * 4},
-            "gpu_launches": 2 * args.steps * world,   # per step: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch)
+            # per step and simulation: rg_step_kernel + rg_order_kernel (work-ordered schedule of the next launch); the dual-simulation
+            # loop also runs a forward of the solver arm (sync to the main arm) before its step
+            "gpu_launches": (5 if tcp else 2) * args.steps * world,
             "roofline": roof,
         }
         if world == 1:
             try:
-                if rearrange:
+                if tcp:
+                    line["cpu_baseline"] = cpu_baseline_rearrange_tcp(blob, load_blob(cfg["solver_asset"]), seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
+                elif rearrange:
                     line["cpu_baseline"] = cpu_baseline_rearrange(blob, names, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))
                 else:
                     line["cpu_baseline"] = cpu_baseline(blob, seconds=float(os.environ.get("RG_CPU_BASELINE_SECONDS", "10")))

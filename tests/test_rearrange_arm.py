@@ -1,0 +1,258 @@
+"""The batched dual-simulation arm controller (robogym_b200/rearrange_arm.py) beside the UNMODIFIED reference
+environment: `robogym.envs.rearrange.blocks.make_env` with ControlMode.TCP_ROLL_YAW + TcpSolverMode.MOCAP_IK (the mode SURVEY
+8(d) row 4 names: 3 tool translations + roll / yaw + gripper) runs on the mujoco_py shim with the oracle as engine; the batched
+controller runs on oracle-backed stand-ins of its two BatchedSims built from the SAME compiled models and started from the SAME
+states.  Both then take the same actions: every env-step must leave the same main-simulation and solver-simulation state
+(fp64 on both sides, so the comparison is tight -- any difference is a difference in the control logic).  The GPU test runs the
+controller on two real BatchedSims (CUDA) against the oracle stand-ins, teacher-forced."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("ROBOGYM_REFERENCE", "/root/reference")
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "robogym")), reason="needs /root/reference")
+for p in (os.path.join(HERE, "stubs"),):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+MAX_POSITION_CHANGE = float(np.float32(0.1))    # the reference stores the parameter as a float32
+ASSETS = os.path.join(HERE, "..", "robogym_b200", "assets")
+
+
+def _reference_env(reset_controller_error):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import robogym_b200.mujoco_py_shim as shim
+
+    shim.install()
+    from oracle_engine import OracleEngine
+
+    shim.set_engine_factory(OracleEngine)
+    from robogym.envs.rearrange.blocks import make_env
+    from robogym.robot.robot_interface import ControlMode, TcpSolverMode
+
+    env = make_env(parameters=dict(n_random_initial_steps=0, simulation_params=dict(num_objects=5),
+                                   robot_control_params=dict(control_mode=ControlMode.TCP_ROLL_YAW, tcp_solver_mode=TcpSolverMode.MOCAP_IK,
+                                                             arm_reset_controller_error=reset_controller_error,
+                                                             max_position_change=MAX_POSITION_CHANGE)), starting_seed=0)
+    env.reset()
+    return env.unwrapped, shim          # the environment itself, below the action wrappers (discretisation, smoothing): continuous actions
+
+
+def _copy_state(sim_stub, mj_sim):
+    import torch
+
+    d = mj_sim.data
+    w = sim_stub.pid.shape[1]
+    sim_stub.qpos[:] = torch.tensor(d.qpos); sim_stub.qvel[:] = torch.tensor(d.qvel); sim_stub.ctrl[:] = torch.tensor(d.ctrl)
+    sim_stub.pid[:] = torch.tensor(d.userdata[:w]); sim_stub.qacc_warmstart[:] = torch.tensor(d.qacc_warmstart)
+    if sim_stub.mocap_pos is not None:
+        sim_stub.mocap_pos[:] = torch.tensor(d.mocap_pos); sim_stub.mocap_quat[:] = torch.tensor(d.mocap_quat)
+    sim_stub.body_xpos[:] = torch.tensor(d.body_xpos); sim_stub.body_xquat[:] = torch.tensor(d.body_xquat)
+
+
+@needs_reference
+@pytest.mark.parametrize("reset_controller_error", [True, False])
+def test_batched_controller_steps_like_the_reference_environment(reset_controller_error):
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    env, shim = _reference_env(reset_controller_error)
+    try:
+        main_mj = env.mujoco_simulation.mj_sim
+        arm = env.robot.robots[0]
+        solver_mj = arm.controller_arm.mj_sim
+        assert type(arm).__name__ == "JointControlledTcpArm" and type(arm.controller_arm).__name__ == "FreeRollYawTcpArm"
+        nenv = 2
+        main = OracleGenericSim(main_mj.model._cm.blob(), nenv, main_mj.nsubsteps)
+        solver = OracleGenericSim(solver_mj.model._cm.blob(), nenv, solver_mj.nsubsteps)
+        assert main.model.host["nu"] == 7 and list(main.model.host["actuator_user0"]) == [1, 1, 1, 1, 1, 1, 0]    # cascaded-PI arm, PID gripper
+        assert solver.model.host["nmocap"] == 1 and solver.model.host["neq"] == 2        # mocap weld + gripper coupling
+        _copy_state(main, main_mj)
+        _copy_state(solver, solver_mj)
+        ctl = BatchedTcpArmController(main, solver, MAX_POSITION_CHANGE, reset_controller_error=reset_controller_error)
+        assert ctl.action_dim == env.action_space.shape[0] == 6
+        rng = np.random.RandomState(0)
+        worst = 0.0
+        for k in range(12):
+            a = rng.uniform(-1, 1, 6).astype(np.float32)   # the environment's action space is float32
+            if k == 5:
+                a[4] = 1.0                  # push the wrist towards its range: exercises constrain_quat_ctrl
+            env.step(a)
+            ctl.step(torch.tensor(np.stack([a, a])))
+            em = np.abs(main.qpos[0].numpy() - main_mj.data.qpos).max()
+            es = np.abs(solver.qpos[0].numpy() - solver_mj.data.qpos).max()
+            ec = np.abs(main.ctrl[0].numpy() - main_mj.data.ctrl).max()
+            emo = np.abs(solver.mocap_pos[0].numpy() - solver_mj.data.mocap_pos).max()
+            worst = max(worst, em, es, ec, emo)
+            assert em < 1e-9 and es < 1e-9 and ec < 1e-9 and emo < 1e-9, (k, em, es, ec, emo)
+            assert torch.equal(main.qpos[0], main.qpos[1])
+        assert worst < 1e-9 and int(main.warn.max()) == 0
+    finally:
+        shim.set_engine_factory(None)
+
+
+@needs_reference
+def test_controller_reset_reseats_the_mocap_weld_like_the_reference():
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    env, shim = _reference_env(True)
+    try:
+        main_mj = env.mujoco_simulation.mj_sim
+        solver_mj = env.robot.robots[0].controller_arm.mj_sim
+        main = OracleGenericSim(main_mj.model._cm.blob(), 1, main_mj.nsubsteps)
+        solver = OracleGenericSim(solver_mj.model._cm.blob(), 1, solver_mj.nsubsteps)
+        _copy_state(main, main_mj)
+        # the solver stand-in starts from its MODEL state (qpos0, compiled weld pose); reset() must bring it to the reference's
+        solver.model.set_field("eq_data", np.tile([0.1, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0], int(solver.model.host["neq"])))
+        ctl = BatchedTcpArmController(main, solver, MAX_POSITION_CHANGE)
+        ctl.reset()
+        weld = [i for i in range(int(solver.model.host["neq"])) if int(solver.model.host["eq_type"][i]) == 1]
+        assert np.allclose(np.asarray(solver.model.host["eq_data"]).reshape(int(solver.model.host["neq"]), -1)[weld, :7], [0, 0, 0, 1, 0, 0, 0])
+        assert np.abs(solver.qpos[0, ctl.arm_qadr_solver].numpy() - main_mj.data.qpos[ctl.arm_qadr_main]).max() == 0
+        tcp = solver.model.name2id("body", "robot0:gripper_tcp")
+        assert torch.equal(solver.mocap_pos[0, 0], solver.body_xpos[0, tcp]) and torch.equal(solver.mocap_quat[0, 0], solver.body_xquat[0, tcp])
+        assert np.abs(solver.mocap_pos[0, 0].numpy() - solver_mj.data.mocap_pos[0]).max() < 2e-3   # the reference's helper arm has drifted a little by then
+    finally:
+        shim.set_engine_factory(None)
+
+
+# ---- the same comparison from the committed fixture (tools/make_rearrange_arm_fixture.py): no reference needed, and the GPU tier
+def _fixture():
+    import json
+
+    fx = json.load(open(os.path.join(HERE, "golden", "rearrange_arm.json")))
+    blobs = [open(os.path.join(ASSETS, n + ".rgm"), "rb").read() for n in ("rearrange_blocks5_tcp", "rearrange_solver_arm")]
+    return fx, blobs
+
+
+def _load_state(sim, st, rows=slice(None)):
+    t = sim.torch
+    f = lambda v: t.as_tensor(np.asarray(v), dtype=sim.qpos.dtype).to(sim.qpos.device)
+    sim.qpos[rows] = f(st["qpos"]); sim.qvel[rows] = f(st["qvel"]); sim.ctrl[rows] = f(st["ctrl"]); sim.pid[rows] = f(st["pid"])
+    sim.qacc_warmstart[rows] = f(st["warm"])
+    if sim.mocap_pos is not None:
+        sim.mocap_pos[rows] = f(st["mocap_pos"]); sim.mocap_quat[rows] = f(st["mocap_quat"])
+    sim.body_xpos[rows] = f(st["body_xpos"]); sim.body_xquat[rows] = f(st["body_xquat"])
+
+
+@pytest.mark.parametrize("key", ["reset_error_true", "reset_error_false"])
+def test_controller_replays_the_recorded_reference_rollout(key):
+    """fp64 stand-ins, free-running for 16 env-steps from the recorded reset state: the reference environment's recorded main /
+    solver states are reproduced to 1e-9 at every step."""
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    fx, blobs = _fixture()
+    rec = fx[key]
+    main = OracleGenericSim(blobs[0], 1, rec["nsub_main"])
+    solver = OracleGenericSim(blobs[1], 1, rec["nsub_solver"])
+    _load_state(main, rec["main0"]); _load_state(solver, rec["solver0"])
+    ctl = BatchedTcpArmController(main, solver, rec["max_position_change"], reset_controller_error=rec["reset_controller_error"])
+    for k, a in enumerate(rec["actions"]):
+        ctl.step(torch.tensor([a], dtype=torch.float32))
+        assert np.abs(main.qpos[0].numpy() - rec["main_qpos"][k]).max() < 1e-9, k
+        assert np.abs(main.ctrl[0].numpy() - rec["main_ctrl"][k]).max() < 1e-9, k
+        assert np.abs(solver.qpos[0].numpy() - rec["solver_qpos"][k]).max() < 1e-9, k
+        assert np.abs(solver.mocap_pos[0].numpy() - np.asarray(rec["solver_mocap_pos"][k])).max() < 1e-9, k
+    # the policy's actions reached the arm: the tool moved by centimetres, the arm joints by tenths of a radian
+    q0, q1 = np.asarray(rec["main0"]["qpos"]), main.qpos[0].numpy()
+    assert np.abs(q1[:6] - q0[:6]).max() > 0.05
+
+
+def _follow(make_sims, key, device="cpu"):
+    """shared by the emulation and the CUDA tier: the fp32 engine beside the fp64 stand-ins"""
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    fx, blobs = _fixture()
+    rec = fx[key]
+    main, solver, nenv, sync = make_sims(blobs, rec)
+    ctl = BatchedTcpArmController(main, solver, rec["max_position_change"], reset_controller_error=rec["reset_controller_error"])
+    omain = OracleGenericSim(blobs[0], 1, rec["nsub_main"])
+    osolver = OracleGenericSim(blobs[1], 1, rec["nsub_solver"])
+    octl = BatchedTcpArmController(omain, osolver, rec["max_position_change"], reset_controller_error=rec["reset_controller_error"])
+    _load_state(omain, rec["main0"]); _load_state(osolver, rec["solver0"])
+
+    def push(dst, src):
+        for n in ("qpos", "qvel", "ctrl", "pid", "qacc_warmstart", "mocap_pos", "mocap_quat", "body_xpos", "body_xquat"):
+            s = getattr(src, n, None)
+            if s is not None:
+                getattr(dst, n).copy_(s.to(torch.float32).expand_as(getattr(dst, n)))
+
+    # teacher-forced: every env-step starts from the oracle stand-in's state
+    err_arm, err_obj, err_sol = [], [], []
+    for k, a in enumerate(rec["actions"]):
+        push(main, omain); push(solver, osolver)
+        ctl.step(torch.tensor([a] * nenv, dtype=torch.float32, device=device))
+        octl.step(torch.tensor([a], dtype=torch.float32))
+        sync()
+        q, qo = main.qpos.cpu().numpy().astype(np.float64), omain.qpos[0].numpy()
+        err_arm.append(np.abs(q[0, :6] - qo[:6]).max()); err_obj.append(np.abs(q[0, 8:] - qo[8:]).max())
+        err_sol.append(np.abs(solver.qpos[0].cpu().numpy() - osolver.qpos[0].numpy()).max())
+        assert np.array_equal(q[0], q[nenv - 1])
+    assert int(main.warn.max()) == 0 and int(solver.warn.max()) == 0
+    # free-running from the recorded reset state
+    _load_state(omain, rec["main0"]); _load_state(osolver, rec["solver0"])
+    push(main, omain); push(solver, osolver)
+    err_free = []
+    for k, a in enumerate(rec["actions"]):
+        ctl.step(torch.tensor([a] * nenv, dtype=torch.float32, device=device))
+        sync()
+        err_free.append(np.abs(main.qpos[0].cpu().numpy().astype(np.float64)[:6] - np.asarray(rec["main_qpos"][k])[:6]).max())
+    return dict(arm=max(err_arm), obj_median=float(np.median(err_obj)), obj_max=max(err_obj), solver=max(err_sol), free=max(err_free)), main
+
+
+@pytest.mark.parametrize("key", ["reset_error_true"])
+def test_emulated_kernels_follow_the_recorded_reference_rollout(key):
+    """The kernel source in CPU emulation (fp32) under the same controller: what the CUDA tier asserts, checked without a GPU."""
+    from emu_generic_sim import EmuGenericSim
+
+    def make(blobs, rec):
+        return (EmuGenericSim(blobs[0], 2, rec["nsub_main"], contact_capacity=64, row_capacity=160), EmuGenericSim(blobs[1], 2, rec["nsub_solver"]), 2, lambda: None)
+
+    err, _ = _follow(make, key)
+    assert err["arm"] < 1e-4 and err["solver"] < 2e-4 and err["obj_median"] < 1e-4 and err["obj_max"] < 2e-3 and err["free"] < 2e-3, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", ["reset_error_true", "reset_error_false"])
+def test_cuda_controller_follows_the_recorded_reference_rollout(key):
+    """Both simulations on the CUDA engine (two BatchedSims, two launches per env-step, the hand-off on the device).
+    Teacher-forced: every env-step starts from the oracle stand-in's state; the fp32 engine must land within 1e-4 rad of the
+    fp64 arm joints and track the blocks.  Free-running for the 16 recorded steps: the arm stays within 2e-3 rad of the
+    reference environment's recorded trajectory (the cascaded-PI loop is contracting), and batch rows agree bit for bit."""
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+    models = {}
+
+    def make(blobs, rec):
+        nenv = 4
+        mm, ms = engine.DeviceModel(blobs[0], 0), engine.DeviceModel(blobs[1], 0)
+        models["main"] = mm
+        main = engine.BatchedSim(mm, nenv, rec["nsub_main"], outputs=("body_xpos", "body_xquat", "ncon", "warn", "sensordata"), contact_capacity=64, row_capacity=160)
+        solver = engine.BatchedSim(ms, nenv, rec["nsub_solver"], outputs=("body_xpos", "body_xquat", "warn"))
+        return main, solver, nenv, torch.cuda.synchronize
+
+    err, main = _follow(make, key, device="cuda:0")
+    assert err["arm"] < 2e-4 and err["solver"] < 4e-4 and err["obj_median"] < 2e-4 and err["obj_max"] < 4e-3 and err["free"] < 4e-3, err
+    mm = models["main"]
+    # force / torque sensors of the tool flange are live on the device (robot/ur16e/mujoco/joint_controlled_arm.py:35-45)
+    sd = main.sensordata[0].cpu().numpy()
+    adr = mm.host["sensor_adr"][mm.name2id("sensor", "toolhead_force")]
+    assert np.isfinite(sd).all() and 5.0 < np.linalg.norm(sd[adr:adr + 3]) < 100.0      # the gripper's weight, give or take its motion

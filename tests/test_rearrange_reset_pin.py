@@ -6,7 +6,7 @@ The reference's documentation prints the observation of `blocks_train.make_env(.
 20) of five blocks on the stiff table -- a stretch of free-running contact dynamics that ends on a repeating orbit, so it tests
 margin / solref mixing / impedance / elliptic-cone regularisation / box-box manifold / integrator all at once.
 
-* the unmodified reference environment (dual-sim MOCAP_IK controller, PID arm calibration) on the mujoco_py shim with the oracle as
+* the unmodified reference environment (dual-sim MOCAP_IK controller, the default cascaded-PI arm calibration) on the mujoco_py shim with the oracle as
   engine reports 0.51167315 (needs /root/reference; tools/make_rearrange_reset_fixture.py stores the simulator state at the start of
   that stretch and the environment's compiled model);
 * replaying the stored stretch: the oracle lands on the documented value to 5e-9; the fp32 kernel logic (CPU emulation) and the
@@ -151,13 +151,12 @@ def test_reference_blocks_env_resets_to_the_documented_height_on_the_shim():
     try:
         from robogym.envs.rearrange.blocks_train import make_env
 
-        env = make_env(parameters={"simulation_params": {"num_objects": 5, "max_num_objects": 8},
-                                   "robot_control_params": {"arm_joint_calibration_path": "pid"}})
+        env = make_env(parameters={"simulation_params": {"num_objects": 5, "max_num_objects": 8}})
         obs = env.reset()
         assert obs["obj_pos"].shape == (8, 3) and np.all(obs["obj_pos"][5:] == 0)
         z = obs["obj_pos"][:5, 2]
         assert np.sum(np.abs(z - DOCUMENTED_Z) < 5e-9) >= 4, z      # the documentation's own sample has one block off the orbit too
-        # and the environment steps: TCP actions through the helper arm's mocap weld, the main arm follows by joint PID
+        # and the environment steps: TCP actions through the helper arm's mocap weld, the main arm follows through its cascaded-PI joint controllers
         for _ in range(3):
             obs, rew, done, info = env.step(env.action_space.sample())
         assert np.all(np.isfinite(obs["obj_pos"])) and np.abs(obs["obj_pos"][:5, 2] - DOCUMENTED_Z).max() < 1e-3
