@@ -609,8 +609,13 @@ class RearrangeTcpWorkload(RearrangeWorkload):
         self.ctrl0 = torch.zeros(N, m["nu"], **f32)
         self.ctrl0[:, self.ctl.arm_act_main] = q0[:, self.ctl.arm_qadr_main]
         self.pending = None
+        self.tcp_main = names["body"].index("robot0:gripper_tcp")
         self.reset(torch.ones(N, dtype=torch.bool, device=dev))
+        sim.forward()
         self.ctl.reset()
+        p0 = sim.body_xpos[0, self.tcp_main].clone()
+        self.lo = p0 + torch.tensor([-0.25, -0.15, -0.06], **f32)      # episode ends when the tool leaves the table-top workspace
+        self.hi = p0 + torch.tensor([0.35, 0.55, 0.25], **f32)
 
     def reset(self, mask):
         t, sim, sol = self.torch, self.sim, self.solver
@@ -627,6 +632,12 @@ class RearrangeTcpWorkload(RearrangeWorkload):
 
     def step_timed(self):
         self.ctl.step(self.pending)
+
+    def auto_reset(self):
+        p = self.sim.body_xpos[:, self.tcp_main]
+        out = ((p < self.lo) | (p > self.hi)).any(dim=1) | ~self.on_palm()
+        self.reset(out)
+        return out
 
     def sample_action(self):
         return self.torch.rand(self.sim.nenv, 6, device=self.dev, generator=self.gen) * 2 - 1
