@@ -4,11 +4,11 @@
  * Stage map (SURVEY.md 8(a'), reference call site robogym/mujoco/simulation_interface.py:184-185):
  *   S1 kinematics ........ rgo_kinematics      S9  impedance ......... make_rows
  *   S2 spatial inertia ... rgo_inertia         S10 passive + bias .... rgo_passive, rgo_bias
- *   S3 tendons ........... rgo_tendon          S11 actuation (PID) ... rgo_actuation
+ *   S3 tendons ........... rgo_tendon          S11 actuation (PID, cascaded PI) ... rgo_actuation
  *   S4 transmission ...... rgo_transmission    S12 smooth accel ...... rgo_smooth
  *   S5/6 mass matrix ..... rgo_massmatrix      S13 Newton solver ..... rgo_solve
  *   S7 collision ......... rgo_collision       S15 Euler ............. rgo_euler
- *   S8 constraint rows ... make_rows
+ *   S8 constraint rows ... make_rows           S14 sensors (touch, jointpos, force / torque) ... rgo_sensors
  */
 #include "rgo_oracle.h"
 

@@ -4,9 +4,10 @@
  * path that robogym runs through mujoco-py:
  *     SimulationInterface.step() = sim.step() (nsubsteps x mj_step) + sim.forward()
  *     (robogym/mujoco/simulation_interface.py:176-207, called from robogym/robot_env.py:837)
- * including mujoco-py's stateful PID actuator callback that robogym switches on with
- * cymj.set_pid_control (robogym/mujoco/simulation_interface.py:86-88; parameter
- * layout robogym/mujoco/constants.py:34-53).
+ * including mujoco-py's stateful PID and cascaded-PI actuator callbacks that robogym
+ * switches on with cymj.set_pid_control (robogym/mujoco/simulation_interface.py:86-88;
+ * parameter layouts robogym/mujoco/constants.py:34-53 and
+ * robogym/assets/xmls/robot/ur16e/jointspec/calibrations/cascaded_pi/joint_actuations.xml:4).
  *
  * PARITY: the arithmetic of this path lives in mujoco-py==2.0.2.13 / MuJoCo 2.0
  * (robogym setup.py:16), which is not vendored in /root/reference and is not installable
@@ -15,8 +16,13 @@
  * pipeline (kinematics -> tendons -> CRB mass matrix -> collision -> constraint rows with
  * solref/solimp impedance -> Newton solver on the pyramidal / elliptic cone convex problem
  * -> semi-implicit Euler with implicit joint damping) from its documentation.  Pinned:
- *   - ONE real-MuJoCo output, the only one the reference repository holds for a simulated
- *     quantity: the block heights 0.51167315 that its documentation prints for
+ *   - the reference's recorded controller response: test_mocap_ik_impulse_response
+ *     (robogym/envs/rearrange/tests/test_rearrange_sim.py:135-230: tool displacement 0.036 /
+ *     0.0363 / 0.022 / 0.022 m +- 1e-3 and rise times after an impulse action, through the
+ *     two-simulation MOCAP_IK loop with cascaded-PI joint controllers) passes unmodified on
+ *     the mujoco_py shim with this oracle as the engine, and fails with the plain-PID
+ *     calibration or without the controller's bias-force term (tests/test_reference_suite.py);
+ *   - a documented real-MuJoCo output of a simulated quantity: the block heights 0.51167315 that its documentation prints for
  *     rearrange/blocks_train after env.reset() (docs/env_param_interface.md:32-38).  The
  *     unmodified reference environment, run on the mujoco_py shim with this oracle as the
  *     engine, reports exactly that number after its 4000 mj_steps of object stabilisation

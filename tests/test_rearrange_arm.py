@@ -255,4 +255,4 @@ def test_cuda_controller_follows_the_recorded_reference_rollout(key):
     # force / torque sensors of the tool flange are live on the device (robot/ur16e/mujoco/joint_controlled_arm.py:35-45)
     sd = main.sensordata[0].cpu().numpy()
     adr = mm.host["sensor_adr"][mm.name2id("sensor", "toolhead_force")]
-    assert np.isfinite(sd).all() and 5.0 < np.linalg.norm(sd[adr:adr + 3]) < 100.0      # the gripper's weight, give or take its motion
+    assert np.isfinite(sd).all() and 2.0 < np.linalg.norm(sd[adr:adr + 3]) < 100.0      # about the gripper's weight (0.5 kg), give or take its motion
