@@ -51,13 +51,40 @@ def quat_mul(t, q0, q1):
                     w0 * y1 + y0 * w1 + z0 * x1 - x0 * z1, w0 * z1 + z0 * w1 + x0 * y1 - y0 * x1], dim=-1)
 
 
+def quat2mat(t, q):
+    """robogym/utils/rotation.py:202-225 (unit-norm input: the degenerate branch is not needed)"""
+    w, x, y, z = q.unbind(-1)
+    s2 = 2.0 / (q * q).sum(-1)
+    X, Y, Z = x * s2, y * s2, z * s2
+    wX, wY, wZ, xX, xY, xZ, yY, yZ, zZ = w * X, w * Y, w * Z, x * X, x * Y, x * Z, y * Y, y * Z, z * Z
+    return t.stack([t.stack([1.0 - (yY + zZ), xY - wZ, xZ + wY], -1), t.stack([xY + wZ, 1.0 - (xX + zZ), yZ - wX], -1),
+                    t.stack([xZ - wY, yZ + wX, 1.0 - (xX + yY)], -1)], -2)
+
+
+def align_axis(t, cmd_quat, axis):
+    """MocapSolver.align_axis (mocap_solver.py:59-75): rotate `cmd_quat` by the shortest arc that brings its body axis closest to
+    world axis `axis` exactly onto it (rotation.vectors2quat, rotation.py:469-486; the antiparallel case cannot occur: the
+    chosen body axis has its largest component along the world axis, sign-flipped to be positive)."""
+    mtx = quat2mat(t, cmd_quat)
+    nr = mtx[:, axis, :].abs().argmax(dim=1)
+    ax = mtx.gather(2, nr.view(-1, 1, 1).expand(-1, 3, 1)).squeeze(2)
+    ax = ax * t.sign(ax[:, axis:axis + 1])
+    e = t.zeros_like(ax)
+    e[:, axis] = 1.0
+    q = t.cat([((ax * ax).sum(1) * 1.0).sqrt().unsqueeze(1) + ax[:, axis:axis + 1], t.linalg.cross(ax, e)], dim=1)
+    q = q / q.norm(dim=1, keepdim=True)
+    q = q * t.where(q[:, :1] < 0, -t.ones_like(q[:, :1]), t.ones_like(q[:, :1]))       # quat_normalize: w >= 0
+    return quat_mul(t, q, cmd_quat)
+
+
 class BatchedTcpArmController:
     """`main`, `solver`: BatchedSim-like objects for the joint-actuated scene and the mocap-welded arm (the solver needs the
     outputs body_xpos / body_xquat).  `dof_dims`: the tool rotations the policy controls -- ("roll", "pitch") is
-    ControlMode.TCP_ROLL_YAW's FreeRollYawTcpArm (free_dof_tcp_arm.py:243-250; it has no alignment axis), which is the mode
-    SURVEY 8(d) row 4 names."""
+    ControlMode.TCP_ROLL_YAW's FreeRollYawTcpArm (free_dof_tcp_arm.py:243-250; no alignment axis), the reference's default and the
+    mode SURVEY 8(d) row 4 names; ("pitch",) with align_axis="pitch" is ControlMode.TCP_WRIST's FreeWristTcpArm (:232-240)."""
 
-    def __init__(self, main, solver, max_position_change, dof_dims=("roll", "pitch"), reset_controller_error=True, prefix="robot0:", main_forwards=2):
+    def __init__(self, main, solver, max_position_change, dof_dims=("roll", "pitch"), reset_controller_error=True, prefix="robot0:", main_forwards=2,
+                 align_axis=None):
         assert max_position_change and max_position_change > 0.0, "Position multiplier must be a positive number"
         self.main, self.solver = main, solver
         self.t = main.torch
@@ -65,6 +92,7 @@ class BatchedTcpArmController:
         self.dof_dims = tuple(dof_dims)
         self.reset_controller_error = bool(reset_controller_error)
         self.main_forwards = int(main_forwards)
+        self.align_axis = None if align_axis is None else EULER_INDEX[align_axis]
         mm, ms = main.model.host, solver.model.host
         arm = [f"{prefix}J{i}" for i in range(1, 7)]
         self.arm_qadr_main = [int(mm["jnt_qposadr"][main.model.name2id("joint", n)]) for n in arm]
@@ -147,7 +175,10 @@ class BatchedTcpArmController:
         for i, d in enumerate(self.dof_dims):
             euler[:, EULER_INDEX[d]] = ang[:, i]
         gq = s.body_xquat[:, self.tcp_body].to(ang.dtype)
-        dquat = quat_mul(t, gq, euler2quat(t, euler)) - gq          # MocapSolver.get_tcp_quat without an alignment axis
+        target = quat_mul(t, gq, euler2quat(t, euler))              # MocapSolver.get_tcp_quat
+        if self.align_axis is not None:
+            target = align_axis(t, target, self.align_axis)
+        dquat = target - gq
         self._seat_mocaps()                                          # mocap_set_action
         k = self.welds[0][1]
         s.mocap_pos[:, k] += pos.to(s.mocap_pos.dtype)

@@ -22,7 +22,7 @@ MAX_POSITION_CHANGE = float(np.float32(0.1))    # the reference stores the param
 ASSETS = os.path.join(HERE, "..", "robogym_b200", "assets")
 
 
-def _reference_env(reset_controller_error):
+def _reference_env(reset_controller_error, wrist=False):
     if REF not in sys.path:
         sys.path.insert(0, REF)
     import robogym_b200.mujoco_py_shim as shim
@@ -35,7 +35,7 @@ def _reference_env(reset_controller_error):
     from robogym.robot.robot_interface import ControlMode, TcpSolverMode
 
     env = make_env(parameters=dict(n_random_initial_steps=0, simulation_params=dict(num_objects=5),
-                                   robot_control_params=dict(control_mode=ControlMode.TCP_ROLL_YAW, tcp_solver_mode=TcpSolverMode.MOCAP_IK,
+                                   robot_control_params=dict(control_mode=ControlMode.TCP_WRIST if wrist else ControlMode.TCP_ROLL_YAW, tcp_solver_mode=TcpSolverMode.MOCAP_IK,
                                                              arm_reset_controller_error=reset_controller_error,
                                                              max_position_change=MAX_POSITION_CHANGE)), starting_seed=0)
     env.reset()
@@ -93,6 +93,40 @@ def test_batched_controller_steps_like_the_reference_environment(reset_controlle
             assert em < 1e-9 and es < 1e-9 and ec < 1e-9 and emo < 1e-9, (k, em, es, ec, emo)
             assert torch.equal(main.qpos[0], main.qpos[1])
         assert worst < 1e-9 and int(main.warn.max()) == 0
+    finally:
+        shim.set_engine_factory(None)
+
+
+@needs_reference
+def test_wrist_mode_with_its_alignment_axis_steps_like_the_reference_environment():
+    """ControlMode.TCP_WRIST: one tool rotation (about the vertical), the commanded orientation re-aligned with the vertical
+    axis every step (MocapSolver.align_axis)."""
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    env, shim = _reference_env(True, wrist=True)
+    try:
+        main_mj = env.mujoco_simulation.mj_sim
+        arm = env.robot.robots[0]
+        solver_mj = arm.controller_arm.mj_sim
+        assert type(arm.controller_arm).__name__ == "FreeWristTcpArm" and env.action_space.shape[0] == 5
+        main = OracleGenericSim(main_mj.model._cm.blob(), 1, main_mj.nsubsteps)
+        solver = OracleGenericSim(solver_mj.model._cm.blob(), 1, solver_mj.nsubsteps)
+        _copy_state(main, main_mj)
+        _copy_state(solver, solver_mj)
+        ctl = BatchedTcpArmController(main, solver, MAX_POSITION_CHANGE, dof_dims=("pitch",), align_axis="pitch")
+        assert ctl.action_dim == 5
+        rng = np.random.RandomState(1)
+        for k in range(8):
+            a = rng.uniform(-1, 1, 5).astype(np.float32)
+            env.step(a)
+            ctl.step(torch.tensor(a[None]))
+            em = np.abs(main.qpos[0].numpy() - main_mj.data.qpos).max()
+            es = np.abs(solver.qpos[0].numpy() - solver_mj.data.qpos).max()
+            eq = np.abs(solver.mocap_quat[0].numpy() - solver_mj.data.mocap_quat).max()
+            assert em < 1e-9 and es < 1e-9 and eq < 1e-9, (k, em, es, eq)
     finally:
         shim.set_engine_factory(None)
 
