@@ -112,6 +112,13 @@ class DeviceModel:
             raise ValueError(f'No "{objtype}" with name {name} exists.')
         return i
 
+    def id2name(self, objtype, i):
+        """mjModel.<objtype>_id2name through the C ABI; None for an unnamed object"""
+        n = lib().rg_model_id2name(self.h, objtype.encode(), int(i))
+        if n is None:
+            raise ValueError(f'No "{objtype}" with id {i} exists.')
+        return n.decode() or None
+
     @property
     def dbg_size(self):
         return lib().rg_dbg_size(self.h)

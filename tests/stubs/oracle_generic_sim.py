@@ -21,6 +21,9 @@ class _Model:
         except ValueError:
             raise ValueError(f'No "{objtype}" with name {name} exists.')
 
+    def id2name(self, objtype, i):
+        return self.names[objtype][i]
+
     def set_field(self, name, values):
         arr = self.host[name]
         arr[...] = np.asarray(values, dtype=arr.dtype).reshape(arr.shape)

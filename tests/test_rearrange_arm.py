@@ -279,7 +279,7 @@ def test_cuda_controller_follows_the_recorded_reference_rollout(key):
         nenv = 4
         mm, ms = engine.DeviceModel(blobs[0], 0), engine.DeviceModel(blobs[1], 0)
         models["main"] = mm
-        main = engine.BatchedSim(mm, nenv, rec["nsub_main"], outputs=("body_xpos", "body_xquat", "ncon", "warn", "sensordata"), contact_capacity=64, row_capacity=160)
+        main = engine.BatchedSim(mm, nenv, rec["nsub_main"], outputs=("body_xpos", "body_xquat", "ncon", "warn", "sensordata", "contact"), contact_capacity=64, row_capacity=160)
         solver = engine.BatchedSim(ms, nenv, rec["nsub_solver"], outputs=("body_xpos", "body_xquat", "warn"))
         return main, solver, nenv, torch.cuda.synchronize
 
@@ -290,3 +290,12 @@ def test_cuda_controller_follows_the_recorded_reference_rollout(key):
     sd = main.sensordata[0].cpu().numpy()
     adr = mm.host["sensor_adr"][mm.name2id("sensor", "toolhead_force")]
     assert np.isfinite(sd).all() and 2.0 < np.linalg.norm(sd[adr:adr + 3]) < 100.0      # about the gripper's weight (0.5 kg), give or take its motion
+    # contact-based observations from the device's contact list (rearrange_contacts.py; the logic is checked against the reference's
+    # functions in tests/test_rearrange_contacts.py): blocks rest on the table, nothing touches the gripper in this rollout
+    from robogym_b200.rearrange_contacts import BatchedRearrangeContacts
+
+    qc = BatchedRearrangeContacts(main, num_objects=5)
+    assert mm.id2name("geom", qc.table_plane) == "table_collision_plane" and bool(qc.is_robot[qc.wrist_sphere]) and int(qc.is_gripper.sum()) >= 9
+    assert int(main.ncon.min()) >= 5                                   # at least the blocks' table contacts
+    assert not bool(qc.gripper_table_contact().any()) and qc.object_gripper_contact().shape == (4, 5, 2)
+    assert not bool(qc.wrist_cam_collisions()["any"].any())
