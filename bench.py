@@ -347,6 +347,9 @@ def newest_profile_metrics():
     import glob
 
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_metrics.csv")), key=lambda f: (os.path.basename(f).split("_")[0][:2], os.path.getmtime(f)))
+    latest = os.path.join(ROOT, "profiles", "latest_ncu_metrics.txt")     # names the capture of the current build (file times do not survive a checkout)
+    if os.path.exists(latest):
+        files.append(os.path.join(ROOT, "profiles", open(latest).read().strip()))
     for f in reversed(files):
         try:
             d = {r[0]: (r[1], float(r[2].replace(",", ""))) for r in csv.reader(open(f)) if len(r) == 3 and r[0] != "metric"}

@@ -72,8 +72,12 @@ extern __shared__ __align__(128) unsigned char rg_smem_raw[];
 #if RG_SKEW == 0
 /* Only the warps that hold an environment in this round take part (the last round of a launch is usually partial): named
  * barrier 1 over rg_bar_threads threads; barrier 0 (__syncthreads) stays for the round boundaries in rg_step_kernel. */
-__shared__ int rg_bar_threads;
-#define RG_CTA_SYNC() asm volatile("bar.sync 1, %0;" ::"r"(rg_bar_threads) : "memory")
+/* The active warps of a round may be split into barrier GROUPS (rg_batch_set_barrier_groups / RG_BAR_GROUPS, default 1):
+ * contiguous runs of warps, each with its own named barrier 1..G.  Barriers order nothing but the instruction stream, so
+ * results do not depend on the grouping; fewer warps per barrier wait less for their slowest member, at the price of more
+ * distinct code regions live in the instruction cache. */
+__shared__ int rg_bar_cfg[16];   /* per warp: barrier id << 16 | threads taking part */
+#define RG_CTA_SYNC() do { const int rg_cfg_ = rg_bar_cfg[threadIdx.x >> 5]; asm volatile("bar.sync %0, %1;" ::"r"(rg_cfg_ >> 16), "r"(rg_cfg_ & 0xffff) : "memory"); } while (0)
 #else
 /* Skewed variant: a warp may run up to RG_SKEW stages ahead of the slowest warp of its CTA.  Stage boundary k is an
  * mbarrier (ring of RG_SKEW+1): arrive on boundary k, then wait for boundary k-RG_SKEW.  A warp passes boundary k+R-1

@@ -35,6 +35,7 @@ struct RgKernelArgs {
   RgBatchIO io;
   const char* arena;  /* device arena base (16B aligned) */
   int nsub, final_forward, warps;
+  int groups;              /* barrier groups per round (>= 1) */
   /* per-environment overrides of float model arrays (domain randomisation) */
   int nover;
   int over_floats;                               /* floats of the per-warp override area */
@@ -149,7 +150,11 @@ __global__ void __launch_bounds__(RG_MAX_WARPS * 32, 1) rg_step_kernel(const __g
     const int slot0 = sh_slot0;
     if (slot0 >= total) break;
     const int nact = total - slot0 < args.warps ? total - slot0 : args.warps;
-    if (threadIdx.x == 0) rg_bar_threads = 32 * nact;
+    if (threadIdx.x < nact) {                          /* warp w of this round: which barrier it meets at, with how many threads */
+      const int w = threadIdx.x, G = args.groups < nact ? args.groups : nact;
+      const int g = w * G / nact, lo = (g * nact + G - 1) / G, hi = ((g + 1) * nact + G - 1) / G;
+      rg_bar_cfg[w] = ((1 + g) << 16) | (32 * (hi - lo));
+    }
     __syncthreads();
     if (warp >= nact) continue;
     const int e = args.order ? args.order[slot0 + warp] : slot0 + warp;
@@ -271,6 +276,7 @@ struct rg_batch {
   int* d_counter = nullptr; /* slot counter of the launch in flight */
   int* d_sep = nullptr;    /* [nenv][RG_NSEP] separating-axis cache of the narrow phase (speeds it up; results do not depend on it) */
   int balance = 1;
+  int groups = 1;          /* barrier groups per round (rg_batch_set_barrier_groups) */
 };
 
 static void rg_wire_device_view(rg_model* mm) {
@@ -446,6 +452,8 @@ int rg_batch_create_ex(const rg_model* m, int nenv, int contact_capacity, int ro
   if (rc) { delete b; return rc; }
   const char* benv = getenv("RG_BALANCE");
   if (benv) b->balance = atoi(benv) != 0;
+  const char* genv = getenv("RG_BAR_GROUPS");
+  if (genv && atoi(genv) >= 1 && atoi(genv) <= 12) b->groups = atoi(genv);
   cudaError_t e = cudaMalloc((void**)&b->d_order, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_cost, sizeof(int) * (size_t)nenv);
   if (e == cudaSuccess) e = cudaMalloc((void**)&b->d_subset, sizeof(int) * ((size_t)nenv + 1));
@@ -579,7 +587,7 @@ static int rg_launch_step(rg_batch* b, const uint8_t* mask, int nsub, int final_
   args.m = b->model->dev;
   args.L = b->L;
   args.arena = b->model->d_arena;
-  args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps;
+  args.nsub = nsub; args.final_forward = final_forward; args.warps = b->warps; args.groups = b->groups;
   args.nover = b->nover;
   args.over_floats = b->over_floats;
   args.order = b->balance ? b->d_order : nullptr;
