@@ -379,6 +379,11 @@ CONFIGS = {
                                  label="rearrange/blocks (BASELINE.json configs[3], SURVEY 8(d) cfg 4): UR16e + Robotiq 2f-85 under the reference's dual-simulation "
                                        "MOCAP_IK controller (solver arm with mocap weld nq8 -> joint targets -> main scene with cascaded-PI joint controllers, "
                                        "5 free blocks, condim 6, elliptic cones, impratio 10), nq43/nv38/nu7"),
+    # BASELINE.json configs[4] with the reference's control loop: the main simulation of the reference's own ycb environment (its draw of 8 objects)
+    "rearrange_ycb_tcp": dict(asset="rearrange_ycb8_tcp", solver_asset="rearrange_solver_arm", nenv=1024, caps=(64, 160, 16), nsub=40, workload="rearrange_tcp", nobj=8,
+                              grid=(3, 9, 1.25, 0.32, 0.27, 0.36),
+                              label="rearrange/ycb (BASELINE.json configs[4], SURVEY 8(d) cfg 5): the main simulation the reference's ycb environment compiles "
+                                    "(8 YCB mesh objects of its own draw) under the dual-simulation MOCAP_IK controller, nq64/nv56/nu7"),
     # BASELINE.json configs[4]: the same world with 8 YCB objects (unions of 1..29 convex meshes each; one fixed draw of the eight)
     "rearrange_ycb": dict(asset="rearrange_ycb8", nenv=1024, caps=(64, 128, 16), nsub=20, workload="rearrange", nobj=8, grid=(3, 9, 1.25, 0.32, 0.27, 0.36),
                           label="rearrange/ycb (BASELINE.json configs[4]): UR16e + Robotiq 2f-85 driven through the mocap weld, 8 YCB mesh objects "
@@ -497,20 +502,7 @@ class RearrangeWorkload:
         self.nobj, self.grid = nobj, grid
         self.tcp = names["body"].index("robot0:gripper_tcp")
         self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(nobj)]
-        # resting height of every object: the table top minus the lowest point of its geoms in the body frame
-        rest = []
-        for i in range(nobj):
-            b = names["body"].index("object%d" % i)
-            zmin = 0.0
-            for g in range(m["ngeom"]):
-                if m["geom_bodyid"][g] != b:
-                    continue
-                if m["geom_dataid"][g] >= 0:
-                    a, n = int(m["mesh_vertadr"][m["geom_dataid"][g]]), int(m["mesh_vertnum"][m["geom_dataid"][g]])
-                    zmin = min(zmin, float((m["mesh_vert"].reshape(-1, 3)[a:a + n, 2] + m["geom_pos"].reshape(-1, 3)[g, 2]).min()))
-                else:
-                    zmin = min(zmin, float(m["geom_pos"].reshape(-1, 3)[g, 2] - m["geom_size"].reshape(-1, 3)[g, 2]))
-            rest.append(0.453 + 0.03324 - zmin + 0.001)
+        rest = self.rest_heights(m, names, nobj)
         self.rest = torch.tensor(rest, **f32)
         cr = m["actuator_ctrlrange"].reshape(-1, 2)
         self.ctrl_lo, self.ctrl_hi = torch.tensor(cr[:, 0], **f32), torch.tensor(cr[:, 1], **f32)
@@ -529,6 +521,24 @@ class RearrangeWorkload:
         self.lo = self.tcp_pos0[0] + torch.tensor([-0.15, -0.05, -0.055], **f32)
         self.hi = self.tcp_pos0[0] + torch.tensor([0.25, 0.45, 0.10], **f32)
         self.reset(torch.ones(N, dtype=torch.bool, device=dev))
+
+    @staticmethod
+    def rest_heights(m, names, nobj):
+        """resting height of every object: the table top minus the lowest point of its geoms in the body frame"""
+        rest = []
+        for i in range(nobj):
+            b = names["body"].index("object%d" % i)
+            zmin = 0.0
+            for g in range(m["ngeom"]):
+                if m["geom_bodyid"][g] != b:
+                    continue
+                if m["geom_dataid"][g] >= 0:
+                    a, n = int(m["mesh_vertadr"][m["geom_dataid"][g]]), int(m["mesh_vertnum"][m["geom_dataid"][g]])
+                    zmin = min(zmin, float((m["mesh_vert"].reshape(-1, 3)[a:a + n, 2] + m["geom_pos"].reshape(-1, 3)[g, 2]).min()))
+                else:
+                    zmin = min(zmin, float(m["geom_pos"].reshape(-1, 3)[g, 2] - m["geom_size"].reshape(-1, 3)[g, 2]))
+            rest.append(0.453 + 0.03324 - zmin + 0.001)
+        return rest
 
     def reset_blocks(self, mask):
         """arm at its start pose, objects re-placed, velocities / controller state / warm start cleared -- for the masked environments"""
@@ -604,7 +614,7 @@ class RearrangeTcpWorkload(RearrangeWorkload):
         f32 = dict(dtype=torch.float32, device=dev)
         self.nobj, self.grid = nobj, grid
         self.blocks = [int(m["jnt_qposadr"][names["joint"].index("object%d:joint" % i)]) for i in range(nobj)]
-        self.rest = torch.full((nobj,), 0.453 + 0.03324 + 0.0254 + 0.001, **f32)
+        self.rest = torch.tensor(self.rest_heights(m, names, nobj), **f32)
         self.ctl = BatchedTcpArmController(sim, solver_sim, max_position_change=0.1, reset_controller_error=True)
         q0 = torch.tensor(m["qpos0"], **f32).repeat(N, 1)
         q0[:, self.ctl.arm_qadr_main] = torch.tensor(np.deg2rad([135.0, -90.0, 135.0, -100.0, -240.0, 135.0]), **f32)   # TABLETOP_EXPERIMENT_INITIAL_POS
