@@ -1,0 +1,49 @@
+"""bench.py's dual-simulation rearrange workload (RearrangeTcpWorkload: placement, controller loop, episode ends, resets) on the
+CPU emulation of the kernel -- the host logic the GPU bench line runs, checked without a GPU."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.join(HERE, "..")
+sys.path.insert(0, os.path.join(HERE, "stubs"))
+sys.path.insert(0, ROOT)
+
+
+@pytest.mark.parametrize("config", ["rearrange_blocks_tcp", "rearrange_ycb_tcp"])
+def test_dual_simulation_workload_runs_on_the_emulated_kernels(config):
+    import torch
+
+    import bench
+    from emu_generic_sim import EmuGenericSim
+
+    cfg = bench.CONFIGS[config]
+    blob, sblob = bench.load_blob(cfg["asset"]), bench.load_blob(cfg["solver_asset"])
+    names = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", cfg["asset"] + ".names.json")))
+    n = 3
+    main = EmuGenericSim(blob, n, cfg["nsub"], contact_capacity=cfg["caps"][0], row_capacity=cfg["caps"][1])
+    solver = EmuGenericSim(sblob, n, cfg["nsub"])
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(1)
+    wl = bench.RearrangeTcpWorkload(main, main.model, names, torch.device("cpu"), gen, cfg["nobj"], cfg["grid"], solver)
+    assert wl.action_dim == 6
+    tcp0 = main.body_xpos[:, wl.tcp_main].clone()
+    q_arm0 = main.qpos[:, wl.ctl.arm_qadr_main].clone()
+    for k in range(6):
+        wl.apply_action(wl.sample_action())
+        wl.step_timed()
+        wl.auto_reset()
+    assert int(main.warn.max()) == 0 and int(solver.warn.max()) == 0
+    z = torch.stack([main.qpos[:, a + 2] for a in wl.blocks], dim=1)
+    assert bool((z > 0.49).all()) and bool((z < 0.56).all())                    # every object still on the table top
+    assert float((main.body_xpos[:, wl.tcp_main] - tcp0).abs().max()) > 0.02   # the tool went where the actions sent it
+    assert float((main.qpos[:, wl.ctl.arm_qadr_main] - q_arm0).abs().max()) > 0.02
+    # a forced episode end re-seats the arm, the objects and both controllers' state
+    mask = torch.tensor([False, True, False])
+    wl.reset(mask)
+    assert torch.allclose(main.qpos[1, wl.ctl.arm_qadr_main], wl.q0[1, wl.ctl.arm_qadr_main]) and not bool(main.pid[1].any())
+    assert torch.equal(solver.qpos[1, wl.ctl.arm_qadr_solver], main.qpos[1, wl.ctl.arm_qadr_main]) and not bool(solver.qvel[1].any())
+    assert bool(main.qvel[0].any())                                              # the others keep going
