@@ -704,10 +704,28 @@ def run_gpu_arm(args):
     else:
         wl = RearrangeWorkload(sim, model, names, dev, gen, cfg["nobj"], cfg["grid"]) if rearrange else Workload(sim, model, names, dev, gen)
     nact = wl.action_dim
+    rnd = None
+    if args.randomize:
+        if rearrange:
+            raise SystemExit("--randomize: dactyl configs only")
+        from robogym_b200.locked_env import TorchRand
+        from robogym_b200.randomization import FullCubeRandomizer, LockedRandomizer
+
+        R = (FullCubeRandomizer if args.config == "full_perpendicular" else LockedRandomizer)(m, names, TorchRand(torch, dev, rank_seed(77, rank)), torch, dev, torch.float32)
+        R.apply(sim, R.sample(N))                                   # one draw per environment (episode-level re-draws are not part of the timed loop)
+        rnd = dict(R=R, ts=R.timestep_state(N), wind=R.wind_state(N, nsub * R.timestep0), timestep=sim.enable_per_env_timestep(),
+                   xfrc=sim.xfrc_applied if sim.xfrc_applied is not None else sim.enable_xfrc())
+
+    def randomize_step():
+        """RandomizedTimestepWrapper.step / RandomizedWindWrapper.step: the next env-step's timestep and gust (untimed, like the action sampling)"""
+        if rnd is not None:
+            rnd["timestep"].copy_(rnd["R"].next_timestep(rnd["ts"]))
+            rnd["R"].next_wind(rnd["wind"], rnd["xfrc"])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     warmup = max(args.warmup, 3)
     for _ in range(warmup):
         wl.apply_action(wl.sample_action())
+        randomize_step()
         wl.step_timed()
         wl.auto_reset()
     torch.cuda.synchronize()
@@ -728,6 +746,7 @@ def run_gpu_arm(args):
         nxt = wl.sample_action()
         flush.zero_()                                   # evict L2 between timed iterations (outside the event pair)
         wl.apply_action(nxt)
+        randomize_step()
         ev[k][0].record()
         wl.step_timed()                                 # one launch (two for the dual-simulation rearrange loop, hand-off included)
         ev[k][1].record()
@@ -767,6 +786,7 @@ def run_gpu_arm(args):
         flush.zero_()                                   # same cold L2 as the device-timed region (0.05 ms of memset, inside the timing)
         d_act.copy_(buf, non_blocking=True)             # H2D of this step's inputs
         wl.apply_action(d_act)
+        randomize_step()
         wl.step_timed()
         h_q.copy_(sim.qpos, non_blocking=True)          # D2H of this step's result
         h_v.copy_(sim.qvel, non_blocking=True)
@@ -806,7 +826,7 @@ def run_gpu_arm(args):
                                                    "(clipped to a box over the table), gripper target from a[3]; auto-reset of environments that lost an object" % N if rearrange else
                                                    ", batch %d per GPU, 10 substeps of 0.008 s + forward per env-step, relative actions a~U(-1,1): "
                                                    "ctrl = clip(P qpos + a*range/2), auto-reset of environments whose cube left the palm" % N),
-                       "envs_per_gpu": N, "substeps": nsub, "physics_substeps_per_s": value * nsub,
+                       "randomize": bool(args.randomize), "envs_per_gpu": N, "substeps": nsub, "physics_substeps_per_s": value * nsub,
                        "l2": "flushed between timed steps (256 MiB memset outside the per-step event pairs)",
                        "launch": info, "cubes_on_palm_at_end": on_palm, "resets_in_timed_region_rank0": int(resets.item()),
                        "mean_contacts": float(ncon_sum.item()) / args.steps, "max_contacts": int(ncon_max.item()), "warn_bits": warn, "env_shard_rank0": [lo_env, hi_env]},
@@ -846,6 +866,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: 8192 envs per GPU; strong: 8192 envs per box")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--randomize", action="store_true", help="dactyl configs: per-environment model parameters drawn with the reference wrappers' distributions "
+                                                             "(locked.py:263-277 / full_perpendicular.py:425-440), per-step timestep and wind -- SURVEY 8(d) cfg 3's randomize=True")
     ap.add_argument("--config", default="locked", choices=sorted(CONFIGS), help="locked = BASELINE.json's headline config; full_perpendicular = configs[2]; rearrange_blocks = configs[3]; rearrange_ycb = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -151,7 +151,7 @@ class LockedRandomizer:
         self.robot_joints = t(robot_j, torch.long)
         self.robot_dofs = t([d for d in range(m["nv"]) if int(m["dof_jntid"][d]) in set(robot_j)], torch.long)
         self.robot_acts = idx(an, lambda s: s.startswith(hand_prefix))
-        self.cube_middle = gn.index(cube_prefix + "middle")
+        self.cube_middle = gn.index(cube_prefix + "middle") if cube_prefix + "middle" in gn else None   # the locked cube is one box geom
         from .batched_env import FINGERTIP_SITES, REFERENCE_SITES
         self.tip_sites = t([sn.index(hand_prefix + s) for s in FINGERTIP_SITES], torch.long)
         self.ref_sites = t([sn.index(hand_prefix + s) for s in REFERENCE_SITES], torch.long)
@@ -219,16 +219,18 @@ class LockedRandomizer:
         out["tendon_range"] = tendon_range_rule(torch, o["tendon_range"].reshape(1, nt, 2).repeat(n, 1, 1),
                                                 draw("tendon_range", lambda: self.rand.randn(n, nt * 2).reshape(n, nt, 2))).reshape(n, -1)
         # cube size: geom_size of cube:middle and the bounds the broad phase derives from it
-        scale = draw("cube_size", lambda: self.rand.uniform(0.95, 1.05, n, 1))
-        gs = o["geom_size"].reshape(1, -1, 3).repeat(n, 1, 1)
-        gs[:, self.cube_middle] = gs[:, self.cube_middle] * scale
-        out["geom_size"] = gs.reshape(n, -1)
-        rb = o["geom_rbound"].repeat(n, 1)
-        rb[:, self.cube_middle] = gs[:, self.cube_middle].norm(dim=1)
-        out["geom_rbound"] = rb
-        ab = o["geom_aabb"].reshape(1, -1, 6).repeat(n, 1, 1)
-        ab[:, self.cube_middle, 3:6] = gs[:, self.cube_middle]
-        out["geom_aabb"] = ab.reshape(n, -1)
+        if self.cube_middle is not None:
+            scale = draw("cube_size", lambda: self.rand.uniform(0.95, 1.05, n, 1))
+            gs = o["geom_size"].reshape(1, -1, 3).repeat(n, 1, 1)
+            gs[:, self.cube_middle] = gs[:, self.cube_middle] * scale
+            out["geom_size"] = gs.reshape(n, -1)
+            rb = o["geom_rbound"].repeat(n, 1)
+            rb[:, self.cube_middle] = gs[:, self.cube_middle].norm(dim=1)
+            out["geom_rbound"] = rb
+            ab = o["geom_aabb"].reshape(1, -1, 6).repeat(n, 1, 1)
+            ab[:, self.cube_middle, 3:6] = gs[:, self.cube_middle]
+            out["geom_aabb"] = ab.reshape(n, -1)
+        self._extra_rules(n, draw, out)
         # phasespace marker sites
         sp = o["site_pos"].reshape(1, -1, 3).repeat(n, 1, 1)
         sp[:, self.tip_sites] += 0.003 * draw("tip_noise", lambda: self.rand.randn(n, 15).reshape(n, 5, 3))
@@ -236,6 +238,9 @@ class LockedRandomizer:
         out["site_pos"] = sp.reshape(n, -1)
         out.update(self.constants.derive(out["body_inertia"]))
         return out
+
+    def _extra_rules(self, n, draw, out):
+        """hook for the scenes that add wrappers to the locked stack"""
 
     def apply(self, sim, params, idx=None):
         """Write sampled rows into the simulator's per-environment parameter tensors (all rows, or rows `idx`)."""
@@ -288,3 +293,23 @@ class LockedRandomizer:
         gust = self.rand.randn(n, 3) * self.cube_mass * force_std
         xfrc[:, self.cube_body, :3] = self.torch.where(hit.unsqueeze(1), gust.to(xfrc.dtype), f)
         return xfrc
+
+
+class FullCubeRandomizer(LockedRandomizer):
+    """The randomisation stack of dactyl/full_perpendicular (robogym/envs/dactyl/full_perpendicular.py:425-440): the locked stack
+    (body inertias, robot / cube friction, gravity, robot damping, Kp, joint limits, tendon ranges, phasespace marker offsets, per-step
+    timestep, wind on `cube:middle`) plus `RandomizedFaceDampingWrapper` (wrappers/face.py:4-9: the damping of the cube's face-driver and
+    cubelet joints times a log-uniform factor in [1/3, 3] per dof).  Cube friction applies to every named cube geom (25 cubelets + the core sphere)
+    (`RandomizedCubeFrictionWrapper` takes every geom whose name starts with "cube:").  NOT covered: `RandomizedPerpendicularCubeSizeWrapper`
+    -- its modifier rescales the cubelet MESH (envs/dactyl/common/mujoco_modifiers.py:55-66), and mesh vertices are shared by the whole
+    batch here; the cube keeps its nominal size."""
+
+    def __init__(self, m, names, rand, torch, device, dtype, hand_prefix="robot0:", cube_prefix="cube:"):
+        super().__init__(m, names, rand, torch, device, dtype, hand_prefix, cube_prefix)
+        jn = names["joint"]
+        face_j = {j for j, nme in enumerate(jn) if nme is not None and (nme.startswith(cube_prefix + "cubelet:driver:") or nme.startswith(cube_prefix + "cubelet:rot"))}
+        self.face_dofs = torch.as_tensor([d for d in range(m["nv"]) if int(m["dof_jntid"][d]) in face_j], dtype=torch.long, device=device)
+
+    def _extra_rules(self, n, draw, out):
+        damp = out["dof_damping"]
+        damp[:, self.face_dofs] = damp[:, self.face_dofs] * draw("face_damping", lambda: self._logu(1 / 3.0, 3.0, n, int(self.face_dofs.numel())))

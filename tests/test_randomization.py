@@ -184,3 +184,35 @@ def test_sampled_parameters_reach_the_engine(locked_blob, locked_names):
     R.apply(sim, q, idx)
     after = sim._params["dof_damping"]
     assert torch.equal(after[idx], q["dof_damping"]) and torch.equal(after[0], before[0]) and not torch.equal(after[3], before[3])
+
+
+def test_full_cube_randomizer_covers_the_cfg3_stack(tmp_path):
+    """dactyl/full_perpendicular's wrapper list (full_perpendicular.py:425-440) = the locked list + face damping (+ the mesh-scaling cube
+    size wrapper, which is documented as not covered): rows for the nv=168 model, face damping confined to the 66 face / cubelet
+    dofs of the manipulated cube with factors in [1/3, 3], robot damping still in [1/1.5, 1.5], cube friction on every cube geom."""
+    import json
+
+    import torch
+
+    from robogym_b200 import modelblob
+    from robogym_b200.randomization import FullCubeRandomizer
+
+    blob = open(os.path.join(HERE, "..", "robogym_b200", "assets", "dactyl_full_perpendicular.rgm"), "rb").read()
+    names = json.load(open(os.path.join(HERE, "..", "robogym_b200", "assets", "dactyl_full_perpendicular.names.json")))
+    m = modelblob.unpack(blob)
+    R = FullCubeRandomizer(m, names, NumpyRand(3, torch), torch, torch.device("cpu"), torch.float64)
+    assert R.cube_middle is None and int(R.face_dofs.numel()) == 66 and int(R.cube_geoms.numel()) == 26
+    n = 64
+    p = R.sample(n)
+    assert "geom_size" not in p and p["dof_damping"].shape == (n, 168)
+    d0 = np.asarray(m["dof_damping"])
+    ratio = p["dof_damping"].numpy() / np.where(d0 > 0, d0, 1.0)
+    face, robot = R.face_dofs.numpy(), R.robot_dofs.numpy()
+    other = np.setdiff1d(np.arange(168), np.concatenate([face, robot]))
+    assert ratio[:, face].min() >= 1 / 3.0 - 1e-12 and ratio[:, face].max() <= 3.0 + 1e-12 and ratio[:, face].std() > 0.3
+    assert ratio[:, robot].min() >= 1 / 1.5 - 1e-12 and ratio[:, robot].max() <= 1.5 + 1e-12
+    assert np.all(p["dof_damping"].numpy()[:, other] == d0[other])                # the target cube's joints are left alone
+    fr = p["geom_friction"].reshape(n, -1, 3).numpy() / np.asarray(m["geom_friction"]).reshape(1, -1, 3)
+    cg = R.cube_geoms.numpy()
+    assert np.allclose(fr[:, cg], fr[:, cg[:1]]) and fr[:, cg, 0].min() >= 0.5 and fr[:, cg, 1].max() <= 5.0   # one draw per env, all cube geoms
+    assert p["body_inertia"].shape == (n, 3 * m["nbody"]) and p["dof_invweight0"].shape == (n, 168)
