@@ -88,7 +88,10 @@ class BatchedBlockScene:
             aabb[:, g, 3:] = hs[:, k]
             mass[:, b] = mk[:, k]
             diag = t.stack([a2[:, k, 1] + a2[:, k, 2], a2[:, k, 0] + a2[:, k, 2], a2[:, k, 0] + a2[:, k, 1]], dim=1) * (mk[:, k] / 3.0)[:, None]
-            for e in range(self.sim.nenv):
+            cube = (hs[:, k, 0] == hs[:, k, 1]) & (hs[:, k, 1] == hs[:, k, 2])     # cubes: equal moments, the compiler keeps the geom axes
+            inertia[cube, b] = diag[cube]
+            iquat[cube, b] = t.tensor([1.0, 0.0, 0.0, 0.0], dtype=iquat.dtype)
+            for e in (~cube).nonzero().flatten().tolist():
                 key = tuple(hs[e, k].tolist())
                 if key not in frames:
                     w, v = mjcf._eig_frame(np.diag(np.array([key[1] ** 2 + key[2] ** 2, key[0] ** 2 + key[2] ** 2, key[0] ** 2 + key[1] ** 2])))
