@@ -187,3 +187,65 @@ def test_cuda_matches_oracle_readings(arm):
     assert int(sim.warn.max()) == 0
     assert np.median(err_f) < 5e-3 and np.median(err_t) < 5e-4, (np.median(err_f), np.median(err_t))
     assert (err_f < 0.05 * np.abs(want[:, :3]).max()).mean() > 0.95
+
+
+# the sensor body below a FREE base and a BALL joint: the axes of a ball / free joint's rotational dofs turn with the velocity that
+# precedes them (mj_comVel), which the one-lane subtree walk of the kernel has to reproduce from the dof bit masks
+FT_TUMBLER = """
+<mujoco>
+  <compiler angle="radian" coordinate="local"/>
+  <option timestep="0.002" iterations="50" tolerance="1e-12"/>
+  <size nuserdata="0" njmax="100" nconmax="20"/>
+  <worldbody>
+    <body name="base" pos="0 0 1.0">
+      <joint name="base_free" type="free"/>
+      <geom name="g_base" type="box" size="0.08 0.05 0.03" density="900" contype="0" conaffinity="0"/>
+      <body name="link" pos="0.1 0 0">
+        <joint name="shoulder_ball" type="ball" damping="0.02"/>
+        <geom name="g_link" type="capsule" fromto="0 0 0 0.2 0 0" size="0.015" density="900" contype="0" conaffinity="0"/>
+        <body name="tool" pos="0.2 0 0">
+          <joint name="wrist" type="hinge" axis="0 1 0" damping="0.01"/>
+          <site name="grip" pos="0.01 0 0.02" quat="0.9238795 0 0.3826834 0"/>
+          <geom name="g_tool" type="box" pos="0.05 0 0" size="0.05 0.03 0.01" density="1200" contype="0" conaffinity="0"/>
+        </body>
+      </body>
+    </body>
+  </worldbody>
+  <sensor>
+    <force name="f_grip" site="grip"/>
+    <torque name="t_grip" site="grip"/>
+    <force name="f_link" site="grip"/>
+  </sensor>
+</mujoco>
+"""
+
+
+def test_emulated_kernel_matches_oracle_below_free_and_ball_joints():
+    cm = mjcf.compile_mjcf(FT_TUMBLER)
+    blob = cm.blob()
+    om, d = oracle_pair(blob)
+    rng = np.random.RandomState(4)
+    d.qvel[:] = rng.uniform(-2, 2, cm.m["nv"])                 # tumbling, swinging, spinning
+    q = rng.normal(size=4); d.qpos[7:11] = q / np.linalg.norm(q)
+    tool = cm.name2id("body", "tool")
+    states, want = [], []
+    for k in range(40):
+        d.xfrc_applied[6 * tool:6 * tool + 6] = rng.uniform(-0.5, 0.5, 6) if k % 3 == 0 else 0.0
+        states.append((d.qpos.copy(), d.qvel.copy(), d.qacc_warmstart.copy(), d.xfrc_applied.copy()))
+        for _ in range(4):
+            d.step()
+        d.forward()
+        want.append(d.sensordata[:9].copy())
+    e = pyemu.EmuBatch(blob, cm.m, len(states))
+    e.xfrc = np.zeros((len(states), cm.m["nbody"], 6), np.float32)
+    for k, st in enumerate(states):
+        e.qpos[k], e.qvel[k], e.warm[k] = st[:3]
+        e.xfrc[k] = st[3].reshape(-1, 6)
+    e.step(4, 1)
+    want = np.stack(want)
+    assert np.abs(want[:, :3]).max() > 1.0 and np.abs(want[:, 3:6]).max() > 0.05            # centrifugal + gravity loads, not noise
+    assert np.abs(e.sensordata[:, :9] - want).max() < 2e-3 * max(1.0, np.abs(want).max()), np.abs(e.sensordata[:, :9] - want).max()
+    # sanity of the oracle side: in free fall (no applied force, nothing spinning) the flange transmits nothing
+    _, d2 = oracle_pair(blob)
+    d2.forward()
+    assert np.abs(d2.sensordata[:6]).max() < 1e-9
