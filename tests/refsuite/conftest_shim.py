@@ -8,6 +8,14 @@ for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "stubs"
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import numpy as np  # noqa: E402
+
+# names numpy 2 removed that the reference's 2020 TEST files still use (np.int in test_rearrange_robots.py:336, np.alltrue in
+# robot/utils/tests/test_reach_helper.py:40, np.Inf in the holdout configs): restored for the test run only
+for _name, _val in (("int", int), ("alltrue", np.all), ("Inf", np.inf)):
+    if not hasattr(np, _name):
+        setattr(np, _name, _val)
+
 import robogym_b200.mujoco_py_shim as shim  # noqa: E402
 
 shim.install()
