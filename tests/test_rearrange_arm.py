@@ -299,3 +299,79 @@ def test_cuda_controller_follows_the_recorded_reference_rollout(key):
     assert int(main.ncon.min()) >= 5                                   # at least the blocks' table contacts
     assert not bool(qc.gripper_table_contact().any()) and qc.object_gripper_contact().shape == (4, 5, 2)
     assert not bool(qc.wrist_cam_collisions()["any"].any())
+
+
+# ---- the reference's recorded controller response (robogym/envs/rearrange/tests/test_rearrange_sim.py:135-230), on the BATCHED controller
+IMPULSE_CASES = [(True, 0.165, 0.036, 5), (False, 0.05, 0.0363, 12), (True, 0.1, 0.022, 5), (False, 0.03, 0.022, 12)]
+
+
+def _impulse_response(make_sims, device="cpu", sync=lambda: None):
+    """test_mocap_ik_impulse_response restated on BatchedTcpArmController: from the environment's reset state (the committed fixture),
+    2 zero actions, one full-scale action on one tool axis, 40 zero actions; all 4 parameter sets x 3 axes run as ONE batch of 12
+    environments.  Returns the tool trajectories [12, 43, 3] (relative to the first sample)."""
+    import torch
+
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    fx, blobs = _fixture()
+    out = []
+    for rce, mpc, _, _ in IMPULSE_CASES:
+        rec = fx["reset_error_true" if rce else "reset_error_false"]
+        main, solver = make_sims(blobs, rec, 3)
+        _load_state(main, rec["main0"]); _load_state(solver, rec["solver0"])
+        ctl = BatchedTcpArmController(main, solver, float(np.float32(mpc)), reset_controller_error=rce)
+        tcp = main.model.name2id("body", "robot0:gripper_tcp")
+        traj = []
+        # the reference test steps the environment below its action discretisation but THROUGH SmoothActionWrapper(alpha=0.3)
+        # (rearrange/common/base.py:987; wrappers/util.py:142-218): a bias-corrected exponential moving average of the actions
+        alpha = 0.3 ** ((main.n_substeps * float(main.model.host["opt_timestep"][0])) / 0.08)
+        ema, t_ema = np.zeros((3, 6)), 0
+        for k in range(43):
+            raw = np.zeros((3, 6))
+            if k == 2:
+                raw[0, 0] = raw[1, 1] = raw[2, 2] = 1.0     # environment d gets the impulse on tool axis d
+            ema = ema * alpha + (1.0 - alpha) * raw
+            t_ema += 1
+            a = torch.tensor((ema / (1.0 - alpha ** t_ema)).astype(np.float32), device=device)
+            ctl.step(a)
+            sync()
+            traj.append(main.body_xpos[:, tcp].detach().cpu().numpy().astype(np.float64).copy())
+        traj = np.stack(traj, axis=1)
+        out.append(traj - traj[:, :1])
+    return np.concatenate(out, axis=0)
+
+
+def _assert_impulse(traj, tol=1e-3):
+    for c, (rce, mpc, want, rise) in enumerate(IMPULSE_CASES):
+        for d in range(3):
+            x = traj[3 * c + d, :, d]
+            assert abs(x[-1] - want) < tol, (rce, mpc, d, x[-1], want)                   # steady-state displacement, the reference's number
+            assert abs(x[2 + rise]) > 0.9 * x[-1], (rce, mpc, d, x[2 + rise], x[-1])    # 90 % within `rise` steps of the impulse
+
+
+def test_recorded_impulse_response_on_the_batched_controller_fp64_and_emulated():
+    """The reference's real-MuJoCo numbers for its controller (tool displacement 0.036 / 0.0363 / 0.022 / 0.022 m +- 1e-3, 90 % rise
+    within 5 / 12 steps) asserted on the batched dual-simulation controller: on the fp64 stand-ins and on the fp32 kernel logic."""
+    from emu_generic_sim import EmuGenericSim
+    from oracle_generic_sim import OracleGenericSim
+
+    _assert_impulse(_impulse_response(lambda blobs, rec, n: (OracleGenericSim(blobs[0], n, rec["nsub_main"]), OracleGenericSim(blobs[1], n, rec["nsub_solver"]))))
+    _assert_impulse(_impulse_response(lambda blobs, rec, n: (EmuGenericSim(blobs[0], n, rec["nsub_main"], contact_capacity=64, row_capacity=160),
+                                                              EmuGenericSim(blobs[1], n, rec["nsub_solver"]))))
+
+
+@pytest.mark.gpu
+def test_recorded_impulse_response_on_cuda():
+    """the same on the CUDA engine: the reference's recorded displacements, asserted on the product path"""
+    import torch
+
+    from robogym_b200 import build, engine
+
+    build.build()
+
+    def make(blobs, rec, n):
+        main = engine.BatchedSim(engine.DeviceModel(blobs[0], 0), n, rec["nsub_main"], outputs=("body_xpos", "body_xquat", "warn"), contact_capacity=64, row_capacity=160)
+        solver = engine.BatchedSim(engine.DeviceModel(blobs[1], 0), n, rec["nsub_solver"], outputs=("body_xpos", "body_xquat", "warn"))
+        return main, solver
+
+    _assert_impulse(_impulse_response(make, device="cuda:0", sync=torch.cuda.synchronize))
