@@ -223,6 +223,13 @@ class BatchedLockedEnv:
             self.wind_state = self.randomizer.wind_state(self.nenv, self.sim.n_substeps * self.randomizer.timestep0)
             self.timestep = self.sim.enable_per_env_timestep()
             self.xfrc = self.sim.enable_xfrc()
+        # RandomizeObservationWrapper with the locked environment's noise levels (locked.py:233-238, randomizations.py:314-389):
+        # noisy_fingertip_pos / noisy_hand_angle / noisy_cube_pos / noisy_cube_quat next to the clean observations
+        self.obs_noise = None
+        if randomize:
+            from .obs_noise import BatchedObservationNoise
+
+            self.obs_noise = BatchedObservationNoise(torch, self.rand, self.nenv, dict(fingertip_pos=15, hand_angle=24, cube_pos=3, cube_quat=4))
         self.pool = InitialStatePool(pool_sim, self.fac, self.rand, reset_initial_steps, n_random_initial_steps, cube_position_wiggle_std, self.randomizer)
         self.relative_action = relative_action
         self.successes_needed, self.max_timesteps_per_goal, self.min_timesteps_per_goal = successes_needed, max_timesteps_per_goal, min_timesteps_per_goal
@@ -316,6 +323,8 @@ class BatchedLockedEnv:
             self.wind_state["hit_prob"][idx] = ws["hit_prob"]
             self.timestep[idx] = self.randomizer.timestep0
             self.xfrc[idx] = 0
+        if self.obs_noise is not None:              # RandomizeObservationWrapper.reset: new per-episode biases
+            self.obs_noise.reset(idx)
         if self.max_delay > 0:                      # RandomizedActionLatency.reset
             self.action_history[idx] = 0
             self.action_delay[idx] = self.rand.randint(self.max_delay + 1, k * self.action_delay.shape[1]).reshape(k, -1)
@@ -352,6 +361,8 @@ class BatchedLockedEnv:
         if self.max_delay > 0:
             obs["action_history"] = self.action_history[:, :-1].clone()
             obs["action_delay"] = self.action_delay.clone()
+        if self.obs_noise is not None:
+            obs = self.obs_noise(obs)
         return obs
 
     # ---------------------------------------------------------------- step
