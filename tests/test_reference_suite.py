@@ -61,14 +61,31 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("path,kexpr,npass", CASES, ids=[c[0].split("/")[-1] for c in CASES])
-def test_reference_test_file_passes_on_the_shim(path, kexpr, npass, tmp_path):
-    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "refsuite"), RG_SHIM_ENGINE="oracle")
-    cmd = [sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-p", "conftest_shim", f"--rootdir={tmp_path}",
+def _run_case(path, kexpr, workdir, extra_env=None):
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "refsuite"), RG_SHIM_ENGINE="oracle", OMP_NUM_THREADS="1", **(extra_env or {}))
+    cmd = [sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-p", "conftest_shim", f"--rootdir={workdir}",
            os.path.join(REF, path)]
     if kexpr:
         cmd += ["-k", kexpr]
-    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1200)
+    return subprocess.run(cmd, cwd=str(workdir), env=env, capture_output=True, text=True, timeout=1800)
+
+
+@pytest.fixture(scope="module")
+def reference_runs(tmp_path_factory):
+    """Every reference test file runs in its own process anyway: start them together (a few at a time) instead of one after
+    the other, the parametrised tests below then only read their verdicts."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    jobs = {}
+    with ThreadPoolExecutor(max_workers=max(1, min(4, (os.cpu_count() or 2) // 2))) as pool:
+        for i, (path, kexpr, _) in enumerate(CASES):
+            jobs[(path, kexpr)] = pool.submit(_run_case, path, kexpr, tmp_path_factory.mktemp("ref%d" % i))
+        return {k: f.result() for k, f in jobs.items()}
+
+
+@pytest.mark.parametrize("path,kexpr,npass", CASES, ids=[c[0].split("/")[-1] for c in CASES])
+def test_reference_test_file_passes_on_the_shim(path, kexpr, npass, reference_runs):
+    out = reference_runs[(path, kexpr)]
     tail = out.stdout[-2000:] + out.stderr[-1000:]
     assert out.returncode == 0, tail
     assert f"{npass} passed" in out.stdout, tail
