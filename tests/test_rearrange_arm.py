@@ -375,3 +375,54 @@ def test_recorded_impulse_response_on_cuda():
         return main, solver
 
     _assert_impulse(_impulse_response(make, device="cuda:0", sync=torch.cuda.synchronize))
+
+
+@needs_reference
+def test_batched_controller_steps_like_the_reference_ycb_environment():
+    """BASELINE configs[4]: the reference's ycb environment (8 mesh objects of its own draw, the first starting_seed whose
+    placement succeeds) beside the batched controller on stand-ins built from the environment's compiled models."""
+    import torch
+
+    from oracle_generic_sim import OracleGenericSim
+    from robogym_b200.rearrange_arm import BatchedTcpArmController
+
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import robogym_b200.mujoco_py_shim as shim
+
+    shim.install()
+    from oracle_engine import OracleEngine
+
+    shim.set_engine_factory(OracleEngine)
+    try:
+        from robogym.envs.rearrange.ycb import make_env
+        from robogym.robot.robot_interface import ControlMode, TcpSolverMode
+
+        env = make_env(parameters=dict(n_random_initial_steps=0, simulation_params=dict(num_objects=8, max_num_objects=8),
+                                       robot_control_params=dict(control_mode=ControlMode.TCP_ROLL_YAW, tcp_solver_mode=TcpSolverMode.MOCAP_IK,
+                                                                 max_position_change=MAX_POSITION_CHANGE)),
+                       constants=dict(stabilize_objects=False), starting_seed=1)
+        env.reset()
+        env = env.unwrapped
+        main_mj = env.mujoco_simulation.mj_sim
+        solver_mj = env.robot.robots[0].controller_arm.mj_sim
+        blob = main_mj.model._cm.blob()
+        # the committed bench asset is this environment's main simulation (tools/make_rearrange_ycb_tcp_asset.py)
+        asset = open(os.path.join(ASSETS, "rearrange_ycb8_tcp.rgm"), "rb").read()
+        assert len(asset) == len(blob)
+        main = OracleGenericSim(blob, 1, main_mj.nsubsteps)
+        solver = OracleGenericSim(solver_mj.model._cm.blob(), 1, solver_mj.nsubsteps)
+        assert (main.model.host["nq"], main.model.host["nv"], main.model.host["nu"]) == (64, 56, 7)
+        _copy_state(main, main_mj)
+        _copy_state(solver, solver_mj)
+        ctl = BatchedTcpArmController(main, solver, MAX_POSITION_CHANGE)
+        rng = np.random.RandomState(2)
+        for k in range(5):
+            a = rng.uniform(-1, 1, 6).astype(np.float32)
+            env.step(a)
+            ctl.step(torch.tensor(a[None]))
+            em = np.abs(main.qpos[0].numpy() - main_mj.data.qpos).max()
+            es = np.abs(solver.qpos[0].numpy() - solver_mj.data.qpos).max()
+            assert em < 1e-9 and es < 1e-9, (k, em, es)
+    finally:
+        shim.set_engine_factory(None)
