@@ -47,3 +47,38 @@ def test_dual_simulation_workload_runs_on_the_emulated_kernels(config):
     assert torch.allclose(main.qpos[1, wl.ctl.arm_qadr_main], wl.q0[1, wl.ctl.arm_qadr_main]) and not bool(main.pid[1].any())
     assert torch.equal(solver.qpos[1, wl.ctl.arm_qadr_solver], main.qpos[1, wl.ctl.arm_qadr_main]) and not bool(solver.qvel[1].any())
     assert bool(main.qvel[0].any())                                              # the others keep going
+
+
+@pytest.mark.parametrize("config", ["rearrange_blocks_tcp", "rearrange_ycb_tcp"])
+def test_emulated_main_scene_follows_the_oracle_from_workload_states(config):
+    """Teacher-forced parity of the scenes the dual-simulation bench lines run: states reached by the workload on the emulated
+    kernels, one env-step (40 substeps + 2 forwards, cascaded-PI arm, objects resting on the table) on the fp32 kernel logic
+    against the fp64 oracle."""
+    import torch
+
+    import bench
+    from emu_generic_sim import EmuGenericSim
+    from oracle_generic_sim import OracleGenericSim
+
+    cfg = bench.CONFIGS[config]
+    blob, sblob = bench.load_blob(cfg["asset"]), bench.load_blob(cfg["solver_asset"])
+    names = json.load(open(os.path.join(ROOT, "robogym_b200", "assets", cfg["asset"] + ".names.json")))
+    n = 2
+    main = EmuGenericSim(blob, n, cfg["nsub"], contact_capacity=cfg["caps"][0], row_capacity=cfg["caps"][1])
+    solver = EmuGenericSim(sblob, n, cfg["nsub"])
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(7)
+    wl = bench.RearrangeTcpWorkload(main, main.model, names, torch.device("cpu"), gen, cfg["nobj"], cfg["grid"], solver)
+    for _ in range(3):
+        wl.apply_action(wl.sample_action()); wl.step_timed()
+    om = OracleGenericSim(blob, n, cfg["nsub"])
+    for f in ("qpos", "qvel", "ctrl", "pid", "qacc_warmstart"):
+        getattr(om, f).copy_(getattr(main, f).to(torch.float64))
+    main.step(final_forward=2)
+    om.step(final_forward=2)
+    dq = (main.qpos.to(torch.float64) - om.qpos).abs()
+    arm = wl.ctl.arm_qadr_main
+    assert int(main.warn.max()) == 0 and int(om.warn.max()) == 0
+    assert float(dq[:, arm].max()) < 5e-5, float(dq[:, arm].max())                      # the arm under its cascaded-PI controllers
+    # objects: resting contacts; a mesh object rocking on a multi-part hull can switch a contact within fp32 noise (tests/test_rearrange_ycb.py)
+    assert float(dq.max()) < (5e-4 if "blocks" in config else 3e-3) and float(dq.median()) < 1e-5, (float(dq.max()), float(dq.median()))
