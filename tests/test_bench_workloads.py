@@ -82,3 +82,21 @@ def test_emulated_main_scene_follows_the_oracle_from_workload_states(config):
     assert float(dq[:, arm].max()) < 5e-5, float(dq[:, arm].max())                      # the arm under its cascaded-PI controllers
     # objects: resting contacts; a mesh object rocking on a multi-part hull can switch a contact within fp32 noise (tests/test_rearrange_ycb.py)
     assert float(dq.max()) < (5e-4 if "blocks" in config else 3e-3) and float(dq.median()) < 1e-5, (float(dq.max()), float(dq.median()))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the contract's keys, the
+    reference-arm extras, and a positive rate -- on a tiny bounded sample."""
+    import subprocess
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-1500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    assert "workload" in line["config"]
