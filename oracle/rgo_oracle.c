@@ -821,7 +821,9 @@ static double cascaded_pi_bias(const rgo_model* m, rgo_data* d, int id, int stri
   const double* g = m->actuator_gainprm + 10 * id;
   double dt = m->opt_timestep[0];
   double* ud = d->userdata + stride * id;
-  double ema = ud[5] != 0 ? g[8] * ud[4] + (1.0 - g[8]) * d->ctrl[id] : d->ctrl[id];
+  static int warm = -1;   /* experiment switch (tests/tools): RGO_CASC_EMA_WARM=0 smooths from the first evaluation on */
+  if (warm < 0) { const char* e = getenv("RGO_CASC_EMA_WARM"); warm = e ? atoi(e) : 1; }
+  double ema = (ud[5] != 0 || !warm) ? g[8] * ud[4] + (1.0 - g[8]) * d->ctrl[id] : d->ctrl[id];
   ud[4] = ema;
   double des_vel = d->ctrl[id];
   if (g[0] != 0) {
