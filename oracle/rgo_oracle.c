@@ -824,6 +824,7 @@ static double cascaded_pi_bias(const rgo_model* m, rgo_data* d, int id, int stri
   static int warm = -1;   /* experiment switch (tests/tools): RGO_CASC_EMA_WARM=0 smooths from the first evaluation on */
   if (warm < 0) { const char* e = getenv("RGO_CASC_EMA_WARM"); warm = e ? atoi(e) : 1; }
   double ema = (ud[5] != 0 || !warm) ? g[8] * ud[4] + (1.0 - g[8]) * d->ctrl[id] : d->ctrl[id];
+  { static int smooth = -1; if (smooth < 0) { const char* e = getenv("RGO_CASC_EMA"); smooth = e ? atoi(e) : 1; } if (!smooth) ema = d->ctrl[id]; }   /* experiment switch: RGO_CASC_EMA=0 = no set-point smoothing */
   ud[4] = ema;
   double des_vel = d->ctrl[id];
   if (g[0] != 0) {
@@ -833,7 +834,9 @@ static double cascaded_pi_bias(const rgo_model* m, rgo_data* d, int id, int stri
     des_vel = g[0] * (err + (g[1] != 0 ? integ / g[1] : 0.0) + g[3] * deriv);
     ud[0] = integ; ud[1] = err; ud[2] = deriv;
   }
-  des_vel = clampd(des_vel, -g[9], g[9]);
+  static int vclamp = -1;   /* experiment switch (tests/tools): RGO_CASC_VCLAMP=0 drops the max_vel clamp */
+  if (vclamp < 0) { const char* e = getenv("RGO_CASC_VCLAMP"); vclamp = e ? atoi(e) : 1; }
+  if (vclamp) des_vel = clampd(des_vel, -g[9], g[9]);
   double errv = des_vel - d->actuator_velocity[id];
   double integv = clampd(ud[3] + errv * dt, -g[7], g[7]);
   ud[3] = integv;

@@ -97,7 +97,9 @@ def test_reference_test_file_passes_on_the_shim(path, kexpr, npass, reference_ru
 
 def test_impulse_response_fixture_tells_the_controllers_apart(tmp_path):
     """The same reference fixture run with the reference's OTHER calibration (plain PID) fails: the recorded displacements
-    belong to the cascaded-PI law, so passing them (above) is evidence for the restatement, not a loose threshold."""
+    belong to the cascaded-PI law, so passing them (above) is evidence for the restatement, not a loose threshold.  (By hand, with the
+    oracle's experiment switches: RGO_CASC_GRAVCOMP=0 -> 2 of 4 fail, RGO_CASC_EMA=0 -> 2 of 4 fail; RGO_CASC_VCLAMP=0 and
+    RGO_CASC_EMA_WARM=0 pass: the velocity clamp and the moving average's warm start are not discriminated by the fixture.)"""
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "refsuite"), RG_SHIM_ENGINE="oracle", RG_REFSUITE_ARM_CALIBRATION="pid")
     cmd = [sys.executable, "-m", "pytest", "-p", "no:cacheprovider", "-q", "-p", "conftest_shim", f"--rootdir={tmp_path}",
            os.path.join(REF, "robogym/envs/rearrange/tests/test_rearrange_sim.py"), "-k", "impulse"]
